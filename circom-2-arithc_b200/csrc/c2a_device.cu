@@ -1,0 +1,964 @@
+// c2a_device.cu — sm_100a kernels + device half of the C ABI (include/c2a.h).
+//
+// Replaces, bit-for-bit, the back end of the reference's Compiler::build_circuit
+// (src/compiler.rs:388-464) and its DFS topological sort (src/topological_sort.rs:3-50).
+//
+// Pipeline (all integer/index work, HBM/L2-bound, no tensor cores):
+//   K1 producer_map   prod1[out[g]] = max(g+1)                       compiler.rs:401-406 (last insert wins)
+//   K2 deps           dep[g] = {prod1[lh]-1, prod1[rh]-1}, out-of-order edge detection
+//                     (no dep >= g  <=>  the DFS post-order is 0..G-1)  compiler.rs:408-421
+//   K5a relax         r[v] = min(v, min over consumers r[u]) = the DFS root that first reaches v
+//   K5b sizes/scan    block offsets per root (roots ascending)          topological_sort.rs:11-13
+//   K5c trees         per-root DFS post-order restricted to its block, lh before rh, cycle detection
+//                                                                       topological_sort.rs:23-50
+//   K6 wire_first/wire_scan   first-seen wire numbering                 compiler.rs:427-443
+//   K7 gather         new_gates[k] = {op, wire[lh], wire[rh], wire[out]}  compiler.rs:452-464
+//   K4 kahn           level-synchronous frontier (levels for the sweeps; c2a_kahn.cu)
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "c2a_internal.h"
+
+namespace c2a {
+
+// ---------------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  // 128-bit load of a gate record; no L1 allocation (each pass touches a record once), L2 keeps it
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+}
+
+constexpr int kBlock = 256;
+constexpr uint32_t kNone = C2A_NONE;
+// wire[] encoding while numbering is in flight (compiler.rs:388-449):
+//   < kOutPending        : final wire id
+//   == kOutPending       : output node, numbered after all intermediates (:431-434, :446-449)
+//   kFirstTag | p        : not numbered yet; p = 3*pos+slot of the earliest appearance seen so far
+//   kNone                : never appears
+constexpr uint32_t kOutPending = 0x7FFFFFFFu;
+constexpr uint32_t kFirstTag = 0x80000000u;
+
+// scalars[] slots on the device
+enum { S_FLAGS = 0, S_Q0N = 1, S_Q1N = 2, S_HEAVYN = 3, S_NMID = 4, S_TICKET = 5, S_ERR_LO = 6, S_ERR_HI = 7, S_COUNT = 16 };
+enum { F_OOO = 1, F_BAD = 2, F_SELF = 4 };
+
+// ---------------------------------------------------------------------------------------------------
+// K1: producer map.  prod1[node] = 1 + (largest gate index whose out is node); 0 = no producer.
+// compiler.rs:403-406: HashMap::insert in ascending gate order => the LAST gate wins.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_producer(const uint4* __restrict__ gates, uint32_t G, uint32_t node_bound,
+                                                     uint32_t* __restrict__ prod1, uint32_t* __restrict__ scalars) {
+  bool bad = false;
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
+    uint4 gt = ldg_stream(gates + g);
+    if (gt.y >= node_bound || gt.z >= node_bound || gt.w >= node_bound) bad = true;
+    else atomicMax(prod1 + gt.w, g + 1);  // RED.MAX, no return value
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(scalars + S_FLAGS, (uint32_t)F_BAD);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2: dependencies.  dep[g] = (producer of lh, producer of rh), kNone where the node has no producer
+// (compiler.rs:412-418).  flags |= F_OOO when some dep index >= g: only then can the DFS post-order differ
+// from 0..G-1 (otherwise every root's deps are already visited when the root loop reaches it).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates, uint32_t G, const uint32_t* __restrict__ prod1,
+                                                 uint2* __restrict__ dep, uint32_t* __restrict__ scalars) {
+  uint32_t f = 0;
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
+    uint4 gt = ldg_stream(gates + g);
+    uint32_t d0 = __ldg(prod1 + gt.y) - 1u;  // 0 -> kNone
+    uint32_t d1 = __ldg(prod1 + gt.z) - 1u;
+    dep[g] = make_uint2(d0, d1);
+    if ((d0 != kNone && d0 >= g) || (d1 != kNone && d1 >= g)) f |= F_OOO;
+    if (d0 == g || d1 == g) f |= F_SELF;
+  }
+  uint32_t any_ooo = __syncthreads_or(f & F_OOO), any_self = __syncthreads_or(f & F_SELF);
+  if (threadIdx.x == 0 && (any_ooo || any_self)) atomicOr(scalars + S_FLAGS, (any_ooo ? F_OOO : 0u) | (any_self ? F_SELF : 0u));
+}
+
+// generic get_deps form (topological_sort.rs:3-6): CSR rows with <= 2 entries
+__global__ void __launch_bounds__(kBlock) k_deps_from_csr(const unsigned long long* __restrict__ dep_off, const uint32_t* __restrict__ dep_idx,
+                                                          uint32_t n, uint2* __restrict__ dep, uint32_t* __restrict__ scalars) {
+  uint32_t f = 0;
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < n; g += gridDim.x * kBlock) {
+    unsigned long long a = dep_off[g], b = dep_off[g + 1];
+    uint32_t d0 = kNone, d1 = kNone;
+    if (b < a || b - a > 2) f |= F_BAD;
+    else {
+      if (b - a >= 1) d0 = dep_idx[a];
+      if (b - a == 2) d1 = dep_idx[a + 1];
+      if (d0 != kNone && d0 >= n) { f |= F_BAD; d0 = kNone; }
+      if (d1 != kNone && d1 >= n) { f |= F_BAD; d1 = kNone; }
+      if (b - a == 2 && d0 == kNone) f |= F_BAD;  // a literal 0xFFFFFFFF index is not representable
+    }
+    dep[g] = make_uint2(d0, d1);
+    if ((d0 != kNone && d0 >= g) || (d1 != kNone && d1 >= g)) f |= F_OOO;
+    if (d0 == g || d1 == g) f |= F_SELF;
+  }
+  uint32_t any_ooo = __syncthreads_or(f & F_OOO), any_bad = __syncthreads_or(f & F_BAD), any_self = __syncthreads_or(f & F_SELF);
+  if (threadIdx.x == 0 && (any_ooo || any_bad || any_self))
+    atomicOr(scalars + S_FLAGS, (any_ooo ? F_OOO : 0u) | (any_bad ? F_BAD : 0u) | (any_self ? F_SELF : 0u));
+}
+
+__global__ void __launch_bounds__(kBlock) k_iota(uint32_t* __restrict__ a, uint32_t n) {
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) a[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5a: r[v] = index of the root of the `for i in 0..len` loop (topological_sort.rs:11-13) whose visit first
+// reaches v = min(v, min over transitive consumers).  Monotone min-propagation along dependency edges,
+// data-driven: whoever lowers r[x] is responsible for x's dependencies - it chases the lh chain itself and
+// queues the rh side for the next round.  inq (bitmask) keeps a queue at <= one entry per item.
+// r only ever decreases, so stale (too high) reads are harmless: they cost one redundant atomicMin.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void enqueue(uint32_t x, uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn) {
+  uint32_t bit = 1u << (x & 31);
+  __threadfence();  // the r[] update must be visible before the flag
+  uint32_t old = atomicOr(inq + (x >> 5), bit);
+  if (!(old & bit)) q[atomicAdd(qn, 1u)] = x;
+}
+
+__device__ __forceinline__ void relax_from(uint32_t cur, uint32_t val, const uint2* __restrict__ dep, uint32_t* __restrict__ r,
+                                           uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn) {
+  // invariant on entry: r[cur] <= val; cur's dependencies may still hold larger values
+  while (cur != kNone) {
+    uint2 d = dep[cur];
+    uint32_t nxt = kNone;
+    if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
+      if (val < atomicMin(r + d.y, val)) enqueue(d.y, inq, q, qn);
+    }
+    if (d.x != kNone && val < __ldcg(r + d.x)) {
+      if (val < atomicMin(r + d.x, val)) nxt = d.x;
+    }
+    cur = nxt;
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_relax_seed(const uint2* __restrict__ dep, uint32_t n, uint32_t* __restrict__ r,
+                                                       uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn) {
+  for (uint32_t u = blockIdx.x * kBlock + threadIdx.x; u < n; u += gridDim.x * kBlock) {
+    uint2 d = dep[u];
+    // r[d] <= d always, so val=u can only lower r[d] along an out-of-order edge (d > u)
+    if ((d.x != kNone && d.x > u) || (d.y != kNone && d.y > u)) relax_from(u, u, dep, r, inq, q, qn);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock) k_relax_round(const uint2* __restrict__ dep, uint32_t* __restrict__ r, uint32_t* __restrict__ inq,
+                                                        const uint32_t* __restrict__ q_in, const uint32_t* __restrict__ q_in_n,
+                                                        uint32_t* __restrict__ q_out, uint32_t* __restrict__ q_out_n) {
+  uint32_t n = *q_in_n;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t x = q_in[i];
+    atomicAnd(inq + (x >> 5), ~(1u << (x & 31)));
+    __threadfence();  // clear the flag before sampling r[x]: a later lowering re-queues x
+    uint32_t val = __ldcg(r + x);
+    relax_from(x, val, dep, r, inq, q_out, q_out_n);
+  }
+}
+
+// K5b: block sizes.  size[root] = number of items first reached from root.
+__global__ void __launch_bounds__(kBlock) k_sizes(const uint32_t* __restrict__ r, uint32_t n, uint32_t* __restrict__ size) {
+  for (uint32_t v = blockIdx.x * kBlock + threadIdx.x; v < n; v += gridDim.x * kBlock) atomicAdd(size + r[v], 1u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Single-pass exclusive scan (decoupled look-back).  Tiles are claimed through a ticket so a tile only ever
+// waits on tiles that are already running.  tile_state word = (status << 32) | value,
+// status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
+// ---------------------------------------------------------------------------------------------------
+constexpr unsigned long long kStAgg = 1ull << 32, kStInc = 2ull << 32;
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// Returns the exclusive prefix of this thread's `thread_sum` over the whole grid-wide sequence of tiles.
+// Must be called by all kBlock threads.  *tile_out = claimed tile index (same for the block).
+// s_mem: >= 10 u32 of shared memory.
+__device__ __forceinline__ uint32_t scan_claim_tile(uint32_t* __restrict__ ticket, uint32_t* s_mem) {
+  if (threadIdx.x == 0) s_mem[9] = atomicAdd(ticket, 1u);
+  __syncthreads();
+  return s_mem[9];
+}
+
+__device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thread_sum, unsigned long long* __restrict__ tile_state,
+                                                     uint32_t* s_mem, uint32_t* total_out, bool is_last_tile) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(thread_sum, lane);
+  if (lane == 31) s_mem[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = lane < (kBlock / 32) ? s_mem[lane] : 0u;
+    uint32_t wi = warp_incl_scan(w, lane);
+    uint32_t block_agg = __shfl_sync(0xFFFFFFFFu, wi, (kBlock / 32) - 1);
+    if (lane < (kBlock / 32)) s_mem[lane] = wi - w;  // exclusive warp offsets
+    // look-back
+    uint32_t prefix = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(tile_state, kStInc | block_agg);
+    } else {
+      if (lane == 0) st_volatile_u64(tile_state + tile, kStAgg | block_agg);
+      long long p = (long long)tile - 1;
+      while (true) {
+        long long idx = p - lane;
+        unsigned long long v = idx >= 0 ? ld_volatile_u64(tile_state + idx) : kStInc;
+        while (__any_sync(0xFFFFFFFFu, (v >> 32) == 0)) {
+          if ((v >> 32) == 0) v = ld_volatile_u64(tile_state + idx);
+        }
+        uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (v >> 32) == 2);
+        uint32_t val = (uint32_t)v;
+        if (inc_mask) {
+          int first = __ffs(inc_mask) - 1;  // nearest predecessor holding an inclusive prefix
+          uint32_t c = lane <= first ? val : 0u;
+#pragma unroll
+          for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
+          prefix += c;
+          break;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, o);
+        prefix += val;
+        p -= 32;
+      }
+      if (lane == 0) st_volatile_u64(tile_state + tile, kStInc | (unsigned long long)(prefix + block_agg));
+    }
+    if (lane == 0) {
+      s_mem[8] = prefix;
+      if (is_last_tile && total_out) *total_out = prefix + block_agg;
+    }
+  }
+  __syncthreads();
+  return s_mem[8] + s_mem[warp] + (incl - thread_sum);
+}
+
+// in-place exclusive scan of a[0..n) ; a[n] = total.  8 items per thread, 128-bit accesses.
+constexpr int kScanItems = 8;
+__global__ void __launch_bounds__(kBlock) k_scan_u32(uint32_t* __restrict__ a, uint32_t n, unsigned long long* __restrict__ tile_state,
+                                                     uint32_t* __restrict__ ticket) {
+  __shared__ uint32_t s_mem[10];
+  const uint32_t tiles = (n + kBlock * kScanItems - 1) / (kBlock * kScanItems);
+  uint32_t tile = scan_claim_tile(ticket, s_mem);
+  uint32_t base = tile * (kBlock * kScanItems) + threadIdx.x * kScanItems;
+  uint32_t v[kScanItems];
+  if (base + kScanItems <= n) {
+    uint4 x = *reinterpret_cast<const uint4*>(a + base), y = *reinterpret_cast<const uint4*>(a + base + 4);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) v[i] = base + i < n ? a[base + i] : 0u;
+  }
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) sum += v[i];
+  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, a + n, tile == tiles - 1);
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) { uint32_t t = v[i]; v[i] = ex; ex += t; }
+  if (base + kScanItems <= n) {
+    *reinterpret_cast<uint4*>(a + base) = make_uint4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<uint4*>(a + base + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) a[base + i] = v[i];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5c: emit.  Blocks of one item are written straight away; larger blocks go to the heavy list and are
+// walked by k_tree_dfs, one thread per block, reproducing topological_sort_visit (topological_sort.rs:23-50)
+// restricted to the block: an item with r < root was emitted by an earlier root ("visited"), r == root is
+// tracked in state[].  The DFS stack lives in the block's own slice of order[] (it grows down from the end
+// while emitted items grow up from the start; |stack| + |emitted| <= block size).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_roots(const uint32_t* __restrict__ r, const uint32_t* __restrict__ off, uint32_t n,
+                                                  const uint2* __restrict__ dep, uint32_t check_self, uint32_t* __restrict__ order,
+                                                  uint32_t* __restrict__ heavy, uint32_t* __restrict__ scalars) {
+  for (uint32_t v = blockIdx.x * kBlock + threadIdx.x; v < n; v += gridDim.x * kBlock) {
+    if (r[v] != v) continue;
+    uint32_t o = off[v], sz = off[v + 1] - o;
+    if (sz == 1) {
+      if (check_self) {
+        uint2 d = dep[v];
+        if (d.x == v || d.y == v)  // visit(v) -> visit(v) while visiting[v]  => "detected at i=v"
+          atomicMin(reinterpret_cast<unsigned long long*>(scalars + S_ERR_LO), ((unsigned long long)v << 32) | v);
+      }
+      order[o] = v;
+    } else {
+      heavy[atomicAdd(scalars + S_HEAVYN, 1u)] = v;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ heavy,
+                                                  const uint2* __restrict__ dep, const uint32_t* __restrict__ r,
+                                                  const uint32_t* __restrict__ off, uint8_t* __restrict__ state,
+                                                  uint32_t* __restrict__ order, uint32_t* scalars) {
+  uint32_t nh = scalars[S_HEAVYN];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += gridDim.x * blockDim.x) {
+    const uint32_t R = heavy[i];
+    const uint32_t base = off[R], end = off[R + 1];
+    uint32_t emit = base, top = end;
+    // state: 0 unvisited, 1 entered (lh next), 2 (rh next), 3 (both examined, emit next), 4 visited
+    state[R] = 1;
+    order[--top] = R;
+    while (top < end) {
+      uint32_t v = order[top];
+      uint8_t s = state[v];
+      if (s <= 2) {
+        uint2 dd = dep[v];
+        uint32_t d = (s == 1) ? dd.x : dd.y;
+        state[v] = s + 1;
+        if (d != kNone && r[d] == R) {
+          uint8_t sd = state[d];
+          if (sd == 0) {
+            state[d] = 1;
+            order[--top] = d;
+          } else if (sd < 4) {  // visiting[d]  (topological_sort.rs:34-38)
+            atomicMin(reinterpret_cast<unsigned long long*>(scalars + S_ERR_LO), ((unsigned long long)R << 32) | d);
+            break;
+          }
+        }
+      } else {
+        ++top;
+        order[emit++] = v;  // sorted.push(i)
+        state[v] = 4;       // visited[i] = true
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K6: wire numbering (compiler.rs:388-449)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_set_pairs(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ ranks, uint32_t n,
+                                                      uint32_t add, const uint32_t* __restrict__ add_dev, uint32_t fixed,
+                                                      uint32_t use_fixed, uint32_t* __restrict__ wire) {
+  uint32_t a = add + (add_dev ? *add_dev : 0u);
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) wire[nodes[i]] = use_fixed ? fixed : a + ranks[i];
+}
+
+// pass 1: earliest appearance p = 3*pos+slot of every not-yet-numbered node, over the SORTED gate stream.
+// One unconditional RED.MIN per slot: inputs / pending outputs hold smaller words and are left untouched.
+__global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
+                                                       uint32_t* __restrict__ wire) {
+  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
+    uint32_t g = order ? order[k] : k;
+    uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
+    uint32_t p = kFirstTag | (3u * k);
+    atomicMin(wire + gt.y, p);
+    if (gt.z != gt.y) atomicMin(wire + gt.z, p + 1);
+    if (gt.w != gt.y && gt.w != gt.z) atomicMin(wire + gt.w, p + 2);
+  }
+}
+
+// pass 2: a slot is a first appearance iff wire[node] still equals its own tagged position; rank them with
+// one single-pass scan and overwrite the tag with n_in + rank  (compiler.rs:440-441).
+constexpr int kWireItems = 4;
+__global__ void __launch_bounds__(kBlock) k_wire_scan(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
+                                                      uint32_t n_in, uint32_t* __restrict__ wire, unsigned long long* __restrict__ tile_state,
+                                                      uint32_t* __restrict__ scalars) {
+  __shared__ uint32_t s_mem[10];
+  const uint32_t tiles = (G + kBlock * kWireItems - 1) / (kBlock * kWireItems);
+  uint32_t tile = scan_claim_tile(scalars + S_TICKET, s_mem);
+  uint32_t base = tile * (kBlock * kWireItems) + threadIdx.x * kWireItems;
+  uint32_t node[kWireItems][3];
+  uint32_t fl[kWireItems];
+  uint32_t sum = 0;
+#pragma unroll
+  for (int i = 0; i < kWireItems; ++i) {
+    uint32_t k = base + i;
+    fl[i] = 0;
+    if (k < G) {
+      uint32_t g = order ? order[k] : k;
+      uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
+      node[i][0] = gt.y; node[i][1] = gt.z; node[i][2] = gt.w;
+      uint32_t p = kFirstTag | (3u * k);
+      uint32_t f0 = __ldcg(wire + gt.y) == p;
+      uint32_t f1 = __ldcg(wire + gt.z) == p + 1;
+      uint32_t f2 = __ldcg(wire + gt.w) == p + 2;
+      fl[i] = f0 | (f1 << 1) | (f2 << 2);
+      sum += f0 + f1 + f2;
+    }
+  }
+  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, scalars + S_NMID, tile == tiles - 1);
+  uint32_t w = n_in + ex;
+#pragma unroll
+  for (int i = 0; i < kWireItems; ++i) {
+    if (fl[i] & 1) wire[node[i][0]] = w++;
+    if (fl[i] & 2) wire[node[i][1]] = w++;
+    if (fl[i] & 4) wire[node[i][2]] = w++;
+  }
+}
+
+// K7: gather (compiler.rs:452-464).  op stays numeric; the host maps it to the strum Display token.
+__global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
+                                                   const uint32_t* __restrict__ wire, uint4* __restrict__ new_gates) {
+  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
+    uint32_t g = order ? order[k] : k;
+    uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
+    stg_stream(new_gates + k, make_uint4(gt.x, __ldg(wire + gt.y), __ldg(wire + gt.z), __ldg(wire + gt.w)));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side plumbing
+// ---------------------------------------------------------------------------------------------------
+int fail(c2a_handle* h, int status, const char* fmt, ...) {
+  if (h) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    h->err = buf;
+  }
+  return status;
+}
+
+bool cuda_ok(c2a_handle* h, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return true;
+  fail(h, C2A_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return false;
+}
+
+void slab_reset(c2a_handle* h) { h->slab_used = 0; }
+
+bool slab_reserve(c2a_handle* h, size_t bytes) {
+  if (bytes <= h->slab_bytes) return true;
+  if (h->slab) {
+    cudaStreamSynchronize(h->stream);
+    cudaFree(h->slab);
+    h->slab = nullptr;
+    h->slab_bytes = 0;
+  }
+  size_t want = bytes + bytes / 8 + (1u << 20);
+  cudaError_t e = cudaMalloc(&h->slab, want);
+  if (e != cudaSuccess) {
+    e = cudaMalloc(&h->slab, bytes);
+    want = bytes;
+  }
+  if (e != cudaSuccess) {
+    fail(h, C2A_ERR_NO_MEMORY, "cudaMalloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return false;
+  }
+  h->slab_bytes = want;
+  return true;
+}
+
+void* slab_alloc(c2a_handle* h, size_t bytes) {
+  size_t b = align256(bytes ? bytes : 1);
+  if (h->slab_used + b > h->slab_bytes) return nullptr;
+  void* p = h->slab + h->slab_used;
+  h->slab_used += b;
+  return p;
+}
+
+static cudaEvent_t next_event(c2a_handle* h) {
+  if (h->ev_next == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+  }
+  return h->ev_pool[h->ev_next++];
+}
+
+void phases_clear(c2a_handle* h) {
+  h->phases.clear();
+  h->ev_next = 0;
+}
+void phase_begin(c2a_handle* h, const char* name) {
+  if (!h->timing) return;
+  c2a_handle::Phase p{name, next_event(h), next_event(h), true};
+  cudaEventRecord(p.a, h->stream);
+  h->phases.push_back(p);
+}
+void phase_end(c2a_handle* h) {
+  if (!h->timing || h->phases.empty() || !h->phases.back().open) return;
+  cudaEventRecord(h->phases.back().b, h->stream);
+  h->phases.back().open = false;
+}
+void phases_collect(c2a_handle* h) {
+  h->last_ms.clear();
+  if (!h->timing || h->phases.empty()) return;
+  std::map<std::string, double> acc;
+  std::vector<std::string> names;
+  for (auto& p : h->phases) {
+    if (p.open) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) { cudaGetLastError(); continue; }
+    if (!acc.count(p.name)) names.push_back(p.name);
+    acc[p.name] += ms;
+  }
+  for (auto& n : names) h->last_ms.push_back({n, acc[n]});
+  float tot = 0;
+  if (cudaEventElapsedTime(&tot, h->phases.front().a, h->phases.back().b) == cudaSuccess) h->last_ms.push_back({"total", tot});
+  else cudaGetLastError();
+}
+
+int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n) {
+  static std::unordered_map<const void*, int> per_sm;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = per_sm.find(kernel);
+  int occ;
+  if (it == per_sm.end()) {
+    occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, block, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 4; }
+    per_sm[kernel] = occ;
+  } else occ = it->second;
+  uint64_t need = (n + block - 1) / block;
+  uint64_t cap = (uint64_t)h->num_sms * occ;  // one full wave of resident CTAs, grid-stride inside
+  uint64_t g = std::min<uint64_t>(std::max<uint64_t>(need, 1), cap);
+  return (int)g;
+}
+
+#define LAUNCH(h, kernel, grid, block, ...)                           \
+  do {                                                                \
+    kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);         \
+    (h)->launches++;                                                  \
+  } while (0)
+
+static inline uint32_t scan_tiles(uint64_t n, int items) { return (uint32_t)((n + (uint64_t)kBlock * items - 1) / ((uint64_t)kBlock * items)); }
+
+size_t sort_scratch_bytes(uint64_t n) {
+  size_t b = 0;
+  b += align256(4 * n);            // r
+  b += align256(4 * (n + 1));      // size_off
+  b += align256(n);                // state
+  b += align256(4 * ((n + 31) / 32 + 1));  // inq
+  b += 3 * align256(4 * n);        // q0 q1 heavy
+  b += align256(8 * (size_t)(scan_tiles(n, kWireItems) + 1));  // tile_state (sized for the finer tiling)
+  b += align256(4 * S_COUNT);
+  return b;
+}
+
+bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s) {
+  s->r = (uint32_t*)slab_alloc(h, 4 * n);
+  s->size_off = (uint32_t*)slab_alloc(h, 4 * (n + 1));
+  s->state = (uint8_t*)slab_alloc(h, n);
+  s->inq = (uint32_t*)slab_alloc(h, 4 * ((n + 31) / 32 + 1));
+  s->q0 = (uint32_t*)slab_alloc(h, 4 * n);
+  s->q1 = (uint32_t*)slab_alloc(h, 4 * n);
+  s->heavy = (uint32_t*)slab_alloc(h, 4 * n);
+  s->tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(n, kWireItems) + 1));
+  s->scalars = (uint32_t*)slab_alloc(h, 4 * S_COUNT);
+  return s->scalars != nullptr;
+}
+
+// Exact reference order from dependency pairs (K5a-c).  Precondition: scalars zeroed except S_FLAGS, S_ERR = ~0.
+int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_flags, const SortScratch& s, uint32_t* d_order,
+                   bool* identity_out, uint64_t* err_index) {
+  const bool nonidentity = (host_flags & (F_OOO | F_SELF)) != 0;
+  *identity_out = !nonidentity;
+  if (!nonidentity || n == 0) return C2A_OK;
+  cudaStream_t st = h->stream;
+  uint32_t* sc = s.scalars;
+  // ---- K5a
+  phase_begin(h, "relax");
+  LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, n), kBlock, s.r, n);
+  cudaMemsetAsync(s.inq, 0, 4 * ((size_t)(n + 31) / 32 + 1), st);
+  LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_Q0N);
+  uint32_t *qin = s.q0, *qout = s.q1;
+  int nin = S_Q0N, nout = S_Q1N;
+  for (int round = 0;; ++round) {
+    if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 32, sc + nin, 4, cudaMemcpyDeviceToHost, st), "relax count copy")) return C2A_ERR_CUDA;
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "relax sync")) return C2A_ERR_CUDA;
+    uint32_t cnt = h->h_pinned[32];
+    if (cnt == 0) break;
+    cudaMemsetAsync(sc + nout, 0, 4, st);
+    LAUNCH(h, k_relax_round, grid_for(h, (const void*)k_relax_round, kBlock, cnt), kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
+    std::swap(qin, qout);
+    std::swap(nin, nout);
+  }
+  phase_end(h);
+  // ---- K5b
+  phase_begin(h, "sizes_scan");
+  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
+  LAUNCH(h, k_sizes, grid_for(h, (const void*)k_sizes, kBlock, n), kBlock, s.r, n, s.size_off);
+  uint32_t tiles = scan_tiles(n, kScanItems);
+  cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
+  cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
+  LAUNCH(h, k_scan_u32, tiles, kBlock, s.size_off, n, s.tile_state, sc + S_TICKET);
+  phase_end(h);
+  // ---- K5c
+  phase_begin(h, "trees");
+  cudaMemsetAsync(s.state, 0, n, st);
+  LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, (host_flags & F_SELF) ? 1u : 0u, d_order, s.heavy, sc);
+  // heavy count is only known on the device: launch a grid sized for the worst case the hardware can hold
+  LAUNCH(h, k_tree_dfs, h->num_sms * 8, 128, s.heavy, d_dep, s.r, s.size_off, s.state, d_order, sc);
+  phase_end(h);
+  if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 40, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "sort status copy")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaStreamSynchronize(st), "sort sync")) return C2A_ERR_CUDA;
+  unsigned long long err = ((unsigned long long)h->h_pinned[40 + S_ERR_HI] << 32) | h->h_pinned[40 + S_ERR_LO];
+  if (err != ~0ull) {
+    uint64_t at = (uint32_t)err;
+    if (err_index) *err_index = at;
+    return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "detected at i=%llu", (unsigned long long)at);
+  }
+  return C2A_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// build_circuit on device-resident gates
+// ---------------------------------------------------------------------------------------------------
+struct IoPairs {
+  std::vector<uint32_t> nodes, ranks;
+};
+// last-wins de-duplication of an ordered node list (HashMap::insert overwrite, compiler.rs:392-395, 446-449)
+static void dedupe_last(const uint32_t* list, uint32_t n, IoPairs* out) {
+  std::unordered_map<uint32_t, uint32_t> m;
+  m.reserve(n * 2 + 1);
+  for (uint32_t i = 0; i < n; ++i) m[list[i]] = i;
+  out->nodes.reserve(m.size());
+  out->ranks.reserve(m.size());
+  for (uint32_t i = 0; i < n; ++i)
+    if (m[list[i]] == i) { out->nodes.push_back(list[i]); out->ranks.push_back(i); }
+}
+
+struct BuildPlan {
+  uint64_t G;
+  uint32_t node_bound, n_in, n_out;
+  bool want_wire;  // wire numbering + gather wanted (build_circuit) or order only (topo_sort)
+};
+
+static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {
+  size_t b = 0;
+  b += align256(4 * (size_t)p.node_bound);  // prod1
+  b += align256(8 * p.G);                   // dep
+  b += sort_scratch_bytes(p.G);
+  b += align256(4 * p.G);                   // order (internal)
+  b += 2 * align256(4 * n_pairs + 4);       // pair nodes / ranks
+  return b;
+}
+
+// Core: everything after the gates are on the device.  d_wire may be null (internal), d_order may be null.
+static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, const uint32_t* in_nodes_host,
+                      const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
+                      uint32_t* wire_count, uint64_t* err_index, bool* identity_out) {
+  cudaStream_t st = h->stream;
+  const uint32_t G = (uint32_t)p.G;
+  // host-side metadata checks
+  IoPairs in_pairs, out_pairs;
+  if (p.want_wire) {
+    for (uint32_t i = 0; i < p.n_in; ++i)
+      if (in_nodes_host[i] >= p.node_bound) return fail(h, C2A_ERR_INVALID_ARGUMENT, "input node %u >= node_bound %u", in_nodes_host[i], p.node_bound);
+    for (uint32_t i = 0; i < p.n_out; ++i)
+      if (out_nodes_host[i] >= p.node_bound) return fail(h, C2A_ERR_INVALID_ARGUMENT, "output node %u >= node_bound %u", out_nodes_host[i], p.node_bound);
+    dedupe_last(in_nodes_host, p.n_in, &in_pairs);
+    dedupe_last(out_nodes_host, p.n_out, &out_pairs);
+  }
+  size_t n_pairs = in_pairs.nodes.size() + out_pairs.nodes.size();
+  if ((4 * n_pairs * 2 + 1024) > h->h_pinned_bytes) {
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned_bytes = 4 * n_pairs * 2 + 4096;
+    if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
+  }
+
+  uint32_t* prod1 = (uint32_t*)slab_alloc(h, 4 * (size_t)p.node_bound);
+  uint2* dep = (uint2*)slab_alloc(h, 8 * p.G);
+  SortScratch s;
+  bool ok = sort_scratch_carve(h, p.G, &s);
+  uint32_t* order_int = (uint32_t*)slab_alloc(h, 4 * p.G);
+  uint32_t* pair_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  uint32_t* pair_ranks = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  if (!ok || !prod1 || !dep || !order_int || !pair_nodes || !pair_ranks) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  uint32_t* sc = s.scalars;
+
+  // scalars: zero, err = ~0
+  uint32_t* hp = h->h_pinned;
+  for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
+  hp[S_ERR_LO] = hp[S_ERR_HI] = 0xFFFFFFFFu;
+  cudaMemcpyAsync(sc, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
+  if (n_pairs) {
+    uint32_t* stage = hp + 256;
+    size_t ni = in_pairs.nodes.size(), no = out_pairs.nodes.size();
+    memcpy(stage, in_pairs.nodes.data(), 4 * ni);
+    memcpy(stage + ni, out_pairs.nodes.data(), 4 * no);
+    memcpy(stage + n_pairs, in_pairs.ranks.data(), 4 * ni);
+    memcpy(stage + n_pairs + ni, out_pairs.ranks.data(), 4 * no);
+    cudaMemcpyAsync(pair_nodes, stage, 4 * n_pairs, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(pair_ranks, stage + n_pairs, 4 * n_pairs, cudaMemcpyHostToDevice, st);
+  }
+
+  phase_begin(h, "producer");
+  cudaMemsetAsync(prod1, 0, 4 * (size_t)p.node_bound, st);
+  if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
+  phase_end(h);
+  phase_begin(h, "deps");
+  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, prod1, dep, sc);
+  phase_end(h);
+  if (!cuda_ok(h, cudaMemcpyAsync(hp, sc, 4, cudaMemcpyDeviceToHost, st), "flags copy")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaStreamSynchronize(st), "deps sync")) return C2A_ERR_CUDA;
+  uint32_t flags = hp[S_FLAGS];
+  if (flags & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", p.node_bound);
+
+  uint32_t* d_order = d_order_user ? d_order_user : order_int;
+  bool identity = true;
+  int stt = sort_from_deps(h, dep, G, flags, s, d_order, &identity, err_index);
+  if (stt != C2A_OK) return stt;
+  if (identity_out) *identity_out = identity;
+  if (identity && d_order_user && G) {
+    phase_begin(h, "iota");
+    LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, G), kBlock, d_order_user, G);
+    phase_end(h);
+  }
+  if (!p.want_wire) return C2A_OK;
+
+  const uint32_t* ord = identity ? nullptr : d_order;
+  uint32_t ni = (uint32_t)in_pairs.nodes.size(), no = (uint32_t)out_pairs.nodes.size();
+  phase_begin(h, "wire_first");
+  cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
+  if (ni) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, ni), kBlock, pair_nodes, pair_ranks, ni, 0u, (const uint32_t*)nullptr, 0u, 0u, d_wire);
+  if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, 0u, (const uint32_t*)nullptr, kOutPending, 1u, d_wire);
+  if (G) LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, G), kBlock, d_gates, ord, G, d_wire);
+  phase_end(h);
+  phase_begin(h, "wire_scan");
+  if (G) {
+    uint32_t tiles = scan_tiles(G, kWireItems);
+    cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
+    cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
+    LAUNCH(h, k_wire_scan, tiles, kBlock, d_gates, ord, G, p.n_in, d_wire, s.tile_state, sc);
+  }
+  if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, p.n_in, (const uint32_t*)(sc + S_NMID), 0u, 0u, d_wire);
+  phase_end(h);
+  if (d_new_gates && G) {
+    phase_begin(h, "gather");
+    LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, G), kBlock, d_gates, ord, G, d_wire, d_new_gates);
+    phase_end(h);
+  }
+  if (!cuda_ok(h, cudaMemcpyAsync(hp + 8, sc + S_NMID, 4, cudaMemcpyDeviceToHost, st), "n_mid copy")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaStreamSynchronize(st), "final sync")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaGetLastError(), "kernel")) return C2A_ERR_CUDA;
+  if (wire_count) *wire_count = p.n_in + hp[8] + p.n_out;
+  return C2A_OK;
+}
+
+static int check_sizes(c2a_handle* h, uint64_t G, uint32_t node_bound) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (G > (1ull << 29)) return fail(h, C2A_ERR_INVALID_ARGUMENT, "G=%llu exceeds the 2^29 gate limit of the u32 position encoding", (unsigned long long)G);
+  if (node_bound >= kOutPending) return fail(h, C2A_ERR_INVALID_ARGUMENT, "node_bound too large");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  return C2A_OK;
+}
+
+}  // namespace c2a
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace c2a;
+
+extern "C" {
+
+int c2a_abi_version(void) { return C2A_ABI_VERSION; }
+
+int c2a_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+int c2a_create(int device, c2a_handle** out) {
+  if (!out) return C2A_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int n = c2a_device_count();
+  if (n <= 0 || device < 0 || device >= n) return C2A_ERR_CUDA;  // no CPU fallback: fail loudly
+  if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return C2A_ERR_CUDA; }
+  c2a_handle* h = new c2a_handle();
+  h->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete h; return C2A_ERR_CUDA; }
+  h->h_pinned_bytes = 1 << 16;
+  if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return C2A_ERR_CUDA;
+  }
+  *out = h;
+  return C2A_OK;
+}
+
+void c2a_destroy(c2a_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto e : h->ev_pool) cudaEventDestroy(e);
+  if (h->slab) cudaFree(h->slab);
+  if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* c2a_last_error(const c2a_handle* h) { return h ? h->err.c_str() : "null handle"; }
+uint64_t c2a_kernel_launches(const c2a_handle* h) { return h ? h->launches : 0; }
+double c2a_last_kernel_ms(const c2a_handle* h, const char* name) {
+  if (!h || !name) return -1.0;
+  for (auto& p : h->last_ms)
+    if (p.first == name) return p.second;
+  return -1.0;
+}
+void* c2a_stream(c2a_handle* h) { return h ? (void*)h->stream : nullptr; }  // cudaStream_t, for callers that time on it
+void c2a_set_timing(c2a_handle* h, int on) { if (h) h->timing = on != 0; }
+// comma-separated "name=ms" list of the last call's phases (diagnostics)
+const char* c2a_last_phases(c2a_handle* h) {
+  static thread_local std::string s;
+  s.clear();
+  if (h) for (auto& p : h->last_ms) { char b[96]; snprintf(b, sizeof b, "%s%s=%.6f", s.empty() ? "" : ",", p.first.c_str(), p.second); s += b; }
+  return s.c_str();
+}
+
+int c2a_build_circuit_device(c2a_handle* h, const c2a_gate* d_gates, uint64_t G, uint32_t node_bound, const uint32_t* input_nodes,
+                             uint32_t n_in, const uint32_t* output_nodes, uint32_t n_out, uint32_t* d_order_out, uint32_t* d_wire_of_node,
+                             c2a_gate* d_new_gates, uint32_t* wire_count, uint64_t* err_index) {
+  int st = check_sizes(h, G, node_bound);
+  if (st) return st;
+  phases_clear(h);
+  BuildPlan p{G, node_bound, n_in, n_out, true};
+  slab_reset(h);
+  size_t need = core_scratch_bytes(p, (size_t)n_in + n_out) + (d_wire_of_node ? 0 : align256(4 * (size_t)node_bound));
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  uint32_t* d_wire = d_wire_of_node ? d_wire_of_node : (uint32_t*)slab_alloc(h, 4 * (size_t)node_bound);
+  st = build_core(h, p, (const uint4*)d_gates, input_nodes, output_nodes, d_order_out, d_wire, (uint4*)d_new_gates, wire_count, err_index, nullptr);
+  cudaStreamSynchronize(h->stream);
+  phases_collect(h);
+  return st;
+}
+
+int c2a_build_circuit(c2a_handle* h, const c2a_gate* gates, uint64_t G, uint32_t node_bound, const uint32_t* input_nodes, uint32_t n_in,
+                      const uint32_t* output_nodes, uint32_t n_out, uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates,
+                      uint32_t* wire_count, uint64_t* err_index) {
+  int st = check_sizes(h, G, node_bound);
+  if (st) return st;
+  phases_clear(h);
+  BuildPlan p{G, node_bound, n_in, n_out, true};
+  slab_reset(h);
+  size_t need = core_scratch_bytes(p, (size_t)n_in + n_out) + align256(16 * G) * 2 + align256(4 * G) + align256(4 * (size_t)node_bound);
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
+  uint4* d_new = new_gates ? (uint4*)slab_alloc(h, 16 * G) : nullptr;
+  uint32_t* d_order = order_out ? (uint32_t*)slab_alloc(h, 4 * G) : nullptr;
+  uint32_t* d_wire = (uint32_t*)slab_alloc(h, 4 * (size_t)node_bound);
+  cudaStream_t s = h->stream;
+  phase_begin(h, "h2d");
+  if (G && !cuda_ok(h, cudaMemcpyAsync(d_gates, gates, 16 * G, cudaMemcpyHostToDevice, s), "gates H2D")) return C2A_ERR_CUDA;
+  phase_end(h);
+  st = build_core(h, p, d_gates, input_nodes, output_nodes, d_order, d_wire, d_new, wire_count, err_index, nullptr);
+  if (st == C2A_OK) {
+    phase_begin(h, "d2h");
+    if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
+    if (wire_of_node && node_bound) cudaMemcpyAsync(wire_of_node, d_wire, 4 * (size_t)node_bound, cudaMemcpyDeviceToHost, s);
+    if (new_gates && G) cudaMemcpyAsync(new_gates, d_new, 16 * G, cudaMemcpyDeviceToHost, s);
+    phase_end(h);
+    if (!cuda_ok(h, cudaStreamSynchronize(s), "D2H")) st = C2A_ERR_CUDA;
+    // nodes that never appear keep an in-flight tag only if something went wrong; kNone otherwise
+  } else {
+    cudaStreamSynchronize(s);
+  }
+  phases_collect(h);
+  return st;
+}
+
+int c2a_topo_sort(c2a_handle* h, const c2a_gate* gates, uint64_t G, uint32_t node_bound, uint32_t* order_out, uint64_t* err_index) {
+  int st = check_sizes(h, G, node_bound);
+  if (st) return st;
+  if (!order_out && G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "order_out is null");
+  phases_clear(h);
+  BuildPlan p{G, node_bound, 0, 0, false};
+  slab_reset(h);
+  size_t need = core_scratch_bytes(p, 0) + align256(16 * G) + align256(4 * G);
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
+  uint32_t* d_order = (uint32_t*)slab_alloc(h, 4 * G);
+  cudaStream_t s = h->stream;
+  phase_begin(h, "h2d");
+  if (G && !cuda_ok(h, cudaMemcpyAsync(d_gates, gates, 16 * G, cudaMemcpyHostToDevice, s), "gates H2D")) return C2A_ERR_CUDA;
+  phase_end(h);
+  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, nullptr, nullptr, nullptr, err_index, nullptr);
+  if (st == C2A_OK && G) {
+    phase_begin(h, "d2h");
+    cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
+    phase_end(h);
+  }
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "topo_sort sync") && st == C2A_OK) st = C2A_ERR_CUDA;
+  phases_collect(h);
+  return st;
+}
+
+int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const uint32_t* dep_idx, uint32_t* order_out, uint64_t* err_index) {
+  int st = check_sizes(h, n, 1);
+  if (st) return st;
+  if (n == 0) return C2A_OK;
+  if (!dep_off || !order_out) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  uint64_t nnz = dep_off[n];
+  if (nnz > 2 * n) return fail(h, C2A_ERR_INVALID_ARGUMENT, "more than 2 dependencies per item on average: not the reference's shape");
+  phases_clear(h);
+  slab_reset(h);
+  size_t need = align256(8 * (n + 1)) + align256(4 * nnz + 4) + align256(8 * n) + sort_scratch_bytes(n) + align256(4 * n);
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  unsigned long long* d_off = (unsigned long long*)slab_alloc(h, 8 * (n + 1));
+  uint32_t* d_idx = (uint32_t*)slab_alloc(h, 4 * nnz + 4);
+  uint2* dep = (uint2*)slab_alloc(h, 8 * n);
+  SortScratch s;
+  bool ok = sort_scratch_carve(h, n, &s);
+  uint32_t* d_order = (uint32_t*)slab_alloc(h, 4 * n);
+  if (!ok || !d_off || !d_idx || !dep || !d_order) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  cudaStream_t stq = h->stream;
+  uint32_t* hp = h->h_pinned;
+  for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
+  hp[S_ERR_LO] = hp[S_ERR_HI] = 0xFFFFFFFFu;
+  cudaMemcpyAsync(s.scalars, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, stq);
+  cudaMemcpyAsync(d_off, dep_off, 8 * (n + 1), cudaMemcpyHostToDevice, stq);
+  if (nnz) cudaMemcpyAsync(d_idx, dep_idx, 4 * nnz, cudaMemcpyHostToDevice, stq);
+  phase_begin(h, "deps");
+  LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, (uint32_t)n, dep, s.scalars);
+  phase_end(h);
+  cudaMemcpyAsync(hp, s.scalars, 4, cudaMemcpyDeviceToHost, stq);
+  if (!cuda_ok(h, cudaStreamSynchronize(stq), "deps sync")) return C2A_ERR_CUDA;
+  uint32_t flags = hp[S_FLAGS];
+  if (flags & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "dependency rows must have <= 2 entries with indices < n");
+  bool identity = true;
+  st = sort_from_deps(h, dep, (uint32_t)n, flags, s, d_order, &identity, err_index);
+  if (st == C2A_OK) {
+    if (identity) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, n), kBlock, d_order, (uint32_t)n);
+    cudaMemcpyAsync(order_out, d_order, 4 * n, cudaMemcpyDeviceToHost, stq);
+  }
+  if (!cuda_ok(h, cudaStreamSynchronize(stq), "sort sync") && st == C2A_OK) st = C2A_ERR_CUDA;
+  phases_collect(h);
+  return st;
+}
+
+}  // extern "C"
+
+#include "c2a_kahn.cuh"

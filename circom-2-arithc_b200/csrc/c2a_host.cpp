@@ -1,0 +1,427 @@
+// c2a_host.cpp — host half of the C ABI: the reference's `Compiler` (src/compiler.rs:107-284) restated over
+// a union-find so that emission is O(alpha) per call instead of the reference's O(signals) scans
+// (add_gate :185-195, add_connection :219-226) and O(gates) rewrite per connection (:260-270).
+//
+// What must be bit-identical to the reference, and how it is kept:
+//   * node ids: one counter, pre-incremented (:497-500); +1 per add_signal (:157), +1 per EFFECTIVE merge
+//     (:257), nothing when both signals already share a node (:235-237).  Each union-find root carries the
+//     id of the node it currently represents.
+//   * merged node = a's signals followed by b's (:254-255), flags OR-ed (:251-252): roots carry an ordered
+//     singly linked list (head/tail) and the two flags.
+//   * gates hold NODE ids that the reference keeps current by rewriting every gate on every merge.  Here
+//     gates hold union-find ELEMENTS and are resolved once, on demand (c2a_get_gates): same result.
+//   * a signal id that is in no node resolves to node id 0 (:183).  Gates that captured "node 0" ARE
+//     rewritten by a later add_connection involving an unknown signal (:260-270 compares against id 0), so
+//     "node 0" is modelled as a virtual union-find element that is replaced by a fresh one once merged.
+//   * errors: SignalAlreadyDeclared (:146), CannotMergeOutputNodes / CannotMergeConstantNodes (:239-245,
+//     evaluated at merge time), add_gate on an undeclared out signal panics upstream (:201) -> C2A_ERR_REFERENCE_PANIC.
+//
+// build_circuit (:321-494): the string maps are built here, the sort / wire numbering / gather run on the
+// device through c2a_build_circuit().  There is no CPU implementation of that part in this library.
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/c2a.h"
+
+namespace {
+
+const char* kGateNames[C2A_GATE_TYPE_COUNT] = {"AAdd", "ADiv", "AEq", "AGEq", "AGt", "ALEq", "ALt", "AMul", "ANeq", "ASub",
+                                               "AXor", "APow", "AIntDiv", "AMod", "AShiftL", "AShiftR", "ABoolOr", "ABoolAnd", "ABitOr", "ABitAnd"};
+
+constexpr uint32_t kNoElem = 0xFFFFFFFFu;
+constexpr uint8_t kConst = 1, kOut = 2;
+
+struct ElemGate {
+  uint32_t op, l, r, o;  // union-find elements
+};
+
+}  // namespace
+
+struct c2a_compiler {
+  // --- union-find over elements; element e < n_elem. Root-only fields are valid at roots.
+  std::vector<uint32_t> parent;
+  std::vector<uint32_t> rank_;
+  std::vector<uint32_t> node_id;   // root: id of the node this class currently is (0 for an unmerged virtual element)
+  std::vector<uint8_t> flags;      // root: kConst | kOut
+  std::vector<uint32_t> head, tail;  // root: first/last element of the ordered signal list (kNoElem when empty)
+  std::vector<uint32_t> next_in_list;  // per element
+  // --- per element signal data (virtual elements have sig_id = kNoElem)
+  std::vector<uint32_t> sig_id;
+  std::vector<uint32_t> sig_value;
+  std::vector<uint8_t> sig_has_value;
+  std::vector<int64_t> name_off;  // -1: unnamed temp ("random_<id>"), -2: "const_signal_<value>", >=0: offset in name_pool
+  std::string name_pool;
+  // --- signal id -> element
+  std::vector<uint32_t> dense;                    // ids < dense.size()
+  std::unordered_map<uint32_t, uint32_t> sparse;  // the rest
+  uint64_t n_signals = 0;
+  uint32_t zero_elem = kNoElem;  // current "node 0" stand-in
+  uint32_t node_count = 0;
+  std::vector<ElemGate> gates;
+  std::map<uint32_t, std::string> inputs, outputs;  // signal id -> name (ascending id = the deterministic stand-in for HashMap order)
+  std::vector<uint32_t> const_signals;              // ids with a value, in declaration order
+  std::string err;
+  // --- build results
+  std::vector<uint32_t> order;
+  std::vector<c2a_gate> new_gates;
+  uint64_t wire_count = 0;
+  std::string info_json;
+
+  uint32_t new_elem(uint32_t sid) {
+    uint32_t e = (uint32_t)parent.size();
+    parent.push_back(e);
+    rank_.push_back(0);
+    node_id.push_back(0);
+    flags.push_back(0);
+    head.push_back(kNoElem);
+    tail.push_back(kNoElem);
+    next_in_list.push_back(kNoElem);
+    sig_id.push_back(sid);
+    sig_value.push_back(0);
+    sig_has_value.push_back(0);
+    name_off.push_back(-1);
+    return e;
+  }
+  uint32_t elem_of(uint32_t sid) const {
+    if (sid < dense.size()) return dense[sid];
+    auto it = sparse.find(sid);
+    return it == sparse.end() ? kNoElem : it->second;
+  }
+  void bind(uint32_t sid, uint32_t e) {
+    // ids are sequential in practice (src/runtime.rs:120-125): keep them in a flat table, spill far-away ids
+    if (sid < dense.size()) { dense[sid] = e; return; }
+    if (sid <= dense.size() + (1u << 20) + dense.size() / 2) {
+      dense.resize((size_t)sid + 1, kNoElem);
+      dense[sid] = e;
+    } else sparse[sid] = e;
+  }
+  uint32_t find(uint32_t e) {
+    uint32_t r = e;
+    while (parent[r] != r) r = parent[r];
+    while (parent[e] != r) { uint32_t n = parent[e]; parent[e] = r; e = n; }
+    return r;
+  }
+  uint32_t zero() {  // element standing for "node id 0" (:183)
+    if (zero_elem == kNoElem) zero_elem = new_elem(kNoElem);
+    return zero_elem;
+  }
+  std::string name_of(uint32_t e) const {
+    if (name_off[e] >= 0) return std::string(name_pool.c_str() + name_off[e]);
+    if (name_off[e] == -2) return "const_signal_" + std::to_string(sig_value[e]);
+    return "random_" + std::to_string(sig_id[e]);
+  }
+
+  int add_signal(uint32_t id, const char* name, int has_value, uint32_t value, int synth_const_name) {
+    if (elem_of(id) != kNoElem) return C2A_ERR_SIGNAL_ALREADY_DECLARED;  // :146-148
+    uint32_t e = new_elem(id);
+    bind(id, e);
+    if (name) { name_off[e] = (int64_t)name_pool.size(); name_pool.append(name); name_pool.push_back('\0'); }
+    else if (synth_const_name) name_off[e] = -2;
+    sig_has_value[e] = has_value ? 1 : 0;
+    sig_value[e] = value;
+    if (has_value) const_signals.push_back(id);
+    node_id[e] = ++node_count;  // :157
+    flags[e] = has_value ? kConst : 0;  // :155
+    head[e] = tail[e] = e;
+    ++n_signals;
+    return C2A_OK;
+  }
+
+  int add_gate(uint32_t op, uint32_t lhs, uint32_t rhs, uint32_t out) {
+    if (op >= C2A_GATE_TYPE_COUNT) { err = "unsupported gate type: " + std::to_string(op); return C2A_ERR_INVALID_ARGUMENT; }
+    uint32_t eo = elem_of(out);
+    if (eo == kNoElem) { err = "add_gate: output signal " + std::to_string(out) + " is in no node (the reference panics at src/compiler.rs:201)"; return C2A_ERR_REFERENCE_PANIC; }
+    uint32_t el = elem_of(lhs), er = elem_of(rhs);
+    if (el == kNoElem) el = zero();
+    if (er == kNoElem) er = zero();
+    flags[find(eo)] |= kOut;  // :201
+    gates.push_back({op, el, er, eo});
+    return C2A_OK;
+  }
+
+  int add_connection(uint32_t a, uint32_t b) {
+    uint32_t ea = elem_of(a), eb = elem_of(b);
+    if (ea == kNoElem && eb == kNoElem) return C2A_OK;  // both resolve to node 0 (:235-237)
+    bool za = ea == kNoElem, zb = eb == kNoElem;
+    if (za) ea = zero();
+    if (zb) eb = zero();
+    uint32_t ra = find(ea), rb = find(eb);
+    if (ra == rb) return C2A_OK;                                                                 // :235-237
+    if ((flags[ra] & kOut) && (flags[rb] & kOut)) return C2A_ERR_CANNOT_MERGE_OUTPUT_NODES;      // :239-241
+    if ((flags[ra] & kConst) && (flags[rb] & kConst)) return C2A_ERR_CANNOT_MERGE_CONSTANT_NODES;  // :243-245
+    // union by rank; the surviving root takes the merged node's data
+    uint32_t root = ra, child = rb;
+    if (rank_[ra] < rank_[rb]) { root = rb; child = ra; }
+    else if (rank_[ra] == rank_[rb]) rank_[ra]++;
+    uint8_t f = flags[ra] | flags[rb];  // :251-252
+    uint32_t h, t;                      // a's signals then b's (:254-255)
+    if (head[ra] == kNoElem) { h = head[rb]; t = tail[rb]; }
+    else if (head[rb] == kNoElem) { h = head[ra]; t = tail[ra]; }
+    else { next_in_list[tail[ra]] = head[rb]; h = head[ra]; t = tail[rb]; }
+    parent[child] = root;
+    flags[root] = f;
+    head[root] = h;
+    tail[root] = t;
+    node_id[root] = ++node_count;  // :257
+    if (za || zb) zero_elem = kNoElem;  // gates that captured node 0 now follow the merged node (:260-270); later unknowns see a fresh 0
+    return C2A_OK;
+  }
+};
+
+extern "C" {
+
+const char* c2a_gate_type_name(uint32_t op) { return op < C2A_GATE_TYPE_COUNT ? kGateNames[op] : nullptr; }
+int c2a_gate_type_from_name(const char* name) {
+  if (!name) return -1;
+  for (int i = 0; i < C2A_GATE_TYPE_COUNT; ++i)
+    if (!strcmp(name, kGateNames[i])) return i;
+  return -1;
+}
+const char* c2a_status_string(int st) {
+  switch (st) {
+    case C2A_OK: return "ok";
+    case C2A_ERR_CYCLIC_DEPENDENCY: return "Cyclic dependency";               // compiler.rs:570 (+ ": {message}")
+    case C2A_ERR_INCONSISTENCY: return "Inconsistency";                        // :572
+    case C2A_ERR_SIGNAL_ALREADY_DECLARED: return "Signal already declared";   // :564
+    case C2A_ERR_CANNOT_MERGE_OUTPUT_NODES: return "Cannot merge output nodes";      // :554
+    case C2A_ERR_CANNOT_MERGE_CONSTANT_NODES: return "Cannot merge constant nodes";  // :552
+    case C2A_ERR_REFERENCE_PANIC: return "reference panics here";
+    case C2A_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case C2A_ERR_CUDA: return "CUDA error";
+    case C2A_ERR_NO_MEMORY: return "out of device memory";
+  }
+  return "unknown status";
+}
+
+c2a_compiler* c2a_compiler_new(void) { return new c2a_compiler(); }
+void c2a_compiler_free(c2a_compiler* c) { delete c; }
+const char* c2a_compiler_last_error(const c2a_compiler* c) { return c ? c->err.c_str() : "null compiler"; }
+
+int c2a_add_signal(c2a_compiler* c, uint32_t id, const char* name, int has_value, uint32_t value) { return c->add_signal(id, name, has_value, value, 0); }
+int c2a_add_gate(c2a_compiler* c, uint32_t op, uint32_t l, uint32_t r, uint32_t o) { return c->add_gate(op, l, r, o); }
+int c2a_add_connection(c2a_compiler* c, uint32_t a, uint32_t b) { return c->add_connection(a, b); }
+
+int c2a_emit_events(c2a_compiler* c, const c2a_event* ev, uint64_t n, uint64_t* err_event) {
+  for (uint64_t i = 0; i < n; ++i) {
+    int st;
+    switch (ev[i].kind & 0xFF) {
+      case C2A_EV_SIGNAL: st = c->add_signal(ev[i].a, nullptr, 0, 0, 0); break;
+      case C2A_EV_SIGNAL_CONST: st = c->add_signal(ev[i].a, nullptr, 1, ev[i].b, 1); break;
+      case C2A_EV_GATE: st = c->add_gate(ev[i].kind >> 8, ev[i].a, ev[i].b, ev[i].c); break;
+      case C2A_EV_CONNECT: st = c->add_connection(ev[i].a, ev[i].b); break;
+      default: st = C2A_ERR_INVALID_ARGUMENT;
+    }
+    if (st) { if (err_event) *err_event = i; return st; }
+  }
+  return C2A_OK;
+}
+
+int c2a_set_signal_name(c2a_compiler* c, uint32_t id, const char* name) {
+  uint32_t e = c->elem_of(id);
+  if (e == kNoElem || !name) return C2A_ERR_INVALID_ARGUMENT;
+  c->name_off[e] = (int64_t)c->name_pool.size();
+  c->name_pool.append(name);
+  c->name_pool.push_back('\0');
+  return C2A_OK;
+}
+
+int64_t c2a_signal_name(c2a_compiler* c, uint32_t id, char* buf, uint64_t cap) {
+  uint32_t e = c->elem_of(id);
+  if (e == kNoElem) return -1;
+  std::string nm = c->name_of(e);
+  if (buf && cap) { size_t k = std::min<size_t>(nm.size(), cap - 1); memcpy(buf, nm.data(), k); buf[k] = 0; }
+  return (int64_t)nm.size();
+}
+
+uint64_t c2a_get_signals_by_prefix(c2a_compiler* c, const char* prefix, uint32_t* ids_out, uint64_t cap) {
+  std::vector<uint32_t> ids;
+  size_t n = strlen(prefix);
+  for (uint32_t e = 0; e < c->parent.size(); ++e)
+    if (c->sig_id[e] != kNoElem && c->name_of(e).compare(0, n, prefix) == 0) ids.push_back(c->sig_id[e]);
+  std::sort(ids.begin(), ids.end());
+  for (size_t i = 0; i < ids.size() && i < cap; ++i) ids_out[i] = ids[i];
+  return ids.size();
+}
+
+int c2a_add_input(c2a_compiler* c, uint32_t id, const char* name) { c->inputs[id] = name ? name : ""; return C2A_OK; }
+int c2a_add_output(c2a_compiler* c, uint32_t id, const char* name) { c->outputs[id] = name ? name : ""; return C2A_OK; }
+
+// src/compiler.rs:163-171 + src/program.rs:57-66: every signal whose name starts with the prefix
+static void tag_prefix(c2a_compiler* c, const char* prefix, bool input) {
+  size_t n = strlen(prefix);
+  for (uint32_t e = 0; e < c->parent.size(); ++e) {
+    if (c->sig_id[e] == kNoElem) continue;
+    std::string nm = c->name_of(e);
+    if (nm.compare(0, n, prefix) == 0) (input ? c->inputs : c->outputs)[c->sig_id[e]] = nm;
+  }
+}
+int c2a_tag_inputs_by_prefix(c2a_compiler* c, const char* p) { if (!p) return C2A_ERR_INVALID_ARGUMENT; tag_prefix(c, p, true); return C2A_OK; }
+int c2a_tag_outputs_by_prefix(c2a_compiler* c, const char* p) { if (!p) return C2A_ERR_INVALID_ARGUMENT; tag_prefix(c, p, false); return C2A_OK; }
+
+uint64_t c2a_num_gates(const c2a_compiler* c) { return c->gates.size(); }
+uint32_t c2a_node_count(const c2a_compiler* c) { return c->node_count; }
+uint64_t c2a_num_signals(const c2a_compiler* c) { return c->n_signals; }
+
+int c2a_get_gates(c2a_compiler* c, c2a_gate* out) {
+  const size_t n = c->gates.size();
+  for (size_t i = 0; i < n; ++i) {
+    const ElemGate& g = c->gates[i];
+    out[i].op = g.op;
+    out[i].lh = c->node_id[c->find(g.l)];
+    out[i].rh = c->node_id[c->find(g.r)];
+    out[i].out = c->node_id[c->find(g.o)];
+  }
+  return C2A_OK;
+}
+
+int c2a_signal_node(c2a_compiler* c, uint32_t sid, uint32_t* node) {
+  uint32_t e = c->elem_of(sid);
+  *node = e == kNoElem ? 0 : c->node_id[c->find(e)];
+  return C2A_OK;
+}
+
+static void live_roots(c2a_compiler* c, std::vector<std::pair<uint32_t, uint32_t>>* out) {  // (node id, root)
+  for (uint32_t e = 0; e < c->parent.size(); ++e)
+    if (c->parent[e] == e && c->node_id[e] != 0) out->push_back({c->node_id[e], e});
+  std::sort(out->begin(), out->end());
+}
+uint64_t c2a_num_nodes(c2a_compiler* c) {
+  std::vector<std::pair<uint32_t, uint32_t>> v;
+  live_roots(c, &v);
+  return v.size();
+}
+int c2a_get_nodes(c2a_compiler* c, uint32_t* ids, uint8_t* flags, uint64_t* sig_off, uint32_t* sig) {
+  std::vector<std::pair<uint32_t, uint32_t>> v;
+  live_roots(c, &v);
+  uint64_t off = 0;
+  for (size_t i = 0; i < v.size(); ++i) {
+    uint32_t r = v[i].second;
+    if (ids) ids[i] = v[i].first;
+    if (flags) flags[i] = c->flags[r];
+    if (sig_off) sig_off[i] = off;
+    for (uint32_t e = c->head[r]; e != kNoElem; e = c->next_in_list[e]) {
+      if (sig) sig[off] = c->sig_id[e];
+      ++off;
+    }
+  }
+  if (sig_off) sig_off[v.size()] = off;
+  return C2A_OK;
+}
+
+static std::string jesc(const std::string& s) {
+  std::string o;
+  for (char ch : s) { if (ch == '"' || ch == '\\') o += '\\'; o += ch; }
+  return o;
+}
+
+// Compiler::build_circuit, src/compiler.rs:321-494
+int c2a_compiler_build_circuit(c2a_compiler* c, c2a_handle* h) {
+  if (!c) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h) { c->err = "no device handle: the back end has no CPU implementation"; return C2A_ERR_CUDA; }
+  // :327-361  IO <=> node, walked in ascending signal id
+  std::vector<std::pair<std::string, uint32_t>> input_to_node, output_to_node;
+  std::set<std::string> in_names, out_names;
+  {
+    auto ii = c->inputs.begin(), oi = c->outputs.begin();
+    while (ii != c->inputs.end() || oi != c->outputs.end()) {
+      uint32_t sid;
+      if (oi == c->outputs.end() || (ii != c->inputs.end() && ii->first <= oi->first)) sid = ii->first; else sid = oi->first;
+      uint32_t e = c->elem_of(sid);
+      bool is_in = ii != c->inputs.end() && ii->first == sid, is_out = oi != c->outputs.end() && oi->first == sid;
+      if (e != kNoElem) {  // signals that are in no node are never reached by the reference's node walk
+        uint32_t node = c->node_id[c->find(e)];
+        if (is_in) {
+          if (!in_names.insert(ii->second).second) { c->err = "Duplicate input " + ii->second; return C2A_ERR_INCONSISTENCY; }  // :337-341
+          input_to_node.push_back({ii->second, node});
+        }
+        if (is_out) {
+          if (!out_names.insert(oi->second).second) { c->err = "Duplicate output " + oi->second; return C2A_ERR_INCONSISTENCY; }  // :347-351
+          output_to_node.push_back({oi->second, node});
+        }
+      }
+      if (is_in) ++ii;
+      if (is_out) ++oi;
+    }
+  }
+  {  // :363-383
+    std::map<uint32_t, std::string> node_to_input;
+    for (auto& p : input_to_node) node_to_input[p.second] = p.first;
+    for (auto& p : output_to_node) {
+      auto f = node_to_input.find(p.second);
+      if (f != node_to_input.end()) {
+        c->err = "Node " + std::to_string(p.second) + " used for both input " + f->second + " and output " + p.first;
+        return C2A_ERR_INCONSISTENCY;
+      }
+    }
+  }
+  std::vector<uint32_t> in_nodes, out_nodes;
+  for (auto& p : input_to_node) in_nodes.push_back(p.second);
+  for (auto& p : output_to_node) out_nodes.push_back(p.second);
+
+  // :385-464 on the device
+  const uint64_t G = c->gates.size();
+  const uint32_t node_bound = c->node_count + 1;
+  std::vector<c2a_gate> gates(G);
+  c2a_get_gates(c, gates.data());
+  c->order.assign(G, 0);
+  c->new_gates.assign(G, c2a_gate{0, 0, 0, 0});
+  std::vector<uint32_t> wire(node_bound, C2A_NONE);
+  uint32_t wire_count = 0;
+  uint64_t err_index = 0;
+  int st = c2a_build_circuit(h, gates.data(), G, node_bound, in_nodes.data(), (uint32_t)in_nodes.size(), out_nodes.data(),
+                             (uint32_t)out_nodes.size(), c->order.data(), wire.data(), c->new_gates.data(), &wire_count, &err_index);
+  if (st == C2A_ERR_CYCLIC_DEPENDENCY) { c->err = "detected at i=" + std::to_string(err_index); return st; }
+  if (st != C2A_OK) { c->err = c2a_last_error(h); return st; }
+  c->wire_count = wire_count;
+
+  // :466-493
+  std::string j = "{\"input_name_to_wire_index\":{";
+  {
+    std::map<std::string, uint32_t> m;
+    for (auto& p : input_to_node) m[p.first] = wire[p.second];
+    bool first = true;
+    for (auto& kv : m) { j += first ? "" : ","; j += "\"" + jesc(kv.first) + "\":" + std::to_string(kv.second); first = false; }
+  }
+  j += "},\"constants\":{";
+  {
+    std::map<std::string, std::pair<uint32_t, std::string>> consts;  // key "<name>_<signal_id>" (:356)
+    std::vector<uint32_t> ids = c->const_signals;
+    std::sort(ids.begin(), ids.end());
+    for (uint32_t sid : ids) {
+      uint32_t e = c->elem_of(sid);
+      consts[c->name_of(e) + "_" + std::to_string(sid)] = {c->node_id[c->find(e)], std::to_string(c->sig_value[e])};
+    }
+    bool first = true;
+    for (auto& kv : consts) {
+      uint32_t w = wire[kv.second.first];
+      if (w == C2A_NONE) { c->err = "constant " + kv.first + " has no wire (the reference panics at src/compiler.rs:473)"; return C2A_ERR_REFERENCE_PANIC; }
+      j += first ? "" : ",";
+      j += "\"" + jesc(kv.first) + "\":{\"value\":\"" + kv.second.second + "\",\"wire_index\":" + std::to_string(w) + "}";
+      first = false;
+    }
+  }
+  j += "},\"output_name_to_wire_index\":{";
+  {
+    std::map<std::string, uint32_t> m;
+    for (auto& p : output_to_node) m[p.first] = wire[p.second];
+    bool first = true;
+    for (auto& kv : m) { j += first ? "" : ","; j += "\"" + jesc(kv.first) + "\":" + std::to_string(kv.second); first = false; }
+  }
+  j += "}}";
+  c->info_json = j;
+  return C2A_OK;
+}
+
+uint64_t c2a_circuit_wire_count(const c2a_compiler* c) { return c->wire_count; }
+const uint32_t* c2a_circuit_order(const c2a_compiler* c) { return c->order.data(); }
+const c2a_gate* c2a_circuit_gates(const c2a_compiler* c) { return c->new_gates.data(); }
+const char* c2a_circuit_info_json(const c2a_compiler* c) { return c->info_json.c_str(); }
+
+}  // extern "C"

@@ -1,0 +1,75 @@
+// c2a_internal.h — shared between the device translation units; not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/c2a.h"
+
+struct c2a_handle {
+  int device = 0;
+  int num_sms = 148;
+  cudaStream_t stream = nullptr;
+  // one growable device slab carved per call by a bump allocator (no per-call cudaMalloc)
+  char* slab = nullptr;
+  size_t slab_bytes = 0;
+  size_t slab_used = 0;
+  // pinned host staging for scalars and small metadata (I/O pairs)
+  uint32_t* h_pinned = nullptr;
+  size_t h_pinned_bytes = 0;
+  std::string err;
+  uint64_t launches = 0;
+  // phase timing: CUDA events recorded on `stream`
+  struct Phase {
+    std::string name;
+    cudaEvent_t a, b;
+    bool open;
+  };
+  std::vector<Phase> phases;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_next = 0;
+  std::vector<std::pair<std::string, double>> last_ms;
+  bool timing = true;
+};
+
+namespace c2a {
+
+int fail(c2a_handle* h, int status, const char* fmt, ...);
+bool cuda_ok(c2a_handle* h, cudaError_t e, const char* what);
+
+// slab allocator
+void slab_reset(c2a_handle* h);
+bool slab_reserve(c2a_handle* h, size_t bytes);  // ensure capacity (may reallocate: only legal right after slab_reset)
+void* slab_alloc(c2a_handle* h, size_t bytes);   // 256-byte aligned; nullptr when exhausted
+inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
+
+// phase timing
+void phase_begin(c2a_handle* h, const char* name);
+void phase_end(c2a_handle* h);
+void phases_collect(c2a_handle* h);  // after a stream sync: fills last_ms, adds "total"
+void phases_clear(c2a_handle* h);
+
+// Dependency pairs already on the device -> exact reference DFS order (K5a-c).
+// d_dep[n] (uint2), flags bit0 = some dep >= item. Writes d_order[n] unless identity && !want_order.
+// *identity_out tells the caller that order == iota (d_order is then only written when want_order).
+struct SortScratch {
+  uint32_t* r;
+  uint32_t* size_off;  // n+1
+  uint8_t* state;
+  uint32_t* inq;       // bitmask, (n+31)/32 words
+  uint32_t* q0;
+  uint32_t* q1;
+  uint32_t* heavy;     // n
+  unsigned long long* tile_state;
+  uint32_t* scalars;   // >= 16 u32 on the device
+};
+size_t sort_scratch_bytes(uint64_t n);
+bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s);
+int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_flags, const SortScratch& s,
+                   uint32_t* d_order, bool* identity_out, uint64_t* err_index);
+
+int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n);
+
+}  // namespace c2a

@@ -1,0 +1,349 @@
+"""Synthetic emission streams shaped like the BASELINE.json configs.
+
+The reference cannot compile circomlib Poseidon / SHA-256 / Keccak / MiMC7 (u32-only constants,
+src/process.rs:302; no `===`, :187; no inline arrays, :310), so these are event streams in the order the
+reference's walker WOULD emit them for an equivalent template written in its supported subset:
+  * a binary expression touching a signal emits: [const signal for a var operand], tmp signal, gate
+    (src/process.rs:426-478, 538-579);  `lhs <== expr` then connects tmp -> lhs (:241-273)
+  * constants are one signal per value per context; loop-body contexts are dropped per iteration
+    (src/runtime.rs:151-187), template calls start from an empty context (:75-77)
+  * a template body is emitted at the call site, BEFORE the caller wires the component inputs
+    (src/process.rs:353-367 vs :218-236)
+Signal ids are sequential (src/runtime.rs:120-125).
+"""
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional
+
+import numpy as np
+
+from .compiler import AGateType as G, EV_CONNECT, EV_GATE, EV_SIGNAL, EV_SIGNAL_CONST
+
+
+@dataclass
+class Workload:
+    name: str
+    events: np.ndarray            # (n,4) u32: kind|op<<8, a, b, c   (c2a_event)
+    inputs: Dict[int, str]        # main-template input signals  (id -> "0.<name>")
+    outputs: Dict[int, str]
+    n_gates: int
+    n_signals: int
+    meta: dict = field(default_factory=dict)
+
+
+class Emitter:
+    """Records the add_signal / add_gate / add_connection calls the walker makes."""
+
+    def __init__(self, first_signal: int = 0):
+        self.next = first_signal
+        self.ev: List[tuple] = []
+        self.names: Dict[int, str] = {}
+        self._consts: List[Dict[int, int]] = [{}]
+        self.n_gates = 0
+
+    # contexts (only the const-signal cache matters for emission)
+    def push_call(self):
+        self._consts.append({})
+
+    def push_scope(self):
+        self._consts.append(dict(self._consts[-1]))
+
+    def pop(self):
+        self._consts.pop()
+
+    def signal(self, name: Optional[str] = None) -> int:
+        i = self.next
+        self.next += 1
+        self.ev.append((EV_SIGNAL, i, 0, 0))
+        if name is not None:
+            self.names[i] = name
+        return i
+
+    def signals(self, n: int) -> List[int]:
+        return [self.signal() for _ in range(n)]
+
+    def const(self, value: int) -> int:  # make_constant, src/process.rs:558-579
+        c = self._consts[-1]
+        if value in c:
+            return c[value]
+        i = self.next
+        self.next += 1
+        self.ev.append((EV_SIGNAL_CONST, i, value & 0xFFFFFFFF, 0))
+        c[value] = i
+        return i
+
+    def gate(self, op: int, lhs: int, rhs: int) -> int:
+        out = self.signal()
+        self.ev.append((EV_GATE | (int(op) << 8), lhs, rhs, out))
+        self.n_gates += 1
+        return out
+
+    def connect(self, a: int, b: int):
+        self.ev.append((EV_CONNECT, a, b, 0))
+
+    def assign(self, lhs_signal: int, op: int, a: int, b: int):  # lhs <== a op b
+        self.connect(self.gate(op, a, b), lhs_signal)
+
+    def assign_c(self, lhs_signal: int, op: int, a: int, value: int):  # lhs <== a op <var>
+        c = self.const(value)
+        self.connect(self.gate(op, a, c), lhs_signal)
+
+    def array(self) -> np.ndarray:
+        return np.asarray(self.ev, dtype=np.uint32).reshape(-1, 4)
+
+
+def _tile(instance: Callable[[Emitter, int], None], base0: int, W: int):
+    """Replicate a per-instance emission W times.  Instances are structurally identical and every operand is
+    affine in the instance index w, so instance w = instance 0 + w * (instance 1 - instance 0); checked on w=2."""
+    def run(w, first):
+        em = Emitter(first)
+        instance(em, w)
+        return em
+    e0 = run(0, base0)
+    S = e0.next - base0
+    a0 = e0.array().astype(np.int64)
+    if W == 1:
+        return a0.astype(np.uint32), S, e0.n_gates
+    a1 = run(1, base0 + S).array().astype(np.int64)
+    stride = a1 - a0
+    assert (stride[:, 0] == 0).all(), "instances are not structurally identical"
+    if W > 2:
+        a2 = run(2, base0 + 2 * S).array().astype(np.int64)
+        assert (a2 == a0 + 2 * stride).all(), "operands are not affine in the instance index"
+    w = np.arange(W, dtype=np.int64)[:, None, None]
+    ev = (a0[None] + stride[None] * w).reshape(-1, 4)
+    return ev.astype(np.uint32), S, e0.n_gates
+
+
+def mimc_chains(W: int, rounds: int = 91, variant: str = "inorder") -> Workload:
+    """W independent MiMC-shaped chains under one main (config 5).  6 gates per round:
+    a=x+k, b=a+c_i, t2=b*b, t4=t2*t2, t6=t4*t2, t7=t6*b  (c_i = i).  G = 6*rounds*W (+W for 'late').
+    variant 'inorder': `c[w].x_in <== in[w]`          -> gate vector already in dependency order
+            'late'   : `c[w].x_in <== in[w] + 1` emitted after the chain body -> non-identity DFS order."""
+    assert variant in ("inorder", "late")
+    n = rounds
+    main = Emitter(0)
+    ins = [main.signal(f"0.in[{w}]") for w in range(W)]
+    k = main.signal("0.k")
+    outs = [main.signal(f"0.out[{w}]") for w in range(W)]
+    base0 = main.next
+
+    def instance(em: Emitter, w: int):
+        em.push_scope()      # main's `for` body context
+        em.push_call()       # template call: fresh context
+        x_in, k_c, out_c = em.signal(), em.signal(), em.signal()
+        a, b, t2, t4, t6, t7 = (em.signals(n) for _ in range(6))
+        for i in range(n):
+            em.push_scope()
+            x = x_in if i == 0 else t7[i - 1]
+            em.assign(a[i], G.AAdd, x, k_c)
+            em.assign_c(b[i], G.AAdd, a[i], i)
+            em.assign(t2[i], G.AMul, b[i], b[i])
+            em.assign(t4[i], G.AMul, t2[i], t2[i])
+            em.assign(t6[i], G.AMul, t4[i], t2[i])
+            em.assign(t7[i], G.AMul, t6[i], b[i])
+            em.pop()
+        em.connect(t7[n - 1], out_c)          # out <== t7[n-1]
+        em.pop()
+        if variant == "late":
+            em.assign_c(x_in, G.AAdd, w, 1)   # c[w].x_in <== in[w] + 1   (in[w] has signal id w)
+        else:
+            em.connect(w, x_in)               # c[w].x_in <== in[w]
+        em.connect(W, k_c)                    # c[w].k <== k
+        em.connect(out_c, W + 1 + w)          # out[w] <== c[w].out
+        em.pop()
+
+    ev, S, gpc = _tile(instance, base0, W)
+    events = np.concatenate([main.array(), ev], axis=0)
+    return Workload(
+        name=f"mimc_chains(W={W},rounds={rounds},{variant})", events=events,
+        inputs={**{i: f"0.in[{i}]" for i in range(W)}, k: "0.k"},
+        outputs={o: f"0.out[{o - W - 1}]" for o in outs},
+        n_gates=gpc * W, n_signals=base0 + S * W, meta={"W": W, "rounds": rounds, "variant": variant, "signals_per_chain": S})
+
+
+def poseidon_shaped(t: int = 3, RF: int = 8, RP: int = 57) -> Workload:
+    """Poseidon(2)-shaped permutation (config 2): ARC = AAdd with per-round constants c=(round*t+lane+1),
+    S-box x^5 = 3 AMul, MDS = t*t AMul-by-const + t*(t-1) AAdd.  t=3,RF=8,RP=57 -> 1413 gates."""
+    em = Emitter(0)
+    ins = [em.signal(f"0.in[{i}]") for i in range(t - 1)]
+    out = em.signal("0.out")
+    state = [em.signal() for _ in range(t)]
+    em.connect(em.const(0), state[0])  # capacity lane <== 0
+    for i in range(t - 1):
+        em.connect(ins[i], state[i + 1])
+    nr = RF + RP
+    for r in range(nr):
+        em.push_scope()
+        full = r < RF // 2 or r >= RF // 2 + RP
+        nxt = []
+        for lane in range(t):
+            nxt.append(em.gate(G.AAdd, state[lane], em.const(r * t + lane + 1)))
+        for lane in range(t if full else 1):
+            x = nxt[lane]
+            x2 = em.gate(G.AMul, x, x)
+            x4 = em.gate(G.AMul, x2, x2)
+            nxt[lane] = em.gate(G.AMul, x4, x)
+        mixed = []
+        for i in range(t):
+            acc = None
+            for j in range(t):
+                term = em.gate(G.AMul, nxt[j], em.const(((i + 1) * (j + 2)) % 7 + 1))
+                acc = term if acc is None else em.gate(G.AAdd, acc, term)
+            s = em.signal()
+            em.connect(acc, s)
+            mixed.append(s)
+        state = mixed
+        em.pop()
+    em.connect(state[0], out)
+    return Workload(name=f"poseidon_shaped(t={t},RF={RF},RP={RP})", events=em.array(),
+                    inputs={i: em.names[i] for i in ins}, outputs={out: "0.out"}, n_gates=em.n_gates, n_signals=em.next)
+
+
+def _xor(em, a, b):
+    return em.gate(G.AXor, a, b)
+
+
+def _and(em, a, b):
+    return em.gate(G.ABitAnd, a, b)
+
+
+def _add32(em: Emitter, a: List[int], b: List[int]) -> List[int]:
+    """bit-sliced ripple-carry adder, 5 gates per bit: s=a^b^c; c'=(a&b)^(c&(a^b))"""
+    out, carry = [], None
+    for i in range(len(a)):
+        axb = _xor(em, a[i], b[i])
+        if carry is None:
+            out.append(axb)
+            carry = _and(em, a[i], b[i])
+        else:
+            out.append(_xor(em, axb, carry))
+            carry = _xor(em, _and(em, a[i], b[i]), _and(em, carry, axb))
+    return out
+
+
+def _rot(a, r):
+    return a[r:] + a[:r]
+
+
+def sha256_shaped(rounds: int = 64) -> Workload:
+    """SHA-256-compression-shaped bit-sliced circuit (config 3): Σ/σ/Ch/Maj as AXor/ABitAnd on single-bit
+    signals, 32-bit ripple-carry adders. ~30 K gates at 64 rounds, depth in the thousands."""
+    em = Emitter(0)
+    w_in = [[em.signal(f"0.w[{i}][{b}]") for b in range(32)] for i in range(16)]
+    outs = [[em.signal(f"0.h[{i}][{b}]") for b in range(32)] for i in range(8)]
+    st = [[em.const((0x6A09E667 >> b) & 1 if i % 2 == 0 else (0xBB67AE85 >> b) & 1) for b in range(32)] for i in range(8)]
+    w = list(w_in)
+    for r in range(rounds):
+        em.push_scope()
+        a, b, c, d, e, f, g, h = st
+        if r >= 16:
+            x, y = w[r - 15], w[r - 2]
+            s0 = [_xor(em, _xor(em, p, q), z) for p, q, z in zip(_rot(x, 7), _rot(x, 18), _rot(x, 3))]
+            s1 = [_xor(em, _xor(em, p, q), z) for p, q, z in zip(_rot(y, 17), _rot(y, 19), _rot(y, 10))]
+            w.append(_add32(em, _add32(em, w[r - 16], s0), _add32(em, w[r - 7], s1)))
+        S1 = [_xor(em, _xor(em, p, q), z) for p, q, z in zip(_rot(e, 6), _rot(e, 11), _rot(e, 25))]
+        ch = [_xor(em, _and(em, p, q), _and(em, _xor(em, p, em.const(1)), z)) for p, q, z in zip(e, f, g)]
+        t1 = _add32(em, _add32(em, h, S1), _add32(em, ch, w[r]))
+        S0 = [_xor(em, _xor(em, p, q), z) for p, q, z in zip(_rot(a, 2), _rot(a, 13), _rot(a, 22))]
+        mj = [_xor(em, _xor(em, _and(em, p, q), _and(em, p, z)), _and(em, q, z)) for p, q, z in zip(a, b, c)]
+        t2 = _add32(em, S0, mj)
+        st = [_add32(em, t1, t2), a, b, c, _add32(em, d, t1), e, f, g]
+        em.pop()
+    for i in range(8):
+        for b_ in range(32):
+            # out <== state bit XOR 0-extended: keep outputs produced by gates (outputs cannot merge with consts)
+            em.connect(_xor(em, st[i][b_], w_in[i][b_]), outs[i][b_])
+    ins = {s: em.names[s] for row in w_in for s in row}
+    return Workload(name=f"sha256_shaped(rounds={rounds})", events=em.array(), inputs=ins,
+                    outputs={s: em.names[s] for row in outs for s in row}, n_gates=em.n_gates, n_signals=em.next)
+
+
+def keccak_shaped(instances: int = 1, rounds: int = 24) -> Workload:
+    """Keccak-f[1600]-shaped bit-sliced sponge permutation (config 4): θ (column parities, XOR), ρ/π as pure
+    rewiring, χ (a ^ (~b & c)), ι (XOR with a round constant on lane 0).  ~150 K gates per instance at 24 rounds.
+    `instances` independent permutations under one main = independent components for the 2-GPU shard."""
+    main = Emitter(0)
+    nin = 1600
+    ins = [[main.signal(f"0.in[{k}][{i}]") for i in range(nin)] for k in range(instances)]
+    outs = [[main.signal(f"0.out[{k}][{i}]") for i in range(nin)] for k in range(instances)]
+    base0 = main.next
+    rho = [0, 1, 62, 28, 27, 36, 44, 6, 55, 20, 3, 10, 43, 25, 39, 41, 45, 15, 21, 8, 18, 2, 61, 56, 14]
+
+    def instance(em: Emitter, k: int):
+        em.push_scope()
+        em.push_call()
+        s_in = [em.signal() for _ in range(nin)]
+        s_out = [em.signal() for _ in range(nin)]
+        A = [[s_in[(x + 5 * y) * 64:(x + 5 * y) * 64 + 64] for y in range(5)] for x in range(5)]
+        for r in range(rounds):
+            em.push_scope()
+            Cp = [[_xor(em, _xor(em, _xor(em, _xor(em, A[x][0][z], A[x][1][z]), A[x][2][z]), A[x][3][z]), A[x][4][z]) for z in range(64)] for x in range(5)]
+            D = [[_xor(em, Cp[(x - 1) % 5][z], Cp[(x + 1) % 5][(z - 1) % 64]) for z in range(64)] for x in range(5)]
+            A = [[[_xor(em, A[x][y][z], D[x][z]) for z in range(64)] for y in range(5)] for x in range(5)]
+            B = [[None] * 5 for _ in range(5)]
+            for x in range(5):
+                for y in range(5):
+                    rr = rho[x + 5 * y] % 64
+                    B[y][(2 * x + 3 * y) % 5] = A[x][y][-rr:] + A[x][y][:-rr] if rr else A[x][y]
+            one = em.const(1)
+            A = [[[_xor(em, B[x][y][z], _and(em, _xor(em, B[(x + 1) % 5][y][z], one), B[(x + 2) % 5][y][z])) for z in range(64)] for y in range(5)] for x in range(5)]
+            rc = (0x8000000080008081 * (r + 1) + 0x9E3779B97F4A7C15 * r) & ((1 << 64) - 1)
+            A[0][0] = [_xor(em, A[0][0][z], em.const((rc >> z) & 1)) for z in range(64)]
+            em.pop()
+        for x in range(5):
+            for y in range(5):
+                for z in range(64):
+                    em.connect(A[x][y][z], s_out[(x + 5 * y) * 64 + z])
+        em.pop()
+        # caller wiring AFTER the body (src/process.rs:353-367 vs :218-236): in -> component, component -> out
+        for i in range(nin):
+            em.connect(k * nin + i, s_in[i])
+        for i in range(nin):
+            em.connect(s_out[i], instances * nin + k * nin + i)
+        em.pop()
+
+    ev, S, gpc = _tile(instance, base0, instances)
+    events = np.concatenate([main.array(), ev], axis=0)
+    return Workload(name=f"keccak_shaped(instances={instances},rounds={rounds})", events=events,
+                    inputs={s: main.names[s] for row in ins for s in row}, outputs={s: main.names[s] for row in outs for s in row},
+                    n_gates=gpc * instances, n_signals=base0 + S * instances, meta={"instances": instances})
+
+
+def shuffle_gates(gates: np.ndarray, seed: int = 1) -> np.ndarray:
+    """Stress variant: permute the gate VECTOR (node ids unchanged) -> heavily out-of-order DFS roots."""
+    rng = np.random.RandomState(seed)
+    return np.ascontiguousarray(gates[rng.permutation(gates.shape[0])])
+
+
+def random_gates(G: int, n_free: int, seed: int, p_forward: float = 0.2, p_dup_out: float = 0.02, window: int = 0) -> tuple:
+    """Random gate vector in NODE-id form for back-end parity tests: node ids 1..n_free are producer-less
+    (inputs/constants), gate g writes node n_free+1+perm[g] (so producers are scattered and a fraction of
+    operands refer to gates that come LATER in the vector).  Cycle-free by construction: operands are chosen
+    among nodes whose producing gate has a smaller rank in a hidden topological order.
+    Returns (gates (G,4) u32, node_bound)."""
+    rng = np.random.RandomState(seed)
+    rank_of_gate = rng.permutation(G) if p_forward > 0 else np.arange(G)   # hidden topological rank
+    if p_forward < 1.0 and p_forward > 0:
+        keep = rng.rand(G) >= p_forward
+        rank_of_gate = np.where(keep, np.arange(G), rank_of_gate)
+        rank_of_gate = np.argsort(np.argsort(rank_of_gate, kind="stable"), kind="stable")
+    gate_of_rank = np.argsort(rank_of_gate)
+    out_node = n_free + 1 + np.arange(G)
+    gates = np.zeros((G, 4), dtype=np.uint32)
+    gates[:, 0] = rng.randint(0, 20, size=G)
+    gates[:, 3] = out_node
+    for slot in (1, 2):
+        rk = rank_of_gate
+        lo = np.maximum(0, rk - window) if window else np.zeros(G, dtype=np.int64)
+        pick_rank = (lo + (rng.rand(G) * np.maximum(rk - lo, 0)).astype(np.int64))
+        use_free = (rng.rand(G) < 0.3) | (rk == 0)
+        src_gate = gate_of_rank[np.minimum(pick_rank, np.maximum(rk - 1, 0))]
+        gates[:, slot] = np.where(use_free, rng.randint(1, n_free + 1, size=G), out_node[src_gate])
+    if p_dup_out > 0 and G > 4:
+        # a few gates share an out node with an EARLIER-ranked gate (merged nodes): last writer wins upstream
+        dup = np.where(rng.rand(G) < p_dup_out)[0]
+        for g in dup:
+            r = rank_of_gate[g]
+            if r > 0:
+                gates[g, 3] = out_node[gate_of_rank[rng.randint(0, r)]]
+    return gates, int(n_free + 1 + G)

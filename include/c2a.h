@@ -1,0 +1,190 @@
+/*
+ * c2a.h — C ABI of the B200-native gate-graph builder / topological sorter for the
+ * circom-2-arithc flattening hot path.
+ *
+ * The reference (namnc/circom-2-arithc, Rust) has no FFI of its own; the seams this ABI replaces are
+ * ordinary Rust calls (all paths relative to the reference tree):
+ *
+ *   emit side   Compiler::add_signal      src/compiler.rs:139-161
+ *               Compiler::add_gate        src/compiler.rs:174-209
+ *               Compiler::add_connection  src/compiler.rs:213-278
+ *               Compiler::add_inputs/add_outputs/get_signals   src/compiler.rs:131-137,163-171
+ *   back end    topological_sort          src/topological_sort.rs:3-50  (call site src/compiler.rs:408-421)
+ *               Compiler::build_circuit   src/compiler.rs:321-494
+ *
+ * Conventions: plain pointers and sizes, caller owns every buffer, one caller thread per handle,
+ * the CUDA device is chosen when the handle is created.  Every entry point returns a c2a_status:
+ * 0 = ok, positive = a reference error (CircuitError variant, src/compiler.rs:550-576, or a place
+ * where the reference panics), negative = CUDA / runtime failure (see c2a_last_error()).
+ * There is NO CPU fallback: if no CUDA device is usable the back-end calls fail with C2A_ERR_CUDA.
+ */
+#ifndef C2A_H_
+#define C2A_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2A_ABI_VERSION 1
+#define C2A_NONE 0xFFFFFFFFu /* "no gate" / "no wire" marker in u32 outputs */
+
+/* AGateType discriminants, declaration order of src/a_gate_type.rs:7-28.  The Bristol op token is the
+ * variant name (strum Display), see c2a_gate_type_name(). */
+typedef enum {
+  C2A_AAdd = 0, C2A_ADiv, C2A_AEq, C2A_AGEq, C2A_AGt, C2A_ALEq, C2A_ALt, C2A_AMul, C2A_ANeq, C2A_ASub,
+  C2A_AXor, C2A_APow, C2A_AIntDiv, C2A_AMod, C2A_AShiftL, C2A_AShiftR, C2A_ABoolOr, C2A_ABoolAnd,
+  C2A_ABitOr, C2A_ABitAnd, C2A_GATE_TYPE_COUNT
+} c2a_gate_type;
+
+typedef enum {
+  C2A_OK = 0,
+  C2A_ERR_CYCLIC_DEPENDENCY = 1,       /* CircuitError::CyclicDependency{"detected at i=<err_index>"}  topological_sort.rs:34-38 */
+  C2A_ERR_INCONSISTENCY = 2,           /* CircuitError::Inconsistency{message}                          compiler.rs:337,347,375 */
+  C2A_ERR_SIGNAL_ALREADY_DECLARED = 3, /* CircuitError::SignalAlreadyDeclared                           compiler.rs:146-148 */
+  C2A_ERR_CANNOT_MERGE_OUTPUT_NODES = 4,   /* compiler.rs:239-241 */
+  C2A_ERR_CANNOT_MERGE_CONSTANT_NODES = 5, /* compiler.rs:243-245 */
+  C2A_ERR_REFERENCE_PANIC = 6,         /* the reference panics here: add_gate on an undeclared out signal
+                                          (compiler.rs:201 unwrap) or a constant whose node never got a
+                                          wire (compiler.rs:473 index) */
+  C2A_ERR_INVALID_ARGUMENT = 7,
+  C2A_ERR_CUDA = -1,                   /* CUDA runtime / launch failure, or no device */
+  C2A_ERR_NO_MEMORY = -2
+} c2a_status;
+
+/* ArithmeticGate{op, lh_in, rh_in, out} (src/compiler.rs:85-90): 16 bytes, fields are NODE ids. */
+typedef struct { uint32_t op, lh, rh, out; } c2a_gate;
+
+/* One record of the emission event stream (what src/process.rs calls on the Compiler, in order). */
+typedef enum { C2A_EV_SIGNAL = 0, C2A_EV_SIGNAL_CONST = 1, C2A_EV_GATE = 2, C2A_EV_CONNECT = 3 } c2a_event_kind;
+typedef struct {
+  uint32_t kind; /* c2a_event_kind | (c2a_gate_type << 8) for C2A_EV_GATE */
+  uint32_t a;    /* SIGNAL: id        GATE: lhs signal   CONNECT: a */
+  uint32_t b;    /* SIGNAL_CONST: value GATE: rhs signal CONNECT: b */
+  uint32_t c;    /* GATE: out signal */
+} c2a_event;
+
+typedef struct c2a_handle c2a_handle;     /* device context: stream, scratch pool */
+typedef struct c2a_compiler c2a_compiler; /* host emitter: the Compiler restated over a union-find */
+
+/* ---- library ---- */
+int c2a_abi_version(void);
+const char* c2a_gate_type_name(uint32_t op);          /* "AAdd" ... "ABitAnd"; NULL if out of range */
+int c2a_gate_type_from_name(const char* name);        /* -1 if unknown (strum EnumString) */
+const char* c2a_status_string(int status);            /* thiserror Display strings of compiler.rs:550-576 */
+
+/* ---- device context ---- */
+int c2a_create(int device, c2a_handle** out);         /* C2A_ERR_CUDA when no usable device */
+void c2a_destroy(c2a_handle* h);
+const char* c2a_last_error(const c2a_handle* h);      /* text of the last non-zero status on this handle */
+int c2a_device_count(void);                           /* 0 when CUDA is unavailable */
+uint64_t c2a_kernel_launches(const c2a_handle* h);    /* number of kernels this handle has launched so far */
+double c2a_last_kernel_ms(const c2a_handle* h, const char* name); /* CUDA-event time of the named phase in the last
+                                                         call ("producer","deps","relax","trees","wire_first",
+                                                         "wire_scan","gather","kahn","total"); <0 if unknown */
+const char* c2a_last_phases(c2a_handle* h);           /* "name=ms,..." for every phase of the last call */
+void c2a_set_timing(c2a_handle* h, int on);           /* phase events on/off (default on) */
+void* c2a_stream(c2a_handle* h);                      /* the cudaStream_t every kernel of this handle runs on */
+
+/* ---- back end (device).  Host-pointer forms copy H2D/D2H inside the call. ---- */
+
+/* topological_sort as called from build_circuit: deps(g) = [producer[lh], producer[rh]] where
+ * producer[node] = LAST gate whose out is node (src/compiler.rs:401-421).  order_out[G] is the exact DFS
+ * post-order of src/topological_sort.rs.  On C2A_ERR_CYCLIC_DEPENDENCY *err_index = the i of the message. */
+int c2a_topo_sort(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t node_bound,
+                  uint32_t* order_out, uint64_t* err_index);
+
+/* Generic get_deps form (src/topological_sort.rs:3-6): item i depends on dep_idx[dep_off[i] .. dep_off[i+1]),
+ * visited in that order.  At most 2 deps per item are accelerated on the device (the only shape the
+ * reference ever passes); rows longer than 2 return C2A_ERR_INVALID_ARGUMENT. */
+int c2a_topo_sort_deps(c2a_handle*, uint64_t n, const uint64_t* dep_off, const uint32_t* dep_idx,
+                       uint32_t* order_out, uint64_t* err_index);
+
+/* Compiler::build_circuit minus the string maps (src/compiler.rs:388-464): inputs take wires 0..n_in in
+ * the order given, intermediate nodes first-seen over the sorted gates [lh, rh, out] skipping output
+ * nodes, outputs last in the order given.  wire_of_node[node_bound] gets C2A_NONE for nodes without a wire.
+ * Any of order_out / wire_of_node / new_gates may be NULL when not wanted. */
+int c2a_build_circuit(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t node_bound,
+                      const uint32_t* input_nodes, uint32_t n_in,
+                      const uint32_t* output_nodes, uint32_t n_out,
+                      uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates,
+                      uint32_t* wire_count, uint64_t* err_index);
+
+/* Same, all pointers are DEVICE pointers on the handle's device (no copies; asynchronous on the handle's
+ * stream until the final status read).  Used by bench.py for the HBM-resident number. */
+int c2a_build_circuit_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, uint32_t node_bound,
+                             const uint32_t* d_input_nodes, uint32_t n_in,
+                             const uint32_t* d_output_nodes, uint32_t n_out,
+                             uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates,
+                             uint32_t* wire_count, uint64_t* err_index);
+
+/* Level-synchronous Kahn frontier over the same dependency relation (not the reference order; used for the
+ * layer-wise sweeps and the evaluator).  level_order[G] is level-major; level_off[*n_levels+1] delimits levels
+ * (caller provides capacity level_cap+1; more levels than level_cap -> C2A_ERR_INVALID_ARGUMENT).
+ * Leftover gates => C2A_ERR_CYCLIC_DEPENDENCY (err_index = smallest gate index on/behind a cycle). */
+int c2a_topo_levels(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t node_bound,
+                    uint32_t* level_order, uint32_t* level_off, uint32_t level_cap, uint32_t* n_levels,
+                    uint64_t* err_index);
+int c2a_topo_levels_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, uint32_t node_bound,
+                           uint32_t* d_level_order, uint32_t* d_level_off, uint32_t level_cap,
+                           uint32_t* n_levels, uint64_t* err_index);
+
+/* Opt-in layer-wise sweeps (NOT in the reference; never alter build_circuit output).
+ * const_mask[g]=1 when both operands are constant or constant-derived, const_value[g] its u32 value under
+ * execute_op semantics (src/process.rs:649-750; gates that would error are left non-constant);
+ * dead_mask[g]=1 when gate g does not reach any node in output_nodes. */
+int c2a_sweep_masks(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t node_bound,
+                    const uint32_t* const_nodes, const uint32_t* const_values, uint32_t n_const,
+                    const uint32_t* output_nodes, uint32_t n_out,
+                    uint8_t* const_mask, uint32_t* const_value, uint8_t* dead_mask, uint64_t* err_index);
+
+/* ---- emit side (host).  Node ids, gate vector and error behaviour identical to the reference Compiler. ---- */
+c2a_compiler* c2a_compiler_new(void);
+void c2a_compiler_free(c2a_compiler*);
+const char* c2a_compiler_last_error(const c2a_compiler*);
+/* name may be NULL (an unnamed temporary); has_value != 0 makes it a constant signal */
+int c2a_add_signal(c2a_compiler*, uint32_t id, const char* name, int has_value, uint32_t value);
+int c2a_add_gate(c2a_compiler*, uint32_t op, uint32_t lhs_signal, uint32_t rhs_signal, uint32_t out_signal);
+int c2a_add_connection(c2a_compiler*, uint32_t a, uint32_t b);
+/* bulk replay of an event stream; stops at the first error and stores its index in *err_event */
+int c2a_emit_events(c2a_compiler*, const c2a_event* ev, uint64_t n, uint64_t* err_event);
+/* I/O tagging: explicit, or the reference's prefix match over signal names (src/program.rs:57-66) */
+int c2a_add_input(c2a_compiler*, uint32_t signal_id, const char* name);
+int c2a_add_output(c2a_compiler*, uint32_t signal_id, const char* name);
+int c2a_tag_inputs_by_prefix(c2a_compiler*, const char* prefix);
+int c2a_tag_outputs_by_prefix(c2a_compiler*, const char* prefix);
+/* resolve gates to node ids (what the reference keeps up to date by rewriting every gate per connection) */
+uint64_t c2a_num_gates(const c2a_compiler*);
+uint32_t c2a_node_count(const c2a_compiler*);        /* the reference's node_count; node ids are 1..node_count */
+uint64_t c2a_num_signals(const c2a_compiler*);
+int c2a_get_gates(c2a_compiler*, c2a_gate* out /* num_gates */);
+int c2a_signal_node(c2a_compiler*, uint32_t signal_id, uint32_t* node_id); /* 0 when the signal is unknown */
+/* name of a declared signal ("random_<id>" for unnamed temporaries, "const_signal_<v>" for bulk constants);
+ * returns the length, or -1 when the signal is unknown; copies at most cap-1 bytes + NUL into buf */
+int64_t c2a_signal_name(c2a_compiler*, uint32_t signal_id, char* buf, uint64_t cap);
+int c2a_set_signal_name(c2a_compiler*, uint32_t signal_id, const char* name);
+/* Compiler::get_signals (src/compiler.rs:163-171): ids of the signals whose name starts with prefix, ascending;
+ * returns the count (writes at most cap ids) */
+uint64_t c2a_get_signals_by_prefix(c2a_compiler*, const char* prefix, uint32_t* ids_out, uint64_t cap);
+/* live nodes: ids ascending; flags bit0=is_const bit1=is_out; signals of node i are
+ * sig[sig_off[i] .. sig_off[i+1]) in the reference's merge order. Pass NULL to size. */
+uint64_t c2a_num_nodes(c2a_compiler*);
+int c2a_get_nodes(c2a_compiler*, uint32_t* node_ids, uint8_t* flags, uint64_t* sig_off, uint32_t* sig);
+
+/* Compiler::build_circuit (src/compiler.rs:321-494): host name maps + device sort/renumber.
+ * Results are held by the compiler object until the next build/free. Inputs/outputs are numbered in
+ * ascending signal-id order (the reference's order is HashMap iteration order, i.e. unspecified). */
+int c2a_compiler_build_circuit(c2a_compiler*, c2a_handle*);
+uint64_t c2a_circuit_wire_count(const c2a_compiler*);
+const uint32_t* c2a_circuit_order(const c2a_compiler*);       /* num_gates */
+const c2a_gate* c2a_circuit_gates(const c2a_compiler*);       /* num_gates, wire ids */
+/* circuit.info as JSON: {"input_name_to_wire_index":{},"constants":{name:{"value":"..","wire_index":n}},
+ * "output_name_to_wire_index":{}} with keys sorted */
+const char* c2a_circuit_info_json(const c2a_compiler*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* C2A_H_ */
