@@ -1,0 +1,304 @@
+"""GPU parity: the CUDA back end (through the C ABI) against the CPU oracle, bit for bit.
+Reference: src/compiler.rs:388-464 + src/topological_sort.rs:3-50."""
+import numpy as np
+import pytest
+
+import miniwalker as mw
+
+pytestmark = pytest.mark.gpu
+
+
+def check_backend(ctx, orc, c2a, gates, node_bound, ins, outs):
+    gates = np.ascontiguousarray(gates, dtype=np.uint32).reshape(-1, 4)
+    st, err, o_order, o_wire, o_gates, o_wc = orc.backend_raw(gates, node_bound, ins, outs)
+    if st != 0:
+        with pytest.raises(c2a.CircuitError) as e:
+            ctx.build_circuit(gates, node_bound, ins, outs)
+        assert int(e.value.status) == st == 1
+        assert e.value.message == f"detected at i={err}"
+        with pytest.raises(c2a.CircuitError) as e:
+            ctx.topo_sort(gates, node_bound)
+        assert e.value.message == f"detected at i={err}"
+        return "cycle"
+    order, wire, ng, wc = ctx.build_circuit(gates, node_bound, ins, outs)
+    assert np.array_equal(order, o_order), f"order differs first at {np.argmax(order != o_order)}"
+    assert wc == o_wc
+    assert np.array_equal(wire, o_wire)
+    assert np.array_equal(ng, o_gates)
+    assert np.array_equal(ctx.topo_sort(gates, node_bound), o_order)
+    return "ok"
+
+
+def io_lists(rng, gates, node_bound, n_free):
+    G = gates.shape[0]
+    ins = rng.choice(np.arange(1, n_free + 1), size=min(n_free, 1 + n_free // 2), replace=False).astype(np.uint32) if n_free else np.zeros(0, np.uint32)
+    if G:
+        cand = np.setdiff1d(np.unique(gates[:, 3]), ins)
+        outs = rng.choice(cand, size=min(len(cand), 1 + G // 10), replace=False).astype(np.uint32) if len(cand) else np.zeros(0, np.uint32)
+    else:
+        outs = np.zeros(0, np.uint32)
+    return ins, outs
+
+
+@pytest.mark.parametrize("G", [0, 1, 2, 3, 31, 32, 33, 257, 1000, 2049, 20000])
+@pytest.mark.parametrize("p_forward", [0.0, 0.05, 0.5, 1.0])
+def test_random_dags(ctx, orc, c2a, G, p_forward):
+    rng = np.random.RandomState(G * 7 + int(p_forward * 100))
+    n_free = 1 + G // 7
+    gates, nb = c2a.workloads.random_gates(G, n_free, seed=G + int(100 * p_forward), p_forward=p_forward, p_dup_out=0.0)
+    ins, outs = io_lists(rng, gates, nb, n_free)
+    assert check_backend(ctx, orc, c2a, gates, nb, ins, outs) == "ok"
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_dags_with_shared_out_nodes(ctx, orc, c2a, seed):
+    """several gates write the same node (merged nodes): the LAST one is the producer (compiler.rs:403-406);
+    this can create cycles, in which case status and 'detected at i=' must match too."""
+    rng = np.random.RandomState(seed)
+    G = int(rng.randint(5, 3000))
+    gates, nb = c2a.workloads.random_gates(G, 1 + G // 5, seed=seed, p_forward=float(rng.choice([0.0, 0.3, 1.0])), p_dup_out=0.05)
+    ins, outs = io_lists(rng, gates, nb, 1 + G // 5)
+    check_backend(ctx, orc, c2a, gates, nb, ins, outs)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_windowed_deep_dags(ctx, orc, c2a, seed):
+    """operands drawn from a short window of the hidden order -> deep dependency chains, big DFS trees."""
+    G = 30000
+    gates, nb = c2a.workloads.random_gates(G, 50, seed=100 + seed, p_forward=[1.0, 0.5, 0.1, 0.01][seed % 4], p_dup_out=0.0, window=[2, 8][seed // 4])
+    rng = np.random.RandomState(seed)
+    ins, outs = io_lists(rng, gates, nb, 50)
+    assert check_backend(ctx, orc, c2a, gates, nb, ins, outs) == "ok"
+
+
+def test_reversed_chain_single_giant_tree(ctx, orc, c2a):
+    """gate 0 is the LAST link of a chain: root 0 reaches everything (one DFS tree of G items)."""
+    G = 5000
+    gates = np.zeros((G, 4), dtype=np.uint32)
+    gates[:, 0] = 7
+    gates[:, 3] = 10 + np.arange(G)          # gate g writes node 10+g
+    gates[:, 1] = 10 + np.arange(G) + 1      # and reads the node written by gate g+1
+    gates[:, 2] = 1
+    gates[G - 1, 1] = 2
+    assert check_backend(ctx, orc, c2a, gates, 10 + G + 1, [1, 2], [10]) == "ok"
+
+
+def test_cycles(ctx, orc, c2a):
+    A = mw.AAdd
+    # self loop: gate reads its own out node
+    assert check_backend(ctx, orc, c2a, [[A, 5, 1, 5]], 6, [1], []) == "cycle"
+    # self loop behind an in-order prefix
+    assert check_backend(ctx, orc, c2a, [[A, 1, 2, 3], [A, 3, 4, 4]], 6, [1, 2], []) == "cycle"
+    # 2-cycle reached from root 0 through rh
+    assert check_backend(ctx, orc, c2a, [[A, 1, 6, 5], [A, 7, 1, 6], [A, 6, 1, 7]], 8, [1], []) == "cycle"
+    # 3-cycle not containing gate 0; plus an unrelated acyclic part
+    g = [[A, 1, 2, 3], [A, 12, 1, 10], [A, 10, 1, 11], [A, 11, 3, 12], [A, 3, 3, 13]]
+    assert check_backend(ctx, orc, c2a, g, 14, [1, 2], [13]) == "cycle"
+    # two cycles: the one met first in DFS order is reported
+    g = [[A, 21, 1, 20], [A, 20, 1, 21], [A, 31, 1, 30], [A, 30, 1, 31]]
+    assert check_backend(ctx, orc, c2a, g, 32, [1], []) == "cycle"
+
+
+def test_same_node_on_both_operands_and_outputs(ctx, orc, c2a):
+    A, M = mw.AAdd, mw.AMul
+    g = [[M, 1, 1, 2], [M, 2, 2, 3], [A, 3, 2, 4], [A, 4, 4, 4 + 1]]
+    assert check_backend(ctx, orc, c2a, g, 6, [1], [5]) == "ok"
+    # out node equal to an input node of the circuit, output listed twice, input listed twice (last insert wins)
+    assert check_backend(ctx, orc, c2a, g, 6, [1, 1], [5, 3, 5]) == "ok"
+    # node that is both an input and an output of the raw call (the clash check lives above this layer)
+    assert check_backend(ctx, orc, c2a, g, 6, [1, 3], [3]) == "ok"
+    # node id 0 (unknown signal upstream) is just another node
+    assert check_backend(ctx, orc, c2a, [[A, 0, 1, 2], [A, 2, 0, 3]], 4, [1], [3]) == "ok"
+
+
+def test_invalid_arguments(ctx, c2a):
+    with pytest.raises(c2a.C2AError):
+        ctx.build_circuit(np.array([[0, 1, 2, 9]], dtype=np.uint32), 5, [1], [])
+    with pytest.raises(c2a.C2AError):
+        ctx.build_circuit(np.array([[0, 1, 2, 3]], dtype=np.uint32), 5, [7], [])
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_generic_get_deps_form(ctx, orc, c2a, seed):
+    """topological_sort(len, get_deps) with arbitrary <=2-entry rows (topological_sort.rs:3-6)."""
+    rng = np.random.RandomState(seed)
+    n = int(rng.randint(1, 4000))
+    hidden = rng.permutation(n)
+    pos = np.argsort(hidden)
+    deps = []
+    for i in range(n):
+        k = int(rng.randint(0, 3))
+        p = pos[i]
+        deps.append([int(hidden[rng.randint(0, p)]) for _ in range(k)] if p > 0 else [])
+    want = orc.topological_sort(deps)
+    got = c2a.topological_sort(n, lambda i: deps[i])
+    assert got == want.tolist()
+    if n > 3:
+        deps[int(hidden[0])] = [int(hidden[n - 1])]  # close a cycle through the whole order? only if reachable
+        try:
+            want = orc.topological_sort(deps).tolist()
+            assert c2a.topological_sort(n, lambda i: deps[i]) == want
+        except orc.OracleError as e:
+            with pytest.raises(c2a.CircuitError) as ge:
+                c2a.topological_sort(n, lambda i: deps[i])
+            assert str(ge.value) == f"Cyclic dependency: {e.message}"
+
+
+FIXTURES = [mw.fixture_add_zero, mw.fixture_sum, mw.fixture_x_eq_x, mw.fixture_constant_sum, mw.fixture_direct_output,
+            mw.fixture_infix_ops, mw.fixture_mat_elem_mul, mw.fixture_array_assignment]
+
+
+@pytest.mark.parametrize("fx", FIXTURES, ids=lambda f: f.__name__)
+def test_reference_fixtures_full_build(ctx, orc, c2a, fx):
+    """Compiler.build_circuit end to end (host maps + device) == oracle, incl. circuit.info."""
+    a = orc.OracleCompiler()
+    fx(a)
+    want = a.build_circuit()
+    b = c2a.Compiler(context=ctx)
+    fx(b)
+    got = b.build_circuit()
+    assert got.wire_count == want["wire_count"]
+    assert np.array_equal(got.order, want["order"]) and np.array_equal(got.gate_array, want["gates"])
+    assert got.info.input_name_to_wire_index == want["info"]["input_name_to_wire_index"]
+    assert got.info.output_name_to_wire_index == want["info"]["output_name_to_wire_index"]
+    assert {k: {"value": v.value, "wire_index": v.wire_index} for k, v in got.info.constants.items()} == want["info"]["constants"]
+
+
+def test_reference_integration_goldens_on_gpu(ctx, c2a):
+    """tests/integration.rs:393-441 exact assertions, through the product."""
+    c = c2a.Compiler(context=ctx)
+    mw.fixture_constant_sum(c)
+    circ = c.build_circuit()
+    assert len(circ.info.constants) == 1
+    assert circ.info.constants["0.const_signal_8_1"] == c2a.compiler.ConstantInfo("8", 0)
+    c = c2a.Compiler(context=ctx)
+    mw.fixture_direct_output(c)
+    circ = c.build_circuit()
+    assert circ.info.output_name_to_wire_index == {"0.out": 0}
+    assert circ.info.constants["0.const_signal_42_1"] == c2a.compiler.ConstantInfo("42", 0)
+    c = c2a.Compiler(context=ctx)
+    mw.fixture_prefix_ops(c)
+    with pytest.raises(c2a.CircuitError) as e:
+        c.build_circuit()
+    assert str(e.value).startswith("Inconsistency: Node ") and "used for both input 0.complement" in str(e.value)
+
+
+def test_reference_simulations_on_gpu(ctx, orc, c2a):
+    """tests/integration.rs:279-374: compile -> build_circuit (GPU) -> simulate."""
+    def run(fx, inputs):
+        c = c2a.Compiler(context=ctx)
+        fx(c)
+        circ = c.build_circuit()
+        vals = {circ.info.input_name_to_wire_index[k]: v for k, v in inputs.items()}
+        for ci in circ.info.constants.values():
+            vals[ci.wire_index] = int(ci.value)
+        wires = orc.simulate(circ.gate_array, circ.wire_count, vals)
+        return {k: wires[w] for k, w in circ.info.output_name_to_wire_index.items()}
+    assert run(mw.fixture_add_zero, {"0.in": 42}) == {"0.out": 42}
+    assert run(mw.fixture_infix_ops, {f"0.x{i}": i for i in range(6)}) == {f"0.{n}": e for n, _o, _l, _r, e in mw.INFIX_OUTPUTS}
+    assert run(mw.fixture_sum, {"0.a": 3, "0.b": 5}) == {"0.out": 8}
+    assert run(mw.fixture_x_eq_x, {"0.x": 37}) == {"0.out": 1}
+    ins = {f"0.{m}[{i}][{j}]": 2 for m in "ab" for i in range(2) for j in range(2)}
+    assert run(mw.fixture_mat_elem_mul, ins) == {f"0.out[{i}][{j}]": 4 for i in range(2) for j in range(2)}
+
+
+def full_compare(ctx, orc, c2a, wl, shuffle_seed=None):
+    b = c2a.Compiler(context=ctx)
+    b.emit_events(wl.events)
+    gates = b.gate_array()
+    nb = b.node_count + 1
+    ins = np.array([b.signal_node(s) for s in sorted(wl.inputs)], dtype=np.uint32)
+    outs = np.array([b.signal_node(s) for s in sorted(wl.outputs)], dtype=np.uint32)
+    if shuffle_seed is not None:
+        gates = c2a.workloads.shuffle_gates(gates, shuffle_seed)
+    assert check_backend(ctx, orc, c2a, gates, nb, ins, outs) == "ok"
+    return gates
+
+
+@pytest.mark.parametrize("variant,shuffle", [("inorder", None), ("late", None), ("inorder", 1), ("late", 2)])
+def test_mimc_chains(ctx, orc, c2a, variant, shuffle):
+    full_compare(ctx, orc, c2a, c2a.workloads.mimc_chains(37, rounds=91, variant=variant), shuffle)
+
+
+def test_poseidon_shaped(ctx, orc, c2a):
+    wl = c2a.workloads.poseidon_shaped()
+    assert wl.n_gates == 1413
+    full_compare(ctx, orc, c2a, wl)
+    full_compare(ctx, orc, c2a, wl, shuffle_seed=3)
+
+
+def test_sha256_shaped(ctx, orc, c2a):
+    wl = c2a.workloads.sha256_shaped(rounds=20)
+    full_compare(ctx, orc, c2a, wl)
+    full_compare(ctx, orc, c2a, wl, shuffle_seed=4)
+
+
+def test_keccak_shaped_two_instances(ctx, orc, c2a):
+    wl = c2a.workloads.keccak_shaped(instances=2, rounds=2)
+    full_compare(ctx, orc, c2a, wl)
+
+
+def test_mimc_full_compiler_path_with_names(ctx, orc, c2a):
+    wl = c2a.workloads.mimc_chains(5, rounds=7, variant="late")
+    a, b = orc.OracleCompiler(), c2a.Compiler(context=ctx)
+    for c in (a, b):
+        c.emit_events(wl.events)
+        for sid, nm in {**wl.inputs, **wl.outputs}.items():
+            c.set_signal_name(sid, nm)
+        c.add_inputs(wl.inputs)
+        c.add_outputs(wl.outputs)
+    want, got = a.build_circuit(), b.build_circuit()
+    assert got.wire_count == want["wire_count"] and np.array_equal(got.gate_array, want["gates"])
+    assert got.info.input_name_to_wire_index == want["info"]["input_name_to_wire_index"]
+    assert {k: {"value": v.value, "wire_index": v.wire_index} for k, v in got.info.constants.items()} == want["info"]["constants"]
+
+
+@pytest.mark.parametrize("variant,shuffle", [("inorder", None), ("late", None), ("late", 1)])
+def test_one_million_gates_vs_oracle(ctx, orc, c2a, variant, shuffle):
+    """BASELINE config 5 at the 1 M-gate point, bit-exact against the oracle."""
+    wl = c2a.workloads.mimc_chains(1832, rounds=91, variant=variant)
+    gates = full_compare(ctx, orc, c2a, wl, shuffle)
+    assert gates.shape[0] >= 1_000_000
+
+
+def test_ten_million_gates_properties(ctx, c2a):
+    """Full BASELINE size (10 M gates): size-independent properties instead of the oracle —
+    order is a permutation, every dependency precedes its consumer, wires are a dense first-seen numbering,
+    and sorting the already-sorted circuit is the identity (idempotence)."""
+    wl = c2a.workloads.mimc_chains(18315, rounds=91, variant="late")
+    b = c2a.Compiler(context=ctx)
+    b.emit_events(wl.events)
+    gates = b.gate_array()
+    G = gates.shape[0]
+    assert G == 18315 * 547
+    nb = b.node_count + 1
+    ins = np.array([b.signal_node(s) for s in sorted(wl.inputs)], dtype=np.uint32)
+    outs = np.array([b.signal_node(s) for s in sorted(wl.outputs)], dtype=np.uint32)
+    order, wire, ng, wc = ctx.build_circuit(gates, nb, ins, outs)
+    assert np.array_equal(np.sort(order), np.arange(G, dtype=np.uint32))
+    pos = np.empty(G, dtype=np.int64)
+    pos[order] = np.arange(G)
+    prod = np.full(nb, -1, dtype=np.int64)
+    prod[gates[:, 3]] = np.arange(G)            # ascending index: last writer wins
+    for slot in (1, 2):
+        d = prod[gates[:, slot]]
+        m = d >= 0
+        assert (pos[d[m]] < pos[np.nonzero(m)[0]]).all()
+    sg = gates[order]
+    assert np.array_equal(ng[:, 0], sg[:, 0])
+    for slot in (1, 2, 3):
+        assert np.array_equal(ng[:, slot], wire[sg[:, slot]])
+    used = np.unique(np.concatenate([gates[:, 1], gates[:, 2], gates[:, 3], ins, outs]))
+    assert wc == len(used) == len(np.unique(wire[used])) and wire[used].max() == wc - 1
+    assert np.array_equal(wire[ins], np.arange(len(ins))) and np.array_equal(wire[outs], wc - len(outs) + np.arange(len(outs)))
+    # first-seen numbering: along the sorted stream, new intermediate wires appear in increasing order
+    mid = ng[:, 1:4].reshape(-1)
+    is_mid = (mid >= len(ins)) & (mid < wc - len(outs))
+    first_pos = np.full(wc, -1, dtype=np.int64)
+    idx = np.nonzero(is_mid)[0][::-1]
+    first_pos[mid[idx]] = idx
+    fp = first_pos[len(ins):wc - len(outs)]
+    assert (np.diff(fp) > 0).all()
+    # idempotence: the sorted circuit is in dependency order -> identity order
+    order2, _, ng2, wc2 = ctx.build_circuit(sg, nb, ins, outs)
+    assert np.array_equal(order2, np.arange(G, dtype=np.uint32)) and wc2 == wc and np.array_equal(ng2, ng)
