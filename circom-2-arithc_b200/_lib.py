@@ -76,6 +76,7 @@ _SIGS = {
     "c2a_topo_sort_deps": (i32, [vp, u64, vp, vp, vp, u64p]),
     "c2a_build_circuit": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_build_circuit_device": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
+    "c2a_rebase_wires_device": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, u32, u32]),
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),
@@ -95,6 +96,7 @@ _SIGS = {
     "c2a_num_signals": (u64, [vp]),
     "c2a_get_gates": (i32, [vp, vp]),
     "c2a_signal_node": (i32, [vp, u32, u32p]),
+    "c2a_signal_nodes": (i32, [vp, vp, u64, vp]),
     "c2a_signal_name": (i64, [vp, u32, C.c_char_p, u64]),
     "c2a_set_signal_name": (i32, [vp, u32, cp]),
     "c2a_get_signals_by_prefix": (u64, [vp, cp, vp, u64]),

@@ -334,6 +334,12 @@ class Compiler:
         lib.c2a_signal_node(self._c, id, C.byref(n))
         return n.value
 
+    def signal_nodes(self, ids) -> np.ndarray:
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        out = np.empty(ids.shape[0], dtype=np.uint32)
+        lib.c2a_signal_nodes(self._c, _ptr(ids), ids.shape[0], _ptr(out))
+        return out
+
     def gate_array(self) -> np.ndarray:
         """(G,4) u32 {op, lh_in, rh_in, out} in NODE ids — `Compiler.gates` of the reference."""
         G = int(lib.c2a_num_gates(self._c))

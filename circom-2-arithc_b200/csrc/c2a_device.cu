@@ -429,6 +429,17 @@ __global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gat
   }
 }
 
+// Multi-GPU: local -> global wire ids / gate indices for one independently sorted component subtree.
+__global__ void __launch_bounds__(kBlock) k_rebase(uint4* __restrict__ new_gates, uint32_t* __restrict__ order, uint32_t G, uint32_t n_in,
+                                                   uint32_t n_mid, uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base) {
+  auto fix = [&](uint32_t w) { return w < n_in ? w + off_in : (w < n_in + n_mid ? w + off_mid : w + off_out); };
+  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
+    uint4 g = new_gates[k];
+    new_gates[k] = make_uint4(g.x, fix(g.y), fix(g.z), fix(g.w));
+    if (order) order[k] += gate_base;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side plumbing
 // ---------------------------------------------------------------------------------------------------
@@ -584,9 +595,13 @@ int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_
   cudaStream_t st = h->stream;
   uint32_t* sc = s.scalars;
   // ---- K5a
-  phase_begin(h, "relax");
+  phase_begin(h, "init");
   LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, n), kBlock, s.r, n);
   cudaMemsetAsync(s.inq, 0, 4 * ((size_t)(n + 31) / 32 + 1), st);
+  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
+  cudaMemsetAsync(s.state, 0, n, st);
+  phase_end(h);
+  phase_begin(h, "k_relax");
   LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_Q0N);
   uint32_t *qin = s.q0, *qout = s.q1;
   int nin = S_Q0N, nout = S_Q1N;
@@ -602,19 +617,21 @@ int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_
   }
   phase_end(h);
   // ---- K5b
-  phase_begin(h, "sizes_scan");
-  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
+  phase_begin(h, "k_sizes");
   LAUNCH(h, k_sizes, grid_for(h, (const void*)k_sizes, kBlock, n), kBlock, s.r, n, s.size_off);
+  phase_end(h);
   uint32_t tiles = scan_tiles(n, kScanItems);
   cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
   cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
+  phase_begin(h, "k_scan_u32");
   LAUNCH(h, k_scan_u32, tiles, kBlock, s.size_off, n, s.tile_state, sc + S_TICKET);
   phase_end(h);
   // ---- K5c
-  phase_begin(h, "trees");
-  cudaMemsetAsync(s.state, 0, n, st);
+  phase_begin(h, "k_roots");
   LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, (host_flags & F_SELF) ? 1u : 0u, d_order, s.heavy, sc);
+  phase_end(h);
   // heavy count is only known on the device: launch a grid sized for the worst case the hardware can hold
+  phase_begin(h, "k_tree_dfs");
   LAUNCH(h, k_tree_dfs, h->num_sms * 8, 128, s.heavy, d_dep, s.r, s.size_off, s.state, d_order, sc);
   phase_end(h);
   if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 40, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "sort status copy")) return C2A_ERR_CUDA;
@@ -710,11 +727,14 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     cudaMemcpyAsync(pair_ranks, stage + n_pairs, 4 * n_pairs, cudaMemcpyHostToDevice, st);
   }
 
-  phase_begin(h, "producer");
+  phase_begin(h, "init");
   cudaMemsetAsync(prod1, 0, 4 * (size_t)p.node_bound, st);
+  if (p.want_wire) cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
+  phase_end(h);
+  phase_begin(h, "k_producer");
   if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
   phase_end(h);
-  phase_begin(h, "deps");
+  phase_begin(h, "k_deps");
   if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, prod1, dep, sc);
   phase_end(h);
   if (!cuda_ok(h, cudaMemcpyAsync(hp, sc, 4, cudaMemcpyDeviceToHost, st), "flags copy")) return C2A_ERR_CUDA;
@@ -728,7 +748,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   if (stt != C2A_OK) return stt;
   if (identity_out) *identity_out = identity;
   if (identity && d_order_user && G) {
-    phase_begin(h, "iota");
+    phase_begin(h, "k_iota");
     LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, G), kBlock, d_order_user, G);
     phase_end(h);
   }
@@ -736,23 +756,22 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
 
   const uint32_t* ord = identity ? nullptr : d_order;
   uint32_t ni = (uint32_t)in_pairs.nodes.size(), no = (uint32_t)out_pairs.nodes.size();
-  phase_begin(h, "wire_first");
-  cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
   if (ni) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, ni), kBlock, pair_nodes, pair_ranks, ni, 0u, (const uint32_t*)nullptr, 0u, 0u, d_wire);
   if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, 0u, (const uint32_t*)nullptr, kOutPending, 1u, d_wire);
+  phase_begin(h, "k_wire_first");
   if (G) LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, G), kBlock, d_gates, ord, G, d_wire);
   phase_end(h);
-  phase_begin(h, "wire_scan");
   if (G) {
     uint32_t tiles = scan_tiles(G, kWireItems);
     cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
     cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
+    phase_begin(h, "k_wire_scan");
     LAUNCH(h, k_wire_scan, tiles, kBlock, d_gates, ord, G, p.n_in, d_wire, s.tile_state, sc);
+    phase_end(h);
   }
   if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, p.n_in, (const uint32_t*)(sc + S_NMID), 0u, 0u, d_wire);
-  phase_end(h);
   if (d_new_gates && G) {
-    phase_begin(h, "gather");
+    phase_begin(h, "k_gather");
     LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, G), kBlock, d_gates, ord, G, d_wire, d_new_gates);
     phase_end(h);
   }
@@ -856,6 +875,16 @@ int c2a_build_circuit_device(c2a_handle* h, const c2a_gate* d_gates, uint64_t G,
   return st;
 }
 
+int c2a_rebase_wires_device(c2a_handle* h, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, uint32_t n_in, uint32_t n_mid,
+                            uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base) {
+  int st = check_sizes(h, G, 1);
+  if (st) return st;
+  if (!d_new_gates) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  if (G) LAUNCH(h, k_rebase, grid_for(h, (const void*)k_rebase, kBlock, G), kBlock, (uint4*)d_new_gates, d_order, (uint32_t)G, n_in, n_mid, off_in, off_mid, off_out, gate_base);
+  if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "rebase")) return C2A_ERR_CUDA;
+  return C2A_OK;
+}
+
 int c2a_build_circuit(c2a_handle* h, const c2a_gate* gates, uint64_t G, uint32_t node_bound, const uint32_t* input_nodes, uint32_t n_in,
                       const uint32_t* output_nodes, uint32_t n_out, uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates,
                       uint32_t* wire_count, uint64_t* err_index) {
@@ -941,7 +970,7 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
   cudaMemcpyAsync(s.scalars, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, stq);
   cudaMemcpyAsync(d_off, dep_off, 8 * (n + 1), cudaMemcpyHostToDevice, stq);
   if (nnz) cudaMemcpyAsync(d_idx, dep_idx, 4 * nnz, cudaMemcpyHostToDevice, stq);
-  phase_begin(h, "deps");
+  phase_begin(h, "k_deps");
   LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, (uint32_t)n, dep, s.scalars);
   phase_end(h);
   cudaMemcpyAsync(hp, s.scalars, 4, cudaMemcpyDeviceToHost, stq);

@@ -287,6 +287,14 @@ int c2a_signal_node(c2a_compiler* c, uint32_t sid, uint32_t* node) {
   return C2A_OK;
 }
 
+int c2a_signal_nodes(c2a_compiler* c, const uint32_t* sids, uint64_t n, uint32_t* nodes) {
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t e = c->elem_of(sids[i]);
+    nodes[i] = e == kNoElem ? 0 : c->node_id[c->find(e)];
+  }
+  return C2A_OK;
+}
+
 static void live_roots(c2a_compiler* c, std::vector<std::pair<uint32_t, uint32_t>>* out) {  // (node id, root)
   for (uint32_t e = 0; e < c->parent.size(); ++e)
     if (c->parent[e] == e && c->node_id[e] != 0) out->push_back({c->node_id[e], e});

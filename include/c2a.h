@@ -120,6 +120,12 @@ int c2a_build_circuit_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, u
                              uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates,
                              uint32_t* wire_count, uint64_t* err_index);
 
+/* Multi-GPU reconciliation: a rank that sorted one independent component subtree rebases its
+ * LOCAL wire ids (inputs [0,n_in), intermediates [n_in,n_in+n_mid), outputs after) and gate indices to the global
+ * numbering once the per-rank counts are known (one NCCL all-gather by the caller).  d_order may be NULL. */
+int c2a_rebase_wires_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, uint32_t n_in, uint32_t n_mid,
+                            uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base);
+
 /* Level-synchronous Kahn frontier over the same dependency relation (not the reference order; used for the
  * layer-wise sweeps and the evaluator).  level_order[G] is level-major; level_off[*n_levels+1] delimits levels
  * (caller provides capacity level_cap+1; more levels than level_cap -> C2A_ERR_INVALID_ARGUMENT).
@@ -161,6 +167,7 @@ uint32_t c2a_node_count(const c2a_compiler*);        /* the reference's node_cou
 uint64_t c2a_num_signals(const c2a_compiler*);
 int c2a_get_gates(c2a_compiler*, c2a_gate* out /* num_gates */);
 int c2a_signal_node(c2a_compiler*, uint32_t signal_id, uint32_t* node_id); /* 0 when the signal is unknown */
+int c2a_signal_nodes(c2a_compiler*, const uint32_t* signal_ids, uint64_t n, uint32_t* node_ids); /* bulk form */
 /* name of a declared signal ("random_<id>" for unnamed temporaries, "const_signal_<v>" for bulk constants);
  * returns the length, or -1 when the signal is unknown; copies at most cap-1 bytes + NUL into buf */
 int64_t c2a_signal_name(c2a_compiler*, uint32_t signal_id, char* buf, uint64_t cap);
