@@ -359,24 +359,44 @@ __global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ h
 // ---------------------------------------------------------------------------------------------------
 // K6: wire numbering (compiler.rs:388-449)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_set_pairs(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ ranks, uint32_t n,
-                                                      uint32_t add, const uint32_t* __restrict__ add_dev, uint32_t fixed,
-                                                      uint32_t use_fixed, uint32_t* __restrict__ wire) {
-  uint32_t a = add + (add_dev ? *add_dev : 0u);
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) wire[nodes[i]] = use_fixed ? fixed : a + ranks[i];
+// I/O node lists (compiler.rs:392-395, 446-449): `insert(node, next_wire_id++)` in list order, a node listed twice
+// keeps the LAST id.  On the device: zero the listed words, then RED.MAX(base + i).
+__global__ void __launch_bounds__(kBlock) k_io_set(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t node_bound, uint32_t value,
+                                                   uint32_t* __restrict__ wire, uint32_t* __restrict__ scalars) {
+  bool bad = false;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t nd = nodes[i];
+    if (nd >= node_bound) bad = true;
+    else wire[nd] = value;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(scalars + S_FLAGS, (uint32_t)F_BAD);
+}
+__global__ void __launch_bounds__(kBlock) k_io_max(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t node_bound, uint32_t base,
+                                                   const uint32_t* __restrict__ base_dev, uint32_t* __restrict__ wire) {
+  uint32_t b = base + (base_dev ? *base_dev : 0u);
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t nd = nodes[i];
+    if (nd < node_bound) atomicMax(wire + nd, b + i);
+  }
 }
 
 // pass 1: earliest appearance p = 3*pos+slot of every not-yet-numbered node, over the SORTED gate stream.
-// One unconditional RED.MIN per slot: inputs / pending outputs hold smaller words and are left untouched.
+// RED.MIN per slot: inputs / pending outputs hold smaller words and are left untouched.
+__device__ __forceinline__ void first_min(uint32_t* __restrict__ wire, uint32_t node, uint32_t p) {
+  // Read before the RED: words only ever decrease, so a (possibly stale) value <= p proves the RED is a no-op.
+  // This removes the serialisation on hot nodes (a shared input such as a key feeds millions of gates).
+  if (wire[node] > p) atomicMin(wire + node, p);
+}
+
 __global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
                                                        uint32_t* __restrict__ wire) {
   for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
     uint32_t g = order ? order[k] : k;
     uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
     uint32_t p = kFirstTag | (3u * k);
-    atomicMin(wire + gt.y, p);
-    if (gt.z != gt.y) atomicMin(wire + gt.z, p + 1);
-    if (gt.w != gt.y && gt.w != gt.z) atomicMin(wire + gt.w, p + 2);
+    first_min(wire, gt.y, p);
+    if (gt.z != gt.y) first_min(wire, gt.z, p + 1);
+    if (gt.w != gt.y && gt.w != gt.z) first_min(wire, gt.w, p + 2);
   }
 }
 
@@ -605,15 +625,19 @@ int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_
   LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_Q0N);
   uint32_t *qin = s.q0, *qout = s.q1;
   int nin = S_Q0N, nout = S_Q1N;
-  for (int round = 0;; ++round) {
+  // Rounds are launched in batches of 4 with a fixed grid (the queue length lives on the device); the host looks
+  // at the queue length once per batch.
+  const int round_grid = h->num_sms * 4;
+  while (true) {
+    for (int b = 0; b < 4; ++b) {
+      cudaMemsetAsync(sc + nout, 0, 4, st);
+      LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
+      std::swap(qin, qout);
+      std::swap(nin, nout);
+    }
     if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 32, sc + nin, 4, cudaMemcpyDeviceToHost, st), "relax count copy")) return C2A_ERR_CUDA;
     if (!cuda_ok(h, cudaStreamSynchronize(st), "relax sync")) return C2A_ERR_CUDA;
-    uint32_t cnt = h->h_pinned[32];
-    if (cnt == 0) break;
-    cudaMemsetAsync(sc + nout, 0, 4, st);
-    LAUNCH(h, k_relax_round, grid_for(h, (const void*)k_relax_round, kBlock, cnt), kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
-    std::swap(qin, qout);
-    std::swap(nin, nout);
+    if (h->h_pinned[32] == 0) break;
   }
   phase_end(h);
   // ---- K5b
@@ -648,33 +672,19 @@ int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_
 // ---------------------------------------------------------------------------------------------------
 // build_circuit on device-resident gates
 // ---------------------------------------------------------------------------------------------------
-struct IoPairs {
-  std::vector<uint32_t> nodes, ranks;
-};
-// last-wins de-duplication of an ordered node list (HashMap::insert overwrite, compiler.rs:392-395, 446-449)
-static void dedupe_last(const uint32_t* list, uint32_t n, IoPairs* out) {
-  std::unordered_map<uint32_t, uint32_t> m;
-  m.reserve(n * 2 + 1);
-  for (uint32_t i = 0; i < n; ++i) m[list[i]] = i;
-  out->nodes.reserve(m.size());
-  out->ranks.reserve(m.size());
-  for (uint32_t i = 0; i < n; ++i)
-    if (m[list[i]] == i) { out->nodes.push_back(list[i]); out->ranks.push_back(i); }
-}
-
 struct BuildPlan {
   uint64_t G;
   uint32_t node_bound, n_in, n_out;
   bool want_wire;  // wire numbering + gather wanted (build_circuit) or order only (topo_sort)
 };
 
-static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {
+static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pairs = n_in + n_out
   size_t b = 0;
   b += align256(4 * (size_t)p.node_bound);  // prod1
   b += align256(8 * p.G);                   // dep
   b += sort_scratch_bytes(p.G);
   b += align256(4 * p.G);                   // order (internal)
-  b += 2 * align256(4 * n_pairs + 4);       // pair nodes / ranks
+  b += align256(4 * n_pairs + 4);           // I/O node lists
   return b;
 }
 
@@ -684,20 +694,10 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
                       uint32_t* wire_count, uint64_t* err_index, bool* identity_out) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
-  // host-side metadata checks
-  IoPairs in_pairs, out_pairs;
-  if (p.want_wire) {
-    for (uint32_t i = 0; i < p.n_in; ++i)
-      if (in_nodes_host[i] >= p.node_bound) return fail(h, C2A_ERR_INVALID_ARGUMENT, "input node %u >= node_bound %u", in_nodes_host[i], p.node_bound);
-    for (uint32_t i = 0; i < p.n_out; ++i)
-      if (out_nodes_host[i] >= p.node_bound) return fail(h, C2A_ERR_INVALID_ARGUMENT, "output node %u >= node_bound %u", out_nodes_host[i], p.node_bound);
-    dedupe_last(in_nodes_host, p.n_in, &in_pairs);
-    dedupe_last(out_nodes_host, p.n_out, &out_pairs);
-  }
-  size_t n_pairs = in_pairs.nodes.size() + out_pairs.nodes.size();
-  if ((4 * n_pairs * 2 + 1024) > h->h_pinned_bytes) {
+  size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
+  if ((4 * n_pairs + 2048) > h->h_pinned_bytes) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    h->h_pinned_bytes = 4 * n_pairs * 2 + 4096;
+    h->h_pinned_bytes = 4 * n_pairs + 8192;
     if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
   }
 
@@ -706,9 +706,8 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   SortScratch s;
   bool ok = sort_scratch_carve(h, p.G, &s);
   uint32_t* order_int = (uint32_t*)slab_alloc(h, 4 * p.G);
-  uint32_t* pair_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
-  uint32_t* pair_ranks = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
-  if (!ok || !prod1 || !dep || !order_int || !pair_nodes || !pair_ranks) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  uint32_t* io_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  if (!ok || !prod1 || !dep || !order_int || !io_nodes) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   uint32_t* sc = s.scalars;
 
   // scalars: zero, err = ~0
@@ -718,13 +717,9 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   cudaMemcpyAsync(sc, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
   if (n_pairs) {
     uint32_t* stage = hp + 256;
-    size_t ni = in_pairs.nodes.size(), no = out_pairs.nodes.size();
-    memcpy(stage, in_pairs.nodes.data(), 4 * ni);
-    memcpy(stage + ni, out_pairs.nodes.data(), 4 * no);
-    memcpy(stage + n_pairs, in_pairs.ranks.data(), 4 * ni);
-    memcpy(stage + n_pairs + ni, out_pairs.ranks.data(), 4 * no);
-    cudaMemcpyAsync(pair_nodes, stage, 4 * n_pairs, cudaMemcpyHostToDevice, st);
-    cudaMemcpyAsync(pair_ranks, stage + n_pairs, 4 * n_pairs, cudaMemcpyHostToDevice, st);
+    if (p.n_in) memcpy(stage, in_nodes_host, 4 * (size_t)p.n_in);
+    if (p.n_out) memcpy(stage + p.n_in, out_nodes_host, 4 * (size_t)p.n_out);
+    cudaMemcpyAsync(io_nodes, stage, 4 * n_pairs, cudaMemcpyHostToDevice, st);
   }
 
   phase_begin(h, "init");
@@ -755,9 +750,14 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   if (!p.want_wire) return C2A_OK;
 
   const uint32_t* ord = identity ? nullptr : d_order;
-  uint32_t ni = (uint32_t)in_pairs.nodes.size(), no = (uint32_t)out_pairs.nodes.size();
-  if (ni) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, ni), kBlock, pair_nodes, pair_ranks, ni, 0u, (const uint32_t*)nullptr, 0u, 0u, d_wire);
-  if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, 0u, (const uint32_t*)nullptr, kOutPending, 1u, d_wire);
+  const uint32_t ni = p.n_in, no = p.n_out;
+  const uint32_t* d_in = io_nodes;
+  const uint32_t* d_out = io_nodes + ni;
+  if (ni) {
+    LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, d_wire, sc);
+    LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
+  }
+  if (no) LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, kOutPending, d_wire, sc);
   phase_begin(h, "k_wire_first");
   if (G) LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, G), kBlock, d_gates, ord, G, d_wire);
   phase_end(h);
@@ -769,16 +769,20 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     LAUNCH(h, k_wire_scan, tiles, kBlock, d_gates, ord, G, p.n_in, d_wire, s.tile_state, sc);
     phase_end(h);
   }
-  if (no) LAUNCH(h, k_set_pairs, grid_for(h, (const void*)k_set_pairs, kBlock, no), kBlock, pair_nodes + ni, pair_ranks + ni, no, p.n_in, (const uint32_t*)(sc + S_NMID), 0u, 0u, d_wire);
+  if (no) {
+    LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, 0u, d_wire, sc);
+    LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, no), kBlock, d_out, no, p.node_bound, p.n_in, (const uint32_t*)(sc + S_NMID), d_wire);
+  }
   if (d_new_gates && G) {
     phase_begin(h, "k_gather");
     LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, G), kBlock, d_gates, ord, G, d_wire, d_new_gates);
     phase_end(h);
   }
-  if (!cuda_ok(h, cudaMemcpyAsync(hp + 8, sc + S_NMID, 4, cudaMemcpyDeviceToHost, st), "n_mid copy")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaMemcpyAsync(hp + 64, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "status copy")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaStreamSynchronize(st), "final sync")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaGetLastError(), "kernel")) return C2A_ERR_CUDA;
-  if (wire_count) *wire_count = p.n_in + hp[8] + p.n_out;
+  if (hp[64 + S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output node id is >= node_bound (%u)", p.node_bound);
+  if (wire_count) *wire_count = p.n_in + hp[64 + S_NMID] + p.n_out;
   return C2A_OK;
 }
 
