@@ -50,6 +50,11 @@ class CircuitError(Exception):
         super().__init__(text)
 
 
+class EmitInfo(C.Structure):  # c2a_emit_info
+    _fields_ = [("n_events", u64), ("n_signals", u64), ("n_gates", u64), ("n_connections", u64), ("n_effective", u64),
+                ("node_count", u32), ("signal_bound", u32), ("path", u32), ("rounds", u32), ("decline_flags", u32), ("reserved", u32)]
+
+
 load_error = None
 try:
     lib = C.CDLL(LIB_PATH)
@@ -80,6 +85,11 @@ _SIGS = {
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),
+    "c2a_emit_events_device": (i32, [vp, vp, u64, vp, u64p]),
+    "c2a_emit_events_resident": (i32, [vp, vp, u64, vp, u64p]),
+    "c2a_emitted_fetch": (i32, [vp, vp, vp]),
+    "c2a_emitted_build_circuit_device": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
+    "c2a_emitted_build_circuit": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_compiler_new": (vp, []),
     "c2a_compiler_free": (None, [vp]),
     "c2a_compiler_last_error": (cp, [vp]),

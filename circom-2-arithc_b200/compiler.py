@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from ._lib import lib, C2AError, CircuitError, Status
+from ._lib import lib, C2AError, CircuitError, Status, EmitInfo
 
 NONE = 0xFFFFFFFF
 EVENT_DTYPE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
@@ -185,6 +185,53 @@ class DeviceContext:
             raise CircuitError(st, f"detected at i={err.value}")
         _raise(st, self.last_error())
         return cm, cval, dm
+
+
+    # ---- device emitter: the event stream is replayed on the GPU and the result stays resident ----
+    def emit_events(self, events: np.ndarray) -> dict:
+        """c2a_emit_events_device: add_signal / add_gate / add_connection (src/compiler.rs:139-278) for a whole event
+        stream on the GPU.  Returns the c2a_emit_info fields; raises CircuitError exactly where the reference errors."""
+        ev = np.ascontiguousarray(events)
+        assert ev.dtype == EVENT_DTYPE or (ev.dtype == np.uint32 and ev.ndim == 2 and ev.shape[1] == 4)
+        info = EmitInfo()
+        bad = C.c_uint64(0)
+        st = lib.c2a_emit_events_device(self._h, _ptr(ev), ev.shape[0], C.byref(info), C.byref(bad))
+        if st != 0:
+            e = None
+            try:
+                _raise(st, f"event {bad.value}: {self.last_error()}")
+            except (CircuitError, C2AError) as ex:
+                ex.err_event = bad.value
+                e = ex
+            raise e
+        self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
+        return dict(self._emit_info)
+
+    def emitted_fetch(self, want_gates=True, want_nodes=True):
+        """-> (gates (G,4) u32 node ids in emission order, node_of_signal[signal_bound])"""
+        info = self._emit_info
+        g = np.empty((info["n_gates"], 4), dtype=np.uint32) if want_gates else None
+        nos = np.empty(info["signal_bound"], dtype=np.uint32) if want_nodes else None
+        _raise(lib.c2a_emitted_fetch(self._h, _ptr(g), _ptr(nos)), self.last_error())
+        return g, nos
+
+    def emitted_build_circuit(self, input_signals, output_signals, want_order=True, want_wires=True, want_gates=True):
+        """build_circuit on the resident emitted circuit -> (order, wire_of_node[node_count+1], new_gates, wire_count)"""
+        info = self._emit_info
+        G, nb = info["n_gates"], info["node_count"] + 1
+        ins = np.ascontiguousarray(input_signals, dtype=np.uint32)
+        outs = np.ascontiguousarray(output_signals, dtype=np.uint32)
+        order = np.empty(G, dtype=np.uint32) if want_order else None
+        wire = np.empty(nb, dtype=np.uint32) if want_wires else None
+        ng = np.empty((G, 4), dtype=np.uint32) if want_gates else None
+        wc = C.c_uint32(0)
+        err = C.c_uint64(0)
+        st = lib.c2a_emitted_build_circuit(self._h, _ptr(ins), ins.shape[0], _ptr(outs), outs.shape[0], _ptr(order), _ptr(wire), _ptr(ng),
+                                           C.byref(wc), C.byref(err))
+        if st == Status.CYCLIC_DEPENDENCY:
+            raise CircuitError(st, f"detected at i={err.value}")
+        _raise(st, self.last_error())
+        return order, wire, ng, wc.value
 
 
 def _as_gates(g) -> np.ndarray:

@@ -54,6 +54,7 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
 
 constexpr int kBlock = 256;
 constexpr uint32_t kNone = C2A_NONE;
+static void emit_drop_host(c2a_handle* h);  // c2a_emit.cuh
 // wire[] encoding while numbering is in flight (compiler.rs:388-449):
 //   < kOutPending        : final wire id
 //   == kOutPending       : output node, numbered after all intermediates (:431-434, :446-449)
@@ -481,20 +482,28 @@ bool cuda_ok(c2a_handle* h, cudaError_t e, const char* what) {
   return false;
 }
 
-void slab_reset(c2a_handle* h) { h->slab_used = 0; }
+void slab_reset(c2a_handle* h) {
+  h->slab_used = 0;
+  h->slab_keep = 0;
+  h->emitted.valid = false;
+}
+void slab_reset_keep(c2a_handle* h) { h->slab_used = h->slab_keep; }
 
 bool slab_reserve(c2a_handle* h, size_t bytes) {
   if (bytes <= h->slab_bytes) return true;
-  if (h->slab) {
-    cudaStreamSynchronize(h->stream);
-    cudaFree(h->slab);
-    h->slab = nullptr;
-    h->slab_bytes = 0;
-  }
+  char* old = h->slab;
   size_t want = bytes + bytes / 8 + (1u << 20);
-  cudaError_t e = cudaMalloc(&h->slab, want);
+  char* fresh = nullptr;
+  cudaError_t e = cudaMalloc(&fresh, want);
   if (e != cudaSuccess) {
-    e = cudaMalloc(&h->slab, bytes);
+    cudaGetLastError();
+    if (old && h->slab_keep == 0) {  // nothing to preserve: release first, then retry at the exact size
+      cudaStreamSynchronize(h->stream);
+      cudaFree(old);
+      old = h->slab = nullptr;
+      h->slab_bytes = 0;
+    }
+    e = cudaMalloc(&fresh, bytes);
     want = bytes;
   }
   if (e != cudaSuccess) {
@@ -502,6 +511,12 @@ bool slab_reserve(c2a_handle* h, size_t bytes) {
     cudaGetLastError();
     return false;
   }
+  if (old) {
+    if (h->slab_keep) cudaMemcpyAsync(fresh, old, h->slab_keep, cudaMemcpyDeviceToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    cudaFree(old);
+  }
+  h->slab = fresh;
   h->slab_bytes = want;
   return true;
 }
@@ -689,13 +704,15 @@ static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pai
 }
 
 // Core: everything after the gates are on the device.  d_wire may be null (internal), d_order may be null.
+// I/O node lists: either host arrays (staged through pinned memory) or, when d_io_ready != null, a device array holding
+// the n_in input nodes followed by the n_out output nodes.
 static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, const uint32_t* in_nodes_host,
                       const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
-                      uint32_t* wire_count, uint64_t* err_index, bool* identity_out) {
+                      uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
   size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
-  if ((4 * n_pairs + 2048) > h->h_pinned_bytes) {
+  if (!d_io_ready && (4 * n_pairs + 2048) > h->h_pinned_bytes) {
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
     h->h_pinned_bytes = 4 * n_pairs + 8192;
     if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
@@ -706,7 +723,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   SortScratch s;
   bool ok = sort_scratch_carve(h, p.G, &s);
   uint32_t* order_int = (uint32_t*)slab_alloc(h, 4 * p.G);
-  uint32_t* io_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  uint32_t* io_nodes = d_io_ready ? const_cast<uint32_t*>(d_io_ready) : (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
   if (!ok || !prod1 || !dep || !order_int || !io_nodes) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   uint32_t* sc = s.scalars;
 
@@ -715,7 +732,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
   hp[S_ERR_LO] = hp[S_ERR_HI] = 0xFFFFFFFFu;
   cudaMemcpyAsync(sc, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
-  if (n_pairs) {
+  if (n_pairs && !d_io_ready) {
     uint32_t* stage = hp + 256;
     if (p.n_in) memcpy(stage, in_nodes_host, 4 * (size_t)p.n_in);
     if (p.n_out) memcpy(stage + p.n_in, out_nodes_host, 4 * (size_t)p.n_out);
@@ -839,6 +856,8 @@ void c2a_destroy(c2a_handle* h) {
   cudaStreamSynchronize(h->stream);
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->slab) cudaFree(h->slab);
+  if (h->ev_buf) cudaFree(h->ev_buf);
+  emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   cudaStreamDestroy(h->stream);
   delete h;
@@ -995,3 +1014,4 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
 }  // extern "C"
 
 #include "c2a_kahn.cuh"
+#include "c2a_emit.cuh"

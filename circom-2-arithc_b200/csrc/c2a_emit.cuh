@@ -1,0 +1,724 @@
+// c2a_emit.cuh — device emitter: the reference's Compiler::{add_signal, add_gate, add_connection}
+// (src/compiler.rs:139-278) replayed over a whole event stream ON THE GPU, producing the same node ids and the
+// same node-id gate vector as the sequential reference, then feeding build_circuit without a host round trip.
+// Included by c2a_device.cu (single translation unit).
+//
+// Why this is parallel at all.  The reference processes connections in event order; a connection is *effective*
+// (consumes a node id, compiler.rs:257) iff its two signals are not already in one node (:235-237).  Processing
+// edges in time order and keeping those that join two classes is Kruskal's algorithm with weight = event index,
+// so the effective connections are exactly the edges of the (unique, weights are distinct) minimum spanning
+// forest of the connection graph -> Boruvka rounds on the device.  Node ids then follow from two prefix counts:
+//   * add_signal at event t:            id = #signals declared up to t  + #effective connections before t   (:157)
+//   * effective connection at event t:  id = #signals declared before t + #effective connections up to t    (:257)
+//   * a class ends with the id of its LAST event, i.e. the largest id among its members / MSF edges.
+// gates hold node ids that the reference keeps current on every merge (:260-270): final value = final class id.
+//
+// What the device path does not decide itself: streams that make the reference return an error or take the
+// "signal in no node => node 0" path (:183).  They are detected (flags below) and replayed by the exact host
+// emitter (c2a_host.cpp), which yields the reference's error code / event index.  Detection is exact for
+// duplicates, unknown references and const+const merges; out+out is flagged conservatively (a final class
+// holding two distinct gate-output signals), which is exact for walker-generated streams where every gate
+// writes a fresh temporary (src/process.rs:470-475).
+//
+//   E0 k_ev_count      per-1024-event tile: #gates, #connections; 1+max signal id; kind/op validation
+//      k_ev_tile_scan  exclusive scan of the tile counts (single CTA)
+//   E1 k_ev_scatter    ballot/popc ranks inside a tile -> gate index / connection index / signal index of every
+//                      event; scatters into SoA arrays (sig_t, sig_meta | egates, gate_t | conn, conn_t, conn_sb)
+//   E2 k_ev_check_*    every reference precedes its use (else node-0 semantics), marks gate-output signals
+//   M  k_msf_pick / k_msf_hook   Boruvka: per class the minimum-time outgoing connection (tagged RED.MIN),
+//                      hook, path compression inside find; edge list shrinks every round
+//   N  k_scan_u32(eff), k_ev_nid_init, k_ev_nid_edges, k_ev_finalize, k_ev_gates
+#pragma once
+
+struct c2a_compiler;
+
+namespace c2a {
+
+constexpr int kEvTile = 1024;  // events per CTA pass: 8 warps x 4 rows x 32 lanes
+enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_COUNT = 16 };
+enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128 };
+
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// ---- E0 ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_cnt,
+                                                     uint32_t* __restrict__ es) {
+  __shared__ uint32_t s_g[8], s_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t tot_g = 0, tot_c = 0, smax = 0, f = 0;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    uint64_t base = (uint64_t)tile * kEvTile + warp * 128;
+    uint32_t g = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t i = base + j * 32 + lane;
+      if (i < n) {
+        uint4 e = ldg_stream(ev + i);
+        uint32_t kind = e.x & 0xFF;
+        if (kind <= C2A_EV_SIGNAL_CONST) {
+          if (e.y == 0xFFFFFFFFu) f |= EF_SPARSE; else smax = max(smax, e.y + 1);
+        } else if (kind == C2A_EV_GATE) {
+          ++g;
+          if ((e.x >> 8) >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP;
+        } else if (kind == C2A_EV_CONNECT) ++c;
+        else f |= EF_BAD_KIND;
+      }
+    }
+    g = warp_sum(g);
+    c = warp_sum(c);
+    if (lane == 0) { s_g[warp] = g; s_c[warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tg = 0, tc = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { tg += s_g[w]; tc += s_c[w]; }
+      tile_cnt[tile] = tg | (tc << 16);
+      tot_g += tg;
+      tot_c += tc;
+    }
+    __syncthreads();
+  }
+  smax = warp_max(smax);
+  f = warp_or(f);
+  if (lane == 0) {
+    if (smax) atomicMax(es + ES_SBOUND, smax);
+    if (f) atomicOr(es + ES_FLAGS, f);
+  }
+  if (threadIdx.x == 0) {
+    if (tot_g) atomicAdd(es + ES_NGATE, tot_g);
+    if (tot_c) atomicAdd(es + ES_NCONN, tot_c);
+  }
+}
+
+// exclusive scan of the per-tile (gates, connections) counts; single CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_ev_tile_scan(const uint32_t* __restrict__ tile_cnt, uint32_t tiles, uint2* __restrict__ tile_base) {
+  __shared__ uint32_t s_g[32], s_c[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t per = (tiles + 1023) / 1024;
+  uint32_t lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
+  uint32_t g = 0, c = 0;
+  for (uint32_t i = lo; i < hi; ++i) { uint32_t v = tile_cnt[i]; g += v & 0xFFFFu; c += v >> 16; }
+  uint32_t ig = warp_incl_scan(g, lane), ic = warp_incl_scan(c, lane);
+  if (lane == 31) { s_g[warp] = ig; s_c[warp] = ic; }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t wg = s_g[lane], wc = s_c[lane];
+    uint32_t sg = warp_incl_scan(wg, lane), sc = warp_incl_scan(wc, lane);
+    s_g[lane] = sg - wg;
+    s_c[lane] = sc - wc;
+  }
+  __syncthreads();
+  uint32_t rg = s_g[warp] + ig - g, rc = s_c[warp] + ic - c;
+  for (uint32_t i = lo; i < hi; ++i) {
+    uint32_t v = tile_cnt[i];
+    tile_base[i] = make_uint2(rg, rc);
+    rg += v & 0xFFFFu;
+    rc += v >> 16;
+  }
+}
+
+// ---- E1 ---------------------------------------------------------------------------------------------------
+// sig_t[sid]    event index of the declaration (kNone = never declared)
+// sig_meta[sid] {signal index (declaration rank) | is_const << 31, #connections before the declaration}
+// egates[g]     {op, lhs signal, rhs signal, out signal};  gate_t[g] event index
+// conn[c]       {a, b};  conn_t[c] event index;  conn_sb[c] #signals declared before the connection
+__global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, const uint2* __restrict__ tile_base,
+                                                       uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta, uint4* __restrict__ egates,
+                                                       uint32_t* __restrict__ gate_t, uint2* __restrict__ conn, uint32_t* __restrict__ conn_t,
+                                                       uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
+  __shared__ uint32_t s_g[8], s_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t f = 0;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    uint64_t base = (uint64_t)tile * kEvTile + warp * 128;
+    uint4 e[4];
+    uint32_t gm[4], cm[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t i = base + j * 32 + lane;
+      e[j] = make_uint4(0xFFu, 0, 0, 0);
+      if (i < n) e[j] = ldg_stream(ev + i);
+    }
+    uint32_t wg = 0, wc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t kind = e[j].x & 0xFF;
+      gm[j] = __ballot_sync(0xFFFFFFFFu, kind == C2A_EV_GATE);
+      cm[j] = __ballot_sync(0xFFFFFFFFu, kind == C2A_EV_CONNECT);
+      wg += __popc(gm[j]);
+      wc += __popc(cm[j]);
+    }
+    if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; }
+    __syncthreads();
+    uint2 tb = tile_base[tile];
+    uint32_t gi = tb.x, ci = tb.y;
+    for (int w = 0; w < warp; ++w) { gi += s_g[w]; ci += s_c[w]; }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t i = base + j * 32 + lane;
+      uint32_t my_g = gi + __popc(gm[j] & lt), my_c = ci + __popc(cm[j] & lt);
+      gi += __popc(gm[j]);
+      ci += __popc(cm[j]);
+      if (i >= n) continue;
+      uint32_t kind = e[j].x & 0xFF;
+      uint32_t t = (uint32_t)i;
+      uint32_t my_s = t - my_g - my_c;  // signals declared before this event
+      if (kind <= C2A_EV_SIGNAL_CONST) {
+        uint32_t sid = e[j].y;
+        uint32_t old = atomicCAS(sig_t + sid, kNone, t);
+        if (old != kNone) f |= EF_DUPLICATE;  // compiler.rs:146-148
+        else sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
+      } else if (kind == C2A_EV_GATE) {
+        egates[my_g] = make_uint4(e[j].x >> 8, e[j].y, e[j].z, e[j].w);
+        gate_t[my_g] = t;
+      } else {
+        conn[my_c] = make_uint2(e[j].y, e[j].z);
+        conn_t[my_c] = t;
+        conn_sb[my_c] = my_s;
+      }
+    }
+  }
+  f = warp_or(f);
+  if (lane == 0 && f) atomicOr(es + ES_FLAGS, f);
+}
+
+// ---- E2 ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_ev_check_gates(const uint4* __restrict__ egates, const uint32_t* __restrict__ gate_t, uint32_t G, uint32_t S,
+                                                           const uint32_t* __restrict__ sig_t, uint8_t* __restrict__ outmark, uint32_t* __restrict__ es) {
+  bool bad = false;
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
+    uint4 e = egates[g];
+    uint32_t t = gate_t[g];
+    // a signal that is not declared BEFORE the gate resolves to node 0 / panics in the reference (compiler.rs:183, :201)
+    bool ok = e.y < S && e.z < S && e.w < S && __ldg(sig_t + e.y) < t && __ldg(sig_t + e.z) < t && __ldg(sig_t + e.w) < t;
+    if (!ok) bad = true;
+    else outmark[e.w] = 1;  // compiler.rs:201 marks the out node is_out
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_UNKNOWN_REF);
+}
+__global__ void __launch_bounds__(kBlock) k_ev_check_conns(const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_t, uint32_t C, uint32_t S,
+                                                           const uint32_t* __restrict__ sig_t, uint32_t* __restrict__ es) {
+  bool bad = false;
+  for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < C; c += gridDim.x * kBlock) {
+    uint2 ab = conn[c];
+    uint32_t t = conn_t[c];
+    if (!(ab.x < S && ab.y < S && __ldg(sig_t + ab.x) < t && __ldg(sig_t + ab.y) < t)) bad = true;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_UNKNOWN_REF);
+}
+
+// ---- M: Boruvka over the connection graph, weight = connection index (= event order) -------------------------
+__device__ __forceinline__ uint32_t uf_find(uint32_t* __restrict__ parent, uint32_t x) {
+  // Roots do not change while a kernel that calls this runs (hooking happens in k_msf_hook only); the compression
+  // stores race benignly: every value written is the current root.
+  uint32_t r = x, p;
+  while ((p = parent[r]) != r) r = p;
+  while (x != r) { p = parent[x]; if (p != r) parent[x] = r; x = p; }
+  return r;
+}
+
+template <typename T>
+__device__ __forceinline__ void warp_append_t(bool ready, const T& item, T* __restrict__ queue, uint32_t* __restrict__ tail) {
+  uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
+  if (!m) return;
+  int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  uint32_t base = 0;
+  if (lane == leader) base = atomicAdd(tail, (uint32_t)__popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, leader);
+  if (ready) queue[base + __popc(m & ((1u << lane) - 1))] = item;
+}
+
+__device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
+  if (*reinterpret_cast<volatile uint32_t*>(p) > v) atomicMin(p, v);  // values only decrease within a round: a stale read costs one RED
+}
+
+// cur == nullptr: first round, the live list is 0..n0-1.  cand[] receives {edge, class of a, class of b, 0}.
+__global__ void __launch_bounds__(kBlock) k_msf_pick(const uint2* __restrict__ conn, const uint32_t* __restrict__ cur, const uint32_t* __restrict__ n_cur,
+                                                     uint32_t n0, uint32_t* __restrict__ parent, uint32_t* __restrict__ best, uint32_t tag,
+                                                     uint4* __restrict__ cand, uint32_t* __restrict__ n_cand) {
+  const uint32_t n = cur ? *n_cur : n0;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i0 = blockIdx.x * kBlock + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kBlock) {
+    uint32_t i = i0 + lane;
+    bool keep = false;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (i < n) {
+      uint32_t e = cur ? cur[i] : i;
+      uint2 ab = conn[e];
+      uint32_t cu = uf_find(parent, ab.x), cv = uf_find(parent, ab.y);
+      if (cu != cv) {  // still joins two classes: candidate; otherwise it is (or became) internal and is dropped
+        uint32_t val = tag | e;
+        red_min_u32(best + cu, val);
+        red_min_u32(best + cv, val);
+        keep = true;
+        out = make_uint4(e, cu, cv, 0);
+      }
+    }
+    warp_append_t(keep, out, cand, n_cand);
+  }
+}
+
+// A class hooks along its minimum edge (an MSF edge => an effective connection).  Mutual minimum: the larger root
+// goes under the smaller.  Edges not chosen by either side stay on the live list.
+__global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ parent,
+                                                     const uint32_t* __restrict__ best, uint32_t tag, uint32_t* __restrict__ eff,
+                                                     uint32_t* __restrict__ cur, uint32_t* __restrict__ n_cur) {
+  const uint32_t n = *n_cand;
+  const int lane = threadIdx.x & 31;
+  for (uint32_t i0 = blockIdx.x * kBlock + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kBlock) {
+    uint32_t i = i0 + lane;
+    bool keep = false;
+    uint32_t e = 0;
+    if (i < n) {
+      uint4 c = cand[i];
+      e = c.x;
+      uint32_t val = tag | e;
+      bool bu = best[c.y] == val, bv = best[c.z] == val;
+      if (bu && bv) { parent[max(c.y, c.z)] = min(c.y, c.z); eff[e] = 1; }
+      else if (bu) { parent[c.y] = c.z; eff[e] = 1; }
+      else if (bv) { parent[c.z] = c.y; eff[e] = 1; }
+      else keep = true;
+    }
+    warp_append_t(keep, e, cur, n_cur);
+  }
+}
+
+// ---- N: node ids ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBlock) k_ev_nid_init(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
+                                                        const uint32_t* __restrict__ effx, uint32_t* __restrict__ nid) {
+  for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
+    uint32_t id = 0;
+    if (sig_t[s] != kNone) {
+      uint2 m = sig_meta[s];
+      id = (m.x & 0x7FFFFFFFu) + 1u + __ldg(effx + m.y);  // compiler.rs:157 with node_count = signals + effective merges so far
+    }
+    nid[s] = id;
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
+                                                         const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint32_t* __restrict__ nid) {
+  for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < C; c += gridDim.x * kBlock) {
+    uint32_t x = effx[c];
+    if (effx[c + 1] == x) continue;                     // not effective: no id consumed (compiler.rs:235-237)
+    uint32_t id = conn_sb[c] + x + 1u;                   // compiler.rs:257
+    atomicMax(nid + uf_find(parent, conn[c].x), id);
+  }
+}
+// node_of_signal + the merge-error screens (compiler.rs:239-245); cnt[] = per class {#const signals, #gate-output signals << 16}
+__global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
+                                                        const uint8_t* __restrict__ outmark, uint32_t* __restrict__ parent,
+                                                        const uint32_t* __restrict__ nid, uint32_t* __restrict__ cnt, uint32_t* __restrict__ nos,
+                                                        uint32_t* __restrict__ es) {
+  uint32_t f = 0;
+  for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
+    uint32_t node = 0;
+    if (sig_t[s] != kNone) {
+      uint32_t r = uf_find(parent, s);
+      node = nid[r];
+      if (sig_meta[s].x & 0x80000000u) { if (atomicAdd(cnt + r, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
+      if (outmark[s]) { if (atomicAdd(cnt + r, 0x10000u) >> 16) f |= EF_OUT_OUT; }
+    }
+    nos[s] = node;
+  }
+  f = warp_or(f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(es + ES_FLAGS, f);
+}
+__global__ void __launch_bounds__(kBlock) k_ev_gates(const uint4* __restrict__ egates, uint32_t G, const uint32_t* __restrict__ nos,
+                                                     uint4* __restrict__ gates) {
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
+    uint4 e = egates[g];
+    stg_stream(gates + g, make_uint4(e.x, __ldg(nos + e.y), __ldg(nos + e.z), __ldg(nos + e.w)));
+  }
+}
+// I/O signal ids -> node ids (compiler.rs:327-361 walks nodes; here the caller lists signals)
+__global__ void __launch_bounds__(kBlock) k_ev_map_io(const uint32_t* __restrict__ sigs, uint32_t n, uint32_t S, const uint32_t* __restrict__ nos,
+                                                      uint32_t* __restrict__ nodes, uint32_t* __restrict__ es) {
+  bool bad = false;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t s = sigs[i], nd = s < S ? nos[s] : 0u;
+    if (nd == 0) bad = true;
+    nodes[i] = nd;
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_BAD_IO);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+static inline size_t emit_scratch_bytes(uint64_t n, uint64_t G, uint64_t C, uint64_t S) {
+  size_t b = 0;
+  b += align256(4 * S) + align256(8 * S);                                   // sig_t, sig_meta
+  b += align256(16 * G) + align256(4 * G);                                  // egates, gate_t
+  b += align256(8 * C) + 2 * align256(4 * C);                               // conn, conn_t, conn_sb
+  b += align256(S);                                                         // outmark
+  b += 3 * align256(4 * S);                                                 // parent, best/cnt, nid
+  b += align256(4 * (C + 1)) + align256(4 * C) + align256(16 * C);          // eff/effx, cur, cand
+  b += align256(8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1)) + 256;     // tile_state + ticket
+  (void)n;
+  return b;
+}
+
+static void emit_flags_text(uint32_t f, char* buf, size_t cap) {
+  snprintf(buf, cap, "%s%s%s%s%s%s%s", (f & EF_BAD_KIND) ? "bad-kind " : "", (f & EF_BAD_OP) ? "bad-op " : "", (f & EF_DUPLICATE) ? "duplicate-signal " : "",
+           (f & EF_UNKNOWN_REF) ? "reference-before-declaration " : "", (f & EF_CONST_CONST) ? "const+const-merge " : "",
+           (f & EF_OUT_OUT) ? "out+out-merge? " : "", (f & EF_SPARSE) ? "sparse-signal-ids " : "");
+}
+
+}  // namespace c2a
+
+using namespace c2a;
+
+extern "C" {
+// host emitter entry points (c2a_host.cpp) used for the exact replay of streams the device path declines
+c2a_compiler* c2a_compiler_new(void);
+void c2a_compiler_free(c2a_compiler*);
+int c2a_emit_events(c2a_compiler*, const c2a_event* ev, uint64_t n, uint64_t* err_event);
+uint64_t c2a_num_gates(const c2a_compiler*);
+uint32_t c2a_node_count(const c2a_compiler*);
+uint64_t c2a_num_signals(const c2a_compiler*);
+int c2a_get_gates(c2a_compiler*, c2a_gate* out);
+int c2a_signal_nodes(c2a_compiler*, const uint32_t* signal_ids, uint64_t n, uint32_t* node_ids);
+const char* c2a_compiler_last_error(const c2a_compiler*);
+}
+
+namespace c2a {
+
+static void emit_drop_host(c2a_handle* h) {
+  if (h->host_comp) { c2a_compiler_free(h->host_comp); h->host_comp = nullptr; }
+}
+
+// Exact replay on the host emitter; uploads the node-id gate vector (and node_of_signal when ids are dense).
+static int emit_host_path(c2a_handle* h, const c2a_event* ev, uint64_t n, uint32_t sbound_hint, bool sparse, c2a_emit_info* info, uint64_t* err_event) {
+  emit_drop_host(h);
+  c2a_compiler* c = c2a_compiler_new();
+  uint64_t bad = 0;
+  int st = c2a_emit_events(c, ev, n, &bad);
+  if (st != C2A_OK) {
+    if (err_event) *err_event = bad;
+    fail(h, st, "event %llu: %s", (unsigned long long)bad, st == C2A_ERR_INVALID_ARGUMENT || st == C2A_ERR_REFERENCE_PANIC ? c2a_compiler_last_error(c) : c2a_status_string(st));
+    c2a_compiler_free(c);
+    return st;
+  }
+  const uint64_t G = c2a_num_gates(c);
+  const uint32_t S = sparse ? 0u : sbound_hint;
+  std::vector<c2a_gate> gates(G);
+  c2a_get_gates(c, gates.data());
+  std::vector<uint32_t> nos(S), ids(S);
+  for (uint32_t i = 0; i < S; ++i) ids[i] = i;
+  if (S) c2a_signal_nodes(c, ids.data(), S, nos.data());
+  slab_reset(h);
+  size_t resident = align256(16 * G) + align256(4 * (size_t)S);
+  if (!slab_reserve(h, resident)) { c2a_compiler_free(c); return C2A_ERR_NO_MEMORY; }
+  uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
+  uint32_t* d_nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  if (G) cudaMemcpyAsync(d_gates, gates.data(), 16 * G, cudaMemcpyHostToDevice, h->stream);
+  if (S) cudaMemcpyAsync(d_nos, nos.data(), 4 * (size_t)S, cudaMemcpyHostToDevice, h->stream);
+  if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "host-path upload")) { c2a_compiler_free(c); return C2A_ERR_CUDA; }
+  h->slab_keep = h->slab_used;
+  h->emitted.valid = true;
+  h->emitted.nos_valid = !sparse;
+  h->emitted.gates_off = (char*)d_gates - h->slab;
+  h->emitted.nos_off = (char*)d_nos - h->slab;
+  h->emitted.G = G;
+  h->emitted.node_count = c2a_node_count(c);
+  h->emitted.signal_bound = S;
+  h->host_comp = c;  // kept: I/O signal lists are mapped through it when node_of_signal is not resident
+  if (info) {
+    info->n_gates = G;
+    info->n_signals = c2a_num_signals(c);
+    info->n_effective = h->emitted.node_count - info->n_signals;
+    info->node_count = h->emitted.node_count;
+    info->signal_bound = S;
+    info->path = C2A_EMIT_PATH_HOST;
+  }
+  return C2A_OK;
+}
+
+}  // namespace c2a
+
+extern "C" {
+
+// ev_host: events in host memory (copied in) or, when ev_dev != null, already resident on the handle's device.
+static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_event* ev_dev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+  int st = check_sizes(h, n, 1);
+  if (st) return st;
+  if (n && !ev_host && !ev_dev) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
+  const c2a_event* ev = ev_host;
+  if (info) memset(info, 0, sizeof *info);
+  if (info) info->n_events = n;
+  phases_clear(h);
+  cudaStream_t s = h->stream;
+  const uint32_t tiles = (uint32_t)((n + kEvTile - 1) / kEvTile);
+  // staging buffer (outside the slab: the slab is sized only once the counts are known)
+  const size_t ev_copy = ev_dev ? 0 : align256(16 * n);
+  size_t ev_need = ev_copy + align256(4 * (size_t)tiles + 4) + align256(8 * (size_t)tiles + 8) + align256(4 * ES_COUNT);
+  if (ev_need > h->ev_bytes) {
+    if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
+    if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+    h->ev_bytes = ev_need + ev_need / 16;
+  }
+  const uint4* d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
+  uint32_t* tile_cnt = (uint32_t*)(h->ev_buf + ev_copy);
+  uint2* tile_base = (uint2*)((char*)tile_cnt + align256(4 * (size_t)tiles + 4));
+  uint32_t* es = (uint32_t*)((char*)tile_base + align256(8 * (size_t)tiles + 8));
+  uint32_t* hp = h->h_pinned;
+
+  phase_begin(h, "h2d");
+  if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
+  phase_end(h);
+  cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
+  phase_begin(h, "k_ev_count");
+  if (n) LAUNCH(h, k_ev_count, std::min<uint32_t>(tiles, (uint32_t)h->num_sms * 8), kBlock, d_ev, n, tiles, tile_cnt, es);
+  phase_end(h);
+  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "count sync")) return C2A_ERR_CUDA;
+  const uint64_t G = hp[ES_NGATE], C = hp[ES_NCONN];
+  const uint32_t S = hp[ES_SBOUND];
+  uint32_t flags = hp[ES_FLAGS];
+  const uint64_t n_sig = n - G - C;
+  if (!(flags & (EF_BAD_KIND | EF_SPARSE)) && (uint64_t)S > 4 * n_sig + (1u << 20)) flags |= EF_SPARSE;  // a dense table would be mostly holes
+  if (info) { info->n_gates = G; info->n_connections = C; info->n_signals = n_sig; info->signal_bound = S; }
+
+  std::vector<c2a_event> ev_back;
+  auto decline = [&](uint32_t f) -> int {
+    if (info) info->decline_flags = f;
+    if (!ev && n) {  // resident events: the exact replay needs them on the host
+      ev_back.resize(n);
+      if (!cuda_ok(h, cudaMemcpy(ev_back.data(), ev_dev, 16 * n, cudaMemcpyDeviceToHost), "events D2H for the host replay")) return C2A_ERR_CUDA;
+      ev = ev_back.data();
+    }
+    int r = emit_host_path(h, ev, n, S, (f & EF_SPARSE) != 0, info, err_event);
+    if (info) info->decline_flags = f;
+    phases_collect(h);
+    return r;
+  };
+  if (flags) return decline(flags);
+
+  // ---- exact sizes are known: one slab for the resident result, the emit scratch and the build that follows
+  const uint32_t NB_ub = (uint32_t)std::min<uint64_t>(n_sig + C + 1, 0x7FFFFFFEull);
+  BuildPlan bp{G, NB_ub, 0, 0, true};
+  size_t resident = align256(16 * G) + align256(4 * (size_t)S);
+  size_t build_need = core_scratch_bytes(bp, 1u << 20) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)NB_ub);
+  slab_reset(h);
+  emit_drop_host(h);
+  if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(n, G, C, S), build_need))) return C2A_ERR_NO_MEMORY;
+  uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
+  uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  const size_t keep = h->slab_used;
+  uint32_t* sig_t = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint2* sig_meta = (uint2*)slab_alloc(h, 8 * (size_t)S);
+  uint4* egates = (uint4*)slab_alloc(h, 16 * G);
+  uint32_t* gate_t = (uint32_t*)slab_alloc(h, 4 * G);
+  uint2* conn = (uint2*)slab_alloc(h, 8 * C);
+  uint32_t* conn_t = (uint32_t*)slab_alloc(h, 4 * C);
+  uint32_t* conn_sb = (uint32_t*)slab_alloc(h, 4 * C);
+  uint8_t* outmark = (uint8_t*)slab_alloc(h, S);
+  uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* nid = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * (C + 1));
+  uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
+  uint4* cand = (uint4*)slab_alloc(h, 16 * C);
+  unsigned long long* tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1));
+  uint32_t* ticket = (uint32_t*)slab_alloc(h, 256);
+  if (!ticket) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+
+  phase_begin(h, "init");
+  cudaMemsetAsync(sig_t, 0xFF, 4 * (size_t)S, s);
+  cudaMemsetAsync(outmark, 0, S, s);
+  cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
+  cudaMemsetAsync(eff, 0, 4 * (C + 1), s);
+  if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
+  phase_end(h);
+  const int wide = h->num_sms * 8;
+  phase_begin(h, "k_ev_scatter");
+  if (tiles) LAUNCH(h, k_ev_tile_scan, 1, 1024, tile_cnt, tiles, tile_base);
+  if (tiles) LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)wide), kBlock, d_ev, n, tiles, tile_base, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
+  phase_end(h);
+  phase_begin(h, "k_ev_check");
+  if (G) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
+  if (C) LAUNCH(h, k_ev_check_conns, grid_for(h, (const void*)k_ev_check_conns, kBlock, C), kBlock, conn, conn_t, (uint32_t)C, S, sig_t, es);
+  phase_end(h);
+  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
+  flags = hp[ES_FLAGS];
+  if (flags) return decline(flags);
+
+  // ---- Boruvka rounds
+  phase_begin(h, "k_msf");
+  uint32_t rounds = 0;
+  if (C) {
+    const uint32_t* cur_in = nullptr;
+    while (true) {
+      uint32_t tag = (6u - (rounds % 7u)) << 29;
+      if (rounds && (rounds % 7u) == 0) cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);  // tags wrapped: forget the old minima
+      cudaMemsetAsync(es + ES_NCAND, 0, 4, s);
+      LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur_in, es + ES_NCUR, (uint32_t)C, parent, best, tag, cand, es + ES_NCAND);
+      cudaMemsetAsync(es + ES_NCUR, 0, 4, s);
+      LAUNCH(h, k_msf_hook, wide, kBlock, cand, es + ES_NCAND, parent, best, tag, eff, cur, es + ES_NCUR);
+      cur_in = cur;
+      ++rounds;
+      cudaMemcpyAsync(hp, es + ES_NCUR, 8, cudaMemcpyDeviceToHost, s);
+      if (!cuda_ok(h, cudaStreamSynchronize(s), "msf sync")) return C2A_ERR_CUDA;
+      if (hp[1] == 0 || hp[0] == 0) break;  // no candidate edges at all, or none left undecided
+      if (rounds > 64) return fail(h, C2A_ERR_CUDA, "Boruvka did not converge");
+    }
+    // edges still on the live list when no candidate was hooked cannot exist: hp[1]==0 means every live edge is internal
+  }
+  phase_end(h);
+
+  // ---- node ids
+  phase_begin(h, "k_ev_nodes");
+  {
+    uint32_t stiles = scan_tiles(C + 1, kScanItems);
+    cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
+    cudaMemsetAsync(ticket, 0, 4, s);
+    // exclusive scan of eff[0..C) in place; eff[C] receives the total (= effective connections)
+    if (C) LAUNCH(h, k_scan_u32, scan_tiles(C, kScanItems), kBlock, eff, (uint32_t)C, tile_state, ticket);
+  }
+  cudaMemsetAsync(best, 0, 4 * (size_t)S, s);  // reused as cnt[]
+  if (S) LAUNCH(h, k_ev_nid_init, grid_for(h, (const void*)k_ev_nid_init, kBlock, S), kBlock, S, sig_t, sig_meta, eff, nid);
+  if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, parent, nid);
+  if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, sig_t, sig_meta, outmark, parent, nid, best, nos, es);
+  phase_end(h);
+  phase_begin(h, "k_ev_gates");
+  if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, nos, d_gates);
+  phase_end(h);
+  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+  cudaMemcpyAsync(hp + ES_COUNT, eff + C, 4, cudaMemcpyDeviceToHost, s);
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaGetLastError(), "emit kernels")) return C2A_ERR_CUDA;
+  flags = hp[ES_FLAGS];
+  if (flags) return decline(flags);
+  const uint32_t n_eff = C ? hp[ES_COUNT] : 0u;
+
+  h->slab_used = keep;
+  h->slab_keep = keep;
+  h->emitted.valid = true;
+  h->emitted.nos_valid = true;
+  h->emitted.gates_off = (char*)d_gates - h->slab;
+  h->emitted.nos_off = (char*)nos - h->slab;
+  h->emitted.G = G;
+  h->emitted.node_count = (uint32_t)(n_sig + n_eff);
+  h->emitted.signal_bound = S;
+  if (info) {
+    info->n_effective = n_eff;
+    info->node_count = h->emitted.node_count;
+    info->path = C2A_EMIT_PATH_DEVICE;
+    info->rounds = rounds;
+  }
+  phases_collect(h);
+  return C2A_OK;
+}
+
+int c2a_emit_events_device(c2a_handle* h, const c2a_event* ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+  return emit_events_impl(h, ev, nullptr, n, info, err_event);
+}
+int c2a_emit_events_resident(c2a_handle* h, const c2a_event* d_ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+  if (n && !d_ev) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
+  return emit_events_impl(h, nullptr, d_ev, n, info, err_event);
+}
+
+int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_signal_out) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h->emitted.valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no emitted circuit is resident on this handle");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  if (gates_out && h->emitted.G) cudaMemcpyAsync(gates_out, h->slab + h->emitted.gates_off, 16 * h->emitted.G, cudaMemcpyDeviceToHost, h->stream);
+  if (node_of_signal_out) {
+    if (!h->emitted.nos_valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "node_of_signal is not resident (sparse signal ids)");
+    if (h->emitted.signal_bound) cudaMemcpyAsync(node_of_signal_out, h->slab + h->emitted.nos_off, 4 * (size_t)h->emitted.signal_bound, cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "emitted fetch")) return C2A_ERR_CUDA;
+  return C2A_OK;
+}
+
+static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
+                              uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index,
+                              bool outputs_on_device) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h->emitted.valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no emitted circuit is resident on this handle");
+  const uint64_t G = h->emitted.G;
+  const uint32_t node_bound = h->emitted.node_count + 1;
+  int st = check_sizes(h, G, node_bound);
+  if (st) return st;
+  phases_clear(h);
+  cudaStream_t s = h->stream;
+  BuildPlan p{G, node_bound, n_in, n_out, true};
+  const size_t n_pairs = (size_t)n_in + n_out;
+  slab_reset_keep(h);
+  size_t need = h->slab_keep + core_scratch_bytes(p, n_pairs) + align256(4 * n_pairs + 4) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)node_bound) + align256(4 * ES_COUNT);
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  const uint4* d_gates = (const uint4*)(h->slab + h->emitted.gates_off);
+  const uint32_t* nos = (const uint32_t*)(h->slab + h->emitted.nos_off);
+  uint32_t* io_sigs = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  uint32_t* io_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
+  uint32_t* es = (uint32_t*)slab_alloc(h, 4 * ES_COUNT);
+  uint4* d_new = outputs_on_device ? (uint4*)new_gates : (new_gates ? (uint4*)slab_alloc(h, 16 * G) : nullptr);
+  uint32_t* d_order = outputs_on_device ? order_out : (order_out ? (uint32_t*)slab_alloc(h, 4 * G) : nullptr);
+  uint32_t* d_wire = outputs_on_device && wire_of_node ? wire_of_node : (uint32_t*)slab_alloc(h, 4 * (size_t)node_bound);
+  if (!d_wire || !io_sigs || !io_nodes || !es) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  if ((4 * n_pairs + 2048) > h->h_pinned_bytes) {
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned_bytes = 4 * n_pairs + 8192;
+    if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
+  }
+  if (n_pairs) {
+    uint32_t* stage = h->h_pinned + 256;
+    if (h->emitted.nos_valid) {
+      if (n_in) memcpy(stage, input_signals, 4 * (size_t)n_in);
+      if (n_out) memcpy(stage + n_in, output_signals, 4 * (size_t)n_out);
+      cudaMemcpyAsync(io_sigs, stage, 4 * n_pairs, cudaMemcpyHostToDevice, s);
+      cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
+      LAUNCH(h, k_ev_map_io, grid_for(h, (const void*)k_ev_map_io, kBlock, n_pairs), kBlock, io_sigs, (uint32_t)n_pairs, h->emitted.signal_bound, nos, io_nodes, es);
+      cudaMemcpyAsync(h->h_pinned + 128, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+      if (!cuda_ok(h, cudaStreamSynchronize(s), "io map")) return C2A_ERR_CUDA;
+      if (h->h_pinned[128 + ES_FLAGS] & EF_BAD_IO) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
+    } else {  // sparse ids: map through the host emitter that produced the circuit
+      if (n_in) c2a_signal_nodes(h->host_comp, input_signals, n_in, stage);
+      if (n_out) c2a_signal_nodes(h->host_comp, output_signals, n_out, stage + n_in);
+      for (size_t i = 0; i < n_pairs; ++i)
+        if (stage[i] == 0) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
+      cudaMemcpyAsync(io_nodes, stage, 4 * n_pairs, cudaMemcpyHostToDevice, s);
+      if (!cuda_ok(h, cudaStreamSynchronize(s), "io upload")) return C2A_ERR_CUDA;
+    }
+  }
+  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, nullptr, io_nodes);
+  if (st == C2A_OK && !outputs_on_device) {
+    phase_begin(h, "d2h");
+    if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
+    if (wire_of_node && node_bound) cudaMemcpyAsync(wire_of_node, d_wire, 4 * (size_t)node_bound, cudaMemcpyDeviceToHost, s);
+    if (new_gates && G) cudaMemcpyAsync(new_gates, d_new, 16 * G, cudaMemcpyDeviceToHost, s);
+    phase_end(h);
+    if (!cuda_ok(h, cudaStreamSynchronize(s), "D2H")) st = C2A_ERR_CUDA;
+  } else {
+    cudaStreamSynchronize(s);
+  }
+  phases_collect(h);
+  return st;
+}
+
+int c2a_emitted_build_circuit(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
+                              uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index) {
+  return emitted_build_impl(h, input_signals, n_in, output_signals, n_out, order_out, wire_of_node, new_gates, wire_count, err_index, false);
+}
+int c2a_emitted_build_circuit_device(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
+                                     uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
+                                     uint64_t* err_index) {
+  return emitted_build_impl(h, input_signals, n_in, output_signals, n_out, d_order_out, d_wire_of_node, d_new_gates, wire_count, err_index, true);
+}
+
+}  // extern "C"

@@ -32,6 +32,20 @@ struct c2a_handle {
   size_t ev_next = 0;
   std::vector<std::pair<std::string, double>> last_ms;
   bool timing = true;
+  // ---- device emitter (c2a_emit.cuh): event staging buffer (separate from the slab) and the resident result
+  char* ev_buf = nullptr;
+  size_t ev_bytes = 0;
+  size_t slab_keep = 0;  // bytes at the start of the slab that slab_reset_keep() preserves (the emitted circuit)
+  struct Emitted {
+    bool valid = false;
+    bool nos_valid = false;      // node_of_signal[] resident (false for sparse signal ids on the host path)
+    size_t gates_off = 0;        // uint4[G], node ids, emission order
+    size_t nos_off = 0;          // u32[signal_bound]
+    uint64_t G = 0;
+    uint32_t node_count = 0;
+    uint32_t signal_bound = 0;
+  } emitted;
+  struct c2a_compiler* host_comp = nullptr;  // kept alive when the exact host emitter had to run (sparse ids)
 };
 
 namespace c2a {
@@ -40,8 +54,9 @@ int fail(c2a_handle* h, int status, const char* fmt, ...);
 bool cuda_ok(c2a_handle* h, cudaError_t e, const char* what);
 
 // slab allocator
-void slab_reset(c2a_handle* h);
-bool slab_reserve(c2a_handle* h, size_t bytes);  // ensure capacity (may reallocate: only legal right after slab_reset)
+void slab_reset(c2a_handle* h);       // drops everything, including a resident emitted circuit
+void slab_reset_keep(c2a_handle* h);  // keeps the first slab_keep bytes
+bool slab_reserve(c2a_handle* h, size_t bytes);  // ensure capacity; reallocation preserves the first slab_keep bytes
 void* slab_alloc(c2a_handle* h, size_t bytes);   // 256-byte aligned; nullptr when exhausted
 inline size_t align256(size_t b) { return (b + 255) & ~size_t(255); }
 

@@ -146,6 +146,40 @@ int c2a_sweep_masks(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t nod
                     const uint32_t* output_nodes, uint32_t n_out,
                     uint8_t* const_mask, uint32_t* const_value, uint8_t* dead_mask, uint64_t* err_index);
 
+/* ---- emit side (device).  The whole event stream is replayed on the GPU: add_signal / add_gate / add_connection
+ * (src/compiler.rs:139-278) with the reference's node-id allocation reproduced exactly (effective connections =
+ * minimum spanning forest of the connection graph under event order; see csrc/c2a_emit.cuh).  The node-id gate vector
+ * and the signal -> node map stay RESIDENT on the handle and feed c2a_emitted_build_circuit without a host round trip.
+ * Streams on which the reference would error, or that use the "signal in no node => node 0" quirk (:183), are replayed
+ * by the exact host emitter below (info.path says which ran); its status / *err_event are returned unchanged. ---- */
+#define C2A_EMIT_PATH_DEVICE 1u
+#define C2A_EMIT_PATH_HOST 2u
+typedef struct {
+  uint64_t n_events, n_signals, n_gates, n_connections;
+  uint64_t n_effective;    /* connections that merged two nodes (each consumes a node id, compiler.rs:257) */
+  uint32_t node_count;     /* the reference's node_count: node ids are 1..node_count */
+  uint32_t signal_bound;   /* 1 + largest declared signal id (0 when ids are too sparse for a dense map) */
+  uint32_t path;           /* C2A_EMIT_PATH_DEVICE / C2A_EMIT_PATH_HOST */
+  uint32_t rounds;         /* Boruvka rounds (device path) */
+  uint32_t decline_flags;  /* non-zero: why the device path handed the stream to the host emitter */
+  uint32_t reserved;
+} c2a_emit_info;
+/* ev: host pointer (pinned memory makes the copy asynchronous). */
+int c2a_emit_events_device(c2a_handle*, const c2a_event* ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event);
+/* same, the events are already resident on the handle's device (DEVICE pointer; used for the HBM-resident bench number) */
+int c2a_emit_events_resident(c2a_handle*, const c2a_event* d_ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event);
+/* copies of the resident result: gates_out[n_gates] (node ids, emission order = Compiler.gates),
+ * node_of_signal_out[signal_bound] (0 = never declared).  Either may be NULL. */
+int c2a_emitted_fetch(c2a_handle*, c2a_gate* gates_out, uint32_t* node_of_signal_out);
+/* c2a_build_circuit on the resident emitted circuit; inputs/outputs are listed as SIGNAL ids (node_bound is
+ * node_count + 1, so wire_of_node needs node_count + 1 entries). */
+int c2a_emitted_build_circuit(c2a_handle*, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
+                              uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index);
+/* same with DEVICE pointers for the three result arrays (the I/O signal lists stay host pointers) */
+int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
+                                     uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
+                                     uint64_t* err_index);
+
 /* ---- emit side (host).  Node ids, gate vector and error behaviour identical to the reference Compiler. ---- */
 c2a_compiler* c2a_compiler_new(void);
 void c2a_compiler_free(c2a_compiler*);
