@@ -9,10 +9,12 @@ W independent chains x 91 rounds x 6 gates emitted in the reference walker's ord
 workloads.py).  Default W=18315 -> 10.0 M gates; 'late' variant = component inputs wired after the body, so the
 DFS post-order is NOT the identity and the full sort path runs.
 
-A step = one pass of the hot path over one circuit:
-  value  build_circuit on HBM-resident gates (K1..K7, c2a_build_circuit_device), CUDA events on the handle's stream
-  e2e    event stream (host) -> c2a_emit_events (host union-find) -> c2a_get_gates -> c2a_build_circuit with PINNED HOST
-         buffers (H2D of the gate array and D2H of order / wire map / new gates inside the timed region)
+A step = one pass of the hot path (emit + build_circuit) over one circuit:
+  value  event stream resident in HBM -> c2a_emit_events_resident (device emitter) -> c2a_emitted_build_circuit_device
+         (K1..K7); results stay in HBM; CUDA events on the handle's stream
+  e2e    event stream in PINNED HOST memory -> c2a_emit_events_device -> c2a_emitted_build_circuit into pinned host
+         buffers (H2D of the events and D2H of order / wire map / new gates inside the timed region)
+  e2e_host_emitter  (one step, for comparison) the same circuit through the host union-find emitter + c2a_build_circuit
 N>1: every rank owns one independent component subtree (its own W chains; weak scaling), ranks exchange their
 input/intermediate/output wire counts with one NCCL all-gather and rebase their wires to the global numbering.
 """
@@ -28,28 +30,40 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# Algorithmic bytes per gate of each kernel (SURVEY.md §8d accounting: every array element counted
-# once per required read and once per required write; nodes/gate measured on the workload).
-def alg_bytes(kernel, G, node_bound, n_nonid):
-    npg = node_bound / max(G, 1)
+# Algorithmic bytes of each kernel per launch (SURVEY.md §8d accounting: every array element counted once
+# per required read and once per required write, atomics = read + write of the word).  c = the workload's counts.
+def alg_bytes(kernel, c):
+    G, NB, n, S, C, Ceff, ns = c["G"], c["NB"], c["n"], c["S"], c["C"], c["Ceff"], c["n_sig"]
+    order = 0 if c["identity"] else 4 * G            # sorted passes also read order[]
     table = {
-        "k_producer": 16 + 4,                 # read gate, RED.MAX producer[out]
-        "k_deps": 16 + 8 + 8,                 # read gate, 2 producer gathers, write dep pair
-        "k_wire_first": 16 + 12,              # read gate (+4 order when sorted), 3 RED.MIN on wire[]
-        "k_wire_scan": 16 + 12 + 4 * npg,     # read gate, 3 wire reads, one wire write per numbered node
-        "k_gather": 16 + 12 + 16,             # read gate, 3 wire gathers, write new gate
-        "k_relax": 8 + 4,                     # read dep pair, r init (+ out-of-order edges, counted separately)
-        "k_sizes": 4 + 4,                     # read r, RED.ADD size[r]
-        "k_scan_u32": 4 + 4,
-        "k_roots": 4 + 8 + 4,                 # read r, read off pair, write order
+        # ---- device emitter (c2a_emit.cuh)
+        "emit:k_ev_count": 16 * n,                                # stream the events
+        "emit:k_ev_tile_scan": 12 * ((n + 1023) // 1024),
+        "emit:k_ev_scatter": 16 * n + ns * (8 + 8) + G * (16 + 4) + C * (8 + 4 + 4),   # sig_t CAS + meta | egates + gate_t | conn + t + sb
+        "emit:k_ev_check_gates": G * (16 + 4 + 12 + 1),
+        "emit:k_ev_check_conns": C * (8 + 4 + 8),
+        "emit:k_msf_pick": C * (8 + 8 + 16 + 16),                 # conn, 2 parent, 2 RED.MIN best, cand (first round; later rounds are on the shrunken list)
+        "emit:k_msf_hook": C * (16 + 8 + 4 + 4),                  # cand, 2 best, parent, eff
+        "emit:k_scan_u32": 8 * C,
+        "emit:k_ev_nid_init": S * (4 + 8 + 4 + 4),
+        "emit:k_ev_nid_edges": C * 8 + Ceff * (4 + 8 + 4 + 8),
+        "emit:k_ev_finalize": S * (4 + 8 + 1 + 4 + 4 + 4) + (G + c["n_const"]) * 8,
+        "emit:k_ev_gates": G * (16 + 12 + 16),
+        "emit:init": S * (4 + 1 + 4 + 4 + 4) + 4 * C,             # memsets: sig_t, outmark, best (x2), parent iota, eff
+        # ---- build_circuit (c2a_device.cu)
+        "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
+        "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair
+        "k_relax": G * (8 + 4),                                   # read dep pair, r init (+ out-of-order edges)
+        "k_sizes": G * (4 + 4),
+        "k_scan_u32": G * (4 + 4),
+        "k_roots": G * (4 + 8 + 4),
         "k_tree_dfs": 0,
-        "init": 8 * npg,                      # zero producer[], fill wire[]
+        "k_wire_first": G * (16 + 12) + order,                    # read gate, 3 RED.MIN on wire[]
+        "k_wire_scan": G * (16 + 12) + 4 * c["n_mid"] + order,    # read gate, 3 wire reads, one wire write per numbered node
+        "k_gather": G * (16 + 12 + 16) + order,                   # read gate, 3 wire gathers, write new gate
+        "init": 8 * NB,                                           # zero producer[], fill wire[]
     }
-    extra_order = 4 if n_nonid else 0
-    b = table.get(kernel, 0)
-    if kernel in ("k_wire_first", "k_wire_scan", "k_gather"):
-        b += extra_order
-    return b * G
+    return table.get(kernel, 0)
 
 
 def clocks_sampler(stop, out, index):
@@ -124,10 +138,10 @@ def main():
     ap.add_argument("--chains", type=int, default=18315, help="MiMC chains per GPU (546/547 gates each)")
     ap.add_argument("--rounds", type=int, default=91)
     ap.add_argument("--variant", default="late", choices=["inorder", "late"])
-    ap.add_argument("--shuffle", type=int, default=0, help="shuffle the gate vector with this seed (stress)")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default min(steps,3))")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed end-to-end steps (default = --steps)")
     ap.add_argument("--sample-chains", type=int, default=37, help="chains in the bounded CPU-reference sample (~20 K gates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-host-emit", action="store_true", help="skip the host-emitter comparison leg")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -139,7 +153,7 @@ def main():
     from c2a_loader import c2a
     import numpy as np
 
-    workload_name = f"mimc_chains W={args.chains} x {args.rounds} rounds x 6 gates, variant={args.variant}" + (f", shuffled(seed={args.shuffle})" if args.shuffle else "")
+    workload_name = f"mimc_chains W={args.chains} x {args.rounds} rounds x 6 gates, variant={args.variant}"
     metric = "gates/sec (emit+topo-sort) on >=1M-gate circuit"
 
     # ------------------------------------------------------------------------------------------------
@@ -183,66 +197,79 @@ def main():
     stream = torch.cuda.ExternalStream(lib.c2a_stream(h), device=torch.device("cuda", local_rank))
 
     # ---- workload (every rank: its own independent component subtree)
+    from circom_2_arithc_b200._lib import EmitInfo
     wl = c2a.workloads.mimc_chains(args.chains, rounds=args.rounds, variant=args.variant)
-    events = np.ascontiguousarray(wl.events)
+    dev = torch.device("cuda", local_rank)
+    p_events = torch.from_numpy(np.ascontiguousarray(wl.events).view(np.int32)).pin_memory()   # the walker's output, host side
+    n_ev = int(p_events.shape[0])
+    d_events = p_events.to(dev)
     in_ids = np.array(sorted(wl.inputs), dtype=np.uint32)
     out_ids = np.array(sorted(wl.outputs), dtype=np.uint32)
+    n_const = int(((wl.events[:, 0] & 0xFF) == 1).sum())
+    vp = C.c_void_p
+    info = EmitInfo()
+    bad = C.c_uint64(0)
+    wc = C.c_uint32(0)
+    err = C.c_uint64(0)
 
-    def emit(ev):
-        comp = c2a.Compiler(context=ctx)
-        comp.emit_events(ev)
-        return comp
-
-    comp = emit(events)
-    gates_h = comp.gate_array()
-    if args.shuffle:
-        gates_h = c2a.workloads.shuffle_gates(gates_h, args.shuffle)
-    G = gates_h.shape[0]
-    nb = comp.node_count + 1
-    ins = comp.signal_nodes(in_ids)
-    outs = comp.signal_nodes(out_ids)
-    del comp
-
-    dev = torch.device("cuda", local_rank)
-    d_gates = torch.from_numpy(gates_h.view(np.int32)).to(dev)
+    # sizes (one untimed emit)
+    st = lib.c2a_emit_events_resident(h, vp(d_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+    if st != 0:
+        raise RuntimeError(f"c2a_emit_events_resident -> {st}: {ctx.last_error()}")
+    if info.path != 1:
+        raise RuntimeError(f"the device emitter declined the workload (flags {info.decline_flags}): nothing to measure")
+    G, nb = int(info.n_gates), int(info.node_count) + 1
     d_order = torch.empty(G, dtype=torch.int32, device=dev)
     d_wire = torch.empty(nb, dtype=torch.int32, device=dev)
     d_new = torch.empty((G, 4), dtype=torch.int32, device=dev)
     d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
     d_all = torch.zeros(4 * world, dtype=torch.int64, device=dev)
-    wc = C.c_uint32(0)
-    err = C.c_uint64(0)
-    vp = C.c_void_p
+    phase_acc = {}
 
-    def device_step():
-        st = lib.c2a_build_circuit_device(h, vp(d_gates.data_ptr()), G, nb, ins.ctypes.data_as(vp), len(ins), outs.ctypes.data_as(vp), len(outs),
-                                          vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+    def acc_phases(prefix):
+        for k, v in ctx.phases().items():
+            phase_acc[prefix + k] = phase_acc.get(prefix + k, 0.0) + v
+
+    def reconcile():
+        # global wire numbering across ranks: one NCCL all-gather of (n_in, n_mid, n_out, G), then a rebase kernel
+        n_mid = wc.value - len(in_ids) - len(out_ids)
+        with torch.cuda.stream(stream):
+            d_counts.copy_(torch.tensor([len(in_ids), n_mid, len(out_ids), G], dtype=torch.int64), non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_counts)
+        stream.synchronize()
+        allc = d_all.view(world, 4).cpu().numpy()
+        tot_in, tot_mid = int(allc[:, 0].sum()), int(allc[:, 1].sum())
+        off_in = int(allc[:rank, 0].sum())
+        off_mid = tot_in + int(allc[:rank, 1].sum()) - len(in_ids)
+        off_out = tot_in + tot_mid + int(allc[:rank, 2].sum()) - len(in_ids) - n_mid
+        st = lib.c2a_rebase_wires_device(h, vp(d_new.data_ptr()), vp(d_order.data_ptr()), G, len(in_ids), n_mid, off_in, off_mid, off_out, int(allc[:rank, 3].sum()))
         if st != 0:
-            raise RuntimeError(f"c2a_build_circuit_device -> {st}: {ctx.last_error()}")
-        if world > 1:  # reconcile the global wire numbering: one NCCL all-gather of (n_in, n_mid, n_out)
-            n_mid = wc.value - len(ins) - len(outs)
-            with torch.cuda.stream(stream):
-                d_counts.copy_(torch.tensor([len(ins), n_mid, len(outs), G], dtype=torch.int64), non_blocking=True)
-                dist.all_gather_into_tensor(d_all, d_counts)
-            stream.synchronize()
-            allc = d_all.view(world, 4).cpu().numpy()
-            tot_in, tot_mid = int(allc[:, 0].sum()), int(allc[:, 1].sum())
-            off_in = int(allc[:rank, 0].sum())
-            off_mid = tot_in + int(allc[:rank, 1].sum()) - len(ins)
-            off_out = tot_in + tot_mid + int(allc[:rank, 2].sum()) - len(ins) - n_mid
-            st = lib.c2a_rebase_wires_device(h, vp(d_new.data_ptr()), vp(d_order.data_ptr()), G, len(ins), n_mid, off_in, off_mid, off_out, int(allc[:rank, 3].sum()))
-            if st != 0:
-                raise RuntimeError(f"c2a_rebase_wires_device -> {st}: {ctx.last_error()}")
+            raise RuntimeError(f"c2a_rebase_wires_device -> {st}: {ctx.last_error()}")
+
+    def device_step(record=False):
+        """emit + build with the event stream already resident in HBM; results stay in HBM"""
+        st = lib.c2a_emit_events_resident(h, vp(d_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        if st != 0 or info.path != 1:
+            raise RuntimeError(f"c2a_emit_events_resident -> {st} path {info.path}: {ctx.last_error()}")
+        if record:
+            acc_phases("emit:")
+        st = lib.c2a_emitted_build_circuit_device(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
+                                                  vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+        if st != 0:
+            raise RuntimeError(f"c2a_emitted_build_circuit_device -> {st}: {ctx.last_error()}")
+        if record:
+            acc_phases("")
+        if world > 1:
+            reconcile()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: HBM-resident
+    # ---- value: HBM-resident events -> emit -> build, CUDA events on the handle's stream
     for _ in range(W):
         device_step()
-    phase_acc = {}
     stop = threading.Event()
     clk_lines = []
     th = threading.Thread(target=clocks_sampler, args=(stop, clk_lines, local_rank), daemon=True)
@@ -254,9 +281,7 @@ def main():
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(K):
-        device_step()
-        for k, v in ctx.phases().items():
-            phase_acc[k] = phase_acc.get(k, 0.0) + v
+        device_step(record=True)
     e1.record(stream)
     barrier()
     ms_total = e0.elapsed_time(e1)
@@ -267,60 +292,87 @@ def main():
     ms_total = float(t.item())
     ms_per_step = ms_total / K
     value = world * G / (ms_per_step * 1e-3)
-    n_identity = bool((d_order[:1024].cpu().numpy().astype(np.uint32) == np.arange(min(G, 1024), dtype=np.uint32)).all())
+    order_dev = d_order.cpu().numpy().astype(np.uint32)
+    gate_base = int(order_dev.min()) if G else 0
+    n_identity = bool((order_dev[:4096] - gate_base == np.arange(min(G, 4096), dtype=np.uint32)).all())
+    n_mid = int(wc.value) - len(in_ids) - len(out_ids)
+    counts = {"G": G, "NB": nb, "n": n_ev, "S": int(info.signal_bound), "C": int(info.n_connections), "Ceff": int(info.n_effective),
+              "n_sig": int(info.n_signals), "n_const": n_const, "n_mid": n_mid, "identity": n_identity}
 
-    # ---- e2e: host events -> emit -> gates -> build (pinned host buffers, H2D + D2H inside)
-    Ke = args.e2e_steps or min(K, 3)
-    p_gates = torch.empty((G, 4), dtype=torch.int32).pin_memory()
+    # ---- e2e: event stream in PINNED HOST memory -> c2a_emit_events_device -> c2a_emitted_build_circuit into pinned host
+    #      buffers (H2D of the events and D2H of order / wire map / new gates inside the timed region)
+    Ke = args.e2e_steps or K
     p_order = torch.empty(G, dtype=torch.int32).pin_memory()
     p_wire = torch.empty(nb, dtype=torch.int32).pin_memory()
     p_new = torch.empty((G, 4), dtype=torch.int32).pin_memory()
-    emit_s = []
 
     def e2e_step():
-        t0 = time.perf_counter()
-        c = lib.c2a_compiler_new()
-        bad = C.c_uint64(0)
-        st = lib.c2a_emit_events(c, events.ctypes.data_as(vp), events.shape[0], C.byref(bad))
-        assert st == 0, st
-        lib.c2a_get_gates(c, vp(p_gates.data_ptr()))
-        ii = np.empty(len(in_ids), dtype=np.uint32)
-        oo = np.empty(len(out_ids), dtype=np.uint32)
-        lib.c2a_signal_nodes(c, in_ids.ctypes.data_as(vp), len(in_ids), ii.ctypes.data_as(vp))
-        lib.c2a_signal_nodes(c, out_ids.ctypes.data_as(vp), len(out_ids), oo.ctypes.data_as(vp))
-        nb_ = lib.c2a_node_count(c) + 1
-        emit_s.append(time.perf_counter() - t0)
-        st = lib.c2a_build_circuit(h, vp(p_gates.data_ptr()), G, nb_, ii.ctypes.data_as(vp), len(ii), oo.ctypes.data_as(vp), len(oo),
-                                   vp(p_order.data_ptr()), vp(p_wire.data_ptr()), vp(p_new.data_ptr()), C.byref(wc), C.byref(err))
-        assert st == 0, (st, ctx.last_error())
-        lib.c2a_compiler_free(c)
+        st = lib.c2a_emit_events_device(h, vp(p_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        if st != 0 or info.path != 1:
+            raise RuntimeError(f"c2a_emit_events_device -> {st} path {info.path}: {ctx.last_error()}")
+        if world == 1:
+            st = lib.c2a_emitted_build_circuit(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
+                                               vp(p_order.data_ptr()), vp(p_wire.data_ptr()), vp(p_new.data_ptr()), C.byref(wc), C.byref(err))
+            if st != 0:
+                raise RuntimeError(f"c2a_emitted_build_circuit -> {st}: {ctx.last_error()}")
+        else:  # results must be rebased to the global numbering before they leave the device
+            st = lib.c2a_emitted_build_circuit_device(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
+                                                      vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+            if st != 0:
+                raise RuntimeError(f"c2a_emitted_build_circuit_device -> {st}: {ctx.last_error()}")
+            reconcile()
+            with torch.cuda.stream(stream):
+                p_order.copy_(d_order, non_blocking=True)
+                p_wire.copy_(d_wire, non_blocking=True)
+                p_new.copy_(d_new, non_blocking=True)
+            stream.synchronize()
 
-    e2e_step()  # warm
-    emit_s.clear()
+    for _ in range(2):
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(Ke):
         e2e_step()
     barrier()
     dt = time.perf_counter() - t0
+    e2e_phases = {"emit": ctx.phases()} if world > 1 else {"build": ctx.phases()}
     tt = torch.tensor([dt], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     dt = float(tt.item())
     e2e_value = world * G * Ke / dt
-    backend_ms = ctx.phases().get("total", 0.0)
     stop.set()
     th.join(timeout=2)
 
-    # parity spot check of the resident result against the e2e (host-buffer) result
-    assert np.array_equal(d_order.cpu().numpy(), p_order.numpy()), "device-resident and host-buffer paths disagree"
+    # parity spot checks: resident vs host-buffer results; device emitter vs the product's host union-find emitter
+    assert np.array_equal(order_dev, p_order.numpy().astype(np.uint32)), "device-resident and host-buffer paths disagree"
+    host_emit = {}
+    if not args.no_host_emit:
+        t0 = time.perf_counter()
+        comp = c2a.Compiler(context=ctx)
+        comp.emit_events(wl.events)
+        gates_h = comp.gate_array()
+        host_emit["emit_s"] = time.perf_counter() - t0
+        ins_n, outs_n = comp.signal_nodes(in_ids), comp.signal_nodes(out_ids)
+        t1 = time.perf_counter()
+        o2, w2, g2, wc2 = ctx.build_circuit(gates_h, comp.node_count + 1, ins_n, outs_n)
+        host_emit["build_s"] = time.perf_counter() - t1
+        host_emit["gates_per_s"] = G / (time.perf_counter() - t0)
+        st = lib.c2a_emit_events_device(h, vp(p_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        ctx._emit_info = {"n_gates": G, "signal_bound": int(info.signal_bound)}
+        gates_d, _ = ctx.emitted_fetch(want_nodes=False)
+        assert np.array_equal(gates_d, gates_h), "device emitter and host emitter disagree on the gate vector"
+        assert np.array_equal(o2 + np.uint32(gate_base), p_order.numpy().astype(np.uint32)), "host-emitter and device-emitter pipelines disagree on the order"
+        del comp
+    else:
+        gates_h = ins_n = outs_n = None
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel
+    # ---- roofline of the dominant kernel (CUDA-event time of the phase, measured live above)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,48 +380,58 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    kern = {k: v / K for k, v in phase_acc.items() if k.startswith("k_")}
+    kern = {k: v / K for k, v in phase_acc.items() if k.split(":")[-1].startswith("k_")}
     dom = max(kern, key=kern.get)
     dom_ms = kern[dom]
-    ab = alg_bytes(dom, G, nb, not n_identity)
+    ab = alg_bytes(dom, counts)
     achieved = ab / (dom_ms * 1e-3) / 1e9
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom.split(":")[-1])
     except Exception:
         pass
-    all_bytes = sum(alg_bytes(k, G, nb, not n_identity) for k in list(kern) + ["init"])
-    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+    inits = {k: v / K for k, v in phase_acc.items() if k.split(":")[-1] == "init"}
+    all_bytes = sum(alg_bytes(k, counts) for k in list(kern) + list(inits))
+    roof = {"bound": "hbm", "kernel": dom.split(":")[-1], "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
             "peak_source": peak_src, "frac_of_nominal_8000": achieved / 8000.0, "alg_bytes_per_launch": ab, "kernel_ms": dom_ms,
             "kernel_share_of_step": dom_ms / ms_per_step,
-            "per_kernel_ms": {k: round(v, 5) for k, v in sorted({**kern, "init": phase_acc.get("init", 0) / K}.items())},
-            "per_kernel_gbs": {k: round(alg_bytes(k, G, nb, not n_identity) / (v * 1e-3) / 1e9, 1) for k, v in kern.items() if v > 0},
-            "whole_step_gbs": all_bytes / (ms_per_step * 1e-3) / 1e9}
+            "per_kernel_ms": {k: round(v, 5) for k, v in sorted({**kern, **inits}.items())},
+            "per_kernel_gbs": {k: round(alg_bytes(k, counts) / (v * 1e-3) / 1e9, 1) for k, v in sorted(kern.items()) if v > 0},
+            "whole_step_gbs": all_bytes / (ms_per_step * 1e-3) / 1e9, "whole_step_alg_bytes": all_bytes}
 
+    h2d = 16 * n_ev + 4 * (len(in_ids) + len(out_ids)) + 4 * 16 * 3
+    d2h = 4 * G + 4 * nb + 16 * G + 4 * 16 * 6
     out = {
         "metric": metric, "value": value, "unit": "gates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name, "gates_per_gpu": int(G), "node_bound": int(nb), "n_inputs": int(len(ins)), "n_outputs": int(len(outs)),
-                   "order_is_identity": n_identity, "events_per_gpu": int(events.shape[0]),
-                   "l2": "inputs larger than L2 (gate array %.0f MB + node arrays %.0f MB each vs 126 MB L2); no flush" % (16 * G / 1e6, 4 * nb / 1e6),
-                   "value_scope": "c2a_build_circuit_device on HBM-resident gates: producer map, deps, DFS-order reconstruction, wire numbering, gather",
-                   "e2e_scope": "host event stream -> c2a_emit_events (host union-find) -> c2a_get_gates -> c2a_build_circuit with pinned host buffers",
+        "config": {"workload": workload_name, "gates_per_gpu": int(G), "node_bound": int(nb), "n_inputs": int(len(in_ids)), "n_outputs": int(len(out_ids)),
+                   "events_per_gpu": n_ev, "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
+                   "boruvka_rounds": int(info.rounds), "order_is_identity": n_identity,
+                   "l2": "inputs larger than L2 (event stream %.0f MB, gate array %.0f MB, node arrays %.0f MB each vs 126 MB L2); no flush" % (16 * n_ev / 1e6, 16 * G / 1e6, 4 * nb / 1e6),
+                   "value_scope": "event stream resident in HBM -> c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "
+                                  "c2a_emitted_build_circuit_device (producer map, deps, DFS-order reconstruction, wire numbering, gather); results stay in HBM",
+                   "e2e_scope": "event stream in pinned host memory -> c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
+                                "(order, wire_of_node, new_gates D2H inside)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts + wire rebase"},
         "roofline": roof,
-        "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(16 * G + 8 * (len(ins) + len(outs)) + 64),
-                "d2h_bytes_per_step": int(4 * G + 4 * nb + 16 * G + 16), "steps": Ke, "s_per_step": dt / Ke,
-                "emit_s_per_step": float(np.mean(emit_s)), "backend_device_ms_last_step": backend_ms,
-                "backend_only_gates_per_s": world * G / max(dt / Ke - float(np.mean(emit_s)), 1e-9)},
+        "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke, "s_per_step": dt / Ke,
+                "last_call_phases_ms": {k: {kk: round(vv, 3) for kk, vv in v.items()} for k, v in e2e_phases.items()}},
         "gpu_launches": int(launches),
         "clocks": summarize_clocks(clk_lines),
     }
+    if host_emit:
+        out["e2e_host_emitter"] = {"value": host_emit["gates_per_s"], "unit": "gates/s", "emit_s": host_emit["emit_s"], "build_s": host_emit["build_s"],
+                                   "note": "same circuit through the host union-find emitter (c2a_emit_events + c2a_build_circuit), pageable buffers, 1 step"}
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_measure(c2a, None, args.sample_chains, args.variant, args.rounds, backend_gates=(gates_h, ins, outs))
+        r = cpu_reference_measure(c2a, None, args.sample_chains, args.variant, args.rounds,
+                                  backend_gates=(gates_h, ins_n, outs_n) if gates_h is not None else None)
         out["cpu_baseline"] = {
             "value": r["gates_per_s"], "unit": "gates/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
             "sample": (f"first {args.sample_chains} chains ({r['sample_gates']} gates): faithful O(G*S) emit {r['emit_s']:.2f}s + HashMap/DFS back end "
-                       f"{r['backend_s']*1e3:.1f}ms; plus the back end alone on the full {r['backend_only_full_gates']} gates"),
-            "emit_s": r["emit_s"], "backend_s": r["backend_s"], "backend_only_gates_per_s": r["backend_only_gates_per_s"]}
+                       f"{r['backend_s']*1e3:.1f}ms" + (f"; plus the back end alone on the full {r['backend_only_full_gates']} gates" if "backend_only_full_gates" in r else "")),
+            "emit_s": r["emit_s"], "backend_s": r["backend_s"]}
+        if "backend_only_gates_per_s" in r:
+            out["cpu_baseline"]["backend_only_gates_per_s"] = r["backend_only_gates_per_s"]
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

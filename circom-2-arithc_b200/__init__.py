@@ -8,3 +8,4 @@ through the repo-root helper:  ``from c2a_loader import c2a``.
 from ._lib import lib, load_error, C2AError, CircuitError, Status, have_device  # noqa: F401
 from .compiler import AGateType, Compiler, BristolCircuit, Gate, DeviceContext, topological_sort  # noqa: F401
 from . import workloads  # noqa: F401
+from . import sharding  # noqa: F401

@@ -82,6 +82,7 @@ _SIGS = {
     "c2a_build_circuit": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_build_circuit_device": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_rebase_wires_device": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, u32, u32]),
+    "c2a_rebase_wire_map_device": (i32, [vp, vp, u64, u32, u32, u32, u32, u32]),
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),

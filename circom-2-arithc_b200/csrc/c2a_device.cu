@@ -461,6 +461,14 @@ __global__ void __launch_bounds__(kBlock) k_rebase(uint4* __restrict__ new_gates
   }
 }
 
+__global__ void __launch_bounds__(kBlock) k_rebase_map(uint32_t* __restrict__ wire, uint32_t n, uint32_t n_in, uint32_t n_mid, uint32_t off_in,
+                                                       uint32_t off_mid, uint32_t off_out) {
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t w = wire[i];
+    if (w != kNone) wire[i] = w < n_in ? w + off_in : (w < n_in + n_mid ? w + off_mid : w + off_out);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host-side plumbing
 // ---------------------------------------------------------------------------------------------------
@@ -905,6 +913,17 @@ int c2a_rebase_wires_device(c2a_handle* h, c2a_gate* d_new_gates, uint32_t* d_or
   if (!d_new_gates) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
   if (G) LAUNCH(h, k_rebase, grid_for(h, (const void*)k_rebase, kBlock, G), kBlock, (uint4*)d_new_gates, d_order, (uint32_t)G, n_in, n_mid, off_in, off_mid, off_out, gate_base);
   if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "rebase")) return C2A_ERR_CUDA;
+  return C2A_OK;
+}
+
+int c2a_rebase_wire_map_device(c2a_handle* h, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid, uint32_t off_in, uint32_t off_mid,
+                               uint32_t off_out) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (n >= kOutPending) return fail(h, C2A_ERR_INVALID_ARGUMENT, "node_bound too large");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  if (n && !d_wire_of_node) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  if (n) LAUNCH(h, k_rebase_map, grid_for(h, (const void*)k_rebase_map, kBlock, n), kBlock, d_wire_of_node, (uint32_t)n, n_in, n_mid, off_in, off_mid, off_out);
+  if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "rebase map")) return C2A_ERR_CUDA;
   return C2A_OK;
 }
 

@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(1024) k_ev_tile_scan(const uint32_t* __restric
 // egates[g]     {op, lhs signal, rhs signal, out signal};  gate_t[g] event index
 // conn[c]       {a, b};  conn_t[c] event index;  conn_sb[c] #signals declared before the connection
 __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, const uint2* __restrict__ tile_base,
-                                                       uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta, uint4* __restrict__ egates,
+                                                       uint32_t S, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta, uint4* __restrict__ egates,
                                                        uint32_t* __restrict__ gate_t, uint2* __restrict__ conn, uint32_t* __restrict__ conn_t,
                                                        uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
   __shared__ uint32_t s_g[8], s_c[8];
@@ -185,10 +185,16 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
         if (old != kNone) f |= EF_DUPLICATE;  // compiler.rs:146-148
         else sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
       } else if (kind == C2A_EV_GATE) {
-        egates[my_g] = make_uint4(e[j].x >> 8, e[j].y, e[j].z, e[j].w);
+        // out-of-range references are flagged and neutralised so that every later kernel stays memory-safe; the flags
+        // are only looked at once, at the end (the stream is then replayed by the host emitter)
+        bool oob = e[j].y >= S || e[j].z >= S || e[j].w >= S;
+        if (oob) f |= EF_UNKNOWN_REF;
+        egates[my_g] = oob ? make_uint4(e[j].x >> 8, 0, 0, 0) : make_uint4(e[j].x >> 8, e[j].y, e[j].z, e[j].w);
         gate_t[my_g] = t;
       } else {
-        conn[my_c] = make_uint2(e[j].y, e[j].z);
+        bool oob = e[j].y >= S || e[j].z >= S;
+        if (oob) f |= EF_UNKNOWN_REF;
+        conn[my_c] = oob ? make_uint2(0, 0) : make_uint2(e[j].y, e[j].z);
         conn_t[my_c] = t;
         conn_sb[my_c] = my_s;
       }
@@ -248,18 +254,35 @@ __device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
   if (*reinterpret_cast<volatile uint32_t*>(p) > v) atomicMin(p, v);  // values only decrease within a round: a stale read costs one RED
 }
 
-// cur == nullptr: first round, the live list is 0..n0-1.  cand[] receives {edge, class of a, class of b, 0}.
+// First round: the live list is every connection, and almost every one is a candidate, so cand[] is written in place
+// (cand[e], kNone in .x for a connection that is already internal) instead of being compacted through one global counter.
+__global__ void __launch_bounds__(kBlock) k_msf_pick_first(const uint2* __restrict__ conn, uint32_t n, uint32_t* __restrict__ parent,
+                                                           uint32_t* __restrict__ best, uint32_t tag, uint4* __restrict__ cand) {
+  for (uint32_t e = blockIdx.x * kBlock + threadIdx.x; e < n; e += gridDim.x * kBlock) {
+    uint2 ab = conn[e];
+    uint4 out = make_uint4(kNone, 0, 0, 0);
+    if (ab.x != ab.y) {  // parent[] is still the identity: the classes are the signals themselves
+      uint32_t val = tag | e;
+      red_min_u32(best + ab.x, val);
+      red_min_u32(best + ab.y, val);
+      out = make_uint4(e, ab.x, ab.y, 0);
+    }
+    cand[e] = out;
+  }
+}
+
+// Later rounds: cur[0..*n_cur) is the live list.  cand[] receives {edge, class of a, class of b, 0}, compacted.
 __global__ void __launch_bounds__(kBlock) k_msf_pick(const uint2* __restrict__ conn, const uint32_t* __restrict__ cur, const uint32_t* __restrict__ n_cur,
-                                                     uint32_t n0, uint32_t* __restrict__ parent, uint32_t* __restrict__ best, uint32_t tag,
+                                                     uint32_t* __restrict__ parent, uint32_t* __restrict__ best, uint32_t tag,
                                                      uint4* __restrict__ cand, uint32_t* __restrict__ n_cand) {
-  const uint32_t n = cur ? *n_cur : n0;
+  const uint32_t n = *n_cur;
   const int lane = threadIdx.x & 31;
   for (uint32_t i0 = blockIdx.x * kBlock + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kBlock) {
     uint32_t i = i0 + lane;
     bool keep = false;
     uint4 out = make_uint4(0, 0, 0, 0);
     if (i < n) {
-      uint32_t e = cur ? cur[i] : i;
+      uint32_t e = cur[i];
       uint2 ab = conn[e];
       uint32_t cu = uf_find(parent, ab.x), cv = uf_find(parent, ab.y);
       if (cu != cv) {  // still joins two classes: candidate; otherwise it is (or became) internal and is dropped
@@ -285,8 +308,9 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
     uint32_t i = i0 + lane;
     bool keep = false;
     uint32_t e = 0;
-    if (i < n) {
-      uint4 c = cand[i];
+    uint4 c = make_uint4(kNone, 0, 0, 0);
+    if (i < n) c = cand[i];
+    if (c.x != kNone) {
       e = c.x;
       uint32_t val = tag | e;
       bool bu = best[c.y] == val, bv = best[c.z] == val;
@@ -339,11 +363,12 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
   f = warp_or(f);
   if ((threadIdx.x & 31) == 0 && f) atomicOr(es + ES_FLAGS, f);
 }
-__global__ void __launch_bounds__(kBlock) k_ev_gates(const uint4* __restrict__ egates, uint32_t G, const uint32_t* __restrict__ nos,
+__global__ void __launch_bounds__(kBlock) k_ev_gates(const uint4* __restrict__ egates, uint32_t G, uint32_t S, const uint32_t* __restrict__ nos,
                                                      uint4* __restrict__ gates) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint4 e = egates[g];
-    stg_stream(gates + g, make_uint4(e.x, __ldg(nos + e.y), __ldg(nos + e.z), __ldg(nos + e.w)));
+    if (S == 0) e.y = e.z = e.w = 0;  // only on a stream that is about to be declined
+    stg_stream(gates + g, S ? make_uint4(e.x, __ldg(nos + e.y), __ldg(nos + e.z), __ldg(nos + e.w)) : make_uint4(e.x, 0, 0, 0));
   }
 }
 // I/O signal ids -> node ids (compiler.rs:327-361 walks nodes; here the caller lists signals)
@@ -545,32 +570,39 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
   phase_end(h);
   const int wide = h->num_sms * 8;
-  phase_begin(h, "k_ev_scatter");
+  phase_begin(h, "k_ev_tile_scan");
   if (tiles) LAUNCH(h, k_ev_tile_scan, 1, 1024, tile_cnt, tiles, tile_base);
-  if (tiles) LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)wide), kBlock, d_ev, n, tiles, tile_base, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
   phase_end(h);
-  phase_begin(h, "k_ev_check");
+  phase_begin(h, "k_ev_scatter");
+  if (tiles) LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)wide), kBlock, d_ev, n, tiles, tile_base, S, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
+  phase_end(h);
+  phase_begin(h, "k_ev_check_gates");
   if (G) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
+  phase_end(h);
+  phase_begin(h, "k_ev_check_conns");
   if (C) LAUNCH(h, k_ev_check_conns, grid_for(h, (const void*)k_ev_check_conns, kBlock, C), kBlock, conn, conn_t, (uint32_t)C, S, sig_t, es);
   phase_end(h);
-  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-  if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
-  flags = hp[ES_FLAGS];
-  if (flags) return decline(flags);
 
   // ---- Boruvka rounds
-  phase_begin(h, "k_msf");
   uint32_t rounds = 0;
   if (C) {
-    const uint32_t* cur_in = nullptr;
     while (true) {
       uint32_t tag = (6u - (rounds % 7u)) << 29;
       if (rounds && (rounds % 7u) == 0) cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);  // tags wrapped: forget the old minima
-      cudaMemsetAsync(es + ES_NCAND, 0, 4, s);
-      LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur_in, es + ES_NCUR, (uint32_t)C, parent, best, tag, cand, es + ES_NCAND);
+      phase_begin(h, "k_msf_pick");
+      if (rounds == 0) {
+        hp[ES_COUNT] = (uint32_t)C;  // every slot of cand[] is written; dead ones carry kNone
+        cudaMemcpyAsync(es + ES_NCAND, hp + ES_COUNT, 4, cudaMemcpyHostToDevice, s);
+        LAUNCH(h, k_msf_pick_first, grid_for(h, (const void*)k_msf_pick_first, kBlock, C), kBlock, conn, (uint32_t)C, parent, best, tag, cand);
+      } else {
+        cudaMemsetAsync(es + ES_NCAND, 0, 4, s);
+        LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur, es + ES_NCUR, parent, best, tag, cand, es + ES_NCAND);
+      }
+      phase_end(h);
       cudaMemsetAsync(es + ES_NCUR, 0, 4, s);
+      phase_begin(h, "k_msf_hook");
       LAUNCH(h, k_msf_hook, wide, kBlock, cand, es + ES_NCAND, parent, best, tag, eff, cur, es + ES_NCUR);
-      cur_in = cur;
+      phase_end(h);
       ++rounds;
       cudaMemcpyAsync(hp, es + ES_NCUR, 8, cudaMemcpyDeviceToHost, s);
       if (!cuda_ok(h, cudaStreamSynchronize(s), "msf sync")) return C2A_ERR_CUDA;
@@ -579,24 +611,31 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     }
     // edges still on the live list when no candidate was hooked cannot exist: hp[1]==0 means every live edge is internal
   }
-  phase_end(h);
 
   // ---- node ids
-  phase_begin(h, "k_ev_nodes");
   {
     uint32_t stiles = scan_tiles(C + 1, kScanItems);
     cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
     cudaMemsetAsync(ticket, 0, 4, s);
     // exclusive scan of eff[0..C) in place; eff[C] receives the total (= effective connections)
+    phase_begin(h, "k_scan_u32");
     if (C) LAUNCH(h, k_scan_u32, scan_tiles(C, kScanItems), kBlock, eff, (uint32_t)C, tile_state, ticket);
+    phase_end(h);
   }
+  phase_begin(h, "init");
   cudaMemsetAsync(best, 0, 4 * (size_t)S, s);  // reused as cnt[]
+  phase_end(h);
+  phase_begin(h, "k_ev_nid_init");
   if (S) LAUNCH(h, k_ev_nid_init, grid_for(h, (const void*)k_ev_nid_init, kBlock, S), kBlock, S, sig_t, sig_meta, eff, nid);
+  phase_end(h);
+  phase_begin(h, "k_ev_nid_edges");
   if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, parent, nid);
+  phase_end(h);
+  phase_begin(h, "k_ev_finalize");
   if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, sig_t, sig_meta, outmark, parent, nid, best, nos, es);
   phase_end(h);
   phase_begin(h, "k_ev_gates");
-  if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, nos, d_gates);
+  if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
   phase_end(h);
   cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
   cudaMemcpyAsync(hp + ES_COUNT, eff + C, 4, cudaMemcpyDeviceToHost, s);

@@ -126,6 +126,10 @@ int c2a_build_circuit_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, u
 int c2a_rebase_wires_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, uint32_t n_in, uint32_t n_mid,
                             uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base);
 
+/* same mapping applied to a node-indexed wire map (entries equal to C2A_NONE are left alone) */
+int c2a_rebase_wire_map_device(c2a_handle*, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid,
+                               uint32_t off_in, uint32_t off_mid, uint32_t off_out);
+
 /* Level-synchronous Kahn frontier over the same dependency relation (not the reference order; used for the
  * layer-wise sweeps and the evaluator).  level_order[G] is level-major; level_off[*n_levels+1] delimits levels
  * (caller provides capacity level_cap+1; more levels than level_cap -> C2A_ERR_INVALID_ARGUMENT).
