@@ -190,6 +190,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback on the sort path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL writes its version banner / debug lines to STDOUT by default; rank 0's stdout must be the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = c2a.lib
     ctx = c2a.DeviceContext(local_rank)
