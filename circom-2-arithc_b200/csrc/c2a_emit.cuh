@@ -35,7 +35,7 @@ struct c2a_compiler;
 namespace c2a {
 
 constexpr int kEvTile = 1024;  // events per CTA pass: 8 warps x 4 rows x 32 lanes
-enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_COUNT = 16 };
+enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_COUNT = 16 };
 enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128 };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
@@ -180,10 +180,11 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
       uint32_t t = (uint32_t)i;
       uint32_t my_s = t - my_g - my_c;  // signals declared before this event
       if (kind <= C2A_EV_SIGNAL_CONST) {
+        // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the
+        // number of declared ids then falls short of the number of signal events (k_ev_nid_init counts them)
         uint32_t sid = e[j].y;
-        uint32_t old = atomicCAS(sig_t + sid, kNone, t);
-        if (old != kNone) f |= EF_DUPLICATE;  // compiler.rs:146-148
-        else sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
+        sig_t[sid] = t;
+        sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
       } else if (kind == C2A_EV_GATE) {
         // out-of-range references are flagged and neutralised so that every later kernel stays memory-safe; the flags
         // are only looked at once, at the end (the stream is then replayed by the host emitter)
@@ -325,15 +326,19 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
 
 // ---- N: node ids ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_ev_nid_init(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
-                                                        const uint32_t* __restrict__ effx, uint32_t* __restrict__ nid) {
+                                                        const uint32_t* __restrict__ effx, uint32_t* __restrict__ nid, uint32_t* __restrict__ es) {
+  uint32_t declared = 0;
   for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
     uint32_t id = 0;
     if (sig_t[s] != kNone) {
       uint2 m = sig_meta[s];
       id = (m.x & 0x7FFFFFFFu) + 1u + __ldg(effx + m.y);  // compiler.rs:157 with node_count = signals + effective merges so far
+      ++declared;
     }
     nid[s] = id;
   }
+  declared = warp_sum(declared);
+  if ((threadIdx.x & 31) == 0 && declared) atomicAdd(es + ES_NDECL, declared);
 }
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
                                                          const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint32_t* __restrict__ nid) {
@@ -626,7 +631,7 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   cudaMemsetAsync(best, 0, 4 * (size_t)S, s);  // reused as cnt[]
   phase_end(h);
   phase_begin(h, "k_ev_nid_init");
-  if (S) LAUNCH(h, k_ev_nid_init, grid_for(h, (const void*)k_ev_nid_init, kBlock, S), kBlock, S, sig_t, sig_meta, eff, nid);
+  if (S) LAUNCH(h, k_ev_nid_init, grid_for(h, (const void*)k_ev_nid_init, kBlock, S), kBlock, S, sig_t, sig_meta, eff, nid, es);
   phase_end(h);
   phase_begin(h, "k_ev_nid_edges");
   if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, parent, nid);
@@ -642,6 +647,7 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaGetLastError(), "emit kernels")) return C2A_ERR_CUDA;
   flags = hp[ES_FLAGS];
+  if (hp[ES_NDECL] != n_sig) flags |= EF_DUPLICATE;  // fewer distinct ids than signal events
   if (flags) return decline(flags);
   const uint32_t n_eff = C ? hp[ES_COUNT] : 0u;
 
