@@ -21,6 +21,7 @@ class Status(enum.IntEnum):
     CANNOT_MERGE_CONSTANT_NODES = 5
     REFERENCE_PANIC = 6
     INVALID_ARGUMENT = 7
+    EVALUATION = 8
     CUDA = -1
     NO_MEMORY = -2
 
@@ -86,6 +87,7 @@ _SIGS = {
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),
+    "c2a_evaluate": (i32, [vp, vp, u64, u32, vp, vp, u64p]),
     "c2a_emit_events_device": (i32, [vp, vp, u64, vp, u64p]),
     "c2a_emit_events_resident": (i32, [vp, vp, u64, vp, u64p]),
     "c2a_emitted_fetch": (i32, [vp, vp, vp]),

@@ -187,6 +187,24 @@ class DeviceContext:
         return cm, cval, dm
 
 
+    def evaluate(self, gates: np.ndarray, wire_count: int, values: Dict[int, int]) -> Dict[int, int]:
+        """c2a_evaluate: run a built circuit (wire-id gates in executable order) on u32 values, level-parallel on the GPU.
+        values: wire -> u32 for inputs and constants.  Returns wire -> value for every wire that holds one."""
+        g = _as_gates(gates)
+        vals = np.zeros(max(wire_count, 1), dtype=np.uint32)
+        has = np.zeros(max(wire_count, 1), dtype=np.uint8)
+        for k, v in values.items():
+            vals[k] = v & 0xFFFFFFFF
+            has[k] = 1
+        err = C.c_uint64(0)
+        st = lib.c2a_evaluate(self._h, _ptr(g), g.shape[0], wire_count, _ptr(vals), _ptr(has), C.byref(err))
+        if st == Status.EVALUATION:
+            e = C2AError(st, self.last_error())
+            e.err_index = err.value
+            raise e
+        _raise(st, self.last_error())
+        return {int(i): int(vals[i]) for i in np.nonzero(has[:wire_count])[0]}
+
     # ---- device emitter: the event stream is replayed on the GPU and the result stays resident ----
     def emit_events(self, events: np.ndarray) -> dict:
         """c2a_emit_events_device: add_signal / add_gate / add_connection (src/compiler.rs:139-278) for a whole event

@@ -195,6 +195,7 @@ const char* c2a_status_string(int st) {
     case C2A_ERR_CANNOT_MERGE_CONSTANT_NODES: return "Cannot merge constant nodes";  // :552
     case C2A_ERR_REFERENCE_PANIC: return "reference panics here";
     case C2A_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case C2A_ERR_EVALUATION: return "evaluation failed";
     case C2A_ERR_CUDA: return "CUDA error";
     case C2A_ERR_NO_MEMORY: return "out of device memory";
   }

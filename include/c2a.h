@@ -50,6 +50,8 @@ typedef enum {
                                           (compiler.rs:201 unwrap) or a constant whose node never got a
                                           wire (compiler.rs:473 index) */
   C2A_ERR_INVALID_ARGUMENT = 7,
+  C2A_ERR_EVALUATION = 8,              /* c2a_evaluate: a gate reads a wire without a value or divides by zero (the reference's
+                                          test-side executor panics there, tests/integration.rs:90-119) */
   C2A_ERR_CUDA = -1,                   /* CUDA runtime / launch failure, or no device */
   C2A_ERR_NO_MEMORY = -2
 } c2a_status;
@@ -149,6 +151,14 @@ int c2a_sweep_masks(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t nod
                     const uint32_t* const_nodes, const uint32_t* const_values, uint32_t n_const,
                     const uint32_t* output_nodes, uint32_t n_out,
                     uint8_t* const_mask, uint32_t* const_value, uint8_t* dead_mask, uint64_t* err_index);
+
+/* u32 circuit evaluator (restates the reference's test-side simulator, tests/integration.rs:90-119, release-build
+ * semantics: add/sub/mul/pow wrap, shifts by >= 32 give 0, division by zero fails).  gates[G] are in WIRE ids and in an
+ * executable order (what build_circuit returns); values[wire_count] / has[wire_count] carry the initial assignment in
+ * (inputs + constants) and every wire's value out.  The circuit must be single-assignment (else INVALID_ARGUMENT).
+ * Evaluated level by level on the device; on C2A_ERR_EVALUATION *err_index = the position of the first gate the
+ * straight-line executor would fail at, and the contents of values/has are unspecified. */
+int c2a_evaluate(c2a_handle*, const c2a_gate* gates, uint64_t G, uint32_t wire_count, uint32_t* values, uint8_t* has, uint64_t* err_index);
 
 /* ---- emit side (device).  The whole event stream is replayed on the GPU: add_signal / add_gate / add_connection
  * (src/compiler.rs:139-278) with the reference's node-id allocation reproduced exactly (effective connections =
