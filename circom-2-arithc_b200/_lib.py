@@ -115,6 +115,20 @@ _SIGS = {
     "c2a_get_signals_by_prefix": (u64, [vp, cp, vp, u64]),
     "c2a_num_nodes": (u64, [vp]),
     "c2a_get_nodes": (i32, [vp, vp, vp, vp, vp]),
+    "c2a_signal_value": (i32, [vp, u32, C.POINTER(i32), u32p]),
+    "c2a_program_new": (vp, []),
+    "c2a_program_free": (None, [vp]),
+    "c2a_program_compile_file": (i32, [vp, cp, vp]),
+    "c2a_program_compile_source": (i32, [vp, cp, cp, vp]),
+    "c2a_program_error": (cp, [vp]),
+    "c2a_program_num_events": (u64, [vp]),
+    "c2a_program_events": (vp, [vp]),
+    "c2a_program_num_signals": (u64, [vp]),
+    "c2a_program_signal_name": (cp, [vp, u32]),
+    "c2a_program_num_inputs": (u32, [vp]),
+    "c2a_program_num_outputs": (u32, [vp]),
+    "c2a_program_inputs": (vp, [vp]),
+    "c2a_program_outputs": (vp, [vp]),
     "c2a_compiler_build_circuit": (i32, [vp, vp]),
     "c2a_circuit_wire_count": (u64, [vp]),
     "c2a_circuit_order": (vp, [vp]),

@@ -380,6 +380,16 @@ class Compiler:
     def set_signal_name(self, id: int, name: str):
         _raise(lib.c2a_set_signal_name(self._c, id, name.encode()), "unknown signal")
 
+    def signal_value(self, id: int) -> Optional[int]:
+        has, val = C.c_int(0), C.c_uint32(0)
+        if lib.c2a_signal_value(self._c, id, C.byref(has), C.byref(val)) != 0 or not has.value:
+            return None
+        return int(val.value)
+
+    def generate_circuit_report(self) -> dict:  # src/compiler.rs:287-319
+        from .program import generate_circuit_report
+        return generate_circuit_report(self)
+
     def signal_name(self, id: int) -> Optional[str]:
         buf = C.create_string_buffer(512)
         n = lib.c2a_signal_name(self._c, id, buf, 512)

@@ -1,0 +1,985 @@
+// c2a_front.cpp — circom-subset front end + AST walker: host C++ restatement of
+//   src/program.rs::compile (:18-74), src/process.rs (:22-764) and the parts of src/runtime.rs (:56-793) the walk needs.
+// The reference parses with the iden3/circom crates (@ e8e125e, not in its tree); this file parses the subset the
+// reference accepts (README.md:16-40) with a hand-written lexer / recursive-descent parser that applies the same
+// desugaring the circom parser does (for -> while, `x++` / `x += e` -> `x = x + ...`, `a ==> b` -> `b <== a`,
+// declarations with initialisers -> declaration + substitution).  The contract is the ORDER of add_signal / add_gate /
+// add_connection calls and the signal ids / names they carry.
+//
+// Runtime model.  The reference deep-clones the whole Context for every `while` iteration / `if` body and merges
+// variables and components back on exit (runtime.rs:151-187).  That is observationally a lexical scope: items declared
+// inside are dropped, writes to items that already existed persist (a re-declared variable overwrites the outer one,
+// :175-178), the return variable is always carried out (:180-184).  Here: one hash map per call frame plus a scope
+// stack of declared names - O(1) per push instead of O(context).  Template / function calls start an empty frame
+// (runtime.rs:75-77).  Temporaries (`random_<u32>` items, :229) are values, not map entries; temporary SIGNALS still
+// consume signal ids and are named "<ctx>.random_<id>" (the reference's suffix is a thread_rng draw, i.e. unspecified).
+// u32 arithmetic on variables follows a release build: + * ** wrap, shifts use the low 5 bits, - / \ % error as in
+// src/process.rs:649-750.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <functional>
+#include <map>
+#include <memory>
+#include <optional>
+#include <set>
+#include <sstream>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/c2a.h"
+
+namespace front {
+
+struct Error {
+  int code;
+  std::string text;
+};
+[[noreturn]] static void fail(int code, const std::string& text) { throw Error{code, text}; }
+static void runtime_error(const std::string& what) { fail(C2A_PROG_RUNTIME_ERROR, "Runtime error: " + what); }
+
+// ======================================================================================================= lexer
+enum Tok { T_EOF, T_ID, T_NUM, T_STR, T_OP };
+struct Token {
+  Tok t;
+  std::string s;
+  int line;
+};
+
+static std::vector<Token> lex(const std::string& src) {
+  static const char* ops[] = {"<<=", ">>=", "**=", "<==", "==>", "<--", "-->", "===", "&&", "||", "==", "!=", "<=", ">=", "<<", ">>", "**", "+=", "-=", "*=",
+                              "/=", "\\=", "%=", "|=", "&=", "^=", "++", "--", nullptr};
+  std::vector<Token> out;
+  size_t i = 0, n = src.size();
+  int line = 1;
+  while (i < n) {
+    char c = src[i];
+    if (c == '\n') { ++line; ++i; continue; }
+    if (isspace((unsigned char)c)) { ++i; continue; }
+    if (c == '/' && i + 1 < n && src[i + 1] == '/') { while (i < n && src[i] != '\n') ++i; continue; }
+    if (c == '/' && i + 1 < n && src[i + 1] == '*') {
+      i += 2;
+      while (i + 1 < n && !(src[i] == '*' && src[i + 1] == '/')) { if (src[i] == '\n') ++line; ++i; }
+      i += 2;
+      continue;
+    }
+    if (isalpha((unsigned char)c) || c == '_' || c == '$') {
+      size_t j = i;
+      while (j < n && (isalnum((unsigned char)src[j]) || src[j] == '_' || src[j] == '$')) ++j;
+      out.push_back({T_ID, src.substr(i, j - i), line});
+      i = j;
+      continue;
+    }
+    if (isdigit((unsigned char)c)) {
+      size_t j = i;
+      if (c == '0' && j + 1 < n && (src[j + 1] == 'x' || src[j + 1] == 'X')) { j += 2; while (j < n && isxdigit((unsigned char)src[j])) ++j; }
+      else while (j < n && isdigit((unsigned char)src[j])) ++j;
+      out.push_back({T_NUM, src.substr(i, j - i), line});
+      i = j;
+      continue;
+    }
+    if (c == '"') {
+      size_t j = i + 1;
+      while (j < n && src[j] != '"') { if (src[j] == '\\') ++j; ++j; }
+      out.push_back({T_STR, src.substr(i + 1, j - i - 1), line});
+      i = j + 1;
+      continue;
+    }
+    bool matched = false;
+    for (int k = 0; ops[k]; ++k) {
+      size_t L = strlen(ops[k]);
+      if (src.compare(i, L, ops[k]) == 0) { out.push_back({T_OP, ops[k], line}); i += L; matched = true; break; }
+    }
+    if (matched) continue;
+    out.push_back({T_OP, std::string(1, c), line});
+    ++i;
+  }
+  out.push_back({T_EOF, "", line});
+  return out;
+}
+
+// ========================================================================================================= AST
+// ExpressionInfixOpcode in the order of c2a_gate_type via src/a_gate_type.rs:30-55
+enum Infix { I_Mul, I_Div, I_Add, I_Sub, I_Pow, I_IntDiv, I_Mod, I_ShiftL, I_ShiftR, I_LesserEq, I_GreaterEq, I_Lesser, I_Greater, I_Eq, I_NotEq, I_BoolOr,
+             I_BoolAnd, I_BitOr, I_BitAnd, I_BitXor };
+static const uint32_t kGateOf[] = {C2A_AMul, C2A_ADiv, C2A_AAdd, C2A_ASub, C2A_APow, C2A_AIntDiv, C2A_AMod, C2A_AShiftL, C2A_AShiftR, C2A_ALEq, C2A_AGEq,
+                                   C2A_ALt, C2A_AGt, C2A_AEq, C2A_ANeq, C2A_ABoolOr, C2A_ABoolAnd, C2A_ABitOr, C2A_ABitAnd, C2A_AXor};
+enum Prefix { P_Sub, P_BoolNot, P_Complement };
+
+struct Expr;
+using ExprP = std::shared_ptr<Expr>;
+struct Access {
+  bool component;    // .name  vs  [expr]
+  std::string name;
+  ExprP index;
+};
+struct Expr {
+  enum Kind { Number, Variable, InfixOp, PrefixOp, Call, Unsupported } kind = Unsupported;
+  std::string text;            // Number: literal; Variable/Call: name
+  std::vector<Access> access;  // Variable
+  int op = 0;
+  ExprP l, r;
+  std::vector<ExprP> args;
+};
+enum AssignOp { A_Var, A_Signal, A_ConstraintSignal };  // =  <--  <==
+enum DataType { D_Variable, D_Signal, D_Component };
+struct Stmt;
+using StmtP = std::shared_ptr<Stmt>;
+struct Stmt {
+  enum Kind { Block, InitBlock, Substitution, Declaration, IfThenElse, While, Return, Assert, Unsupported } kind = Unsupported;
+  std::vector<StmtP> stmts;    // Block / InitBlock
+  std::string name;            // Substitution var / Declaration name
+  std::vector<Access> access;  // Substitution
+  AssignOp op = A_Var;
+  ExprP e;                     // rhe / cond / value / arg
+  DataType dtype = D_Variable;  // Declaration
+  int sigkind = 0;             // 0 intermediate, 1 input, 2 output
+  std::vector<ExprP> dims;
+  StmtP a, b;                  // if / else / while body
+};
+struct Callable {
+  bool is_function = false;
+  std::vector<std::string> params;
+  std::vector<StmtP> body;
+  std::vector<std::string> inputs, outputs;  // templates: declared input / output signal names
+};
+struct Program {
+  std::map<std::string, Callable> defs;
+  ExprP main;
+};
+
+// ====================================================================================================== parser
+struct Parser {
+  std::vector<Token> t;
+  size_t p = 0;
+  std::string file;
+  explicit Parser(std::vector<Token> toks, std::string f) : t(std::move(toks)), file(std::move(f)) {}
+
+  const Token& cur() const { return t[p]; }
+  [[noreturn]] void err(const std::string& what) const {
+    fail(C2A_PROG_PARSING_ERROR, "Parsing error: " + file + ":" + std::to_string(cur().line) + ": " + what + " near '" + cur().s + "'");
+  }
+  bool is_op(const char* s) const { return cur().t == T_OP && cur().s == s; }
+  bool is_id(const char* s) const { return cur().t == T_ID && cur().s == s; }
+  bool accept_op(const char* s) { if (is_op(s)) { ++p; return true; } return false; }
+  bool accept_id(const char* s) { if (is_id(s)) { ++p; return true; } return false; }
+  void expect_op(const char* s) { if (!accept_op(s)) err(std::string("expected '") + s + "'"); }
+  std::string ident() { if (cur().t != T_ID) err("expected identifier"); return t[p++].s; }
+
+  // ---- expressions: precedence of circom's grammar (lowest first): ?: || && cmp | ^ & shift +- */\% ** prefix
+  ExprP mk_infix(int op, ExprP l, ExprP r) { auto e = std::make_shared<Expr>(); e->kind = Expr::InfixOp; e->op = op; e->l = l; e->r = r; return e; }
+  ExprP expr() { return ternary(); }
+  ExprP ternary() {
+    ExprP c = level(0);
+    if (accept_op("?")) {  // InlineSwitchOp: parsed, rejected by the walker (src/process.rs:310)
+      ExprP a = ternary();
+      expect_op(":");
+      ExprP b = ternary();
+      auto e = std::make_shared<Expr>();
+      e->kind = Expr::Unsupported;
+      e->text = "InlineSwitchOp";
+      return e;
+    }
+    return c;
+  }
+  ExprP level(int lv) {
+    static const std::vector<std::vector<std::pair<const char*, int>>> L = {
+        {{"||", I_BoolOr}}, {{"&&", I_BoolAnd}},
+        {{"==", I_Eq}, {"!=", I_NotEq}, {"<=", I_LesserEq}, {">=", I_GreaterEq}, {"<", I_Lesser}, {">", I_Greater}},
+        {{"|", I_BitOr}}, {{"^", I_BitXor}}, {{"&", I_BitAnd}}, {{"<<", I_ShiftL}, {">>", I_ShiftR}}, {{"+", I_Add}, {"-", I_Sub}},
+        {{"*", I_Mul}, {"/", I_Div}, {"\\", I_IntDiv}, {"%", I_Mod}}, {{"**", I_Pow}}};
+    if (lv == (int)L.size()) return prefix();
+    ExprP l = level(lv + 1);
+    while (true) {
+      bool hit = false;
+      for (auto& o : L[lv])
+        if (is_op(o.first)) { ++p; l = mk_infix(o.second, l, level(lv + 1)); hit = true; break; }
+      if (!hit) return l;
+    }
+  }
+  ExprP prefix() {
+    int op = -1;
+    if (is_op("-")) op = P_Sub; else if (is_op("!")) op = P_BoolNot; else if (is_op("~")) op = P_Complement;
+    if (op >= 0) {
+      ++p;
+      auto e = std::make_shared<Expr>();
+      e->kind = Expr::PrefixOp;
+      e->op = op;
+      e->r = prefix();
+      return e;
+    }
+    return term();
+  }
+  std::vector<Access> accesses() {
+    std::vector<Access> a;
+    while (true) {
+      if (accept_op("[")) { Access x{false, "", expr()}; expect_op("]"); a.push_back(x); }
+      else if (is_op(".") ) { ++p; a.push_back(Access{true, ident(), nullptr}); }
+      else return a;
+    }
+  }
+  ExprP term() {
+    auto e = std::make_shared<Expr>();
+    if (cur().t == T_NUM) { e->kind = Expr::Number; e->text = t[p++].s; return e; }
+    if (accept_op("(")) { ExprP in = expr(); expect_op(")"); return in; }
+    if (accept_op("[")) {  // ArrayInLine: parsed, rejected by the walker
+      if (!is_op("]")) { expr(); while (accept_op(",")) expr(); }
+      expect_op("]");
+      e->text = "ArrayInLine";
+      return e;
+    }
+    if (cur().t == T_ID) {
+      if (is_id("parallel")) { ++p; ExprP in = term(); (void)in; e->text = "ParallelOp"; return e; }
+      std::string name = ident();
+      if (accept_op("(")) {
+        e->kind = Expr::Call;
+        e->text = name;
+        if (!is_op(")")) { e->args.push_back(expr()); while (accept_op(",")) e->args.push_back(expr()); }
+        expect_op(")");
+        if (is_op("(")) {  // anonymous component T(..)(..)
+          int depth = 0;
+          do { if (is_op("(")) ++depth; if (is_op(")")) --depth; ++p; } while (depth > 0 && cur().t != T_EOF);
+          e->kind = Expr::Unsupported;
+          e->text = "AnonymousComp";
+        }
+        return e;
+      }
+      e->kind = Expr::Variable;
+      e->text = name;
+      e->access = accesses();
+      return e;
+    }
+    err("expected expression");
+  }
+
+  // ---- statements
+  StmtP mk(Stmt::Kind k) { auto s = std::make_shared<Stmt>(); s->kind = k; return s; }
+  StmtP block_of(std::vector<StmtP> v) { auto s = mk(Stmt::Block); s->stmts = std::move(v); return s; }
+  StmtP subst(const std::string& var, std::vector<Access> acc, AssignOp op, ExprP rhe) {
+    auto s = mk(Stmt::Substitution);
+    s->name = var; s->access = std::move(acc); s->op = op; s->e = rhe;
+    return s;
+  }
+  ExprP var_expr(const std::string& n, const std::vector<Access>& a) { auto e = std::make_shared<Expr>(); e->kind = Expr::Variable; e->text = n; e->access = a; return e; }
+  ExprP num_expr(const std::string& v) { auto e = std::make_shared<Expr>(); e->kind = Expr::Number; e->text = v; return e; }
+
+  // declaration list -> InitializationBlock [Declaration, (Substitution)]* in symbol order (circom: split_declaration_into_single_nodes)
+  StmtP declaration() {
+    DataType dt;
+    int sigkind = 0;
+    if (accept_id("var")) dt = D_Variable;
+    else if (accept_id("component")) dt = D_Component;
+    else if (accept_id("signal")) {
+      dt = D_Signal;
+      if (accept_id("input")) sigkind = 1; else if (accept_id("output")) sigkind = 2;
+      if (accept_op("{")) { while (!accept_op("}")) { if (cur().t == T_EOF) err("unterminated tag list"); ++p; } }  // tags are ignored
+    } else err("expected declaration");
+    auto init = mk(Stmt::InitBlock);
+    if (is_op("(")) err("tuple declarations are not supported");
+    while (true) {
+      auto d = mk(Stmt::Declaration);
+      d->dtype = dt; d->sigkind = sigkind; d->name = ident();
+      while (accept_op("[")) { d->dims.push_back(expr()); expect_op("]"); }
+      init->stmts.push_back(d);
+      AssignOp op;
+      bool has = true;
+      if (accept_op("=")) op = A_Var; else if (accept_op("<==")) op = A_ConstraintSignal; else if (accept_op("<--")) op = A_Signal; else has = false;
+      if (has) init->stmts.push_back(subst(d->name, {}, op, expr()));
+      if (!accept_op(",")) break;
+    }
+    return init;
+  }
+
+  // expression-statement: substitution in all its spellings
+  StmtP simple_statement() {
+    if (is_id("var") || is_id("signal") || is_id("component")) return declaration();
+    ExprP lhs = expr();
+    static const std::pair<const char*, int> compound[] = {{"+=", I_Add}, {"-=", I_Sub}, {"*=", I_Mul}, {"**=", I_Pow}, {"/=", I_Div}, {"\\=", I_IntDiv},
+                                                           {"%=", I_Mod}, {"|=", I_BitOr}, {"&=", I_BitAnd}, {"^=", I_BitXor}, {"<<=", I_ShiftL}, {">>=", I_ShiftR}};
+    auto need_var = [&](const ExprP& e) { if (e->kind != Expr::Variable) err("left-hand side must be a variable, signal or component access"); };
+    if (accept_op("=")) { need_var(lhs); return subst(lhs->text, lhs->access, A_Var, expr()); }
+    if (accept_op("<==")) { need_var(lhs); return subst(lhs->text, lhs->access, A_ConstraintSignal, expr()); }
+    if (accept_op("<--")) { need_var(lhs); return subst(lhs->text, lhs->access, A_Signal, expr()); }
+    if (accept_op("==>")) { ExprP r = expr(); need_var(r); return subst(r->text, r->access, A_ConstraintSignal, lhs); }
+    if (accept_op("-->")) { ExprP r = expr(); need_var(r); return subst(r->text, r->access, A_Signal, lhs); }
+    if (accept_op("===")) { expr(); auto s = mk(Stmt::Unsupported); s->name = "ConstraintEquality"; return s; }
+    if (accept_op("++")) { need_var(lhs); return subst(lhs->text, lhs->access, A_Var, mk_infix(I_Add, var_expr(lhs->text, lhs->access), num_expr("1"))); }
+    if (accept_op("--")) { need_var(lhs); return subst(lhs->text, lhs->access, A_Var, mk_infix(I_Sub, var_expr(lhs->text, lhs->access), num_expr("1"))); }
+    for (auto& c : compound)
+      if (accept_op(c.first)) { need_var(lhs); return subst(lhs->text, lhs->access, A_Var, mk_infix(c.second, var_expr(lhs->text, lhs->access), expr())); }
+    err("expected an assignment");
+  }
+
+  StmtP statement() {
+    if (accept_op("{")) {
+      std::vector<StmtP> v;
+      while (!accept_op("}")) { if (cur().t == T_EOF) err("unterminated block"); v.push_back(statement()); }
+      return block_of(std::move(v));
+    }
+    if (accept_id("if")) {
+      auto s = mk(Stmt::IfThenElse);
+      expect_op("("); s->e = expr(); expect_op(")");
+      s->a = statement();
+      if (accept_id("else")) s->b = statement();
+      return s;
+    }
+    if (accept_id("while")) {
+      auto s = mk(Stmt::While);
+      expect_op("("); s->e = expr(); expect_op(")");
+      s->a = statement();
+      return s;
+    }
+    if (accept_id("for")) {  // Block[init, While(cond, Block[body, step])]
+      expect_op("(");
+      StmtP init = simple_statement(); expect_op(";");
+      ExprP cond = expr(); expect_op(";");
+      StmtP step = simple_statement(); expect_op(")");
+      StmtP body = statement();
+      auto w = mk(Stmt::While);
+      w->e = cond;
+      w->a = block_of({body, step});
+      return block_of({init, w});
+    }
+    if (accept_id("return")) { auto s = mk(Stmt::Return); s->e = expr(); expect_op(";"); return s; }
+    if (accept_id("assert")) { auto s = mk(Stmt::Assert); expect_op("("); s->e = expr(); expect_op(")"); expect_op(";"); return s; }
+    if (is_id("log")) {
+      ++p; expect_op("(");
+      int depth = 1;
+      while (depth > 0) { if (cur().t == T_EOF) err("unterminated log"); if (is_op("(")) ++depth; if (is_op(")")) --depth; ++p; }
+      expect_op(";");
+      auto s = mk(Stmt::Unsupported); s->name = "LogCall"; return s;
+    }
+    StmtP s = simple_statement();
+    expect_op(";");
+    return s;
+  }
+
+  static void collect_io(const std::vector<StmtP>& body, Callable& c) {
+    for (auto& s : body) {
+      if (!s) continue;
+      if (s->kind == Stmt::Declaration && s->dtype == D_Signal) {
+        if (s->sigkind == 1) c.inputs.push_back(s->name);
+        if (s->sigkind == 2) c.outputs.push_back(s->name);
+      }
+      collect_io(s->stmts, c);
+      if (s->a) collect_io({s->a}, c);
+      if (s->b) collect_io({s->b}, c);
+    }
+  }
+
+  void definitions(Program& prog, const std::function<void(const std::string&)>& include) {
+    while (cur().t != T_EOF) {
+      if (accept_id("pragma")) { while (!accept_op(";")) { if (cur().t == T_EOF) err("unterminated pragma"); ++p; } continue; }
+      if (accept_id("include")) { if (cur().t != T_STR) err("expected a file name"); std::string f = t[p++].s; expect_op(";"); include(f); continue; }
+      if (is_id("template") || is_id("function")) {
+        Callable c;
+        c.is_function = cur().s == "function";
+        ++p;
+        while (is_id("custom") || is_id("parallel")) ++p;
+        std::string name = ident();
+        expect_op("(");
+        if (!is_op(")")) { c.params.push_back(ident()); while (accept_op(",")) c.params.push_back(ident()); }
+        expect_op(")");
+        StmtP b = statement();
+        if (b->kind != Stmt::Block) err("expected a body");
+        c.body = b->stmts;
+        if (!c.is_function) collect_io(c.body, c);
+        prog.defs[name] = std::move(c);
+        continue;
+      }
+      if (accept_id("component")) {
+        if (!accept_id("main")) err("only `component main` is allowed at top level");
+        if (accept_op("{")) { while (!accept_op("}")) { if (cur().t == T_EOF) err("unterminated public list"); ++p; } }
+        expect_op("=");
+        prog.main = expr();
+        expect_op(";");
+        continue;
+      }
+      err("expected template, function, include, pragma or component main");
+    }
+  }
+};
+
+static std::string read_file(const std::string& path) {
+  std::ifstream f(path, std::ios::binary);
+  if (!f) fail(C2A_PROG_PARSING_ERROR, "Parsing error: cannot open " + path);
+  std::stringstream ss;
+  ss << f.rdbuf();
+  return ss.str();
+}
+static std::string dir_of(const std::string& path) {
+  size_t k = path.find_last_of('/');
+  return k == std::string::npos ? std::string(".") : path.substr(0, k);
+}
+static void parse_into(Program& prog, const std::string& src, const std::string& file, const std::string& dir, std::set<std::string>& seen) {
+  Parser ps(lex(src), file);
+  ps.definitions(prog, [&](const std::string& inc) {
+    std::string path = inc.size() && inc[0] == '/' ? inc : dir + "/" + inc;
+    if (path.size() < 7 || path.compare(path.size() - 7, 7, ".circom") != 0) path += ".circom";
+    if (!seen.insert(path).second) return;
+    parse_into(prog, read_file(path), path, dir_of(path), seen);
+  });
+}
+
+// ===================================================================================================== runtime
+template <class T>
+struct Nested {
+  bool is_array = false;
+  std::vector<Nested<T>> arr;
+  T val{};
+};
+using SigTree = Nested<uint32_t>;
+using SigMap = std::map<std::string, SigTree>;
+struct Item {
+  DataType type = D_Variable;
+  Nested<std::optional<uint32_t>> var;
+  SigTree sig;
+  Nested<SigMap> comp;
+};
+struct SubAccess {
+  bool component;
+  uint32_t index;
+  std::string name;
+};
+// result of process_expression: a named item access, or a temporary
+struct Ref {
+  enum Kind { Named, TempVar, TempSignal, TempComp } kind = TempVar;
+  std::string name;
+  std::vector<SubAccess> access;
+  std::optional<uint32_t> value;  // TempVar
+  uint32_t signal = 0;            // TempSignal
+  std::shared_ptr<SigMap> comp;   // TempComp
+};
+static const char* RETURN_VAR = "function_return_value";
+
+template <class T>
+static const Nested<T>& nested_get(const Nested<T>& v, const std::vector<uint32_t>& path) {  // runtime.rs:668-688
+  const Nested<T>* cur = &v;
+  for (uint32_t i : path) {
+    if (!cur->is_array) runtime_error("Access Error");
+    if (i >= cur->arr.size()) runtime_error("Index out of bounds");
+    cur = &cur->arr[i];
+  }
+  return *cur;
+}
+template <class T>
+static Nested<T>& nested_get_mut(Nested<T>& v, const std::vector<uint32_t>& path) {
+  return const_cast<Nested<T>&>(nested_get(const_cast<const Nested<T>&>(v), path));
+}
+template <class T>
+static Nested<T> nested_new(const std::vector<uint32_t>& dims, size_t k, const std::function<T()>& leaf) {
+  Nested<T> n;
+  if (k == dims.size()) { n.val = leaf(); return n; }
+  n.is_array = true;
+  n.arr.reserve(dims[k]);
+  for (uint32_t i = 0; i < dims[k]; ++i) n.arr.push_back(nested_new<T>(dims, k + 1, leaf));
+  return n;
+}
+static std::vector<uint32_t> access_to_u32(const std::vector<SubAccess>& a) {  // runtime.rs:701-710
+  std::vector<uint32_t> v;
+  for (auto& s : a) { if (s.component) runtime_error("Access Error"); v.push_back(s.index); }
+  return v;
+}
+
+struct Frame {
+  std::string ctx_name;
+  std::unordered_map<std::string, Item> items;
+  std::vector<std::vector<std::string>> scopes;  // names declared per open scope
+};
+
+struct Sink {  // where add_signal / add_gate / add_connection go
+  c2a_compiler* into = nullptr;
+  std::vector<c2a_event> events;
+  std::vector<std::string> names;  // by signal id (ids are sequential from 0)
+  void check(int st) {
+    if (st == C2A_OK) return;
+    std::string why = st == C2A_ERR_INVALID_ARGUMENT || st == C2A_ERR_REFERENCE_PANIC ? c2a_compiler_last_error(into) : c2a_status_string(st);
+    fail(C2A_PROG_CIRCUIT_ERROR, "Circuit error: " + why);
+  }
+  void add_signal(uint32_t id, const std::string& name, std::optional<uint32_t> value) {
+    if (names.size() <= id) names.resize((size_t)id + 1);
+    names[id] = name;
+    events.push_back(c2a_event{value ? (uint32_t)C2A_EV_SIGNAL_CONST : (uint32_t)C2A_EV_SIGNAL, id, value.value_or(0), 0});
+    if (into) check(c2a_add_signal(into, id, name.c_str(), value.has_value(), value.value_or(0)));
+  }
+  void add_gate(uint32_t op, uint32_t l, uint32_t r, uint32_t o) {
+    events.push_back(c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), l, r, o});
+    if (into) check(c2a_add_gate(into, op, l, r, o));
+  }
+  void add_connection(uint32_t a, uint32_t b) {
+    events.push_back(c2a_event{(uint32_t)C2A_EV_CONNECT, a, b, 0});
+    if (into) check(c2a_add_connection(into, a, b));
+  }
+};
+
+struct Walker {
+  const Program& prog;
+  Sink& ac;
+  std::vector<Frame> frames;
+  uint32_t next_signal_id = 0;  // runtime.rs:120-125
+  uint64_t depth = 0;
+
+  Walker(const Program& p, Sink& s) : prog(p), ac(s) {
+    frames.push_back(Frame{"0", {}, {{}}});  // runtime.rs:63-68: the root context is named "0"
+  }
+  Frame& ctx() { return frames.back(); }
+
+  // ---- contexts (runtime.rs:71-117, 151-187)
+  void push_scope() { ctx().scopes.emplace_back(); }
+  void pop_scope() {
+    Frame& f = ctx();
+    std::vector<std::string> names = std::move(f.scopes.back());
+    f.scopes.pop_back();
+    for (auto& n : names) {
+      if (n == RETURN_VAR && !f.scopes.empty()) { f.scopes.back().push_back(n); continue; }  // :180-184 forced merge
+      f.items.erase(n);
+    }
+  }
+  void declare_item(DataType type, const std::string& name, const std::vector<uint32_t>& dims) {  // runtime.rs:190-222
+    Frame& f = ctx();
+    auto it = f.items.find(name);
+    if (it != f.items.end() && type != D_Variable) runtime_error("Item already declared");
+    if (it == f.items.end()) f.scopes.back().push_back(name);
+    Item item;
+    item.type = type;
+    if (type == D_Signal) item.sig = nested_new<uint32_t>(dims, 0, [&] { return next_signal_id++; });  // row-major ids, :431-445
+    else if (type == D_Variable) item.var = nested_new<std::optional<uint32_t>>(dims, 0, [] { return std::optional<uint32_t>(); });
+    else item.comp = nested_new<SigMap>(dims, 0, [] { return SigMap(); });
+    f.items[name] = std::move(item);
+  }
+  Item& item(const std::string& name, const char* who) {
+    auto it = ctx().items.find(name);
+    if (it == ctx().items.end()) runtime_error(std::string("Item not declared: ") + who + ": " + name);
+    return it->second;
+  }
+  DataType type_of(const Ref& r) {  // runtime.rs:235-249
+    switch (r.kind) {
+      case Ref::TempVar: return D_Variable;
+      case Ref::TempSignal: return D_Signal;
+      case Ref::TempComp: return D_Component;
+      default: return item(r.name, "get_item_data_type").type;
+    }
+  }
+  std::optional<uint32_t> variable_value(const Ref& r) {  // runtime.rs:296-307
+    if (r.kind == Ref::TempVar) return r.value;
+    if (r.kind != Ref::Named) runtime_error("Item not declared: get_variable_value: " + r.name);
+    Item& it = item(r.name, "get_variable_value");
+    if (it.type != D_Variable) runtime_error("Item not declared: get_variable_value: " + r.name);
+    const auto& n = nested_get(it.var, access_to_u32(r.access));
+    if (n.is_array) runtime_error("Data Item content is not a single value");
+    return n.val;
+  }
+  uint32_t value_or_empty(const Ref& r) {
+    auto v = variable_value(r);
+    if (!v) fail(C2A_PROG_EMPTY_DATA_ITEM, "Empty data item");
+    return *v;
+  }
+  // (component access, signal access) split, runtime.rs:617-663
+  static void split_component_access(const Ref& r, std::vector<uint32_t>& comp_path, std::string& signal, std::vector<uint32_t>& sig_path) {
+    bool has = false;
+    for (auto& s : r.access) {
+      if (!s.component) (has ? sig_path : comp_path).push_back(s.index);
+      else { if (has) runtime_error("Access Error"); signal = s.name; has = true; }
+    }
+    if (!has) runtime_error("Access Error");
+  }
+  const SigTree& component_signal_content(const Ref& r) {  // runtime.rs:389-405, 560-580
+    std::vector<uint32_t> cp, sp;
+    std::string sname;
+    split_component_access(r, cp, sname, sp);
+    const SigMap* map;
+    if (r.kind == Ref::TempComp) { if (!cp.empty()) runtime_error("Access Error"); map = r.comp.get(); }
+    else {
+      Item& it = item(r.name, "get_component_signal_id");
+      if (it.type != D_Component) runtime_error("Item not declared: get_component_signal_id: " + r.name);
+      const auto& n = nested_get(it.comp, cp);
+      if (n.is_array) runtime_error("Data Item content is not a single value");
+      map = &n.val;
+    }
+    auto f = map->find(sname);
+    if (f == map->end()) runtime_error("Item not declared: get_signal_id: " + sname);
+    return nested_get(f->second, sp);
+  }
+  const SigTree& signal_content(const Ref& r) {  // runtime.rs:323-337
+    static thread_local SigTree tmp;
+    if (r.kind == Ref::TempSignal) { tmp = SigTree(); tmp.val = r.signal; return tmp; }
+    Item& it = item(r.name, "get_signal_content");
+    if (it.type != D_Signal) runtime_error("Item not declared: get_signal_content: " + r.name);
+    return nested_get(it.sig, access_to_u32(r.access));
+  }
+  uint32_t signal_id(const Ref& r) {  // runtime.rs:341-355
+    const SigTree& n = signal_content(r);
+    if (n.is_array) runtime_error("Data Item content is not a single value");
+    return n.val;
+  }
+  uint32_t component_signal_id(const Ref& r) {
+    const SigTree& n = component_signal_content(r);
+    if (n.is_array) runtime_error("Data Item content is not a single value");
+    return n.val;
+  }
+  const SigTree& content_for_access(const Ref& r) {  // process.rs:582-591
+    switch (type_of(r)) {
+      case D_Signal: return signal_content(r);
+      case D_Component: return component_signal_content(r);
+      default: fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
+    }
+  }
+  std::string access_str(const std::string& name, const std::vector<uint32_t>& idx) {  // runtime.rs:594-608
+    std::string s = ctx().ctx_name + "." + name;
+    for (uint32_t i : idx) s += "[" + std::to_string(i) + "]";
+    return s;
+  }
+
+  // ---- process.rs
+  uint32_t make_constant(uint32_t value) {  // :558-579 — one constant signal per value per visible context
+    std::string name = "const_signal_" + std::to_string(value);
+    auto it = ctx().items.find(name);
+    if (it != ctx().items.end() && it->second.type == D_Signal && !it->second.sig.is_array) return it->second.sig.val;
+    declare_item(D_Signal, name, {});
+    uint32_t id = ctx().items[name].sig.val;
+    ac.add_signal(id, access_str(name, {}), value);
+    return id;
+  }
+  uint32_t signal_for_access(const Ref& r) {  // :538-556
+    switch (type_of(r)) {
+      case D_Signal: return signal_id(r);
+      case D_Variable: return make_constant(value_or_empty(r));
+      default: return component_signal_id(r);
+    }
+  }
+  Ref temp_signal() {  // declare_random_item(Signal) + add_signal, :464-474
+    Ref r;
+    r.kind = Ref::TempSignal;
+    r.signal = next_signal_id++;
+    ac.add_signal(r.signal, ctx().ctx_name + ".random_" + std::to_string(r.signal), std::nullopt);
+    return r;
+  }
+  static uint32_t execute_op(uint32_t l, uint32_t r, int op) {  // :649-750 (release-build wrapping for + * ** << >>)
+    auto op_err = [](const char* m) { fail(C2A_PROG_OPERATION_ERROR, std::string("Operation error: ") + m); };
+    switch (op) {
+      case I_Mul: return l * r;
+      case I_Div: if (!r) op_err("Division by zero"); return l / r;
+      case I_Add: return l + r;
+      case I_Sub: if (l < r) op_err("Subtraction underflow"); return l - r;
+      case I_Pow: { uint32_t acc = 1, base = l, e = r; while (e) { if (e & 1) acc *= base; e >>= 1; base *= base; } return acc; }
+      case I_IntDiv: if (!r) op_err("Integer division by zero"); return l / r;
+      case I_Mod: if (!r) op_err("Modulo by zero"); return l % r;
+      case I_ShiftL: return l << (r & 31);
+      case I_ShiftR: return l >> (r & 31);
+      case I_LesserEq: return l <= r;
+      case I_GreaterEq: return l >= r;
+      case I_Lesser: return l < r;
+      case I_Greater: return l > r;
+      case I_Eq: return l == r;
+      case I_NotEq: return l != r;
+      case I_BoolOr: return l != 0 || r != 0;
+      case I_BoolAnd: return l != 0 && r != 0;
+      case I_BitOr: return l | r;
+      case I_BitAnd: return l & r;
+      default: return l ^ r;
+    }
+  }
+  Ref temp_var(std::optional<uint32_t> v) { Ref r; r.kind = Ref::TempVar; r.value = v; return r; }
+
+  Ref build_access(const std::string& name, const std::vector<Access>& access) {  // :620-646
+    Ref r;
+    r.kind = Ref::Named;
+    r.name = name;
+    for (auto& a : access) {
+      if (a.component) r.access.push_back(SubAccess{true, 0, a.name});
+      else r.access.push_back(SubAccess{false, value_or_empty(process_expression(*a.index)), ""});
+    }
+    return r;
+  }
+
+  Ref process_expression(const Expr& e) {  // :280-312
+    switch (e.kind) {
+      case Expr::Call: return handle_call(e);
+      case Expr::InfixOp: {  // :426-478
+        Ref l = process_expression(*e.l);
+        Ref r = process_expression(*e.r);
+        DataType lt = type_of(l), rt = type_of(r);
+        if (lt == D_Variable && rt == D_Variable) return temp_var(execute_op(value_or_empty(l), value_or_empty(r), e.op));
+        uint32_t lid = signal_for_access(l);
+        uint32_t rid = signal_for_access(r);
+        Ref out = temp_signal();
+        ac.add_gate(kGateOf[e.op], lid, rid, out.signal);
+        return out;
+      }
+      case Expr::PrefixOp: {  // :485-533, 758-764
+        Ref r = process_expression(*e.r);
+        uint32_t lhs_value = e.op == P_Complement ? 0xFFFFFFFFu : 0u;
+        int infix = e.op == P_Sub ? I_Sub : (e.op == P_BoolNot ? I_Eq : I_BitXor);
+        if (type_of(r) == D_Variable) return temp_var(execute_op(lhs_value, value_or_empty(r), infix));
+        uint32_t lid = make_constant(lhs_value);
+        uint32_t rid = signal_for_access(r);
+        Ref out = temp_signal();
+        ac.add_gate(kGateOf[infix], lid, rid, out.signal);
+        return out;
+      }
+      case Expr::Number: {  // :294-306: the literal must fit u32
+        const std::string& s = e.text;
+        unsigned long long v = 0;
+        bool hex = s.size() > 2 && (s[1] == 'x' || s[1] == 'X');
+        for (size_t i = hex ? 2 : 0; i < s.size(); ++i) {
+          int d = isdigit((unsigned char)s[i]) ? s[i] - '0' : (tolower(s[i]) - 'a' + 10);
+          v = v * (hex ? 16 : 10) + d;
+          if (v > 0xFFFFFFFFull) fail(C2A_PROG_PARSING_ERROR, "Parsing error");
+        }
+        return temp_var((uint32_t)v);
+      }
+      case Expr::Variable: return build_access(e.text, e.access);
+      default: fail(C2A_PROG_EXPRESSION_NOT_IMPLEMENTED, "Expression not implemented");
+    }
+  }
+
+  Ref handle_call(const Expr& e) {  // :315-419
+    auto def = prog.defs.find(e.text);
+    if (def == prog.defs.end()) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
+    const Callable& c = def->second;
+    std::vector<uint32_t> args;
+    for (auto& a : e.args) args.push_back(value_or_empty(process_expression(*a)));
+    if (++depth > 10000) fail(C2A_PROG_CALL_ERROR, "Call error");
+    frames.push_back(Frame{e.text, {}, {{}}});  // push_context(false, id): empty context named after the callee
+    for (size_t i = 0; i < c.params.size() && i < args.size(); ++i) {
+      declare_item(D_Variable, c.params[i], {});
+      ctx().items[c.params[i]].var.val = args[i];
+    }
+    process_statements(c.body);
+    Ref ret;
+    if (c.is_function) {
+      ret.kind = Ref::TempVar;
+      auto it = ctx().items.find(RETURN_VAR);
+      if (it != ctx().items.end() && it->second.type == D_Variable && !it->second.var.is_array) ret.value = it->second.var.val;
+    } else {
+      ret.kind = Ref::TempComp;
+      ret.comp = std::make_shared<SigMap>();
+      for (auto* list : {&c.inputs, &c.outputs})
+        for (auto& name : *list) {
+          auto it = ctx().items.find(name);
+          if (it == ctx().items.end() || it->second.type != D_Signal) runtime_error("Item not declared: get_signal: " + name);
+          (*ret.comp)[name] = it->second.sig;
+        }
+    }
+    frames.pop_back();
+    --depth;
+    return ret;
+  }
+
+  void connect_signal_arrays(const SigTree& a, const SigTree& b) {  // :594-617
+    if (!a.is_array || !b.is_array || a.arr.size() != b.arr.size()) fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
+    for (size_t i = 0; i < a.arr.size(); ++i) {
+      if (!a.arr[i].is_array && !b.arr[i].is_array) ac.add_connection(a.arr[i].val, b.arr[i].val);
+      else if (a.arr[i].is_array && b.arr[i].is_array) connect_signal_arrays(a.arr[i], b.arr[i]);
+      else fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
+    }
+  }
+
+  void handle_substitution(const Stmt& s) {  // :192-277
+    Ref lh = build_access(s.name, s.access);
+    Ref rh = process_expression(*s.e);
+    Item& target = item(s.name, "get_item_data_type");
+    switch (target.type) {
+      case D_Variable: {
+        std::optional<uint32_t> v = variable_value(rh);
+        Item& it = item(s.name, "set_variable");
+        auto& slot = nested_get_mut(it.var, access_to_u32(lh.access));
+        if (slot.is_array) runtime_error("Data Item content is not a single value");
+        slot.val = v;
+        break;
+      }
+      case D_Component:
+        if (s.op == A_Var) {  // component instantiation
+          SigMap map;
+          if (rh.kind == Ref::TempComp) map = *rh.comp;
+          else {
+            if (rh.kind != Ref::Named) runtime_error("Item not declared: get_component_map: " + rh.name);
+            Item& src = item(rh.name, "get_component_map");
+            if (src.type != D_Component) runtime_error("Item not declared: get_component_map: " + rh.name);
+            const auto& n = nested_get(src.comp, access_to_u32(rh.access));
+            if (n.is_array) runtime_error("Data Item content is not a single value");
+            map = n.val;
+          }
+          auto& slot = nested_get_mut(item(s.name, "set_component").comp, access_to_u32(lh.access));
+          if (slot.is_array) runtime_error("Data Item content is not a single value");
+          slot.val = std::move(map);
+        } else if (s.op == A_ConstraintSignal) {
+          SigTree lhs_content = component_signal_content(lh);
+          if (lhs_content.is_array) {
+            SigTree rhs_content = content_for_access(rh);
+            if (!rhs_content.is_array) fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
+            connect_signal_arrays(lhs_content, rhs_content);
+          } else {
+            uint32_t comp_sig = lhs_content.val;
+            uint32_t assigned = signal_for_access(rh);
+            ac.add_connection(assigned, comp_sig);
+          }
+        } else fail(C2A_PROG_OPERATION_NOT_SUPPORTED, "Operation not supported");
+        break;
+      case D_Signal:
+        if (s.e->kind == Expr::Variable) {
+          SigTree lhs_content = signal_content(lh);
+          if (lhs_content.is_array) {
+            SigTree rhs_content = content_for_access(rh);
+            if (!rhs_content.is_array) fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
+            connect_signal_arrays(lhs_content, rhs_content);
+          } else {
+            uint32_t out = signal_for_access(rh);
+            ac.add_connection(out, lhs_content.val);
+          }
+        } else if (s.e->kind == Expr::Call || s.e->kind == Expr::InfixOp || s.e->kind == Expr::PrefixOp || s.e->kind == Expr::Number) {
+          uint32_t given = signal_id(lh);
+          uint32_t out = signal_for_access(rh);
+          ac.add_connection(out, given);
+        } else fail(C2A_PROG_SIGNAL_SUBSTITUTION_NOT_IMPLEMENTED, "Signal substitution not implemented");
+        break;
+    }
+  }
+
+  void process_statements(const std::vector<StmtP>& v) { for (auto& s : v) process_statement(*s); }
+
+  void process_statement(const Stmt& s) {  // :36-189
+    switch (s.kind) {
+      case Stmt::InitBlock:
+      case Stmt::Block: process_statements(s.stmts); break;
+      case Stmt::Substitution: handle_substitution(s); break;
+      case Stmt::Declaration: {
+        std::vector<Ref> dim_refs;
+        for (auto& d : s.dims) dim_refs.push_back(process_expression(*d));
+        std::vector<uint32_t> dims;
+        for (auto& r : dim_refs) dims.push_back(value_or_empty(r));
+        declare_item(s.dtype, s.name, dims);
+        if (s.dtype == D_Signal) {  // one add_signal per element, row-major (:79-108)
+          const SigTree& tree = ctx().items[s.name].sig;
+          std::vector<uint32_t> idx;
+          std::function<void(const SigTree&)> rec = [&](const SigTree& n) {
+            if (!n.is_array) { ac.add_signal(n.val, access_str(s.name, idx), std::nullopt); return; }
+            for (uint32_t i = 0; i < n.arr.size(); ++i) { idx.push_back(i); rec(n.arr[i]); idx.pop_back(); }
+          };
+          // a zero-length dimension: the reference's index loop still visits index 0 once and fails (:96, IndexOutOfBounds)
+          for (uint32_t d : dims) if (d == 0) runtime_error("Index out of bounds");
+          rec(tree);
+        }
+        break;
+      }
+      case Stmt::IfThenElse: {
+        uint32_t c = value_or_empty(process_expression(*s.e));
+        const Stmt* branch = c ? s.a.get() : s.b.get();
+        if (branch) { push_scope(); process_statement(*branch); pop_scope(); }
+        break;
+      }
+      case Stmt::While: {
+        push_scope();  // WHILE_PRE
+        while (true) {
+          uint32_t c = value_or_empty(process_expression(*s.e));
+          if (!c) break;
+          push_scope();  // WHILE_EXE
+          process_statement(*s.a);
+          pop_scope();
+        }
+        pop_scope();
+        break;
+      }
+      case Stmt::Return: {  // :160-174 — no early exit in the reference either
+        uint32_t v = value_or_empty(process_expression(*s.e));
+        declare_item(D_Variable, RETURN_VAR, {});
+        ctx().items[RETURN_VAR].var.val = v;
+        break;
+      }
+      case Stmt::Assert:
+        if (!value_or_empty(process_expression(*s.e))) runtime_error("Assertion failed");
+        break;
+      default: fail(C2A_PROG_STATEMENT_NOT_IMPLEMENTED, "Statement not implemented");
+    }
+  }
+};
+
+}  // namespace front
+
+// ============================================================================================================ C ABI
+struct c2a_program {
+  front::Sink sink;
+  std::string error;
+  std::vector<uint32_t> inputs, outputs;          // signal ids tagged by the prefix match of src/program.rs:57-66, ascending
+  std::vector<std::string> input_names, output_names;
+  std::vector<std::string> main_inputs, main_outputs;  // declared names of the main template
+};
+
+static int compile_impl(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
+  using namespace front;
+  p->sink = Sink();
+  p->sink.into = into;
+  p->error.clear();
+  p->inputs.clear(); p->outputs.clear(); p->input_names.clear(); p->output_names.clear();
+  try {
+    Program prog;
+    std::set<std::string> seen;
+    parse_into(prog, src, file, dir, seen);
+    if (!prog.main || prog.main->kind != Expr::Call) fail(C2A_PROG_MAIN_NOT_A_CALL, "Main expression not a call");  // program.rs:68
+    auto def = prog.defs.find(prog.main->text);
+    if (def == prog.defs.end() || def->second.is_function) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
+    const Callable& main = def->second;
+    Walker w(prog, p->sink);
+    std::vector<std::optional<uint32_t>> values;  // program.rs:30-37
+    for (auto& a : prog.main->args) values.push_back(w.variable_value(w.process_expression(*a)));
+    for (size_t i = 0; i < main.params.size() && i < values.size(); ++i) {  // :40-51 declared in the ROOT context
+      w.declare_item(D_Variable, main.params[i], {});
+      w.ctx().items[main.params[i]].var.val = values[i];
+    }
+    w.process_statements(main.body);  // :54-55
+    p->main_inputs = main.inputs;
+    p->main_outputs = main.outputs;
+    // :57-66 — prefix match over ALL signal names ("0.c" also tags "0.const_signal_*"): replicate
+    auto tag = [&](const std::vector<std::string>& keys, std::vector<uint32_t>& ids, std::vector<std::string>& names, bool input) {
+      std::map<uint32_t, std::string> m;
+      for (auto& k : keys) {
+        std::string filter = "0." + k;
+        for (uint32_t id = 0; id < p->sink.names.size(); ++id)
+          if (p->sink.names[id].compare(0, filter.size(), filter) == 0) m[id] = p->sink.names[id];
+      }
+      for (auto& kv : m) {
+        ids.push_back(kv.first);
+        names.push_back(kv.second);
+        if (into) (input ? c2a_add_input : c2a_add_output)(into, kv.first, kv.second.c_str());
+      }
+    };
+    tag(main.inputs, p->inputs, p->input_names, true);
+    tag(main.outputs, p->outputs, p->output_names, false);
+  } catch (const front::Error& e) {
+    p->error = e.text;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    p->error = "out of memory";
+    return C2A_ERR_NO_MEMORY;
+  }
+  return C2A_OK;
+}
+
+extern "C" {
+
+c2a_program* c2a_program_new(void) { return new c2a_program(); }
+void c2a_program_free(c2a_program* p) { delete p; }
+const char* c2a_program_error(const c2a_program* p) { return p ? p->error.c_str() : "null program"; }
+
+int c2a_program_compile_file(c2a_program* p, const char* path, c2a_compiler* into) {
+  if (!p || !path) return C2A_ERR_INVALID_ARGUMENT;
+  std::string src;
+  try { src = front::read_file(path); } catch (const front::Error& e) { p->error = e.text; return e.code; }
+  return compile_impl(p, src, path, front::dir_of(path), into);
+}
+int c2a_program_compile_source(c2a_program* p, const char* source, const char* include_dir, c2a_compiler* into) {
+  if (!p || !source) return C2A_ERR_INVALID_ARGUMENT;
+  return compile_impl(p, source, "<source>", include_dir ? include_dir : ".", into);
+}
+uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.events.size(); }
+const c2a_event* c2a_program_events(const c2a_program* p) { return p->sink.events.data(); }
+uint64_t c2a_program_num_signals(const c2a_program* p) { return p->sink.names.size(); }
+const char* c2a_program_signal_name(const c2a_program* p, uint32_t id) { return id < p->sink.names.size() ? p->sink.names[id].c_str() : nullptr; }
+uint32_t c2a_program_num_inputs(const c2a_program* p) { return (uint32_t)p->inputs.size(); }
+uint32_t c2a_program_num_outputs(const c2a_program* p) { return (uint32_t)p->outputs.size(); }
+const uint32_t* c2a_program_inputs(const c2a_program* p) { return p->inputs.data(); }
+const uint32_t* c2a_program_outputs(const c2a_program* p) { return p->outputs.data(); }
+
+}  // extern "C"

@@ -247,6 +247,14 @@ int64_t c2a_signal_name(c2a_compiler* c, uint32_t id, char* buf, uint64_t cap) {
   return (int64_t)nm.size();
 }
 
+int c2a_signal_value(c2a_compiler* c, uint32_t id, int* has_value, uint32_t* value) {
+  uint32_t e = c->elem_of(id);
+  if (e == kNoElem) return C2A_ERR_INVALID_ARGUMENT;
+  if (has_value) *has_value = c->el[e].has_value;
+  if (value) *value = c->el[e].value;
+  return C2A_OK;
+}
+
 uint64_t c2a_get_signals_by_prefix(c2a_compiler* c, const char* prefix, uint32_t* ids_out, uint64_t cap) {
   std::vector<uint32_t> ids;
   size_t n = strlen(prefix);

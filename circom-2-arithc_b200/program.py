@@ -1,0 +1,144 @@
+"""Mirror of the reference's program layer (src/program.rs, src/main.rs, src/cli.rs) on top of the native front end
+(csrc/c2a_front.cpp) and the device back end:
+
+    compile(Args | path)            src/program.rs:18-74  -> Compiler (signals named, inputs/outputs tagged, event stream kept)
+    Compiler.generate_circuit_report  src/compiler.rs:287-319, 503-531
+    write_outputs / main()          src/main.rs:15-50     circuit.txt, circuit_info.json, report.json
+
+Third-party output formats whose source is not in the reference tree (bristol-circuit @ 2a8b001 `write_bristol`) are
+restated from their published layout and are PARITY UNPINNED.  `--boolify-width` (boolify @ 6376405,
+un-vendored, untested upstream) is accepted and rejected with a clear message.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from ._lib import lib
+from .compiler import AGateType, BristolCircuit, Compiler, DeviceContext, EVENT_DTYPE
+
+
+class ProgramError(Exception):
+    """src/program.rs:77-117; str() is the thiserror Display text (e.g. 'Runtime error: Index out of bounds')."""
+
+    def __init__(self, status: int, text: str):
+        self.status = status
+        super().__init__(text)
+
+
+@dataclass
+class Args:  # src/cli.rs:19-53 (same names and defaults)
+    input: str = "./input/circuit.circom"
+    output: str = "./output/"
+    value_type: str = "sint"
+    boolify_width: Optional[int] = None
+
+
+def build_output(output_path: str, filename: str, ext: str) -> str:  # src/cli.rs:72-76
+    return os.path.join(output_path, f"{filename}.{ext}")
+
+
+def compile(args, *, source: Optional[str] = None, include_dir: str = ".", device: int = 0, context: Optional[DeviceContext] = None) -> Compiler:
+    """src/program.rs::compile.  `args` is an Args or a path; `source=` compiles a string instead of a file."""
+    if not isinstance(args, Args):
+        args = Args(input=str(args)) if args is not None else Args()
+    comp = Compiler(device=device, context=context)
+    prog = lib.c2a_program_new()
+    try:
+        if source is not None:
+            st = lib.c2a_program_compile_source(prog, source.encode(), include_dir.encode(), comp._c)
+        else:
+            st = lib.c2a_program_compile_file(prog, os.fsencode(args.input), comp._c)
+        if st != 0:
+            raise ProgramError(st, lib.c2a_program_error(prog).decode())
+        n = int(lib.c2a_program_num_events(prog))
+        ev = np.zeros((n, 4), dtype=np.uint32)
+        if n:
+            C.memmove(ev.ctypes.data, lib.c2a_program_events(prog), 16 * n)
+        comp.events = ev
+        ni, no = int(lib.c2a_program_num_inputs(prog)), int(lib.c2a_program_num_outputs(prog))
+        comp.input_signals = np.ctypeslib.as_array(C.cast(lib.c2a_program_inputs(prog), C.POINTER(C.c_uint32)), shape=(ni,)).copy() if ni else np.zeros(0, np.uint32)
+        comp.output_signals = np.ctypeslib.as_array(C.cast(lib.c2a_program_outputs(prog), C.POINTER(C.c_uint32)), shape=(no,)).copy() if no else np.zeros(0, np.uint32)
+    finally:
+        lib.c2a_program_free(prog)
+    comp.update_type(args.value_type)  # src/program.rs:71
+    return comp
+
+
+def generate_circuit_report(comp: Compiler) -> dict:
+    """src/compiler.rs:287-319 + :503-531: inputs = nodes that no gate writes, outputs = written nodes that no gate reads,
+    both ascending by node id; names skip the temporaries ('random_'), value = the last constant among the node's signals."""
+    nodes = comp.nodes()
+    gates = comp.gate_array()
+    consumed = set(gates[:, 1].tolist()) | set(gates[:, 2].tolist()) if gates.shape[0] else set()
+    ins = sorted(i for i, n in nodes.items() if not n["is_out"])
+    outs = sorted(i for i, n in nodes.items() if n["is_out"] and i not in consumed)
+
+    def rep(i):
+        names, value = [], None
+        for sid in nodes[i]["signals"]:
+            name = comp.signal_name(sid)
+            if "random_" not in name:
+                names.append(name)
+            v = comp.signal_value(sid)
+            if v is not None:
+                value = v
+        return {"id": i, "names": names, "value": value}
+    return {"inputs": [rep(i) for i in ins], "outputs": [rep(i) for i in outs], "value_type": comp.value_type}
+
+
+def bristol_text(circ: BristolCircuit) -> str:
+    """bristol-circuit `write_bristol` (un-vendored; PARITY UNPINNED): '<gates> <wires>', '<n_in> 1 ...', '<n_out> 1 ...',
+    blank line, then one line per gate '2 1 <in0> <in1> <out> <Op>' with the strum Display op token."""
+    g = circ.gate_array
+    n_in = len(circ.info.input_name_to_wire_index) + len(circ.info.constants)
+    n_out = len(circ.info.output_name_to_wire_index)
+    lines = [f"{g.shape[0]} {circ.wire_count}", " ".join([str(n_in)] + ["1"] * n_in), " ".join([str(n_out)] + ["1"] * n_out), ""]
+    names = [t.name for t in AGateType]
+    lines += [f"2 1 {a} {b} {o} {names[op]}" for op, a, b, o in g.tolist()]
+    return "\n".join(lines) + "\n"
+
+
+def circuit_info_dict(circ: BristolCircuit) -> dict:
+    return {"input_name_to_wire_index": dict(circ.info.input_name_to_wire_index),
+            "constants": {k: {"value": v.value, "wire_index": v.wire_index} for k, v in circ.info.constants.items()},
+            "output_name_to_wire_index": dict(circ.info.output_name_to_wire_index)}
+
+
+def write_outputs(comp: Compiler, output_dir: str) -> BristolCircuit:
+    """src/main.rs:21-47 — report first, then build_circuit (GPU), then the three files."""
+    report = generate_circuit_report(comp)
+    try:
+        os.makedirs(output_dir, exist_ok=True)
+    except OSError:
+        raise ProgramError(0, "Output directory creation error")
+    circ = comp.build_circuit()
+    with open(build_output(output_dir, "circuit", "txt"), "w") as f:
+        f.write(bristol_text(circ))
+    with open(build_output(output_dir, "circuit_info", "json"), "w") as f:
+        f.write(json.dumps(circuit_info_dict(circ), indent=2))
+    with open(build_output(output_dir, "report", "json"), "w") as f:
+        f.write(json.dumps(report, indent=2))
+    return circ
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(prog="circom-2-arithc", description="Arithmetic Circuits Compiler (B200-native back end)")
+    ap.add_argument("-i", "--input", default="./input/circuit.circom", help="Path to the input file")
+    ap.add_argument("-o", "--output", default="./output/", help="Path to the directory where the output will be written")
+    ap.add_argument("-v", "--value-type", default="sint", choices=["sint", "sfloat"], help="Type that'll be used for values in MPC backend")
+    ap.add_argument("--boolify-width", type=int, default=None, help="Optional: Convert to a boolean circuit by using integers with this number of bits")
+    ap.add_argument("--device", type=int, default=0, help="CUDA device index")
+    a = ap.parse_args(argv)
+    if a.boolify_width is not None:
+        raise SystemExit("--boolify-width: the boolify crate (voltrevo/boolify @ 6376405) is not part of the reference tree; not supported")
+    try:
+        comp = compile(Args(a.input, a.output, a.value_type, a.boolify_width), device=a.device)
+        write_outputs(comp, a.output)
+    except ProgramError as e:
+        raise SystemExit(f"Error: {e}")
+    return 0

@@ -239,6 +239,35 @@ const c2a_gate* c2a_circuit_gates(const c2a_compiler*);       /* num_gates, wire
  * "output_name_to_wire_index":{}} with keys sorted */
 const char* c2a_circuit_info_json(const c2a_compiler*);
 
+int c2a_signal_value(c2a_compiler*, uint32_t signal_id, int* has_value, uint32_t* value); /* Signal.value (src/compiler.rs:17-27) */
+
+/* ---- front end (host): src/program.rs::compile (:18-74) = parse a .circom program (the subset the reference accepts,
+ * README.md:16-40) and walk its main template (src/process.rs, src/runtime.rs), issuing add_signal / add_gate /
+ * add_connection in the reference's order.  The calls are recorded as a c2a_event stream (for c2a_emit_events_device)
+ * and, when `into` is non-NULL, also applied to a host emitter together with the signal names and the prefix-match
+ * input/output tagging of src/program.rs:57-66.  Status: 0, or a c2a_program_status whose text (the thiserror Display
+ * string of ProgramError, src/program.rs:77-117) is returned by c2a_program_error(). ---- */
+typedef enum {
+  C2A_PROG_PARSING_ERROR = 101, C2A_PROG_RUNTIME_ERROR = 102, C2A_PROG_CIRCUIT_ERROR = 103, C2A_PROG_EMPTY_DATA_ITEM = 104,
+  C2A_PROG_EXPRESSION_NOT_IMPLEMENTED = 105, C2A_PROG_STATEMENT_NOT_IMPLEMENTED = 106, C2A_PROG_INVALID_DATA_TYPE = 107,
+  C2A_PROG_MAIN_NOT_A_CALL = 108, C2A_PROG_OPERATION_ERROR = 109, C2A_PROG_OPERATION_NOT_SUPPORTED = 110,
+  C2A_PROG_SIGNAL_SUBSTITUTION_NOT_IMPLEMENTED = 111, C2A_PROG_UNDEFINED_CALLABLE = 112, C2A_PROG_CALL_ERROR = 113
+} c2a_program_status;
+typedef struct c2a_program c2a_program;
+c2a_program* c2a_program_new(void);
+void c2a_program_free(c2a_program*);
+int c2a_program_compile_file(c2a_program*, const char* path, c2a_compiler* into);
+int c2a_program_compile_source(c2a_program*, const char* source, const char* include_dir, c2a_compiler* into);
+const char* c2a_program_error(const c2a_program*);
+uint64_t c2a_program_num_events(const c2a_program*);
+const c2a_event* c2a_program_events(const c2a_program*);
+uint64_t c2a_program_num_signals(const c2a_program*);
+const char* c2a_program_signal_name(const c2a_program*, uint32_t signal_id);
+uint32_t c2a_program_num_inputs(const c2a_program*);   /* signals tagged as circuit inputs (ascending ids) */
+uint32_t c2a_program_num_outputs(const c2a_program*);
+const uint32_t* c2a_program_inputs(const c2a_program*);
+const uint32_t* c2a_program_outputs(const c2a_program*);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,234 @@
+"""The circom-subset front end + walker (csrc/c2a_front.cpp) against the reference's own integration tests
+(tests/integration.rs:279-475) and the hand-derived goldens of SURVEY.md §4.  CPU only: the emitted event stream is
+replayed into the ORACLE (faithful Compiler restatement), built and simulated there."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import circom_fixtures as fx
+import miniwalker as mw
+
+
+def to_oracle(orc, comp):
+    """replay the walker's calls (with names and I/O tags) into the oracle"""
+    oc = orc.OracleCompiler()
+    oc.emit_events(comp.events)
+    kinds = comp.events[:, 0] & 0xFF
+    for sid in comp.events[kinds <= 1, 1]:
+        oc.set_signal_name(int(sid), comp.signal_name(int(sid)))
+    oc.add_inputs({int(s): comp.signal_name(int(s)) for s in comp.input_signals})
+    oc.add_outputs({int(s): comp.signal_name(int(s)) for s in comp.output_signals})
+    return oc
+
+
+def run_named(orc, circ, inputs):
+    info = circ["info"]
+    vals = {info["input_name_to_wire_index"][k]: v for k, v in inputs.items()}
+    for ci in info["constants"].values():
+        vals[ci["wire_index"]] = int(ci["value"])
+    wires = orc.simulate(circ["gates"], circ["wire_count"], vals)
+    return {k: wires[w] for k, w in info["output_name_to_wire_index"].items()}
+
+
+def compile_run(c2a, orc, src, inputs):
+    comp = c2a.compile(None, source=src)
+    circ = to_oracle(orc, comp).build_circuit()
+    return comp, circ, run_named(orc, circ, inputs)
+
+
+# ---- tests/integration.rs -----------------------------------------------------------------------------------
+def test_add_zero(c2a, orc):  # :279-286
+    comp, circ, out = compile_run(c2a, orc, fx.ADD_ZERO, {"0.in": 42})
+    assert out == {"0.out": 42}
+    assert comp.gate_array().tolist() == [[mw.AAdd, 1, 3, 5]] and comp.node_count == 5          # SURVEY §4 golden
+    assert circ["info"]["constants"] == {"0.const_signal_0_2": {"value": "0", "wire_index": 1}}
+
+
+def test_infix_ops(c2a, orc):  # :288-333
+    _, circ, out = compile_run(c2a, orc, fx.INFIX_OPS, {f"0.x{i}": i for i in range(6)})
+    assert out == {f"0.{n}": e for n, _o, _l, _r, e in mw.INFIX_OUTPUTS}
+
+
+def test_matrix_element_multiplication(c2a, orc):  # :335-356
+    ins = {f"0.{m}[{i}][{j}]": 2 for m in "ab" for i in range(2) for j in range(2)}
+    _, _, out = compile_run(c2a, orc, fx.MAT_ELEM_MUL, ins)
+    assert out == {f"0.out[{i}][{j}]": 4 for i in range(2) for j in range(2)}
+
+
+def test_sum(c2a, orc):  # :358-365
+    comp, _, out = compile_run(c2a, orc, fx.SUM, {"0.a": 3, "0.b": 5})
+    assert out == {"0.out": 8} and comp.gate_array().tolist() == [[mw.AAdd, 1, 2, 5]] and comp.node_count == 5
+
+
+def test_x_eq_x(c2a, orc):  # :367-374
+    assert compile_run(c2a, orc, fx.X_EQ_X, {"0.x": 37})[2] == {"0.out": 1}
+
+
+def test_out_of_bounds(c2a):  # :376-391 — exact error string
+    with pytest.raises(c2a.ProgramError) as e:
+        c2a.compile(None, source=fx.INDEX_OUT_OF_BOUNDS)
+    assert str(e.value) == "Runtime error: Index out of bounds"
+
+
+def test_constant_sum(c2a, orc):  # :393-415 — exact maps
+    comp, circ, _ = compile_run(c2a, orc, fx.CONSTANT_SUM, {})
+    assert circ["info"]["input_name_to_wire_index"] == {}
+    assert circ["info"]["constants"] == {"0.const_signal_8_1": {"value": "8", "wire_index": 0}}
+    assert comp.gate_array().shape[0] == 0 and comp.node_count == 3
+
+
+def test_direct_output(c2a, orc):  # :417-441 — exact maps
+    _, circ, _ = compile_run(c2a, orc, fx.DIRECT_OUTPUT, {})
+    assert circ["info"]["output_name_to_wire_index"] == {"0.out": 0}
+    assert circ["info"]["constants"] == {"0.const_signal_42_1": {"value": "42", "wire_index": 0}}
+
+
+def test_prefix_ops_negative_golden(c2a, orc):  # :455-475 (ignored upstream): input `c` prefix-matches 0.complementC
+    comp = c2a.compile(None, source=fx.PREFIX_OPS)
+    with pytest.raises(orc.OracleError) as e:
+        to_oracle(orc, comp).build_circuit()
+    assert "used for both input 0.complement" in e.value.message and "and output 0.complement" in e.value.message
+    assert "0.const_signal_0" in [comp.signal_name(int(s)) for s in comp.input_signals]  # the `c` filter also tags constants
+
+
+def test_under_constrained_compiles_like_the_reference(c2a):  # :443-453 (ignored upstream: "should error" but does not)
+    comp = c2a.compile(None, source=fx.UNDER_CONSTRAINED)
+    assert comp.node_count == 1 and comp.gate_array().shape[0] == 0
+
+
+# ---- same calls as the hand-written stand-in walker (tests/miniwalker.py), fixture by fixture --------------------------
+@pytest.mark.parametrize("src,fixture", [(fx.ADD_ZERO, mw.fixture_add_zero), (fx.SUM, mw.fixture_sum), (fx.X_EQ_X, mw.fixture_x_eq_x),
+                                         (fx.CONSTANT_SUM, mw.fixture_constant_sum), (fx.DIRECT_OUTPUT, mw.fixture_direct_output),
+                                         (fx.INFIX_OPS, mw.fixture_infix_ops), (fx.PREFIX_OPS, mw.fixture_prefix_ops),
+                                         (fx.ARRAY_ASSIGNMENT, mw.fixture_array_assignment)], ids=lambda x: getattr(x, "__name__", "src"))
+def test_same_emission_as_miniwalker(c2a, orc, src, fixture):
+    a = orc.OracleCompiler()
+    fixture(a)
+    comp = c2a.compile(None, source=src)
+    b = to_oracle(orc, comp)
+    assert a.gate_array().tolist() == b.gate_array().tolist() == comp.gate_array().tolist()
+    assert a.nodes() == b.nodes() == comp.nodes()
+    assert a.node_count == comp.node_count
+
+
+def test_array_assignment_golden(c2a, orc):  # callee body first, caller wiring after
+    comp, circ, out = compile_run(c2a, orc, fx.ARRAY_ASSIGNMENT, {f"0.a_in[{i}][{j}]": 1 + 2 * i + j for i in range(2) for j in range(2)})
+    assert comp.gate_array().tolist() == [[mw.AAdd, 15, 16, 11], [mw.AAdd, 11, 17, 12], [mw.AAdd, 12, 18, 19]] and comp.node_count == 19
+    assert comp.nodes()[19]["signals"] == [12, 9, 4]
+    assert circ["order"].tolist() == [0, 1, 2] and circ["wire_count"] == 7 and out == {"0.out": 10}
+    assert comp.signal_name(5) == "componentA.in[0][0]"   # callee context is named after the template (runtime.rs:75-77)
+
+
+def test_main_template_argument(c2a, orc):
+    comp, circ, out = compile_run(c2a, orc, fx.MAIN_TEMPLATE_ARGUMENT, {"0.in": 7})
+    assert out == {"0.out": 107}
+    assert "0.const_signal_100_2" in circ["info"]["constants"]
+
+
+@pytest.mark.parametrize("n,vals,want", [(2, [2, 3], 1), (5, [2, 3, 1, 5, 4], 3), (4, [9, 1, 1, 1], 0)])
+def test_argmax_component_arrays_in_loops(c2a, orc, n, vals, want):  # input/circuit.circom, the CLI's default program
+    src = fx.ARGMAX.replace("ArgMax(N)", f"ArgMax({n})")
+    comp, circ, out = compile_run(c2a, orc, src, {f"0.in[{i}]": v for i, v in enumerate(vals)})
+    assert out == {"0.out": want}
+    assert comp.gate_array().shape[0] == 11 * n  # 1 comparison + 2 switchers x 5 gates per element
+    # loop-body contexts are dropped per iteration (runtime.rs:166-187): the constant `i` is re-created every time,
+    # and each Switcher call has its own const_signal_0 for the prefix minus
+    names = [comp.signal_name(int(s)) for s in comp.events[(comp.events[:, 0] & 0xFF) == 1, 1]]
+    assert names.count("Switcher.const_signal_0") == 2 * n
+
+
+# ---- language coverage and errors ----------------------------------------------------------------------------------
+def test_functions_while_if_and_compound_assignment(c2a, orc):
+    src = """
+    function fact(k) { var r = 1; while (k > 1) { r *= k; k -= 1; } return r; }
+    function pick(a, b) { if (a > b) { return a; } else { return b; } }
+    template T(n) {
+        signal input x;
+        signal output y[n];
+        var acc = 0;
+        for (var i = 0; i < n; i++) {
+            if (i % 2 == 0) { acc += fact(i + 1); } else { acc = pick(acc, 100); }
+            y[i] <== x * acc;
+        }
+    }
+    component main = T(4);
+    """
+    comp, circ, out = compile_run(c2a, orc, src, {"0.x": 3})
+    # acc: i=0 -> 1, i=1 -> 100, i=2 -> 106, i=3 -> 106
+    assert out == {"0.y[0]": 3, "0.y[1]": 300, "0.y[2]": 318, "0.y[3]": 318}
+
+
+def test_reversed_arrows_and_signal_initialisers(c2a, orc):
+    src = """
+    template T() {
+        signal input a; signal input b;
+        signal t <== a * b;
+        signal output o;
+        t + 1 ==> o;
+    }
+    component main {public [a]} = T();
+    """
+    _, _, out = compile_run(c2a, orc, src, {"0.a": 6, "0.b": 7})
+    assert out == {"0.o": 43}
+
+
+def test_include(c2a, orc, tmp_path):
+    (tmp_path / "lib").mkdir()
+    (tmp_path / "lib" / "mul.circom").write_text("template Mul() { signal input a; signal input b; signal output c; c <== a * b; }\n")
+    (tmp_path / "main.circom").write_text('pragma circom 2.1.0;\ninclude "lib/mul.circom";\ninclude "lib/mul";\n'
+                                          "template Top() { signal input p; signal input q; signal output r; component m = Mul();\n"
+                                          " m.a <== p; m.b <== q; r <== m.c; }\ncomponent main = Top();\n")
+    comp = c2a.compile(str(tmp_path / "main.circom"))
+    circ = to_oracle(orc, comp).build_circuit()
+    assert run_named(orc, circ, {"0.p": 5, "0.q": 9}) == {"0.r": 45}
+
+
+@pytest.mark.parametrize("body,text", [
+    ("signal input a; signal output b; a === b;", "Statement not implemented"),                        # process.rs:187, README.md:27
+    ("signal input a; signal output b; b <== a > 1 ? a : 1;", "Expression not implemented"),            # :310 InlineSwitchOp
+    ("signal output b; var v[2] = [1, 2]; b <== v[0];", "Expression not implemented"),                  # :310 ArrayInLine
+    ("signal output b; b <== 4294967296;", "Parsing error"),                                            # :302 constants must fit u32
+    ("signal output b; var z = 0 - 5; b <== z;", "Operation error: Subtraction underflow"),             # :805-810
+    ("signal output b; var z = 1 / 0; b <== z;", "Operation error: Division by zero"),
+    ("signal output b; b <== nope(3);", "Undefined function or template"),
+    ("signal output b; signal b;", "Runtime error: Item already declared"),
+    ("signal output b; assert(1 == 2);", "Runtime error: Assertion failed"),
+    ("signal output b; var u; b <== u + 1;", "Empty data item"),
+])
+def test_error_strings(c2a, body, text):
+    with pytest.raises(c2a.ProgramError) as e:
+        c2a.compile(None, source="template T() { %s }\ncomponent main = T();" % body)
+    assert str(e.value) == text
+
+
+def test_main_must_be_a_call(c2a):
+    with pytest.raises(c2a.ProgramError) as e:
+        c2a.compile(None, source="template T() { signal output b; }\ncomponent main = 3;")
+    assert str(e.value) == "Main expression not a call"
+
+
+def test_merge_errors_surface_as_circuit_errors(c2a):  # compiler.rs:239-245 through process.rs `?`
+    with pytest.raises(c2a.ProgramError) as e:
+        c2a.compile(None, source="template T() { signal input a; signal output b; b <== a + 1; b <== a * 2; }\ncomponent main = T();")
+    assert str(e.value) == "Circuit error: Cannot merge output nodes"
+
+
+def test_report_matches_oracle(c2a, orc):  # compiler.rs:287-319, 503-531
+    for src in (fx.ADD_ZERO, fx.ARRAY_ASSIGNMENT, fx.MAT_ELEM_MUL, fx.ARGMAX.replace("ArgMax(N)", "ArgMax(3)")):
+        comp = c2a.compile(None, source=src)
+        assert comp.generate_circuit_report() == to_oracle(orc, comp).report()
+    rep = c2a.compile(None, source=fx.ADD_ZERO).generate_circuit_report()
+    assert rep["outputs"] == [{"id": 5, "names": ["0.out"], "value": None}] and rep["value_type"] == "sint"
+
+
+def test_large_loop_is_linear(c2a):
+    """the reference clones the whole context per iteration (runtime.rs:151-159) and scans all nodes per gate; here a
+    200 K-gate loop compiles in about a second"""
+    import time
+    src = "template T(n) { signal input x; signal output y; signal t[n+1]; t[0] <== x; for (var i = 0; i < n; i++) { t[i+1] <== t[i] * t[i] + i; } y <== t[n]; }\ncomponent main = T(100000);"
+    t0 = time.time()
+    comp = c2a.compile(None, source=src)
+    assert comp.gate_array().shape[0] == 200000
+    assert time.time() - t0 < 30

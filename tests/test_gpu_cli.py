@@ -1,0 +1,89 @@
+"""End to end on the GPU: .circom -> front end -> (host or device) emitter -> build_circuit -> evaluate / output files.
+Reference: src/main.rs:15-50, tests/integration.rs:257-277 (`simulation_test`)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import circom_fixtures as fx
+import miniwalker as mw
+
+pytestmark = pytest.mark.gpu
+
+
+def simulation_test(c2a, ctx, src, inputs):
+    """compile -> build_circuit -> run, all through the product (tests/integration.rs:257-277)"""
+    comp = c2a.compile(None, source=src, context=ctx)
+    circ = comp.build_circuit()
+    vals = {circ.info.input_name_to_wire_index[k]: v for k, v in inputs.items()}
+    for ci in circ.info.constants.values():
+        vals[ci.wire_index] = int(ci.value)
+    wires = ctx.evaluate(circ.gate_array, circ.wire_count, vals)
+    return {k: wires[w] for k, w in circ.info.output_name_to_wire_index.items()}, circ, comp
+
+
+def test_reference_integration_suite(c2a, ctx):
+    assert simulation_test(c2a, ctx, fx.ADD_ZERO, {"0.in": 42})[0] == {"0.out": 42}
+    assert simulation_test(c2a, ctx, fx.INFIX_OPS, {f"0.x{i}": i for i in range(6)})[0] == {f"0.{n}": e for n, _o, _l, _r, e in mw.INFIX_OUTPUTS}
+    ins = {f"0.{m}[{i}][{j}]": 2 for m in "ab" for i in range(2) for j in range(2)}
+    assert simulation_test(c2a, ctx, fx.MAT_ELEM_MUL, ins)[0] == {f"0.out[{i}][{j}]": 4 for i in range(2) for j in range(2)}
+    assert simulation_test(c2a, ctx, fx.SUM, {"0.a": 3, "0.b": 5})[0] == {"0.out": 8}
+    assert simulation_test(c2a, ctx, fx.X_EQ_X, {"0.x": 37})[0] == {"0.out": 1}
+    _, circ, _ = simulation_test(c2a, ctx, fx.CONSTANT_SUM, {})
+    assert {k: (v.value, v.wire_index) for k, v in circ.info.constants.items()} == {"0.const_signal_8_1": ("8", 0)}
+    _, circ, _ = simulation_test(c2a, ctx, fx.DIRECT_OUTPUT, {})
+    assert circ.info.output_name_to_wire_index == {"0.out": 0}
+    with pytest.raises(c2a.CircuitError) as e:
+        simulation_test(c2a, ctx, fx.PREFIX_OPS, {})
+    assert "used for both input 0.complement" in str(e.value)
+    out, _, _ = simulation_test(c2a, ctx, fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), {f"0.in[{i}]": v for i, v in enumerate([2, 3, 1, 5, 4])})
+    assert out == {"0.out": 3}
+
+
+def test_walker_stream_through_the_device_emitter(c2a, ctx, orc):
+    """a loop-heavy program: the walker's event stream replayed on the GPU gives the host emitter's circuit"""
+    src = ("template Sq() { signal input a; signal output b; b <== a * a + 1; }\n"
+           "template T(n) { signal input x[n]; signal output y[n]; component s[n];\n"
+           " for (var i = 0; i < n; i++) { s[i] = Sq(); s[i].a <== x[i]; y[i] <== s[i].b * x[i]; } }\ncomponent main = T(3000);")
+    comp = c2a.compile(None, source=src, context=ctx)
+    info = ctx.emit_events(comp.events)
+    assert info["path"] == 1 and info["n_gates"] == 9000
+    gates, nos = ctx.emitted_fetch()
+    assert np.array_equal(gates, comp.gate_array()) and info["node_count"] == comp.node_count
+    order, wire, ng, wc = ctx.emitted_build_circuit(comp.input_signals, comp.output_signals)
+    circ = comp.build_circuit()
+    assert np.array_equal(ng, circ.gate_array) and wc == circ.wire_count and np.array_equal(order, circ.order)
+    assert not np.array_equal(order, np.arange(9000))  # component bodies precede their input wiring: real reordering
+    vals = {int(wire[nos[s]]): 2 + (int(s) % 7) for s in comp.input_signals}
+    for k, ci in circ.info.constants.items():
+        vals[ci.wire_index] = int(ci.value)
+    got = ctx.evaluate(ng, wc, vals)
+    for i in range(3000):
+        x = 2 + (i % 7)
+        assert got[circ.info.output_name_to_wire_index[f"0.y[{i}]"]] == (x * x + 1) * x
+
+
+def test_cli_writes_the_three_files(c2a, orc, tmp_path):  # src/main.rs:34-47
+    src = tmp_path / "circuit.circom"
+    src.write_text(fx.ARGMAX.replace("ArgMax(N)", "ArgMax(2)"))
+    out = tmp_path / "out"
+    assert c2a.cli_main(["-i", str(src), "-o", str(out), "-v", "sfloat"]) == 0
+    info = json.loads((out / "circuit_info.json").read_text())
+    report = json.loads((out / "report.json").read_text())
+    lines = (out / "circuit.txt").read_text().split("\n")
+    comp = c2a.compile(str(src))
+    oc = orc.OracleCompiler()
+    oc.emit_events(comp.events)
+    kinds = comp.events[:, 0] & 0xFF
+    for sid in comp.events[kinds <= 1, 1]:
+        oc.set_signal_name(int(sid), comp.signal_name(int(sid)))
+    oc.add_inputs({int(s): comp.signal_name(int(s)) for s in comp.input_signals})
+    oc.add_outputs({int(s): comp.signal_name(int(s)) for s in comp.output_signals})
+    want = oc.build_circuit()
+    assert info == want["info"]
+    assert report == oc.report("sfloat") and report["value_type"] == "sfloat"
+    G = want["gates"].shape[0]
+    assert lines[0] == f"{G} {want['wire_count']}" and lines[3] == ""
+    names = [t.name for t in c2a.AGateType]
+    assert lines[4:4 + G] == [f"2 1 {a} {b} {o} {names[op]}" for op, a, b, o in want["gates"].tolist()]
