@@ -45,23 +45,23 @@ def test_walker_stream_through_the_device_emitter(c2a, ctx, orc):
     """a loop-heavy program: the walker's event stream replayed on the GPU gives the host emitter's circuit"""
     src = ("template Sq() { signal input a; signal output b; b <== a * a + 1; }\n"
            "template T(n) { signal input x[n]; signal output y[n]; component s[n];\n"
-           " for (var i = 0; i < n; i++) { s[i] = Sq(); s[i].a <== x[i]; y[i] <== s[i].b * x[i]; } }\ncomponent main = T(3000);")
+           " for (var i = 0; i < n; i++) { s[i] = Sq(); s[i].a <== x[i] + 1; y[i] <== s[i].b * x[i]; } }\ncomponent main = T(3000);")
     comp = c2a.compile(None, source=src, context=ctx)
     info = ctx.emit_events(comp.events)
-    assert info["path"] == 1 and info["n_gates"] == 9000
+    assert info["path"] == 1 and info["n_gates"] == 12000
     gates, nos = ctx.emitted_fetch()
     assert np.array_equal(gates, comp.gate_array()) and info["node_count"] == comp.node_count
     order, wire, ng, wc = ctx.emitted_build_circuit(comp.input_signals, comp.output_signals)
     circ = comp.build_circuit()
     assert np.array_equal(ng, circ.gate_array) and wc == circ.wire_count and np.array_equal(order, circ.order)
-    assert not np.array_equal(order, np.arange(9000))  # component bodies precede their input wiring: real reordering
+    assert not np.array_equal(order, np.arange(12000))  # component bodies precede their input wiring: real reordering
     vals = {int(wire[nos[s]]): 2 + (int(s) % 7) for s in comp.input_signals}
     for k, ci in circ.info.constants.items():
         vals[ci.wire_index] = int(ci.value)
     got = ctx.evaluate(ng, wc, vals)
     for i in range(3000):
         x = 2 + (i % 7)
-        assert got[circ.info.output_name_to_wire_index[f"0.y[{i}]"]] == (x * x + 1) * x
+        assert got[circ.info.output_name_to_wire_index[f"0.y[{i}]"]] == ((x + 1) * (x + 1) + 1) * x
 
 
 def test_cli_writes_the_three_files(c2a, orc, tmp_path):  # src/main.rs:34-47
