@@ -37,19 +37,17 @@ def alg_bytes(kernel, c):
     order = 0 if c["identity"] else 4 * G            # sorted passes also read order[]
     table = {
         # ---- device emitter (c2a_emit.cuh)
-        "emit:k_ev_count": 16 * n,                                # stream the events
-        "emit:k_ev_tile_scan": 12 * ((n + 1023) // 1024),
-        "emit:k_ev_scatter": 16 * n + ns * (8 + 8) + G * (16 + 4) + C * (8 + 4 + 4),   # sig_t CAS + meta | egates + gate_t | conn + t + sb
+        # single pass: stream the events once, look-back tile states, scatter to sig_t + sig_meta | egates + gate_t | conn + conn_t + conn_sb
+        "emit:k_ev_scatter": 16 * n + 16 * ((n + 1023) // 1024) + ns * (4 + 8) + G * (16 + 4) + C * (8 + 4 + 4),
         "emit:k_ev_check_gates": G * (16 + 4 + 12 + 1),
         "emit:k_ev_check_conns": C * (8 + 4 + 8),
         "emit:k_msf_pick": C * (8 + 8 + 16 + 16),                 # conn, 2 parent, 2 RED.MIN best, cand (first round; later rounds are on the shrunken list)
         "emit:k_msf_hook": C * (16 + 8 + 4 + 4),                  # cand, 2 best, parent, eff
         "emit:k_scan_u32": 8 * C,
-        "emit:k_ev_nid_init": S * (4 + 8 + 4 + 4),
         "emit:k_ev_nid_edges": C * 8 + Ceff * (4 + 8 + 4 + 8),
-        "emit:k_ev_finalize": S * (4 + 8 + 1 + 4 + 4 + 4) + (G + c["n_const"]) * 8,
+        "emit:k_ev_finalize": S * (4 + 8 + 1 + 4 + 8 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, {nid,cnt}, nos + screen atomics
         "emit:k_ev_gates": G * (16 + 12 + 16),
-        "emit:init": S * (4 + 1 + 4 + 4 + 4) + 4 * C,             # memsets: sig_t, outmark, best (x2), parent iota, eff
+        "emit:init": 4 * (n + (1 << 20)) + S * (1 + 4 + 4 + 8) + 4 * C,   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
         # ---- build_circuit (c2a_device.cu)
         "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
         "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair
@@ -61,7 +59,7 @@ def alg_bytes(kernel, c):
         "k_wire_first": G * (16 + 12) + order,                    # read gate, 3 RED.MIN on wire[]
         "k_wire_scan": G * (16 + 12) + 4 * c["n_mid"] + order,    # read gate, 3 wire reads, one wire write per numbered node
         "k_gather": G * (16 + 12 + 16) + order,                   # read gate, 3 wire gathers, write new gate
-        "init": 8 * NB,                                           # zero producer[], fill wire[]
+        "init": 8 * NB + (0 if c["identity"] else 9 * G + G // 8),   # zero producer[], fill wire[]; sort scratch (r, size_off, state, inq)
     }
     return table.get(kernel, 0)
 

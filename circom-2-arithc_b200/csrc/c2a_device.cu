@@ -64,8 +64,26 @@ constexpr uint32_t kOutPending = 0x7FFFFFFFu;
 constexpr uint32_t kFirstTag = 0x80000000u;
 
 // scalars[] slots on the device
-enum { S_FLAGS = 0, S_Q0N = 1, S_Q1N = 2, S_HEAVYN = 3, S_NMID = 4, S_TICKET = 5, S_ERR_LO = 6, S_ERR_HI = 7, S_COUNT = 16 };
-enum { F_OOO = 1, F_BAD = 2, F_SELF = 4 };
+// S_QN0 .. S_QN0+kSpecRounds: queue lengths of the speculative relax rounds (round j reads S_QN0+j, appends to S_QN0+j+1);
+// S_QN_LAST != 0 after them means "r[] has not converged yet": every later kernel of the call parks itself and the host
+// drains the queue with synchronised rounds (S_QA / S_QB) before re-issuing the tail of the pipeline.
+constexpr int kSpecRounds = 4;
+enum { S_FLAGS = 0, S_HEAVYN = 1, S_NMID = 2, S_TICKET = 3, S_TICKET2 = 4, S_ERR_LO = 6, S_ERR_HI = 7, S_QN0 = 8, S_QN_LAST = S_QN0 + kSpecRounds,
+       S_QA = 13, S_QB = 14, S_COUNT = 32 };
+enum { F_OOO = 1, F_BAD = 2, F_SELF = 4, F_BAD_IO = 8 };
+
+// Device-side control flow: the host enqueues the whole pipeline without looking at intermediate results; kernels decide
+// from the scalars whether they have work.  (One status read at the very end instead of a round trip per decision.)
+__device__ __forceinline__ bool sort_wanted(const uint32_t* __restrict__ sc) {  // the DFS order differs from 0..n-1
+  uint32_t f = sc[S_FLAGS];
+  return !(f & F_BAD) && (f & (F_OOO | F_SELF));
+}
+__device__ __forceinline__ bool sort_parked(const uint32_t* __restrict__ sc) {  // r[] not converged within the speculative rounds
+  return sc[S_QN_LAST] != 0;
+}
+__device__ __forceinline__ bool tail_parked(const uint32_t* __restrict__ sc) {  // kernels after the sort: bad input, pending sort, cycle found
+  return (sc[S_FLAGS] & F_BAD) || sc[S_QN_LAST] != 0 || sc[S_ERR_HI] != 0xFFFFFFFFu;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // K1: producer map.  prod1[node] = 1 + (largest gate index whose out is node); 0 = no producer.
@@ -87,13 +105,14 @@ __global__ void __launch_bounds__(kBlock) k_producer(const uint4* __restrict__ g
 // (compiler.rs:412-418).  flags |= F_OOO when some dep index >= g: only then can the DFS post-order differ
 // from 0..G-1 (otherwise every root's deps are already visited when the root loop reaches it).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates, uint32_t G, const uint32_t* __restrict__ prod1,
+__global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates, uint32_t G, uint32_t node_bound, const uint32_t* __restrict__ prod1,
                                                  uint2* __restrict__ dep, uint32_t* __restrict__ scalars) {
   uint32_t f = 0;
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint4 gt = ldg_stream(gates + g);
-    uint32_t d0 = __ldg(prod1 + gt.y) - 1u;  // 0 -> kNone
-    uint32_t d1 = __ldg(prod1 + gt.z) - 1u;
+    // ids >= node_bound were flagged by k_producer (F_BAD); stay memory-safe here, the call fails at the status read
+    uint32_t d0 = gt.y < node_bound ? __ldg(prod1 + gt.y) - 1u : kNone;  // 0 -> kNone
+    uint32_t d1 = gt.z < node_bound ? __ldg(prod1 + gt.z) - 1u : kNone;
     dep[g] = make_uint2(d0, d1);
     if ((d0 != kNone && d0 >= g) || (d1 != kNone && d1 >= g)) f |= F_OOO;
     if (d0 == g || d1 == g) f |= F_SELF;
@@ -129,6 +148,21 @@ __global__ void __launch_bounds__(kBlock) k_deps_from_csr(const unsigned long lo
 __global__ void __launch_bounds__(kBlock) k_iota(uint32_t* __restrict__ a, uint32_t n) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) a[i] = i;
 }
+// order = 0..n-1 when no dependency points forward (topological_sort.rs:11-13: every root's deps are already visited)
+__global__ void __launch_bounds__(kBlock) k_iota_if_identity(uint32_t* __restrict__ a, uint32_t n, const uint32_t* __restrict__ sc) {
+  if (sort_wanted(sc) || (sc[S_FLAGS] & F_BAD)) return;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) a[i] = i;
+}
+// K5 scratch: r = iota, size_off = 0, state = 0, inq = 0 (only when the sort has to run)
+__global__ void __launch_bounds__(kBlock) k_sort_init(uint32_t n, uint32_t* __restrict__ r, uint32_t* __restrict__ size_off, uint8_t* __restrict__ state,
+                                                      uint32_t* __restrict__ inq, const uint32_t* __restrict__ sc) {
+  if (!sort_wanted(sc)) return;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i <= n; i += gridDim.x * kBlock) {
+    size_off[i] = 0;
+    if (i < n) { r[i] = i; state[i] = 0; }
+    if (i <= (n + 31) / 32) inq[i] = 0;
+  }
+}
 
 // ---------------------------------------------------------------------------------------------------
 // K5a: r[v] = index of the root of the `for i in 0..len` loop (topological_sort.rs:11-13) whose visit first
@@ -161,7 +195,9 @@ __device__ __forceinline__ void relax_from(uint32_t cur, uint32_t val, const uin
 }
 
 __global__ void __launch_bounds__(kBlock) k_relax_seed(const uint2* __restrict__ dep, uint32_t n, uint32_t* __restrict__ r,
-                                                       uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn) {
+                                                       uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn,
+                                                       const uint32_t* __restrict__ sc) {
+  if (!sort_wanted(sc)) return;
   for (uint32_t u = blockIdx.x * kBlock + threadIdx.x; u < n; u += gridDim.x * kBlock) {
     uint2 d = dep[u];
     // r[d] <= d always, so val=u can only lower r[d] along an out-of-order edge (d > u)
@@ -183,7 +219,8 @@ __global__ void __launch_bounds__(kBlock) k_relax_round(const uint2* __restrict_
 }
 
 // K5b: block sizes.  size[root] = number of items first reached from root.
-__global__ void __launch_bounds__(kBlock) k_sizes(const uint32_t* __restrict__ r, uint32_t n, uint32_t* __restrict__ size) {
+__global__ void __launch_bounds__(kBlock) k_sizes(const uint32_t* __restrict__ r, uint32_t n, uint32_t* __restrict__ size, const uint32_t* __restrict__ sc) {
+  if (!sort_wanted(sc) || sort_parked(sc)) return;
   for (uint32_t v = blockIdx.x * kBlock + threadIdx.x; v < n; v += gridDim.x * kBlock) atomicAdd(size + r[v], 1u);
 }
 
@@ -212,6 +249,51 @@ __device__ __forceinline__ uint32_t scan_claim_tile(uint32_t* __restrict__ ticke
   return s_mem[9];
 }
 
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// Decoupled look-back for tile > 0, called by one full warp: sum of the values of all tiles before `tile`.
+// State word = status << kShift | value  (status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix).
+// The chain of inclusive prefixes advances by one window per L2 round trip, so the window is what bounds a scan with many
+// small tiles (measured: ~60 tiles/us with a 32-tile window).  Here every lane keeps kLookWin states in flight: the window is
+// 32 * kLookWin tiles, fetched with one round trip.
+constexpr int kLookWin = 4;
+template <int kShift>
+__device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ tile_state, uint32_t tile, int lane) {
+  constexpr unsigned long long kValMask = (1ull << kShift) - 1;
+  unsigned long long prefix = 0;
+  long long p = (long long)tile - 1;
+  while (true) {
+    unsigned long long v[kLookWin];
+#pragma unroll
+    for (int j = 0; j < kLookWin; ++j) {
+      long long idx = p - lane - 32 * j;
+      v[j] = idx >= 0 ? ld_volatile_u64(tile_state + idx) : (2ull << kShift);  // before tile 0: an inclusive prefix of 0
+    }
+#pragma unroll
+    for (int j = 0; j < kLookWin; ++j) {
+      long long idx = p - lane - 32 * j;
+      while (true) {
+        uint32_t st = (uint32_t)(v[j] >> kShift);
+        uint32_t empty = __ballot_sync(0xFFFFFFFFu, st == 0), inc = __ballot_sync(0xFFFFFFFFu, st == 2);
+        unsigned long long val = v[j] & kValMask;
+        if (inc) {
+          int first = __ffs(inc) - 1;  // nearest predecessor holding an inclusive prefix
+          if (!(empty & ((1u << first) - 1u))) return prefix + warp_sum_u64(lane <= first ? val : 0ull);
+        } else if (!empty) {
+          prefix += warp_sum_u64(val);
+          break;  // next 32 predecessors
+        }
+        if (st == 0) v[j] = ld_volatile_u64(tile_state + idx);
+      }
+    }
+    p -= 32 * kLookWin;
+  }
+}
+
 __device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thread_sum, unsigned long long* __restrict__ tile_state,
                                                      uint32_t* s_mem, uint32_t* total_out, bool is_last_tile) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -223,34 +305,12 @@ __device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thr
     uint32_t wi = warp_incl_scan(w, lane);
     uint32_t block_agg = __shfl_sync(0xFFFFFFFFu, wi, (kBlock / 32) - 1);
     if (lane < (kBlock / 32)) s_mem[lane] = wi - w;  // exclusive warp offsets
-    // look-back
     uint32_t prefix = 0;
     if (tile == 0) {
       if (lane == 0) st_volatile_u64(tile_state, kStInc | block_agg);
     } else {
       if (lane == 0) st_volatile_u64(tile_state + tile, kStAgg | block_agg);
-      long long p = (long long)tile - 1;
-      while (true) {
-        long long idx = p - lane;
-        unsigned long long v = idx >= 0 ? ld_volatile_u64(tile_state + idx) : kStInc;
-        while (__any_sync(0xFFFFFFFFu, (v >> 32) == 0)) {
-          if ((v >> 32) == 0) v = ld_volatile_u64(tile_state + idx);
-        }
-        uint32_t inc_mask = __ballot_sync(0xFFFFFFFFu, (v >> 32) == 2);
-        uint32_t val = (uint32_t)v;
-        if (inc_mask) {
-          int first = __ffs(inc_mask) - 1;  // nearest predecessor holding an inclusive prefix
-          uint32_t c = lane <= first ? val : 0u;
-#pragma unroll
-          for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-          prefix += c;
-          break;
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, o);
-        prefix += val;
-        p -= 32;
-      }
+      prefix = (uint32_t)lookback_exclusive<32>(tile_state, tile, lane);
       if (lane == 0) st_volatile_u64(tile_state + tile, kStInc | (unsigned long long)(prefix + block_agg));
     }
     if (lane == 0) {
@@ -262,34 +322,39 @@ __device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thr
   return s_mem[8] + s_mem[warp] + (incl - thread_sum);
 }
 
-// in-place exclusive scan of a[0..n) ; a[n] = total.  8 items per thread, 128-bit accesses.
-constexpr int kScanItems = 8;
-__global__ void __launch_bounds__(kBlock) k_scan_u32(uint32_t* __restrict__ a, uint32_t n, unsigned long long* __restrict__ tile_state,
-                                                     uint32_t* __restrict__ ticket) {
+// exclusive scan of src[0..n) into dst[0..n) (may alias) ; dst[n] = total.  8 items per thread, 128-bit accesses.
+// guard: nullptr, or the scalars of a sort whose device-side state decides whether this launch has work.
+constexpr int kScanItems = 16;  // 4096 elements per tile: fewer links in the look-back chain
+__global__ void __launch_bounds__(kBlock) k_scan_u32(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
+                                                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ guard) {
   __shared__ uint32_t s_mem[10];
+  if (guard && (!sort_wanted(guard) || sort_parked(guard))) return;
   const uint32_t tiles = (n + kBlock * kScanItems - 1) / (kBlock * kScanItems);
   uint32_t tile = scan_claim_tile(ticket, s_mem);
   uint32_t base = tile * (kBlock * kScanItems) + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   if (base + kScanItems <= n) {
-    uint4 x = *reinterpret_cast<const uint4*>(a + base), y = *reinterpret_cast<const uint4*>(a + base + 4);
-    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+#pragma unroll
+    for (int i = 0; i < kScanItems; i += 4) {
+      uint4 x = *reinterpret_cast<const uint4*>(src + base + i);
+      v[i] = x.x; v[i + 1] = x.y; v[i + 2] = x.z; v[i + 3] = x.w;
+    }
   } else {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) v[i] = base + i < n ? a[base + i] : 0u;
+    for (int i = 0; i < kScanItems; ++i) v[i] = base + i < n ? src[base + i] : 0u;
   }
   uint32_t sum = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) sum += v[i];
-  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, a + n, tile == tiles - 1);
+  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, dst + n, tile == tiles - 1);
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) { uint32_t t = v[i]; v[i] = ex; ex += t; }
   if (base + kScanItems <= n) {
-    *reinterpret_cast<uint4*>(a + base) = make_uint4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<uint4*>(a + base + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i += 4) *reinterpret_cast<uint4*>(dst + base + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
   } else {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) if (base + i < n) a[base + i] = v[i];
+    for (int i = 0; i < kScanItems; ++i) if (base + i < n) dst[base + i] = v[i];
   }
 }
 
@@ -301,8 +366,10 @@ __global__ void __launch_bounds__(kBlock) k_scan_u32(uint32_t* __restrict__ a, u
 // while emitted items grow up from the start; |stack| + |emitted| <= block size).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_roots(const uint32_t* __restrict__ r, const uint32_t* __restrict__ off, uint32_t n,
-                                                  const uint2* __restrict__ dep, uint32_t check_self, uint32_t* __restrict__ order,
+                                                  const uint2* __restrict__ dep, uint32_t* __restrict__ order,
                                                   uint32_t* __restrict__ heavy, uint32_t* __restrict__ scalars) {
+  if (!sort_wanted(scalars) || sort_parked(scalars)) return;
+  const bool check_self = scalars[S_FLAGS] & F_SELF;
   for (uint32_t v = blockIdx.x * kBlock + threadIdx.x; v < n; v += gridDim.x * kBlock) {
     if (r[v] != v) continue;
     uint32_t o = off[v], sz = off[v + 1] - o;
@@ -323,6 +390,7 @@ __global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ h
                                                   const uint2* __restrict__ dep, const uint32_t* __restrict__ r,
                                                   const uint32_t* __restrict__ off, uint8_t* __restrict__ state,
                                                   uint32_t* __restrict__ order, uint32_t* scalars) {
+  if (!sort_wanted(scalars) || sort_parked(scalars)) return;
   uint32_t nh = scalars[S_HEAVYN];
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += gridDim.x * blockDim.x) {
     const uint32_t R = heavy[i];
@@ -370,7 +438,7 @@ __global__ void __launch_bounds__(kBlock) k_io_set(const uint32_t* __restrict__ 
     if (nd >= node_bound) bad = true;
     else wire[nd] = value;
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(scalars + S_FLAGS, (uint32_t)F_BAD);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(scalars + S_FLAGS, (uint32_t)F_BAD_IO);
 }
 __global__ void __launch_bounds__(kBlock) k_io_max(const uint32_t* __restrict__ nodes, uint32_t n, uint32_t node_bound, uint32_t base,
                                                    const uint32_t* __restrict__ base_dev, uint32_t* __restrict__ wire) {
@@ -383,70 +451,104 @@ __global__ void __launch_bounds__(kBlock) k_io_max(const uint32_t* __restrict__ 
 
 // pass 1: earliest appearance p = 3*pos+slot of every not-yet-numbered node, over the SORTED gate stream.
 // RED.MIN per slot: inputs / pending outputs hold smaller words and are left untouched.
-__device__ __forceinline__ void first_min(uint32_t* __restrict__ wire, uint32_t node, uint32_t p) {
-  // Read before the RED: words only ever decrease, so a (possibly stale) value <= p proves the RED is a no-op.
-  // This removes the serialisation on hot nodes (a shared input such as a key feeds millions of gates).
-  if (wire[node] > p) atomicMin(wire + node, p);
-}
-
-__global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
-                                                       uint32_t* __restrict__ wire) {
-  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
-    uint32_t g = order ? order[k] : k;
-    uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
-    uint32_t p = kFirstTag | (3u * k);
-    first_min(wire, gt.y, p);
-    if (gt.z != gt.y) first_min(wire, gt.z, p + 1);
-    if (gt.w != gt.y && gt.w != gt.z) first_min(wire, gt.w, p + 2);
+// Every thread keeps kWireIlp independent gates in flight: the order[] loads, then the gate loads, then the wire[] probes are
+// issued as batches (a single gate is a chain of three dependent memory round trips).
+constexpr int kWireIlp = 4;
+__global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
+                                                       uint32_t* __restrict__ wire, const uint32_t* __restrict__ sc) {
+  if (tail_parked(sc)) return;
+  const uint32_t* __restrict__ order = sort_wanted(sc) ? order_arr : nullptr;
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t k0 = blockIdx.x * kBlock + threadIdx.x; k0 < G; k0 += stride * kWireIlp) {
+    uint32_t g[kWireIlp];
+    uint4 gt[kWireIlp];
+    uint32_t w[kWireIlp][3];
+#pragma unroll
+    for (int i = 0; i < kWireIlp; ++i) {
+      uint32_t k = min(k0 + i * stride, G - 1);  // clamped duplicates are harmless: RED.MIN of the same value
+      g[i] = order ? __ldg(order + k) : k;
+    }
+#pragma unroll
+    for (int i = 0; i < kWireIlp; ++i) gt[i] = order ? __ldg(gates + g[i]) : ldg_stream(gates + g[i]);
+    // Read before the RED: words only ever decrease, so a (possibly stale) value <= p proves the RED is a no-op.
+    // This removes the serialisation on hot nodes (a shared input such as a key feeds millions of gates).
+#pragma unroll
+    for (int i = 0; i < kWireIlp; ++i) { w[i][0] = wire[gt[i].y]; w[i][1] = wire[gt[i].z]; w[i][2] = wire[gt[i].w]; }
+#pragma unroll
+    for (int i = 0; i < kWireIlp; ++i) {
+      uint32_t k = min(k0 + i * stride, G - 1);
+      uint32_t p = kFirstTag | (3u * k);
+      if (w[i][0] > p) atomicMin(wire + gt[i].y, p);
+      if (gt[i].z != gt[i].y && w[i][1] > p + 1) atomicMin(wire + gt[i].z, p + 1);
+      if (gt[i].w != gt[i].y && gt[i].w != gt[i].z && w[i][2] > p + 2) atomicMin(wire + gt[i].w, p + 2);
+    }
   }
 }
 
 // pass 2: a slot is a first appearance iff wire[node] still equals its own tagged position; rank them with
 // one single-pass scan and overwrite the tag with n_in + rank  (compiler.rs:440-441).
 constexpr int kWireItems = 4;
-__global__ void __launch_bounds__(kBlock) k_wire_scan(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
+__global__ void __launch_bounds__(kBlock) k_wire_scan(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
                                                       uint32_t n_in, uint32_t* __restrict__ wire, unsigned long long* __restrict__ tile_state,
                                                       uint32_t* __restrict__ scalars) {
   __shared__ uint32_t s_mem[10];
+  if (tail_parked(scalars)) return;
+  const uint32_t* __restrict__ order = sort_wanted(scalars) ? order_arr : nullptr;
   const uint32_t tiles = (G + kBlock * kWireItems - 1) / (kBlock * kWireItems);
-  uint32_t tile = scan_claim_tile(scalars + S_TICKET, s_mem);
+  uint32_t tile = scan_claim_tile(scalars + S_TICKET2, s_mem);
   uint32_t base = tile * (kBlock * kWireItems) + threadIdx.x * kWireItems;
-  uint32_t node[kWireItems][3];
-  uint32_t fl[kWireItems];
-  uint32_t sum = 0;
+  uint32_t g[kWireItems];
+  uint4 gt[kWireItems];
+  uint32_t w[kWireItems][3];
+  // batched loads: 4 order entries (one 128-bit load), 4 gates, 12 wire words in flight per thread
+  if (order && base + kWireItems <= G) {
+    uint4 o = __ldg(reinterpret_cast<const uint4*>(order + base));
+    g[0] = o.x; g[1] = o.y; g[2] = o.z; g[3] = o.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < kWireItems; ++i) { uint32_t k = min(base + i, G - 1); g[i] = order ? __ldg(order + k) : k; }
+  }
+#pragma unroll
+  for (int i = 0; i < kWireItems; ++i) gt[i] = order ? __ldg(gates + g[i]) : ldg_stream(gates + g[i]);
+#pragma unroll
+  for (int i = 0; i < kWireItems; ++i) { w[i][0] = __ldcg(wire + gt[i].y); w[i][1] = __ldcg(wire + gt[i].z); w[i][2] = __ldcg(wire + gt[i].w); }
+  uint32_t fl = 0, sum = 0;
 #pragma unroll
   for (int i = 0; i < kWireItems; ++i) {
     uint32_t k = base + i;
-    fl[i] = 0;
-    if (k < G) {
-      uint32_t g = order ? order[k] : k;
-      uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
-      node[i][0] = gt.y; node[i][1] = gt.z; node[i][2] = gt.w;
-      uint32_t p = kFirstTag | (3u * k);
-      uint32_t f0 = __ldcg(wire + gt.y) == p;
-      uint32_t f1 = __ldcg(wire + gt.z) == p + 1;
-      uint32_t f2 = __ldcg(wire + gt.w) == p + 2;
-      fl[i] = f0 | (f1 << 1) | (f2 << 2);
-      sum += f0 + f1 + f2;
-    }
+    uint32_t p = kFirstTag | (3u * k);
+    uint32_t f = k < G ? (uint32_t)(w[i][0] == p) | ((uint32_t)(w[i][1] == p + 1) << 1) | ((uint32_t)(w[i][2] == p + 2) << 2) : 0u;
+    fl |= f << (3 * i);
+    sum += __popc(f);
   }
   uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, scalars + S_NMID, tile == tiles - 1);
-  uint32_t w = n_in + ex;
+  uint32_t wid = n_in + ex;
 #pragma unroll
   for (int i = 0; i < kWireItems; ++i) {
-    if (fl[i] & 1) wire[node[i][0]] = w++;
-    if (fl[i] & 2) wire[node[i][1]] = w++;
-    if (fl[i] & 4) wire[node[i][2]] = w++;
+    if (fl & (1u << (3 * i))) wire[gt[i].y] = wid++;
+    if (fl & (2u << (3 * i))) wire[gt[i].z] = wid++;
+    if (fl & (4u << (3 * i))) wire[gt[i].w] = wid++;
   }
 }
 
 // K7: gather (compiler.rs:452-464).  op stays numeric; the host maps it to the strum Display token.
-__global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gates, const uint32_t* __restrict__ order, uint32_t G,
-                                                   const uint32_t* __restrict__ wire, uint4* __restrict__ new_gates) {
-  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
-    uint32_t g = order ? order[k] : k;
-    uint4 gt = order ? __ldg(gates + g) : ldg_stream(gates + g);
-    stg_stream(new_gates + k, make_uint4(gt.x, __ldg(wire + gt.y), __ldg(wire + gt.z), __ldg(wire + gt.w)));
+constexpr int kGatherIlp = 2;
+__global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
+                                                   const uint32_t* __restrict__ wire, uint4* __restrict__ new_gates, const uint32_t* __restrict__ sc) {
+  if (tail_parked(sc)) return;
+  const uint32_t* __restrict__ order = sort_wanted(sc) ? order_arr : nullptr;
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t k0 = blockIdx.x * kBlock + threadIdx.x; k0 < G; k0 += stride * kGatherIlp) {
+    uint32_t g[kGatherIlp];
+    uint4 gt[kGatherIlp];
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) { uint32_t k = min(k0 + i * stride, G - 1); g[i] = order ? __ldg(order + k) : k; }
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) gt[i] = order ? __ldg(gates + g[i]) : ldg_stream(gates + g[i]);
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) { gt[i].y = __ldg(wire + gt[i].y); gt[i].z = __ldg(wire + gt[i].z); gt[i].w = __ldg(wire + gt[i].w); }
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) { uint32_t k = k0 + i * stride; if (k < G) stg_stream(new_gates + k, gt[i]); }
   }
 }
 
@@ -549,6 +651,7 @@ static cudaEvent_t next_event(c2a_handle* h) {
 void phases_clear(c2a_handle* h) {
   h->phases.clear();
   h->ev_next = 0;
+  h->relax_fallback_rounds = 0;
 }
 void phase_begin(c2a_handle* h, const char* name) {
   if (!h->timing) return;
@@ -563,6 +666,7 @@ void phase_end(c2a_handle* h) {
 }
 void phases_collect(c2a_handle* h) {
   h->last_ms.clear();
+  h->last_ms.push_back({"n_relax_fallback_rounds", (double)h->relax_fallback_rounds});  // a count, not a time (diagnostics)
   if (!h->timing || h->phases.empty()) return;
   std::map<std::string, double> acc;
   std::vector<std::string> names;
@@ -611,7 +715,7 @@ size_t sort_scratch_bytes(uint64_t n) {
   b += align256(n);                // state
   b += align256(4 * ((n + 31) / 32 + 1));  // inq
   b += 3 * align256(4 * n);        // q0 q1 heavy
-  b += align256(8 * (size_t)(scan_tiles(n, kWireItems) + 1));  // tile_state (sized for the finer tiling)
+  b += align256(8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(n, kWireItems) + 2));  // tile_state: block-offset scan + wire scan
   b += align256(4 * S_COUNT);
   return b;
 }
@@ -624,66 +728,106 @@ bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s) {
   s->q0 = (uint32_t*)slab_alloc(h, 4 * n);
   s->q1 = (uint32_t*)slab_alloc(h, 4 * n);
   s->heavy = (uint32_t*)slab_alloc(h, 4 * n);
-  s->tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(n, kWireItems) + 1));
+  s->tile_state_bytes = 8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(n, kWireItems) + 2);
+  s->tile_state = (unsigned long long*)slab_alloc(h, s->tile_state_bytes);
+  s->tile_state2 = s->tile_state ? s->tile_state + scan_tiles(n, kScanItems) + 1 : nullptr;
   s->scalars = (uint32_t*)slab_alloc(h, 4 * S_COUNT);
   return s->scalars != nullptr;
 }
 
-// Exact reference order from dependency pairs (K5a-c).  Precondition: scalars zeroed except S_FLAGS, S_ERR = ~0.
-int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_flags, const SortScratch& s, uint32_t* d_order,
-                   bool* identity_out, uint64_t* err_index) {
-  const bool nonidentity = (host_flags & (F_OOO | F_SELF)) != 0;
-  *identity_out = !nonidentity;
-  if (!nonidentity || n == 0) return C2A_OK;
-  cudaStream_t st = h->stream;
+// scalars = 0, err = ~0; look-back tile states = 0.  Stream-ordered, no host wait.
+void sort_scalars_reset(c2a_handle* h, const SortScratch& s) {
+  cudaMemsetAsync(s.scalars, 0, 4 * S_COUNT, h->stream);
+  cudaMemsetAsync(s.scalars + S_ERR_LO, 0xFF, 8, h->stream);
+  cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, h->stream);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Exact reference order from dependency pairs (K5a-c), enqueued WITHOUT host round trips:
+//   sort_enqueue_relax   scratch init, seed, kSpecRounds relax rounds (a round with an empty queue exits at once)
+//   sort_enqueue_emit    block sizes, offsets scan, size-1 blocks, per-tree DFS
+// every kernel reads scalars[] to decide whether it has work (identity order / bad input / r[] not yet converged).
+// After the caller's final status read, sort_pending() tells whether the speculative rounds were not enough; then
+// sort_drain() finishes the relaxation with host-synchronised rounds and the caller re-issues everything from
+// sort_enqueue_emit on (sort_rearm() restores the scalars those kernels consume).
+// Precondition: scalars zeroed except S_FLAGS, S_ERR = ~0 (sort_scalars_reset + the deps kernel).
+// ---------------------------------------------------------------------------------------------------
+void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s) {
+  if (n == 0) return;
   uint32_t* sc = s.scalars;
-  // ---- K5a
   phase_begin(h, "init");
-  LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, n), kBlock, s.r, n);
-  cudaMemsetAsync(s.inq, 0, 4 * ((size_t)(n + 31) / 32 + 1), st);
-  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
-  cudaMemsetAsync(s.state, 0, n, st);
+  LAUNCH(h, k_sort_init, grid_for(h, (const void*)k_sort_init, kBlock, (uint64_t)n + 1), kBlock, n, s.r, s.size_off, s.state, s.inq, sc);
   phase_end(h);
   phase_begin(h, "k_relax");
-  LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_Q0N);
-  uint32_t *qin = s.q0, *qout = s.q1;
-  int nin = S_Q0N, nout = S_Q1N;
-  // Rounds are launched in batches of 4 with a fixed grid (the queue length lives on the device); the host looks
-  // at the queue length once per batch.
+  LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_QN0, sc);
   const int round_grid = h->num_sms * 4;
-  while (true) {
-    for (int b = 0; b < 4; ++b) {
-      cudaMemsetAsync(sc + nout, 0, 4, st);
-      LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
-      std::swap(qin, qout);
-      std::swap(nin, nout);
-    }
-    if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 32, sc + nin, 4, cudaMemcpyDeviceToHost, st), "relax count copy")) return C2A_ERR_CUDA;
-    if (!cuda_ok(h, cudaStreamSynchronize(st), "relax sync")) return C2A_ERR_CUDA;
-    if (h->h_pinned[32] == 0) break;
-  }
+  for (int j = 0; j < kSpecRounds; ++j)
+    LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, (j & 1) ? s.q1 : s.q0, sc + S_QN0 + j, (j & 1) ? s.q0 : s.q1, sc + S_QN0 + j + 1);
   phase_end(h);
-  // ---- K5b
+}
+
+void sort_enqueue_emit(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s, uint32_t* d_order) {
+  if (n == 0) return;
+  uint32_t* sc = s.scalars;
   phase_begin(h, "k_sizes");
-  LAUNCH(h, k_sizes, grid_for(h, (const void*)k_sizes, kBlock, n), kBlock, s.r, n, s.size_off);
+  LAUNCH(h, k_sizes, grid_for(h, (const void*)k_sizes, kBlock, n), kBlock, s.r, n, s.size_off, sc);
   phase_end(h);
-  uint32_t tiles = scan_tiles(n, kScanItems);
-  cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
-  cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
   phase_begin(h, "k_scan_u32");
-  LAUNCH(h, k_scan_u32, tiles, kBlock, s.size_off, n, s.tile_state, sc + S_TICKET);
+  LAUNCH(h, k_scan_u32, scan_tiles(n, kScanItems), kBlock, s.size_off, s.size_off, n, s.tile_state, sc + S_TICKET, sc);
   phase_end(h);
-  // ---- K5c
   phase_begin(h, "k_roots");
-  LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, (host_flags & F_SELF) ? 1u : 0u, d_order, s.heavy, sc);
+  LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, d_order, s.heavy, sc);
   phase_end(h);
   // heavy count is only known on the device: launch a grid sized for the worst case the hardware can hold
   phase_begin(h, "k_tree_dfs");
   LAUNCH(h, k_tree_dfs, h->num_sms * 8, 128, s.heavy, d_dep, s.r, s.size_off, s.state, d_order, sc);
   phase_end(h);
-  if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 40, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "sort status copy")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaStreamSynchronize(st), "sort sync")) return C2A_ERR_CUDA;
-  unsigned long long err = ((unsigned long long)h->h_pinned[40 + S_ERR_HI] << 32) | h->h_pinned[40 + S_ERR_LO];
+}
+
+bool sort_pending(const uint32_t* host_scalars) { return host_scalars[S_QN_LAST] != 0; }
+
+// host-synchronised continuation of the relaxation (deep out-of-order cones); returns the number of extra rounds or <0
+int sort_drain(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s) {
+  cudaStream_t st = h->stream;
+  uint32_t* sc = s.scalars;
+  // the live queue is the output of the last speculative round
+  uint32_t *qin = (kSpecRounds & 1) ? s.q1 : s.q0, *qout = (kSpecRounds & 1) ? s.q0 : s.q1;
+  int nin = S_QN_LAST, nout = S_QA, extra = 0;
+  const int round_grid = h->num_sms * 4;
+  phase_begin(h, "k_relax");
+  while (true) {
+    for (int b = 0; b < 4; ++b) {
+      cudaMemsetAsync(sc + nout, 0, 4, st);
+      LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
+      std::swap(qin, qout);
+      nin = nout;
+      nout = (nin == S_QA) ? S_QB : S_QA;
+      ++extra;
+    }
+    if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 32, sc + nin, 4, cudaMemcpyDeviceToHost, st), "relax count copy")) return -1;
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "relax sync")) return -1;
+    if (h->h_pinned[32] == 0) break;
+  }
+  phase_end(h);
+  h->relax_fallback_rounds += extra;
+  return extra;
+}
+
+// after sort_drain: everything sort_enqueue_emit and the wire kernels consume is put back to its initial state
+void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s) {
+  cudaStream_t st = h->stream;
+  uint32_t* sc = s.scalars;
+  cudaMemsetAsync(sc + S_HEAVYN, 0, 4 * (S_TICKET2 - S_HEAVYN + 1), st);  // heavy count, n_mid, both tickets
+  cudaMemsetAsync(sc + S_ERR_LO, 0xFF, 8, st);
+  cudaMemsetAsync(sc + S_QN_LAST, 0, 4, st);
+  cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, st);
+  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
+  cudaMemsetAsync(s.state, 0, n, st);
+}
+
+// status words -> reference error (topological_sort.rs:34-38)
+int sort_status(c2a_handle* h, const uint32_t* host_scalars, uint64_t* err_index) {
+  unsigned long long err = ((unsigned long long)host_scalars[S_ERR_HI] << 32) | host_scalars[S_ERR_LO];
   if (err != ~0ull) {
     uint64_t at = (uint32_t)err;
     if (err_index) *err_index = at;
@@ -713,10 +857,13 @@ static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pai
 
 // Core: everything after the gates are on the device.  d_wire may be null (internal), d_order may be null.
 // I/O node lists: either host arrays (staged through pinned memory) or, when d_io_ready != null, a device array holding
-// the n_in input nodes followed by the n_out output nodes.
+// the n_in input nodes followed by the n_out output nodes.  io_flags_dev (optional): a device word whose non-zero value
+// means "an I/O signal could not be mapped" (set by the caller's mapping kernel); it is read with the final status.
+// The whole pipeline is enqueued without intermediate host reads; ONE status read at the end.
 static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, const uint32_t* in_nodes_host,
                       const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
-                      uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr) {
+                      uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr,
+                      const uint32_t* io_flags_dev = nullptr) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
   size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
@@ -734,12 +881,9 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   uint32_t* io_nodes = d_io_ready ? const_cast<uint32_t*>(d_io_ready) : (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
   if (!ok || !prod1 || !dep || !order_int || !io_nodes) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   uint32_t* sc = s.scalars;
-
-  // scalars: zero, err = ~0
   uint32_t* hp = h->h_pinned;
-  for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
-  hp[S_ERR_LO] = hp[S_ERR_HI] = 0xFFFFFFFFu;
-  cudaMemcpyAsync(sc, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
+
+  sort_scalars_reset(h, s);
   if (n_pairs && !d_io_ready) {
     uint32_t* stage = hp + 256;
     if (p.n_in) memcpy(stage, in_nodes_host, 4 * (size_t)p.n_in);
@@ -755,59 +899,72 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
   phase_end(h);
   phase_begin(h, "k_deps");
-  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, prod1, dep, sc);
+  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, sc);
   phase_end(h);
-  if (!cuda_ok(h, cudaMemcpyAsync(hp, sc, 4, cudaMemcpyDeviceToHost, st), "flags copy")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaStreamSynchronize(st), "deps sync")) return C2A_ERR_CUDA;
-  uint32_t flags = hp[S_FLAGS];
-  if (flags & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", p.node_bound);
 
   uint32_t* d_order = d_order_user ? d_order_user : order_int;
-  bool identity = true;
-  int stt = sort_from_deps(h, dep, G, flags, s, d_order, &identity, err_index);
-  if (stt != C2A_OK) return stt;
-  if (identity_out) *identity_out = identity;
-  if (identity && d_order_user && G) {
-    phase_begin(h, "k_iota");
-    LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, G), kBlock, d_order_user, G);
-    phase_end(h);
-  }
-  if (!p.want_wire) return C2A_OK;
+  sort_enqueue_relax(h, dep, G, s);
 
-  const uint32_t* ord = identity ? nullptr : d_order;
   const uint32_t ni = p.n_in, no = p.n_out;
   const uint32_t* d_in = io_nodes;
   const uint32_t* d_out = io_nodes + ni;
-  if (ni) {
-    LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, d_wire, sc);
-    LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
+  // everything downstream of the relaxation; issued again after sort_drain() when the speculative rounds did not converge
+  auto enqueue_tail = [&]() {
+    sort_enqueue_emit(h, dep, G, s, d_order);
+    if (d_order_user && G) {
+      phase_begin(h, "k_iota");
+      LAUNCH(h, k_iota_if_identity, grid_for(h, (const void*)k_iota_if_identity, kBlock, G), kBlock, d_order_user, G, sc);
+      phase_end(h);
+    }
+    if (!p.want_wire) return;
+    if (ni) {
+      LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, d_wire, sc);
+      LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
+    }
+    if (no) LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, kOutPending, d_wire, sc);
+    if (G) {
+      phase_begin(h, "k_wire_first");
+      LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, ((uint64_t)G + kWireIlp - 1) / kWireIlp), kBlock, d_gates, d_order, G, d_wire, sc);
+      phase_end(h);
+      phase_begin(h, "k_wire_scan");
+      LAUNCH(h, k_wire_scan, scan_tiles(G, kWireItems), kBlock, d_gates, d_order, G, p.n_in, d_wire, s.tile_state2, sc);
+      phase_end(h);
+    }
+    if (no) {
+      LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, 0u, d_wire, sc);
+      LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, no), kBlock, d_out, no, p.node_bound, p.n_in, (const uint32_t*)(sc + S_NMID), d_wire);
+    }
+    if (d_new_gates && G) {
+      phase_begin(h, "k_gather");
+      LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, ((uint64_t)G + kGatherIlp - 1) / kGatherIlp), kBlock, d_gates, d_order, G, d_wire, d_new_gates, sc);
+      phase_end(h);
+    }
+  };
+  auto read_status = [&]() -> bool {
+    if (!cuda_ok(h, cudaMemcpyAsync(hp + 64, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "status copy")) return false;
+    if (io_flags_dev) cudaMemcpyAsync(hp + 64 + S_COUNT, io_flags_dev, 4, cudaMemcpyDeviceToHost, st);
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "final sync")) return false;
+    return cuda_ok(h, cudaGetLastError(), "kernel");
+  };
+
+  enqueue_tail();
+  if (!read_status()) return C2A_ERR_CUDA;
+  const uint32_t* hs = hp + 64;
+  if (io_flags_dev && hs[S_COUNT]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
+  if (hs[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", p.node_bound);
+  if (sort_pending(hs)) {
+    if (sort_drain(h, dep, G, s) < 0) return C2A_ERR_CUDA;
+    sort_rearm(h, G, s);
+    if (p.want_wire) cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
+    enqueue_tail();
+    if (!read_status()) return C2A_ERR_CUDA;
   }
-  if (no) LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, kOutPending, d_wire, sc);
-  phase_begin(h, "k_wire_first");
-  if (G) LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, G), kBlock, d_gates, ord, G, d_wire);
-  phase_end(h);
-  if (G) {
-    uint32_t tiles = scan_tiles(G, kWireItems);
-    cudaMemsetAsync(s.tile_state, 0, 8 * (size_t)tiles, st);
-    cudaMemsetAsync(sc + S_TICKET, 0, 4, st);
-    phase_begin(h, "k_wire_scan");
-    LAUNCH(h, k_wire_scan, tiles, kBlock, d_gates, ord, G, p.n_in, d_wire, s.tile_state, sc);
-    phase_end(h);
-  }
-  if (no) {
-    LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, 0u, d_wire, sc);
-    LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, no), kBlock, d_out, no, p.node_bound, p.n_in, (const uint32_t*)(sc + S_NMID), d_wire);
-  }
-  if (d_new_gates && G) {
-    phase_begin(h, "k_gather");
-    LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, G), kBlock, d_gates, ord, G, d_wire, d_new_gates);
-    phase_end(h);
-  }
-  if (!cuda_ok(h, cudaMemcpyAsync(hp + 64, sc, 4 * S_COUNT, cudaMemcpyDeviceToHost, st), "status copy")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaStreamSynchronize(st), "final sync")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaGetLastError(), "kernel")) return C2A_ERR_CUDA;
-  if (hp[64 + S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output node id is >= node_bound (%u)", p.node_bound);
-  if (wire_count) *wire_count = p.n_in + hp[64 + S_NMID] + p.n_out;
+  int stt = sort_status(h, hs, err_index);
+  if (stt != C2A_OK) return stt;
+  if (identity_out) *identity_out = !(hs[S_FLAGS] & (F_OOO | F_SELF));
+  if (!p.want_wire) return C2A_OK;
+  if (hs[S_FLAGS] & F_BAD_IO) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output node id is >= node_bound (%u)", p.node_bound);
+  if (wire_count) *wire_count = p.n_in + hs[S_NMID] + p.n_out;
   return C2A_OK;
 }
 
@@ -1007,25 +1164,33 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
   if (!ok || !d_off || !d_idx || !dep || !d_order) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   cudaStream_t stq = h->stream;
   uint32_t* hp = h->h_pinned;
-  for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
-  hp[S_ERR_LO] = hp[S_ERR_HI] = 0xFFFFFFFFu;
-  cudaMemcpyAsync(s.scalars, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, stq);
+  const uint32_t nn = (uint32_t)n;
+  sort_scalars_reset(h, s);
   cudaMemcpyAsync(d_off, dep_off, 8 * (n + 1), cudaMemcpyHostToDevice, stq);
   if (nnz) cudaMemcpyAsync(d_idx, dep_idx, 4 * nnz, cudaMemcpyHostToDevice, stq);
   phase_begin(h, "k_deps");
-  LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, (uint32_t)n, dep, s.scalars);
+  LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, nn, dep, s.scalars);
   phase_end(h);
-  cudaMemcpyAsync(hp, s.scalars, 4, cudaMemcpyDeviceToHost, stq);
-  if (!cuda_ok(h, cudaStreamSynchronize(stq), "deps sync")) return C2A_ERR_CUDA;
-  uint32_t flags = hp[S_FLAGS];
-  if (flags & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "dependency rows must have <= 2 entries with indices < n");
-  bool identity = true;
-  st = sort_from_deps(h, dep, (uint32_t)n, flags, s, d_order, &identity, err_index);
-  if (st == C2A_OK) {
-    if (identity) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, n), kBlock, d_order, (uint32_t)n);
-    cudaMemcpyAsync(order_out, d_order, 4 * n, cudaMemcpyDeviceToHost, stq);
+  sort_enqueue_relax(h, dep, nn, s);
+  auto tail = [&]() {
+    sort_enqueue_emit(h, dep, nn, s, d_order);
+    LAUNCH(h, k_iota_if_identity, grid_for(h, (const void*)k_iota_if_identity, kBlock, n), kBlock, d_order, nn, s.scalars);
+    cudaMemcpyAsync(hp + 64, s.scalars, 4 * S_COUNT, cudaMemcpyDeviceToHost, stq);
+    return cuda_ok(h, cudaStreamSynchronize(stq), "sort sync") && cuda_ok(h, cudaGetLastError(), "sort kernels");
+  };
+  if (!tail()) return C2A_ERR_CUDA;
+  const uint32_t* hs = hp + 64;
+  if (hs[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "dependency rows must have <= 2 entries with indices < n");
+  if (sort_pending(hs)) {
+    if (sort_drain(h, dep, nn, s) < 0) return C2A_ERR_CUDA;
+    sort_rearm(h, nn, s);
+    if (!tail()) return C2A_ERR_CUDA;
   }
-  if (!cuda_ok(h, cudaStreamSynchronize(stq), "sort sync") && st == C2A_OK) st = C2A_ERR_CUDA;
+  st = sort_status(h, hs, err_index);
+  if (st == C2A_OK) {
+    cudaMemcpyAsync(order_out, d_order, 4 * n, cudaMemcpyDeviceToHost, stq);
+    if (!cuda_ok(h, cudaStreamSynchronize(stq), "order D2H")) st = C2A_ERR_CUDA;
+  }
   phases_collect(h);
   return st;
 }

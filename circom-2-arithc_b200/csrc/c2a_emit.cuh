@@ -21,13 +21,16 @@
 // writes a fresh temporary (src/process.rs:470-475).
 //
 //   E0 k_ev_count      per-1024-event tile: #gates, #connections; 1+max signal id; kind/op validation
-//      k_ev_tile_scan  exclusive scan of the tile counts (single CTA)
+//      k_scan_u32 x2   exclusive scans of the two per-tile count arrays (single-pass, decoupled look-back)
 //   E1 k_ev_scatter    ballot/popc ranks inside a tile -> gate index / connection index / signal index of every
-//                      event; scatters into SoA arrays (sig_t, sig_meta | egates, gate_t | conn, conn_t, conn_sb)
+//                      event; scatters into SoA arrays (sig_t, sig_meta | egates, gate_t | conn, conn_t, conn_sb).
+//                      E0..E1 run back to back: their targets are sized by upper bounds and live in the staging allocation,
+//                      so the counts are only read by the host once, after the scatter.
 //   E2 k_ev_check_*    every reference precedes its use (else node-0 semantics), marks gate-output signals
 //   M  k_msf_pick / k_msf_hook   Boruvka: per class the minimum-time outgoing connection (tagged RED.MIN),
-//                      hook, path compression inside find; edge list shrinks every round
-//   N  k_scan_u32(eff), k_ev_nid_init, k_ev_nid_edges, k_ev_finalize, k_ev_gates
+//                      hook, path compression inside find; edge list shrinks every round.  kSpecMsf rounds are enqueued
+//                      unconditionally (an exhausted round exits at once); more only if the final status says so.
+//   N  k_scan_u32(eff), k_ev_nid_edges, k_ev_finalize, k_ev_gates
 #pragma once
 
 struct c2a_compiler;
@@ -35,8 +38,12 @@ struct c2a_compiler;
 namespace c2a {
 
 constexpr int kEvTile = 1024;  // events per CTA pass: 8 warps x 4 rows x 32 lanes
-enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_COUNT = 16 };
-enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128 };
+constexpr int kSpecMsf = 2;    // Boruvka rounds enqueued without looking at the live-edge count
+// ES_MC0 + 2r / + 2r + 1: candidate / live counts of speculative round r (zeroed once); ES_NCUR / ES_NCAND: the host-driven rounds
+enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_TICKET = 7, ES_ROUNDS = 8, ES_IOBAD = 9, ES_TICKET2 = 10,
+       ES_MC0 = 16, ES_COUNT = 32 };
+enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128,
+       EF_CAP = 256 /* a signal id beyond the table bound the pass was launched with: rerun with the exact bound */ };
 
 __device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
 #pragma unroll
@@ -55,11 +62,13 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) {
 }
 
 // ---- E0 ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_cnt,
-                                                     uint32_t* __restrict__ es) {
+// (A single fused pass - tile counts chained by a decoupled look-back inside the scatter - was measured at 0.67 ms on the
+//  42 M-event stream: every tile then carries ticket + load + look-back latency in series.  Reading the stream twice is faster.)
+__global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_g,
+                                                     uint32_t* __restrict__ tile_c, uint32_t* __restrict__ es) {
   __shared__ uint32_t s_g[8], s_c[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t tot_g = 0, tot_c = 0, smax = 0, f = 0;
+  uint32_t smax = 0, f = 0;
   for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     uint64_t base = (uint64_t)tile * kEvTile + warp * 128;
     uint32_t g = 0, c = 0;
@@ -86,9 +95,8 @@ __global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ e
       uint32_t tg = 0, tc = 0;
 #pragma unroll
       for (int w = 0; w < 8; ++w) { tg += s_g[w]; tc += s_c[w]; }
-      tile_cnt[tile] = tg | (tc << 16);
-      tot_g += tg;
-      tot_c += tc;
+      tile_g[tile] = tg;
+      tile_c[tile] = tc;
     }
     __syncthreads();
   }
@@ -98,46 +106,17 @@ __global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ e
     if (smax) atomicMax(es + ES_SBOUND, smax);
     if (f) atomicOr(es + ES_FLAGS, f);
   }
-  if (threadIdx.x == 0) {
-    if (tot_g) atomicAdd(es + ES_NGATE, tot_g);
-    if (tot_c) atomicAdd(es + ES_NCONN, tot_c);
-  }
-}
-
-// exclusive scan of the per-tile (gates, connections) counts; single CTA of 1024 threads
-__global__ void __launch_bounds__(1024) k_ev_tile_scan(const uint32_t* __restrict__ tile_cnt, uint32_t tiles, uint2* __restrict__ tile_base) {
-  __shared__ uint32_t s_g[32], s_c[32];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t per = (tiles + 1023) / 1024;
-  uint32_t lo = min(tiles, threadIdx.x * per), hi = min(tiles, lo + per);
-  uint32_t g = 0, c = 0;
-  for (uint32_t i = lo; i < hi; ++i) { uint32_t v = tile_cnt[i]; g += v & 0xFFFFu; c += v >> 16; }
-  uint32_t ig = warp_incl_scan(g, lane), ic = warp_incl_scan(c, lane);
-  if (lane == 31) { s_g[warp] = ig; s_c[warp] = ic; }
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t wg = s_g[lane], wc = s_c[lane];
-    uint32_t sg = warp_incl_scan(wg, lane), sc = warp_incl_scan(wc, lane);
-    s_g[lane] = sg - wg;
-    s_c[lane] = sc - wc;
-  }
-  __syncthreads();
-  uint32_t rg = s_g[warp] + ig - g, rc = s_c[warp] + ic - c;
-  for (uint32_t i = lo; i < hi; ++i) {
-    uint32_t v = tile_cnt[i];
-    tile_base[i] = make_uint2(rg, rc);
-    rg += v & 0xFFFFu;
-    rc += v >> 16;
-  }
 }
 
 // ---- E1 ---------------------------------------------------------------------------------------------------
+// tile_g / tile_c: exclusive scans of the per-tile counts (k_scan_u32), entry [tiles] = totals.
 // sig_t[sid]    event index of the declaration (kNone = never declared)
 // sig_meta[sid] {signal index (declaration rank) | is_const << 31, #connections before the declaration}
 // egates[g]     {op, lhs signal, rhs signal, out signal};  gate_t[g] event index
 // conn[c]       {a, b};  conn_t[c] event index;  conn_sb[c] #signals declared before the connection
-__global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, const uint2* __restrict__ tile_base,
-                                                       uint32_t S, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta, uint4* __restrict__ egates,
+__global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, uint32_t S_cap,
+                                                       const uint32_t* __restrict__ tile_g, const uint32_t* __restrict__ tile_c,
+                                                       uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta, uint4* __restrict__ egates,
                                                        uint32_t* __restrict__ gate_t, uint2* __restrict__ conn, uint32_t* __restrict__ conn_t,
                                                        uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
   __shared__ uint32_t s_g[8], s_c[8];
@@ -154,6 +133,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
       e[j] = make_uint4(0xFFu, 0, 0, 0);
       if (i < n) e[j] = ldg_stream(ev + i);
     }
+    uint32_t gi = __ldg(tile_g + tile), ci = __ldg(tile_c + tile);
     uint32_t wg = 0, wc = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -165,8 +145,6 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
     }
     if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; }
     __syncthreads();
-    uint2 tb = tile_base[tile];
-    uint32_t gi = tb.x, ci = tb.y;
     for (int w = 0; w < warp; ++w) { gi += s_g[w]; ci += s_c[w]; }
     __syncthreads();
 #pragma unroll
@@ -181,21 +159,19 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
       uint32_t my_s = t - my_g - my_c;  // signals declared before this event
       if (kind <= C2A_EV_SIGNAL_CONST) {
         // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the
-        // number of declared ids then falls short of the number of signal events (k_ev_nid_init counts them)
+        // number of declared ids then falls short of the number of signal events (k_ev_finalize counts them)
         uint32_t sid = e[j].y;
-        sig_t[sid] = t;
-        sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
+        if (sid >= S_cap) f |= EF_CAP;
+        else {
+          sig_t[sid] = t;
+          sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
+        }
       } else if (kind == C2A_EV_GATE) {
-        // out-of-range references are flagged and neutralised so that every later kernel stays memory-safe; the flags
-        // are only looked at once, at the end (the stream is then replayed by the host emitter)
-        bool oob = e[j].y >= S || e[j].z >= S || e[j].w >= S;
-        if (oob) f |= EF_UNKNOWN_REF;
-        egates[my_g] = oob ? make_uint4(e[j].x >> 8, 0, 0, 0) : make_uint4(e[j].x >> 8, e[j].y, e[j].z, e[j].w);
+        // operands are range-checked (and neutralised) by k_ev_check_gates
+        egates[my_g] = make_uint4(e[j].x >> 8, e[j].y, e[j].z, e[j].w);
         gate_t[my_g] = t;
-      } else {
-        bool oob = e[j].y >= S || e[j].z >= S;
-        if (oob) f |= EF_UNKNOWN_REF;
-        conn[my_c] = oob ? make_uint2(0, 0) : make_uint2(e[j].y, e[j].z);
+      } else if (kind == C2A_EV_CONNECT) {
+        conn[my_c] = make_uint2(e[j].y, e[j].z);
         conn_t[my_c] = t;
         conn_sb[my_c] = my_s;
       }
@@ -206,26 +182,34 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
 }
 
 // ---- E2 ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_ev_check_gates(const uint4* __restrict__ egates, const uint32_t* __restrict__ gate_t, uint32_t G, uint32_t S,
+__global__ void __launch_bounds__(kBlock) k_ev_check_gates(uint4* __restrict__ egates, const uint32_t* __restrict__ gate_t, uint32_t G, uint32_t S,
                                                            const uint32_t* __restrict__ sig_t, uint8_t* __restrict__ outmark, uint32_t* __restrict__ es) {
   bool bad = false;
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint4 e = egates[g];
     uint32_t t = gate_t[g];
+    if (!(e.y < S && e.z < S && e.w < S)) {
+      // out-of-range reference: flagged, and neutralised so that every later kernel stays memory-safe; the flags are only
+      // looked at once, at the end (the stream is then replayed by the host emitter)
+      bad = true;
+      egates[g] = make_uint4(e.x, 0, 0, 0);
+      continue;
+    }
     // a signal that is not declared BEFORE the gate resolves to node 0 / panics in the reference (compiler.rs:183, :201)
-    bool ok = e.y < S && e.z < S && e.w < S && __ldg(sig_t + e.y) < t && __ldg(sig_t + e.z) < t && __ldg(sig_t + e.w) < t;
+    bool ok = __ldg(sig_t + e.y) < t && __ldg(sig_t + e.z) < t && __ldg(sig_t + e.w) < t;
     if (!ok) bad = true;
     else outmark[e.w] = 1;  // compiler.rs:201 marks the out node is_out
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_UNKNOWN_REF);
 }
-__global__ void __launch_bounds__(kBlock) k_ev_check_conns(const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_t, uint32_t C, uint32_t S,
+__global__ void __launch_bounds__(kBlock) k_ev_check_conns(uint2* __restrict__ conn, const uint32_t* __restrict__ conn_t, uint32_t C, uint32_t S,
                                                            const uint32_t* __restrict__ sig_t, uint32_t* __restrict__ es) {
   bool bad = false;
   for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < C; c += gridDim.x * kBlock) {
     uint2 ab = conn[c];
     uint32_t t = conn_t[c];
-    if (!(ab.x < S && ab.y < S && __ldg(sig_t + ab.x) < t && __ldg(sig_t + ab.y) < t)) bad = true;
+    if (!(ab.x < S && ab.y < S)) { bad = true; conn[c] = make_uint2(0, 0); continue; }
+    if (!(__ldg(sig_t + ab.x) < t && __ldg(sig_t + ab.y) < t)) bad = true;
   }
   if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_UNKNOWN_REF);
 }
@@ -258,7 +242,9 @@ __device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
 // First round: the live list is every connection, and almost every one is a candidate, so cand[] is written in place
 // (cand[e], kNone in .x for a connection that is already internal) instead of being compacted through one global counter.
 __global__ void __launch_bounds__(kBlock) k_msf_pick_first(const uint2* __restrict__ conn, uint32_t n, uint32_t* __restrict__ parent,
-                                                           uint32_t* __restrict__ best, uint32_t tag, uint4* __restrict__ cand) {
+                                                           uint32_t* __restrict__ best, uint32_t tag, uint4* __restrict__ cand,
+                                                           uint32_t* __restrict__ n_cand) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_cand = n;  // every slot of cand[] is written; dead ones carry kNone
   for (uint32_t e = blockIdx.x * kBlock + threadIdx.x; e < n; e += gridDim.x * kBlock) {
     uint2 ab = conn[e];
     uint4 out = make_uint4(kNone, 0, 0, 0);
@@ -302,9 +288,10 @@ __global__ void __launch_bounds__(kBlock) k_msf_pick(const uint2* __restrict__ c
 // goes under the smaller.  Edges not chosen by either side stay on the live list.
 __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ parent,
                                                      const uint32_t* __restrict__ best, uint32_t tag, uint32_t* __restrict__ eff,
-                                                     uint32_t* __restrict__ cur, uint32_t* __restrict__ n_cur) {
+                                                     uint32_t* __restrict__ cur, uint32_t* __restrict__ n_cur, uint32_t* __restrict__ n_rounds) {
   const uint32_t n = *n_cand;
   const int lane = threadIdx.x & 31;
+  if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_rounds, 1u);  // a round that examined candidates
   for (uint32_t i0 = blockIdx.x * kBlock + (threadIdx.x & ~31u); i0 < n; i0 += gridDim.x * kBlock) {
     uint32_t i = i0 + lane;
     bool keep = false;
@@ -325,48 +312,47 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
 }
 
 // ---- N: node ids ----------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_ev_nid_init(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
-                                                        const uint32_t* __restrict__ effx, uint32_t* __restrict__ nid, uint32_t* __restrict__ es) {
-  uint32_t declared = 0;
-  for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
-    uint32_t id = 0;
-    if (sig_t[s] != kNone) {
-      uint2 m = sig_meta[s];
-      id = (m.x & 0x7FFFFFFFu) + 1u + __ldg(effx + m.y);  // compiler.rs:157 with node_count = signals + effective merges so far
-      ++declared;
-    }
-    nid[s] = id;
-  }
-  declared = warp_sum(declared);
-  if ((threadIdx.x & 31) == 0 && declared) atomicAdd(es + ES_NDECL, declared);
-}
+// nc[root] = {largest id among the class's effective connections (0 = none), merge-screen counters}.  The ids grow with the
+// event index, and every member of a class of >= 2 signals is joined by an effective connection AFTER its declaration, so the
+// class ends with the id of its last effective connection (compiler.rs:257); a class without one is a single signal and keeps
+// the id of its declaration (compiler.rs:157).
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
-                                                         const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint32_t* __restrict__ nid) {
+                                                         const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint2* __restrict__ nc) {
   for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < C; c += gridDim.x * kBlock) {
     uint32_t x = effx[c];
     if (effx[c + 1] == x) continue;                     // not effective: no id consumed (compiler.rs:235-237)
-    uint32_t id = conn_sb[c] + x + 1u;                   // compiler.rs:257
-    atomicMax(nid + uf_find(parent, conn[c].x), id);
+    uint32_t id = conn_sb[c] + x + 1u;                   // compiler.rs:257 with node_count = signals + effective merges so far
+    atomicMax(&nc[uf_find(parent, conn[c].x)].x, id);
   }
 }
-// node_of_signal + the merge-error screens (compiler.rs:239-245); cnt[] = per class {#const signals, #gate-output signals << 16}
+// node_of_signal + the merge-error screens (compiler.rs:239-245); nc[root].y = {#const signals, #gate-output signals << 16}
 __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
-                                                        const uint8_t* __restrict__ outmark, uint32_t* __restrict__ parent,
-                                                        const uint32_t* __restrict__ nid, uint32_t* __restrict__ cnt, uint32_t* __restrict__ nos,
+                                                        const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ effx,
+                                                        uint32_t* __restrict__ parent, uint2* __restrict__ nc, uint32_t* __restrict__ nos,
                                                         uint32_t* __restrict__ es) {
-  uint32_t f = 0;
+  uint32_t f = 0, declared = 0;
   for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
     uint32_t node = 0;
     if (sig_t[s] != kNone) {
+      ++declared;
+      uint2 m = sig_meta[s];
       uint32_t r = uf_find(parent, s);
-      node = nid[r];
-      if (sig_meta[s].x & 0x80000000u) { if (atomicAdd(cnt + r, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
-      if (outmark[s]) { if (atomicAdd(cnt + r, 0x10000u) >> 16) f |= EF_OUT_OUT; }
+      node = __ldcg(&nc[r].x);
+      if (node == 0) {
+        node = (m.x & 0x7FFFFFFFu) + 1u + __ldg(effx + m.y);  // a class of one: compiler.rs:157
+      } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
+        if (m.x & 0x80000000u) { if (atomicAdd(&nc[r].y, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
+        if (outmark[s]) { if (atomicAdd(&nc[r].y, 0x10000u) >> 16) f |= EF_OUT_OUT; }
+      }
     }
     nos[s] = node;
   }
   f = warp_or(f);
-  if ((threadIdx.x & 31) == 0 && f) atomicOr(es + ES_FLAGS, f);
+  declared = warp_sum(declared);
+  if ((threadIdx.x & 31) == 0) {
+    if (f) atomicOr(es + ES_FLAGS, f);
+    if (declared) atomicAdd(es + ES_NDECL, declared);
+  }
 }
 __global__ void __launch_bounds__(kBlock) k_ev_gates(const uint4* __restrict__ egates, uint32_t G, uint32_t S, const uint32_t* __restrict__ nos,
                                                      uint4* __restrict__ gates) {
@@ -385,20 +371,17 @@ __global__ void __launch_bounds__(kBlock) k_ev_map_io(const uint32_t* __restrict
     if (nd == 0) bad = true;
     nodes[i] = nd;
   }
-  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(es + ES_FLAGS, (uint32_t)EF_BAD_IO);
+  if (__syncthreads_or(bad) && threadIdx.x == 0) es[ES_IOBAD] = 1u;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-static inline size_t emit_scratch_bytes(uint64_t n, uint64_t G, uint64_t C, uint64_t S) {
+static inline size_t emit_scratch_bytes(uint64_t G, uint64_t C, uint64_t S) {  // slab part (exact sizes; the scatter targets live in the staging buffer)
   size_t b = 0;
-  b += align256(4 * S) + align256(8 * S);                                   // sig_t, sig_meta
-  b += align256(16 * G) + align256(4 * G);                                  // egates, gate_t
-  b += align256(8 * C) + 2 * align256(4 * C);                               // conn, conn_t, conn_sb
   b += align256(S);                                                         // outmark
-  b += 3 * align256(4 * S);                                                 // parent, best/cnt, nid
-  b += align256(4 * (C + 1)) + align256(4 * C) + align256(16 * C);          // eff/effx, cur, cand
+  b += 2 * align256(4 * S) + align256(8 * S);                               // parent, best, nc
+  b += 2 * align256(4 * (C + 1)) + align256(4 * C) + align256(16 * C);      // eff, effx, cur, cand
   b += align256(8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1)) + 256;     // tile_state + ticket
-  (void)n;
+  (void)G;
   return b;
 }
 
@@ -493,34 +476,88 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   phases_clear(h);
   cudaStream_t s = h->stream;
   const uint32_t tiles = (uint32_t)((n + kEvTile - 1) / kEvTile);
-  // staging buffer (outside the slab: the slab is sized only once the counts are known)
-  const size_t ev_copy = ev_dev ? 0 : align256(16 * n);
-  size_t ev_need = ev_copy + align256(4 * (size_t)tiles + 4) + align256(8 * (size_t)tiles + 8) + align256(4 * ES_COUNT);
-  if (ev_need > h->ev_bytes) {
-    if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
-    if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
-    h->ev_bytes = ev_need + ev_need / 16;
-  }
-  const uint4* d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
-  uint32_t* tile_cnt = (uint32_t*)(h->ev_buf + ev_copy);
-  uint2* tile_base = (uint2*)((char*)tile_cnt + align256(4 * (size_t)tiles + 4));
-  uint32_t* es = (uint32_t*)((char*)tile_base + align256(8 * (size_t)tiles + 8));
   uint32_t* hp = h->h_pinned;
+  const int wide = h->num_sms * 8;
 
-  phase_begin(h, "h2d");
-  if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
-  phase_end(h);
-  cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
-  phase_begin(h, "k_ev_count");
-  if (n) LAUNCH(h, k_ev_count, std::min<uint32_t>(tiles, (uint32_t)h->num_sms * 8), kBlock, d_ev, n, tiles, tile_cnt, es);
-  phase_end(h);
-  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-  if (!cuda_ok(h, cudaStreamSynchronize(s), "count sync")) return C2A_ERR_CUDA;
-  const uint64_t G = hp[ES_NGATE], C = hp[ES_NCONN];
-  const uint32_t S = hp[ES_SBOUND];
-  uint32_t flags = hp[ES_FLAGS];
-  const uint64_t n_sig = n - G - C;
-  if (!(flags & (EF_BAD_KIND | EF_SPARSE)) && (uint64_t)S > 4 * n_sig + (1u << 20)) flags |= EF_SPARSE;  // a dense table would be mostly holes
+  // ---- E1: one pass over the events.  Its targets are sized by upper bounds (G, C <= n; signal ids < S_cap) and live in the
+  // staging allocation next to the event copy, so nothing has to be counted first.  Walker streams number their signals
+  // densely (runtime.rs:120-125), so S_cap = n + 2^20 holds them; a stream with larger ids reruns the pass with its exact bound.
+  uint64_t S_cap = std::min<uint64_t>(n + (1u << 20), 0x7FFFFFFEull);
+  uint32_t *es = nullptr, *sig_t = nullptr, *gate_t = nullptr, *conn_t = nullptr, *conn_sb = nullptr;
+  uint2 *sig_meta = nullptr, *conn = nullptr;
+  uint4* egates = nullptr;
+  const uint4* d_ev = nullptr;
+  uint64_t G = 0, C = 0, n_sig = 0;
+  uint32_t S = 0, flags = 0;
+  bool copied = false;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    const size_t ev_copy = ev_dev ? 0 : align256(16 * n);
+    const size_t ev_need = ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
+                           align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n);
+    if (ev_need > h->ev_bytes) {
+      if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
+      if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+      h->ev_bytes = ev_need + ev_need / 16;
+      copied = false;
+    }
+    char* q = h->ev_buf + ev_copy;
+    auto take = [&](size_t bytes) { char* r = q; q += align256(bytes); return r; };
+    const uint32_t ctiles = scan_tiles((uint64_t)tiles + 1, kScanItems);
+    uint32_t* tile_g = (uint32_t*)take(4 * ((size_t)tiles + 2));
+    uint32_t* tile_c = (uint32_t*)take(4 * ((size_t)tiles + 2));
+    unsigned long long* cnt_state = (unsigned long long*)take(16 * ((size_t)ctiles + 1));  // look-back states of the two count scans
+    es = (uint32_t*)take(4 * ES_COUNT);
+    sig_t = (uint32_t*)take(4 * S_cap);
+    sig_meta = (uint2*)take(8 * S_cap);
+    egates = (uint4*)take(16 * n);
+    gate_t = (uint32_t*)take(4 * n);
+    conn_t = (uint32_t*)take(4 * n);
+    conn_sb = (uint32_t*)take(4 * n);
+    conn = (uint2*)take(8 * n);
+    d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
+
+    if (!copied) {
+      phase_begin(h, "h2d");
+      if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
+      phase_end(h);
+      copied = true;
+    }
+    phase_begin(h, "init");
+    cudaMemsetAsync(cnt_state, 0, 16 * ((size_t)ctiles + 1), s);
+    cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
+    cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
+    phase_end(h);
+    if (tiles) {
+      const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
+      phase_begin(h, "k_ev_count");
+      LAUNCH(h, k_ev_count, egrid, kBlock, d_ev, n, tiles, tile_g, tile_c, es);
+      phase_end(h);
+      phase_begin(h, "k_scan_u32");
+      LAUNCH(h, k_scan_u32, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, es + ES_TICKET, (const uint32_t*)nullptr);
+      LAUNCH(h, k_scan_u32, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, es + ES_TICKET2, (const uint32_t*)nullptr);
+      phase_end(h);
+      phase_begin(h, "k_ev_scatter");
+      LAUNCH(h, k_ev_scatter, egrid, kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
+      phase_end(h);
+      cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
+      cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
+    }
+    cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+    if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
+    if (!cuda_ok(h, cudaGetLastError(), "event scatter")) return C2A_ERR_CUDA;
+    G = hp[ES_NGATE];
+    C = hp[ES_NCONN];
+    S = hp[ES_SBOUND];
+    flags = hp[ES_FLAGS];
+    n_sig = n - G - C;
+    if (!(flags & (EF_BAD_KIND | EF_SPARSE)) && (uint64_t)S > 4 * n_sig + (1u << 20)) flags |= EF_SPARSE;  // a dense table would be mostly holes
+    if ((flags & EF_CAP) && !(flags & (EF_BAD_KIND | EF_BAD_OP | EF_SPARSE)) && attempt == 0) {
+      S_cap = S;  // valid but gappy ids: once more with the exact table bound
+      continue;
+    }
+    break;
+  }
+  flags &= ~(uint32_t)EF_CAP;
   if (info) { info->n_gates = G; info->n_connections = C; info->n_signals = n_sig; info->signal_bound = S; }
 
   std::vector<c2a_event> ev_back;
@@ -545,22 +582,16 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   size_t build_need = core_scratch_bytes(bp, 1u << 20) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)NB_ub);
   slab_reset(h);
   emit_drop_host(h);
-  if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(n, G, C, S), build_need))) return C2A_ERR_NO_MEMORY;
+  if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(G, C, S), build_need))) return C2A_ERR_NO_MEMORY;
   uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
   uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   const size_t keep = h->slab_used;
-  uint32_t* sig_t = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
-  uint2* sig_meta = (uint2*)slab_alloc(h, 8 * (size_t)S);
-  uint4* egates = (uint4*)slab_alloc(h, 16 * G);
-  uint32_t* gate_t = (uint32_t*)slab_alloc(h, 4 * G);
-  uint2* conn = (uint2*)slab_alloc(h, 8 * C);
-  uint32_t* conn_t = (uint32_t*)slab_alloc(h, 4 * C);
-  uint32_t* conn_sb = (uint32_t*)slab_alloc(h, 4 * C);
   uint8_t* outmark = (uint8_t*)slab_alloc(h, S);
   uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
-  uint32_t* nid = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint2* nc = (uint2*)slab_alloc(h, 8 * (size_t)S);
   uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * (C + 1));
+  uint32_t* effx = (uint32_t*)slab_alloc(h, 4 * (C + 1));
   uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
   uint4* cand = (uint4*)slab_alloc(h, 16 * C);
   unsigned long long* tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1));
@@ -568,18 +599,10 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   if (!ticket) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
 
   phase_begin(h, "init");
-  cudaMemsetAsync(sig_t, 0xFF, 4 * (size_t)S, s);
   cudaMemsetAsync(outmark, 0, S, s);
   cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
   cudaMemsetAsync(eff, 0, 4 * (C + 1), s);
   if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
-  phase_end(h);
-  const int wide = h->num_sms * 8;
-  phase_begin(h, "k_ev_tile_scan");
-  if (tiles) LAUNCH(h, k_ev_tile_scan, 1, 1024, tile_cnt, tiles, tile_base);
-  phase_end(h);
-  phase_begin(h, "k_ev_scatter");
-  if (tiles) LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)wide), kBlock, d_ev, n, tiles, tile_base, S, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
   phase_end(h);
   phase_begin(h, "k_ev_check_gates");
   if (G) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
@@ -588,64 +611,69 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   if (C) LAUNCH(h, k_ev_check_conns, grid_for(h, (const void*)k_ev_check_conns, kBlock, C), kBlock, conn, conn_t, (uint32_t)C, S, sig_t, es);
   phase_end(h);
 
-  // ---- Boruvka rounds
-  uint32_t rounds = 0;
+  // ---- Boruvka rounds.  Round r: candidates counted in *ncand, surviving (undecided) edges in *ncur.
+  uint32_t rounds_issued = 0;
+  auto msf_round = [&](uint32_t* ncur_prev, uint32_t* ncand, uint32_t* ncur) {
+    uint32_t tag = (6u - (rounds_issued % 7u)) << 29;
+    if (rounds_issued && (rounds_issued % 7u) == 0) cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);  // tags wrapped: forget the old minima
+    phase_begin(h, "k_msf_pick");
+    if (rounds_issued == 0) LAUNCH(h, k_msf_pick_first, grid_for(h, (const void*)k_msf_pick_first, kBlock, C), kBlock, conn, (uint32_t)C, parent, best, tag, cand, ncand);
+    else LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur, ncur_prev, parent, best, tag, cand, ncand);
+    phase_end(h);
+    phase_begin(h, "k_msf_hook");
+    LAUNCH(h, k_msf_hook, wide, kBlock, cand, ncand, parent, best, tag, eff, cur, ncur, es + ES_ROUNDS);
+    phase_end(h);
+    ++rounds_issued;
+  };
+  // ---- node ids (re-issued when the speculative rounds turn out not to have finished the forest)
+  auto node_ids = [&]() {
+    uint32_t stiles = scan_tiles(C + 1, kScanItems);
+    phase_begin(h, "init");
+    cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
+    cudaMemsetAsync(ticket, 0, 4, s);
+    cudaMemsetAsync(nc, 0, 8 * (size_t)S, s);
+    cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
+    phase_end(h);
+    // effx = exclusive scan of eff[0..C); effx[C] receives the total (= effective connections)
+    phase_begin(h, "k_scan_u32");
+    if (C) LAUNCH(h, k_scan_u32, scan_tiles(C, kScanItems), kBlock, eff, effx, (uint32_t)C, tile_state, ticket, (const uint32_t*)nullptr);
+    else cudaMemsetAsync(effx, 0, 4, s);
+    phase_end(h);
+    phase_begin(h, "k_ev_nid_edges");
+    if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, effx, parent, nc);
+    phase_end(h);
+    phase_begin(h, "k_ev_finalize");
+    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, sig_t, sig_meta, outmark, effx, parent, nc, nos, es);
+    phase_end(h);
+    phase_begin(h, "k_ev_gates");
+    if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
+    phase_end(h);
+    cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(hp + ES_COUNT, effx + C, 4, cudaMemcpyDeviceToHost, s);
+    if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return false;
+    return cuda_ok(h, cudaGetLastError(), "emit kernels");
+  };
+
   if (C) {
+    for (int r = 0; r < kSpecMsf; ++r)
+      msf_round(r ? es + ES_MC0 + 2 * (r - 1) + 1 : nullptr, es + ES_MC0 + 2 * r, es + ES_MC0 + 2 * r + 1);
+  }
+  if (!node_ids()) return C2A_ERR_CUDA;
+  if (C && hp[ES_MC0 + 2 * (kSpecMsf - 1)] != 0 && hp[ES_MC0 + 2 * (kSpecMsf - 1) + 1] != 0) {
+    // the last speculative round still had candidates and left edges undecided: finish with host-checked rounds, then redo the ids.
+    // (eff[] is only ever added to, parent[] only compressed/hooked further: the re-run starts from a consistent state.)
+    cudaMemcpyAsync(es + ES_NCUR, es + ES_MC0 + 2 * (kSpecMsf - 1) + 1, 4, cudaMemcpyDeviceToDevice, s);
     while (true) {
-      uint32_t tag = (6u - (rounds % 7u)) << 29;
-      if (rounds && (rounds % 7u) == 0) cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);  // tags wrapped: forget the old minima
-      phase_begin(h, "k_msf_pick");
-      if (rounds == 0) {
-        hp[ES_COUNT] = (uint32_t)C;  // every slot of cand[] is written; dead ones carry kNone
-        cudaMemcpyAsync(es + ES_NCAND, hp + ES_COUNT, 4, cudaMemcpyHostToDevice, s);
-        LAUNCH(h, k_msf_pick_first, grid_for(h, (const void*)k_msf_pick_first, kBlock, C), kBlock, conn, (uint32_t)C, parent, best, tag, cand);
-      } else {
-        cudaMemsetAsync(es + ES_NCAND, 0, 4, s);
-        LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur, es + ES_NCUR, parent, best, tag, cand, es + ES_NCAND);
-      }
-      phase_end(h);
-      cudaMemsetAsync(es + ES_NCUR, 0, 4, s);
-      phase_begin(h, "k_msf_hook");
-      LAUNCH(h, k_msf_hook, wide, kBlock, cand, es + ES_NCAND, parent, best, tag, eff, cur, es + ES_NCUR);
-      phase_end(h);
-      ++rounds;
+      cudaMemcpyAsync(es + ES_TICKET, es + ES_NCUR, 4, cudaMemcpyDeviceToDevice, s);  // ES_TICKET is free after E1: holds the previous live count
+      cudaMemsetAsync(es + ES_NCUR, 0, 8, s);                                         // ES_NCUR, ES_NCAND
+      msf_round(es + ES_TICKET, es + ES_NCAND, es + ES_NCUR);
       cudaMemcpyAsync(hp, es + ES_NCUR, 8, cudaMemcpyDeviceToHost, s);
       if (!cuda_ok(h, cudaStreamSynchronize(s), "msf sync")) return C2A_ERR_CUDA;
       if (hp[1] == 0 || hp[0] == 0) break;  // no candidate edges at all, or none left undecided
-      if (rounds > 64) return fail(h, C2A_ERR_CUDA, "Boruvka did not converge");
+      if (rounds_issued > 96) return fail(h, C2A_ERR_CUDA, "Boruvka did not converge");
     }
-    // edges still on the live list when no candidate was hooked cannot exist: hp[1]==0 means every live edge is internal
+    if (!node_ids()) return C2A_ERR_CUDA;
   }
-
-  // ---- node ids
-  {
-    uint32_t stiles = scan_tiles(C + 1, kScanItems);
-    cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
-    cudaMemsetAsync(ticket, 0, 4, s);
-    // exclusive scan of eff[0..C) in place; eff[C] receives the total (= effective connections)
-    phase_begin(h, "k_scan_u32");
-    if (C) LAUNCH(h, k_scan_u32, scan_tiles(C, kScanItems), kBlock, eff, (uint32_t)C, tile_state, ticket);
-    phase_end(h);
-  }
-  phase_begin(h, "init");
-  cudaMemsetAsync(best, 0, 4 * (size_t)S, s);  // reused as cnt[]
-  phase_end(h);
-  phase_begin(h, "k_ev_nid_init");
-  if (S) LAUNCH(h, k_ev_nid_init, grid_for(h, (const void*)k_ev_nid_init, kBlock, S), kBlock, S, sig_t, sig_meta, eff, nid, es);
-  phase_end(h);
-  phase_begin(h, "k_ev_nid_edges");
-  if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, parent, nid);
-  phase_end(h);
-  phase_begin(h, "k_ev_finalize");
-  if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, sig_t, sig_meta, outmark, parent, nid, best, nos, es);
-  phase_end(h);
-  phase_begin(h, "k_ev_gates");
-  if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
-  phase_end(h);
-  cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-  cudaMemcpyAsync(hp + ES_COUNT, eff + C, 4, cudaMemcpyDeviceToHost, s);
-  if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaGetLastError(), "emit kernels")) return C2A_ERR_CUDA;
   flags = hp[ES_FLAGS];
   if (hp[ES_NDECL] != n_sig) flags |= EF_DUPLICATE;  // fewer distinct ids than signal events
   if (flags) return decline(flags);
@@ -664,7 +692,7 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     info->n_effective = n_eff;
     info->node_count = h->emitted.node_count;
     info->path = C2A_EMIT_PATH_DEVICE;
-    info->rounds = rounds;
+    info->rounds = hp[ES_ROUNDS];
   }
   phases_collect(h);
   return C2A_OK;
@@ -721,6 +749,7 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
     h->h_pinned_bytes = 4 * n_pairs + 8192;
     if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
   }
+  const uint32_t* io_flag = nullptr;
   if (n_pairs) {
     uint32_t* stage = h->h_pinned + 256;
     if (h->emitted.nos_valid) {
@@ -729,9 +758,7 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
       cudaMemcpyAsync(io_sigs, stage, 4 * n_pairs, cudaMemcpyHostToDevice, s);
       cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
       LAUNCH(h, k_ev_map_io, grid_for(h, (const void*)k_ev_map_io, kBlock, n_pairs), kBlock, io_sigs, (uint32_t)n_pairs, h->emitted.signal_bound, nos, io_nodes, es);
-      cudaMemcpyAsync(h->h_pinned + 128, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-      if (!cuda_ok(h, cudaStreamSynchronize(s), "io map")) return C2A_ERR_CUDA;
-      if (h->h_pinned[128 + ES_FLAGS] & EF_BAD_IO) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
+      io_flag = es + ES_IOBAD;  // read together with the build's final status: an unmapped signal yields node 0, which is harmless until then
     } else {  // sparse ids: map through the host emitter that produced the circuit
       if (n_in) c2a_signal_nodes(h->host_comp, input_signals, n_in, stage);
       if (n_out) c2a_signal_nodes(h->host_comp, output_signals, n_out, stage + n_in);
@@ -741,7 +768,7 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
       if (!cuda_ok(h, cudaStreamSynchronize(s), "io upload")) return C2A_ERR_CUDA;
     }
   }
-  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, nullptr, io_nodes);
+  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, nullptr, io_nodes, io_flag);
   if (st == C2A_OK && !outputs_on_device) {
     phase_begin(h, "d2h");
     if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);

@@ -21,6 +21,7 @@ struct c2a_handle {
   size_t h_pinned_bytes = 0;
   std::string err;
   uint64_t launches = 0;
+  uint64_t relax_fallback_rounds = 0;  // host-synchronised relax rounds beyond the speculative ones (diagnostics)
   // phase timing: CUDA events recorded on `stream`
   struct Phase {
     std::string name;
@@ -66,9 +67,7 @@ void phase_end(c2a_handle* h);
 void phases_collect(c2a_handle* h);  // after a stream sync: fills last_ms, adds "total"
 void phases_clear(c2a_handle* h);
 
-// Dependency pairs already on the device -> exact reference DFS order (K5a-c).
-// d_dep[n] (uint2), flags bit0 = some dep >= item. Writes d_order[n] unless identity && !want_order.
-// *identity_out tells the caller that order == iota (d_order is then only written when want_order).
+// Dependency pairs already on the device -> exact reference DFS order (K5a-c); see c2a_device.cu for the protocol.
 struct SortScratch {
   uint32_t* r;
   uint32_t* size_off;  // n+1
@@ -77,13 +76,20 @@ struct SortScratch {
   uint32_t* q0;
   uint32_t* q1;
   uint32_t* heavy;     // n
-  unsigned long long* tile_state;
-  uint32_t* scalars;   // >= 16 u32 on the device
+  unsigned long long* tile_state;   // look-back states of the block-offset scan ...
+  unsigned long long* tile_state2;  // ... and of the wire-numbering scan (one allocation, zeroed together)
+  size_t tile_state_bytes;
+  uint32_t* scalars;   // S_COUNT u32 on the device
 };
 size_t sort_scratch_bytes(uint64_t n);
 bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s);
-int sort_from_deps(c2a_handle* h, const uint2* d_dep, uint32_t n, uint32_t host_flags, const SortScratch& s,
-                   uint32_t* d_order, bool* identity_out, uint64_t* err_index);
+void sort_scalars_reset(c2a_handle* h, const SortScratch& s);
+void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s);
+void sort_enqueue_emit(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s, uint32_t* d_order);
+bool sort_pending(const uint32_t* host_scalars);
+int sort_drain(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s);
+void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s);
+int sort_status(c2a_handle* h, const uint32_t* host_scalars, uint64_t* err_index);
 
 int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n);
 

@@ -381,11 +381,11 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
   cudaStream_t st = h->stream;
   uint32_t* hp = h->h_pinned;
   for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
-  for (int i = 0; i < KC_COUNT; ++i) hp[16 + i] = 0;
-  hp[16 + KC_LEVEL] = 0xFFFFFFFFu;  // first advance -> level 0
-  hp[16 + KC_ERRMIN] = kNone;
+  for (int i = 0; i < KC_COUNT; ++i) hp[S_COUNT + i] = 0;
+  hp[S_COUNT + KC_LEVEL] = 0xFFFFFFFFu;  // first advance -> level 0
+  hp[S_COUNT + KC_ERRMIN] = kNone;
   cudaMemcpyAsync(b.scalars, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
-  cudaMemcpyAsync(b.ctrl, hp + 16, 4 * KC_COUNT, cudaMemcpyHostToDevice, st);
+  cudaMemcpyAsync(b.ctrl, hp + S_COUNT, 4 * KC_COUNT, cudaMemcpyHostToDevice, st);
   phase_begin(h, "init");
   cudaMemsetAsync(b.prod1, 0, 4 * (size_t)node_bound, st);
   cudaMemsetAsync(b.row_off, 0, 4 * ((size_t)G + 1), st);
@@ -396,7 +396,7 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.scalars);
     phase_end(h);
     phase_begin(h, "k_deps");
-    LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, b.prod1, b.dep, b.scalars);
+    LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, b.scalars);
     phase_end(h);
     phase_begin(h, "k_kahn_count");
     LAUNCH(h, k_kahn_count, grid_for(h, (const void*)k_kahn_count, kBlock, G), kBlock, b.dep, G, b.indeg, b.row_off);
@@ -404,7 +404,7 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     uint32_t tiles = scan_tiles(G, kScanItems);
     cudaMemsetAsync(b.tile_state, 0, 8 * (size_t)tiles, st);
     phase_begin(h, "k_scan_u32");
-    LAUNCH(h, k_scan_u32, tiles, kBlock, b.row_off, G, b.tile_state, b.scalars + S_TICKET);
+    LAUNCH(h, k_scan_u32, tiles, kBlock, b.row_off, b.row_off, G, b.tile_state, b.scalars + S_TICKET, (const uint32_t*)nullptr);
     phase_end(h);
     phase_begin(h, "k_kahn_fill");
     LAUNCH(h, k_kahn_fill, grid_for(h, (const void*)k_kahn_fill, kBlock, G), kBlock, b.dep, G, b.row_off, b.cursor, b.col);
@@ -425,19 +425,19 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     phase_end(h);
     LAUNCH(h, k_kahn_leftover, grid_for(h, (const void*)k_kahn_leftover, kBlock, G), kBlock, b.indeg, G, b.ctrl);
   }
-  cudaMemcpyAsync(hp + 16, b.ctrl, 4 * KC_COUNT, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(hp + S_COUNT, b.ctrl, 4 * KC_COUNT, cudaMemcpyDeviceToHost, st);
   cudaMemcpyAsync(hp, b.scalars, 4 * S_COUNT, cudaMemcpyDeviceToHost, st);
   if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn sync")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaGetLastError(), "kahn kernels")) return C2A_ERR_CUDA;
   if (hp[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", node_bound);
-  uint32_t tail = hp[16 + KC_TAIL];
+  uint32_t tail = hp[S_COUNT + KC_TAIL];
   if (tail != G) {
-    if (err_index) *err_index = hp[16 + KC_ERRMIN];
-    return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "%u of %u gates are on or behind a dependency cycle (smallest index %u)", G - tail, G, hp[16 + KC_ERRMIN]);
+    if (err_index) *err_index = hp[S_COUNT + KC_ERRMIN];
+    return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "%u of %u gates are on or behind a dependency cycle (smallest index %u)", G - tail, G, hp[S_COUNT + KC_ERRMIN]);
   }
-  if (hp[16 + KC_OVERFLOW]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "more levels than level_cap (%u)", level_cap);
+  if (hp[S_COUNT + KC_OVERFLOW]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "more levels than level_cap (%u)", level_cap);
   // the final advance recorded an empty level: levels = KC_LEVEL (0-based index of that empty level)
-  uint32_t levels = G ? hp[16 + KC_LEVEL] : 0;
+  uint32_t levels = G ? hp[S_COUNT + KC_LEVEL] : 0;
   if (n_levels) *n_levels = levels;
   return C2A_OK;
 }
