@@ -77,6 +77,7 @@ _SIGS = {
     "c2a_last_kernel_ms": (C.c_double, [vp, cp]),
     "c2a_last_phases": (cp, [vp]),
     "c2a_set_timing": (None, [vp, i32]),
+    "c2a_set_timing_only": (None, [vp, cp]),
     "c2a_stream": (vp, [vp]),
     "c2a_topo_sort": (i32, [vp, vp, u64, u32, vp, u64p]),
     "c2a_topo_sort_deps": (i32, [vp, u64, vp, vp, vp, u64p]),

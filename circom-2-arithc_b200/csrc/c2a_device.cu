@@ -43,13 +43,14 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 __device__ __forceinline__ void stg_stream(uint4* p, const uint4& v) {
   asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+// look-back tile states: relaxed, GPU scope (ld/st.volatile compile to .STRONG.SYS accesses)
 __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
   unsigned long long v;
-  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v));
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 constexpr int kBlock = 256;
@@ -225,9 +226,11 @@ __global__ void __launch_bounds__(kBlock) k_sizes(const uint32_t* __restrict__ r
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Single-pass exclusive scan (decoupled look-back).  Tiles are claimed through a ticket so a tile only ever
-// waits on tiles that are already running.  tile_state word = (status << 32) | value,
-// status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
+// Single-pass exclusive scan (decoupled look-back).  Tile index = blockIdx.x: CTAs are dispatched in index order and run to
+// completion, so a tile only ever waits on tiles that are already resident (the scheme of CUB's DeviceScan).  A global ticket
+// per tile was measured instead: same-address atomics with a return value retire at one per ~18 ns, which alone bounded
+// every look-back kernel here (2 446 / 9 784 / 40 905 tiles -> 47 / 197 / 672 us).
+// tile_state word = (status << 32) | value, status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix.
 // ---------------------------------------------------------------------------------------------------
 constexpr unsigned long long kStAgg = 1ull << 32, kStInc = 2ull << 32;
 
@@ -240,15 +243,8 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
   return v;
 }
 
-// Returns the exclusive prefix of this thread's `thread_sum` over the whole grid-wide sequence of tiles.
-// Must be called by all kBlock threads.  *tile_out = claimed tile index (same for the block).
-// s_mem: >= 10 u32 of shared memory.
-__device__ __forceinline__ uint32_t scan_claim_tile(uint32_t* __restrict__ ticket, uint32_t* s_mem) {
-  if (threadIdx.x == 0) s_mem[9] = atomicAdd(ticket, 1u);
-  __syncthreads();
-  return s_mem[9];
-}
-
+// scan_tile_prefix returns the exclusive prefix of this thread's `thread_sum` over the whole grid-wide sequence of tiles.
+// Must be called by all kBlock threads.  s_mem: >= 10 u32 of shared memory.
 __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -257,15 +253,16 @@ __device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v)
 
 // Decoupled look-back for tile > 0, called by one full warp: sum of the values of all tiles before `tile`.
 // State word = status << kShift | value  (status 0 = empty, 1 = tile aggregate, 2 = inclusive prefix).
-// The chain of inclusive prefixes advances by one window per L2 round trip, so the window is what bounds a scan with many
-// small tiles (measured: ~60 tiles/us with a 32-tile window).  Here every lane keeps kLookWin states in flight: the window is
-// 32 * kLookWin tiles, fetched with one round trip.
-constexpr int kLookWin = 4;
+// Every lane keeps kLookWin states in flight (window = 32 * kLookWin tiles per round trip).  Measured with
+// tools/lookback_bench.cu on B200 (10 M u32): the look-back adds ~15 us + ~5 ns per tile on top of the 15-18 us the data
+// movement takes, and wider windows are slower (more polling traffic), so kLookWin = 1 and the tiles are made large instead.
+constexpr int kLookWin = 1;
 template <int kShift>
 __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned long long* __restrict__ tile_state, uint32_t tile, int lane) {
   constexpr unsigned long long kValMask = (1ull << kShift) - 1;
   unsigned long long prefix = 0;
   long long p = (long long)tile - 1;
+  uint32_t spins = 0;
   while (true) {
     unsigned long long v[kLookWin];
 #pragma unroll
@@ -288,6 +285,7 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(const unsigned 
           break;  // next 32 predecessors
         }
         if (st == 0) v[j] = ld_volatile_u64(tile_state + idx);
+        if (++spins > (1u << 25)) __trap();  // tens of seconds of polling: a predecessor never published (fail loudly, do not hang)
       }
     }
     p -= 32 * kLookWin;
@@ -322,15 +320,17 @@ __device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thr
   return s_mem[8] + s_mem[warp] + (incl - thread_sum);
 }
 
-// exclusive scan of src[0..n) into dst[0..n) (may alias) ; dst[n] = total.  8 items per thread, 128-bit accesses.
-// guard: nullptr, or the scalars of a sort whose device-side state decides whether this launch has work.
+// exclusive scan of src[0..n) into dst[0..n) (may alias); the total goes to *total_out (default dst[n]).  128-bit accesses.
+// guard_kind: 0 none, 1 = part of the sort (guard = its scalars), 2 = part of the wire numbering.
 constexpr int kScanItems = 16;  // 4096 elements per tile: fewer links in the look-back chain
-__global__ void __launch_bounds__(kBlock) k_scan_u32(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
-                                                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ guard) {
+template <bool kPopc>  // kPopc: scan popcount(src[i]) instead of src[i] (rank structure over a bitmap)
+__global__ void __launch_bounds__(kBlock) k_scan_u32_t(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
+                                                       uint32_t* __restrict__ total_out, const uint32_t* __restrict__ guard, int guard_kind) {
   __shared__ uint32_t s_mem[10];
-  if (guard && (!sort_wanted(guard) || sort_parked(guard))) return;
+  if (guard_kind == 1 && (!sort_wanted(guard) || sort_parked(guard))) return;
+  if (guard_kind == 2 && tail_parked(guard)) return;
   const uint32_t tiles = (n + kBlock * kScanItems - 1) / (kBlock * kScanItems);
-  uint32_t tile = scan_claim_tile(ticket, s_mem);
+  const uint32_t tile = blockIdx.x;
   uint32_t base = tile * (kBlock * kScanItems) + threadIdx.x * kScanItems;
   uint32_t v[kScanItems];
   if (base + kScanItems <= n) {
@@ -343,10 +343,14 @@ __global__ void __launch_bounds__(kBlock) k_scan_u32(const uint32_t* src, uint32
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) v[i] = base + i < n ? src[base + i] : 0u;
   }
+  if (kPopc) {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) v[i] = __popc(v[i]);
+  }
   uint32_t sum = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) sum += v[i];
-  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, dst + n, tile == tiles - 1);
+  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, total_out ? total_out : dst + n, tile == tiles - 1);
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) { uint32_t t = v[i]; v[i] = ex; ex += t; }
   if (base + kScanItems <= n) {
@@ -485,50 +489,49 @@ __global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__
   }
 }
 
-// pass 2: a slot is a first appearance iff wire[node] still equals its own tagged position; rank them with
-// one single-pass scan and overwrite the tag with n_in + rank  (compiler.rs:440-441).
-constexpr int kWireItems = 4;
-__global__ void __launch_bounds__(kBlock) k_wire_scan(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
-                                                      uint32_t n_in, uint32_t* __restrict__ wire, unsigned long long* __restrict__ tile_state,
-                                                      uint32_t* __restrict__ scalars) {
-  __shared__ uint32_t s_mem[10];
-  if (tail_parked(scalars)) return;
-  const uint32_t* __restrict__ order = sort_wanted(scalars) ? order_arr : nullptr;
-  const uint32_t tiles = (G + kBlock * kWireItems - 1) / (kBlock * kWireItems);
-  uint32_t tile = scan_claim_tile(scalars + S_TICKET2, s_mem);
-  uint32_t base = tile * (kBlock * kWireItems) + threadIdx.x * kWireItems;
-  uint32_t g[kWireItems];
-  uint4 gt[kWireItems];
-  uint32_t w[kWireItems][3];
-  // batched loads: 4 order entries (one 128-bit load), 4 gates, 12 wire words in flight per thread
-  if (order && base + kWireItems <= G) {
-    uint4 o = __ldg(reinterpret_cast<const uint4*>(order + base));
-    g[0] = o.x; g[1] = o.y; g[2] = o.z; g[3] = o.w;
-  } else {
+// pass 2 (compiler.rs:440-441): a node that still carries a tag was first seen at position p = 3*pos+slot and gets the wire
+// n_in + #{first appearances before p}.  Done from the NODE side, fully coalesced over wire[]:
+//   k_wire_mark    bitmap[p] = 1 for every tagged node              (3G bits: L2-resident)
+//   k_scan_u32<popc>  pre[w] = number of set bits before word w;  total = number of intermediate wires
+//   k_wire_assign  wire[node] = n_in + pre[p / 32] + popc(bitmap[p / 32] below bit p % 32)
+// (A gate-side single-pass scan - three wire[] gathers per gate chained to a decoupled look-back - took 0.165-0.2 ms at 10 M
+//  gates: its tiles spend half their life waiting for the prefix.)
+__global__ void __launch_bounds__(kBlock) k_wire_mark(const uint32_t* __restrict__ wire, uint32_t node_bound, uint32_t* __restrict__ bitmap,
+                                                      const uint32_t* __restrict__ sc) {
+  if (tail_parked(sc)) return;
+  const uint32_t n4 = (reinterpret_cast<uintptr_t>(wire) & 15) ? 0u : node_bound / 4;  // 128-bit path needs a 16-byte aligned map
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n4; i += gridDim.x * kBlock) {
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(wire) + i);
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-    for (int i = 0; i < kWireItems; ++i) { uint32_t k = min(base + i, G - 1); g[i] = order ? __ldg(order + k) : k; }
+    for (int j = 0; j < 4; ++j)
+      if ((w[j] & kFirstTag) && w[j] != kNone) { uint32_t p = w[j] & ~kFirstTag; atomicOr(bitmap + (p >> 5), 1u << (p & 31)); }
   }
-#pragma unroll
-  for (int i = 0; i < kWireItems; ++i) gt[i] = order ? __ldg(gates + g[i]) : ldg_stream(gates + g[i]);
-#pragma unroll
-  for (int i = 0; i < kWireItems; ++i) { w[i][0] = __ldcg(wire + gt[i].y); w[i][1] = __ldcg(wire + gt[i].z); w[i][2] = __ldcg(wire + gt[i].w); }
-  uint32_t fl = 0, sum = 0;
-#pragma unroll
-  for (int i = 0; i < kWireItems; ++i) {
-    uint32_t k = base + i;
-    uint32_t p = kFirstTag | (3u * k);
-    uint32_t f = k < G ? (uint32_t)(w[i][0] == p) | ((uint32_t)(w[i][1] == p + 1) << 1) | ((uint32_t)(w[i][2] == p + 2) << 2) : 0u;
-    fl |= f << (3 * i);
-    sum += __popc(f);
+  for (uint32_t nd = n4 * 4 + blockIdx.x * kBlock + threadIdx.x; nd < node_bound; nd += gridDim.x * kBlock) {
+    uint32_t w = wire[nd];
+    if ((w & kFirstTag) && w != kNone) { uint32_t p = w & ~kFirstTag; atomicOr(bitmap + (p >> 5), 1u << (p & 31)); }
   }
-  uint32_t ex = scan_tile_prefix(tile, sum, tile_state, s_mem, scalars + S_NMID, tile == tiles - 1);
-  uint32_t wid = n_in + ex;
-#pragma unroll
-  for (int i = 0; i < kWireItems; ++i) {
-    if (fl & (1u << (3 * i))) wire[gt[i].y] = wid++;
-    if (fl & (2u << (3 * i))) wire[gt[i].z] = wid++;
-    if (fl & (4u << (3 * i))) wire[gt[i].w] = wid++;
+}
+__device__ __forceinline__ uint32_t wire_rank(uint32_t w, uint32_t n_in, const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ pre) {
+  if (!(w & kFirstTag) || w == kNone) return w;  // input / output / never seen
+  uint32_t p = w & ~kFirstTag;
+  return n_in + __ldg(pre + (p >> 5)) + __popc(__ldg(bitmap + (p >> 5)) & ((1u << (p & 31)) - 1u));
+}
+__global__ void __launch_bounds__(kBlock) k_wire_assign(uint32_t* __restrict__ wire, uint32_t node_bound, uint32_t n_in,
+                                                        const uint32_t* __restrict__ bitmap, const uint32_t* __restrict__ pre,
+                                                        const uint32_t* __restrict__ sc) {
+  if (tail_parked(sc)) return;
+  const uint32_t n4 = (reinterpret_cast<uintptr_t>(wire) & 15) ? 0u : node_bound / 4;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n4; i += gridDim.x * kBlock) {
+    uint4 v = reinterpret_cast<const uint4*>(wire)[i];
+    v.x = wire_rank(v.x, n_in, bitmap, pre);
+    v.y = wire_rank(v.y, n_in, bitmap, pre);
+    v.z = wire_rank(v.z, n_in, bitmap, pre);
+    v.w = wire_rank(v.w, n_in, bitmap, pre);
+    reinterpret_cast<uint4*>(wire)[i] = v;
   }
+  for (uint32_t nd = n4 * 4 + blockIdx.x * kBlock + threadIdx.x; nd < node_bound; nd += gridDim.x * kBlock)
+    wire[nd] = wire_rank(wire[nd], n_in, bitmap, pre);
 }
 
 // K7: gather (compiler.rs:452-464).  op stays numeric; the host maps it to the strum Display token.
@@ -655,6 +658,7 @@ void phases_clear(c2a_handle* h) {
 }
 void phase_begin(c2a_handle* h, const char* name) {
   if (!h->timing) return;
+  if (!h->timing_only.empty() && h->timing_only != name) return;
   c2a_handle::Phase p{name, next_event(h), next_event(h), true};
   cudaEventRecord(p.a, h->stream);
   h->phases.push_back(p);
@@ -708,6 +712,8 @@ int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n) {
 
 static inline uint32_t scan_tiles(uint64_t n, int items) { return (uint32_t)((n + (uint64_t)kBlock * items - 1) / ((uint64_t)kBlock * items)); }
 
+static inline uint32_t wire_bitmap_words(uint64_t n) { return (uint32_t)((3 * n + 31) / 32); }  // one bit per (sorted position, slot)
+
 size_t sort_scratch_bytes(uint64_t n) {
   size_t b = 0;
   b += align256(4 * n);            // r
@@ -715,7 +721,8 @@ size_t sort_scratch_bytes(uint64_t n) {
   b += align256(n);                // state
   b += align256(4 * ((n + 31) / 32 + 1));  // inq
   b += 3 * align256(4 * n);        // q0 q1 heavy
-  b += align256(8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(n, kWireItems) + 2));  // tile_state: block-offset scan + wire scan
+  b += align256(8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(wire_bitmap_words(n), kScanItems) + 2));  // tile_state: block-offset scan + bitmap scan
+  b += 2 * align256(4 * ((size_t)wire_bitmap_words(n) + 4));  // first-appearance bitmap + its rank prefix
   b += align256(4 * S_COUNT);
   return b;
 }
@@ -728,7 +735,10 @@ bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s) {
   s->q0 = (uint32_t*)slab_alloc(h, 4 * n);
   s->q1 = (uint32_t*)slab_alloc(h, 4 * n);
   s->heavy = (uint32_t*)slab_alloc(h, 4 * n);
-  s->tile_state_bytes = 8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(n, kWireItems) + 2);
+  s->tile_state_bytes = 8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(wire_bitmap_words(n), kScanItems) + 2);
+  s->bitmap_words = wire_bitmap_words(n);
+  s->bitmap = (uint32_t*)slab_alloc(h, 4 * ((size_t)s->bitmap_words + 4));
+  s->bitmap_pre = (uint32_t*)slab_alloc(h, 4 * ((size_t)s->bitmap_words + 4));
   s->tile_state = (unsigned long long*)slab_alloc(h, s->tile_state_bytes);
   s->tile_state2 = s->tile_state ? s->tile_state + scan_tiles(n, kScanItems) + 1 : nullptr;
   s->scalars = (uint32_t*)slab_alloc(h, 4 * S_COUNT);
@@ -740,6 +750,7 @@ void sort_scalars_reset(c2a_handle* h, const SortScratch& s) {
   cudaMemsetAsync(s.scalars, 0, 4 * S_COUNT, h->stream);
   cudaMemsetAsync(s.scalars + S_ERR_LO, 0xFF, 8, h->stream);
   cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, h->stream);
+  cudaMemsetAsync(s.bitmap, 0, 4 * ((size_t)s.bitmap_words + 4), h->stream);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -773,7 +784,7 @@ void sort_enqueue_emit(c2a_handle* h, const uint2* d_dep, uint32_t n, const Sort
   LAUNCH(h, k_sizes, grid_for(h, (const void*)k_sizes, kBlock, n), kBlock, s.r, n, s.size_off, sc);
   phase_end(h);
   phase_begin(h, "k_scan_u32");
-  LAUNCH(h, k_scan_u32, scan_tiles(n, kScanItems), kBlock, s.size_off, s.size_off, n, s.tile_state, sc + S_TICKET, sc);
+  LAUNCH(h, k_scan_u32_t<false>, scan_tiles(n, kScanItems), kBlock, s.size_off, s.size_off, n, s.tile_state, (uint32_t*)nullptr, sc, 1);
   phase_end(h);
   phase_begin(h, "k_roots");
   LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, d_order, s.heavy, sc);
@@ -821,6 +832,7 @@ void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s) {
   cudaMemsetAsync(sc + S_ERR_LO, 0xFF, 8, st);
   cudaMemsetAsync(sc + S_QN_LAST, 0, 4, st);
   cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, st);
+  cudaMemsetAsync(s.bitmap, 0, 4 * ((size_t)s.bitmap_words + 4), st);
   cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
   cudaMemsetAsync(s.state, 0, n, st);
 }
@@ -926,8 +938,14 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
       phase_begin(h, "k_wire_first");
       LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, ((uint64_t)G + kWireIlp - 1) / kWireIlp), kBlock, d_gates, d_order, G, d_wire, sc);
       phase_end(h);
-      phase_begin(h, "k_wire_scan");
-      LAUNCH(h, k_wire_scan, scan_tiles(G, kWireItems), kBlock, d_gates, d_order, G, p.n_in, d_wire, s.tile_state2, sc);
+      phase_begin(h, "k_wire_mark");
+      LAUNCH(h, k_wire_mark, grid_for(h, (const void*)k_wire_mark, kBlock, p.node_bound / 4 + 4), kBlock, d_wire, p.node_bound, s.bitmap, sc);
+      phase_end(h);
+      phase_begin(h, "k_scan_u32");
+      LAUNCH(h, k_scan_u32_t<true>, scan_tiles(s.bitmap_words, kScanItems), kBlock, s.bitmap, s.bitmap_pre, s.bitmap_words, s.tile_state2, sc + S_NMID, sc, 2);
+      phase_end(h);
+      phase_begin(h, "k_wire_assign");
+      LAUNCH(h, k_wire_assign, grid_for(h, (const void*)k_wire_assign, kBlock, p.node_bound / 4 + 4), kBlock, d_wire, p.node_bound, p.n_in, s.bitmap, s.bitmap_pre, sc);
       phase_end(h);
     }
     if (no) {
@@ -1038,6 +1056,7 @@ double c2a_last_kernel_ms(const c2a_handle* h, const char* name) {
 }
 void* c2a_stream(c2a_handle* h) { return h ? (void*)h->stream : nullptr; }  // cudaStream_t, for callers that time on it
 void c2a_set_timing(c2a_handle* h, int on) { if (h) h->timing = on != 0; }
+void c2a_set_timing_only(c2a_handle* h, const char* phase) { if (h) h->timing_only = phase ? phase : ""; }
 // comma-separated "name=ms" list of the last call's phases (diagnostics)
 const char* c2a_last_phases(c2a_handle* h) {
   static thread_local std::string s;

@@ -316,36 +316,75 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
 // event index, and every member of a class of >= 2 signals is joined by an effective connection AFTER its declaration, so the
 // class ends with the id of its last effective connection (compiler.rs:257); a class without one is a single signal and keeps
 // the id of its declaration (compiler.rs:157).
+// Pointer chases are latency chains (coalesced loads -> parent[a] -> parent[root] -> atomic); every thread keeps kChaseIlp of
+// them in flight and probes the second hop speculatively (after one Boruvka round every tree has depth 1).
+constexpr int kChaseIlp = 4;
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
                                                          const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint2* __restrict__ nc) {
-  for (uint32_t c = blockIdx.x * kBlock + threadIdx.x; c < C; c += gridDim.x * kBlock) {
-    uint32_t x = effx[c];
-    if (effx[c + 1] == x) continue;                     // not effective: no id consumed (compiler.rs:235-237)
-    uint32_t id = conn_sb[c] + x + 1u;                   // compiler.rs:257 with node_count = signals + effective merges so far
-    atomicMax(&nc[uf_find(parent, conn[c].x)].x, id);
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t c0 = blockIdx.x * kBlock + threadIdx.x; c0 < C; c0 += stride * kChaseIlp) {
+    uint32_t x[kChaseIlp], x1[kChaseIlp], sb[kChaseIlp], a[kChaseIlp], r0[kChaseIlp], r1[kChaseIlp];
+#pragma unroll
+    for (int i = 0; i < kChaseIlp; ++i) {
+      uint32_t c = min(c0 + i * stride, C - 1);
+      x[i] = effx[c];
+      x1[i] = effx[c + 1];
+      sb[i] = conn_sb[c];
+      a[i] = conn[c].x;
+    }
+#pragma unroll
+    for (int i = 0; i < kChaseIlp; ++i) r0[i] = parent[a[i]];
+#pragma unroll
+    for (int i = 0; i < kChaseIlp; ++i) r1[i] = parent[r0[i]];
+#pragma unroll
+    for (int i = 0; i < kChaseIlp; ++i) {
+      if (c0 + i * stride >= C || x1[i] == x[i]) continue;   // not effective: no id consumed (compiler.rs:235-237)
+      uint32_t id = sb[i] + x[i] + 1u;                        // compiler.rs:257 with node_count = signals + effective merges so far
+      uint32_t r = r1[i] == r0[i] ? r0[i] : uf_find(parent, a[i]);
+      atomicMax(&nc[r].x, id);
+    }
   }
 }
 // node_of_signal + the merge-error screens (compiler.rs:239-245); nc[root].y = {#const signals, #gate-output signals << 16}
+constexpr int kFinIlp = 2;
 __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
                                                         const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ effx,
                                                         uint32_t* __restrict__ parent, uint2* __restrict__ nc, uint32_t* __restrict__ nos,
                                                         uint32_t* __restrict__ es) {
   uint32_t f = 0, declared = 0;
-  for (uint32_t s = blockIdx.x * kBlock + threadIdx.x; s < S; s += gridDim.x * kBlock) {
-    uint32_t node = 0;
-    if (sig_t[s] != kNone) {
-      ++declared;
-      uint2 m = sig_meta[s];
-      uint32_t r = uf_find(parent, s);
-      node = __ldcg(&nc[r].x);
-      if (node == 0) {
-        node = (m.x & 0x7FFFFFFFu) + 1u + __ldg(effx + m.y);  // a class of one: compiler.rs:157
-      } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
-        if (m.x & 0x80000000u) { if (atomicAdd(&nc[r].y, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
-        if (outmark[s]) { if (atomicAdd(&nc[r].y, 0x10000u) >> 16) f |= EF_OUT_OUT; }
-      }
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t s0 = blockIdx.x * kBlock + threadIdx.x; s0 < S; s0 += stride * kFinIlp) {
+    uint32_t t[kFinIlp], r0[kFinIlp], r1[kFinIlp], nid[kFinIlp], om[kFinIlp];
+    uint2 m[kFinIlp];
+#pragma unroll
+    for (int i = 0; i < kFinIlp; ++i) {
+      uint32_t s = min(s0 + i * stride, S - 1);
+      t[i] = sig_t[s];
+      m[i] = sig_meta[s];
+      om[i] = outmark[s];
+      r0[i] = parent[s];
     }
-    nos[s] = node;
+#pragma unroll
+    for (int i = 0; i < kFinIlp; ++i) { r1[i] = parent[r0[i]]; nid[i] = __ldcg(&nc[r0[i]].x); }
+#pragma unroll
+    for (int i = 0; i < kFinIlp; ++i) {
+      uint32_t s = s0 + i * stride;
+      if (s >= S) continue;
+      uint32_t node = 0;
+      if (t[i] != kNone) {
+        ++declared;
+        uint32_t r = r0[i];
+        node = nid[i];
+        if (r1[i] != r0[i]) { r = uf_find(parent, s); node = __ldcg(&nc[r].x); }
+        if (node == 0) {
+          node = (m[i].x & 0x7FFFFFFFu) + 1u + __ldg(effx + m[i].y);  // a class of one: compiler.rs:157
+        } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
+          if (m[i].x & 0x80000000u) { if (atomicAdd(&nc[r].y, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
+          if (om[i]) { if (atomicAdd(&nc[r].y, 0x10000u) >> 16) f |= EF_OUT_OUT; }
+        }
+      }
+      nos[s] = node;
+    }
   }
   f = warp_or(f);
   declared = warp_sum(declared);
@@ -533,8 +572,8 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
       LAUNCH(h, k_ev_count, egrid, kBlock, d_ev, n, tiles, tile_g, tile_c, es);
       phase_end(h);
       phase_begin(h, "k_scan_u32");
-      LAUNCH(h, k_scan_u32, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, es + ES_TICKET, (const uint32_t*)nullptr);
-      LAUNCH(h, k_scan_u32, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, es + ES_TICKET2, (const uint32_t*)nullptr);
+      LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
+      LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
       phase_begin(h, "k_ev_scatter");
       LAUNCH(h, k_ev_scatter, egrid, kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
@@ -636,7 +675,7 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     phase_end(h);
     // effx = exclusive scan of eff[0..C); effx[C] receives the total (= effective connections)
     phase_begin(h, "k_scan_u32");
-    if (C) LAUNCH(h, k_scan_u32, scan_tiles(C, kScanItems), kBlock, eff, effx, (uint32_t)C, tile_state, ticket, (const uint32_t*)nullptr);
+    if (C) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(C, kScanItems), kBlock, eff, effx, (uint32_t)C, tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
     else cudaMemsetAsync(effx, 0, 4, s);
     phase_end(h);
     phase_begin(h, "k_ev_nid_edges");

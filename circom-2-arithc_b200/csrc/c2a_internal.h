@@ -33,6 +33,7 @@ struct c2a_handle {
   size_t ev_next = 0;
   std::vector<std::pair<std::string, double>> last_ms;
   bool timing = true;
+  std::string timing_only;  // non-empty: events are recorded around this phase only
   // ---- device emitter (c2a_emit.cuh): event staging buffer (separate from the slab) and the resident result
   char* ev_buf = nullptr;
   size_t ev_bytes = 0;
@@ -77,7 +78,10 @@ struct SortScratch {
   uint32_t* q1;
   uint32_t* heavy;     // n
   unsigned long long* tile_state;   // look-back states of the block-offset scan ...
-  unsigned long long* tile_state2;  // ... and of the wire-numbering scan (one allocation, zeroed together)
+  unsigned long long* tile_state2;  // ... and of the wire-numbering bitmap scan (one allocation, zeroed together)
+  uint32_t* bitmap;                 // first-appearance bitmap over the 3n (position, slot) pairs
+  uint32_t* bitmap_pre;             // number of set bits before each bitmap word
+  uint32_t bitmap_words;
   size_t tile_state_bytes;
   uint32_t* scalars;   // S_COUNT u32 on the device
 };

@@ -75,7 +75,11 @@ __device__ __forceinline__ void kahn_grid_barrier(uint32_t* ctrl, uint32_t& gen,
       __threadfence();
       st_release_u32(ctrl + KC_RELEASE, gen + 1);
     } else {
-      while (ld_acquire_u32(ctrl + KC_RELEASE) < gen + 1) { __nanosleep(32); }
+      uint32_t spins = 0;
+      while (ld_acquire_u32(ctrl + KC_RELEASE) < gen + 1) {
+        __nanosleep(32);
+        if (++spins > (1u << 27)) __trap();  // ~10 s: a CTA never arrived (fail loudly, do not hang)
+      }
     }
   }
   ++gen;
@@ -404,7 +408,7 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     uint32_t tiles = scan_tiles(G, kScanItems);
     cudaMemsetAsync(b.tile_state, 0, 8 * (size_t)tiles, st);
     phase_begin(h, "k_scan_u32");
-    LAUNCH(h, k_scan_u32, tiles, kBlock, b.row_off, b.row_off, G, b.tile_state, b.scalars + S_TICKET, (const uint32_t*)nullptr);
+    LAUNCH(h, k_scan_u32_t<false>, tiles, kBlock, b.row_off, b.row_off, G, b.tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
     phase_end(h);
     phase_begin(h, "k_kahn_fill");
     LAUNCH(h, k_kahn_fill, grid_for(h, (const void*)k_kahn_fill, kBlock, G), kBlock, b.dep, G, b.row_off, b.cursor, b.col);

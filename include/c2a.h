@@ -88,6 +88,9 @@ double c2a_last_kernel_ms(const c2a_handle* h, const char* name); /* CUDA-event 
                                                          "wire_scan","gather","kahn","total"); <0 if unknown */
 const char* c2a_last_phases(c2a_handle* h);           /* "name=ms,..." for every phase of the last call */
 void c2a_set_timing(c2a_handle* h, int on);           /* phase events on/off (default on) */
+void c2a_set_timing_only(c2a_handle* h, const char* phase); /* record events around this one phase only (NULL = every phase).
+                                                         Each event pair costs ~4 us of stream time; ~35 phases per step add up
+                                                         to 0.3 ms at 10 M gates, so a throughput run times one kernel at a time. */
 void* c2a_stream(c2a_handle* h);                      /* the cudaStream_t every kernel of this handle runs on */
 
 /* ---- back end (device).  Host-pointer forms copy H2D/D2H inside the call. ---- */
