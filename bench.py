@@ -37,8 +37,9 @@ def alg_bytes(kernel, c):
     order = 0 if c["identity"] else 4 * G            # sorted passes also read order[]
     table = {
         # ---- device emitter (c2a_emit.cuh)
-        # single pass: stream the events once, look-back tile states, scatter to sig_t + sig_meta | egates + gate_t | conn + conn_t + conn_sb
-        "emit:k_ev_scatter": 16 * n + 16 * ((n + 1023) // 1024) + ns * (4 + 8) + G * (16 + 4) + C * (8 + 4 + 4),
+        # count pass, then scatter to sig_t + sig_meta | egates + gate_t | conn + conn_t + conn_sb
+        "emit:k_ev_count": c["stream_bytes_count"] + 8 * ((n + 1023) // 1024),   # AoS: 16 B/event; packed: the kind bytes only
+        "emit:k_ev_scatter": c["stream_bytes"] + 16 * ((n + 1023) // 1024) + ns * (4 + 8) + G * (16 + 4) + C * (8 + 4 + 4),
         "emit:k_ev_check_gates": G * (16 + 4 + 12 + 1),
         "emit:k_ev_check_conns": C * (8 + 4 + 8),
         "emit:k_msf_pick": C * (8 + 8 + 16 + 16),                 # conn, 2 parent, 2 RED.MIN best, cand (first round; later rounds are on the shrunken list)
@@ -141,6 +142,8 @@ def main():
     ap.add_argument("--sample-chains", type=int, default=37, help="chains in the bounded CPU-reference sample (~20 K gates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-emit", action="store_true", help="skip the host-emitter comparison leg")
+    ap.add_argument("--stream", default="packed", choices=["packed", "aos"],
+                    help="event stream format handed to the emitter: packed (kinds byte + payload words, c2a_emit_packed_*) or 16-byte c2a_event records")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
     args = ap.parse_args()
 
@@ -202,9 +205,33 @@ def main():
     from circom_2_arithc_b200._lib import EmitInfo
     wl = c2a.workloads.mimc_chains(args.chains, rounds=args.rounds, variant=args.variant)
     dev = torch.device("cuda", local_rank)
-    p_events = torch.from_numpy(np.ascontiguousarray(wl.events).view(np.int32)).pin_memory()   # the walker's output, host side
-    n_ev = int(p_events.shape[0])
-    d_events = p_events.to(dev)
+    from circom_2_arithc_b200._lib import PackedEvents
+    packed = args.stream == "packed"
+    ev_np = np.ascontiguousarray(wl.events)
+    n_ev = int(ev_np.shape[0])
+    if packed:   # the walker's output, host side: kinds byte + payload words (c2a_program_packed / c2a_pack_events)
+        kinds_np, words_np, pk_flags = c2a.pack_events(ev_np)
+        p_kinds = torch.from_numpy(kinds_np).pin_memory()
+        p_words = torch.from_numpy(words_np.view(np.int32)).pin_memory()
+        d_kinds, d_words = p_kinds.to(dev), p_words.to(dev)
+        pk_host = PackedEvents(p_kinds.data_ptr(), p_words.data_ptr(), n_ev, int(words_np.shape[0]), pk_flags, 0)
+        pk_dev = PackedEvents(d_kinds.data_ptr(), d_words.data_ptr(), n_ev, int(words_np.shape[0]), pk_flags, 0)
+        stream_bytes, stream_bytes_count = n_ev + 4 * int(words_np.shape[0]), n_ev
+    else:
+        p_events = torch.from_numpy(ev_np.view(np.int32)).pin_memory()
+        d_events = p_events.to(dev)
+        stream_bytes = stream_bytes_count = 16 * n_ev
+
+    def emit_resident():
+        if packed:
+            return lib.c2a_emit_packed_resident(h, C.byref(pk_dev), C.byref(info), C.byref(bad))
+        return lib.c2a_emit_events_resident(h, vp(d_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+
+    def emit_from_host():
+        if packed:
+            return lib.c2a_emit_packed_device(h, C.byref(pk_host), C.byref(info), C.byref(bad))
+        return lib.c2a_emit_events_device(h, vp(p_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+
     in_ids = np.array(sorted(wl.inputs), dtype=np.uint32)
     out_ids = np.array(sorted(wl.outputs), dtype=np.uint32)
     n_const = int(((wl.events[:, 0] & 0xFF) == 1).sum())
@@ -215,9 +242,9 @@ def main():
     err = C.c_uint64(0)
 
     # sizes (one untimed emit)
-    st = lib.c2a_emit_events_resident(h, vp(d_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+    st = emit_resident()
     if st != 0:
-        raise RuntimeError(f"c2a_emit_events_resident -> {st}: {ctx.last_error()}")
+        raise RuntimeError(f"emit (resident) -> {st}: {ctx.last_error()}")
     if info.path != 1:
         raise RuntimeError(f"the device emitter declined the workload (flags {info.decline_flags}): nothing to measure")
     G, nb = int(info.n_gates), int(info.node_count) + 1
@@ -250,9 +277,9 @@ def main():
 
     def device_step(record=False):
         """emit + build with the event stream already resident in HBM; results stay in HBM"""
-        st = lib.c2a_emit_events_resident(h, vp(d_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        st = emit_resident()
         if st != 0 or info.path != 1:
-            raise RuntimeError(f"c2a_emit_events_resident -> {st} path {info.path}: {ctx.last_error()}")
+            raise RuntimeError(f"emit (resident) -> {st} path {info.path}: {ctx.last_error()}")
         if record:
             acc_phases("emit:")
         st = lib.c2a_emitted_build_circuit_device(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
@@ -318,7 +345,8 @@ def main():
     n_identity = bool((order_dev[:4096] - gate_base == np.arange(min(G, 4096), dtype=np.uint32)).all())
     n_mid = int(wc.value) - len(in_ids) - len(out_ids)
     counts = {"G": G, "NB": nb, "n": n_ev, "S": int(info.signal_bound), "C": int(info.n_connections), "Ceff": int(info.n_effective),
-              "n_sig": int(info.n_signals), "n_const": n_const, "n_mid": n_mid, "identity": n_identity, "W": (3 * G + 31) // 32}
+              "n_sig": int(info.n_signals), "n_const": n_const, "n_mid": n_mid, "identity": n_identity, "W": (3 * G + 31) // 32,
+              "stream_bytes": stream_bytes, "stream_bytes_count": stream_bytes_count}
 
     # ---- e2e: event stream in PINNED HOST memory -> c2a_emit_events_device -> c2a_emitted_build_circuit into pinned host
     #      buffers (H2D of the events and D2H of order / wire map / new gates inside the timed region)
@@ -328,9 +356,9 @@ def main():
     p_new = torch.empty((G, 4), dtype=torch.int32).pin_memory()
 
     def e2e_step():
-        st = lib.c2a_emit_events_device(h, vp(p_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        st = emit_from_host()
         if st != 0 or info.path != 1:
-            raise RuntimeError(f"c2a_emit_events_device -> {st} path {info.path}: {ctx.last_error()}")
+            raise RuntimeError(f"emit (host stream) -> {st} path {info.path}: {ctx.last_error()}")
         if world == 1:
             st = lib.c2a_emitted_build_circuit(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
                                                vp(p_order.data_ptr()), vp(p_wire.data_ptr()), vp(p_new.data_ptr()), C.byref(wc), C.byref(err))
@@ -379,7 +407,7 @@ def main():
         o2, w2, g2, wc2 = ctx.build_circuit(gates_h, comp.node_count + 1, ins_n, outs_n)
         host_emit["build_s"] = time.perf_counter() - t1
         host_emit["gates_per_s"] = G / (time.perf_counter() - t0)
-        st = lib.c2a_emit_events_device(h, vp(p_events.data_ptr()), n_ev, C.byref(info), C.byref(bad))
+        st = emit_from_host()
         ctx._emit_info = {"n_gates": G, "signal_bound": int(info.signal_bound)}
         gates_d, _ = ctx.emitted_fetch(want_nodes=False)
         assert np.array_equal(gates_d, gates_h), "device emitter and host emitter disagree on the gate vector"
@@ -422,18 +450,20 @@ def main():
             "per_kernel_gbs": {k: round(alg_bytes(k, counts) / (v * 1e-3) / 1e9, 1) for k, v in sorted(kern.items()) if v > 0},
             "whole_step_gbs": all_bytes / (ms_per_step * 1e-3) / 1e9, "whole_step_alg_bytes": all_bytes}
 
-    h2d = 16 * n_ev + 4 * (len(in_ids) + len(out_ids)) + 4 * 16 * 3
-    d2h = 4 * G + 4 * nb + 16 * G + 4 * 16 * 6
+    h2d = stream_bytes + 4 * (len(in_ids) + len(out_ids))
+    d2h = 4 * G + 4 * nb + 16 * G + 4 * 32 * 3
     out = {
         "metric": metric, "value": value, "unit": "gates/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name, "gates_per_gpu": int(G), "node_bound": int(nb), "n_inputs": int(len(in_ids)), "n_outputs": int(len(out_ids)),
-                   "events_per_gpu": n_ev, "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
+                   "events_per_gpu": n_ev,
+                   "stream_format": ("packed: 1 kind byte per event + u32 payload words (3 per gate, 2 per connection; dense signal ids implicit), %.2f B/event"
+                                     % (stream_bytes / n_ev)) if packed else "c2a_event records, 16 B/event", "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
                    "boruvka_rounds": int(info.rounds), "order_is_identity": n_identity,
-                   "l2": "inputs larger than L2 (event stream %.0f MB, gate array %.0f MB, node arrays %.0f MB each vs 126 MB L2); no flush" % (16 * n_ev / 1e6, 16 * G / 1e6, 4 * nb / 1e6),
-                   "value_scope": "event stream resident in HBM -> c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "
+                   "l2": "inputs larger than L2 (event stream %.0f MB, gate array %.0f MB, node arrays %.0f MB each vs 126 MB L2); no flush" % (stream_bytes / 1e6, 16 * G / 1e6, 4 * nb / 1e6),
+                   "value_scope": "event stream resident in HBM -> c2a_emit_packed_resident / c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "
                                   "c2a_emitted_build_circuit_device (producer map, deps, DFS-order reconstruction, wire numbering, gather); results stay in HBM",
-                   "e2e_scope": "event stream in pinned host memory -> c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
+                   "e2e_scope": "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
                                 "(order, wire_of_node, new_gates D2H inside)",
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts + wire rebase"},
         "roofline": roof,

@@ -56,6 +56,10 @@ class EmitInfo(C.Structure):  # c2a_emit_info
                 ("node_count", u32), ("signal_bound", u32), ("path", u32), ("rounds", u32), ("decline_flags", u32), ("reserved", u32)]
 
 
+class PackedEvents(C.Structure):  # c2a_packed_events
+    _fields_ = [("kinds", vp), ("words", vp), ("n_events", u64), ("n_words", u64), ("flags", u32), ("reserved", u32)]
+
+
 load_error = None
 try:
     lib = C.CDLL(LIB_PATH)
@@ -91,6 +95,11 @@ _SIGS = {
     "c2a_evaluate": (i32, [vp, vp, u64, u32, vp, vp, u64p]),
     "c2a_emit_events_device": (i32, [vp, vp, u64, vp, u64p]),
     "c2a_emit_events_resident": (i32, [vp, vp, u64, vp, u64p]),
+    "c2a_pack_events": (u64, [vp, u64, vp, vp, u32p]),
+    "c2a_unpack_events": (i32, [vp, vp]),
+    "c2a_emit_packed_device": (i32, [vp, vp, vp, u64p]),
+    "c2a_emit_packed_resident": (i32, [vp, vp, vp, u64p]),
+    "c2a_program_packed": (i32, [vp, vp]),
     "c2a_emitted_fetch": (i32, [vp, vp, vp]),
     "c2a_emitted_build_circuit_device": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_emitted_build_circuit": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),

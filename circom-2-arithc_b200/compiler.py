@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from ._lib import lib, C2AError, CircuitError, Status, EmitInfo
+from ._lib import lib, C2AError, CircuitError, Status, EmitInfo, PackedEvents
 
 NONE = 0xFFFFFFFF
 EVENT_DTYPE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
@@ -71,6 +71,28 @@ def _raise(status: int, message: str):
 
 def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pack_events(events: np.ndarray):
+    """c2a_pack_events: AoS events -> (kinds u8[n], words u32[n_words], flags)."""
+    ev = np.ascontiguousarray(events)
+    n = ev.shape[0]
+    flags = C.c_uint32(0)
+    nw = int(lib.c2a_pack_events(_ptr(ev), n, None, None, C.byref(flags)))
+    kinds = np.empty(n, dtype=np.uint8)
+    words = np.empty(nw, dtype=np.uint32)
+    lib.c2a_pack_events(_ptr(ev), n, _ptr(kinds), _ptr(words), C.byref(flags))
+    return kinds, words, int(flags.value)
+
+
+def unpack_events(kinds: np.ndarray, words: np.ndarray, flags: int) -> np.ndarray:
+    """c2a_unpack_events -> (n, 4) u32 AoS events (constant values read back as 0)."""
+    kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+    words = np.ascontiguousarray(words, dtype=np.uint32)
+    pk = PackedEvents(_ptr(kinds), _ptr(words), kinds.shape[0], words.shape[0], flags, 0)
+    out = np.empty((kinds.shape[0], 4), dtype=np.uint32)
+    _raise(lib.c2a_unpack_events(C.byref(pk), _ptr(out)), "n_words does not match the kinds")
+    return out
 
 
 class DeviceContext:
@@ -214,6 +236,25 @@ class DeviceContext:
         info = EmitInfo()
         bad = C.c_uint64(0)
         st = lib.c2a_emit_events_device(self._h, _ptr(ev), ev.shape[0], C.byref(info), C.byref(bad))
+        if st != 0:
+            e = None
+            try:
+                _raise(st, f"event {bad.value}: {self.last_error()}")
+            except (CircuitError, C2AError) as ex:
+                ex.err_event = bad.value
+                e = ex
+            raise e
+        self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
+        return dict(self._emit_info)
+
+    def emit_packed(self, kinds: np.ndarray, words: np.ndarray, flags: int) -> dict:
+        """c2a_emit_packed_device: the same replay from a packed stream (pack_events() / Program.packed())."""
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        pk = PackedEvents(_ptr(kinds), _ptr(words), kinds.shape[0], words.shape[0], flags, 0)
+        info = EmitInfo()
+        bad = C.c_uint64(0)
+        st = lib.c2a_emit_packed_device(self._h, C.byref(pk), C.byref(info), C.byref(bad))
         if st != 0:
             e = None
             try:

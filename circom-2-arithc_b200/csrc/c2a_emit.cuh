@@ -181,6 +181,129 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
   if (lane == 0 && f) atomicOr(es + ES_FLAGS, f);
 }
 
+// ---- E0 / E1 on a PACKED stream (include/c2a.h: kinds byte + payload words) ------------------------------------------
+// Same ranks, same scatter targets.  The count pass only reads the kind bytes (1 B per event instead of 16); the payload of a
+// tile is one contiguous word range [3*g0 + 2*c0 (+ s0), ...) known from the scanned tile counts, so the scatter stages it in
+// shared memory with coalesced loads issued together with the kind loads.
+__global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__ kinds, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_g,
+                                                     uint32_t* __restrict__ tile_c, uint32_t* __restrict__ es) {
+  __shared__ uint32_t s_g[8], s_c[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t f = 0;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // one 32-bit load = 4 consecutive events per lane: a warp covers its 128 events with one coalesced request
+    uint64_t i0 = (uint64_t)tile * kEvTile + warp * 128 + lane * 4;
+    uint32_t kb4 = 0;
+    if (i0 + 4 <= n && !(reinterpret_cast<uintptr_t>(kinds) & 3)) kb4 = __ldg(reinterpret_cast<const uint32_t*>(kinds + i0));
+    else
+      for (int j = 0; j < 4; ++j) kb4 |= (i0 + j < n ? (uint32_t)kinds[i0 + j] : 0u) << (8 * j);  // padding = SIGNAL: not counted
+    uint32_t g = 0, c = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint32_t kb = (kb4 >> (8 * j)) & 0xFFu, kind = kb & 3u, op = kb >> 2;
+      if (kind == C2A_EV_GATE) { ++g; if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
+      else {
+        if (kind == C2A_EV_CONNECT) ++c;
+        if (op) f |= EF_BAD_KIND;  // op bits on a non-gate: how c2a_pack_events marks an invalid kind
+      }
+    }
+    g = warp_sum(g);
+    c = warp_sum(c);
+    if (lane == 0) { s_g[warp] = g; s_c[warp] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t tg = 0, tc = 0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { tg += s_g[w]; tc += s_c[w]; }
+      tile_g[tile] = tg;
+      tile_c[tile] = tc;
+    }
+    __syncthreads();
+  }
+  f = warp_or(f);
+  if (lane == 0 && f) atomicOr(es + ES_FLAGS, f);
+}
+
+__global__ void __launch_bounds__(kBlock) k_pk_scatter(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+                                                       uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
+                                                       const uint32_t* __restrict__ tile_c, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
+                                                       uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
+                                                       uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
+  __shared__ uint32_t s_g[8], s_c[8];
+  __shared__ uint32_t s_w[3 * kEvTile];  // a tile's payload: at most 3 words per event
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t f = 0, smax = 0;
+  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const uint64_t tbase = (uint64_t)tile * kEvTile, tend = min(n, tbase + kEvTile);
+    const uint32_t g0 = __ldg(tile_g + tile), c0 = __ldg(tile_c + tile), g1 = __ldg(tile_g + tile + 1), c1 = __ldg(tile_c + tile + 1);
+    const uint32_t s0 = (uint32_t)tbase - g0 - c0, s1 = (uint32_t)tend - g1 - c1;
+    const uint64_t w0 = 3ull * g0 + 2ull * c0 + (dense ? 0u : s0), w1 = 3ull * g1 + 2ull * c1 + (dense ? 0u : s1);
+    const uint32_t wn = (uint32_t)(w1 - w0);  // <= 3 * kEvTile
+    uint64_t base = tbase + warp * 128;
+    uint32_t kb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t i = base + j * 32 + lane;
+      kb[j] = i < n ? (uint32_t)__ldg(kinds + i) : 0x100u;  // 0x100: past the end (neither gate nor connection)
+    }
+    for (uint32_t k = threadIdx.x; k < wn; k += kBlock) s_w[k] = w0 + k < n_words ? __ldg(words + w0 + k) : 0u;
+    uint32_t gm[4], cm[4];
+    uint32_t wg = 0, wc = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      gm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_GATE);
+      cm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_CONNECT);
+      wg += __popc(gm[j]);
+      wc += __popc(cm[j]);
+    }
+    if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; }
+    __syncthreads();  // also: s_w is complete
+    uint32_t gi = g0, ci = c0;
+    for (int w = 0; w < warp; ++w) { gi += s_g[w]; ci += s_c[w]; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint64_t i = base + j * 32 + lane;
+      uint32_t my_g = gi + __popc(gm[j] & lt), my_c = ci + __popc(cm[j] & lt);
+      gi += __popc(gm[j]);
+      ci += __popc(cm[j]);
+      if (i >= n) continue;
+      uint32_t kind = kb[j] & 3u, op = kb[j] >> 2;
+      uint32_t t = (uint32_t)i;
+      uint32_t my_s = t - my_g - my_c;  // signals declared before this event
+      uint32_t wl = 3u * (my_g - g0) + 2u * (my_c - c0) + (dense ? 0u : my_s - s0);  // offset inside the staged payload
+      if (kind <= C2A_EV_SIGNAL_CONST) {
+        uint32_t sid = dense ? my_s : s_w[min(wl, 3u * kEvTile - 1)];
+        if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
+        else {
+          smax = max(smax, sid + 1);
+          if (sid >= S_cap) f |= EF_CAP;
+          else {
+            sig_t[sid] = t;
+            sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
+          }
+        }
+      } else if (kind == C2A_EV_GATE) {
+        uint32_t w = min(wl, 3u * kEvTile - 3);
+        egates[my_g] = make_uint4(op, s_w[w], s_w[w + 1], s_w[w + 2]);
+        gate_t[my_g] = t;
+      } else {
+        uint32_t w = min(wl, 3u * kEvTile - 2);
+        conn[my_c] = make_uint2(s_w[w], s_w[w + 1]);
+        conn_t[my_c] = t;
+        conn_sb[my_c] = my_s;
+      }
+    }
+    __syncthreads();  // s_w / s_g / s_c are reused by the next tile
+  }
+  smax = warp_max(smax);
+  f = warp_or(f);
+  if (lane == 0) {
+    if (smax) atomicMax(es + ES_SBOUND, smax);
+    if (f) atomicOr(es + ES_FLAGS, f);
+  }
+}
+
 // ---- E2 ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_ev_check_gates(uint4* __restrict__ egates, const uint32_t* __restrict__ gate_t, uint32_t G, uint32_t S,
                                                            const uint32_t* __restrict__ sig_t, uint8_t* __restrict__ outmark, uint32_t* __restrict__ es) {
@@ -505,10 +628,24 @@ static int emit_host_path(c2a_handle* h, const c2a_event* ev, uint64_t n, uint32
 extern "C" {
 
 // ev_host: events in host memory (copied in) or, when ev_dev != null, already resident on the handle's device.
-static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_event* ev_dev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+// Source of the stream: AoS events (host or device pointer) or a packed stream (kinds / words on the host or on the device).
+struct EmitSrc {
+  const c2a_event* ev_host = nullptr;
+  const c2a_event* ev_dev = nullptr;
+  const c2a_packed_events* pk = nullptr;
+  bool pk_on_device = false;
+};
+
+static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+  const c2a_event* ev_host = src.ev_host;
+  const c2a_event* ev_dev = src.ev_dev;
+  const c2a_packed_events* pk = src.pk;
+  const bool pk_dense = pk && (pk->flags & C2A_PACKED_DENSE_IDS);
   int st = check_sizes(h, n, 1);
   if (st) return st;
-  if (n && !ev_host && !ev_dev) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
+  if (n && !ev_host && !ev_dev && !pk) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
+  if (pk && n && (!pk->kinds || (pk->n_words && !pk->words))) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null packed arrays");
+  if (pk && pk->n_words > 3 * n) return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words does not match the kinds");
   const c2a_event* ev = ev_host;
   if (info) memset(info, 0, sizeof *info);
   if (info) info->n_events = n;
@@ -530,7 +667,8 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   uint32_t S = 0, flags = 0;
   bool copied = false;
   for (int attempt = 0; attempt < 2; ++attempt) {
-    const size_t ev_copy = ev_dev ? 0 : align256(16 * n);
+    const size_t pk_kbytes = pk ? align256(n + 4) : 0;  // packed staging: kinds, then words
+    const size_t ev_copy = pk ? (src.pk_on_device ? 0 : pk_kbytes + align256(4 * pk->n_words + 4)) : (ev_dev ? 0 : align256(16 * n));
     const size_t ev_need = ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
                            align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n);
     if (ev_need > h->ev_bytes) {
@@ -554,10 +692,17 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     conn_sb = (uint32_t*)take(4 * n);
     conn = (uint2*)take(8 * n);
     d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
+    const uint8_t* d_kinds = pk ? (src.pk_on_device ? pk->kinds : (const uint8_t*)h->ev_buf) : nullptr;
+    const uint32_t* d_words = pk ? (src.pk_on_device ? pk->words : (const uint32_t*)(h->ev_buf + pk_kbytes)) : nullptr;
 
     if (!copied) {
       phase_begin(h, "h2d");
-      if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
+      if (pk) {
+        if (n && !src.pk_on_device) {
+          if (!cuda_ok(h, cudaMemcpyAsync(h->ev_buf, pk->kinds, n, cudaMemcpyHostToDevice, s), "kinds H2D")) return C2A_ERR_CUDA;
+          if (pk->n_words && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf + pk_kbytes, pk->words, 4 * pk->n_words, cudaMemcpyHostToDevice, s), "words H2D")) return C2A_ERR_CUDA;
+        }
+      } else if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
       phase_end(h);
       copied = true;
     }
@@ -569,14 +714,17 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     if (tiles) {
       const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
       phase_begin(h, "k_ev_count");
-      LAUNCH(h, k_ev_count, egrid, kBlock, d_ev, n, tiles, tile_g, tile_c, es);
+      if (pk) LAUNCH(h, k_pk_count, egrid, kBlock, d_kinds, n, tiles, tile_g, tile_c, es);
+      else LAUNCH(h, k_ev_count, egrid, kBlock, d_ev, n, tiles, tile_g, tile_c, es);
       phase_end(h);
       phase_begin(h, "k_scan_u32");
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
       phase_begin(h, "k_ev_scatter");
-      LAUNCH(h, k_ev_scatter, egrid, kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
+      if (pk) LAUNCH(h, k_pk_scatter, egrid, kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta,
+                     egates, gate_t, conn, conn_t, conn_sb, es);
+      else LAUNCH(h, k_ev_scatter, egrid, kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
       cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
       cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
@@ -589,6 +737,9 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
     S = hp[ES_SBOUND];
     flags = hp[ES_FLAGS];
     n_sig = n - G - C;
+    if (pk && !(flags & EF_BAD_KIND) && pk->n_words != 3 * G + 2 * C + (pk_dense ? 0 : n_sig))
+      return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words (%llu) does not match the kinds (%llu gates, %llu connections, %llu signals)",
+                  (unsigned long long)pk->n_words, (unsigned long long)G, (unsigned long long)C, (unsigned long long)n_sig);
     if (!(flags & (EF_BAD_KIND | EF_SPARSE)) && (uint64_t)S > 4 * n_sig + (1u << 20)) flags |= EF_SPARSE;  // a dense table would be mostly holes
     if ((flags & EF_CAP) && !(flags & (EF_BAD_KIND | EF_BAD_OP | EF_SPARSE)) && attempt == 0) {
       S_cap = S;  // valid but gappy ids: once more with the exact table bound
@@ -602,9 +753,22 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
   std::vector<c2a_event> ev_back;
   auto decline = [&](uint32_t f) -> int {
     if (info) info->decline_flags = f;
-    if (!ev && n) {  // resident events: the exact replay needs them on the host
+    if (!ev && n) {  // the exact replay needs AoS events on the host
       ev_back.resize(n);
-      if (!cuda_ok(h, cudaMemcpy(ev_back.data(), ev_dev, 16 * n, cudaMemcpyDeviceToHost), "events D2H for the host replay")) return C2A_ERR_CUDA;
+      if (pk) {
+        c2a_packed_events hp_pk = *pk;
+        std::vector<uint8_t> kb;
+        std::vector<uint32_t> wb;
+        if (src.pk_on_device) {
+          kb.resize(n);
+          wb.resize(pk->n_words);
+          if (!cuda_ok(h, cudaMemcpy(kb.data(), pk->kinds, n, cudaMemcpyDeviceToHost), "kinds D2H for the host replay")) return C2A_ERR_CUDA;
+          if (pk->n_words && !cuda_ok(h, cudaMemcpy(wb.data(), pk->words, 4 * pk->n_words, cudaMemcpyDeviceToHost), "words D2H for the host replay")) return C2A_ERR_CUDA;
+          hp_pk.kinds = kb.data();
+          hp_pk.words = wb.data();
+        }
+        if (c2a_unpack_events(&hp_pk, ev_back.data()) != C2A_OK) return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words does not match the kinds");
+      } else if (!cuda_ok(h, cudaMemcpy(ev_back.data(), ev_dev, 16 * n, cudaMemcpyDeviceToHost), "events D2H for the host replay")) return C2A_ERR_CUDA;
       ev = ev_back.data();
     }
     int r = emit_host_path(h, ev, n, S, (f & EF_SPARSE) != 0, info, err_event);
@@ -738,11 +902,28 @@ static int emit_events_impl(c2a_handle* h, const c2a_event* ev_host, const c2a_e
 }
 
 int c2a_emit_events_device(c2a_handle* h, const c2a_event* ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
-  return emit_events_impl(h, ev, nullptr, n, info, err_event);
+  EmitSrc src;
+  src.ev_host = ev;
+  return emit_events_impl(h, src, n, info, err_event);
 }
 int c2a_emit_events_resident(c2a_handle* h, const c2a_event* d_ev, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
   if (n && !d_ev) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
-  return emit_events_impl(h, nullptr, d_ev, n, info, err_event);
+  EmitSrc src;
+  src.ev_dev = d_ev;
+  return emit_events_impl(h, src, n, info, err_event);
+}
+int c2a_emit_packed_device(c2a_handle* h, const c2a_packed_events* pk, c2a_emit_info* info, uint64_t* err_event) {
+  if (!pk) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null packed stream");
+  EmitSrc src;
+  src.pk = pk;
+  return emit_events_impl(h, src, pk->n_events, info, err_event);
+}
+int c2a_emit_packed_resident(c2a_handle* h, const c2a_packed_events* d_pk, c2a_emit_info* info, uint64_t* err_event) {
+  if (!d_pk) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null packed stream");
+  EmitSrc src;
+  src.pk = d_pk;
+  src.pk_on_device = true;
+  return emit_events_impl(h, src, d_pk->n_events, info, err_event);
 }
 
 int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_signal_out) {

@@ -905,6 +905,8 @@ struct c2a_program {
   std::vector<uint32_t> inputs, outputs;          // signal ids tagged by the prefix match of src/program.rs:57-66, ascending
   std::vector<std::string> input_names, output_names;
   std::vector<std::string> main_inputs, main_outputs;  // declared names of the main template
+  std::vector<uint8_t> packed_kinds;                   // c2a_program_packed(): the recorded calls as a packed stream
+  std::vector<uint32_t> packed_words;
 };
 
 static int compile_impl(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
@@ -972,6 +974,17 @@ int c2a_program_compile_file(c2a_program* p, const char* path, c2a_compiler* int
 int c2a_program_compile_source(c2a_program* p, const char* source, const char* include_dir, c2a_compiler* into) {
   if (!p || !source) return C2A_ERR_INVALID_ARGUMENT;
   return compile_impl(p, source, "<source>", include_dir ? include_dir : ".", into);
+}
+int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {
+  if (!p || !out) return C2A_ERR_INVALID_ARGUMENT;
+  const auto& ev = p->sink.events;
+  uint32_t flags = 0;
+  uint64_t nw = c2a_pack_events(ev.data(), ev.size(), nullptr, nullptr, &flags);
+  p->packed_kinds.resize(ev.size());
+  p->packed_words.resize(nw);
+  c2a_pack_events(ev.data(), ev.size(), p->packed_kinds.data(), p->packed_words.data(), &flags);
+  *out = c2a_packed_events{p->packed_kinds.data(), p->packed_words.data(), (uint64_t)ev.size(), nw, flags, 0};
+  return C2A_OK;
 }
 uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.events.size(); }
 const c2a_event* c2a_program_events(const c2a_program* p) { return p->sink.events.data(); }

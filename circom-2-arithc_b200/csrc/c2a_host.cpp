@@ -232,6 +232,59 @@ int c2a_emit_events(c2a_compiler* c, const c2a_event* ev, uint64_t n, uint64_t* 
   return C2A_OK;
 }
 
+// ---- packed event stream (include/c2a.h): kinds byte + payload words -----------------------------------------------
+uint64_t c2a_pack_events(const c2a_event* ev, uint64_t n, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out) {
+  // dense = the declared ids are exactly 0, 1, 2, ... in declaration order (Runtime::gen_signal, src/runtime.rs:120-125)
+  bool dense = true;
+  uint64_t ns = 0, ng = 0, nc = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t k = ev[i].kind & 0xFF;
+    if (k <= C2A_EV_SIGNAL_CONST) { if (ev[i].a != ns) dense = false; ++ns; }
+    else if (k == C2A_EV_GATE) ++ng;
+    else ++nc;  // CONNECT, or an invalid kind (kept as kind 3 with op bits set below so that the device flags it)
+  }
+  const uint64_t n_words = 3 * ng + 2 * nc + (dense ? 0 : ns);
+  if (flags_out) *flags_out = dense ? C2A_PACKED_DENSE_IDS : 0u;
+  if (!kinds_out || !words_out) return n_words;
+  uint64_t w = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    uint32_t k = ev[i].kind & 0xFF;
+    if (k <= C2A_EV_SIGNAL_CONST) {
+      kinds_out[i] = (uint8_t)k;
+      if (!dense) words_out[w++] = ev[i].a;
+    } else if (k == C2A_EV_GATE) {
+      uint32_t op = ev[i].kind >> 8;
+      kinds_out[i] = (uint8_t)(C2A_EV_GATE | (op < 63 ? op << 2 : 63u << 2));  // an out-of-range op stays out of range
+      words_out[w++] = ev[i].a; words_out[w++] = ev[i].b; words_out[w++] = ev[i].c;
+    } else {
+      kinds_out[i] = (uint8_t)(C2A_EV_CONNECT | (k == C2A_EV_CONNECT ? 0u : 1u << 2));  // op bits on a non-gate = invalid kind
+      words_out[w++] = ev[i].a; words_out[w++] = ev[i].b;
+    }
+  }
+  return n_words;
+}
+
+int c2a_unpack_events(const c2a_packed_events* pk, c2a_event* out) {
+  if (!pk || (pk->n_events && (!pk->kinds || !out))) return C2A_ERR_INVALID_ARGUMENT;
+  const bool dense = pk->flags & C2A_PACKED_DENSE_IDS;
+  uint64_t w = 0, ns = 0;
+  for (uint64_t i = 0; i < pk->n_events; ++i) {
+    uint32_t kb = pk->kinds[i], k = kb & 3u, op = kb >> 2;
+    uint32_t need = k <= C2A_EV_SIGNAL_CONST ? (dense ? 0u : 1u) : (k == C2A_EV_GATE ? 3u : 2u);
+    if (w + need > pk->n_words || (need && !pk->words)) return C2A_ERR_INVALID_ARGUMENT;
+    if (k <= C2A_EV_SIGNAL_CONST) {
+      out[i] = c2a_event{op ? 0xFFu : k, dense ? (uint32_t)ns : pk->words[w], 0, 0};
+      ++ns;
+    } else if (k == C2A_EV_GATE) {
+      out[i] = c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), pk->words[w], pk->words[w + 1], pk->words[w + 2]};
+    } else {
+      out[i] = c2a_event{op ? 0xFFu : (uint32_t)C2A_EV_CONNECT, pk->words[w], pk->words[w + 1], 0};
+    }
+    w += need;
+  }
+  return w == pk->n_words ? C2A_OK : C2A_ERR_INVALID_ARGUMENT;
+}
+
 int c2a_set_signal_name(c2a_compiler* c, uint32_t id, const char* name) {
   uint32_t e = c->elem_of(id);
   if (e == kNoElem || !name) return C2A_ERR_INVALID_ARGUMENT;

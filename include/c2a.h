@@ -197,6 +197,32 @@ int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals,
                                      uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
                                      uint64_t* err_index);
 
+/* ---- packed event stream.  The same emission calls at ~6 bytes per event instead of 16: what the walker hands to the
+ * device emitter when the stream has to cross PCIe (c2a_program_packed) and what the device reads from HBM.
+ *   kinds[n_events]  one byte per event: c2a_event_kind | (c2a_gate_type << 2)
+ *   words[n_words]   payload in event order:  SIGNAL / SIGNAL_CONST: the signal id - omitted when C2A_PACKED_DENSE_IDS is set
+ *                    (the ids are 0, 1, 2, ... in declaration order, which is what Runtime::gen_signal produces,
+ *                    src/runtime.rs:120-125);  GATE: lhs, rhs, out signal;  CONNECT: a, b.
+ * Constant VALUES are not part of it: they never influence node ids, gates or errors (src/compiler.rs:139-278) and stay with
+ * the host-side name / constant maps.  n_words must equal 3*gates + 2*connections (+ signals without DENSE_IDS). ---- */
+#define C2A_PACKED_DENSE_IDS 1u
+typedef struct {
+  const uint8_t* kinds;
+  const uint32_t* words;
+  uint64_t n_events, n_words;
+  uint32_t flags, reserved;
+} c2a_packed_events;
+/* AoS -> packed.  Returns n_words and *flags_out; writes kinds_out[n] / words_out[n_words] when they are non-NULL
+ * (call once with NULL buffers to size them). */
+uint64_t c2a_pack_events(const c2a_event* ev, uint64_t n, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out);
+/* packed -> AoS (constant values read back as 0); C2A_ERR_INVALID_ARGUMENT when n_words does not match the kinds */
+int c2a_unpack_events(const c2a_packed_events* pk, c2a_event* ev_out /* n_events */);
+/* c2a_emit_events_device / _resident on a packed stream (kinds / words are host, resp. DEVICE pointers; the struct itself is
+ * always in host memory).  Same results, same c2a_emit_info, same error behaviour (declined streams are unpacked and replayed
+ * by the host emitter). */
+int c2a_emit_packed_device(c2a_handle*, const c2a_packed_events* pk, c2a_emit_info* info, uint64_t* err_event);
+int c2a_emit_packed_resident(c2a_handle*, const c2a_packed_events* d_pk, c2a_emit_info* info, uint64_t* err_event);
+
 /* ---- emit side (host).  Node ids, gate vector and error behaviour identical to the reference Compiler. ---- */
 c2a_compiler* c2a_compiler_new(void);
 void c2a_compiler_free(c2a_compiler*);
@@ -270,6 +296,8 @@ uint32_t c2a_program_num_inputs(const c2a_program*);   /* signals tagged as circ
 uint32_t c2a_program_num_outputs(const c2a_program*);
 const uint32_t* c2a_program_inputs(const c2a_program*);
 const uint32_t* c2a_program_outputs(const c2a_program*);
+/* the recorded calls as a packed stream (arrays owned by the program object, valid until it is freed or recompiled) */
+int c2a_program_packed(c2a_program*, c2a_packed_events* out);
 
 #ifdef __cplusplus
 }

@@ -124,6 +124,14 @@ def check_against(ctx, ref, ev, expect_path=DEVICE):
     assert np.array_equal(nos[sids], want)
     undeclared = np.setdiff1d(np.arange(info["signal_bound"]), sids)
     assert (nos[undeclared] == 0).all()
+    # the packed form of the same stream (kinds byte + payload words) must replay to the identical result
+    from c2a_loader import c2a
+    kinds_b, words, flags = c2a.pack_events(ev)
+    assert bool(flags & 1) == bool(np.array_equal(sids, np.arange(len(sids))))  # C2A_PACKED_DENSE_IDS
+    info_p = ctx.emit_packed(kinds_b, words, flags)
+    gates_p, nos_p = ctx.emitted_fetch()
+    assert {k: v for k, v in info_p.items() if k != "decline_flags"} == {k: v for k, v in info.items() if k != "decline_flags"}
+    assert np.array_equal(gates_p, gates) and np.array_equal(nos_p, nos)
     return info, gates, nos
 
 
@@ -212,6 +220,10 @@ def test_streams_the_device_declines_replay_exactly(ctx, orc, c2a, seed):
             ctx.emit_events(ev)
         assert int(ex.value.status) == err.status
         assert f"event {ex.value.err_event}" == err.message
+        with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:  # same through the packed stream
+            ctx.emit_packed(*c2a.pack_events(ev))
+        assert int(ex.value.status) == err.status
+        assert f"event {ex.value.err_event}" == err.message
 
 
 def test_merge_errors(ctx, c2a):
@@ -239,6 +251,24 @@ def test_merge_errors(ctx, c2a):
     assert info["path"] == HOST and info["decline_flags"] != 0
     gates, _ = ctx.emitted_fetch()
     assert gates.tolist() == [[0, 1, 2, 5], [0, 1, 2, 5]]
+
+
+def test_packed_stream_rejects_inconsistent_word_count(ctx, c2a):
+    ev = np.asarray([(EV_S, 0, 0, 0), (EV_S, 1, 0, 0), (EV_S, 2, 0, 0), (EV_G, 0, 1, 2), (EV_C, 2, 1, 0)], dtype=np.uint32)
+    kinds_b, words, flags = c2a.pack_events(ev)
+    assert flags == 1 and words.tolist() == [0, 1, 2, 2, 1] and kinds_b.tolist() == [0, 0, 0, 2, 3]
+    with pytest.raises(c2a.C2AError):
+        ctx.emit_packed(kinds_b, words[:-1], flags)
+    with pytest.raises(c2a.C2AError):
+        ctx.emit_packed(kinds_b, np.concatenate([words, words[:1]]), flags)
+    with pytest.raises(c2a.C2AError):
+        ctx.emit_packed(kinds_b, words, 0)  # without DENSE_IDS the signals would need an id word each
+    bad = kinds_b.copy()
+    bad[3] = 2 | (25 << 2)                  # gate type out of range (src/a_gate_type.rs has 20)
+    with pytest.raises((c2a.C2AError, c2a.CircuitError)):
+        ctx.emit_packed(bad, words, flags)
+    info = ctx.emit_packed(kinds_b, words, flags)
+    assert info["path"] == DEVICE and info["n_gates"] == 1 and info["node_count"] == 4
 
 
 def test_sparse_ids_go_through_the_host_emitter(ctx, c2a):

@@ -1,0 +1,67 @@
+"""Packed event stream (include/c2a.h: kinds byte + payload words): host-side pack / unpack round trips.  No GPU."""
+import numpy as np
+import pytest
+
+EV_S, EV_SC, EV_G, EV_C = 0, 1, 2, 3
+
+
+def _zero_values(ev):
+    ev = ev.copy()
+    ev[(ev[:, 0] & 0xFF) == EV_SC, 2] = 0  # constant values are not part of the packed stream
+    return ev
+
+
+@pytest.mark.parametrize("variant", ["inorder", "late"])
+def test_round_trip_workloads(c2a, variant):
+    wl = c2a.workloads.mimc_chains(9, rounds=7, variant=variant)
+    ev = np.ascontiguousarray(wl.events)
+    kinds, words, flags = c2a.pack_events(ev)
+    k = ev[:, 0] & 0xFF
+    assert flags == 1                                   # workload ids are dense, like Runtime::gen_signal (src/runtime.rs:120-125)
+    assert len(words) == 3 * (k == EV_G).sum() + 2 * (k == EV_C).sum()
+    assert kinds.nbytes + words.nbytes < 0.45 * ev.nbytes
+    assert np.array_equal(c2a.unpack_events(kinds, words, flags), _zero_values(ev))
+
+
+def test_round_trip_explicit_ids_and_all_ops(c2a):
+    rng = np.random.RandomState(3)
+    ids = rng.permutation(500).astype(np.uint32) * 3 + 1
+    ev = [(EV_SC, int(s), int(i), 0) if i % 7 == 0 else (EV_S, int(s), 0, 0) for i, s in enumerate(ids)]
+    for op in range(20):
+        a, b, o = (int(x) for x in rng.choice(ids, 3))
+        ev.append((EV_G | (op << 8), a, b, o))
+        ev.append((EV_C, a, o, 0))
+    ev = np.asarray(ev, dtype=np.uint32)
+    ev = ev[rng.permutation(len(ev))]                    # order is irrelevant to the format
+    kinds, words, flags = c2a.pack_events(ev)
+    assert flags == 0 and len(words) == 500 + 3 * 20 + 2 * 20
+    assert np.array_equal(c2a.unpack_events(kinds, words, flags), _zero_values(ev))
+    with pytest.raises(c2a.C2AError):
+        c2a.unpack_events(kinds, words[:-1], flags)
+
+
+def test_empty(c2a):
+    kinds, words, flags = c2a.pack_events(np.zeros((0, 4), dtype=np.uint32))
+    assert len(kinds) == 0 and len(words) == 0 and flags == 1
+    assert c2a.unpack_events(kinds, words, flags).shape == (0, 4)
+
+
+def test_program_packed_matches_events(c2a):
+    """the front end hands out the recorded calls in both forms (c2a_program_events / c2a_program_packed)"""
+    import ctypes as C
+    from circom_2_arithc_b200._lib import lib, PackedEvents
+    src = b"pragma circom 2.0.0; template T(){ signal input a; signal input b; signal output c; c <== a*b + 3; } component main = T();"
+    p = lib.c2a_program_new()
+    try:
+        assert lib.c2a_program_compile_source(p, src, None, None) == 0, lib.c2a_program_error(p)
+        n = lib.c2a_program_num_events(p)
+        ev = np.ctypeslib.as_array(C.cast(lib.c2a_program_events(p), C.POINTER(C.c_uint32)), shape=(n, 4)).copy()
+        pk = PackedEvents()
+        assert lib.c2a_program_packed(p, C.byref(pk)) == 0 and pk.n_events == n
+        kinds = np.ctypeslib.as_array(C.cast(pk.kinds, C.POINTER(C.c_uint8)), shape=(n,)).copy()
+        words = np.ctypeslib.as_array(C.cast(pk.words, C.POINTER(C.c_uint32)), shape=(pk.n_words,)).copy()
+        assert np.array_equal(c2a.unpack_events(kinds, words, pk.flags), _zero_values(ev))
+        k2, w2, f2 = c2a.pack_events(ev)
+        assert np.array_equal(k2, kinds) and np.array_equal(w2, words) and f2 == pk.flags
+    finally:
+        lib.c2a_program_free(p)
