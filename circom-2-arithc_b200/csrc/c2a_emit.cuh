@@ -187,114 +187,198 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
 // shared memory with coalesced loads issued together with the kind loads.
 __global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__ kinds, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_g,
                                                      uint32_t* __restrict__ tile_c, uint32_t* __restrict__ es) {
-  __shared__ uint32_t s_g[8], s_c[8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // one WARP per 1024-event tile: two coalesced 128-bit loads per lane, no block-level synchronisation
+  const int lane = threadIdx.x & 31;
+  const uint32_t nwarps = gridDim.x * (kBlock / 32);
+  const bool aligned = !(reinterpret_cast<uintptr_t>(kinds) & 15);
   uint32_t f = 0;
-  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    // one 32-bit load = 4 consecutive events per lane: a warp covers its 128 events with one coalesced request
-    uint64_t i0 = (uint64_t)tile * kEvTile + warp * 128 + lane * 4;
-    uint32_t kb4 = 0;
-    if (i0 + 4 <= n && !(reinterpret_cast<uintptr_t>(kinds) & 3)) kb4 = __ldg(reinterpret_cast<const uint32_t*>(kinds + i0));
-    else
-      for (int j = 0; j < 4; ++j) kb4 |= (i0 + j < n ? (uint32_t)kinds[i0 + j] : 0u) << (8 * j);  // padding = SIGNAL: not counted
+  for (uint32_t tile = blockIdx.x * (kBlock / 32) + (threadIdx.x >> 5); tile < tiles; tile += nwarps) {
+    const uint64_t tbase = (uint64_t)tile * kEvTile;
+    uint32_t w[8];
+    if (aligned && tbase + kEvTile <= n) {
+      uint4 x = __ldg(reinterpret_cast<const uint4*>(kinds + tbase) + lane), y = __ldg(reinterpret_cast<const uint4*>(kinds + tbase + 512) + lane);
+      w[0] = x.x; w[1] = x.y; w[2] = x.z; w[3] = x.w; w[4] = y.x; w[5] = y.y; w[6] = y.z; w[7] = y.w;
+    } else {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        w[q] = 0;  // padding = SIGNAL with op 0: neither counted nor flagged
+        for (int j = 0; j < 4; ++j) {
+          uint64_t i = tbase + (q < 4 ? 0 : 512) + lane * 16 + (q & 3) * 4 + j;
+          if (i < n) w[q] |= (uint32_t)kinds[i] << (8 * j);
+        }
+      }
+    }
     uint32_t g = 0, c = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t kb = (kb4 >> (8 * j)) & 0xFFu, kind = kb & 3u, op = kb >> 2;
-      if (kind == C2A_EV_GATE) { ++g; if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
-      else {
-        if (kind == C2A_EV_CONNECT) ++c;
-        if (op) f |= EF_BAD_KIND;  // op bits on a non-gate: how c2a_pack_events marks an invalid kind
+    for (int q = 0; q < 8; ++q) {
+      const uint32_t lo = w[q] & 0x01010101u, hi = (w[q] >> 1) & 0x01010101u;  // kind bit 0 / bit 1 of each byte
+      const uint32_t is_g = hi & ~lo, is_c = hi & lo;
+      g += __popc(is_g);
+      c += __popc(is_c);
+      // op field (bits 2..7 of each byte): must be < 20 on a gate, 0 elsewhere (c2a_pack_events marks an invalid kind that way)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t kb = (w[q] >> (8 * j)) & 0xFFu, op = kb >> 2;
+        if ((kb & 3u) == C2A_EV_GATE) { if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
+        else if (op) f |= EF_BAD_KIND;
       }
     }
     g = warp_sum(g);
     c = warp_sum(c);
-    if (lane == 0) { s_g[warp] = g; s_c[warp] = c; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t tg = 0, tc = 0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) { tg += s_g[w]; tc += s_c[w]; }
-      tile_g[tile] = tg;
-      tile_c[tile] = tc;
-    }
-    __syncthreads();
+    if (lane == 0) { tile_g[tile] = g; tile_c[tile] = c; }
   }
   f = warp_or(f);
   if (lane == 0 && f) atomicOr(es + ES_FLAGS, f);
 }
 
+// TMA 1-D bulk copy global -> shared with completion on an mbarrier (cp.async.bulk; SASS: UBLKCP); src/dst/bytes multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, unsigned long long* mbar) {
+  uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst), bar = (uint32_t)__cvta_generic_to_shared(mbar);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Persistent CTAs, two-stage shared-memory pipeline fed by TMA bulk copies: while the CTA ranks and scatters tile t, the kind
+// bytes and the payload word range of its next tile are already in flight.  One elected thread computes the (16-byte aligned)
+// ranges from the scanned tile counts and issues the copies; everybody waits on the stage's mbarrier.
+constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words per event) + alignment slack
 __global__ void __launch_bounds__(kBlock) k_pk_scatter(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
                                                        uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
                                                        uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
+  __shared__ __align__(16) uint32_t s_w[2][kPkWordsCap];
+  __shared__ __align__(16) uint8_t s_k[2][kEvTile];
+  __shared__ __align__(8) unsigned long long s_bar[2];
+  __shared__ uint32_t s_meta[2][8];  // g0, c0, s0, first payload word - aligned start, words staged, kind bytes staged, #gates, #connections
   __shared__ uint32_t s_g[8], s_c[8];
-  __shared__ uint32_t s_w[3 * kEvTile];  // a tile's payload: at most 3 words per event
+  __shared__ uint32_t s_list[kEvTile];  // the tile's events filed by kind (phase A -> phase B)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
-  uint32_t f = 0, smax = 0;
-  for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const uint64_t tbase = (uint64_t)tile * kEvTile, tend = min(n, tbase + kEvTile);
-    const uint32_t g0 = __ldg(tile_g + tile), c0 = __ldg(tile_c + tile), g1 = __ldg(tile_g + tile + 1), c1 = __ldg(tile_c + tile + 1);
-    const uint32_t s0 = (uint32_t)tbase - g0 - c0, s1 = (uint32_t)tend - g1 - c1;
-    const uint64_t w0 = 3ull * g0 + 2ull * c0 + (dense ? 0u : s0), w1 = 3ull * g1 + 2ull * c1 + (dense ? 0u : s1);
-    const uint32_t wn = (uint32_t)(w1 - w0);  // <= 3 * kEvTile
-    uint64_t base = tbase + warp * 128;
-    uint32_t kb[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint64_t i = base + j * 32 + lane;
-      kb[j] = i < n ? (uint32_t)__ldg(kinds + i) : 0x100u;  // 0x100: past the end (neither gate nor connection)
+  const bool tma_ok = !((reinterpret_cast<uintptr_t>(kinds) | reinterpret_cast<uintptr_t>(words)) & 15);
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < 2; ++b) {
+      uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[b]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
     }
-    for (uint32_t k = threadIdx.x; k < wn; k += kBlock) s_w[k] = w0 + k < n_words ? __ldg(words + w0 + k) : 0u;
-    uint32_t gm[4], cm[4];
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer side (thread 0 only): counts of a tile -> ranges -> bulk copies into `stage`
+  auto issue = [&](uint32_t tile, int stage, uint4 cnt) {  // cnt = {g0, c0, g1, c1}
+    const uint64_t tbase = (uint64_t)tile * kEvTile, tend = min(n, tbase + kEvTile);
+    const uint32_t s0 = (uint32_t)tbase - cnt.x - cnt.y, s1 = (uint32_t)tend - cnt.z - cnt.w;
+    const uint64_t w0 = 3ull * cnt.x + 2ull * cnt.y + (dense ? 0u : s0), w1 = 3ull * cnt.z + 2ull * cnt.w + (dense ? 0u : s1);
+    uint64_t a0 = w0 & ~3ull, a1 = min((w1 + 3) & ~3ull, n_words & ~3ull);
+    if (a1 < a0 || !tma_ok || a1 - a0 > (uint64_t)kPkWordsCap) a1 = a0;       // (a corrupt count pair cannot overrun the stage)
+    const uint32_t wbytes = (uint32_t)(a1 - a0) * 4u;
+    const uint32_t kbytes = tma_ok ? (uint32_t)(tend - tbase) & ~15u : 0u;
+    s_meta[stage][0] = cnt.x; s_meta[stage][1] = cnt.y; s_meta[stage][2] = s0;
+    s_meta[stage][3] = (uint32_t)(w0 - a0); s_meta[stage][4] = (uint32_t)(a1 - a0); s_meta[stage][5] = kbytes;
+    s_meta[stage][6] = min(cnt.z - cnt.x, (uint32_t)kEvTile); s_meta[stage][7] = min(cnt.w - cnt.y, (uint32_t)kEvTile);
+    uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was last read through the generic proxy
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + kbytes) : "memory");
+    if (wbytes) bulk_g2s(&s_w[stage][0], words + a0, wbytes, &s_bar[stage]);
+    if (kbytes) bulk_g2s(&s_k[stage][0], kinds + tbase, kbytes, &s_bar[stage]);
+  };
+  auto load_counts = [&](uint32_t tile) { return make_uint4(__ldg(tile_g + tile), __ldg(tile_c + tile), __ldg(tile_g + tile + 1), __ldg(tile_c + tile + 1)); };
+
+  uint4 next_cnt = make_uint4(0, 0, 0, 0);
+  uint32_t tile = blockIdx.x;
+  if (threadIdx.x == 0 && tile < tiles) {
+    issue(tile, 0, load_counts(tile));
+    if (tile + gridDim.x < tiles) next_cnt = load_counts(tile + gridDim.x);
+  }
+  uint32_t f = 0, smax = 0;
+  for (uint32_t it = 0; tile < tiles; tile += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (threadIdx.x == 0) {
+      const uint32_t nt = tile + gridDim.x;
+      if (nt < tiles) {
+        issue(nt, stage ^ 1, next_cnt);
+        if (nt + gridDim.x < tiles) next_cnt = load_counts(nt + gridDim.x);  // consumed one iteration later
+      }
+    }
+    {  // wait for this stage's bytes
+      uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]), parity = (it >> 1) & 1u, done = 0;
+      while (!done)
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    }
+    const uint32_t g0 = s_meta[stage][0], c0 = s_meta[stage][1], s0 = s_meta[stage][2], woff = s_meta[stage][3], wcov = s_meta[stage][4], kcov = s_meta[stage][5];
+    const uint32_t ng = s_meta[stage][6], nc = s_meta[stage][7];  // gates / connections in this tile
+    const uint64_t tbase = (uint64_t)tile * kEvTile;
+    const uint32_t nev = (uint32_t)(min(n, tbase + kEvTile) - tbase);
+    const uint64_t w0 = 3ull * g0 + 2ull * c0 + (dense ? 0u : s0);
+    auto word = [&](uint32_t wl) -> uint32_t {  // payload word wl of this tile: staged, or (unaligned source / stream tail) straight from global
+      uint32_t k = wl + woff;
+      if (k < wcov) return s_w[stage][k];
+      return w0 + wl < n_words ? __ldg(words + w0 + wl) : 0u;
+    };
+    // ---- phase A, one lane per event: rank the event inside the tile and file it under its kind.
+    // s_list = [gates | connections | signals]; entry = local event index | (a second rank << 10): together with the entry's own
+    // position they give all three in-tile ranks (dg + dc + ds = local index), hence the payload offset 3*dg + 2*dc (+ ds).
+    uint32_t kb[4], gm[4], cm[4];
     uint32_t wg = 0, wc = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
+      uint32_t k = warp * 128 + j * 32 + lane;
+      kb[j] = k < nev ? (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) : 0x100u;  // 0x100: past the end
       gm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_GATE);
       cm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_CONNECT);
       wg += __popc(gm[j]);
       wc += __popc(cm[j]);
     }
     if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; }
-    __syncthreads();  // also: s_w is complete
-    uint32_t gi = g0, ci = c0;
-    for (int w = 0; w < warp; ++w) { gi += s_g[w]; ci += s_c[w]; }
+    __syncthreads();
+    uint32_t dg = 0, dc = 0;  // in-tile ranks
+    for (int w = 0; w < warp; ++w) { dg += s_g[w]; dc += s_c[w]; }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint64_t i = base + j * 32 + lane;
-      uint32_t my_g = gi + __popc(gm[j] & lt), my_c = ci + __popc(cm[j] & lt);
-      gi += __popc(gm[j]);
-      ci += __popc(cm[j]);
-      if (i >= n) continue;
-      uint32_t kind = kb[j] & 3u, op = kb[j] >> 2;
-      uint32_t t = (uint32_t)i;
-      uint32_t my_s = t - my_g - my_c;  // signals declared before this event
-      uint32_t wl = 3u * (my_g - g0) + 2u * (my_c - c0) + (dense ? 0u : my_s - s0);  // offset inside the staged payload
-      if (kind <= C2A_EV_SIGNAL_CONST) {
-        uint32_t sid = dense ? my_s : s_w[min(wl, 3u * kEvTile - 1)];
-        if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
+      uint32_t k = warp * 128 + j * 32 + lane;
+      uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
+      dg += __popc(gm[j]);
+      dc += __popc(cm[j]);
+      if (k >= nev) continue;
+      uint32_t kind = kb[j] & 3u;
+      if (kind == C2A_EV_GATE) s_list[min(my_dg, (uint32_t)kEvTile - 1)] = k | (my_dc << 10);
+      else if (kind == C2A_EV_CONNECT) s_list[min(ng + my_dc, (uint32_t)kEvTile - 1)] = k | (my_dg << 10);
+      else s_list[min(ng + nc + (k - my_dg - my_dc), (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
+    }
+    __syncthreads();
+    // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores
+    for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
+      uint32_t e = s_list[r], k = e & 1023u, my_dc = e >> 10;
+      uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : k - r - my_dc);
+      uint32_t op = (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) >> 2;
+      egates[g0 + r] = make_uint4(op, word(wl), word(wl + 1), word(wl + 2));
+      gate_t[g0 + r] = (uint32_t)tbase + k;
+    }
+    for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
+      uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = e >> 10;
+      uint32_t ds = k - my_dg - r;
+      uint32_t wl = 3u * my_dg + 2u * r + (dense ? 0u : ds);
+      conn[c0 + r] = make_uint2(word(wl), word(wl + 1));
+      conn_t[c0 + r] = (uint32_t)tbase + k;
+      conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
+    }
+    const uint32_t ns = nev - min(nev, ng + nc);
+    for (uint32_t r = threadIdx.x; r < ns; r += kBlock) {  // signal r of the tile
+      uint32_t e = s_list[ng + nc + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_dc = k - my_dg - r;
+      uint32_t sid = dense ? s0 + r : word(3u * my_dg + 2u * my_dc + r);
+      if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
+      else {
+        smax = max(smax, sid + 1);
+        if (sid >= S_cap) f |= EF_CAP;
         else {
-          smax = max(smax, sid + 1);
-          if (sid >= S_cap) f |= EF_CAP;
-          else {
-            sig_t[sid] = t;
-            sig_meta[sid] = make_uint2(my_s | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), my_c);
-          }
+          // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the number of
+          // declared ids then falls short of the number of signal events (k_ev_finalize counts them)
+          sig_t[sid] = (uint32_t)tbase + k;
+          sig_meta[sid] = make_uint2((s0 + r) | (e & 0x80000000u), c0 + my_dc);
         }
-      } else if (kind == C2A_EV_GATE) {
-        uint32_t w = min(wl, 3u * kEvTile - 3);
-        egates[my_g] = make_uint4(op, s_w[w], s_w[w + 1], s_w[w + 2]);
-        gate_t[my_g] = t;
-      } else {
-        uint32_t w = min(wl, 3u * kEvTile - 2);
-        conn[my_c] = make_uint2(s_w[w], s_w[w + 1]);
-        conn_t[my_c] = t;
-        conn_sb[my_c] = my_s;
       }
     }
-    __syncthreads();  // s_w / s_g / s_c are reused by the next tile
+    __syncthreads();  // the stage (and s_g / s_c) may be refilled from the next iteration on
   }
   smax = warp_max(smax);
   f = warp_or(f);

@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--variant", default="late")
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--levels", action="store_true", help="also time the Kahn level kernel")
+    ap.add_argument("--stream", default="packed", choices=["packed", "aos"])
     a = ap.parse_args()
     import torch
     wl = c2a.workloads.mimc_chains(a.chains, variant=a.variant)
@@ -26,7 +27,12 @@ def main():
     outs = np.array(sorted(wl.outputs), dtype=np.uint32)
     ctx = c2a.DeviceContext(0)
     lib, h, vp = c2a.lib, ctx.handle, C.c_void_p
-    from circom_2_arithc_b200._lib import EmitInfo
+    from circom_2_arithc_b200._lib import EmitInfo, PackedEvents
+    if a.stream == "packed":
+        kinds, words, flags = c2a.pack_events(np.ascontiguousarray(wl.events))
+        p_k = torch.from_numpy(kinds).pin_memory()
+        p_w = torch.from_numpy(words.view(np.int32)).pin_memory()
+        pk = PackedEvents(p_k.data_ptr(), p_w.data_ptr(), kinds.shape[0], words.shape[0], flags, 0)
     info = EmitInfo()
     bad = C.c_uint64(0)
     n = ev.shape[0]
@@ -34,7 +40,10 @@ def main():
     wc, err = C.c_uint32(0), C.c_uint64(0)
     for rep in range(a.reps):
         t0 = time.perf_counter()
-        st = lib.c2a_emit_events_device(h, vp(ev.data_ptr()), n, C.byref(info), C.byref(bad))
+        if a.stream == "packed":
+            st = lib.c2a_emit_packed_device(h, C.byref(pk), C.byref(info), C.byref(bad))
+        else:
+            st = lib.c2a_emit_events_device(h, vp(ev.data_ptr()), n, C.byref(info), C.byref(bad))
         t1 = time.perf_counter()
         assert st == 0, (st, ctx.last_error())
         ph_emit = ctx.phases()
