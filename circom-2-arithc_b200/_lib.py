@@ -89,12 +89,14 @@ _SIGS = {
     "c2a_build_circuit_device": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_rebase_wires_device": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, u32, u32]),
     "c2a_rebase_wire_map_device": (i32, [vp, vp, u64, u32, u32, u32, u32, u32]),
+    "c2a_rebase_wires_gathered_device": (i32, [vp, vp, vp, u64, vp, u32, u32]),
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),
     "c2a_evaluate": (i32, [vp, vp, u64, u32, vp, vp, u64p]),
     "c2a_emit_events_device": (i32, [vp, vp, u64, vp, u64p]),
     "c2a_emit_events_resident": (i32, [vp, vp, u64, vp, u64p]),
+    "c2a_emitted_signal_wires": (i32, [vp, vp, u64, vp]),
     "c2a_pack_events": (u64, [vp, u64, vp, vp, u32p]),
     "c2a_unpack_events": (i32, [vp, vp]),
     "c2a_emit_packed_device": (i32, [vp, vp, vp, u64p]),

@@ -566,6 +566,27 @@ __global__ void __launch_bounds__(kBlock) k_rebase(uint4* __restrict__ new_gates
   }
 }
 
+// same, offsets derived from the all-gathered counts (rank-major {n_in, n_mid, n_out, G}) by every thread: <= 8 ranks x 4 words
+__global__ void __launch_bounds__(kBlock) k_rebase_gathered(uint4* __restrict__ new_gates, uint32_t* __restrict__ order, uint32_t G,
+                                                            const unsigned long long* __restrict__ counts, uint32_t rank, uint32_t world) {
+  unsigned long long tot_in = 0, tot_mid = 0, pre_in = 0, pre_mid = 0, pre_out = 0, pre_g = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    unsigned long long a = counts[4 * r], b = counts[4 * r + 1], c = counts[4 * r + 2], g = counts[4 * r + 3];
+    tot_in += a;
+    tot_mid += b;
+    if (r < rank) { pre_in += a; pre_mid += b; pre_out += c; pre_g += g; }
+  }
+  const uint32_t n_in = (uint32_t)counts[4 * rank], n_mid = (uint32_t)counts[4 * rank + 1];
+  const uint32_t off_in = (uint32_t)pre_in, off_mid = (uint32_t)(tot_in + pre_mid) - n_in, off_out = (uint32_t)(tot_in + tot_mid + pre_out) - n_in - n_mid;
+  const uint32_t gate_base = (uint32_t)pre_g;
+  auto fix = [&](uint32_t w) { return w < n_in ? w + off_in : (w < n_in + n_mid ? w + off_mid : w + off_out); };
+  for (uint32_t k = blockIdx.x * kBlock + threadIdx.x; k < G; k += gridDim.x * kBlock) {
+    uint4 g = new_gates[k];
+    new_gates[k] = make_uint4(g.x, fix(g.y), fix(g.z), fix(g.w));
+    if (order) order[k] += gate_base;
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_rebase_map(uint32_t* __restrict__ wire, uint32_t n, uint32_t n_in, uint32_t n_mid, uint32_t off_in,
                                                        uint32_t off_mid, uint32_t off_out) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
@@ -599,6 +620,7 @@ void slab_reset(c2a_handle* h) {
   h->slab_used = 0;
   h->slab_keep = 0;
   h->emitted.valid = false;
+  h->emitted.wire = nullptr;
 }
 void slab_reset_keep(c2a_handle* h) { h->slab_used = h->slab_keep; }
 
@@ -1090,6 +1112,16 @@ int c2a_rebase_wires_device(c2a_handle* h, c2a_gate* d_new_gates, uint32_t* d_or
   if (G) LAUNCH(h, k_rebase, grid_for(h, (const void*)k_rebase, kBlock, G), kBlock, (uint4*)d_new_gates, d_order, (uint32_t)G, n_in, n_mid, off_in, off_mid, off_out, gate_base);
   if (!cuda_ok(h, cudaStreamSynchronize(h->stream), "rebase")) return C2A_ERR_CUDA;
   return C2A_OK;
+}
+
+int c2a_rebase_wires_gathered_device(c2a_handle* h, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, const uint64_t* d_counts, uint32_t rank,
+                                     uint32_t world) {
+  int st = check_sizes(h, G, 1);
+  if (st) return st;
+  if (!d_new_gates || !d_counts || rank >= world) return fail(h, C2A_ERR_INVALID_ARGUMENT, "bad argument");
+  if (G) LAUNCH(h, k_rebase_gathered, grid_for(h, (const void*)k_rebase_gathered, kBlock, G), kBlock, (uint4*)d_new_gates, d_order, (uint32_t)G,
+                (const unsigned long long*)d_counts, rank, world);
+  return cuda_ok(h, cudaGetLastError(), "rebase launch") ? C2A_OK : C2A_ERR_CUDA;
 }
 
 int c2a_rebase_wire_map_device(c2a_handle* h, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid, uint32_t off_in, uint32_t off_mid,

@@ -620,6 +620,16 @@ __global__ void __launch_bounds__(kBlock) k_ev_map_io(const uint32_t* __restrict
   if (__syncthreads_or(bad) && threadIdx.x == 0) es[ES_IOBAD] = 1u;
 }
 
+// selected signals -> wire ids (name-map lookups of compiler.rs:323-383, 466-493)
+__global__ void __launch_bounds__(kBlock) k_sig_wires(const uint32_t* __restrict__ sigs, uint64_t n, uint32_t S, const uint32_t* __restrict__ nos,
+                                                      const uint32_t* __restrict__ wire, uint32_t node_bound, uint32_t* __restrict__ out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) {
+    uint32_t s = sigs[i];
+    uint32_t nd = nos ? (s < S ? nos[s] : 0u) : s;  // nos == nullptr: the list already holds node ids
+    out[i] = nd && nd < node_bound ? wire[nd] : kNone;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 static inline size_t emit_scratch_bytes(uint64_t G, uint64_t C, uint64_t S) {  // slab part (exact sizes; the scatter targets live in the staging buffer)
   size_t b = 0;
@@ -695,6 +705,7 @@ static int emit_host_path(c2a_handle* h, const c2a_event* ev, uint64_t n, uint32
   h->emitted.G = G;
   h->emitted.node_count = c2a_node_count(c);
   h->emitted.signal_bound = S;
+  h->emitted.wire = nullptr;
   h->host_comp = c;  // kept: I/O signal lists are mapped through it when node_of_signal is not resident
   if (info) {
     info->n_gates = G;
@@ -975,6 +986,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   h->emitted.G = G;
   h->emitted.node_count = (uint32_t)(n_sig + n_eff);
   h->emitted.signal_bound = S;
+  h->emitted.wire = nullptr;
   if (info) {
     info->n_effective = n_eff;
     info->node_count = h->emitted.node_count;
@@ -1072,7 +1084,9 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
       if (!cuda_ok(h, cudaStreamSynchronize(s), "io upload")) return C2A_ERR_CUDA;
     }
   }
+  h->emitted.wire = nullptr;
   st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, nullptr, io_nodes, io_flag);
+  if (st == C2A_OK) h->emitted.wire = d_wire;  // stays valid until the next call that carves the slab
   if (st == C2A_OK && !outputs_on_device) {
     phase_begin(h, "d2h");
     if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
@@ -1085,6 +1099,38 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   }
   phases_collect(h);
   return st;
+}
+
+int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n, uint32_t* wires_out) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h->emitted.valid || !h->emitted.wire) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no built circuit is resident on this handle");
+  if (n == 0) return C2A_OK;
+  if (!signals || !wires_out) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  cudaStream_t s = h->stream;
+  // the event staging buffer is idle between calls: use it for the two lists (the slab holds the wire map itself)
+  const size_t need = 2 * align256(4 * n);
+  if (need > h->ev_bytes) {
+    if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
+    if (!cuda_ok(h, cudaMalloc(&h->ev_buf, need), "cudaMalloc(signal list)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+    h->ev_bytes = need;
+  }
+  uint32_t* d_sig = (uint32_t*)h->ev_buf;
+  uint32_t* d_out = (uint32_t*)(h->ev_buf + align256(4 * n));
+  const uint32_t* nos = h->emitted.nos_valid ? (const uint32_t*)(h->slab + h->emitted.nos_off) : nullptr;
+  std::vector<uint32_t> nodes;
+  const uint32_t* src = signals;
+  if (!nos) {  // sparse ids: the host emitter that produced the circuit knows the nodes
+    nodes.resize(n);
+    c2a_signal_nodes(h->host_comp, signals, n, nodes.data());
+    src = nodes.data();
+  }
+  if (!cuda_ok(h, cudaMemcpyAsync(d_sig, src, 4 * n, cudaMemcpyHostToDevice, s), "signal list H2D")) return C2A_ERR_CUDA;
+  LAUNCH(h, k_sig_wires, grid_for(h, (const void*)k_sig_wires, kBlock, n), kBlock, d_sig, n, h->emitted.signal_bound, nos, h->emitted.wire,
+         h->emitted.node_count + 1, d_out);
+  if (!cuda_ok(h, cudaMemcpyAsync(wires_out, d_out, 4 * n, cudaMemcpyDeviceToHost, s), "wires D2H")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "signal wires")) return C2A_ERR_CUDA;
+  return cuda_ok(h, cudaGetLastError(), "k_sig_wires") ? C2A_OK : C2A_ERR_CUDA;
 }
 
 int c2a_emitted_build_circuit(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,

@@ -46,6 +46,7 @@ struct c2a_handle {
     uint64_t G = 0;
     uint32_t node_count = 0;
     uint32_t signal_bound = 0;
+    const uint32_t* wire = nullptr;  // wire map of the last successful build on this circuit (device; slab scratch or the caller's array)
   } emitted;
   struct c2a_compiler* host_comp = nullptr;  // kept alive when the exact host emitter had to run (sparse ids)
 };

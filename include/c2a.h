@@ -131,6 +131,12 @@ int c2a_build_circuit_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, u
 int c2a_rebase_wires_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, uint32_t n_in, uint32_t n_mid,
                             uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base);
 
+/* Same rebase with the offsets computed ON THE DEVICE from the all-gathered per-rank counts: d_counts[world][4] (u64, rank-major:
+ * n_in, n_mid, n_out, G) as NCCL left them.  No host read of the counts, and the call only enqueues work on the handle's
+ * stream (it returns before the kernel ran; the next synchronising call on the handle orders after it). */
+int c2a_rebase_wires_gathered_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, const uint64_t* d_counts,
+                                     uint32_t rank, uint32_t world);
+
 /* same mapping applied to a node-indexed wire map (entries equal to C2A_NONE are left alone) */
 int c2a_rebase_wire_map_device(c2a_handle*, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid,
                                uint32_t off_in, uint32_t off_mid, uint32_t off_out);
@@ -196,6 +202,12 @@ int c2a_emitted_build_circuit(c2a_handle*, const uint32_t* input_signals, uint32
 int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                                      uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
                                      uint64_t* err_index);
+
+/* Wire ids of selected signals after c2a_emitted_build_circuit[_device] on this handle (what Compiler::build_circuit looks up for
+ * its input / output / constant name maps, src/compiler.rs:323-383, 466-493): wires_out[i] = wire of the node holding
+ * signals[i], C2A_NONE when the signal was never declared or its node has no wire.  With this a caller that wants the
+ * reference's result (gates + named wires) can pass NULL for order_out and wire_of_node and skip their device->host copies. */
+int c2a_emitted_signal_wires(c2a_handle*, const uint32_t* signals, uint64_t n, uint32_t* wires_out);
 
 /* ---- packed event stream.  The same emission calls at ~6 bytes per event instead of 16: what the walker hands to the
  * device emitter when the stream has to cross PCIe (c2a_program_packed) and what the device reads from HBM.

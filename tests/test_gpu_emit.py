@@ -253,6 +253,18 @@ def test_merge_errors(ctx, c2a):
     assert gates.tolist() == [[0, 1, 2, 5], [0, 1, 2, 5]]
 
 
+def test_signal_wires_need_a_built_circuit(ctx, c2a):
+    ev = np.asarray([(EV_S, 0, 0, 0), (EV_S, 1, 0, 0), (EV_S, 2, 0, 0), (EV_G, 0, 1, 2)], dtype=np.uint32)
+    ctx.emit_events(ev)
+    with pytest.raises(c2a.C2AError):
+        ctx.emitted_signal_wires([0, 1])           # emitted, not built yet
+    ctx.emitted_build_circuit([0, 1], [2])
+    assert ctx.emitted_signal_wires([2, 0, 1, 7]).tolist() == [2, 0, 1, 0xFFFFFFFF]
+    ctx.emit_events(ev)                            # a new emit drops the wire map
+    with pytest.raises(c2a.C2AError):
+        ctx.emitted_signal_wires([0])
+
+
 def test_packed_stream_rejects_inconsistent_word_count(ctx, c2a):
     ev = np.asarray([(EV_S, 0, 0, 0), (EV_S, 1, 0, 0), (EV_S, 2, 0, 0), (EV_G, 0, 1, 2), (EV_C, 2, 1, 0)], dtype=np.uint32)
     kinds_b, words, flags = c2a.pack_events(ev)
@@ -298,6 +310,14 @@ def _workload_case(ctx, orc, c2a, wl, vs_oracle_emit):
     st, _, o_order, o_wire, o_gates, o_wc = orc.backend_raw(gates, nb, nos[ins], nos[outs])
     assert st == 0 and wc == o_wc
     assert np.array_equal(order, o_order) and np.array_equal(wire, o_wire) and np.array_equal(ng, o_gates)
+    # named-wire lookups without the whole wire map (compiler.rs:323-383, 466-493): gates only + selected signals
+    kinds = ev[:, 0] & 0xFF
+    consts = ev[kinds == 1, 1][:1000]
+    o2, w2, g2, wc2 = ctx.emitted_build_circuit(ins, outs, want_order=False, want_wires=False)
+    assert o2 is None and w2 is None and wc2 == wc and np.array_equal(g2, ng)
+    probe = np.concatenate([ins, outs, consts, np.array([info["signal_bound"] + 5], dtype=np.uint32)]).astype(np.uint32)
+    got = ctx.emitted_signal_wires(probe)
+    assert np.array_equal(got[:-1], o_wire[nos[probe[:-1]]]) and got[-1] == 0xFFFFFFFF
     return info
 
 

@@ -302,3 +302,28 @@ def test_ten_million_gates_properties(ctx, c2a):
     # idempotence: the sorted circuit is in dependency order -> identity order
     order2, _, ng2, wc2 = ctx.build_circuit(sg, nb, ins, outs)
     assert np.array_equal(order2, np.arange(G, dtype=np.uint32)) and wc2 == wc and np.array_equal(ng2, ng)
+
+
+def test_rebase_from_gathered_counts_matches_host_offsets(ctx, c2a):
+    """c2a_rebase_wires_gathered_device (offsets derived on the device from the all-gathered counts) against
+    c2a_rebase_wires_device with the host-side offsets of sharding.rebase_offsets, one GPU standing in for rank 1 of 3"""
+    import ctypes as C
+    import torch
+    lib, vp = c2a.lib, C.c_void_p
+    rng = np.random.RandomState(5)
+    counts = np.array([[7, 100, 3, 50], [5, 40, 2, 33], [9, 77, 4, 21]], dtype=np.int64)
+    rank, world = 1, 3
+    n_in, n_mid, n_out, G = (int(x) for x in counts[rank])
+    gates = np.stack([rng.randint(0, 20, G), rng.randint(0, n_in + n_mid + n_out, G), rng.randint(0, n_in + n_mid + n_out, G),
+                      rng.randint(0, n_in + n_mid + n_out, G)], axis=1).astype(np.uint32)
+    order = rng.permutation(G).astype(np.uint32)
+    dev = torch.device("cuda", 0)
+    a_g, a_o = torch.from_numpy(gates.view(np.int32)).to(dev), torch.from_numpy(order.view(np.int32)).to(dev)
+    b_g, b_o = a_g.clone(), a_o.clone()
+    off_in, off_mid, off_out, gate_base = c2a.sharding.rebase_offsets(counts, rank, shared_io=False)
+    assert lib.c2a_rebase_wires_device(ctx.handle, vp(a_g.data_ptr()), vp(a_o.data_ptr()), G, n_in, n_mid, off_in, off_mid, off_out, gate_base) == 0
+    d_counts = torch.from_numpy(counts).to(dev)
+    assert lib.c2a_rebase_wires_gathered_device(ctx.handle, vp(b_g.data_ptr()), vp(b_o.data_ptr()), G, vp(d_counts.data_ptr()), rank, world) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(a_g, b_g) and torch.equal(a_o, b_o)
+    assert not np.array_equal(a_g.cpu().numpy().view(np.uint32), gates)
