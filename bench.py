@@ -144,6 +144,7 @@ def main():
     ap.add_argument("--no-host-emit", action="store_true", help="skip the host-emitter comparison leg")
     ap.add_argument("--stream", default="packed", choices=["packed", "aos"],
                     help="event stream format handed to the emitter: packed (kinds byte + payload words, c2a_emit_packed_*) or 16-byte c2a_event records")
+    ap.add_argument("--no-pipelined", action="store_true", help="skip the two-circuits-in-flight e2e leg")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
     args = ap.parse_args()
 
@@ -404,6 +405,68 @@ def main():
     e2e_value = world * G * Ke / dt
     named_w = p_named_w.numpy().astype(np.uint32).copy()
     dt_all = e2e_measure(all_arrays=True) if lean else dt
+    # ---- e2e_pipelined (N = 1, extra): two circuits in flight - a second handle on a second host thread - so that the H2D copy
+    #      of one step overlaps the D2H copy and the kernels of the other (PCIe is full duplex; every step still copies its own
+    #      input and its own result).  Same calls as `e2e`; reported beside it, not instead of it.
+    pipe = None
+    if lean and not args.no_pipelined:
+        ctx2 = c2a.DeviceContext(local_rank)
+        lib.c2a_set_timing(ctx2.handle, 0)
+        lib.c2a_set_timing(h, 0)
+        p_new2 = torch.empty((G, 4), dtype=torch.int32).pin_memory()
+        p_named_w2 = torch.empty(len(named), dtype=torch.int32).pin_memory()
+        if packed:
+            p_kinds2, p_words2 = p_kinds.clone().pin_memory(), p_words.clone().pin_memory()
+            pk_host2 = PackedEvents(p_kinds2.data_ptr(), p_words2.data_ptr(), n_ev, int(words_np.shape[0]), pk_flags, 0)
+        else:
+            p_events2 = p_events.clone().pin_memory()
+        errs = []
+
+        stagger = 0.5 * dt / Ke   # start the second circuit half a step later: its H2D then meets the first one's kernels + D2H
+
+        def worker(hh, which, steps):
+            inf, b, w, e = EmitInfo(), C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
+            if which:
+                time.sleep(stagger)
+            try:
+                for _ in range(steps):
+                    if packed:
+                        st = lib.c2a_emit_packed_device(hh, C.byref(pk_host if which == 0 else pk_host2), C.byref(inf), C.byref(b))
+                    else:
+                        st = lib.c2a_emit_events_device(hh, vp((p_events if which == 0 else p_events2).data_ptr()), n_ev, C.byref(inf), C.byref(b))
+                    if st == 0:
+                        st = lib.c2a_emitted_build_circuit(hh, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids), None, None,
+                                                           vp((p_new if which == 0 else p_new2).data_ptr()), C.byref(w), C.byref(e))
+                    if st == 0:
+                        st = lib.c2a_emitted_signal_wires(hh, vp(p_named.data_ptr()), len(named), vp((p_named_w if which == 0 else p_named_w2).data_ptr()))
+                    if st != 0:
+                        errs.append(st)
+                        return
+            except Exception as ex:  # noqa: BLE001
+                errs.append(repr(ex))
+
+        def run_pair(steps):
+            ts = [threading.Thread(target=worker, args=(h, 0, steps)), threading.Thread(target=worker, args=(ctx2.handle, 1, steps))]
+            for t_ in ts:
+                t_.start()
+            for t_ in ts:
+                t_.join()
+
+        run_pair(2)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        run_pair(Ke)
+        torch.cuda.synchronize()
+        dtp = time.perf_counter() - t0
+        lib.c2a_set_timing(h, 1)
+        if errs:
+            pipe = {"error": str(errs[:2])}
+        else:
+            assert torch.equal(p_new, p_new2) and torch.equal(p_named_w, p_named_w2), "the two pipelined handles disagree"
+            pipe = {"value": 2 * Ke * G / dtp, "unit": "gates/s", "s_per_step": dtp / (2 * Ke), "in_flight": 2, "steps": 2 * Ke,
+                    "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                    "note": "two handles on two host threads, same calls as e2e; each step copies its own input and result"}
+        del ctx2
     stop.set()
     th.join(timeout=2)
 
@@ -496,6 +559,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": summarize_clocks(clk_lines),
     }
+    if pipe is not None:
+        if "value" in pipe:
+            pipe["h2d_bytes_per_step"], pipe["d2h_bytes_per_step"] = int(h2d), int(d2h)
+        out["e2e_pipelined"] = pipe
     if host_emit:
         out["e2e_host_emitter"] = {"value": host_emit["gates_per_s"], "unit": "gates/s", "emit_s": host_emit["emit_s"], "build_s": host_emit["build_s"],
                                    "note": "same circuit through the host union-find emitter (c2a_emit_events + c2a_build_circuit), pageable buffers, 1 step"}

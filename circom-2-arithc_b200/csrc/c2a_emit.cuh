@@ -241,7 +241,7 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // bytes and the payload word range of its next tile are already in flight.  One elected thread computes the (16-byte aligned)
 // ranges from the scanned tile counts and issues the copies; everybody waits on the stage's mbarrier.
 constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words per event) + alignment slack
-__global__ void __launch_bounds__(kBlock) k_pk_scatter(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+__global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
                                                        uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
@@ -346,38 +346,48 @@ __global__ void __launch_bounds__(kBlock) k_pk_scatter(const uint8_t* __restrict
       else s_list[min(ng + nc + (k - my_dg - my_dc), (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
     }
     __syncthreads();
-    // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores
-    for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
-      uint32_t e = s_list[r], k = e & 1023u, my_dc = e >> 10;
-      uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : k - r - my_dc);
-      uint32_t op = (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) >> 2;
-      egates[g0 + r] = make_uint4(op, word(wl), word(wl + 1), word(wl + 2));
-      gate_t[g0 + r] = (uint32_t)tbase + k;
-    }
-    for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
-      uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = e >> 10;
-      uint32_t ds = k - my_dg - r;
-      uint32_t wl = 3u * my_dg + 2u * r + (dense ? 0u : ds);
-      conn[c0 + r] = make_uint2(word(wl), word(wl + 1));
-      conn_t[c0 + r] = (uint32_t)tbase + k;
-      conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
-    }
-    const uint32_t ns = nev - min(nev, ng + nc);
-    for (uint32_t r = threadIdx.x; r < ns; r += kBlock) {  // signal r of the tile
-      uint32_t e = s_list[ng + nc + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_dc = k - my_dg - r;
-      uint32_t sid = dense ? s0 + r : word(3u * my_dg + 2u * my_dc + r);
-      if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
-      else {
-        smax = max(smax, sid + 1);
-        if (sid >= S_cap) f |= EF_CAP;
+    // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores.
+    // Interior tiles (everything staged by the bulk copies) take the check-free instantiation.
+    auto phase_b = [&](auto fast_tag) {
+      constexpr bool kFast = decltype(fast_tag)::value;
+      const uint32_t* __restrict__ sw = &s_w[stage][woff];
+      const uint8_t* __restrict__ sk = &s_k[stage][0];
+      auto W = [&](uint32_t wl) -> uint32_t { return kFast ? sw[wl] : word(wl); };
+      auto K = [&](uint32_t k) -> uint32_t { return kFast ? (uint32_t)sk[k] : (k < kcov ? (uint32_t)sk[k] : (uint32_t)__ldg(kinds + tbase + k)); };
+      for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
+        uint32_t e = s_list[r], k = e & 1023u, my_dc = e >> 10;
+        uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : k - r - my_dc);
+        egates[g0 + r] = make_uint4(K(k) >> 2, W(wl), W(wl + 1), W(wl + 2));
+        gate_t[g0 + r] = (uint32_t)tbase + k;
+      }
+      for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
+        uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = e >> 10;
+        uint32_t ds = k - my_dg - r;
+        uint32_t wl = 3u * my_dg + 2u * r + (dense ? 0u : ds);
+        conn[c0 + r] = make_uint2(W(wl), W(wl + 1));
+        conn_t[c0 + r] = (uint32_t)tbase + k;
+        conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
+      }
+      const uint32_t ns = nev - min(nev, ng + nc);
+      for (uint32_t r = threadIdx.x; r < ns; r += kBlock) {  // signal r of the tile
+        uint32_t e = s_list[ng + nc + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_dc = k - my_dg - r;
+        uint32_t sid = dense ? s0 + r : W(3u * my_dg + 2u * my_dc + r);
+        if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
         else {
-          // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the number of
-          // declared ids then falls short of the number of signal events (k_ev_finalize counts them)
-          sig_t[sid] = (uint32_t)tbase + k;
-          sig_meta[sid] = make_uint2((s0 + r) | (e & 0x80000000u), c0 + my_dc);
+          smax = max(smax, sid + 1);
+          if (sid >= S_cap) f |= EF_CAP;
+          else {
+            // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the number of
+            // declared ids then falls short of the number of signal events (k_ev_finalize counts them)
+            sig_t[sid] = (uint32_t)tbase + k;
+            sig_meta[sid] = make_uint2((s0 + r) | (e & 0x80000000u), c0 + my_dc);
+          }
         }
       }
-    }
+    };
+    const uint32_t wn = 3u * ng + 2u * nc + (dense ? 0u : nev - min(nev, ng + nc));  // payload words of the tile
+    if (kcov == nev && woff + wn <= wcov && ng + nc <= nev) phase_b(std::true_type{});
+    else phase_b(std::false_type{});
     __syncthreads();  // the stage (and s_g / s_c) may be refilled from the next iteration on
   }
   smax = warp_max(smax);
@@ -810,16 +820,17 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
       phase_begin(h, "k_ev_count");
       if (pk) LAUNCH(h, k_pk_count, egrid, kBlock, d_kinds, n, tiles, tile_g, tile_c, es);
-      else LAUNCH(h, k_ev_count, egrid, kBlock, d_ev, n, tiles, tile_g, tile_c, es);
+      else LAUNCH(h, k_ev_count, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_count, kBlock, n)), kBlock, d_ev, n, tiles, tile_g, tile_c, es);
       phase_end(h);
       phase_begin(h, "k_scan_u32");
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
       phase_begin(h, "k_ev_scatter");
-      if (pk) LAUNCH(h, k_pk_scatter, egrid, kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta,
+      // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
+      if (pk) LAUNCH(h, k_pk_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta,
                      egates, gate_t, conn, conn_t, conn_sb, es);
-      else LAUNCH(h, k_ev_scatter, egrid, kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
+      else LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_scatter, kBlock, n)), kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
       cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
       cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
