@@ -54,6 +54,23 @@ __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned 
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// warp reductions
+__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+  return v;
+}
+__device__ __forceinline__ uint32_t warp_or(uint32_t v) {
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
 constexpr int kBlock = 256;
 constexpr uint32_t kNone = C2A_NONE;
 static void emit_drop_host(c2a_handle* h);  // c2a_emit.cuh

@@ -45,22 +45,6 @@ enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_
 enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128,
        EF_CAP = 256 /* a signal id beyond the table bound the pass was launched with: rerun with the exact bound */ };
 
-__device__ __forceinline__ uint32_t warp_sum(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_max(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
-  return v;
-}
-__device__ __forceinline__ uint32_t warp_or(uint32_t v) {
-#pragma unroll
-  for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xFFFFFFFFu, v, o);
-  return v;
-}
-
 // ---- E0 ---------------------------------------------------------------------------------------------------
 // (A single fused pass - tile counts chained by a decoupled look-back inside the scatter - was measured at 0.67 ms on the
 //  42 M-event stream: every tile then carries ticket + load + look-back latency in series.  Reading the stream twice is faster.)

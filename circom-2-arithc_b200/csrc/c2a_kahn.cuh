@@ -1,37 +1,39 @@
-// c2a_kahn.cuh — K3/K4: consumer CSR + level-synchronous Kahn frontier, and the opt-in layer-wise sweeps
-// (K8 constant-fold mask, K9 dead-gate mask).  Included by c2a_device.cu (single translation unit).
+// c2a_kahn.cuh — K3/K4: consumer CSR + Kahn levels, and the opt-in layer-wise sweeps (K8 constant-fold mask, K9 dead-gate
+// mask).  Included by c2a_device.cu (single translation unit).
 //
 // The dependency relation is the reference's (src/compiler.rs:401-421): gate g depends on the LAST producer
-// of its lh and rh nodes.  Kahn yields a valid topological order and the levels, NOT the reference's DFS
-// post-order (that is K5, c2a_device.cu); it is used for cycle screening, the sweeps and evaluators.
+// of its lh and rh nodes.  Kahn yields a valid topological order and the levels (longest-path depth), NOT the reference's
+// DFS post-order (that is K5, c2a_device.cu); it is used for cycle screening, the sweeps and the evaluator.
 //
-//   K3  k_kahn_count / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G]  (multiplicity kept)
-//   K4  k_kahn_frontier   ONE persistent cooperative launch for all levels:
-//         * the output array level_order[] is the BFS queue itself: [lo,hi) is the current frontier
-//         * in-degree decrements are atomicSub on indeg[]; newly ready gates are appended with one
-//           warp-aggregated atomicAdd per warp (ballot + popc)
-//         * rows of >= kBulkRow consumers are staged into shared memory with a TMA bulk copy
-//           (cp.async.bulk + mbarrier) by the whole CTA
-//         * one grid barrier per level; when the frontier is small (<= kSmallFrontier) CTA 0 runs consecutive
-//           levels alone with __syncthreads() only while the other CTAs wait at the barrier
+//   K3  k_kahn_count / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G]  (multiplicity kept; bit 31 of a col
+//       entry says "this consumer has two dependency slots", i.e. it is released by its SECOND arrival)
+//   K4  asynchronous Kahn, no level barrier (round 1 measured the level-synchronous cooperative kernel at 8.5 us per level -
+//       one grid barrier + a six-deep dependent load/atomic chain - which is 4.7 ms on the 547-level, 10 M-gate MiMC stream):
+//         k_kahn_walk     every gate without dependencies is a root; the thread that releases a consumer keeps walking it
+//                         (chain following: ~2-3 dependent L2 round trips per hop, no synchronisation), further released
+//                         consumers go to a small per-thread stack, its overflow to a global queue (next launch).
+//                         A one-slot consumer is released by its only producer with level L+1, no atomic at all;
+//                         a two-slot consumer by ONE atomicMax(lv[c], L+1): the first arrival reads 0, the second reads the
+//                         other level - in-degree decrement and level maximum in a single word.
+//         k_kahn_long     rows of >= kLongRow consumers: one CTA per row, the row staged through shared memory by TMA bulk
+//                         copies (cp.async.bulk + mbarrier), released consumers appended with one warp-aggregated atomicAdd
+//         k_level_pass<hist> / scan / k_level_pass<scatter>   counting sort by level -> level-major order + level_off[]
 #pragma once
 
 namespace c2a {
 
 constexpr int kKahnBlock = 512;
-constexpr uint32_t kSmallFrontier = 2048;
-constexpr uint32_t kBulkRow = 1024;       // consumers; rows at least this long go through the TMA bulk path
+constexpr uint32_t kLongRow = 512;        // consumers; rows at least this long are walked by a whole CTA
 constexpr uint32_t kBulkChunk = 4096;     // u32 entries staged per bulk copy (16 KB)
-enum { KC_TAIL = 0, KC_LO = 1, KC_HI = 2, KC_LEVEL = 3, KC_ARRIVE = 4, KC_RELEASE = 5, KC_ERRMIN = 6, KC_OVERFLOW = 7, KC_BIGN = 8, KC_COUNT = 16 };
+constexpr int kWalkStack = 16;            // released-but-not-yet-walked consumers a thread keeps for itself
+constexpr uint32_t kTwoSlots = 0x80000000u;
+enum { KC_QN0 = 0, KC_QN1 = 1, KC_LONGN0 = 2, KC_LONGN1 = 3, KC_DONE = 4, KC_MAXLV = 5, KC_ERRMIN = 6, KC_COUNT = 16 };
 
-__global__ void __launch_bounds__(kBlock) k_kahn_count(const uint2* __restrict__ dep, uint32_t G, uint32_t* __restrict__ indeg,
-                                                       uint32_t* __restrict__ cnt) {
+__global__ void __launch_bounds__(kBlock) k_kahn_count(const uint2* __restrict__ dep, uint32_t G, uint32_t* __restrict__ cnt) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint2 d = dep[g];
-    uint32_t n = 0;
-    if (d.x != kNone) { atomicAdd(cnt + d.x, 1u); ++n; }
-    if (d.y != kNone) { atomicAdd(cnt + d.y, 1u); ++n; }  // lh == rh: the same consumer twice, decremented twice
-    indeg[g] = n;
+    if (d.x != kNone) atomicAdd(cnt + d.x, 1u);
+    if (d.y != kNone) atomicAdd(cnt + d.y, 1u);  // lh == rh: the same consumer twice, it arrives twice
   }
 }
 
@@ -39,55 +41,15 @@ __global__ void __launch_bounds__(kBlock) k_kahn_fill(const uint2* __restrict__ 
                                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ col) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint2 d = dep[g];
-    if (d.x != kNone) col[row_off[d.x] + atomicAdd(cursor + d.x, 1u)] = g;
-    if (d.y != kNone) col[row_off[d.y] + atomicAdd(cursor + d.y, 1u)] = g;
+    const uint32_t e = g | ((d.x != kNone && d.y != kNone) ? kTwoSlots : 0u);
+    if (d.x != kNone) col[row_off[d.x] + atomicAdd(cursor + d.x, 1u)] = e;
+    if (d.y != kNone) col[row_off[d.y] + atomicAdd(cursor + d.y, 1u)] = e;
   }
-}
-
-// ---- grid barrier with a serial section run by the last CTA to arrive --------------------------------------
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-
-// Advance the frontier window: called by exactly one thread when every append of the level is visible.
-__device__ __forceinline__ void kahn_advance(uint32_t* ctrl, uint32_t* __restrict__ level_off, uint32_t level_cap) {
-  uint32_t hi = ctrl[KC_HI], tail = ld_acquire_u32(ctrl + KC_TAIL), lvl = ctrl[KC_LEVEL] + 1;
-  ctrl[KC_LO] = hi;
-  ctrl[KC_HI] = tail;
-  ctrl[KC_LEVEL] = lvl;
-  if (lvl <= level_cap) level_off[lvl] = hi; else ctrl[KC_OVERFLOW] = 1;
-}
-
-template <bool kAdvance>
-__device__ __forceinline__ void kahn_grid_barrier(uint32_t* ctrl, uint32_t& gen, uint32_t nblocks, uint32_t* level_off, uint32_t level_cap,
-                                                  bool advance) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    uint32_t old = atomicAdd(ctrl + KC_ARRIVE, 1u);
-    if (old == nblocks * (gen + 1) - 1) {  // last to arrive: everything of this level is visible
-      if (kAdvance && advance) kahn_advance(ctrl, level_off, level_cap);
-      __threadfence();
-      st_release_u32(ctrl + KC_RELEASE, gen + 1);
-    } else {
-      uint32_t spins = 0;
-      while (ld_acquire_u32(ctrl + KC_RELEASE) < gen + 1) {
-        __nanosleep(32);
-        if (++spins > (1u << 27)) __trap();  // ~10 s: a CTA never arrived (fail loudly, do not hang)
-      }
-    }
-  }
-  ++gen;
-  __syncthreads();
 }
 
 // warp-aggregated append of `item` for lanes with ready != 0 (all 32 lanes must call)
-__device__ __forceinline__ void warp_append(bool ready, uint32_t item, uint32_t* __restrict__ queue, uint32_t* __restrict__ tail) {
+template <typename T>
+__device__ __forceinline__ void warp_append(bool ready, const T& item, T* __restrict__ queue, uint32_t* __restrict__ tail) {
   uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
   if (!m) return;
   int lane = threadIdx.x & 31;
@@ -97,11 +59,81 @@ __device__ __forceinline__ void warp_append(bool ready, uint32_t item, uint32_t*
   if (ready) queue[base + __popc(m & ((1u << lane) - 1))] = item;
 }
 
-__device__ __forceinline__ void kahn_relax_consumer(bool valid, uint32_t c, uint32_t* __restrict__ indeg, uint32_t* __restrict__ queue,
-                                                    uint32_t* __restrict__ tail) {
-  bool ready = false;
-  if (valid) ready = atomicSub(indeg + c, 1u) == 1u;
-  warp_append(ready, c, queue, tail);
+// one arrival at consumer entry e from a producer of level L: returns true when this arrival releases it (*lc = its level)
+__device__ __forceinline__ bool kahn_arrive(uint32_t e, uint32_t L, uint32_t* __restrict__ lv, uint32_t* lc) {
+  if (!(e & kTwoSlots)) { *lc = L + 1; return true; }
+  uint32_t old = atomicMax(lv + (e & ~kTwoSlots), L + 1);  // lv = 0: nobody arrived yet (levels stored here are >= 1)
+  *lc = max(old, L + 1);
+  return old != 0;
+}
+
+// Walk from (g, L): record the level, release consumers, continue with one of them.  queue entries are {gate, level}.
+__device__ __forceinline__ void kahn_walk(uint32_t g, uint32_t L, const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col,
+                                          uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of, uint2* __restrict__ q_out,
+                                          uint32_t* __restrict__ q_out_n, uint2* __restrict__ long_out, uint32_t* __restrict__ long_out_n,
+                                          uint32_t& done, uint32_t& maxl) {
+  uint32_t sg[kWalkStack], sl[kWalkStack];
+  int sp = 0;
+  while (true) {
+    level_of[g] = L;
+    ++done;
+    maxl = max(maxl, L);
+    const uint32_t beg = row_off[g], end = row_off[g + 1];
+    uint32_t ng = kNone, nl = 0;
+    if (end - beg >= kLongRow) {
+      long_out[atomicAdd(long_out_n, 1u)] = make_uint2(g, L);  // a whole CTA takes this row (k_kahn_long)
+    } else {
+      for (uint32_t j = beg; j < end; ++j) {
+        uint32_t e = col[j], lc;
+        if (!kahn_arrive(e, L, lv, &lc)) continue;
+        uint32_t c = e & ~kTwoSlots;
+        if (ng == kNone) { ng = c; nl = lc; }
+        else if (sp < kWalkStack) { sg[sp] = c; sl[sp] = lc; ++sp; }
+        else q_out[atomicAdd(q_out_n, 1u)] = make_uint2(c, lc);
+      }
+    }
+    if (ng == kNone) {
+      if (sp == 0) break;
+      --sp;
+      ng = sg[sp];
+      nl = sl[sp];
+    }
+    g = ng;
+    L = nl;
+  }
+}
+
+__device__ __forceinline__ void kahn_commit(uint32_t done, uint32_t maxl, uint32_t* ctrl) {
+  done = warp_sum(done);
+  maxl = warp_max(maxl);
+  if ((threadIdx.x & 31) == 0 && done) { atomicAdd(ctrl + KC_DONE, done); atomicMax(ctrl + KC_MAXLV, maxl); }
+}
+
+// roots: gates without dependencies (level 0)
+__global__ void __launch_bounds__(kBlock) k_kahn_walk_roots(const uint2* __restrict__ dep, uint32_t G, const uint32_t* __restrict__ row_off,
+                                                            const uint32_t* __restrict__ col, uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of,
+                                                            uint2* __restrict__ q_out, uint2* __restrict__ long_out, uint32_t* ctrl) {
+  uint32_t done = 0, maxl = 0;
+  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
+    uint2 d = dep[g];
+    if (d.x == kNone && d.y == kNone) kahn_walk(g, 0, row_off, col, lv, level_of, q_out, ctrl + KC_QN0, long_out, ctrl + KC_LONGN0, done, maxl);
+  }
+  kahn_commit(done, maxl, ctrl);
+}
+
+// overflow queue of the previous launch: released consumers nobody has walked yet
+__global__ void __launch_bounds__(kBlock) k_kahn_walk_queue(const uint2* __restrict__ q_in, const uint32_t* __restrict__ q_in_n,
+                                                            const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col,
+                                                            uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of, uint2* __restrict__ q_out,
+                                                            uint32_t* __restrict__ q_out_n, uint2* __restrict__ long_out, uint32_t* __restrict__ long_out_n,
+                                                            uint32_t* ctrl) {
+  uint32_t done = 0, maxl = 0;
+  const uint32_t n = *q_in_n;
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint2 it = q_in[i];
+    kahn_walk(it.x, it.y, row_off, col, lv, level_of, q_out, q_out_n, long_out, long_out_n, done, maxl);
+  }
+  kahn_commit(done, maxl, ctrl);
 }
 
 // TMA 1-D bulk copy global -> shared, completion on an mbarrier (cp.async.bulk; SASS: UBLKCP)
@@ -109,6 +141,7 @@ __device__ __forceinline__ void bulk_load_row(uint32_t* smem_dst, const uint32_t
   uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_dst);
   uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
   if (threadIdx.x == 0) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar)
                  : "memory");
@@ -120,150 +153,117 @@ __device__ __forceinline__ void bulk_load_row(uint32_t* smem_dst, const uint32_t
   }
 }
 
-// Process frontier items [lo,hi) with the threads of this CTA that are given (stride = number of cooperating
-// threads across the grid).  Rows shorter than kBulkRow: one lane per item, the warp walks the rows in lock
-// step (ballots stay converged).  Longer rows: recorded in s_big and handled by the whole CTA through smem.
-__device__ __forceinline__ void kahn_process(uint32_t lo, uint32_t hi, uint32_t first, uint32_t stride, const uint32_t* __restrict__ row_off,
-                                             const uint32_t* __restrict__ col, uint32_t* __restrict__ indeg, uint32_t* __restrict__ queue,
-                                             uint32_t* ctrl, uint32_t* s_big, uint32_t* s_bign, uint32_t* s_stage, unsigned long long* s_mbar,
-                                             uint32_t& mbar_phase) {
-  const int lane = threadIdx.x & 31;
-  // every warp iterates the same number of times over its slice so that the ballots are full-warp
-  uint32_t n = hi - lo;
-  uint32_t iters = (n + stride - 1) / stride;
-  for (uint32_t it = 0; it < iters; ++it) {
-    uint32_t i = lo + it * stride + first;
-    uint32_t beg = 0, len = 0;
-    if (i < hi) {
-      uint32_t g = queue[i];
-      beg = row_off[g];
-      len = row_off[g + 1] - beg;
-      if (len >= kBulkRow) {  // defer to the CTA-wide bulk path
-        uint32_t slot = atomicAdd(s_bign, 1u);
-        if (slot < 64) { s_big[2 * slot] = beg; s_big[2 * slot + 1] = len; len = 0; }
-        // more than 64 long rows in one CTA pass: fall through and walk it here (correct, just slower)
-      }
-    }
-    // short rows: lock-step walk
-    uint32_t maxlen = len;
-#pragma unroll
-    for (int o = 16; o; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(0xFFFFFFFFu, maxlen, o));
-    if (maxlen <= 32) {
-      for (uint32_t j = 0; j < maxlen; ++j) {
-        bool v = j < len;
-        uint32_t c = v ? col[beg + j] : 0u;
-        kahn_relax_consumer(v, c, indeg, queue, ctrl + KC_TAIL);
-      }
-    } else {  // medium rows: the warp takes the lanes' rows one after the other, 32 consumers at a time
-      uint32_t has = __ballot_sync(0xFFFFFFFFu, len > 0);
-      while (has) {
-        int src = __ffs(has) - 1;
-        has &= has - 1;
-        uint32_t b = __shfl_sync(0xFFFFFFFFu, beg, src), l = __shfl_sync(0xFFFFFFFFu, len, src);
-        for (uint32_t j = 0; j < l; j += 32) {
-          bool v = j + lane < l;
-          uint32_t c = v ? col[b + j + lane] : 0u;
-          kahn_relax_consumer(v, c, indeg, queue, ctrl + KC_TAIL);
-        }
-      }
-    }
+// long rows: one CTA per row; the gate itself was already recorded by the walker that found it.  Released consumers are
+// queued (they are walked by the next k_kahn_walk_queue launch).
+__global__ void __launch_bounds__(kKahnBlock) k_kahn_long(const uint2* __restrict__ long_in, const uint32_t* __restrict__ long_in_n,
+                                                          const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col, uint32_t* __restrict__ lv,
+                                                          uint2* __restrict__ q_out, uint32_t* __restrict__ q_out_n) {
+  __shared__ __align__(16) uint32_t s_stage[kBulkChunk];
+  __shared__ __align__(8) unsigned long long s_mbar;
+  uint32_t mbar_phase = 0;
+  if (threadIdx.x == 0) {
+    uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  // long rows: CTA-wide, staged through shared memory by TMA bulk copies of 16-byte aligned chunks
-  uint32_t nb = min(*s_bign, 64u);
-  for (uint32_t r = 0; r < nb; ++r) {
-    uint32_t beg = s_big[2 * r], len = s_big[2 * r + 1];
-    uint32_t pos = beg, end = beg + len;
-    // unaligned head straight from global
+  const uint32_t n = *long_in_n;
+  auto relax = [&](bool valid, uint32_t e, uint32_t L) {
+    uint32_t lc = 0;
+    bool ready = valid && kahn_arrive(e, L, lv, &lc);
+    warp_append(ready, make_uint2(e & ~kTwoSlots, lc), q_out, q_out_n);
+  };
+  for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
+    const uint2 it = long_in[r];
+    const uint32_t L = it.y;
+    uint32_t pos = row_off[it.x];
+    const uint32_t end = row_off[it.x + 1];
+    // unaligned head straight from global (bulk copies need 16-byte aligned sources)
     uint32_t head_end = min(end, (pos + 3u) & ~3u);
     for (uint32_t j = pos + threadIdx.x; j < ((head_end - pos + 31) / 32) * 32 + pos; j += blockDim.x) {
       bool v = j < head_end;
-      kahn_relax_consumer(v, v ? col[j] : 0u, indeg, queue, ctrl + KC_TAIL);
+      relax(v, v ? col[j] : 0u, L);
     }
     pos = head_end;
     while (pos + 4 <= end) {
       uint32_t cnt = min((end - pos) & ~3u, kBulkChunk);
-      bulk_load_row(s_stage, col + pos, cnt * 4, s_mbar, mbar_phase);
+      bulk_load_row(s_stage, col + pos, cnt * 4, &s_mbar, mbar_phase);
       mbar_phase ^= 1;
       for (uint32_t j = threadIdx.x; j < ((cnt + 31) / 32) * 32; j += blockDim.x) {
         bool v = j < cnt;
-        kahn_relax_consumer(v, v ? s_stage[j] : 0u, indeg, queue, ctrl + KC_TAIL);
+        relax(v, v ? s_stage[j] : 0u, L);
       }
       __syncthreads();  // everyone is done with the staging buffer
       pos += cnt;
     }
     for (uint32_t j = pos + threadIdx.x; j < ((end - pos + 31) / 32) * 32 + pos; j += blockDim.x) {  // tail (<4 entries)
       bool v = j < end;
-      kahn_relax_consumer(v, v ? col[j] : 0u, indeg, queue, ctrl + KC_TAIL);
+      relax(v, v ? col[j] : 0u, L);
     }
+    __syncthreads();
   }
-  __syncthreads();
-  if (threadIdx.x == 0) *s_bign = 0;
-  __syncthreads();
 }
 
-__global__ void __launch_bounds__(kKahnBlock) k_kahn_frontier(uint32_t G, const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col,
-                                                              uint32_t* __restrict__ indeg, uint32_t* __restrict__ queue,
-                                                              uint32_t* __restrict__ level_off, uint32_t level_cap, uint32_t* ctrl) {
-  __shared__ uint32_t s_big[128];
-  __shared__ uint32_t s_bign;
-  __shared__ __align__(16) uint32_t s_stage[kBulkChunk];
-  __shared__ __align__(8) unsigned long long s_mbar;
-  __shared__ uint32_t s_lo, s_hi;
-  const uint32_t nblocks = gridDim.x;
-  uint32_t gen = 0, mbar_phase = 0;
-  if (threadIdx.x == 0) {
-    s_bign = 0;
-    uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_mbar);
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+// Counting sort by level.  A 4096-gate tile of the (chain-major) gate vector spans few distinct levels, so both passes count in
+// shared memory and touch the global per-level counters once per (tile, level) instead of once per gate; tiles spanning more
+// than kLvTile levels fall back to per-gate global atomics.  kScatter = false: histogram; true: reserve + place.
+constexpr int kLvItems = 16, kLvTile = kBlock * kLvItems;
+template <bool kScatter>
+__global__ void __launch_bounds__(kBlock) k_level_pass(const uint32_t* __restrict__ level_of, uint32_t G, uint32_t* __restrict__ counter,
+                                                       const uint32_t* __restrict__ level_off, uint32_t* __restrict__ level_order) {
+  __shared__ uint32_t s_bin[kLvTile];
+  __shared__ uint32_t s_min, s_max;
+  const uint32_t base = blockIdx.x * kLvTile;
+  uint32_t lv[kLvItems], rk[kLvItems];
+  uint32_t mn = 0xFFFFFFFFu, mx = 0;
+  if (threadIdx.x == 0) { s_min = 0xFFFFFFFFu; s_max = 0; }
+#pragma unroll
+  for (int i = 0; i < kLvItems; ++i) {
+    uint32_t g = base + i * kBlock + threadIdx.x;
+    lv[i] = g < G ? level_of[g] : 0xFFFFFFFFu;
+    if (g < G) { mn = min(mn, lv[i]); mx = max(mx, lv[i]); }
   }
   __syncthreads();
-  // level 0: gates without dependencies, in ascending index order per warp chunk
-  {
-    uint32_t stride = nblocks * kKahnBlock;
-    uint32_t iters = (G + stride - 1) / stride;
-    for (uint32_t it = 0; it < iters; ++it) {
-      uint32_t g = it * stride + blockIdx.x * kKahnBlock + threadIdx.x;
-      bool ready = g < G && indeg[g] == 0;
-      warp_append(ready, g, queue, ctrl + KC_TAIL);
-    }
-  }
-  // the last arriver publishes [0, tail) as level 0  (ctrl starts as lo=hi=0, level=-1 -> advance gives level 0)
-  kahn_grid_barrier<true>(ctrl, gen, nblocks, level_off, level_cap, true);
-  while (true) {
-    uint32_t lo = ld_acquire_u32(ctrl + KC_LO), hi = ld_acquire_u32(ctrl + KC_HI);
-    if (lo == hi) break;
-    bool small = hi - lo <= kSmallFrontier;
-    if (!small) {
-      kahn_process(lo, hi, blockIdx.x * kKahnBlock + threadIdx.x, nblocks * kKahnBlock, row_off, col, indeg, queue, ctrl, s_big, &s_bign, s_stage,
-                   &s_mbar, mbar_phase);
-    } else if (blockIdx.x == 0) {
-      // small-frontier mode: this CTA alone runs consecutive levels; no grid barrier in between
-      while (true) {
-        kahn_process(lo, hi, threadIdx.x, kKahnBlock, row_off, col, indeg, queue, ctrl, s_big, &s_bign, s_stage, &s_mbar, mbar_phase);
-        if (threadIdx.x == 0) {
-          __threadfence();
-          kahn_advance(ctrl, level_off, level_cap);
-          s_lo = ctrl[KC_LO];
-          s_hi = ctrl[KC_HI];
-        }
-        __syncthreads();
-        lo = s_lo;
-        hi = s_hi;
-        __syncthreads();
-        if (lo == hi || hi - lo > kSmallFrontier) break;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { mn = min(mn, __shfl_xor_sync(0xFFFFFFFFu, mn, o)); mx = max(mx, __shfl_xor_sync(0xFFFFFFFFu, mx, o)); }
+  if ((threadIdx.x & 31) == 0 && mn != 0xFFFFFFFFu) { atomicMin(&s_min, mn); atomicMax(&s_max, mx); }
+  __syncthreads();
+  const uint32_t lo = s_min, range = s_max - lo + 1;
+  if (range <= (uint32_t)kLvTile) {
+    for (uint32_t b = threadIdx.x; b < range; b += kBlock) s_bin[b] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kLvItems; ++i)
+      if (lv[i] != 0xFFFFFFFFu) rk[i] = atomicAdd(&s_bin[lv[i] - lo], 1u);
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < range; b += kBlock) {
+      uint32_t c = s_bin[b];
+      if (c) {
+        uint32_t at = atomicAdd(counter + lo + b, c);
+        if (kScatter) s_bin[b] = level_off[lo + b] + at;  // where this tile's members of the level go
       }
     }
-    kahn_grid_barrier<true>(ctrl, gen, nblocks, level_off, level_cap, !small);
+    if (kScatter) {
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < kLvItems; ++i)
+        if (lv[i] != 0xFFFFFFFFu) level_order[s_bin[lv[i] - lo] + rk[i]] = base + i * kBlock + threadIdx.x;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kLvItems; ++i)
+      if (lv[i] != 0xFFFFFFFFu) {
+        uint32_t at = atomicAdd(counter + lv[i], 1u);
+        if (kScatter) level_order[level_off[lv[i]] + at] = base + i * kBlock + threadIdx.x;
+      }
   }
 }
 
-// after the frontier ran dry: gates that were never released sit on or behind a cycle
-__global__ void __launch_bounds__(kBlock) k_kahn_leftover(const uint32_t* __restrict__ indeg, uint32_t G, uint32_t* ctrl) {
+// after the walk ran dry: gates that were never released sit on or behind a cycle
+__global__ void __launch_bounds__(kBlock) k_kahn_leftover(const uint32_t* __restrict__ level_of, uint32_t G, uint32_t* ctrl) {
   uint32_t m = kNone;
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock)
-    if (indeg[g] != 0) { m = g; break; }
+    if (level_of[g] == kNone) { m = g; break; }
   if (m != kNone) atomicMin(ctrl + KC_ERRMIN, m);
 }
 
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(kBlock) k_live_level(const uint4* __restrict__
     uint32_t g = level_order[i];
     uint4 gt = gates[g];
     bool l = out_mark[gt.w] && prod1[gt.w] == g + 1;
-    for (uint32_t j = row_off[g]; !l && j < row_off[g + 1]; ++j) l = live[col[j]] != 0;
+    for (uint32_t j = row_off[g]; !l && j < row_off[g + 1]; ++j) l = live[col[j] & ~kTwoSlots] != 0;
     live[g] = l;
   }
 }
@@ -352,28 +352,36 @@ __global__ void __launch_bounds__(kBlock) k_invert_u8(const uint8_t* __restrict_
 struct KahnBuffers {
   uint32_t* prod1;
   uint2* dep;
-  uint32_t* indeg;
-  uint32_t* row_off;  // G+1
-  uint32_t* cursor;
-  uint32_t* col;      // 2G
+  uint32_t* row_off;   // G+1
+  uint32_t* cursor;    // G: CSR fill cursors, later the per-level scatter cursors
+  uint32_t* col;       // 2G (+ flag bit)
+  uint32_t* lv;        // G: arrival word of two-slot consumers
+  uint32_t* level_of;  // G
+  uint2* q[2];         // overflow queues {gate, level}
+  uint2* longq[2];     // long-row queues {gate, level}
   unsigned long long* tile_state;
   uint32_t* scalars;
   uint32_t* ctrl;
 };
 
+static inline size_t kahn_long_cap(uint64_t G) { return (size_t)(G / (kLongRow / 2)) + 64; }  // <= 2G consumer entries in total
+
 static size_t kahn_scratch_bytes(uint64_t G, uint32_t node_bound) {
-  return align256(4 * (size_t)node_bound) + align256(8 * G) + align256(4 * G) + align256(4 * (G + 1)) + align256(4 * G) + align256(8 * G + 4) +
-         align256(8 * (size_t)(scan_tiles(G, kScanItems) + 1)) + align256(4 * S_COUNT) + align256(4 * KC_COUNT);
+  return align256(4 * (size_t)node_bound) + align256(8 * G) + align256(4 * (G + 1)) + 3 * align256(4 * G) + align256(8 * G + 4) + 2 * align256(8 * G) +
+         2 * align256(8 * kahn_long_cap(G)) + align256(8 * (size_t)(scan_tiles(G + 1, kScanItems) + 1)) + align256(4 * S_COUNT) + align256(4 * KC_COUNT);
 }
 
 static bool kahn_carve(c2a_handle* h, uint64_t G, uint32_t node_bound, KahnBuffers* b) {
   b->prod1 = (uint32_t*)slab_alloc(h, 4 * (size_t)node_bound);
   b->dep = (uint2*)slab_alloc(h, 8 * G);
-  b->indeg = (uint32_t*)slab_alloc(h, 4 * G);
   b->row_off = (uint32_t*)slab_alloc(h, 4 * (G + 1));
   b->cursor = (uint32_t*)slab_alloc(h, 4 * G);
   b->col = (uint32_t*)slab_alloc(h, 8 * G + 4);
-  b->tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(G, kScanItems) + 1));
+  b->lv = (uint32_t*)slab_alloc(h, 4 * G);
+  b->level_of = (uint32_t*)slab_alloc(h, 4 * G);
+  for (int i = 0; i < 2; ++i) b->q[i] = (uint2*)slab_alloc(h, 8 * G);
+  for (int i = 0; i < 2; ++i) b->longq[i] = (uint2*)slab_alloc(h, 8 * kahn_long_cap(G));
+  b->tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(G + 1, kScanItems) + 1));
   b->scalars = (uint32_t*)slab_alloc(h, 4 * S_COUNT);
   b->ctrl = (uint32_t*)slab_alloc(h, 4 * KC_COUNT);
   return b->ctrl != nullptr;
@@ -386,7 +394,6 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
   uint32_t* hp = h->h_pinned;
   for (int i = 0; i < S_COUNT; ++i) hp[i] = 0;
   for (int i = 0; i < KC_COUNT; ++i) hp[S_COUNT + i] = 0;
-  hp[S_COUNT + KC_LEVEL] = 0xFFFFFFFFu;  // first advance -> level 0
   hp[S_COUNT + KC_ERRMIN] = kNone;
   cudaMemcpyAsync(b.scalars, hp, 4 * S_COUNT, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(b.ctrl, hp + S_COUNT, 4 * KC_COUNT, cudaMemcpyHostToDevice, st);
@@ -394,7 +401,10 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
   cudaMemsetAsync(b.prod1, 0, 4 * (size_t)node_bound, st);
   cudaMemsetAsync(b.row_off, 0, 4 * ((size_t)G + 1), st);
   cudaMemsetAsync(b.cursor, 0, 4 * (size_t)G, st);
+  cudaMemsetAsync(b.lv, 0, 4 * (size_t)G, st);
+  cudaMemsetAsync(b.level_of, 0xFF, 4 * (size_t)G, st);
   phase_end(h);
+  uint32_t* hc = hp + S_COUNT;  // host copy of ctrl
   if (G) {
     phase_begin(h, "k_producer");
     LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.scalars);
@@ -403,7 +413,7 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, b.scalars);
     phase_end(h);
     phase_begin(h, "k_kahn_count");
-    LAUNCH(h, k_kahn_count, grid_for(h, (const void*)k_kahn_count, kBlock, G), kBlock, b.dep, G, b.indeg, b.row_off);
+    LAUNCH(h, k_kahn_count, grid_for(h, (const void*)k_kahn_count, kBlock, G), kBlock, b.dep, G, b.row_off);
     phase_end(h);
     uint32_t tiles = scan_tiles(G, kScanItems);
     cudaMemsetAsync(b.tile_state, 0, 8 * (size_t)tiles, st);
@@ -413,35 +423,64 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     phase_begin(h, "k_kahn_fill");
     LAUNCH(h, k_kahn_fill, grid_for(h, (const void*)k_kahn_fill, kBlock, G), kBlock, b.dep, G, b.row_off, b.cursor, b.col);
     phase_end(h);
-    // persistent cooperative launch: every CTA must be resident for the grid barrier
-    int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_kahn_frontier, kKahnBlock, 0) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
-    int grid = h->num_sms * std::min(occ, 2);
-    const uint32_t* row_off = b.row_off;
-    const uint32_t* col = b.col;
-    uint32_t* indeg = b.indeg;
-    uint32_t* ctrl = b.ctrl;
-    uint32_t Gv = G;
-    void* args[] = {&Gv, &row_off, &col, &indeg, &d_level_order, &d_level_off, &level_cap, &ctrl};
-    phase_begin(h, "k_kahn_frontier");
-    if (!cuda_ok(h, cudaLaunchCooperativeKernel((const void*)k_kahn_frontier, dim3(grid), dim3(kKahnBlock), args, 0, st), "kahn cooperative launch")) return C2A_ERR_CUDA;
-    h->launches++;
+    // ---- K4: walk from the roots; overflow / long rows are handed to follow-up launches until nothing is queued
+    phase_begin(h, "k_kahn_walk");
+    LAUNCH(h, k_kahn_walk_roots, grid_for(h, (const void*)k_kahn_walk_roots, kBlock, G), kBlock, b.dep, G, b.row_off, b.col, b.lv, b.level_of, b.q[0], b.longq[0], b.ctrl);
     phase_end(h);
-    LAUNCH(h, k_kahn_leftover, grid_for(h, (const void*)k_kahn_leftover, kBlock, G), kBlock, b.indeg, G, b.ctrl);
+    int cur = 0;
+    for (int round = 0;; ++round) {
+      cudaMemcpyAsync(hc, b.ctrl, 4 * KC_COUNT, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(hp, b.scalars, 4 * S_COUNT, cudaMemcpyDeviceToHost, st);
+      if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn sync")) return C2A_ERR_CUDA;
+      if (!cuda_ok(h, cudaGetLastError(), "kahn kernels")) return C2A_ERR_CUDA;
+      if (hp[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", node_bound);
+      const uint32_t nq = hc[KC_QN0 + cur], nlong = hc[KC_LONGN0 + cur];
+      if (!nq && !nlong) break;
+      if (round > (int)G + 8) return fail(h, C2A_ERR_CUDA, "Kahn walk did not converge");
+      const int nxt = cur ^ 1;
+      cudaMemsetAsync(b.ctrl + KC_QN0 + nxt, 0, 4, st);
+      cudaMemsetAsync(b.ctrl + KC_LONGN0 + nxt, 0, 4, st);
+      if (nlong) {
+        phase_begin(h, "k_kahn_long");
+        LAUNCH(h, k_kahn_long, std::min<uint32_t>(nlong, (uint32_t)h->num_sms * 2), kKahnBlock, b.longq[cur], b.ctrl + KC_LONGN0 + cur, b.row_off, b.col, b.lv, b.q[nxt],
+               b.ctrl + KC_QN0 + nxt);
+        phase_end(h);
+      }
+      if (nq) {
+        phase_begin(h, "k_kahn_walk");
+        LAUNCH(h, k_kahn_walk_queue, grid_for(h, (const void*)k_kahn_walk_queue, kBlock, nq), kBlock, b.q[cur], b.ctrl + KC_QN0 + cur, b.row_off, b.col, b.lv, b.level_of,
+               b.q[nxt], b.ctrl + KC_QN0 + nxt, b.longq[nxt], b.ctrl + KC_LONGN0 + nxt, b.ctrl);
+        phase_end(h);
+      }
+      cur = nxt;
+    }
+    if (hc[KC_DONE] != G) {  // gates that were never released sit on or behind a cycle
+      LAUNCH(h, k_kahn_leftover, grid_for(h, (const void*)k_kahn_leftover, kBlock, G), kBlock, b.level_of, G, b.ctrl);
+      cudaMemcpyAsync(hc, b.ctrl, 4 * KC_COUNT, cudaMemcpyDeviceToHost, st);
+      if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn leftover")) return C2A_ERR_CUDA;
+      if (err_index) *err_index = hc[KC_ERRMIN];
+      return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "%u of %u gates are on or behind a dependency cycle (smallest index %u)", G - hc[KC_DONE], G, hc[KC_ERRMIN]);
+    }
+  } else {
+    if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn sync")) return C2A_ERR_CUDA;
   }
-  cudaMemcpyAsync(hp + S_COUNT, b.ctrl, 4 * KC_COUNT, cudaMemcpyDeviceToHost, st);
-  cudaMemcpyAsync(hp, b.scalars, 4 * S_COUNT, cudaMemcpyDeviceToHost, st);
-  if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn sync")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaGetLastError(), "kahn kernels")) return C2A_ERR_CUDA;
-  if (hp[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", node_bound);
-  uint32_t tail = hp[S_COUNT + KC_TAIL];
-  if (tail != G) {
-    if (err_index) *err_index = hp[S_COUNT + KC_ERRMIN];
-    return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "%u of %u gates are on or behind a dependency cycle (smallest index %u)", G - tail, G, hp[S_COUNT + KC_ERRMIN]);
+  const uint32_t levels = G ? hc[KC_MAXLV] + 1 : 0;
+  if (levels > level_cap) return fail(h, C2A_ERR_INVALID_ARGUMENT, "more levels than level_cap (%u)", level_cap);
+  // ---- counting sort by level -> level-major order; level_off = exclusive scan of the level sizes (level_off[levels] = G)
+  cudaMemsetAsync(d_level_off, 0, 4 * ((size_t)levels + 1), st);
+  if (G) {
+    phase_begin(h, "k_level_sort");
+    cudaMemsetAsync(b.cursor, 0, 4 * (size_t)levels, st);
+    const uint32_t lvtiles = (G + kLvTile - 1) / kLvTile;
+    LAUNCH(h, k_level_pass<false>, lvtiles, kBlock, b.level_of, G, d_level_off, (const uint32_t*)nullptr, (uint32_t*)nullptr);
+    uint32_t ltiles = scan_tiles(levels, kScanItems);
+    cudaMemsetAsync(b.tile_state, 0, 8 * (size_t)ltiles, st);
+    LAUNCH(h, k_scan_u32_t<false>, ltiles, kBlock, d_level_off, d_level_off, levels, b.tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
+    LAUNCH(h, k_level_pass<true>, lvtiles, kBlock, b.level_of, G, b.cursor, d_level_off, d_level_order);
+    phase_end(h);
   }
-  if (hp[S_COUNT + KC_OVERFLOW]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "more levels than level_cap (%u)", level_cap);
-  // the final advance recorded an empty level: levels = KC_LEVEL (0-based index of that empty level)
-  uint32_t levels = G ? hp[S_COUNT + KC_LEVEL] : 0;
+  if (!cuda_ok(h, cudaStreamSynchronize(st), "kahn level sort")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaGetLastError(), "kahn level sort kernels")) return C2A_ERR_CUDA;
   if (n_levels) *n_levels = levels;
   return C2A_OK;
 }

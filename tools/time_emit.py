@@ -16,12 +16,13 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--chains", type=int, default=18315)
     ap.add_argument("--variant", default="late")
+    ap.add_argument("--rounds", type=int, default=91)
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--levels", action="store_true", help="also time the Kahn level kernel")
     ap.add_argument("--stream", default="packed", choices=["packed", "aos"])
     a = ap.parse_args()
     import torch
-    wl = c2a.workloads.mimc_chains(a.chains, variant=a.variant)
+    wl = c2a.workloads.mimc_chains(a.chains, rounds=a.rounds, variant=a.variant)
     ev = torch.from_numpy(np.ascontiguousarray(wl.events).view(np.int32)).pin_memory()
     ins = np.array(sorted(wl.inputs), dtype=np.uint32)
     outs = np.array(sorted(wl.outputs), dtype=np.uint32)
