@@ -5,8 +5,10 @@
 // of its lh and rh nodes.  Kahn yields a valid topological order and the levels (longest-path depth), NOT the reference's
 // DFS post-order (that is K5, c2a_device.cu); it is used for cycle screening, the sweeps and the evaluator.
 //
-//   K3  k_kahn_count / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G]  (multiplicity kept; bit 31 of a col
-//       entry says "this consumer has two dependency slots", i.e. it is released by its SECOND arrival)
+//   K3  k_kahn_count / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G].  A col entry is 16 bytes:
+//       {consumer | two-producer flag << 31, the consumer's own row begin, its row length, 0} - the walker that releases the
+//       consumer already holds its row, so a hop costs one dependent load (plus one atomic for a two-producer consumer).
+//       A gate that reads the same producer on both operands is listed once and counts as a one-producer consumer.
 //   K4  asynchronous Kahn, no level barrier (round 1 measured the level-synchronous cooperative kernel at 8.5 us per level -
 //       one grid barrier + a six-deep dependent load/atomic chain - which is 4.7 ms on the 547-level, 10 M-gate MiMC stream):
 //         k_kahn_walk     every gate without dependencies is a root; the thread that releases a consumer keeps walking it
@@ -24,7 +26,6 @@ namespace c2a {
 
 constexpr int kKahnBlock = 512;
 constexpr uint32_t kLongRow = 512;        // consumers; rows at least this long are walked by a whole CTA
-constexpr uint32_t kBulkChunk = 4096;     // u32 entries staged per bulk copy (16 KB)
 constexpr int kWalkStack = 16;            // released-but-not-yet-walked consumers a thread keeps for itself
 constexpr uint32_t kTwoSlots = 0x80000000u;
 enum { KC_QN0 = 0, KC_QN1 = 1, KC_LONGN0 = 2, KC_LONGN1 = 3, KC_DONE = 4, KC_MAXLV = 5, KC_ERRMIN = 6, KC_COUNT = 16 };
@@ -33,15 +34,18 @@ __global__ void __launch_bounds__(kBlock) k_kahn_count(const uint2* __restrict__
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint2 d = dep[g];
     if (d.x != kNone) atomicAdd(cnt + d.x, 1u);
-    if (d.y != kNone) atomicAdd(cnt + d.y, 1u);  // lh == rh: the same consumer twice, it arrives twice
+    if (d.y != kNone && d.y != d.x) atomicAdd(cnt + d.y, 1u);  // lh == rh: one producer, listed once
   }
 }
 
 __global__ void __launch_bounds__(kBlock) k_kahn_fill(const uint2* __restrict__ dep, uint32_t G, const uint32_t* __restrict__ row_off,
-                                                      uint32_t* __restrict__ cursor, uint32_t* __restrict__ col) {
+                                                      uint32_t* __restrict__ cursor, uint4* __restrict__ col) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint2 d = dep[g];
-    const uint32_t e = g | ((d.x != kNone && d.y != kNone) ? kTwoSlots : 0u);
+    if (d.y == d.x) d.y = kNone;
+    if (d.x == kNone && d.y == kNone) continue;
+    const uint32_t beg = row_off[g], len = row_off[g + 1] - beg;
+    const uint4 e = make_uint4(g | ((d.x != kNone && d.y != kNone) ? kTwoSlots : 0u), beg, len, 0u);
     if (d.x != kNone) col[row_off[d.x] + atomicAdd(cursor + d.x, 1u)] = e;
     if (d.y != kNone) col[row_off[d.y] + atomicAdd(cursor + d.y, 1u)] = e;
   }
@@ -67,39 +71,37 @@ __device__ __forceinline__ bool kahn_arrive(uint32_t e, uint32_t L, uint32_t* __
   return old != 0;
 }
 
-// Walk from (g, L): record the level, release consumers, continue with one of them.  queue entries are {gate, level}.
-__device__ __forceinline__ void kahn_walk(uint32_t g, uint32_t L, const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col,
-                                          uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of, uint2* __restrict__ q_out,
-                                          uint32_t* __restrict__ q_out_n, uint2* __restrict__ long_out, uint32_t* __restrict__ long_out_n,
+// Walk from gate g (level L, consumer row [beg, beg+len)): record the level, release consumers, continue with one of them.
+// queue entries are {gate, level, row begin, row length}.
+__device__ __forceinline__ void kahn_walk(uint32_t g, uint32_t L, uint32_t beg, uint32_t len, const uint4* __restrict__ col,
+                                          uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of, uint4* __restrict__ q_out,
+                                          uint32_t* __restrict__ q_out_n, uint4* __restrict__ long_out, uint32_t* __restrict__ long_out_n,
                                           uint32_t& done, uint32_t& maxl) {
-  uint32_t sg[kWalkStack], sl[kWalkStack];
+  uint4 stack[kWalkStack];
   int sp = 0;
   while (true) {
     level_of[g] = L;
     ++done;
     maxl = max(maxl, L);
-    const uint32_t beg = row_off[g], end = row_off[g + 1];
-    uint32_t ng = kNone, nl = 0;
-    if (end - beg >= kLongRow) {
-      long_out[atomicAdd(long_out_n, 1u)] = make_uint2(g, L);  // a whole CTA takes this row (k_kahn_long)
+    uint4 nxt = make_uint4(kNone, 0, 0, 0);
+    if (len >= kLongRow) {
+      long_out[atomicAdd(long_out_n, 1u)] = make_uint4(g, L, beg, len);  // a whole CTA takes this row (k_kahn_long)
     } else {
-      for (uint32_t j = beg; j < end; ++j) {
-        uint32_t e = col[j], lc;
-        if (!kahn_arrive(e, L, lv, &lc)) continue;
-        uint32_t c = e & ~kTwoSlots;
-        if (ng == kNone) { ng = c; nl = lc; }
-        else if (sp < kWalkStack) { sg[sp] = c; sl[sp] = lc; ++sp; }
-        else q_out[atomicAdd(q_out_n, 1u)] = make_uint2(c, lc);
+      for (uint32_t j = 0; j < len; ++j) {
+        uint4 e = __ldg(col + beg + j);
+        uint32_t lc;
+        if (!kahn_arrive(e.x, L, lv, &lc)) continue;
+        uint4 item = make_uint4(e.x & ~kTwoSlots, lc, e.y, e.z);
+        if (nxt.x == kNone) nxt = item;
+        else if (sp < kWalkStack) stack[sp++] = item;
+        else q_out[atomicAdd(q_out_n, 1u)] = item;
       }
     }
-    if (ng == kNone) {
+    if (nxt.x == kNone) {
       if (sp == 0) break;
-      --sp;
-      ng = sg[sp];
-      nl = sl[sp];
+      nxt = stack[--sp];
     }
-    g = ng;
-    L = nl;
+    g = nxt.x; L = nxt.y; beg = nxt.z; len = nxt.w;
   }
 }
 
@@ -111,27 +113,29 @@ __device__ __forceinline__ void kahn_commit(uint32_t done, uint32_t maxl, uint32
 
 // roots: gates without dependencies (level 0)
 __global__ void __launch_bounds__(kBlock) k_kahn_walk_roots(const uint2* __restrict__ dep, uint32_t G, const uint32_t* __restrict__ row_off,
-                                                            const uint32_t* __restrict__ col, uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of,
-                                                            uint2* __restrict__ q_out, uint2* __restrict__ long_out, uint32_t* ctrl) {
+                                                            const uint4* __restrict__ col, uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of,
+                                                            uint4* __restrict__ q_out, uint4* __restrict__ long_out, uint32_t* ctrl) {
   uint32_t done = 0, maxl = 0;
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint2 d = dep[g];
-    if (d.x == kNone && d.y == kNone) kahn_walk(g, 0, row_off, col, lv, level_of, q_out, ctrl + KC_QN0, long_out, ctrl + KC_LONGN0, done, maxl);
+    if (d.x == kNone && d.y == kNone) {
+      uint32_t beg = row_off[g];
+      kahn_walk(g, 0, beg, row_off[g + 1] - beg, col, lv, level_of, q_out, ctrl + KC_QN0, long_out, ctrl + KC_LONGN0, done, maxl);
+    }
   }
   kahn_commit(done, maxl, ctrl);
 }
 
 // overflow queue of the previous launch: released consumers nobody has walked yet
-__global__ void __launch_bounds__(kBlock) k_kahn_walk_queue(const uint2* __restrict__ q_in, const uint32_t* __restrict__ q_in_n,
-                                                            const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col,
-                                                            uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of, uint2* __restrict__ q_out,
-                                                            uint32_t* __restrict__ q_out_n, uint2* __restrict__ long_out, uint32_t* __restrict__ long_out_n,
-                                                            uint32_t* ctrl) {
+__global__ void __launch_bounds__(kBlock) k_kahn_walk_queue(const uint4* __restrict__ q_in, const uint32_t* __restrict__ q_in_n,
+                                                            const uint4* __restrict__ col, uint32_t* __restrict__ lv, uint32_t* __restrict__ level_of,
+                                                            uint4* __restrict__ q_out, uint32_t* __restrict__ q_out_n, uint4* __restrict__ long_out,
+                                                            uint32_t* __restrict__ long_out_n, uint32_t* ctrl) {
   uint32_t done = 0, maxl = 0;
   const uint32_t n = *q_in_n;
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    uint2 it = q_in[i];
-    kahn_walk(it.x, it.y, row_off, col, lv, level_of, q_out, q_out_n, long_out, long_out_n, done, maxl);
+    uint4 it = q_in[i];
+    kahn_walk(it.x, it.y, it.z, it.w, col, lv, level_of, q_out, q_out_n, long_out, long_out_n, done, maxl);
   }
   kahn_commit(done, maxl, ctrl);
 }
@@ -153,12 +157,14 @@ __device__ __forceinline__ void bulk_load_row(uint32_t* smem_dst, const uint32_t
   }
 }
 
-// long rows: one CTA per row; the gate itself was already recorded by the walker that found it.  Released consumers are
-// queued (they are walked by the next k_kahn_walk_queue launch).
-__global__ void __launch_bounds__(kKahnBlock) k_kahn_long(const uint2* __restrict__ long_in, const uint32_t* __restrict__ long_in_n,
-                                                          const uint32_t* __restrict__ row_off, const uint32_t* __restrict__ col, uint32_t* __restrict__ lv,
-                                                          uint2* __restrict__ q_out, uint32_t* __restrict__ q_out_n) {
-  __shared__ __align__(16) uint32_t s_stage[kBulkChunk];
+// long rows: one CTA per row; the gate itself was already recorded by the walker that found it.  The row (16-byte entries, so
+// every chunk is bulk-copy aligned) is staged through shared memory; released consumers are queued with their own row
+// (they are walked by the next k_kahn_walk_queue launch).
+constexpr uint32_t kBulkEntries = 1024;  // 16 KB per bulk copy
+__global__ void __launch_bounds__(kKahnBlock) k_kahn_long(const uint4* __restrict__ long_in, const uint32_t* __restrict__ long_in_n,
+                                                          const uint4* __restrict__ col, uint32_t* __restrict__ lv, uint4* __restrict__ q_out,
+                                                          uint32_t* __restrict__ q_out_n) {
+  __shared__ __align__(16) uint4 s_stage[kBulkEntries];
   __shared__ __align__(8) unsigned long long s_mbar;
   uint32_t mbar_phase = 0;
   if (threadIdx.x == 0) {
@@ -168,39 +174,22 @@ __global__ void __launch_bounds__(kKahnBlock) k_kahn_long(const uint2* __restric
   }
   __syncthreads();
   const uint32_t n = *long_in_n;
-  auto relax = [&](bool valid, uint32_t e, uint32_t L) {
-    uint32_t lc = 0;
-    bool ready = valid && kahn_arrive(e, L, lv, &lc);
-    warp_append(ready, make_uint2(e & ~kTwoSlots, lc), q_out, q_out_n);
-  };
   for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
-    const uint2 it = long_in[r];
+    const uint4 it = long_in[r];  // {gate, level, row begin, row length}
     const uint32_t L = it.y;
-    uint32_t pos = row_off[it.x];
-    const uint32_t end = row_off[it.x + 1];
-    // unaligned head straight from global (bulk copies need 16-byte aligned sources)
-    uint32_t head_end = min(end, (pos + 3u) & ~3u);
-    for (uint32_t j = pos + threadIdx.x; j < ((head_end - pos + 31) / 32) * 32 + pos; j += blockDim.x) {
-      bool v = j < head_end;
-      relax(v, v ? col[j] : 0u, L);
-    }
-    pos = head_end;
-    while (pos + 4 <= end) {
-      uint32_t cnt = min((end - pos) & ~3u, kBulkChunk);
-      bulk_load_row(s_stage, col + pos, cnt * 4, &s_mbar, mbar_phase);
+    for (uint32_t pos = 0; pos < it.w; pos += kBulkEntries) {
+      const uint32_t cnt = min(it.w - pos, kBulkEntries);
+      bulk_load_row(reinterpret_cast<uint32_t*>(s_stage), reinterpret_cast<const uint32_t*>(col + it.z + pos), cnt * 16, &s_mbar, mbar_phase);
       mbar_phase ^= 1;
       for (uint32_t j = threadIdx.x; j < ((cnt + 31) / 32) * 32; j += blockDim.x) {
         bool v = j < cnt;
-        relax(v, v ? s_stage[j] : 0u, L);
+        uint4 e = v ? s_stage[j] : make_uint4(0, 0, 0, 0);
+        uint32_t lc = 0;
+        bool ready = v && kahn_arrive(e.x, L, lv, &lc);
+        warp_append(ready, make_uint4(e.x & ~kTwoSlots, lc, e.y, e.z), q_out, q_out_n);
       }
       __syncthreads();  // everyone is done with the staging buffer
-      pos += cnt;
     }
-    for (uint32_t j = pos + threadIdx.x; j < ((end - pos + 31) / 32) * 32 + pos; j += blockDim.x) {  // tail (<4 entries)
-      bool v = j < end;
-      relax(v, v ? col[j] : 0u, L);
-    }
-    __syncthreads();
   }
 }
 
@@ -333,13 +322,13 @@ __global__ void __launch_bounds__(kBlock) k_mark_nodes(const uint32_t* __restric
 // reverse sweep: a gate is live when it produces an output node or feeds a live gate
 __global__ void __launch_bounds__(kBlock) k_live_level(const uint4* __restrict__ gates, const uint32_t* __restrict__ level_order, uint32_t lo,
                                                        uint32_t hi, const uint32_t* __restrict__ prod1, const uint32_t* __restrict__ row_off,
-                                                       const uint32_t* __restrict__ col, const uint8_t* __restrict__ out_mark,
+                                                       const uint4* __restrict__ col, const uint8_t* __restrict__ out_mark,
                                                        uint8_t* __restrict__ live) {
   for (uint32_t i = lo + blockIdx.x * kBlock + threadIdx.x; i < hi; i += gridDim.x * kBlock) {
     uint32_t g = level_order[i];
     uint4 gt = gates[g];
     bool l = out_mark[gt.w] && prod1[gt.w] == g + 1;
-    for (uint32_t j = row_off[g]; !l && j < row_off[g + 1]; ++j) l = live[col[j] & ~kTwoSlots] != 0;
+    for (uint32_t j = row_off[g]; !l && j < row_off[g + 1]; ++j) l = live[col[j].x & ~kTwoSlots] != 0;
     live[g] = l;
   }
 }
@@ -354,11 +343,11 @@ struct KahnBuffers {
   uint2* dep;
   uint32_t* row_off;   // G+1
   uint32_t* cursor;    // G: CSR fill cursors, later the per-level scatter cursors
-  uint32_t* col;       // 2G (+ flag bit)
+  uint4* col;          // 2G entries of 16 bytes
   uint32_t* lv;        // G: arrival word of two-slot consumers
   uint32_t* level_of;  // G
-  uint2* q[2];         // overflow queues {gate, level}
-  uint2* longq[2];     // long-row queues {gate, level}
+  uint4* q[2];         // overflow queues {gate, level, row begin, row length}
+  uint4* longq[2];     // long-row queues, same record
   unsigned long long* tile_state;
   uint32_t* scalars;
   uint32_t* ctrl;
@@ -367,8 +356,8 @@ struct KahnBuffers {
 static inline size_t kahn_long_cap(uint64_t G) { return (size_t)(G / (kLongRow / 2)) + 64; }  // <= 2G consumer entries in total
 
 static size_t kahn_scratch_bytes(uint64_t G, uint32_t node_bound) {
-  return align256(4 * (size_t)node_bound) + align256(8 * G) + align256(4 * (G + 1)) + 3 * align256(4 * G) + align256(8 * G + 4) + 2 * align256(8 * G) +
-         2 * align256(8 * kahn_long_cap(G)) + align256(8 * (size_t)(scan_tiles(G + 1, kScanItems) + 1)) + align256(4 * S_COUNT) + align256(4 * KC_COUNT);
+  return align256(4 * (size_t)node_bound) + align256(8 * G) + align256(4 * (G + 1)) + 3 * align256(4 * G) + align256(32 * G + 16) + 2 * align256(16 * G) +
+         2 * align256(16 * kahn_long_cap(G)) + align256(8 * (size_t)(scan_tiles(G + 1, kScanItems) + 1)) + align256(4 * S_COUNT) + align256(4 * KC_COUNT);
 }
 
 static bool kahn_carve(c2a_handle* h, uint64_t G, uint32_t node_bound, KahnBuffers* b) {
@@ -376,11 +365,11 @@ static bool kahn_carve(c2a_handle* h, uint64_t G, uint32_t node_bound, KahnBuffe
   b->dep = (uint2*)slab_alloc(h, 8 * G);
   b->row_off = (uint32_t*)slab_alloc(h, 4 * (G + 1));
   b->cursor = (uint32_t*)slab_alloc(h, 4 * G);
-  b->col = (uint32_t*)slab_alloc(h, 8 * G + 4);
+  b->col = (uint4*)slab_alloc(h, 32 * G + 16);
   b->lv = (uint32_t*)slab_alloc(h, 4 * G);
   b->level_of = (uint32_t*)slab_alloc(h, 4 * G);
-  for (int i = 0; i < 2; ++i) b->q[i] = (uint2*)slab_alloc(h, 8 * G);
-  for (int i = 0; i < 2; ++i) b->longq[i] = (uint2*)slab_alloc(h, 8 * kahn_long_cap(G));
+  for (int i = 0; i < 2; ++i) b->q[i] = (uint4*)slab_alloc(h, 16 * G);
+  for (int i = 0; i < 2; ++i) b->longq[i] = (uint4*)slab_alloc(h, 16 * kahn_long_cap(G));
   b->tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(G + 1, kScanItems) + 1));
   b->scalars = (uint32_t*)slab_alloc(h, 4 * S_COUNT);
   b->ctrl = (uint32_t*)slab_alloc(h, 4 * KC_COUNT);
@@ -442,13 +431,13 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
       cudaMemsetAsync(b.ctrl + KC_LONGN0 + nxt, 0, 4, st);
       if (nlong) {
         phase_begin(h, "k_kahn_long");
-        LAUNCH(h, k_kahn_long, std::min<uint32_t>(nlong, (uint32_t)h->num_sms * 2), kKahnBlock, b.longq[cur], b.ctrl + KC_LONGN0 + cur, b.row_off, b.col, b.lv, b.q[nxt],
+        LAUNCH(h, k_kahn_long, std::min<uint32_t>(nlong, (uint32_t)h->num_sms * 2), kKahnBlock, b.longq[cur], b.ctrl + KC_LONGN0 + cur, b.col, b.lv, b.q[nxt],
                b.ctrl + KC_QN0 + nxt);
         phase_end(h);
       }
       if (nq) {
         phase_begin(h, "k_kahn_walk");
-        LAUNCH(h, k_kahn_walk_queue, grid_for(h, (const void*)k_kahn_walk_queue, kBlock, nq), kBlock, b.q[cur], b.ctrl + KC_QN0 + cur, b.row_off, b.col, b.lv, b.level_of,
+        LAUNCH(h, k_kahn_walk_queue, grid_for(h, (const void*)k_kahn_walk_queue, kBlock, nq), kBlock, b.q[cur], b.ctrl + KC_QN0 + cur, b.col, b.lv, b.level_of,
                b.q[nxt], b.ctrl + KC_QN0 + nxt, b.longq[nxt], b.ctrl + KC_LONGN0 + nxt, b.ctrl);
         phase_end(h);
       }
