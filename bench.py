@@ -39,16 +39,18 @@ def alg_bytes(kernel, c):
         # ---- device emitter (c2a_emit.cuh)
         # count pass, then scatter to sig_t + sig_meta | egates + gate_t | conn + conn_t + conn_sb
         "emit:k_ev_count": c["stream_bytes_count"] + 8 * ((n + 1023) // 1024),   # AoS: 16 B/event; packed: the kind bytes only
-        "emit:k_ev_scatter": c["stream_bytes"] + 16 * ((n + 1023) // 1024) + ns * (4 + 8) + G * (16 + 4) + C * (8 + 4 + 4),
-        "emit:k_ev_check_gates": G * (16 + 4 + 12 + 1),
-        "emit:k_ev_check_conns": C * (8 + 4 + 8),
+        # dense packed stream: validated in place (no event-time arrays, no declaration table, no E2 kernels)
+        "emit:k_ev_scatter": c["stream_bytes"] + 16 * ((n + 1023) // 1024) + (ns * 8 + G * (16 + 1) + C * (8 + 4) if c["dense"] else
+                                                                             ns * (4 + 8) + G * (16 + 4) + C * (8 + 4 + 4)),
+        "emit:k_ev_check_gates": 0 if c["dense"] else G * (16 + 4 + 12 + 1),
+        "emit:k_ev_check_conns": 0 if c["dense"] else C * (8 + 4 + 8),
         "emit:k_msf_pick": C * (8 + 8 + 16 + 16),                 # conn, 2 parent, 2 RED.MIN best, cand (first round; later rounds are on the shrunken list)
         "emit:k_msf_hook": C * (16 + 8 + 4 + 4),                  # cand, 2 best, parent, eff
         "emit:k_scan_u32": 8 * C,
         "emit:k_ev_nid_edges": C * 8 + Ceff * (4 + 8 + 4 + 8),
-        "emit:k_ev_finalize": S * (4 + 8 + 1 + 4 + 8 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, {nid,cnt}, nos + screen atomics
+        "emit:k_ev_finalize": S * ((0 if c["dense"] else 4) + 8 + 1 + 4 + 8 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, {nid,cnt}, nos + screen atomics
         "emit:k_ev_gates": G * (16 + 12 + 16),
-        "emit:init": 4 * (n + (1 << 20)) + S * (1 + 4 + 4 + 8) + 4 * C,   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
+        "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 8) + 4 * C,   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
         # ---- build_circuit (c2a_device.cu)
         "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
         "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair
@@ -344,7 +346,7 @@ def main():
     n_mid = int(wc.value) - len(in_ids) - len(out_ids)
     counts = {"G": G, "NB": nb, "n": n_ev, "S": int(info.signal_bound), "C": int(info.n_connections), "Ceff": int(info.n_effective),
               "n_sig": int(info.n_signals), "n_const": n_const, "n_mid": n_mid, "identity": n_identity, "W": (3 * G + 31) // 32,
-              "stream_bytes": stream_bytes, "stream_bytes_count": stream_bytes_count}
+              "stream_bytes": stream_bytes, "stream_bytes_count": stream_bytes_count, "dense": bool(packed and (pk_flags & 1))}
 
     # ---- e2e: event stream in PINNED HOST memory -> emit -> build -> result in pinned host memory, all copies inside the timed region.
     #   e2e (headline)   the reference's result shape (BristolCircuit, src/compiler.rs:452-493): the renumbered gates plus the

@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
                                                        uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
-                                                       uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint32_t* __restrict__ es) {
+                                                       uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint8_t* __restrict__ outmark,
+                                                       uint32_t* __restrict__ es) {
   __shared__ __align__(16) uint32_t s_w[2][kPkWordsCap];
   __shared__ __align__(16) uint8_t s_k[2][kEvTile];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -338,18 +339,30 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
       const uint8_t* __restrict__ sk = &s_k[stage][0];
       auto W = [&](uint32_t wl) -> uint32_t { return kFast ? sw[wl] : word(wl); };
       auto K = [&](uint32_t k) -> uint32_t { return kFast ? (uint32_t)sk[k] : (k < kcov ? (uint32_t)sk[k] : (uint32_t)__ldg(kinds + tbase + k)); };
+      // Dense ids (id = declaration rank): "declared before use" (compiler.rs:183, :201 resolve an undeclared signal to node 0 /
+      // panic) is the local test id < #signals declared before this event, so the E2 kernels, the event-time arrays and the
+      // declaration table are not needed at all; out-of-range references are flagged and neutralised right here.
       for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
         uint32_t e = s_list[r], k = e & 1023u, my_dc = e >> 10;
-        uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : k - r - my_dc);
-        egates[g0 + r] = make_uint4(K(k) >> 2, W(wl), W(wl + 1), W(wl + 2));
-        gate_t[g0 + r] = (uint32_t)tbase + k;
+        uint32_t ds = k - r - my_dc;
+        uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : ds);
+        uint4 gt = make_uint4(K(k) >> 2, W(wl), W(wl + 1), W(wl + 2));
+        if (dense) {
+          const uint32_t before = s0 + ds;
+          if (gt.y < before && gt.z < before && gt.w < before) outmark[gt.w] = 1;  // compiler.rs:201 marks the out node is_out
+          else { f |= EF_UNKNOWN_REF; gt.y = gt.z = gt.w = 0; }
+        } else gate_t[g0 + r] = (uint32_t)tbase + k;
+        egates[g0 + r] = gt;
       }
       for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
         uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = e >> 10;
         uint32_t ds = k - my_dg - r;
         uint32_t wl = 3u * my_dg + 2u * r + (dense ? 0u : ds);
-        conn[c0 + r] = make_uint2(W(wl), W(wl + 1));
-        conn_t[c0 + r] = (uint32_t)tbase + k;
+        uint2 ab = make_uint2(W(wl), W(wl + 1));
+        if (dense) {
+          if (!(ab.x < s0 + ds && ab.y < s0 + ds)) { f |= EF_UNKNOWN_REF; ab = make_uint2(0, 0); }
+        } else conn_t[c0 + r] = (uint32_t)tbase + k;
+        conn[c0 + r] = ab;
         conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
       }
       const uint32_t ns = nev - min(nev, ng + nc);
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
           else {
             // plain stores: a duplicate declaration (compiler.rs:146-148) overwrites, and is caught later because the number of
             // declared ids then falls short of the number of signal events (k_ev_finalize counts them)
-            sig_t[sid] = (uint32_t)tbase + k;
+            if (!dense) sig_t[sid] = (uint32_t)tbase + k;
             sig_meta[sid] = make_uint2((s0 + r) | (e & 0x80000000u), c0 + my_dc);
           }
         }
@@ -560,7 +573,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
 #pragma unroll
     for (int i = 0; i < kFinIlp; ++i) {
       uint32_t s = min(s0 + i * stride, S - 1);
-      t[i] = sig_t[s];
+      t[i] = sig_t ? sig_t[s] : 0u;  // dense ids: no declaration table, every id below S is declared
       m[i] = sig_meta[s];
       om[i] = outmark[s];
       r0[i] = parent[s];
@@ -627,7 +640,6 @@ __global__ void __launch_bounds__(kBlock) k_sig_wires(const uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------------------------
 static inline size_t emit_scratch_bytes(uint64_t G, uint64_t C, uint64_t S) {  // slab part (exact sizes; the scatter targets live in the staging buffer)
   size_t b = 0;
-  b += align256(S);                                                         // outmark
   b += 2 * align256(4 * S) + align256(8 * S);                               // parent, best, nc
   b += 2 * align256(4 * (C + 1)) + align256(4 * C) + align256(16 * C);      // eff, effx, cur, cand
   b += align256(8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1)) + 256;     // tile_state + ticket
@@ -751,6 +763,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint32_t *es = nullptr, *sig_t = nullptr, *gate_t = nullptr, *conn_t = nullptr, *conn_sb = nullptr;
   uint2 *sig_meta = nullptr, *conn = nullptr;
   uint4* egates = nullptr;
+  uint8_t* outmark = nullptr;
   const uint4* d_ev = nullptr;
   uint64_t G = 0, C = 0, n_sig = 0;
   uint32_t S = 0, flags = 0;
@@ -759,7 +772,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     const size_t pk_kbytes = pk ? align256(n + 4) : 0;  // packed staging: kinds, then words
     const size_t ev_copy = pk ? (src.pk_on_device ? 0 : pk_kbytes + align256(4 * pk->n_words + 4)) : (ev_dev ? 0 : align256(16 * n));
     const size_t ev_need = ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
-                           align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n);
+                           align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
     if (ev_need > h->ev_bytes) {
       if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
       if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
@@ -780,6 +793,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     conn_t = (uint32_t*)take(4 * n);
     conn_sb = (uint32_t*)take(4 * n);
     conn = (uint2*)take(8 * n);
+    outmark = (uint8_t*)take(S_cap);
     d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
     const uint8_t* d_kinds = pk ? (src.pk_on_device ? pk->kinds : (const uint8_t*)h->ev_buf) : nullptr;
     const uint32_t* d_words = pk ? (src.pk_on_device ? pk->words : (const uint32_t*)(h->ev_buf + pk_kbytes)) : nullptr;
@@ -798,7 +812,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     phase_begin(h, "init");
     cudaMemsetAsync(cnt_state, 0, 16 * ((size_t)ctiles + 1), s);
     cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
-    cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
+    if (!pk_dense) cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
+    cudaMemsetAsync(outmark, 0, pk_dense ? std::min<uint64_t>(S_cap, n + 1) : S_cap, s);
     phase_end(h);
     if (tiles) {
       const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
@@ -813,7 +828,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
       if (pk) LAUNCH(h, k_pk_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta,
-                     egates, gate_t, conn, conn_t, conn_sb, es);
+                     egates, gate_t, conn, conn_t, conn_sb, outmark, es);
       else LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_scatter, kBlock, n)), kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
       cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
@@ -879,7 +894,6 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
   uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   const size_t keep = h->slab_used;
-  uint8_t* outmark = (uint8_t*)slab_alloc(h, S);
   uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint2* nc = (uint2*)slab_alloc(h, 8 * (size_t)S);
@@ -892,16 +906,16 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   if (!ticket) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
 
   phase_begin(h, "init");
-  cudaMemsetAsync(outmark, 0, S, s);
   cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
   cudaMemsetAsync(eff, 0, 4 * (C + 1), s);
   if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
   phase_end(h);
+  // E2 runs only when the ids are explicit; a dense stream was validated inside the scatter
   phase_begin(h, "k_ev_check_gates");
-  if (G) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
+  if (G && !pk_dense) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
   phase_end(h);
   phase_begin(h, "k_ev_check_conns");
-  if (C) LAUNCH(h, k_ev_check_conns, grid_for(h, (const void*)k_ev_check_conns, kBlock, C), kBlock, conn, conn_t, (uint32_t)C, S, sig_t, es);
+  if (C && !pk_dense) LAUNCH(h, k_ev_check_conns, grid_for(h, (const void*)k_ev_check_conns, kBlock, C), kBlock, conn, conn_t, (uint32_t)C, S, sig_t, es);
   phase_end(h);
 
   // ---- Boruvka rounds.  Round r: candidates counted in *ncand, surviving (undecided) edges in *ncur.
@@ -936,7 +950,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, effx, parent, nc);
     phase_end(h);
     phase_begin(h, "k_ev_finalize");
-    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, sig_t, sig_meta, outmark, effx, parent, nc, nos, es);
+    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, effx, parent, nc, nos, es);
     phase_end(h);
     phase_begin(h, "k_ev_gates");
     if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
