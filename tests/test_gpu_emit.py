@@ -226,6 +226,50 @@ def test_streams_the_device_declines_replay_exactly(ctx, orc, c2a, seed):
         assert f"event {ex.value.err_event}" == err.message
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_dense_packed_streams_with_forward_references(ctx, orc, c2a, seed):
+    """DENSE packed streams are validated inside the scatter (id < signals declared so far).  References to signals that are
+    declared LATER (node-0 semantics for operands, compiler.rs:183; panic for the out signal, :201) must still come out
+    exactly like the reference: the device declines and the host emitter replays the unpacked stream."""
+    rng = np.random.RandomState(4000 + seed)
+    n_sig_total = int(rng.randint(6, 60))
+    ev, declared = [], 0
+    while declared < n_sig_total:
+        x = rng.rand()
+        if x < 0.45 or declared < 3:
+            ev.append((EV_S, declared, 0, 0))
+            declared += 1
+        elif x < 0.8:
+            hi = declared + (3 if rng.rand() < 0.25 else 0)          # sometimes reach past what is declared
+            a, b = (int(rng.randint(0, min(hi, n_sig_total))) for _ in range(2))
+            ev.append((EV_S, declared, 0, 0))                           # fresh out signal
+            o = declared if rng.rand() < 0.9 else min(declared + 2, n_sig_total - 1)
+            declared += 1
+            ev.append((EV_G | (int(rng.randint(0, 20)) << 8), a, b, o))
+        else:
+            hi = declared + (2 if rng.rand() < 0.2 else 0)
+            a, b = (int(rng.randint(0, min(hi, n_sig_total))) for _ in range(2))
+            ev.append((EV_C, a, b, 0))
+    ev = np.asarray(ev, dtype=np.uint32)
+    kinds_b, words, flags = c2a.pack_events(ev)
+    assert flags == 1
+    oc = orc.OracleCompiler()
+    try:
+        oc.emit_events(ev)
+        err = None
+    except orc.OracleError as e:
+        err = e
+    if err is None:
+        info = ctx.emit_packed(kinds_b, words, flags)
+        gates, _ = ctx.emitted_fetch()
+        assert np.array_equal(gates, oc.gate_array()) and info["node_count"] == oc.node_count
+    else:
+        with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:
+            ctx.emit_packed(kinds_b, words, flags)
+        assert int(ex.value.status) == err.status
+        assert f"event {ex.value.err_event}" == err.message
+
+
 def test_merge_errors(ctx, c2a):
     S = lambda i: (EV_S, i, 0, 0)
     K = lambda i, v: (EV_SC, i, v, 0)
