@@ -30,7 +30,7 @@
 //   M  k_msf_pick / k_msf_hook   Boruvka: per class the minimum-time outgoing connection (tagged RED.MIN),
 //                      hook, path compression inside find; edge list shrinks every round.  kSpecMsf rounds are enqueued
 //                      unconditionally (an exhausted round exits at once); more only if the final status says so.
-//   N  k_scan_u32(eff), k_ev_nid_edges, k_ev_finalize, k_ev_gates
+//   N  k_scan_u32<popc>(effective-connection bitmap), k_ev_nid_edges, k_ev_finalize, k_ev_gates
 #pragma once
 
 struct c2a_compiler;
@@ -453,22 +453,18 @@ __device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
   if (*reinterpret_cast<volatile uint32_t*>(p) > v) atomicMin(p, v);  // values only decrease within a round: a stale read costs one RED
 }
 
-// First round: the live list is every connection, and almost every one is a candidate, so cand[] is written in place
-// (cand[e], kNone in .x for a connection that is already internal) instead of being compacted through one global counter.
-__global__ void __launch_bounds__(kBlock) k_msf_pick_first(const uint2* __restrict__ conn, uint32_t n, uint32_t* __restrict__ parent,
-                                                           uint32_t* __restrict__ best, uint32_t tag, uint4* __restrict__ cand,
+// First round: the live list is every connection and the classes are the signals themselves, so a candidate record would
+// only repeat conn[e]: nothing is materialised, k_msf_hook_first reads conn[] again.
+__global__ void __launch_bounds__(kBlock) k_msf_pick_first(const uint2* __restrict__ conn, uint32_t n, uint32_t* __restrict__ best, uint32_t tag,
                                                            uint32_t* __restrict__ n_cand) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *n_cand = n;  // every slot of cand[] is written; dead ones carry kNone
+  if (blockIdx.x == 0 && threadIdx.x == 0) *n_cand = n;
   for (uint32_t e = blockIdx.x * kBlock + threadIdx.x; e < n; e += gridDim.x * kBlock) {
     uint2 ab = conn[e];
-    uint4 out = make_uint4(kNone, 0, 0, 0);
     if (ab.x != ab.y) {  // parent[] is still the identity: the classes are the signals themselves
       uint32_t val = tag | e;
       red_min_u32(best + ab.x, val);
       red_min_u32(best + ab.y, val);
-      out = make_uint4(e, ab.x, ab.y, 0);
     }
-    cand[e] = out;
   }
 }
 
@@ -500,9 +496,10 @@ __global__ void __launch_bounds__(kBlock) k_msf_pick(const uint2* __restrict__ c
 
 // A class hooks along its minimum edge (an MSF edge => an effective connection).  Mutual minimum: the larger root
 // goes under the smaller.  Edges not chosen by either side stay on the live list.
-__global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ cand, const uint32_t* __restrict__ n_cand, uint32_t* __restrict__ parent,
-                                                     const uint32_t* __restrict__ best, uint32_t tag, uint32_t* __restrict__ eff,
-                                                     uint32_t* __restrict__ cur, uint32_t* __restrict__ n_cur, uint32_t* __restrict__ n_rounds) {
+template <bool kFirst>  // kFirst: candidates are conn[0..n) themselves (round 1); otherwise cand[0..*n_cand)
+__global__ void __launch_bounds__(kBlock) k_msf_hook_t(const uint4* __restrict__ cand, const uint2* __restrict__ conn, const uint32_t* __restrict__ n_cand,
+                                                       uint32_t* __restrict__ parent, const uint32_t* __restrict__ best, uint32_t tag, uint32_t* __restrict__ eff,
+                                                       uint32_t* __restrict__ cur, uint32_t* __restrict__ n_cur, uint32_t* __restrict__ n_rounds) {
   const uint32_t n = *n_cand;
   const int lane = threadIdx.x & 31;
   if (n && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(n_rounds, 1u);  // a round that examined candidates
@@ -511,15 +508,25 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
     bool keep = false;
     uint32_t e = 0;
     uint4 c = make_uint4(kNone, 0, 0, 0);
-    if (i < n) c = cand[i];
+    if (i < n) {
+      if (kFirst) {
+        uint2 ab = conn[i];
+        if (ab.x != ab.y) c = make_uint4(i, ab.x, ab.y, 0);
+      } else c = cand[i];
+    }
     if (c.x != kNone) {
       e = c.x;
       uint32_t val = tag | e;
       bool bu = best[c.y] == val, bv = best[c.z] == val;
-      if (bu && bv) { parent[max(c.y, c.z)] = min(c.y, c.z); eff[e] = 1; }
-      else if (bu) { parent[c.y] = c.z; eff[e] = 1; }
-      else if (bv) { parent[c.z] = c.y; eff[e] = 1; }
+      if (bu && bv) parent[max(c.y, c.z)] = min(c.y, c.z);
+      else if (bu) parent[c.y] = c.z;
+      else if (bv) parent[c.z] = c.y;
       else keep = true;
+      if (!kFirst && !keep) atomicOr(eff + (e >> 5), 1u << (e & 31));  // effective connection: one bit (the bitmap is L2-resident)
+    }
+    if (kFirst) {  // round 1: the warp's 32 connections are exactly one bitmap word - one store, no atomics
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, c.x != kNone && !keep);
+      if (lane == 0 && m) atomicOr(eff + (i0 >> 5), m);
     }
     warp_append_t(keep, e, cur, n_cur);
   }
@@ -532,17 +539,25 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook(const uint4* __restrict__ c
 // the id of its declaration (compiler.rs:157).
 // Pointer chases are latency chains (coalesced loads -> parent[a] -> parent[root] -> atomic); every thread keeps kChaseIlp of
 // them in flight and probes the second hop speculatively (after one Boruvka round every tree has depth 1).
+// eff[] is a bitmap over the connections, effp[w] the number of effective connections before word w (k_scan_u32_t<popc>):
+// #effective connections before connection c
+__device__ __forceinline__ uint32_t eff_rank(const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp, uint32_t c) {
+  return __ldg(effp + (c >> 5)) + __popc(__ldg(eff + (c >> 5)) & ((1u << (c & 31)) - 1u));
+}
 constexpr int kChaseIlp = 4;
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
-                                                         const uint32_t* __restrict__ effx, uint32_t* __restrict__ parent, uint2* __restrict__ nc) {
+                                                         const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
+                                                         uint32_t* __restrict__ parent, uint2* __restrict__ nc) {
   const uint32_t stride = gridDim.x * kBlock;
   for (uint32_t c0 = blockIdx.x * kBlock + threadIdx.x; c0 < C; c0 += stride * kChaseIlp) {
-    uint32_t x[kChaseIlp], x1[kChaseIlp], sb[kChaseIlp], a[kChaseIlp], r0[kChaseIlp], r1[kChaseIlp];
+    uint32_t x[kChaseIlp], sb[kChaseIlp], a[kChaseIlp], r0[kChaseIlp], r1[kChaseIlp];
+    bool is_eff[kChaseIlp];
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) {
       uint32_t c = min(c0 + i * stride, C - 1);
-      x[i] = effx[c];
-      x1[i] = effx[c + 1];
+      uint32_t w = __ldg(eff + (c >> 5));
+      is_eff[i] = (w >> (c & 31)) & 1u;
+      x[i] = __ldg(effp + (c >> 5)) + __popc(w & ((1u << (c & 31)) - 1u));
       sb[i] = conn_sb[c];
       a[i] = conn[c].x;
     }
@@ -552,7 +567,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2
     for (int i = 0; i < kChaseIlp; ++i) r1[i] = parent[r0[i]];
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) {
-      if (c0 + i * stride >= C || x1[i] == x[i]) continue;   // not effective: no id consumed (compiler.rs:235-237)
+      if (c0 + i * stride >= C || !is_eff[i]) continue;      // not effective: no id consumed (compiler.rs:235-237)
       uint32_t id = sb[i] + x[i] + 1u;                        // compiler.rs:257 with node_count = signals + effective merges so far
       uint32_t r = r1[i] == r0[i] ? r0[i] : uf_find(parent, a[i]);
       atomicMax(&nc[r].x, id);
@@ -562,7 +577,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2
 // node_of_signal + the merge-error screens (compiler.rs:239-245); nc[root].y = {#const signals, #gate-output signals << 16}
 constexpr int kFinIlp = 2;
 __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
-                                                        const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ effx,
+                                                        const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
                                                         uint32_t* __restrict__ parent, uint2* __restrict__ nc, uint32_t* __restrict__ nos,
                                                         uint32_t* __restrict__ es) {
   uint32_t f = 0, declared = 0;
@@ -591,7 +606,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
         node = nid[i];
         if (r1[i] != r0[i]) { r = uf_find(parent, s); node = __ldcg(&nc[r].x); }
         if (node == 0) {
-          node = (m[i].x & 0x7FFFFFFFu) + 1u + __ldg(effx + m[i].y);  // a class of one: compiler.rs:157
+          node = (m[i].x & 0x7FFFFFFFu) + 1u + eff_rank(eff, effp, m[i].y);  // a class of one: compiler.rs:157
         } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
           if (m[i].x & 0x80000000u) { if (atomicAdd(&nc[r].y, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
           if (om[i]) { if (atomicAdd(&nc[r].y, 0x10000u) >> 16) f |= EF_OUT_OUT; }
@@ -641,7 +656,7 @@ __global__ void __launch_bounds__(kBlock) k_sig_wires(const uint32_t* __restrict
 static inline size_t emit_scratch_bytes(uint64_t G, uint64_t C, uint64_t S) {  // slab part (exact sizes; the scatter targets live in the staging buffer)
   size_t b = 0;
   b += 2 * align256(4 * S) + align256(8 * S);                               // parent, best, nc
-  b += 2 * align256(4 * (C + 1)) + align256(4 * C) + align256(16 * C);      // eff, effx, cur, cand
+  b += 2 * align256(4 * (C / 32 + 4)) + align256(4 * C) + align256(16 * C); // eff bitmap, its rank prefix, cur, cand
   b += align256(8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1)) + 256;     // tile_state + ticket
   (void)G;
   return b;
@@ -897,8 +912,9 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint2* nc = (uint2*)slab_alloc(h, 8 * (size_t)S);
-  uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * (C + 1));
-  uint32_t* effx = (uint32_t*)slab_alloc(h, 4 * (C + 1));
+  const uint32_t effw = (uint32_t)(C / 32 + 1);  // bitmap words; one spare bit at least, so rank(C) = total is addressable
+  uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
+  uint32_t* effp = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
   uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
   uint4* cand = (uint4*)slab_alloc(h, 16 * C);
   unsigned long long* tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1));
@@ -907,7 +923,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
 
   phase_begin(h, "init");
   cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
-  cudaMemsetAsync(eff, 0, 4 * (C + 1), s);
+  cudaMemsetAsync(eff, 0, 4 * ((size_t)effw + 3), s);
   if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
   phase_end(h);
   // E2 runs only when the ids are explicit; a dense stream was validated inside the scatter
@@ -924,11 +940,13 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     uint32_t tag = (6u - (rounds_issued % 7u)) << 29;
     if (rounds_issued && (rounds_issued % 7u) == 0) cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);  // tags wrapped: forget the old minima
     phase_begin(h, "k_msf_pick");
-    if (rounds_issued == 0) LAUNCH(h, k_msf_pick_first, grid_for(h, (const void*)k_msf_pick_first, kBlock, C), kBlock, conn, (uint32_t)C, parent, best, tag, cand, ncand);
+    const bool first = rounds_issued == 0;
+    if (first) LAUNCH(h, k_msf_pick_first, grid_for(h, (const void*)k_msf_pick_first, kBlock, C), kBlock, conn, (uint32_t)C, best, tag, ncand);
     else LAUNCH(h, k_msf_pick, wide, kBlock, conn, cur, ncur_prev, parent, best, tag, cand, ncand);
     phase_end(h);
     phase_begin(h, "k_msf_hook");
-    LAUNCH(h, k_msf_hook, wide, kBlock, cand, ncand, parent, best, tag, eff, cur, ncur, es + ES_ROUNDS);
+    if (first) LAUNCH(h, k_msf_hook_t<true>, wide, kBlock, cand, conn, ncand, parent, best, tag, eff, cur, ncur, es + ES_ROUNDS);
+    else LAUNCH(h, k_msf_hook_t<false>, wide, kBlock, cand, conn, ncand, parent, best, tag, eff, cur, ncur, es + ES_ROUNDS);
     phase_end(h);
     ++rounds_issued;
   };
@@ -941,22 +959,21 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     cudaMemsetAsync(nc, 0, 8 * (size_t)S, s);
     cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
     phase_end(h);
-    // effx = exclusive scan of eff[0..C); effx[C] receives the total (= effective connections)
+    // effp = exclusive scan of popcount(eff words); effp[effw] receives the total (= effective connections)
     phase_begin(h, "k_scan_u32");
-    if (C) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(C, kScanItems), kBlock, eff, effx, (uint32_t)C, tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
-    else cudaMemsetAsync(effx, 0, 4, s);
+    LAUNCH(h, k_scan_u32_t<true>, scan_tiles(effw, kScanItems), kBlock, eff, effp, effw, tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
     phase_end(h);
     phase_begin(h, "k_ev_nid_edges");
-    if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, effx, parent, nc);
+    if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, effp, parent, nc);
     phase_end(h);
     phase_begin(h, "k_ev_finalize");
-    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, effx, parent, nc, nos, es);
+    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, eff, effp, parent, nc, nos, es);
     phase_end(h);
     phase_begin(h, "k_ev_gates");
     if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
     phase_end(h);
     cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(hp + ES_COUNT, effx + C, 4, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(hp + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, s);
     if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return false;
     return cuda_ok(h, cudaGetLastError(), "emit kernels");
   };
