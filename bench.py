@@ -48,9 +48,9 @@ def alg_bytes(kernel, c):
         "emit:k_msf_hook": C * (8 + 8 + 4 + 4),                   # first round: conn, 2 best, parent, eff
         "emit:k_scan_u32": 8 * (C // 32 + 1) + 16 * ((n + 1023) // 1024),   # effective-connection bitmap ranks + the two tile-count scans
         "emit:k_ev_nid_edges": C * (4 + 8) + Ceff * (4 + 8),      # conn_sb, conn (+ bitmap words, L2) ; parent chase + atomicMax on the root
-        "emit:k_ev_finalize": S * ((0 if c["dense"] else 4) + 8 + 1 + 4 + 8 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, {nid,cnt}, nos + screen atomics
+        "emit:k_ev_finalize": S * ((0 if c["dense"] else 4) + 8 + 1 + 4 + 4 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, id word, nos + screen atomics
         "emit:k_ev_gates": G * (16 + 12 + 16),
-        "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 8),   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
+        "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 4),   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
         # ---- build_circuit (c2a_device.cu)
         "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
         "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair

@@ -533,7 +533,11 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook_t(const uint4* __restrict__
 }
 
 // ---- N: node ids ----------------------------------------------------------------------------------------------
-// nc[root] = {largest id among the class's effective connections (0 = none), merge-screen counters}.  The ids grow with the
+// nidf[root] = largest id among the class's effective connections (0 = none) in the low 30 bits (ids < 2^29: n <= 2^29 events);
+// bits 31 / 30 are the merge screens "the class already holds a constant / a gate output" (set in k_ev_finalize, after every
+// atomicMax of k_ev_nid_edges has landed).  One 4-byte word per signal: the gathers of both kernels touch half the sectors an
+// {id, counters} pair did - these kernels are bound by L1 wavefronts (one per distinct sector per warp instruction), not by DRAM.
+// The ids grow with the
 // event index, and every member of a class of >= 2 signals is joined by an effective connection AFTER its declaration, so the
 // class ends with the id of its last effective connection (compiler.rs:257); a class without one is a single signal and keeps
 // the id of its declaration (compiler.rs:157).
@@ -547,7 +551,7 @@ __device__ __forceinline__ uint32_t eff_rank(const uint32_t* __restrict__ eff, c
 constexpr int kChaseIlp = 4;
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
                                                          const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
-                                                         uint32_t* __restrict__ parent, uint2* __restrict__ nc) {
+                                                         uint32_t* __restrict__ parent, uint32_t* __restrict__ nidf) {
   const uint32_t stride = gridDim.x * kBlock;
   for (uint32_t c0 = blockIdx.x * kBlock + threadIdx.x; c0 < C; c0 += stride * kChaseIlp) {
     uint32_t x[kChaseIlp], sb[kChaseIlp], a[kChaseIlp], r0[kChaseIlp], r1[kChaseIlp];
@@ -564,21 +568,22 @@ __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) r0[i] = parent[a[i]];
 #pragma unroll
-    for (int i = 0; i < kChaseIlp; ++i) r1[i] = parent[r0[i]];
+    for (int i = 0; i < kChaseIlp; ++i) r1[i] = r0[i] == a[i] ? r0[i] : parent[r0[i]];  // a root needs no second probe (fewer sectors per warp)
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) {
       if (c0 + i * stride >= C || !is_eff[i]) continue;      // not effective: no id consumed (compiler.rs:235-237)
       uint32_t id = sb[i] + x[i] + 1u;                        // compiler.rs:257 with node_count = signals + effective merges so far
       uint32_t r = r1[i] == r0[i] ? r0[i] : uf_find(parent, a[i]);
-      atomicMax(&nc[r].x, id);
+      atomicMax(nidf + r, id);
     }
   }
 }
-// node_of_signal + the merge-error screens (compiler.rs:239-245); nc[root].y = {#const signals, #gate-output signals << 16}
+// node_of_signal + the merge-error screens (compiler.rs:239-245)
+constexpr uint32_t kHasConst = 0x80000000u, kHasOut = 0x40000000u, kNidMask = 0x3FFFFFFFu;
 constexpr int kFinIlp = 2;
 __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
                                                         const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
-                                                        uint32_t* __restrict__ parent, uint2* __restrict__ nc, uint32_t* __restrict__ nos,
+                                                        uint32_t* __restrict__ parent, uint32_t* __restrict__ nidf, uint32_t* __restrict__ nos,
                                                         uint32_t* __restrict__ es) {
   uint32_t f = 0, declared = 0;
   const uint32_t stride = gridDim.x * kBlock;
@@ -594,7 +599,10 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
       r0[i] = parent[s];
     }
 #pragma unroll
-    for (int i = 0; i < kFinIlp; ++i) { r1[i] = parent[r0[i]]; nid[i] = __ldcg(&nc[r0[i]].x); }
+    for (int i = 0; i < kFinIlp; ++i) {
+      r1[i] = r0[i] == min(s0 + i * stride, S - 1) ? r0[i] : parent[r0[i]];  // a root needs no second probe
+      nid[i] = __ldcg(nidf + r0[i]) & kNidMask;
+    }
 #pragma unroll
     for (int i = 0; i < kFinIlp; ++i) {
       uint32_t s = s0 + i * stride;
@@ -604,12 +612,12 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
         ++declared;
         uint32_t r = r0[i];
         node = nid[i];
-        if (r1[i] != r0[i]) { r = uf_find(parent, s); node = __ldcg(&nc[r].x); }
+        if (r1[i] != r0[i]) { r = uf_find(parent, s); node = __ldcg(nidf + r) & kNidMask; }
         if (node == 0) {
           node = (m[i].x & 0x7FFFFFFFu) + 1u + eff_rank(eff, effp, m[i].y);  // a class of one: compiler.rs:157
         } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
-          if (m[i].x & 0x80000000u) { if (atomicAdd(&nc[r].y, 1u) & 0xFFFFu) f |= EF_CONST_CONST; }
-          if (om[i]) { if (atomicAdd(&nc[r].y, 0x10000u) >> 16) f |= EF_OUT_OUT; }
+          if (m[i].x & 0x80000000u) { if (atomicOr(nidf + r, kHasConst) & kHasConst) f |= EF_CONST_CONST; }
+          if (om[i]) { if (atomicOr(nidf + r, kHasOut) & kHasOut) f |= EF_OUT_OUT; }
         }
       }
       nos[s] = node;
@@ -655,7 +663,7 @@ __global__ void __launch_bounds__(kBlock) k_sig_wires(const uint32_t* __restrict
 // ---------------------------------------------------------------------------------------------------------------
 static inline size_t emit_scratch_bytes(uint64_t G, uint64_t C, uint64_t S) {  // slab part (exact sizes; the scatter targets live in the staging buffer)
   size_t b = 0;
-  b += 2 * align256(4 * S) + align256(8 * S);                               // parent, best, nc
+  b += 3 * align256(4 * S);                                                 // parent, best, nidf
   b += 2 * align256(4 * (C / 32 + 4)) + align256(4 * C) + align256(16 * C); // eff bitmap, its rank prefix, cur, cand
   b += align256(8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1)) + 256;     // tile_state + ticket
   (void)G;
@@ -911,7 +919,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   const size_t keep = h->slab_used;
   uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
-  uint2* nc = (uint2*)slab_alloc(h, 8 * (size_t)S);
+  uint32_t* nidf = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   const uint32_t effw = (uint32_t)(C / 32 + 1);  // bitmap words; one spare bit at least, so rank(C) = total is addressable
   uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
   uint32_t* effp = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
@@ -956,7 +964,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     phase_begin(h, "init");
     cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
     cudaMemsetAsync(ticket, 0, 4, s);
-    cudaMemsetAsync(nc, 0, 8 * (size_t)S, s);
+    cudaMemsetAsync(nidf, 0, 4 * (size_t)S, s);
     cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
     phase_end(h);
     // effp = exclusive scan of popcount(eff words); effp[effw] receives the total (= effective connections)
@@ -964,10 +972,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     LAUNCH(h, k_scan_u32_t<true>, scan_tiles(effw, kScanItems), kBlock, eff, effp, effw, tile_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
     phase_end(h);
     phase_begin(h, "k_ev_nid_edges");
-    if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, effp, parent, nc);
+    if (C) LAUNCH(h, k_ev_nid_edges, grid_for(h, (const void*)k_ev_nid_edges, kBlock, C), kBlock, (uint32_t)C, conn, conn_sb, eff, effp, parent, nidf);
     phase_end(h);
     phase_begin(h, "k_ev_finalize");
-    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, eff, effp, parent, nc, nos, es);
+    if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, eff, effp, parent, nidf, nos, es);
     phase_end(h);
     phase_begin(h, "k_ev_gates");
     if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
