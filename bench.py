@@ -360,6 +360,8 @@ def main():
     named = np.concatenate([in_ids, out_ids, wl.events[kinds_all == 1, 1]]).astype(np.uint32)
     p_named = torch.from_numpy(named.view(np.int32)).pin_memory()
     p_named_w = torch.empty(len(named), dtype=torch.int32).pin_memory()
+    d_named = torch.empty(len(named), dtype=torch.int32, device=dev)
+    d_named_w = torch.empty(len(named), dtype=torch.int32, device=dev)
 
     def e2e_step(all_arrays):
         st = emit_from_host()
@@ -381,9 +383,22 @@ def main():
             if st != 0:
                 raise RuntimeError(f"c2a_emitted_build_circuit_device -> {st}: {ctx.last_error()}")
             reconcile()
+            if all_arrays:
+                st = lib.c2a_rebase_wire_ids_gathered_device(h, vp(d_wire.data_ptr()), nb, vp(d_all.data_ptr()), rank, world)
+            else:
+                with torch.cuda.stream(stream):
+                    d_named.copy_(p_named, non_blocking=True)
+                st = lib.c2a_emitted_signal_wires_device(h, vp(d_named.data_ptr()), len(named), vp(d_named_w.data_ptr()))
+                if st == 0:
+                    st = lib.c2a_rebase_wire_ids_gathered_device(h, vp(d_named_w.data_ptr()), len(named), vp(d_all.data_ptr()), rank, world)
+            if st != 0:
+                raise RuntimeError(f"named wires / rebase -> {st}: {ctx.last_error()}")
             with torch.cuda.stream(stream):
-                p_order.copy_(d_order, non_blocking=True)
-                p_wire.copy_(d_wire, non_blocking=True)
+                if all_arrays:
+                    p_order.copy_(d_order, non_blocking=True)
+                    p_wire.copy_(d_wire, non_blocking=True)
+                else:
+                    p_named_w.copy_(d_named_w, non_blocking=True)
                 p_new.copy_(d_new, non_blocking=True)
             stream.synchronize()
 
@@ -401,17 +416,17 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    lean = world == 1   # N > 1 ships the rebased arrays (the global named-wire lookup is not sharded yet)
-    dt = e2e_measure(all_arrays=not lean)
+    lean = True
+    dt = e2e_measure(all_arrays=False)
     e2e_phases = {"emit": ctx.phases()} if world > 1 else {"build": ctx.phases()}
     e2e_value = world * G * Ke / dt
     named_w = p_named_w.numpy().astype(np.uint32).copy()
-    dt_all = e2e_measure(all_arrays=True) if lean else dt
+    dt_all = e2e_measure(all_arrays=True)
     # ---- e2e_pipelined (N = 1, extra): two circuits in flight - a second handle on a second host thread - so that the H2D copy
     #      of one step overlaps the D2H copy and the kernels of the other (PCIe is full duplex; every step still copies its own
     #      input and its own result).  Same calls as `e2e`; reported beside it, not instead of it.
     pipe = None
-    if lean and not args.no_pipelined:
+    if world == 1 and not args.no_pipelined:
         ctx2 = c2a.DeviceContext(local_rank)
         lib.c2a_set_timing(ctx2.handle, 0)
         lib.c2a_set_timing(h, 0)
@@ -474,7 +489,7 @@ def main():
 
     # parity spot checks: resident vs host-buffer results; device emitter vs the product's host union-find emitter
     assert np.array_equal(order_dev, p_order.numpy().astype(np.uint32)), "device-resident and host-buffer paths disagree"
-    if lean:
+    if world == 1:
         ctx._emit_info = {"n_gates": G, "signal_bound": int(info.signal_bound)}
         nos_all = ctx.emitted_fetch(want_gates=False)[1]
         assert np.array_equal(named_w, p_wire.numpy().astype(np.uint32)[nos_all[named]]), "c2a_emitted_signal_wires disagrees with the wire map"

@@ -605,6 +605,22 @@ __global__ void __launch_bounds__(kBlock) k_rebase_gathered(uint4* __restrict__ 
   }
 }
 
+__global__ void __launch_bounds__(kBlock) k_rebase_ids_gathered(uint32_t* __restrict__ ids, uint64_t n, const unsigned long long* __restrict__ counts,
+                                                                uint32_t rank, uint32_t world) {
+  unsigned long long tot_in = 0, tot_mid = 0, pre_in = 0, pre_mid = 0, pre_out = 0;
+  for (uint32_t r = 0; r < world; ++r) {
+    tot_in += counts[4 * r];
+    tot_mid += counts[4 * r + 1];
+    if (r < rank) { pre_in += counts[4 * r]; pre_mid += counts[4 * r + 1]; pre_out += counts[4 * r + 2]; }
+  }
+  const uint32_t n_in = (uint32_t)counts[4 * rank], n_mid = (uint32_t)counts[4 * rank + 1];
+  const uint32_t off_in = (uint32_t)pre_in, off_mid = (uint32_t)(tot_in + pre_mid) - n_in, off_out = (uint32_t)(tot_in + tot_mid + pre_out) - n_in - n_mid;
+  for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) {
+    uint32_t w = ids[i];
+    if (w != kNone) ids[i] = w < n_in ? w + off_in : (w < n_in + n_mid ? w + off_mid : w + off_out);
+  }
+}
+
 __global__ void __launch_bounds__(kBlock) k_rebase_map(uint32_t* __restrict__ wire, uint32_t n, uint32_t n_in, uint32_t n_mid, uint32_t off_in,
                                                        uint32_t off_mid, uint32_t off_out) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
@@ -1139,6 +1155,14 @@ int c2a_rebase_wires_gathered_device(c2a_handle* h, c2a_gate* d_new_gates, uint3
   if (!d_new_gates || !d_counts || rank >= world) return fail(h, C2A_ERR_INVALID_ARGUMENT, "bad argument");
   if (G) LAUNCH(h, k_rebase_gathered, grid_for(h, (const void*)k_rebase_gathered, kBlock, G), kBlock, (uint4*)d_new_gates, d_order, (uint32_t)G,
                 (const unsigned long long*)d_counts, rank, world);
+  return cuda_ok(h, cudaGetLastError(), "rebase launch") ? C2A_OK : C2A_ERR_CUDA;
+}
+
+int c2a_rebase_wire_ids_gathered_device(c2a_handle* h, uint32_t* d_wire_ids, uint64_t n, const uint64_t* d_counts, uint32_t rank, uint32_t world) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if ((n && !d_wire_ids) || !d_counts || rank >= world) return fail(h, C2A_ERR_INVALID_ARGUMENT, "bad argument");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  if (n) LAUNCH(h, k_rebase_ids_gathered, grid_for(h, (const void*)k_rebase_ids_gathered, kBlock, n), kBlock, d_wire_ids, n, (const unsigned long long*)d_counts, rank, world);
   return cuda_ok(h, cudaGetLastError(), "rebase launch") ? C2A_OK : C2A_ERR_CUDA;
 }
 

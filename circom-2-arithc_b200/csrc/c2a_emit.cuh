@@ -1167,6 +1167,18 @@ int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n,
   return cuda_ok(h, cudaGetLastError(), "k_sig_wires") ? C2A_OK : C2A_ERR_CUDA;
 }
 
+int c2a_emitted_signal_wires_device(c2a_handle* h, const uint32_t* d_signals, uint64_t n, uint32_t* d_wires_out) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h->emitted.valid || !h->emitted.wire) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no built circuit is resident on this handle");
+  if (!h->emitted.nos_valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "the signal -> node map is not resident (sparse signal ids): use c2a_emitted_signal_wires");
+  if (n == 0) return C2A_OK;
+  if (!d_signals || !d_wires_out) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  LAUNCH(h, k_sig_wires, grid_for(h, (const void*)k_sig_wires, kBlock, n), kBlock, d_signals, n, h->emitted.signal_bound, (const uint32_t*)(h->slab + h->emitted.nos_off),
+         h->emitted.wire, h->emitted.node_count + 1, d_wires_out);
+  return cuda_ok(h, cudaGetLastError(), "k_sig_wires") ? C2A_OK : C2A_ERR_CUDA;
+}
+
 int c2a_emitted_build_circuit(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                               uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index) {
   return emitted_build_impl(h, input_signals, n_in, output_signals, n_out, order_out, wire_of_node, new_gates, wire_count, err_index, false);

@@ -137,6 +137,9 @@ int c2a_rebase_wires_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_orde
 int c2a_rebase_wires_gathered_device(c2a_handle*, c2a_gate* d_new_gates, uint32_t* d_order, uint64_t G, const uint64_t* d_counts,
                                      uint32_t rank, uint32_t world);
 
+/* the gathered-counts rebase for any array of LOCAL wire ids (a wire map, a list of named wires); C2A_NONE entries stay; enqueue-only */
+int c2a_rebase_wire_ids_gathered_device(c2a_handle*, uint32_t* d_wire_ids, uint64_t n, const uint64_t* d_counts, uint32_t rank, uint32_t world);
+
 /* same mapping applied to a node-indexed wire map (entries equal to C2A_NONE are left alone) */
 int c2a_rebase_wire_map_device(c2a_handle*, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid,
                                uint32_t off_in, uint32_t off_mid, uint32_t off_out);
@@ -208,6 +211,8 @@ int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals,
  * signals[i], C2A_NONE when the signal was never declared or its node has no wire.  With this a caller that wants the
  * reference's result (gates + named wires) can pass NULL for order_out and wire_of_node and skip their device->host copies. */
 int c2a_emitted_signal_wires(c2a_handle*, const uint32_t* signals, uint64_t n, uint32_t* wires_out);
+/* same with DEVICE pointers for both lists; enqueue-only (dense signal ids only: the signal -> node map must be resident) */
+int c2a_emitted_signal_wires_device(c2a_handle*, const uint32_t* d_signals, uint64_t n, uint32_t* d_wires_out);
 
 /* ---- packed event stream.  The same emission calls at ~6 bytes per event instead of 16: what the walker hands to the
  * device emitter when the stream has to cross PCIe (c2a_program_packed) and what the device reads from HBM.

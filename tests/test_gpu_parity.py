@@ -327,3 +327,34 @@ def test_rebase_from_gathered_counts_matches_host_offsets(ctx, c2a):
     torch.cuda.synchronize()
     assert torch.equal(a_g, b_g) and torch.equal(a_o, b_o)
     assert not np.array_equal(a_g.cpu().numpy().view(np.uint32), gates)
+
+
+def test_named_wires_on_the_device_and_their_rebase(ctx, c2a):
+    """c2a_emitted_signal_wires_device == c2a_emitted_signal_wires; c2a_rebase_wire_ids_gathered_device == the host offsets"""
+    import ctypes as C
+    import torch
+    lib, vp = c2a.lib, C.c_void_p
+    wl = c2a.workloads.mimc_chains(5, rounds=4, variant="late")
+    ev = np.ascontiguousarray(wl.events)
+    info = ctx.emit_events(ev)
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    order, wire, ng, wc = ctx.emitted_build_circuit(ins, outs)
+    probe = np.concatenate([ins, outs, ev[(ev[:, 0] & 0xFF) == 1, 1], [info["signal_bound"] + 3]]).astype(np.uint32)
+    want = ctx.emitted_signal_wires(probe)
+    dev = torch.device("cuda", 0)
+    d_sig = torch.from_numpy(probe.view(np.int32)).to(dev)
+    d_out = torch.empty_like(d_sig)
+    assert lib.c2a_emitted_signal_wires_device(ctx.handle, vp(d_sig.data_ptr()), len(probe), vp(d_out.data_ptr())) == 0
+    torch.cuda.synchronize()
+    got = d_out.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, want) and got[-1] == 0xFFFFFFFF
+    n_in, n_out = len(ins), len(outs)
+    n_mid = wc - n_in - n_out
+    counts = np.array([[3, 11, 2, 9], [n_in, n_mid, n_out, len(order)], [4, 6, 1, 5]], dtype=np.int64)
+    off_in, off_mid, off_out, _ = c2a.sharding.rebase_offsets(counts, 1, shared_io=False)
+    d_counts = torch.from_numpy(counts).to(dev)
+    assert lib.c2a_rebase_wire_ids_gathered_device(ctx.handle, vp(d_out.data_ptr()), len(probe), vp(d_counts.data_ptr()), 1, 3) == 0
+    torch.cuda.synchronize()
+    w = want.astype(np.int64)
+    exp = np.where(w == 0xFFFFFFFF, w, np.where(w < n_in, w + off_in, np.where(w < n_in + n_mid, w + off_mid, w + off_out)))
+    assert np.array_equal(d_out.cpu().numpy().view(np.uint32).astype(np.int64), exp)
