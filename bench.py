@@ -53,8 +53,8 @@ def alg_bytes(kernel, c):
         "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 4),   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
         # ---- build_circuit (c2a_device.cu)
         "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
-        "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair
-        "k_relax": G * (8 + 4),                                   # read dep pair, r init (+ out-of-order edges)
+        "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair (+ the forward-edge list)
+        "k_relax": 0,                                             # data-driven from the forward-edge list k_deps collects: traffic ~ the moved cones only
         "k_sizes": G * (4 + 4),
         "k_scan_u32": G * (4 + 4) + (0 if "W" not in c else 8 * c["W"]),   # block-offset scan + bitmap rank scan
         "k_roots": G * (4 + 8 + 4),

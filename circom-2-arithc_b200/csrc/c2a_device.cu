@@ -87,7 +87,7 @@ constexpr uint32_t kFirstTag = 0x80000000u;
 // S_QN_LAST != 0 after them means "r[] has not converged yet": every later kernel of the call parks itself and the host
 // drains the queue with synchronised rounds (S_QA / S_QB) before re-issuing the tail of the pipeline.
 constexpr int kSpecRounds = 4;
-enum { S_FLAGS = 0, S_HEAVYN = 1, S_NMID = 2, S_TICKET = 3, S_TICKET2 = 4, S_ERR_LO = 6, S_ERR_HI = 7, S_QN0 = 8, S_QN_LAST = S_QN0 + kSpecRounds,
+enum { S_FLAGS = 0, S_HEAVYN = 1, S_NMID = 2, S_SEEDN = 3, S_ERR_LO = 6, S_ERR_HI = 7, S_QN0 = 8, S_QN_LAST = S_QN0 + kSpecRounds,
        S_QA = 13, S_QB = 14, S_COUNT = 32 };
 enum { F_OOO = 1, F_BAD = 2, F_SELF = 4, F_BAD_IO = 8 };
 
@@ -125,16 +125,32 @@ __global__ void __launch_bounds__(kBlock) k_producer(const uint4* __restrict__ g
 // from 0..G-1 (otherwise every root's deps are already visited when the root loop reaches it).
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates, uint32_t G, uint32_t node_bound, const uint32_t* __restrict__ prod1,
-                                                 uint2* __restrict__ dep, uint32_t* __restrict__ scalars) {
+                                                 uint2* __restrict__ dep, uint32_t* __restrict__ seeds, uint32_t* __restrict__ scalars) {
   uint32_t f = 0;
-  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
-    uint4 gt = ldg_stream(gates + g);
-    // ids >= node_bound were flagged by k_producer (F_BAD); stay memory-safe here, the call fails at the status read
-    uint32_t d0 = gt.y < node_bound ? __ldg(prod1 + gt.y) - 1u : kNone;  // 0 -> kNone
-    uint32_t d1 = gt.z < node_bound ? __ldg(prod1 + gt.z) - 1u : kNone;
-    dep[g] = make_uint2(d0, d1);
-    if ((d0 != kNone && d0 >= g) || (d1 != kNone && d1 >= g)) f |= F_OOO;
-    if (d0 == g || d1 == g) f |= F_SELF;
+  const uint32_t iters = (G + gridDim.x * kBlock - 1) / (gridDim.x * kBlock);  // full-warp iterations (warp-aggregated append below)
+  for (uint32_t it = 0; it < iters; ++it) {
+    const uint32_t g = it * gridDim.x * kBlock + blockIdx.x * kBlock + threadIdx.x;
+    bool fwd = false;
+    if (g < G) {
+      uint4 gt = ldg_stream(gates + g);
+      // ids >= node_bound were flagged by k_producer (F_BAD); stay memory-safe here, the call fails at the status read
+      uint32_t d0 = gt.y < node_bound ? __ldg(prod1 + gt.y) - 1u : kNone;  // 0 -> kNone
+      uint32_t d1 = gt.z < node_bound ? __ldg(prod1 + gt.z) - 1u : kNone;
+      dep[g] = make_uint2(d0, d1);
+      fwd = (d0 != kNone && d0 > g) || (d1 != kNone && d1 > g);
+      if (fwd) f |= F_OOO;
+      if (d0 == g || d1 == g) f |= F_SELF;
+    }
+    // gates with a forward dependency are where the relaxation starts (K5a): collect them, the seed kernel does not
+    // have to stream dep[] again to find them
+    uint32_t m = __ballot_sync(0xFFFFFFFFu, fwd);
+    if (m) {
+      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(scalars + S_SEEDN, (uint32_t)__popc(m));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (fwd) seeds[base + __popc(m & ((1u << lane) - 1))] = g;
+    }
   }
   uint32_t any_ooo = __syncthreads_or(f & F_OOO), any_self = __syncthreads_or(f & F_SELF);
   if (threadIdx.x == 0 && (any_ooo || any_self)) atomicOr(scalars + S_FLAGS, (any_ooo ? F_OOO : 0u) | (any_self ? F_SELF : 0u));
@@ -142,7 +158,7 @@ __global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates
 
 // generic get_deps form (topological_sort.rs:3-6): CSR rows with <= 2 entries
 __global__ void __launch_bounds__(kBlock) k_deps_from_csr(const unsigned long long* __restrict__ dep_off, const uint32_t* __restrict__ dep_idx,
-                                                          uint32_t n, uint2* __restrict__ dep, uint32_t* __restrict__ scalars) {
+                                                          uint32_t n, uint2* __restrict__ dep, uint32_t* __restrict__ seeds, uint32_t* __restrict__ scalars) {
   uint32_t f = 0;
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < n; g += gridDim.x * kBlock) {
     unsigned long long a = dep_off[g], b = dep_off[g + 1];
@@ -156,7 +172,7 @@ __global__ void __launch_bounds__(kBlock) k_deps_from_csr(const unsigned long lo
       if (b - a == 2 && d0 == kNone) f |= F_BAD;  // a literal 0xFFFFFFFF index is not representable
     }
     dep[g] = make_uint2(d0, d1);
-    if ((d0 != kNone && d0 >= g) || (d1 != kNone && d1 >= g)) f |= F_OOO;
+    if ((d0 != kNone && d0 > g) || (d1 != kNone && d1 > g)) { f |= F_OOO; seeds[atomicAdd(scalars + S_SEEDN, 1u)] = g; }
     if (d0 == g || d1 == g) f |= F_SELF;
   }
   uint32_t any_ooo = __syncthreads_or(f & F_OOO), any_bad = __syncthreads_or(f & F_BAD), any_self = __syncthreads_or(f & F_SELF);
@@ -213,14 +229,15 @@ __device__ __forceinline__ void relax_from(uint32_t cur, uint32_t val, const uin
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_relax_seed(const uint2* __restrict__ dep, uint32_t n, uint32_t* __restrict__ r,
+__global__ void __launch_bounds__(kBlock) k_relax_seed(const uint2* __restrict__ dep, const uint32_t* __restrict__ seeds, uint32_t* __restrict__ r,
                                                        uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn,
                                                        const uint32_t* __restrict__ sc) {
   if (!sort_wanted(sc)) return;
-  for (uint32_t u = blockIdx.x * kBlock + threadIdx.x; u < n; u += gridDim.x * kBlock) {
-    uint2 d = dep[u];
-    // r[d] <= d always, so val=u can only lower r[d] along an out-of-order edge (d > u)
-    if ((d.x != kNone && d.x > u) || (d.y != kNone && d.y > u)) relax_from(u, u, dep, r, inq, q, qn);
+  const uint32_t n = sc[S_SEEDN];
+  // r[d] <= d always, so val=u can only lower r[d] along a forward edge (d > u): exactly the gates k_deps collected
+  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+    uint32_t u = seeds[i];
+    relax_from(u, u, dep, r, inq, q, qn);
   }
 }
 
@@ -826,7 +843,7 @@ void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const Sor
   LAUNCH(h, k_sort_init, grid_for(h, (const void*)k_sort_init, kBlock, (uint64_t)n + 1), kBlock, n, s.r, s.size_off, s.state, s.inq, sc);
   phase_end(h);
   phase_begin(h, "k_relax");
-  LAUNCH(h, k_relax_seed, grid_for(h, (const void*)k_relax_seed, kBlock, n), kBlock, d_dep, n, s.r, s.inq, s.q0, sc + S_QN0, sc);
+  LAUNCH(h, k_relax_seed, h->num_sms * 4, kBlock, d_dep, s.heavy, s.r, s.inq, s.q0, sc + S_QN0, sc);  // seeds live in heavy[] until k_roots reuses it
   const int round_grid = h->num_sms * 4;
   for (int j = 0; j < kSpecRounds; ++j)
     LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, (j & 1) ? s.q1 : s.q0, sc + S_QN0 + j, (j & 1) ? s.q0 : s.q1, sc + S_QN0 + j + 1);
@@ -884,7 +901,7 @@ int sort_drain(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch&
 void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s) {
   cudaStream_t st = h->stream;
   uint32_t* sc = s.scalars;
-  cudaMemsetAsync(sc + S_HEAVYN, 0, 4 * (S_TICKET2 - S_HEAVYN + 1), st);  // heavy count, n_mid, both tickets
+  cudaMemsetAsync(sc + S_HEAVYN, 0, 4 * 2, st);  // heavy count, n_mid
   cudaMemsetAsync(sc + S_ERR_LO, 0xFF, 8, st);
   cudaMemsetAsync(sc + S_QN_LAST, 0, 4, st);
   cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, st);
@@ -967,7 +984,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
   phase_end(h);
   phase_begin(h, "k_deps");
-  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, sc);
+  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, s.heavy, sc);
   phase_end(h);
 
   uint32_t* d_order = d_order_user ? d_order_user : order_int;
@@ -1262,7 +1279,7 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
   cudaMemcpyAsync(d_off, dep_off, 8 * (n + 1), cudaMemcpyHostToDevice, stq);
   if (nnz) cudaMemcpyAsync(d_idx, dep_idx, 4 * nnz, cudaMemcpyHostToDevice, stq);
   phase_begin(h, "k_deps");
-  LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, nn, dep, s.scalars);
+  LAUNCH(h, k_deps_from_csr, grid_for(h, (const void*)k_deps_from_csr, kBlock, n), kBlock, d_off, d_idx, nn, dep, s.heavy, s.scalars);
   phase_end(h);
   sort_enqueue_relax(h, dep, nn, s);
   auto tail = [&]() {

@@ -40,7 +40,7 @@ namespace c2a {
 constexpr int kEvTile = 1024;  // events per CTA pass: 8 warps x 4 rows x 32 lanes
 constexpr int kSpecMsf = 2;    // Boruvka rounds enqueued without looking at the live-edge count
 // ES_MC0 + 2r / + 2r + 1: candidate / live counts of speculative round r (zeroed once); ES_NCUR / ES_NCAND: the host-driven rounds
-enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_TICKET = 7, ES_ROUNDS = 8, ES_IOBAD = 9, ES_TICKET2 = 10,
+enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_PREV = 7, ES_ROUNDS = 8, ES_IOBAD = 9,
        ES_MC0 = 16, ES_COUNT = 32 };
 enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128,
        EF_CAP = 256 /* a signal id beyond the table bound the pass was launched with: rerun with the exact bound */ };
@@ -996,9 +996,9 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     // (eff[] is only ever added to, parent[] only compressed/hooked further: the re-run starts from a consistent state.)
     cudaMemcpyAsync(es + ES_NCUR, es + ES_MC0 + 2 * (kSpecMsf - 1) + 1, 4, cudaMemcpyDeviceToDevice, s);
     while (true) {
-      cudaMemcpyAsync(es + ES_TICKET, es + ES_NCUR, 4, cudaMemcpyDeviceToDevice, s);  // ES_TICKET is free after E1: holds the previous live count
+      cudaMemcpyAsync(es + ES_PREV, es + ES_NCUR, 4, cudaMemcpyDeviceToDevice, s);  // the previous round's live count
       cudaMemsetAsync(es + ES_NCUR, 0, 8, s);                                         // ES_NCUR, ES_NCAND
-      msf_round(es + ES_TICKET, es + ES_NCAND, es + ES_NCUR);
+      msf_round(es + ES_PREV, es + ES_NCAND, es + ES_NCUR);
       cudaMemcpyAsync(hp, es + ES_NCUR, 8, cudaMemcpyDeviceToHost, s);
       if (!cuda_ok(h, cudaStreamSynchronize(s), "msf sync")) return C2A_ERR_CUDA;
       if (hp[1] == 0 || hp[0] == 0) break;  // no candidate edges at all, or none left undecided

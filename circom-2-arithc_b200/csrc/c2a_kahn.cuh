@@ -399,7 +399,7 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.scalars);
     phase_end(h);
     phase_begin(h, "k_deps");
-    LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, b.scalars);
+    LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, (uint32_t*)b.q[0], b.scalars);  // the forward-edge list is not used here: park it in a queue buffer
     phase_end(h);
     phase_begin(h, "k_kahn_count");
     LAUNCH(h, k_kahn_count, grid_for(h, (const void*)k_kahn_count, kBlock, G), kBlock, b.dep, G, b.row_off);
