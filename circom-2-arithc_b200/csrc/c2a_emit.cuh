@@ -328,7 +328,14 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
       uint32_t kind = kb[j] & 3u;
       if (kind == C2A_EV_GATE) s_list[min(my_dg, (uint32_t)kEvTile - 1)] = k | (my_dc << 10);
       else if (kind == C2A_EV_CONNECT) s_list[min(ng + my_dc, (uint32_t)kEvTile - 1)] = k | (my_dg << 10);
-      else s_list[min(ng + nc + (k - my_dg - my_dc), (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
+      else if (dense) {
+        // dense ids: the id IS the declaration rank - the record is complete right here, lanes holding signals write consecutive
+        // slots (no filing, no phase-B pass for the most frequent kind)
+        const uint32_t sid = s0 + (k - my_dg - my_dc);
+        smax = max(smax, sid + 1);
+        if (sid < S_cap) sig_meta[sid] = make_uint2(sid | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), c0 + my_dc);
+        else f |= EF_CAP;
+      } else s_list[min(ng + nc + (k - my_dg - my_dc), (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
     }
     __syncthreads();
     // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores.
@@ -365,7 +372,7 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
         conn[c0 + r] = ab;
         conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
       }
-      const uint32_t ns = nev - min(nev, ng + nc);
+      const uint32_t ns = dense ? 0u : nev - min(nev, ng + nc);  // (dense: already stored in phase A)
       for (uint32_t r = threadIdx.x; r < ns; r += kBlock) {  // signal r of the tile
         uint32_t e = s_list[ng + nc + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_dc = k - my_dg - r;
         uint32_t sid = dense ? s0 + r : W(3u * my_dg + 2u * my_dc + r);
