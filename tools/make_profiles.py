@@ -1,0 +1,109 @@
+#!/usr/bin/env python
+"""Regenerate profiles/ (README.md tables, traffic.json, the ncu table inside r01_ncu_full_summary.md) from one evidence set
+in gpurun_out/ (developer tool).   usage: tools/make_profiles.py <prefix>     e.g. r01e  ->  gpurun_out/r01e_bench.json, ...
+Needs: <prefix>_bench.json, _bench_ref.json, _bench_aos.json, _launches.csv, _full.ncu-rep; optional profiles/r01_bench_{2,4}gpu.json."""
+import collections, csv, json, os, shutil, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pre = sys.argv[1]
+G = lambda n: os.path.join(ROOT, "gpurun_out", f"{pre}_{n}")
+P = lambda n: os.path.join(ROOT, "profiles", n)
+L = lambda p: json.loads(open(p).read().strip().splitlines()[-1])
+shutil.copy(G("bench.json"), P("r01_bench_packed_10M.json"))
+shutil.copy(G("bench_ref.json"), P("r01_bench_reference_arm.json"))
+shutil.copy(G("bench_aos.json"), P("r01_bench_aos_stream_10M.json"))
+shutil.copy(G("launches.csv"), P("r01_launches_bench_packed_10M.csv"))
+raw = subprocess.run(["ncu", "-i", G("full.ncu-rep"), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+open("/tmp/raw_mp.csv", "w").write(raw)
+ncu_table = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_table.py"), "/tmp/raw_mp.csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(raw.splitlines()))
+hdr = rows[0]; ix = {h: i for i, h in enumerate(hdr)}
+def nbytes(r, k):
+    v = float(r[ix[k]].replace(",", "")); u = rows[1][ix[k]]
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+traffic = {"_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, bytes (largest launch of each kernel); ncu --set full, round 1 final capture "
+                    "(profiles/r01_ncu_full_summary.md); workload mimc_chains W=18315 late (10 018 305 gates), packed dense event stream"}
+for r in rows[2:]:
+    name = r[ix["Kernel Name"]].split("(")[0].replace("c2a::", "").replace("void ", "")
+    name = {"k_pk_scatter": "k_ev_scatter", "k_pk_count": "k_ev_count", "k_msf_pick_first": "k_msf_pick"}.get(name, name)
+    for a, b in (("k_scan_u32", "k_scan_u32"), ("k_msf_hook", "k_msf_hook"), ("k_level_pass", "k_level_sort")):
+        if name.startswith(a): name = b
+    t = nbytes(r, "dram__bytes_read.sum") + nbytes(r, "dram__bytes_write.sum")
+    if name not in traffic or t > traffic[name]: traffic[name] = int(t)
+json.dump(traffic, open(P("traffic.json"), "w"), indent=1)
+lrows = list(csv.reader(l for l in open(P("r01_launches_bench_packed_10M.csv")) if not l.startswith("==")))
+lh = lrows[0]; lx = {h: i for i, h in enumerate(lh)}
+acc = collections.defaultdict(lambda: [0, 0.0])
+for x in lrows[1:]:
+    if len(x) < len(lh) or x[lx["Metric Name"]] != "gpu__time_duration.sum": continue
+    name = x[lx["Kernel Name"]].split("(")[0].replace("c2a::", "").replace("void ", "")
+    v = float(x[lx["Metric Value"]].replace(",", "")); u = x[lx["Metric Unit"]]
+    acc[name][0] += 1; acc[name][1] += v / 1000 if u in ("ns", "nsecond") else (v if u in ("us", "usecond") else v * 1000)
+tot = sum(v[1] for k, v in acc.items() if k.startswith("k_"))
+launch = "\n".join(f"| `{k}` | {v[0]} | {v[1]/v[0]:.1f} | {v[1]/tot:.3f} |" for k, v in sorted(acc.items(), key=lambda kv: -kv[1][1]) if k.startswith("k_"))
+d = L(P("r01_bench_packed_10M.json")); r = d["roofline"]; e = d["e2e"]
+# bench.py read the previous traffic.json: refresh the field from this capture
+r["traffic"] = traffic.get(r["kernel"], r.get("traffic"))
+da = L(P("r01_bench_aos_stream_10M.json")); ref = L(P("r01_bench_reference_arm.json"))
+multi = []
+for n in (2, 4, 8):
+    if os.path.exists(P(f"r01_bench_{n}gpu.json")):
+        m = L(P(f"r01_bench_{n}gpu.json"))
+        multi.append(f"| N = {n} | value {m['value']/1e9:.2f} G gates/s ({m['ms_per_step']:.3f} ms/step), e2e {m['e2e']['value']/1e6:.0f} M gates/s ({m['e2e']['s_per_step']*1e3:.2f} ms/step) |")
+kern = "\n".join(f"| `{k}` | {v:.4f} | {r['per_kernel_gbs'].get(k, '')} |" for k, v in sorted(r["per_kernel_ms"].items(), key=lambda x: -x[1]))
+pipe, alla, cb = d.get("e2e_pipelined", {}), d.get("e2e_all_arrays", {}), d.get("cpu_baseline", {})
+readme = f'''# profiles/ — measured evidence, one set per round
+
+All captures: B200 (sm_100a, 148 SMs, `clocks.max.sm` 1965 MHz), driver 580, CUDA 12.9, `--clock-control none`.
+Per-launch times in an ncu launch list are cold-cache and serialised: compare SHARES with `bench.py`, not absolutes.
+`superseded/` holds the first captures of this round (before the sync-free pipeline, the node-side wire numbering and the
+packed event stream); they are kept only for the history of the numbers.  `tools/make_profiles.py <prefix>` regenerates this
+directory from one evidence set in `gpurun_out/`.
+
+## Round 1 (final state of the round)
+
+| file | what | command |
+|---|---|---|
+| `r01_bench_packed_10M.json` | the bench line (N = 1, packed event stream, default flags) | `python bench.py --steps 10 --warmup 3` |
+| `r01_bench_aos_stream_10M.json` | same workload handed over as 16-byte `c2a_event` records | `python bench.py --steps 10 --warmup 3 --stream aos --no-cpu-baseline --no-host-emit --no-pipelined` |
+| `r01_bench_2gpu.json`, `r01_bench_4gpu.json` | N = 2, 4 (one independent component subtree per rank, NCCL all-gather + device-side rebase) | `torchrun --nproc-per-node N bench.py --gpus N --steps 10 --warmup 3` under `gpurun --gpus N` |
+| `r01_bench_reference_arm.json` | the reference's CPU path restated (oracle port, 1 thread) on the same box | `python bench.py --impl reference --steps 2 --warmup 1` |
+| `r01_launches_bench_packed_10M.csv` | every kernel launch of one `bench.py` run, `gpu__time_duration.sum` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file … python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-host-emit --no-pipelined` |
+| `r01_ncu_full_summary.md` | `ncu --set full` of every kernel of the step and of the Kahn levels (DRAM bytes, throughput, occupancy, stall reading) | see the file |
+| `traffic.json` | `dram__bytes_read.sum + dram__bytes_write.sum` per launch from that capture; `bench.py` copies the dominant kernel's entry into `roofline.traffic` | |
+
+Headline (10 018 305 gates, MiMC chains W = 18 315, `late` variant = non-identity DFS order, 41.9 M events):
+
+| | value |
+|---|---|
+| `value` (stream resident in HBM, emit + build, results in HBM) | **{d['value']/1e9:.2f} G gates/s**, {d['ms_per_step']:.3f} ms/step, {r['whole_step_gbs']:.0f} GB/s algorithmic over the whole step (run-to-run: 1.47–1.53 ms) |
+| `e2e` (packed stream in pinned host memory → renumbered gates + named wires in pinned host memory) | **{e['value']/1e6:.0f} M gates/s**, {e['s_per_step']*1e3:.2f} ms/step, {e['h2d_bytes_per_step']/1e6:.0f} MB H2D + {e['d2h_bytes_per_step']/1e6:.0f} MB D2H |
+| `e2e_all_arrays` (also `order` and the whole node→wire map) | {alla.get('value', 0)/1e6:.0f} M gates/s, {alla.get('s_per_step', 0)*1e3:.2f} ms/step, {alla.get('d2h_bytes_per_step', 0)/1e6:.0f} MB D2H |
+| `e2e_pipelined` (two handles / two circuits in flight) | {pipe.get('value', 0)/1e6:.0f} M gates/s, {pipe.get('s_per_step', 0)*1e3:.2f} ms/step |
+| same workload as 16-byte AoS events | value {da['value']/1e9:.2f} G gates/s, e2e {da['e2e']['value']/1e6:.0f} M gates/s ({da['e2e']['s_per_step']*1e3:.2f} ms, {da['e2e']['h2d_bytes_per_step']/1e6:.0f} MB H2D) |
+{chr(10).join(multi)}
+| dominant kernel | `{r['kernel']}`: {r['kernel_ms']*1e3:.0f} µs live in the timed steps, {r['achieved']:.0f} GB/s algorithmic = **{r['frac']:.2f} of the measured {r['peak']:.0f} GB/s**; ncu DRAM traffic {r['traffic']/1e6:.0f} MB vs {r['alg_bytes_per_launch']/1e6:.0f} MB algorithmic |
+| reference arm (oracle port, 1 thread, {ref['config']['sample'].split(':')[0]}) | {ref['value']:.0f} gates/s; its back end alone on the full 10 M gates: {cb.get('backend_only_gates_per_s', 0)/1e6:.1f} M gates/s |
+| host union-find emitter + `c2a_build_circuit` (same circuit, 1 step) | {d.get('e2e_host_emitter', {}).get('value', 0)/1e6:.1f} M gates/s |
+| clocks during the timed region | {d['clocks']} |
+
+Per-kernel table of the bench run ({r.get('per_kernel_note', '')}):
+
+| kernel | ms per step | algorithmic GB/s |
+|---|---:|---:|
+{kern}
+
+Launch-list summary (`r01_launches_bench_packed_10M.csv`; kernels only, memsets excluded; share = of the kernel time under ncu):
+
+| kernel | launches | avg µs (ncu, cold, serialised) | share |
+|---|---:|---:|---:|
+{launch}
+
+The dominant kernel agrees in both views: `k_pk_scatter` (phase name `k_ev_scatter`) is the largest entry under ncu and has
+{r['kernel_ms']/d['ms_per_step']:.3f} of the step in the bench (the step also contains the memset nodes and three host round trips).
+'''
+open(P("README.md"), "w").write(readme)
+open("/tmp/ncu_table.md", "w").write(ncu_table)
+s = open(P("r01_ncu_full_summary.md")).read()
+a = s.index("| kernel | time us |"); b = s.index("Reading it:")
+open(P("r01_ncu_full_summary.md"), "w").write(s[:a] + ncu_table + "\n" + s[b:])
+print("profiles regenerated from", pre, "| value %.2f G gates/s" % (d["value"] / 1e9))
