@@ -318,24 +318,26 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     __syncthreads();
     uint32_t dg = 0, dc = 0;  // in-tile ranks
     for (int w = 0; w < warp; ++w) { dg += s_g[w]; dc += s_c[w]; }
+    // (this loop is the hot spot of an issue-bound kernel: one select-built shared-memory store for gates and connections,
+    //  one predicated 8-byte store for a dense signal, no per-event bounds checks or reductions)
+    if (dense && threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      uint32_t k = warp * 128 + j * 32 + lane;
-      uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
+      const uint32_t k = warp * 128 + j * 32 + lane;
+      const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
       dg += __popc(gm[j]);
       dc += __popc(cm[j]);
-      if (k >= nev) continue;
-      uint32_t kind = kb[j] & 3u;
-      if (kind == C2A_EV_GATE) s_list[min(my_dg, (uint32_t)kEvTile - 1)] = k | (my_dc << 10);
-      else if (kind == C2A_EV_CONNECT) s_list[min(ng + my_dc, (uint32_t)kEvTile - 1)] = k | (my_dg << 10);
-      else if (dense) {
-        // dense ids: the id IS the declaration rank - the record is complete right here, lanes holding signals write consecutive
-        // slots (no filing, no phase-B pass for the most frequent kind)
-        const uint32_t sid = s0 + (k - my_dg - my_dc);
-        smax = max(smax, sid + 1);
-        if (sid < S_cap) sig_meta[sid] = make_uint2(sid | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), c0 + my_dc);
-        else f |= EF_CAP;
-      } else s_list[min(ng + nc + (k - my_dg - my_dc), (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | (kind == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
+      const bool is_g = (gm[j] >> lane) & 1u, is_c = (cm[j] >> lane) & 1u;
+      const uint32_t ds = k - my_dg - my_dc;
+      if (is_g | is_c) {  // (both masks exclude lanes past the end of the stream)
+        s_list[min(is_g ? my_dg : ng + my_dc, (uint32_t)kEvTile - 1)] = k | ((is_g ? my_dc : my_dg) << 10);
+      } else if (k < nev) {
+        const uint32_t cbit = (kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u;
+        // dense ids: the id IS the declaration rank (< n <= S_cap) - the record is complete right here, lanes holding signals write
+        // consecutive slots (no filing, no phase-B pass for the most frequent kind)
+        if (dense) sig_meta[s0 + ds] = make_uint2((s0 + ds) | cbit, c0 + my_dc);
+        else s_list[min(ng + nc + ds, (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | cbit;
+      }
     }
     __syncthreads();
     // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores.
