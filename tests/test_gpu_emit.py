@@ -297,6 +297,42 @@ def test_merge_errors(ctx, c2a):
     assert gates.tolist() == [[0, 1, 2, 5], [0, 1, 2, 5]]
 
 
+@pytest.mark.parametrize("dense", [True, False])
+def test_packed_resident_with_unaligned_device_pointers(ctx, c2a, dense):
+    """c2a_emit_packed_resident takes the caller's device pointers as they are: when they are not 16-byte aligned the TMA bulk
+    staging is skipped (plain loads) and the result must not change"""
+    import ctypes as C
+    import torch
+    from circom_2_arithc_b200._lib import lib, EmitInfo, PackedEvents
+    wl = c2a.workloads.mimc_chains(40, rounds=9, variant="late")
+    ev = np.ascontiguousarray(wl.events).copy()
+    if not dense:  # explicit ids: renumber the signals with gaps
+        ev_kind = ev[:, 0] & 0xFF
+        remap = np.arange(int(ev[ev_kind <= 1, 1].max()) + 1, dtype=np.uint32) * 2 + 3
+        ev[ev_kind <= 1, 1] = remap[ev[ev_kind <= 1, 1]]
+        for col in (1, 2, 3):
+            ev[ev_kind == 2, col] = remap[ev[ev_kind == 2, col]]
+        for col in (1, 2):
+            ev[ev_kind == 3, col] = remap[ev[ev_kind == 3, col]]
+    kinds_b, words, flags = c2a.pack_events(ev)
+    assert bool(flags & 1) == dense
+    want = ctx.emit_packed(kinds_b, words, flags)
+    g_want, nos_want = ctx.emitted_fetch()
+    dev = torch.device("cuda", 0)
+    dk = torch.zeros(len(kinds_b) + 64, dtype=torch.uint8, device=dev)
+    dw = torch.zeros(len(words) + 64, dtype=torch.int32, device=dev)
+    for ko, wo in ((0, 0), (1, 1), (3, 2), (16, 5)):
+        dk[ko:ko + len(kinds_b)] = torch.from_numpy(kinds_b).to(dev)
+        dw[wo:wo + len(words)] = torch.from_numpy(words.view(np.int32)).to(dev)
+        pk = PackedEvents(dk.data_ptr() + ko, dw.data_ptr() + 4 * wo, len(kinds_b), len(words), flags, 0)
+        info, bad = EmitInfo(), C.c_uint64(0)
+        assert lib.c2a_emit_packed_resident(ctx.handle, C.byref(pk), C.byref(info), C.byref(bad)) == 0, ctx.last_error()
+        assert info.path == DEVICE and info.node_count == want["node_count"] and info.n_gates == want["n_gates"]
+        ctx._emit_info = {"n_gates": int(info.n_gates), "signal_bound": int(info.signal_bound)}
+        g, nos = ctx.emitted_fetch()
+        assert np.array_equal(g, g_want) and np.array_equal(nos, nos_want), (ko, wo)
+
+
 def test_signal_wires_need_a_built_circuit(ctx, c2a):
     ev = np.asarray([(EV_S, 0, 0, 0), (EV_S, 1, 0, 0), (EV_S, 2, 0, 0), (EV_G, 0, 1, 2)], dtype=np.uint32)
     ctx.emit_events(ev)
