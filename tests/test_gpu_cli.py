@@ -87,3 +87,71 @@ def test_cli_writes_the_three_files(c2a, orc, tmp_path):  # src/main.rs:34-47
     assert lines[0] == f"{G} {want['wire_count']}" and lines[3] == ""
     names = [t.name for t in c2a.AGateType]
     assert lines[4:4 + G] == [f"2 1 {a} {b} {o} {names[op]}" for op, a, b, o in want["gates"].tolist()]
+
+
+MIMC_SRC = """pragma circom 2.0.0;
+template Round(c) {
+    signal input x; signal input k; signal output y;
+    signal t; signal t2; signal t4; signal t6;
+    t <== x + k + c;
+    t2 <== t * t; t4 <== t2 * t2; t6 <== t4 * t2;
+    y <== t6 * t;
+}
+template MiMC(n) {
+    signal input x_in; signal input k; signal output out;
+    component r[n];
+    for (var i = 0; i < n; i++) {
+        r[i] = Round(i);
+        r[i].k <== k;
+        if (i == 0) { r[i].x <== x_in; } else { r[i].x <== r[i - 1].y; }
+    }
+    out <== r[n - 1].y + k;
+}
+template Main(W, n) {
+    signal input in[W]; signal input key; signal output out[W];
+    component m[W];
+    for (var w = 0; w < W; w++) { m[w] = MiMC(n); m[w].x_in <== in[w]; m[w].k <== key; out[w] <== m[w].out; }
+}
+component main = Main(48, 91);
+"""
+
+
+def test_mimc_circom_through_packed_stream_named_wires_and_evaluator(c2a, ctx):
+    """BASELINE config 5 as a real .circom program (MiMC-7 rounds x^7 with c_i = i, u32 arithmetic): front end -> packed stream ->
+    device emitter -> build (gates only) -> named-wire lookup -> GPU evaluator, checked against the function computed in Python"""
+    comp = c2a.compile(None, source=MIMC_SRC, context=ctx)
+    kinds_b, words, flags = c2a.pack_events(comp.events)
+    assert flags == 1                                     # the walker numbers its signals densely (src/runtime.rs:120-125)
+    info = ctx.emit_packed(kinds_b, words, flags)
+    assert info["path"] == 1 and info["n_gates"] == comp.gate_array().shape[0] and info["node_count"] == comp.node_count
+    order, wire, ng, wc = ctx.emitted_build_circuit(comp.input_signals, comp.output_signals, want_order=False, want_wires=False)
+    assert order is None and wire is None
+    ev = comp.events
+    const_sigs = ev[(ev[:, 0] & 0xFF) == 1]
+    in_w = ctx.emitted_signal_wires(comp.input_signals)
+    out_w = ctx.emitted_signal_wires(comp.output_signals)
+    const_w = ctx.emitted_signal_wires(const_sigs[:, 1])
+    circ = comp.build_circuit()                           # host emitter + c2a_build_circuit on the same handle (drops the resident circuit)
+    assert np.array_equal(ng, circ.gate_array) and wc == circ.wire_count
+    names_in = [comp.signal_name(int(s)) for s in comp.input_signals]
+    assert {n: int(w) for n, w in zip(names_in, in_w)} == circ.info.input_name_to_wire_index
+    M = 0xFFFFFFFF
+    key, xs = 0x9E3779B9, [(7919 * (w + 1)) & M for w in range(48)]
+    vals = {}
+    for n, w in zip(names_in, in_w):
+        vals[int(w)] = key if n == "0.key" else xs[int(n[len("0.in["):-1])]
+    for (_, _sid, v, _), w in zip(const_sigs.tolist(), const_w.tolist()):
+        vals[int(w)] = int(v)
+    got = ctx.evaluate(ng, wc, vals)
+
+    def mimc(x):
+        for i in range(91):
+            t = (x + key + i) & M
+            t2 = t * t & M
+            t4 = t2 * t2 & M
+            x = (t4 * t2 & M) * t & M
+        return (x + key) & M
+
+    names_out = [comp.signal_name(int(s)) for s in comp.output_signals]
+    for n, w in zip(names_out, out_w):
+        assert got[int(w)] == mimc(xs[int(n[len("0.out["):-1])]), n
