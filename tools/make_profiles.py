@@ -101,7 +101,9 @@ Launch-list summary (`r01_launches_bench_packed_10M.csv`; kernels only, memsets 
 The dominant kernel agrees in both views: `k_pk_scatter` (phase name `k_ev_scatter`) is the largest entry under ncu and has
 {r['kernel_ms']/d['ms_per_step']:.3f} of the step in the bench (the step also contains the memset nodes and three host round trips).
 '''
-open(P("README.md"), "w").write(readme)
+old_readme = open(P("README.md")).read() if os.path.exists(P("README.md")) else ""
+keep = old_readme[old_readme.index("\n## MiMC-chain sweep"):] if "\n## MiMC-chain sweep" in old_readme else ""
+open(P("README.md"), "w").write(readme + keep)
 open("/tmp/ncu_table.md", "w").write(ncu_table)
 s = open(P("r01_ncu_full_summary.md")).read()
 a = s.index("| kernel | time us |"); b = s.index("Reading it:")
