@@ -103,6 +103,26 @@ def summarize_clocks(lines):
     return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the CPUs next to its GPU.  With 4-8 ranks the e2e leg moves
+    ~0.4 GB per rank and step over PCIe; buffers on the wrong socket make every copy cross the inter-socket link."""
+    try:
+        pr = torch.cuda.get_device_properties(local_rank)
+        dev = "%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id, pr.pci_device_id)
+        base = f"/sys/bus/pci/devices/{dev}"
+        node = int(open(base + "/numa_node").read())
+        cpus = set()
+        for part in open(base + "/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if node >= 0 and cpus:
+            os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_measure(c2a, wl_full, sample_chains, variant, rounds, backend_gates=None):
     """The reference's CPU path, restated (oracle, faithful data structures), single thread like the reference.
     emit: O(G*S) scans (src/compiler.rs:185-195, 219-226, 260-270) on a bounded prefix of the workload;
@@ -195,6 +215,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback on the sort path")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         # NCCL writes its version banner / debug lines to STDOUT by default; rank 0's stdout must be the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
@@ -565,6 +586,7 @@ def main():
                                   "c2a_emitted_build_circuit_device (producer map, deps, DFS-order reconstruction, wire numbering, gather); results stay in HBM",
                    "e2e_scope": "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
                                 "(new_gates D2H inside) -> c2a_emitted_signal_wires (named signals H2D, their wires D2H); e2e_all_arrays also copies order and the whole wire map",
+                   "numa_node": numa,
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts + wire rebase"},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke, "s_per_step": dt / Ke,
