@@ -286,15 +286,16 @@ def main():
     h_counts = torch.zeros(4, dtype=torch.int64).pin_memory()
 
     def reconcile():
-        # global wire numbering across ranks: one NCCL all-gather of (n_in, n_mid, n_out, G); the rebase kernel derives its
-        # offsets from the gathered counts on the device - no host read in between, everything is stream-ordered
+        # global wire numbering across ranks: the build above numbered this rank's circuit without gathering the gates; one NCCL
+        # all-gather of (n_in, n_mid, n_out, G), then the gather kernel applies the global offsets it derives from the gathered
+        # counts on the device - no host read in between, no separate rebase pass, everything is stream-ordered
         h_counts[0], h_counts[1], h_counts[2], h_counts[3] = len(in_ids), wc.value - len(in_ids) - len(out_ids), len(out_ids), G
         with torch.cuda.stream(stream):
             d_counts.copy_(h_counts, non_blocking=True)
             dist.all_gather_into_tensor(d_all, d_counts)
-        st = lib.c2a_rebase_wires_gathered_device(h, vp(d_new.data_ptr()), vp(d_order.data_ptr()), G, vp(d_all.data_ptr()), rank, world)
+        st = lib.c2a_emitted_gather_device(h, vp(d_order.data_ptr()), vp(d_new.data_ptr()), vp(d_all.data_ptr()), rank, world)
         if st != 0:
-            raise RuntimeError(f"c2a_rebase_wires_gathered_device -> {st}: {ctx.last_error()}")
+            raise RuntimeError(f"c2a_emitted_gather_device -> {st}: {ctx.last_error()}")
 
     def device_step(record=False):
         """emit + build with the event stream already resident in HBM; results stay in HBM"""
@@ -304,7 +305,8 @@ def main():
         if record:
             acc_phases("emit:")
         st = lib.c2a_emitted_build_circuit_device(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
-                                                  vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+                                                  vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()) if world == 1 else None,
+                                                  C.byref(wc), C.byref(err))
         if st != 0:
             raise RuntimeError(f"c2a_emitted_build_circuit_device -> {st}: {ctx.last_error()}")
         if record:
@@ -400,7 +402,7 @@ def main():
                     raise RuntimeError(f"c2a_emitted_signal_wires -> {st}: {ctx.last_error()}")
         else:  # results must be rebased to the global numbering before they leave the device
             st = lib.c2a_emitted_build_circuit_device(h, in_ids.ctypes.data_as(vp), len(in_ids), out_ids.ctypes.data_as(vp), len(out_ids),
-                                                      vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+                                                      vp(d_order.data_ptr()), vp(d_wire.data_ptr()), None, C.byref(wc), C.byref(err))
             if st != 0:
                 raise RuntimeError(f"c2a_emitted_build_circuit_device -> {st}: {ctx.last_error()}")
             reconcile()
@@ -587,7 +589,7 @@ def main():
                    "e2e_scope": "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
                                 "(new_gates D2H inside) -> c2a_emitted_signal_wires (named signals H2D, their wires D2H); e2e_all_arrays also copies order and the whole wire map",
                    "numa_node": numa,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts + wire rebase"},
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts, global offsets applied inside the gate gather"},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke, "s_per_step": dt / Ke,
                 "result": ("renumbered gates + wire ids of the %d input/output/constant signals + wire_count (the reference's BristolCircuit contents)" % len(named))

@@ -590,6 +590,48 @@ __global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gat
   }
 }
 
+// K7 for a sharded build: the gather applies the global offsets derived from the all-gathered counts (rank-major
+// {n_in, n_mid, n_out, G}) and shifts order[] to global gate indices in the same pass.  order == nullptr: identity order.
+__global__ void __launch_bounds__(kBlock) k_gather_global(const uint4* __restrict__ gates, uint32_t* __restrict__ order, uint32_t identity, uint32_t G,
+                                                          const uint32_t* __restrict__ wire, uint4* __restrict__ new_gates,
+                                                          const unsigned long long* __restrict__ counts, uint32_t rank, uint32_t world) {
+  uint32_t n_in = 0xFFFFFFFFu, n_mid = 0, off_in = 0, off_mid = 0, off_out = 0, gate_base = 0;
+  if (counts) {
+    unsigned long long tot_in = 0, tot_mid = 0, pre_in = 0, pre_mid = 0, pre_out = 0, pre_g = 0;
+    for (uint32_t r = 0; r < world; ++r) {
+      tot_in += counts[4 * r];
+      tot_mid += counts[4 * r + 1];
+      if (r < rank) { pre_in += counts[4 * r]; pre_mid += counts[4 * r + 1]; pre_out += counts[4 * r + 2]; pre_g += counts[4 * r + 3]; }
+    }
+    n_in = (uint32_t)counts[4 * rank];
+    n_mid = (uint32_t)counts[4 * rank + 1];
+    off_in = (uint32_t)pre_in;
+    off_mid = (uint32_t)(tot_in + pre_mid) - n_in;
+    off_out = (uint32_t)(tot_in + tot_mid + pre_out) - n_in - n_mid;
+    gate_base = (uint32_t)pre_g;
+  }
+  auto fix = [&](uint32_t w) { return !counts ? w : (w < n_in ? w + off_in : (w < n_in + n_mid ? w + off_mid : w + off_out)); };
+  const uint32_t stride = gridDim.x * kBlock;
+  for (uint32_t k0 = blockIdx.x * kBlock + threadIdx.x; k0 < G; k0 += stride * kGatherIlp) {
+    uint32_t g[kGatherIlp];
+    uint4 gt[kGatherIlp];
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) { uint32_t k = min(k0 + i * stride, G - 1); g[i] = identity ? k : order[k]; }
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) gt[i] = identity ? ldg_stream(gates + g[i]) : __ldg(gates + g[i]);
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) { gt[i].y = __ldg(wire + gt[i].y); gt[i].z = __ldg(wire + gt[i].z); gt[i].w = __ldg(wire + gt[i].w); }
+#pragma unroll
+    for (int i = 0; i < kGatherIlp; ++i) {
+      uint32_t k = k0 + i * stride;
+      if (k < G) {
+        stg_stream(new_gates + k, make_uint4(gt[i].x, fix(gt[i].y), fix(gt[i].z), fix(gt[i].w)));
+        if (order && gate_base) order[k] = g[i] + gate_base;  // each position is read and written by this thread only
+      }
+    }
+  }
+}
+
 // Multi-GPU: local -> global wire ids / gate indices for one independently sorted component subtree.
 __global__ void __launch_bounds__(kBlock) k_rebase(uint4* __restrict__ new_gates, uint32_t* __restrict__ order, uint32_t G, uint32_t n_in,
                                                    uint32_t n_mid, uint32_t off_in, uint32_t off_mid, uint32_t off_out, uint32_t gate_base) {

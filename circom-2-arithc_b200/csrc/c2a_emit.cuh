@@ -1128,8 +1128,9 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
     }
   }
   h->emitted.wire = nullptr;
-  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, nullptr, io_nodes, io_flag);
-  if (st == C2A_OK) h->emitted.wire = d_wire;  // stays valid until the next call that carves the slab
+  bool identity = true;
+  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, &identity, io_nodes, io_flag);
+  if (st == C2A_OK) { h->emitted.wire = d_wire; h->emitted.identity = identity; }  // stay valid until the next call that carves the slab
   if (st == C2A_OK && !outputs_on_device) {
     phase_begin(h, "d2h");
     if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
@@ -1174,6 +1175,19 @@ int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n,
   if (!cuda_ok(h, cudaMemcpyAsync(wires_out, d_out, 4 * n, cudaMemcpyDeviceToHost, s), "wires D2H")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaStreamSynchronize(s), "signal wires")) return C2A_ERR_CUDA;
   return cuda_ok(h, cudaGetLastError(), "k_sig_wires") ? C2A_OK : C2A_ERR_CUDA;
+}
+
+int c2a_emitted_gather_device(c2a_handle* h, uint32_t* d_order, c2a_gate* d_new_gates, const uint64_t* d_counts, uint32_t rank, uint32_t world) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!h->emitted.valid || !h->emitted.wire) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no built circuit is resident on this handle");
+  if (!d_new_gates || (d_counts && rank >= world)) return fail(h, C2A_ERR_INVALID_ARGUMENT, "bad argument");
+  if (!h->emitted.identity && !d_order) return fail(h, C2A_ERR_INVALID_ARGUMENT, "the build's order is not the identity: pass its order array");
+  if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
+  const uint32_t G = (uint32_t)h->emitted.G;
+  if (G) LAUNCH(h, k_gather_global, grid_for(h, (const void*)k_gather_global, kBlock, ((uint64_t)G + kGatherIlp - 1) / kGatherIlp), kBlock,
+                (const uint4*)(h->slab + h->emitted.gates_off), d_order, h->emitted.identity ? 1u : 0u, G, h->emitted.wire, (uint4*)d_new_gates,
+                (const unsigned long long*)d_counts, rank, world);
+  return cuda_ok(h, cudaGetLastError(), "k_gather_global") ? C2A_OK : C2A_ERR_CUDA;
 }
 
 int c2a_emitted_signal_wires_device(c2a_handle* h, const uint32_t* d_signals, uint64_t n, uint32_t* d_wires_out) {

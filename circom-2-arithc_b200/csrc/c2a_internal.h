@@ -47,6 +47,7 @@ struct c2a_handle {
     uint32_t node_count = 0;
     uint32_t signal_bound = 0;
     const uint32_t* wire = nullptr;  // wire map of the last successful build on this circuit (device; slab scratch or the caller's array)
+    bool identity = true;            // that build's DFS order was 0..G-1
   } emitted;
   struct c2a_compiler* host_comp = nullptr;  // kept alive when the exact host emitter had to run (sparse ids)
 };

@@ -206,6 +206,13 @@ int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals,
                                      uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
                                      uint64_t* err_index);
 
+/* Sharded builds, second half: after c2a_emitted_build_circuit_device(..., d_new_gates = NULL, ...) numbered the
+ * rank's own circuit and the ranks all-gathered their (n_in, n_mid, n_out, G) counts, this gathers the renumbered gates and
+ * applies the global offsets on the fly - no separate rebase pass over the gates.  d_order is the order array of that build
+ * (its entries are shifted to global gate indices; may be NULL); d_counts as for c2a_rebase_wires_gathered_device, or NULL for a
+ * plain gather (world = 1).  Enqueue-only. */
+int c2a_emitted_gather_device(c2a_handle*, uint32_t* d_order, c2a_gate* d_new_gates, const uint64_t* d_counts, uint32_t rank, uint32_t world);
+
 /* Wire ids of selected signals after c2a_emitted_build_circuit[_device] on this handle (what Compiler::build_circuit looks up for
  * its input / output / constant name maps, src/compiler.rs:323-383, 466-493): wires_out[i] = wire of the node holding
  * signals[i], C2A_NONE when the signal was never declared or its node has no wire.  With this a caller that wants the

@@ -358,3 +358,47 @@ def test_named_wires_on_the_device_and_their_rebase(ctx, c2a):
     w = want.astype(np.int64)
     exp = np.where(w == 0xFFFFFFFF, w, np.where(w < n_in, w + off_in, np.where(w < n_in + n_mid, w + off_mid, w + off_out)))
     assert np.array_equal(d_out.cpu().numpy().view(np.uint32).astype(np.int64), exp)
+
+
+@pytest.mark.parametrize("variant", ["late", "inorder"])
+def test_two_phase_sharded_build_gather_applies_global_offsets(ctx, c2a, variant):
+    """c2a_emitted_build_circuit_device(new_gates = NULL) + c2a_emitted_gather_device(gathered counts) must equal the one-call
+    build followed by c2a_rebase_wires_device with the host offsets; counts = NULL must equal the one-call build itself"""
+    import ctypes as C
+    import torch
+    lib, vp = c2a.lib, C.c_void_p
+    wl = c2a.workloads.mimc_chains(9, rounds=13, variant=variant)
+    ev = np.ascontiguousarray(wl.events)
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    info = ctx.emit_events(ev)
+    G, nb = info["n_gates"], info["node_count"] + 1
+    order, wire, ng, wc = ctx.emitted_build_circuit(ins, outs)     # one call, host buffers: the reference result
+    assert (variant == "inorder") == bool(np.array_equal(order, np.arange(G)))
+    dev = torch.device("cuda", 0)
+    d_order = torch.empty(G, dtype=torch.int32, device=dev)
+    d_wire = torch.empty(nb, dtype=torch.int32, device=dev)
+    d_new = torch.empty((G, 4), dtype=torch.int32, device=dev)
+    wc2, err = C.c_uint32(0), C.c_uint64(0)
+
+    def phase1():
+        assert lib.c2a_emitted_build_circuit_device(ctx.handle, ins.ctypes.data_as(vp), len(ins), outs.ctypes.data_as(vp), len(outs), vp(d_order.data_ptr()),
+                                                    vp(d_wire.data_ptr()), None, C.byref(wc2), C.byref(err)) == 0, ctx.last_error()
+        assert wc2.value == wc
+
+    phase1()
+    assert lib.c2a_emitted_gather_device(ctx.handle, vp(d_order.data_ptr()), vp(d_new.data_ptr()), None, 0, 1) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_new.cpu().numpy().view(np.uint32), ng) and np.array_equal(d_order.cpu().numpy().view(np.uint32), order)
+    n_in, n_out = len(ins), len(outs)
+    counts = np.array([[5, 17, 2, 40], [n_in, wc - n_in - n_out, n_out, G], [1, 3, 1, 6]], dtype=np.int64)
+    off_in, off_mid, off_out, gate_base = c2a.sharding.rebase_offsets(counts, 1, shared_io=False)
+    w = ng.astype(np.int64)
+    n_mid = wc - n_in - n_out
+    fix = lambda a: np.where(a < n_in, a + off_in, np.where(a < n_in + n_mid, a + off_mid, a + off_out))
+    want = np.stack([w[:, 0], fix(w[:, 1]), fix(w[:, 2]), fix(w[:, 3])], axis=1)
+    phase1()
+    d_counts = torch.from_numpy(counts).to(dev)
+    assert lib.c2a_emitted_gather_device(ctx.handle, vp(d_order.data_ptr()), vp(d_new.data_ptr()), vp(d_counts.data_ptr()), 1, 3) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_new.cpu().numpy().view(np.uint32).astype(np.int64), want)
+    assert np.array_equal(d_order.cpu().numpy().view(np.uint32).astype(np.int64), order.astype(np.int64) + gate_base)
