@@ -616,7 +616,11 @@ __global__ void __launch_bounds__(kBlock) k_gather_global(const uint4* __restric
     uint32_t g[kGatherIlp];
     uint4 gt[kGatherIlp];
 #pragma unroll
-    for (int i = 0; i < kGatherIlp; ++i) { uint32_t k = min(k0 + i * stride, G - 1); g[i] = identity ? k : order[k]; }
+    for (int i = 0; i < kGatherIlp; ++i) {
+      // a position past the end must NOT read order[]: its owner may already have shifted that entry to a global index
+      uint32_t k = k0 + i * stride;
+      g[i] = k < G ? (identity ? k : order[k]) : 0u;
+    }
 #pragma unroll
     for (int i = 0; i < kGatherIlp; ++i) gt[i] = identity ? ldg_stream(gates + g[i]) : __ldg(gates + g[i]);
 #pragma unroll

@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
     for (int i = 0; i < kFinIlp; ++i) {
       uint32_t s = min(s0 + i * stride, S - 1);
       t[i] = sig_t ? sig_t[s] : 0u;  // dense ids: no declaration table, every id below S is declared
-      m[i] = sig_meta[s];
+      m[i] = t[i] != kNone ? sig_meta[s] : make_uint2(0, 0);  // (an undeclared id has no record: do not read uninitialised memory)
       om[i] = outmark[s];
       r0[i] = parent[s];
     }

@@ -390,7 +390,7 @@ def test_two_phase_sharded_build_gather_applies_global_offsets(ctx, c2a, variant
     torch.cuda.synchronize()
     assert np.array_equal(d_new.cpu().numpy().view(np.uint32), ng) and np.array_equal(d_order.cpu().numpy().view(np.uint32), order)
     n_in, n_out = len(ins), len(outs)
-    counts = np.array([[5, 17, 2, 40], [n_in, wc - n_in - n_out, n_out, G], [1, 3, 1, 6]], dtype=np.int64)
+    counts = np.array([[5, 17, 2, 3_000_000_000], [n_in, wc - n_in - n_out, n_out, G], [1, 3, 1, 6]], dtype=np.int64)  # a huge gate base: a stale read of a shifted order entry would fault
     off_in, off_mid, off_out, gate_base = c2a.sharding.rebase_offsets(counts, 1, shared_io=False)
     w = ng.astype(np.int64)
     n_mid = wc - n_in - n_out
