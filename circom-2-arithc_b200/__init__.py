@@ -9,4 +9,4 @@ from ._lib import lib, load_error, C2AError, CircuitError, Status, have_device  
 from .compiler import AGateType, Compiler, BristolCircuit, Gate, DeviceContext, topological_sort, pack_events, unpack_events  # noqa: F401
 from . import workloads  # noqa: F401
 from . import sharding  # noqa: F401
-from .program import compile, Args, ProgramError, generate_circuit_report, write_outputs, bristol_text, main as cli_main  # noqa: F401,E402
+from .program import compile, Args, ProgramError, DeviceCompiler, generate_circuit_report, write_outputs, bristol_text, main as cli_main  # noqa: F401,E402

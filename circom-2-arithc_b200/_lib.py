@@ -98,6 +98,7 @@ _SIGS = {
     "c2a_emit_events_resident": (i32, [vp, vp, u64, vp, u64p]),
     "c2a_emitted_gather_device": (i32, [vp, vp, vp, vp, u32, u32]),
     "c2a_emitted_signal_wires": (i32, [vp, vp, u64, vp]),
+    "c2a_emitted_signal_nodes": (i32, [vp, vp, u64, vp]),
     "c2a_emitted_signal_wires_device": (i32, [vp, vp, u64, vp]),
     "c2a_rebase_wire_ids_gathered_device": (i32, [vp, vp, u64, vp, u32, u32]),
     "c2a_pack_events": (u64, [vp, u64, vp, vp, u32p]),

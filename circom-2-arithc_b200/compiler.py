@@ -273,6 +273,13 @@ class DeviceContext:
         _raise(lib.c2a_emitted_signal_wires(self._h, _ptr(sig), sig.shape[0], _ptr(out)), self.last_error())
         return out
 
+    def emitted_signal_nodes(self, signals) -> np.ndarray:
+        """c2a_emitted_signal_nodes: node ids of the given signals of the resident emitted circuit (0 = never declared)."""
+        sig = np.ascontiguousarray(signals, dtype=np.uint32)
+        out = np.empty(sig.shape[0], dtype=np.uint32)
+        _raise(lib.c2a_emitted_signal_nodes(self._h, _ptr(sig), sig.shape[0], _ptr(out)), self.last_error())
+        return out
+
     def emitted_fetch(self, want_gates=True, want_nodes=True):
         """-> (gates (G,4) u32 node ids in emission order, node_of_signal[signal_bound])"""
         info = self._emit_info

@@ -447,16 +447,6 @@ __device__ __forceinline__ uint32_t uf_find(uint32_t* __restrict__ parent, uint3
   return r;
 }
 
-template <typename T>
-__device__ __forceinline__ void warp_append_t(bool ready, const T& item, T* __restrict__ queue, uint32_t* __restrict__ tail) {
-  uint32_t m = __ballot_sync(0xFFFFFFFFu, ready);
-  if (!m) return;
-  int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-  uint32_t base = 0;
-  if (lane == leader) base = atomicAdd(tail, (uint32_t)__popc(m));
-  base = __shfl_sync(0xFFFFFFFFu, base, leader);
-  if (ready) queue[base + __popc(m & ((1u << lane) - 1))] = item;
-}
 
 __device__ __forceinline__ void red_min_u32(uint32_t* p, uint32_t v) {
   if (*reinterpret_cast<volatile uint32_t*>(p) > v) atomicMin(p, v);  // values only decrease within a round: a stale read costs one RED
@@ -499,7 +489,7 @@ __global__ void __launch_bounds__(kBlock) k_msf_pick(const uint2* __restrict__ c
         out = make_uint4(e, cu, cv, 0);
       }
     }
-    warp_append_t(keep, out, cand, n_cand);
+    warp_append(keep, out, cand, n_cand);
   }
 }
 
@@ -537,7 +527,7 @@ __global__ void __launch_bounds__(kBlock) k_msf_hook_t(const uint4* __restrict__
       uint32_t m = __ballot_sync(0xFFFFFFFFu, c.x != kNone && !keep);
       if (lane == 0 && m) atomicOr(eff + (i0 >> 5), m);
     }
-    warp_append_t(keep, e, cur, n_cur);
+    warp_append(keep, e, cur, n_cur);
   }
 }
 
@@ -665,7 +655,7 @@ __global__ void __launch_bounds__(kBlock) k_sig_wires(const uint32_t* __restrict
   for (uint64_t i = (uint64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += (uint64_t)gridDim.x * kBlock) {
     uint32_t s = sigs[i];
     uint32_t nd = nos ? (s < S ? nos[s] : 0u) : s;  // nos == nullptr: the list already holds node ids
-    out[i] = nd && nd < node_bound ? wire[nd] : kNone;
+    out[i] = wire ? (nd && nd < node_bound ? wire[nd] : kNone) : nd;  // wire == nullptr: the node ids themselves
   }
 }
 
@@ -1145,13 +1135,24 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   return st;
 }
 
-int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n, uint32_t* wires_out) {
+// selected signals -> wires (want_wires) or -> node ids, host lists in and out
+static int emitted_signal_lookup(c2a_handle* h, const uint32_t* signals, uint64_t n, uint32_t* out_host, bool want_wires) {
   if (!h) return C2A_ERR_INVALID_ARGUMENT;
-  if (!h->emitted.valid || !h->emitted.wire) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no built circuit is resident on this handle");
+  if (!h->emitted.valid || (want_wires && !h->emitted.wire))
+    return fail(h, C2A_ERR_INVALID_ARGUMENT, want_wires ? "no built circuit is resident on this handle" : "no emitted circuit is resident on this handle");
   if (n == 0) return C2A_OK;
-  if (!signals || !wires_out) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  if (!signals || !out_host) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
   if (!cuda_ok(h, cudaSetDevice(h->device), "cudaSetDevice")) return C2A_ERR_CUDA;
   cudaStream_t s = h->stream;
+  const uint32_t* nos = h->emitted.nos_valid ? (const uint32_t*)(h->slab + h->emitted.nos_off) : nullptr;
+  std::vector<uint32_t> nodes;
+  const uint32_t* src = signals;
+  if (!nos) {  // sparse ids: the host emitter that produced the circuit knows the nodes
+    nodes.resize(n);
+    c2a_signal_nodes(h->host_comp, signals, n, nodes.data());
+    if (!want_wires) { memcpy(out_host, nodes.data(), 4 * n); return C2A_OK; }
+    src = nodes.data();
+  }
   // the event staging buffer is idle between calls: use it for the two lists (the slab holds the wire map itself)
   const size_t need = 2 * align256(4 * n);
   if (need > h->ev_bytes) {
@@ -1161,20 +1162,18 @@ int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n,
   }
   uint32_t* d_sig = (uint32_t*)h->ev_buf;
   uint32_t* d_out = (uint32_t*)(h->ev_buf + align256(4 * n));
-  const uint32_t* nos = h->emitted.nos_valid ? (const uint32_t*)(h->slab + h->emitted.nos_off) : nullptr;
-  std::vector<uint32_t> nodes;
-  const uint32_t* src = signals;
-  if (!nos) {  // sparse ids: the host emitter that produced the circuit knows the nodes
-    nodes.resize(n);
-    c2a_signal_nodes(h->host_comp, signals, n, nodes.data());
-    src = nodes.data();
-  }
   if (!cuda_ok(h, cudaMemcpyAsync(d_sig, src, 4 * n, cudaMemcpyHostToDevice, s), "signal list H2D")) return C2A_ERR_CUDA;
-  LAUNCH(h, k_sig_wires, grid_for(h, (const void*)k_sig_wires, kBlock, n), kBlock, d_sig, n, h->emitted.signal_bound, nos, h->emitted.wire,
-         h->emitted.node_count + 1, d_out);
-  if (!cuda_ok(h, cudaMemcpyAsync(wires_out, d_out, 4 * n, cudaMemcpyDeviceToHost, s), "wires D2H")) return C2A_ERR_CUDA;
-  if (!cuda_ok(h, cudaStreamSynchronize(s), "signal wires")) return C2A_ERR_CUDA;
+  LAUNCH(h, k_sig_wires, grid_for(h, (const void*)k_sig_wires, kBlock, n), kBlock, d_sig, n, h->emitted.signal_bound, nos,
+         want_wires ? h->emitted.wire : (const uint32_t*)nullptr, h->emitted.node_count + 1, d_out);
+  if (!cuda_ok(h, cudaMemcpyAsync(out_host, d_out, 4 * n, cudaMemcpyDeviceToHost, s), "lookup D2H")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "signal lookup")) return C2A_ERR_CUDA;
   return cuda_ok(h, cudaGetLastError(), "k_sig_wires") ? C2A_OK : C2A_ERR_CUDA;
+}
+int c2a_emitted_signal_wires(c2a_handle* h, const uint32_t* signals, uint64_t n, uint32_t* wires_out) {
+  return emitted_signal_lookup(h, signals, n, wires_out, true);
+}
+int c2a_emitted_signal_nodes(c2a_handle* h, const uint32_t* signals, uint64_t n, uint32_t* nodes_out) {
+  return emitted_signal_lookup(h, signals, n, nodes_out, false);
 }
 
 int c2a_emitted_gather_device(c2a_handle* h, uint32_t* d_order, c2a_gate* d_new_gates, const uint64_t* d_counts, uint32_t rank, uint32_t world) {

@@ -18,8 +18,8 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import lib
-from .compiler import AGateType, BristolCircuit, Compiler, DeviceContext, EVENT_DTYPE
+from ._lib import lib, CircuitError, PackedEvents, Status
+from .compiler import AGateType, BristolCircuit, CircuitInfo, Compiler, ConstantInfo, DeviceContext, EVENT_DTYPE, default_context
 
 
 class ProgramError(Exception):
@@ -42,10 +42,98 @@ def build_output(output_path: str, filename: str, ext: str) -> str:  # src/cli.r
     return os.path.join(output_path, f"{filename}.{ext}")
 
 
-def compile(args, *, source: Optional[str] = None, include_dir: str = ".", device: int = 0, context: Optional[DeviceContext] = None) -> Compiler:
-    """src/program.rs::compile.  `args` is an Args or a path; `source=` compiles a string instead of a file."""
+class DeviceCompiler:
+    """compile(..., emitter="device"): the walk only RECORDS the add_signal / add_gate / add_connection calls (no host union-find);
+    build_circuit() replays them on the GPU as a packed stream (c2a_emit_packed_device), numbers and gathers the gates
+    (c2a_emitted_build_circuit) and looks up the wires of the named signals (c2a_emitted_signal_nodes / _wires) - the same
+    BristolCircuit, the same CircuitError conditions as Compiler.build_circuit (src/compiler.rs:321-494)."""
+
+    def __init__(self, prog, device: int, context: Optional[DeviceContext]):
+        self._prog, self._device, self._ctx = prog, device, context
+        self.value_type = "sint"
+        n = int(lib.c2a_program_num_events(prog))
+        self.events = np.zeros((n, 4), dtype=np.uint32)
+        if n:
+            C.memmove(self.events.ctypes.data, lib.c2a_program_events(prog), 16 * n)
+        ni, no = int(lib.c2a_program_num_inputs(prog)), int(lib.c2a_program_num_outputs(prog))
+        as_u32 = lambda p, k: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(k,)).copy() if k else np.zeros(0, np.uint32)
+        self.input_signals, self.output_signals = as_u32(lib.c2a_program_inputs(prog), ni), as_u32(lib.c2a_program_outputs(prog), no)
+        pk = PackedEvents()
+        lib.c2a_program_packed(prog, C.byref(pk))
+        self._kinds = np.ctypeslib.as_array(C.cast(pk.kinds, C.POINTER(C.c_uint8)), shape=(n,)).copy() if n else np.zeros(0, np.uint8)
+        self._words = as_u32(pk.words, int(pk.n_words))
+        self._flags = int(pk.flags)
+
+    def __del__(self):
+        try:
+            if self._prog:
+                lib.c2a_program_free(self._prog)
+                self._prog = None
+        except Exception:
+            pass
+
+    def update_type(self, value_type: str):
+        self.value_type = value_type
+
+    def signal_name(self, sid: int) -> str:
+        p = lib.c2a_program_signal_name(self._prog, int(sid))
+        return p.decode() if p is not None else ""
+
+    def build_circuit(self) -> BristolCircuit:
+        ctx = self._ctx or default_context(self._device)
+        info = ctx.emit_packed(self._kinds, self._words, self._flags)        # raises the reference's CircuitError on a bad stream
+        ins, outs = self.input_signals, self.output_signals
+        in_names, out_names = [self.signal_name(s) for s in ins], [self.signal_name(s) for s in outs]
+        # src/compiler.rs:327-383: input / output <=> node, walked in ascending signal id
+        seen_in, seen_out = set(), set()
+        nodes = ctx.emitted_signal_nodes(np.concatenate([ins, outs]))
+        in_nodes, out_nodes = nodes[:len(ins)], nodes[len(ins):]
+        merged = sorted([(int(s), 0, i) for i, s in enumerate(ins)] + [(int(s), 1, i) for i, s in enumerate(outs)])
+        for _sid, kind, i in merged:
+            name, seen = (in_names[i], seen_in) if kind == 0 else (out_names[i], seen_out)
+            if name in seen:                                                 # :337-341, :347-351
+                raise CircuitError(Status.INCONSISTENCY, f"Duplicate {'input' if kind == 0 else 'output'} {name}")
+            seen.add(name)
+        node_to_input = {int(nd): nm for nd, nm in zip(in_nodes, in_names)}
+        for nd, nm in zip(out_nodes, out_names):                             # :363-383
+            if int(nd) in node_to_input:
+                raise CircuitError(Status.INCONSISTENCY, f"Node {int(nd)} used for both input {node_to_input[int(nd)]} and output {nm}")
+        order, _wire, gates, wire_count = ctx.emitted_build_circuit(ins, outs, want_wires=False)
+        ev = self.events
+        consts = ev[(ev[:, 0] & 0xFF) == 1]
+        consts = consts[np.argsort(consts[:, 1], kind="stable")]
+        named = ctx.emitted_signal_wires(np.concatenate([ins, outs, consts[:, 1]]).astype(np.uint32))
+        w_in, w_out, w_c = named[:len(ins)], named[len(ins):len(ins) + len(outs)], named[len(ins) + len(outs):]
+        ci = CircuitInfo()
+        ci.input_name_to_wire_index = {nm: int(w) for nm, w in sorted(zip(in_names, w_in.tolist()))}
+        for (_k, sid, val, _z), w in sorted(((tuple(r), w) for r, w in zip(consts.tolist(), w_c.tolist())), key=lambda t: f"{self.signal_name(t[0][1])}_{t[0][1]}"):
+            key = f"{self.signal_name(sid)}_{sid}"                           # :356
+            if w == 0xFFFFFFFF:
+                raise CircuitError(Status.REFERENCE_PANIC, f"constant {key} has no wire (the reference panics at src/compiler.rs:473)")
+            ci.constants[key] = ConstantInfo(str(int(val)), int(w))
+        ci.output_name_to_wire_index = {nm: int(w) for nm, w in sorted(zip(out_names, w_out.tolist()))}
+        self.emit_info = info
+        return BristolCircuit(wire_count=int(wire_count), info=ci, gate_array=gates, order=order)
+
+
+def compile(args, *, source: Optional[str] = None, include_dir: str = ".", device: int = 0, context: Optional[DeviceContext] = None,
+            emitter: str = "host"):
+    """src/program.rs::compile.  `args` is an Args or a path; `source=` compiles a string instead of a file.
+    emitter="host": the walk drives the native union-find emitter (a Compiler with names, nodes and the report);
+    emitter="device": the walk only records its calls and build_circuit() replays them on the GPU (a DeviceCompiler)."""
     if not isinstance(args, Args):
         args = Args(input=str(args)) if args is not None else Args()
+    if emitter == "device":
+        prog = lib.c2a_program_new()
+        st = (lib.c2a_program_compile_source(prog, source.encode(), include_dir.encode(), None) if source is not None
+              else lib.c2a_program_compile_file(prog, os.fsencode(args.input), None))
+        if st != 0:
+            text = lib.c2a_program_error(prog).decode()
+            lib.c2a_program_free(prog)
+            raise ProgramError(st, text)
+        dc = DeviceCompiler(prog, device, context)
+        dc.update_type(args.value_type)
+        return dc
     comp = Compiler(device=device, context=context)
     prog = lib.c2a_program_new()
     try:

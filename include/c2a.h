@@ -218,6 +218,9 @@ int c2a_emitted_gather_device(c2a_handle*, uint32_t* d_order, c2a_gate* d_new_ga
  * signals[i], C2A_NONE when the signal was never declared or its node has no wire.  With this a caller that wants the
  * reference's result (gates + named wires) can pass NULL for order_out and wire_of_node and skip their device->host copies. */
 int c2a_emitted_signal_wires(c2a_handle*, const uint32_t* signals, uint64_t n, uint32_t* wires_out);
+/* node ids of selected signals of the resident emitted circuit (0 = never declared): the input / output <=> node pairing of
+ * Compiler::build_circuit (src/compiler.rs:327-383) without copying the whole signal -> node map.  Needs only the emit. */
+int c2a_emitted_signal_nodes(c2a_handle*, const uint32_t* signals, uint64_t n, uint32_t* nodes_out);
 /* same with DEVICE pointers for both lists; enqueue-only (dense signal ids only: the signal -> node map must be resident) */
 int c2a_emitted_signal_wires_device(c2a_handle*, const uint32_t* d_signals, uint64_t n, uint32_t* d_wires_out);
 

@@ -155,3 +155,31 @@ def test_mimc_circom_through_packed_stream_named_wires_and_evaluator(c2a, ctx):
     names_out = [comp.signal_name(int(s)) for s in comp.output_signals]
     for n, w in zip(names_out, out_w):
         assert got[int(w)] == mimc(xs[int(n[len("0.out["):-1])]), n
+
+
+def _same_circuit(a, b):
+    assert a.wire_count == b.wire_count
+    assert np.array_equal(a.gate_array, b.gate_array) and np.array_equal(a.order, b.order)
+    assert a.info.input_name_to_wire_index == b.info.input_name_to_wire_index
+    assert a.info.output_name_to_wire_index == b.info.output_name_to_wire_index
+    assert {k: (v.value, v.wire_index) for k, v in a.info.constants.items()} == {k: (v.value, v.wire_index) for k, v in b.info.constants.items()}
+    assert list(a.info.constants) == list(b.info.constants)  # same (sorted) key order as the JSON of the host path
+
+
+def test_compile_with_the_device_emitter_gives_the_same_bristol_circuit(c2a, ctx):
+    """compile(emitter="device"): the walk only records its calls, build_circuit() replays them on the GPU (packed stream) and
+    looks the named wires up - same BristolCircuit and same CircuitError as the host-emitter Compiler (src/compiler.rs:321-494)"""
+    sources = [fx.ADD_ZERO, fx.INFIX_OPS, fx.MAT_ELEM_MUL, fx.SUM, fx.X_EQ_X, fx.CONSTANT_SUM, fx.DIRECT_OUTPUT,
+               fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), MIMC_SRC.replace("Main(48, 91)", "Main(5, 7)")]
+    for src in sources:
+        host = c2a.compile(None, source=src, context=ctx).build_circuit()
+        dev = c2a.compile(None, source=src, context=ctx, emitter="device")
+        _same_circuit(dev.build_circuit(), host)
+        assert dev.emit_info["path"] == 1
+    with pytest.raises(c2a.CircuitError) as e_host:
+        c2a.compile(None, source=fx.PREFIX_OPS, context=ctx).build_circuit()
+    with pytest.raises(c2a.CircuitError) as e_dev:
+        c2a.compile(None, source=fx.PREFIX_OPS, context=ctx, emitter="device").build_circuit()
+    assert str(e_dev.value) == str(e_host.value) and "used for both input 0.complement" in str(e_dev.value)
+    with pytest.raises(c2a.ProgramError):
+        c2a.compile(None, source="template T() { signal input a; a === 1; } component main = T();", emitter="device")
