@@ -65,3 +65,16 @@ def test_program_packed_matches_events(c2a):
         assert np.array_equal(k2, kinds) and np.array_equal(w2, words) and f2 == pk.flags
     finally:
         lib.c2a_program_free(p)
+
+
+def test_device_compiler_records_without_a_gpu(c2a):
+    """compile(emitter="device") needs no device until build_circuit(): it holds the recorded calls (both forms), the tagged
+    inputs / outputs and the names"""
+    src = "template T(){ signal input a; signal input b; signal output c; c <== a*b + 3; } component main = T();"
+    dc = c2a.compile(None, source=src, emitter="device")
+    host = c2a.compile(None, source=src) if c2a.have_device() else None
+    assert isinstance(dc, c2a.DeviceCompiler) and dc._flags == 1
+    assert np.array_equal(c2a.unpack_events(dc._kinds, dc._words, dc._flags), _zero_values(dc.events))
+    assert [dc.signal_name(s) for s in dc.input_signals] == ["0.a", "0.b"] and [dc.signal_name(s) for s in dc.output_signals] == ["0.c"]
+    if host is not None:
+        assert np.array_equal(host.events, dc.events)
