@@ -75,6 +75,8 @@ def test_device_compiler_records_without_a_gpu(c2a):
     host = c2a.compile(None, source=src) if c2a.have_device() else None
     assert isinstance(dc, c2a.DeviceCompiler) and dc._flags == 1
     assert np.array_equal(c2a.unpack_events(dc._kinds, dc._words, dc._flags), _zero_values(dc.events))
-    assert [dc.signal_name(s) for s in dc.input_signals] == ["0.a", "0.b"] and [dc.signal_name(s) for s in dc.output_signals] == ["0.c"]
+    assert [dc.signal_name(s) for s in dc.input_signals] == ["0.a", "0.b"]
+    # the reference tags outputs by PREFIX match on "0.c" (src/program.rs:62-66), which also catches the constant's name
+    assert [dc.signal_name(s) for s in dc.output_signals] == ["0.c", "0.const_signal_3"]
     if host is not None:
         assert np.array_equal(host.events, dc.events)
