@@ -1141,9 +1141,19 @@ int c2a_create(int device, c2a_handle** out) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete h; return C2A_ERR_CUDA; }
+  if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();
+    if (h->stream2) cudaStreamDestroy(h->stream2);
+    cudaStreamDestroy(h->stream);
+    delete h;
+    return C2A_ERR_CUDA;
+  }
   h->h_pinned_bytes = 1 << 16;
   if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
+    cudaEventDestroy(h->ev_side);
+    cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
     return C2A_ERR_CUDA;
@@ -1161,6 +1171,9 @@ void c2a_destroy(c2a_handle* h) {
   if (h->ev_buf) cudaFree(h->ev_buf);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  cudaStreamSynchronize(h->stream2);
+  cudaEventDestroy(h->ev_side);
+  cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);
   delete h;
 }

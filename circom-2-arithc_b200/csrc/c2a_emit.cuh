@@ -786,6 +786,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint2 *sig_meta = nullptr, *conn = nullptr;
   uint4* egates = nullptr;
   uint8_t* outmark = nullptr;
+  uint32_t *side_best = nullptr, *side_parent = nullptr, *side_nidf = nullptr, *side_eff = nullptr, *side_effp = nullptr;
   const uint4* d_ev = nullptr;
   uint64_t G = 0, C = 0, n_sig = 0;
   uint32_t S = 0, flags = 0;
@@ -793,7 +794,13 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t pk_kbytes = pk ? align256(n + 4) : 0;  // packed staging: kinds, then words
     const size_t ev_copy = pk ? (src.pk_on_device ? 0 : pk_kbytes + align256(4 * pk->n_words + 4)) : (ev_dev ? 0 : align256(16 * n));
-    const size_t ev_need = ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
+    // Dense packed stream: S = n - G - C and n_words = 3G + 2C give S <= n - n_words/3 and C <= n_words/2 BEFORE anything is
+    // counted, so the union-find arrays can be carved (here, in the staging allocation) and initialised on the side stream
+    // while the count / scatter kernels run; the main stream joins just before the first Boruvka kernel.
+    const uint64_t S_side = pk_dense ? n - (pk->n_words + 2) / 3 + 1 : 0;
+    const uint64_t effw_side = pk_dense ? pk->n_words / 64 + 4 : 0;
+    const size_t side_bytes = pk_dense ? 3 * align256(4 * S_side) + 2 * align256(4 * effw_side) : 0;
+    const size_t ev_need = side_bytes + ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
                            align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
     if (ev_need > h->ev_bytes) {
       if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
@@ -816,6 +823,19 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     conn_sb = (uint32_t*)take(4 * n);
     conn = (uint2*)take(8 * n);
     outmark = (uint8_t*)take(S_cap);
+    if (pk_dense) {
+      side_best = (uint32_t*)take(4 * S_side);
+      side_parent = (uint32_t*)take(4 * S_side);
+      side_nidf = (uint32_t*)take(4 * S_side);
+      side_eff = (uint32_t*)take(4 * effw_side);
+      side_effp = (uint32_t*)take(4 * effw_side);
+      cudaMemsetAsync(side_best, 0xFF, 4 * S_side, h->stream2);
+      cudaMemsetAsync(side_nidf, 0, 4 * S_side, h->stream2);
+      cudaMemsetAsync(side_eff, 0, 4 * effw_side, h->stream2);
+      k_iota<<<grid_for(h, (const void*)k_iota, kBlock, S_side), kBlock, 0, h->stream2>>>(side_parent, (uint32_t)S_side);
+      h->launches++;
+      cudaEventRecord(h->ev_side, h->stream2);
+    }
     d_ev = ev_dev ? (const uint4*)ev_dev : (const uint4*)h->ev_buf;
     const uint8_t* d_kinds = pk ? (src.pk_on_device ? pk->kinds : (const uint8_t*)h->ev_buf) : nullptr;
     const uint32_t* d_words = pk ? (src.pk_on_device ? pk->words : (const uint32_t*)(h->ev_buf + pk_kbytes)) : nullptr;
@@ -916,12 +936,13 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
   uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   const size_t keep = h->slab_used;
-  uint32_t* parent = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
-  uint32_t* best = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
-  uint32_t* nidf = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   const uint32_t effw = (uint32_t)(C / 32 + 1);  // bitmap words; one spare bit at least, so rank(C) = total is addressable
-  uint32_t* eff = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
-  uint32_t* effp = (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
+  uint32_t* parent = pk_dense ? side_parent : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* best = pk_dense ? side_best : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* nidf = pk_dense ? side_nidf : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* eff = pk_dense ? side_eff : (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
+  uint32_t* effp = pk_dense ? side_effp : (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
+  if (!parent || !best || !nidf || !eff || !effp) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
   uint4* cand = (uint4*)slab_alloc(h, 16 * C);
   unsigned long long* tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1));
@@ -929,9 +950,12 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   if (!ticket) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
 
   phase_begin(h, "init");
-  cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
-  cudaMemsetAsync(eff, 0, 4 * ((size_t)effw + 3), s);
-  if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
+  if (pk_dense) cudaStreamWaitEvent(s, h->ev_side, 0);  // initialised on the side stream while E0 / E1 ran
+  else {
+    cudaMemsetAsync(best, 0xFF, 4 * (size_t)S, s);
+    cudaMemsetAsync(eff, 0, 4 * ((size_t)effw + 3), s);
+    if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
+  }
   phase_end(h);
   // E2 runs only when the ids are explicit; a dense stream was validated inside the scatter
   phase_begin(h, "k_ev_check_gates");
@@ -958,12 +982,13 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     ++rounds_issued;
   };
   // ---- node ids (re-issued when the speculative rounds turn out not to have finished the forest)
+  int nid_runs = 0;
   auto node_ids = [&]() {
     uint32_t stiles = scan_tiles(C + 1, kScanItems);
     phase_begin(h, "init");
     cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
     cudaMemsetAsync(ticket, 0, 4, s);
-    cudaMemsetAsync(nidf, 0, 4 * (size_t)S, s);
+    if (!pk_dense || nid_runs++) cudaMemsetAsync(nidf, 0, 4 * (size_t)S, s);  // (dense, first run: zeroed on the side stream)
     cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
     phase_end(h);
     // effp = exclusive scan of popcount(eff words); effp[effw] receives the total (= effective connections)

@@ -12,6 +12,8 @@ struct c2a_handle {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // side stream: initialisation of arrays that are only needed later runs next to the kernels before them
+  cudaEvent_t ev_side = nullptr;
   // one growable device slab carved per call by a bump allocator (no per-call cudaMalloc)
   char* slab = nullptr;
   size_t slab_bytes = 0;
