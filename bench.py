@@ -49,10 +49,10 @@ def alg_bytes(kernel, c):
         "emit:k_scan_u32": 8 * (C // 32 + 1) + 16 * ((n + 1023) // 1024),   # effective-connection bitmap ranks + the two tile-count scans
         "emit:k_ev_nid_edges": C * (4 + 8) + Ceff * (4 + 8),      # conn_sb, conn (+ bitmap words, L2) ; parent chase + atomicMax on the root
         "emit:k_ev_finalize": S * ((0 if c["dense"] else 4) + 8 + 1 + 4 + 4 + 4) + (G + c["n_const"]) * 8,   # sig_t, meta, outmark, parent, id word, nos + screen atomics
-        "emit:k_ev_gates": G * (16 + 12 + 16),
-        "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 4),   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff
+        "emit:k_ev_gates": G * (16 + 12 + 16 + 4),                # signal-id gate, 3 node gathers, node-id gate, RED.MAX producer[out] (K1 of the build)
+        "emit:init": (0 if c["dense"] else 4 * (n + (1 << 20))) + S * (1 + 4 + 4 + 4) + 4 * NB,   # memsets: sig_t (bound-sized), outmark, best, parent iota, {nid,cnt}, eff; producer[] (side stream)
         # ---- build_circuit (c2a_device.cu)
-        "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out]
+        "k_producer": G * (16 + 4),                               # read gate, RED.MAX producer[out] (only for gates that did not come from the device emitter)
         "k_deps": G * (16 + 8 + 8),                               # read gate, 2 producer gathers, write dep pair (+ the forward-edge list)
         "k_relax": 0,                                             # data-driven from the forward-edge list k_deps collects: traffic ~ the moved cones only
         "k_sizes": G * (4 + 4),
@@ -63,7 +63,7 @@ def alg_bytes(kernel, c):
         "k_wire_mark": 4 * NB + 8 * c["W"],                       # stream wire[], set first-appearance bits (bitmap RMW)
         "k_wire_assign": 4 * NB + 4 * c["n_mid"] + 8 * c["W"],    # stream wire[], bitmap + rank-prefix lookups, one write per numbered node
         "k_gather": G * (16 + 12 + 16) + order,                   # read gate, 3 wire gathers, write new gate
-        "init": 8 * NB + (0 if c["identity"] else 9 * G + G // 8),   # zero producer[], fill wire[]; sort scratch (r, size_off, state, inq)
+        "init": 4 * NB + (0 if c["identity"] else 9 * G + G // 8),   # fill wire[] (side stream); sort scratch (r, size_off, state, inq)
     }
     return table.get(kernel, 0)
 

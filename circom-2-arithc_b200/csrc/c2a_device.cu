@@ -717,6 +717,7 @@ void slab_reset(c2a_handle* h) {
   h->slab_used = 0;
   h->slab_keep = 0;
   h->emitted.valid = false;
+  h->emitted.prod1_valid = false;
   h->emitted.wire = nullptr;
 }
 void slab_reset_keep(c2a_handle* h) { h->slab_used = h->slab_keep; }
@@ -994,7 +995,7 @@ static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pai
 static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, const uint32_t* in_nodes_host,
                       const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
                       uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr,
-                      const uint32_t* io_flags_dev = nullptr) {
+                      const uint32_t* io_flags_dev = nullptr, const uint32_t* prod1_ready = nullptr) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
   size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
@@ -1004,7 +1005,8 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
   }
 
-  uint32_t* prod1 = (uint32_t*)slab_alloc(h, 4 * (size_t)p.node_bound);
+  // prod1_ready: the producer map of these gates already exists (the device emitter fills it while it resolves the gates)
+  uint32_t* prod1 = prod1_ready ? const_cast<uint32_t*>(prod1_ready) : (uint32_t*)slab_alloc(h, 4 * (size_t)p.node_bound);
   uint2* dep = (uint2*)slab_alloc(h, 8 * p.G);
   SortScratch s;
   bool ok = sort_scratch_carve(h, p.G, &s);
@@ -1022,13 +1024,24 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     cudaMemcpyAsync(io_nodes, stage, 4 * n_pairs, cudaMemcpyHostToDevice, st);
   }
 
-  phase_begin(h, "init");
-  cudaMemsetAsync(prod1, 0, 4 * (size_t)p.node_bound, st);
-  if (p.want_wire) cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
-  phase_end(h);
-  phase_begin(h, "k_producer");
-  if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
-  phase_end(h);
+  // wire[] is first touched after the sort: its fill runs on the side stream next to K1 / K2 / K5 (several of which are
+  // latency-bound) and the main stream joins in front of the first wire kernel
+  bool wire_join = false;
+  if (p.want_wire && p.node_bound) {
+    cudaEventRecord(h->ev_main, st);
+    cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
+    cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, h->stream2);
+    cudaEventRecord(h->ev_side, h->stream2);
+    wire_join = true;
+  }
+  if (!prod1_ready) {
+    phase_begin(h, "init");
+    cudaMemsetAsync(prod1, 0, 4 * (size_t)p.node_bound, st);
+    phase_end(h);
+    phase_begin(h, "k_producer");
+    if (G) LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, sc);
+    phase_end(h);
+  }
   phase_begin(h, "k_deps");
   if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, s.heavy, sc);
   phase_end(h);
@@ -1048,6 +1061,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
       phase_end(h);
     }
     if (!p.want_wire) return;
+    if (wire_join) { cudaStreamWaitEvent(st, h->ev_side, 0); wire_join = false; }
     if (ni) {
       LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, d_wire, sc);
       LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
@@ -1142,8 +1156,10 @@ int c2a_create(int device, c2a_handle** out) {
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete h; return C2A_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
+    if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1153,6 +1169,7 @@ int c2a_create(int device, c2a_handle** out) {
   if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     cudaEventDestroy(h->ev_side);
+    cudaEventDestroy(h->ev_main);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1173,6 +1190,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   cudaStreamSynchronize(h->stream2);
   cudaEventDestroy(h->ev_side);
+  cudaEventDestroy(h->ev_main);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);
   delete h;

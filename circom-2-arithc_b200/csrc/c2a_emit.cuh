@@ -629,12 +629,19 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
     if (declared) atomicAdd(es + ES_NDECL, declared);
   }
 }
+// Also K1 of the build that follows (compiler.rs:401-406): prod1[out node] = 1 + last gate writing it, while the node ids are in
+// registers - the build then neither zeroes prod1 nor reads the gate array a second time for k_producer.
 __global__ void __launch_bounds__(kBlock) k_ev_gates(const uint4* __restrict__ egates, uint32_t G, uint32_t S, const uint32_t* __restrict__ nos,
-                                                     uint4* __restrict__ gates) {
+                                                     uint4* __restrict__ gates, uint32_t* __restrict__ prod1, uint32_t prod_bound) {
   for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
     uint4 e = egates[g];
-    if (S == 0) e.y = e.z = e.w = 0;  // only on a stream that is about to be declined
-    stg_stream(gates + g, S ? make_uint4(e.x, __ldg(nos + e.y), __ldg(nos + e.z), __ldg(nos + e.w)) : make_uint4(e.x, 0, 0, 0));
+    if (S == 0) {  // only on a stream that is about to be declined
+      stg_stream(gates + g, make_uint4(e.x, 0, 0, 0));
+      continue;
+    }
+    const uint32_t o = __ldg(nos + e.w);
+    stg_stream(gates + g, make_uint4(e.x, __ldg(nos + e.y), __ldg(nos + e.z), o));
+    if (o < prod_bound) atomicMax(prod1 + o, g + 1);  // RED.MAX, no return value
   }
 }
 // I/O signal ids -> node ids (compiler.rs:327-361 walks nodes; here the caller lists signals)
@@ -898,8 +905,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   if (info) { info->n_gates = G; info->n_connections = C; info->n_signals = n_sig; info->signal_bound = S; }
 
   std::vector<c2a_event> ev_back;
+  bool prod1_pending = false;  // a memset of the slab is in flight on the side stream
   auto decline = [&](uint32_t f) -> int {
     if (info) info->decline_flags = f;
+    if (prod1_pending) { cudaStreamWaitEvent(s, h->ev_side, 0); prod1_pending = false; }  // the host path reuses the slab
     if (!ev && n) {  // the exact replay needs AoS events on the host
       ev_back.resize(n);
       if (pk) {
@@ -928,13 +937,15 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   // ---- exact sizes are known: one slab for the resident result, the emit scratch and the build that follows
   const uint32_t NB_ub = (uint32_t)std::min<uint64_t>(n_sig + C + 1, 0x7FFFFFFEull);
   BuildPlan bp{G, NB_ub, 0, 0, true};
-  size_t resident = align256(16 * G) + align256(4 * (size_t)S);
+  size_t resident = align256(16 * G) + align256(4 * (size_t)S) + align256(4 * (size_t)NB_ub);
   size_t build_need = core_scratch_bytes(bp, 1u << 20) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)NB_ub);
   slab_reset(h);
   emit_drop_host(h);
   if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(G, C, S), build_need))) return C2A_ERR_NO_MEMORY;
   uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
   uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
+  uint32_t* prod1 = (uint32_t*)slab_alloc(h, 4 * (size_t)NB_ub);  // producer map of the build (K1), filled by k_ev_gates
+  if (!prod1) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   const size_t keep = h->slab_used;
   const uint32_t effw = (uint32_t)(C / 32 + 1);  // bitmap words; one spare bit at least, so rank(C) = total is addressable
   uint32_t* parent = pk_dense ? side_parent : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
@@ -957,6 +968,11 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
   }
   phase_end(h);
+  // prod1 is zeroed on the side stream next to the Boruvka / node-id kernels; k_ev_gates joins.  (The main stream is idle
+  // after the scatter sync, so the side stream needs no event from it.)
+  cudaMemsetAsync(prod1, 0, 4 * (size_t)NB_ub, h->stream2);
+  cudaEventRecord(h->ev_side, h->stream2);
+  prod1_pending = true;
   // E2 runs only when the ids are explicit; a dense stream was validated inside the scatter
   phase_begin(h, "k_ev_check_gates");
   if (G && !pk_dense) LAUNCH(h, k_ev_check_gates, grid_for(h, (const void*)k_ev_check_gates, kBlock, G), kBlock, egates, gate_t, (uint32_t)G, S, sig_t, outmark, es);
@@ -1001,8 +1017,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     phase_begin(h, "k_ev_finalize");
     if (S) LAUNCH(h, k_ev_finalize, grid_for(h, (const void*)k_ev_finalize, kBlock, S), kBlock, S, pk_dense ? (const uint32_t*)nullptr : sig_t, sig_meta, outmark, eff, effp, parent, nidf, nos, es);
     phase_end(h);
+    if (prod1_pending) { cudaStreamWaitEvent(s, h->ev_side, 0); prod1_pending = false; }
+    else cudaMemsetAsync(prod1, 0, 4 * (size_t)NB_ub, s);  // second run (the forest needed more rounds): forget the first run's producers
     phase_begin(h, "k_ev_gates");
-    if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates);
+    if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates, prod1, NB_ub);
     phase_end(h);
     cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
     cudaMemcpyAsync(hp + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, s);
@@ -1041,6 +1059,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   h->emitted.nos_valid = true;
   h->emitted.gates_off = (char*)d_gates - h->slab;
   h->emitted.nos_off = (char*)nos - h->slab;
+  h->emitted.prod1_valid = true;
+  h->emitted.prod1_off = (char*)prod1 - h->slab;
   h->emitted.G = G;
   h->emitted.node_count = (uint32_t)(n_sig + n_eff);
   h->emitted.signal_bound = S;
@@ -1144,7 +1164,8 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   }
   h->emitted.wire = nullptr;
   bool identity = true;
-  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, &identity, io_nodes, io_flag);
+  st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, &identity, io_nodes, io_flag,
+                  h->emitted.prod1_valid ? (const uint32_t*)(h->slab + h->emitted.prod1_off) : nullptr);
   if (st == C2A_OK) { h->emitted.wire = d_wire; h->emitted.identity = identity; }  // stay valid until the next call that carves the slab
   if (st == C2A_OK && !outputs_on_device) {
     phase_begin(h, "d2h");

@@ -14,6 +14,7 @@ struct c2a_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: initialisation of arrays that are only needed later runs next to the kernels before them
   cudaEvent_t ev_side = nullptr;
+  cudaEvent_t ev_main = nullptr;   // orders the side stream after what the main stream already holds
   // one growable device slab carved per call by a bump allocator (no per-call cudaMalloc)
   char* slab = nullptr;
   size_t slab_bytes = 0;
@@ -45,6 +46,8 @@ struct c2a_handle {
     bool nos_valid = false;      // node_of_signal[] resident (false for sparse signal ids on the host path)
     size_t gates_off = 0;        // uint4[G], node ids, emission order
     size_t nos_off = 0;          // u32[signal_bound]
+    bool prod1_valid = false;    // the producer map (K1) was filled by the emitter's gate kernel: builds skip its memset and k_producer
+    size_t prod1_off = 0;        // u32[>= node_count + 1], kept with the circuit (a pure function of the gates)
     uint64_t G = 0;
     uint32_t node_count = 0;
     uint32_t signal_bound = 0;

@@ -160,6 +160,33 @@ def test_long_connection_path_needs_many_rounds(ctx, orc):
     assert len(set(nos[:n].tolist())) == 1
 
 
+def test_many_rounds_with_gates_then_build(ctx, orc):
+    """gates over a class that needs more Boruvka rounds than the speculative ones: the node ids are computed twice, so the
+    producer map the gate kernel fills for the build (compiler.rs:401-406) must be the second run's; build twice (it is kept)"""
+    rng = np.random.RandomState(11)
+    n, ng = 2048, 600
+    ev = [(EV_S, i, 0, 0) for i in range(n)]
+    pool = list(range(n))
+    for j in range(ng):
+        o = n + j
+        ev.append((EV_S, o, 0, 0))
+        a, b = (int(pool[rng.randint(len(pool))]) for _ in range(2))
+        ev.append((EV_G | (int(rng.randint(0, 20)) << 8), a, b, o))
+        pool.append(o)
+    for k in rng.permutation(n - 1):
+        ev.append((EV_C, int(k), int(k) + 1, 0))
+    ev = np.asarray(ev, dtype=np.uint32)
+    info, gates, nos = check_against(ctx, oracle_emit(orc, ev), ev)
+    assert info["rounds"] > 2
+    ins, outs = np.array([0], dtype=np.uint32), np.array([n + ng - 1], dtype=np.uint32)
+    nb = info["node_count"] + 1
+    st, _, o_order, o_wire, o_gates, o_wc = orc.backend_raw(gates, nb, nos[ins], nos[outs])
+    assert st == 0
+    for _ in range(2):
+        order, wire, g2, wc = ctx.emitted_build_circuit(ins, outs)
+        assert wc == o_wc and np.array_equal(order, o_order) and np.array_equal(wire, o_wire) and np.array_equal(g2, o_gates)
+
+
 def test_tag_wraparound_many_rounds(ctx, c2a):
     """a 2^17-signal path whose connections arrive ordered by the number of trailing zeros of their position: every
     Boruvka round only pairs up neighbouring classes, so it takes 17 rounds (more than 7: the best[] tags wrap)"""
