@@ -9,10 +9,13 @@
 // Runtime model.  The reference deep-clones the whole Context for every `while` iteration / `if` body and merges
 // variables and components back on exit (runtime.rs:151-187).  That is observationally a lexical scope: items declared
 // inside are dropped, writes to items that already existed persist (a re-declared variable overwrites the outer one,
-// :175-178), the return variable is always carried out (:180-184).  Here: one hash map per call frame plus a scope
-// stack of declared names - O(1) per push instead of O(context).  Template / function calls start an empty frame
-// (runtime.rs:75-77).  Temporaries (`random_<u32>` items, :229) are values, not map entries; temporary SIGNALS still
-// consume signal ids and are named "<ctx>.random_<id>" (the reference's suffix is a thread_rng draw, i.e. unspecified).
+// :175-178), the return variable is always carried out (:180-184).  Here: one item STACK per call frame plus a stack of
+// scope marks - push is O(1), pop truncates.  Template / function calls start an empty frame (runtime.rs:75-77).
+// Temporaries (`random_<u32>` items, :229) are values, not entries; temporary SIGNALS still consume signal ids and are
+// named "<ctx>.random_<id>" (the reference's suffix is a thread_rng draw, i.e. unspecified).
+// The walk never touches a string: identifiers are interned after parsing (Symbols), `const_signal_<v>` items are keyed
+// by their value, and signal names are kept as 16-byte records that are spelled out only when somebody asks for one
+// (c2a_program_signal_name, the input / output prefix match, a host Compiler that wants the names).
 // u32 arithmetic on variables follows a release build: + * ** wrap, shifts use the low 5 bits, - / \ % error as in
 // src/process.rs:649-750.
 #include <cstdint>
@@ -109,11 +112,14 @@ static const uint32_t kGateOf[] = {C2A_AMul, C2A_ADiv, C2A_AAdd, C2A_ASub, C2A_A
 enum Prefix { P_Sub, P_BoolNot, P_Complement };
 
 struct Expr;
+struct Callable;
 using ExprP = std::shared_ptr<Expr>;
+using Key = uint64_t;  // interned item name (see Symbols): what the walker compares instead of strings
 struct Access {
   bool component;    // .name  vs  [expr]
   std::string name;
   ExprP index;
+  Key key = 0;       // component: interned name (filled by Symbols::annotate)
 };
 struct Expr {
   enum Kind { Number, Variable, InfixOp, PrefixOp, Call, Unsupported } kind = Unsupported;
@@ -122,6 +128,11 @@ struct Expr {
   int op = 0;
   ExprP l, r;
   std::vector<ExprP> args;
+  // filled by Symbols::annotate after parsing
+  Key key = 0;                       // Variable: interned name; Call: the callee's name symbol
+  const Callable* callee = nullptr;  // Call: resolved definition (null: undefined)
+  uint32_t num = 0;                  // Number: the literal's value ...
+  bool num_overflow = false;         // ... or "does not fit u32" (src/process.rs:294-306; raised only when evaluated)
 };
 enum AssignOp { A_Var, A_Signal, A_ConstraintSignal };  // =  <--  <==
 enum DataType { D_Variable, D_Signal, D_Component };
@@ -138,12 +149,14 @@ struct Stmt {
   int sigkind = 0;             // 0 intermediate, 1 input, 2 output
   std::vector<ExprP> dims;
   StmtP a, b;                  // if / else / while body
+  Key key = 0;                 // interned `name` (Symbols::annotate)
 };
 struct Callable {
   bool is_function = false;
   std::vector<std::string> params;
   std::vector<StmtP> body;
   std::vector<std::string> inputs, outputs;  // templates: declared input / output signal names
+  std::vector<Key> param_keys, input_keys, output_keys;  // the same names interned (Symbols::annotate)
 };
 struct Program {
   std::map<std::string, Callable> defs;
@@ -423,7 +436,109 @@ static void parse_into(Program& prog, const std::string& src, const std::string&
   });
 }
 
+// ===================================================================================================== symbols
+// Item keys.  An identifier is its interned id; the items process.rs creates for constants ("const_signal_<value>",
+// :558-579) are keyed by the value, and an identifier that happens to be spelled that way maps to the same key, so the two
+// still meet in one namespace exactly as the reference's string-keyed map does.
+constexpr Key kConstKey = 1ull << 32;
+struct Symbols {
+  std::unordered_map<std::string, uint32_t> ids;
+  std::vector<std::string> strs;
+  uint32_t intern(const std::string& s) {
+    auto it = ids.find(s);
+    if (it != ids.end()) return it->second;
+    uint32_t id = (uint32_t)strs.size();
+    strs.push_back(s);
+    ids.emplace(s, id);
+    return id;
+  }
+  Key key(const std::string& s) {
+    static const char kPrefix[] = "const_signal_";
+    const size_t L = sizeof(kPrefix) - 1;
+    if (s.size() > L && s.size() <= L + 10 && s.compare(0, L, kPrefix) == 0) {
+      bool digits = true;
+      unsigned long long v = 0;
+      for (size_t i = L; i < s.size(); ++i) { if (!isdigit((unsigned char)s[i])) { digits = false; break; } v = v * 10 + (s[i] - '0'); }
+      if (digits && v <= 0xFFFFFFFFull && std::to_string(v) == s.substr(L)) return kConstKey | v;  // canonical spelling only
+    }
+    return intern(s);
+  }
+  std::string str(Key k) const { return k >= kConstKey ? "const_signal_" + std::to_string((uint32_t)k) : strs[(size_t)k]; }
+
+  // ---- one pass over the parsed program: names -> keys, literals -> values, calls -> definitions
+  void annotate(Program& prog) {
+    for (auto& kv : prog.defs) {
+      Callable& c = kv.second;
+      c.param_keys.clear(); c.input_keys.clear(); c.output_keys.clear();
+      for (auto& p : c.params) c.param_keys.push_back(key(p));
+      for (auto& p : c.inputs) c.input_keys.push_back(key(p));
+      for (auto& p : c.outputs) c.output_keys.push_back(key(p));
+      for (auto& s : c.body) stmt(prog, s.get());
+    }
+    if (prog.main) expr(prog, prog.main.get());
+  }
+  void accesses(Program& prog, std::vector<Access>& acc) {
+    for (auto& a : acc) {
+      if (a.component) a.key = key(a.name);
+      else if (a.index) expr(prog, a.index.get());
+    }
+  }
+  void expr(Program& prog, Expr* e) {
+    if (!e) return;
+    switch (e->kind) {
+      case Expr::Number: {
+        const std::string& s = e->text;
+        unsigned long long v = 0;
+        bool hex = s.size() > 2 && (s[1] == 'x' || s[1] == 'X');
+        e->num_overflow = false;
+        for (size_t i = hex ? 2 : 0; i < s.size(); ++i) {
+          int d = isdigit((unsigned char)s[i]) ? s[i] - '0' : (tolower(s[i]) - 'a' + 10);
+          v = v * (hex ? 16 : 10) + d;
+          if (v > 0xFFFFFFFFull) { e->num_overflow = true; break; }
+        }
+        e->num = (uint32_t)v;
+        break;
+      }
+      case Expr::Variable: e->key = key(e->text); accesses(prog, e->access); break;
+      case Expr::Call: {
+        e->key = intern(e->text);
+        auto def = prog.defs.find(e->text);
+        e->callee = def == prog.defs.end() ? nullptr : &def->second;
+        for (auto& a : e->args) expr(prog, a.get());
+        break;
+      }
+      default: break;
+    }
+    expr(prog, e->l.get());
+    expr(prog, e->r.get());
+  }
+  void stmt(Program& prog, Stmt* s) {
+    if (!s) return;
+    if (s->kind == Stmt::Substitution || s->kind == Stmt::Declaration) s->key = key(s->name);
+    accesses(prog, s->access);
+    expr(prog, s->e.get());
+    for (auto& d : s->dims) expr(prog, d.get());
+    for (auto& c : s->stmts) stmt(prog, c.get());
+    stmt(prog, s->a.get());
+    stmt(prog, s->b.get());
+  }
+};
+
 // ===================================================================================================== runtime
+// a few elements inline, the rest on the heap (access paths and dimension lists are almost always <= 4 long)
+template <class T, int N>
+struct Small {
+  T a[N];
+  uint32_t n = 0;
+  std::vector<T> more;
+  void push_back(const T& v) { if (n < (uint32_t)N) a[n] = v; else more.push_back(v); ++n; }
+  void pop_back() { if (n > (uint32_t)N) more.pop_back(); --n; }
+  uint32_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  const T& operator[](uint32_t i) const { return i < (uint32_t)N ? a[i] : more[i - N]; }
+};
+using Path = Small<uint32_t, 6>;
+
 template <class T>
 struct Nested {
   bool is_array = false;
@@ -431,7 +546,17 @@ struct Nested {
   T val{};
 };
 using SigTree = Nested<uint32_t>;
-using SigMap = std::map<std::string, SigTree>;
+struct SigMap {  // a component's input / output signals by name (runtime.rs: HashMap<String, Signal>); a handful of entries
+  std::vector<std::pair<Key, SigTree>> v;
+  const SigTree* find(Key k) const {
+    for (auto& e : v) if (e.first == k) return &e.second;
+    return nullptr;
+  }
+  void set(Key k, const SigTree& t) {
+    for (auto& e : v) if (e.first == k) { e.second = t; return; }
+    v.emplace_back(k, t);
+  }
+};
 struct Item {
   DataType type = D_Variable;
   Nested<std::optional<uint32_t>> var;
@@ -440,24 +565,24 @@ struct Item {
 };
 struct SubAccess {
   bool component;
-  uint32_t index;
-  std::string name;
+  Key v;  // component: the signal's name key; otherwise the index
 };
+using AccessList = Small<SubAccess, 4>;
 // result of process_expression: a named item access, or a temporary
 struct Ref {
   enum Kind { Named, TempVar, TempSignal, TempComp } kind = TempVar;
-  std::string name;
-  std::vector<SubAccess> access;
+  Key name = 0;
+  AccessList access;
   std::optional<uint32_t> value;  // TempVar
   uint32_t signal = 0;            // TempSignal
   std::shared_ptr<SigMap> comp;   // TempComp
 };
-static const char* RETURN_VAR = "function_return_value";
 
 template <class T>
-static const Nested<T>& nested_get(const Nested<T>& v, const std::vector<uint32_t>& path) {  // runtime.rs:668-688
+static const Nested<T>& nested_get(const Nested<T>& v, const Path& path) {  // runtime.rs:668-688
   const Nested<T>* cur = &v;
-  for (uint32_t i : path) {
+  for (uint32_t k = 0; k < path.size(); ++k) {
+    const uint32_t i = path[k];
     if (!cur->is_array) runtime_error("Access Error");
     if (i >= cur->arr.size()) runtime_error("Index out of bounds");
     cur = &cur->arr[i];
@@ -465,11 +590,11 @@ static const Nested<T>& nested_get(const Nested<T>& v, const std::vector<uint32_
   return *cur;
 }
 template <class T>
-static Nested<T>& nested_get_mut(Nested<T>& v, const std::vector<uint32_t>& path) {
+static Nested<T>& nested_get_mut(Nested<T>& v, const Path& path) {
   return const_cast<Nested<T>&>(nested_get(const_cast<const Nested<T>&>(v), path));
 }
-template <class T>
-static Nested<T> nested_new(const std::vector<uint32_t>& dims, size_t k, const std::function<T()>& leaf) {
+template <class T, class Leaf>
+static Nested<T> nested_new(const Path& dims, uint32_t k, Leaf&& leaf) {
   Nested<T> n;
   if (k == dims.size()) { n.val = leaf(); return n; }
   n.is_array = true;
@@ -477,32 +602,101 @@ static Nested<T> nested_new(const std::vector<uint32_t>& dims, size_t k, const s
   for (uint32_t i = 0; i < dims[k]; ++i) n.arr.push_back(nested_new<T>(dims, k + 1, leaf));
   return n;
 }
-static std::vector<uint32_t> access_to_u32(const std::vector<SubAccess>& a) {  // runtime.rs:701-710
-  std::vector<uint32_t> v;
-  for (auto& s : a) { if (s.component) runtime_error("Access Error"); v.push_back(s.index); }
+static Path access_to_u32(const AccessList& a) {  // runtime.rs:701-710
+  Path v;
+  for (uint32_t k = 0; k < a.size(); ++k) { if (a[k].component) runtime_error("Access Error"); v.push_back((uint32_t)a[k].v); }
   return v;
 }
 
+// One call frame: the items in declaration order (a stack: a scope's items are the ones above its mark) and the open scopes.
+// Lookups scan the stack from the top while it is short and go through an index once it is not.
 struct Frame {
-  std::string ctx_name;
-  std::unordered_map<std::string, Item> items;
-  std::vector<std::vector<std::string>> scopes;  // names declared per open scope
+  uint32_t ctx = 0;  // name of the context = the callee's name symbol ("0" for the root, runtime.rs:63-68)
+  std::vector<Key> keys;    // keys[i] names items[i]; kept apart so that a scan touches two cache lines, not one per item
+  std::vector<Item> items;
+  std::vector<uint32_t> marks;  // items.size() when each open scope began
+  std::unordered_map<Key, uint32_t> index;
+  bool indexed = false;
+  static constexpr size_t kScan = 16;
+
+  void reset(uint32_t ctx_sym) {
+    ctx = ctx_sym;
+    keys.clear();
+    items.clear();
+    marks.clear();
+    marks.push_back(0);
+    if (indexed) { index.clear(); indexed = false; }
+  }
+  size_t size() const { return keys.size(); }
+  Item* find(Key k) {
+    if (!indexed) {
+      for (size_t i = keys.size(); i-- > 0;)
+        if (keys[i] == k) return &items[i];
+      return nullptr;
+    }
+    auto it = index.find(k);
+    return it == index.end() ? nullptr : &items[it->second];
+  }
+  Item& push(Key k, Item&& item) {
+    keys.push_back(k);
+    items.push_back(std::move(item));
+    if (indexed) index[k] = (uint32_t)keys.size() - 1;
+    else if (keys.size() > kScan) {
+      for (uint32_t i = 0; i < keys.size(); ++i) index[keys[i]] = i;
+      indexed = true;
+    }
+    return items.back();
+  }
+  void truncate(size_t n) {
+    if (indexed) for (size_t i = n; i < keys.size(); ++i) index.erase(keys[i]);
+    keys.resize(n);
+    items.resize(n);
+  }
+};
+
+struct SigName {  // "<ctx>.<base>[i][j]..." spelled on demand (runtime.rs:594-608, process.rs:464-474, 558-579)
+  uint32_t ctx;       // context name symbol
+  uint32_t kind_n;    // kind (2 bits: 0 declared name, 1 const_signal_<a>, 2 random_<a>) | number of indices << 2
+  uint32_t a;         // name symbol / constant value / random suffix
+  uint32_t idx_off;   // first index in Sink::idx
 };
 
 struct Sink {  // where add_signal / add_gate / add_connection go
   c2a_compiler* into = nullptr;
   std::vector<c2a_event> events;
-  std::vector<std::string> names;  // by signal id (ids are sequential from 0)
+  std::vector<SigName> names;  // by signal id (ids are sequential from 0)
+  std::vector<uint32_t> idx;   // array indices of the declared names
+  Symbols sym;
   void check(int st) {
     if (st == C2A_OK) return;
     std::string why = st == C2A_ERR_INVALID_ARGUMENT || st == C2A_ERR_REFERENCE_PANIC ? c2a_compiler_last_error(into) : c2a_status_string(st);
     fail(C2A_PROG_CIRCUIT_ERROR, "Circuit error: " + why);
   }
-  void add_signal(uint32_t id, const std::string& name, std::optional<uint32_t> value) {
-    if (names.size() <= id) names.resize((size_t)id + 1);
-    names[id] = name;
+  std::string name_of(uint32_t id) const {
+    const SigName& n = names[id];
+    std::string s = sym.strs[n.ctx];
+    s += '.';
+    switch (n.kind_n & 3u) {
+      case 0: s += sym.strs[n.a]; break;
+      case 1: s += "const_signal_"; s += std::to_string(n.a); break;
+      default: s += "random_"; s += std::to_string(n.a); break;
+    }
+    for (uint32_t k = 0; k < (n.kind_n >> 2); ++k) { s += '['; s += std::to_string(idx[n.idx_off + k]); s += ']'; }
+    return s;
+  }
+  void add_signal(uint32_t id, uint32_t ctx, Key name, const Path* indices, bool random, std::optional<uint32_t> value) {
+    if (names.size() == id) names.emplace_back();
+    else if (names.size() < id) names.resize((size_t)id + 1);
+    SigName& n = names[id];
+    n.ctx = ctx;
+    n.idx_off = (uint32_t)idx.size();
+    const uint32_t ni = indices ? indices->size() : 0u;
+    if (random) { n.kind_n = 2u; n.a = id; }
+    else if (name >= kConstKey) { n.kind_n = 1u | (ni << 2); n.a = (uint32_t)name; }
+    else { n.kind_n = 0u | (ni << 2); n.a = (uint32_t)name; }
+    for (uint32_t k = 0; k < ni; ++k) idx.push_back((*indices)[k]);
     events.push_back(c2a_event{value ? (uint32_t)C2A_EV_SIGNAL_CONST : (uint32_t)C2A_EV_SIGNAL, id, value.value_or(0), 0});
-    if (into) check(c2a_add_signal(into, id, name.c_str(), value.has_value(), value.value_or(0)));
+    if (into) check(c2a_add_signal(into, id, name_of(id).c_str(), value.has_value(), value.value_or(0)));
   }
   void add_gate(uint32_t op, uint32_t l, uint32_t r, uint32_t o) {
     events.push_back(c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), l, r, o});
@@ -517,42 +711,59 @@ struct Sink {  // where add_signal / add_gate / add_connection go
 struct Walker {
   const Program& prog;
   Sink& ac;
-  std::vector<Frame> frames;
+  std::vector<std::unique_ptr<Frame>> frames;  // [0, nframes) live; the rest are kept for reuse (their vectors stay allocated)
+  size_t nframes = 0;
   uint32_t next_signal_id = 0;  // runtime.rs:120-125
   uint64_t depth = 0;
+  const Key kReturn;            // "function_return_value"
 
-  Walker(const Program& p, Sink& s) : prog(p), ac(s) {
-    frames.push_back(Frame{"0", {}, {{}}});  // runtime.rs:63-68: the root context is named "0"
+  Walker(const Program& p, Sink& s) : prog(p), ac(s), kReturn(s.sym.key("function_return_value")) {
+    push_frame(s.sym.intern("0"));  // runtime.rs:63-68: the root context is named "0"
   }
-  Frame& ctx() { return frames.back(); }
+  Frame& ctx() { return *frames[nframes - 1]; }
+  void push_frame(uint32_t ctx_sym) {
+    if (nframes == frames.size()) frames.emplace_back(new Frame());
+    frames[nframes++]->reset(ctx_sym);
+  }
+  void pop_frame() { --nframes; }
+  std::string key_str(Key k) const { return ac.sym.str(k); }
 
   // ---- contexts (runtime.rs:71-117, 151-187)
-  void push_scope() { ctx().scopes.emplace_back(); }
+  void push_scope() { Frame& f = ctx(); f.marks.push_back((uint32_t)f.size()); }
   void pop_scope() {
     Frame& f = ctx();
-    std::vector<std::string> names = std::move(f.scopes.back());
-    f.scopes.pop_back();
-    for (auto& n : names) {
-      if (n == RETURN_VAR && !f.scopes.empty()) { f.scopes.back().push_back(n); continue; }  // :180-184 forced merge
-      f.items.erase(n);
-    }
+    const size_t mark = f.marks.back();
+    f.marks.pop_back();
+    // :180-184 forced merge: the return variable is carried into the enclosing scope
+    size_t keep = f.size();
+    if (!f.marks.empty())
+      for (size_t i = mark; i < f.size(); ++i)
+        if (f.keys[i] == kReturn) { keep = i; break; }
+    if (keep < f.size()) {
+      Item carried = std::move(f.items[keep]);
+      f.truncate(mark);
+      f.push(kReturn, std::move(carried));
+    } else f.truncate(mark);
   }
-  void declare_item(DataType type, const std::string& name, const std::vector<uint32_t>& dims) {  // runtime.rs:190-222
+  Item& declare_item(DataType type, Key name, const Path& dims) {  // runtime.rs:190-222
     Frame& f = ctx();
-    auto it = f.items.find(name);
-    if (it != f.items.end() && type != D_Variable) runtime_error("Item already declared");
-    if (it == f.items.end()) f.scopes.back().push_back(name);
+    Item* existing = f.find(name);
+    if (existing && type != D_Variable) runtime_error("Item already declared");
     Item item;
     item.type = type;
-    if (type == D_Signal) item.sig = nested_new<uint32_t>(dims, 0, [&] { return next_signal_id++; });  // row-major ids, :431-445
-    else if (type == D_Variable) item.var = nested_new<std::optional<uint32_t>>(dims, 0, [] { return std::optional<uint32_t>(); });
-    else item.comp = nested_new<SigMap>(dims, 0, [] { return SigMap(); });
-    f.items[name] = std::move(item);
+    if (type == D_Signal) {
+      if (dims.empty()) item.sig.val = next_signal_id++;
+      else item.sig = nested_new<uint32_t>(dims, 0, [&] { return next_signal_id++; });  // row-major ids, :431-445
+    } else if (type == D_Variable) {
+      if (!dims.empty()) item.var = nested_new<std::optional<uint32_t>>(dims, 0, [] { return std::optional<uint32_t>(); });
+    } else if (!dims.empty()) item.comp = nested_new<SigMap>(dims, 0, [] { return SigMap(); });
+    if (existing) { *existing = std::move(item); return *existing; }  // a re-declared variable overwrites the visible one (:175-178)
+    return f.push(name, std::move(item));
   }
-  Item& item(const std::string& name, const char* who) {
-    auto it = ctx().items.find(name);
-    if (it == ctx().items.end()) runtime_error(std::string("Item not declared: ") + who + ": " + name);
-    return it->second;
+  Item& item(Key name, const char* who) {
+    Item* it = ctx().find(name);
+    if (!it) runtime_error(std::string("Item not declared: ") + who + ": " + key_str(name));
+    return *it;
   }
   DataType type_of(const Ref& r) {  // runtime.rs:235-249
     switch (r.kind) {
@@ -562,11 +773,13 @@ struct Walker {
       default: return item(r.name, "get_item_data_type").type;
     }
   }
+  std::string ref_name(const Ref& r) const { return r.kind == Ref::Named ? key_str(r.name) : std::string(); }
   std::optional<uint32_t> variable_value(const Ref& r) {  // runtime.rs:296-307
     if (r.kind == Ref::TempVar) return r.value;
-    if (r.kind != Ref::Named) runtime_error("Item not declared: get_variable_value: " + r.name);
+    if (r.kind != Ref::Named) runtime_error("Item not declared: get_variable_value: " + ref_name(r));
     Item& it = item(r.name, "get_variable_value");
-    if (it.type != D_Variable) runtime_error("Item not declared: get_variable_value: " + r.name);
+    if (it.type != D_Variable) runtime_error("Item not declared: get_variable_value: " + ref_name(r));
+    if (r.access.empty() && !it.var.is_array) return it.var.val;
     const auto& n = nested_get(it.var, access_to_u32(r.access));
     if (n.is_array) runtime_error("Data Item content is not a single value");
     return n.val;
@@ -577,36 +790,38 @@ struct Walker {
     return *v;
   }
   // (component access, signal access) split, runtime.rs:617-663
-  static void split_component_access(const Ref& r, std::vector<uint32_t>& comp_path, std::string& signal, std::vector<uint32_t>& sig_path) {
+  static void split_component_access(const Ref& r, Path& comp_path, Key& signal, Path& sig_path) {
     bool has = false;
-    for (auto& s : r.access) {
-      if (!s.component) (has ? sig_path : comp_path).push_back(s.index);
-      else { if (has) runtime_error("Access Error"); signal = s.name; has = true; }
+    for (uint32_t k = 0; k < r.access.size(); ++k) {
+      const SubAccess& s = r.access[k];
+      if (!s.component) (has ? sig_path : comp_path).push_back((uint32_t)s.v);
+      else { if (has) runtime_error("Access Error"); signal = s.v; has = true; }
     }
     if (!has) runtime_error("Access Error");
   }
   const SigTree& component_signal_content(const Ref& r) {  // runtime.rs:389-405, 560-580
-    std::vector<uint32_t> cp, sp;
-    std::string sname;
+    Path cp, sp;
+    Key sname = 0;
     split_component_access(r, cp, sname, sp);
     const SigMap* map;
     if (r.kind == Ref::TempComp) { if (!cp.empty()) runtime_error("Access Error"); map = r.comp.get(); }
     else {
       Item& it = item(r.name, "get_component_signal_id");
-      if (it.type != D_Component) runtime_error("Item not declared: get_component_signal_id: " + r.name);
+      if (it.type != D_Component) runtime_error("Item not declared: get_component_signal_id: " + ref_name(r));
       const auto& n = nested_get(it.comp, cp);
       if (n.is_array) runtime_error("Data Item content is not a single value");
       map = &n.val;
     }
-    auto f = map->find(sname);
-    if (f == map->end()) runtime_error("Item not declared: get_signal_id: " + sname);
-    return nested_get(f->second, sp);
+    const SigTree* f = map->find(sname);
+    if (!f) runtime_error("Item not declared: get_signal_id: " + key_str(sname));
+    return nested_get(*f, sp);
   }
   const SigTree& signal_content(const Ref& r) {  // runtime.rs:323-337
     static thread_local SigTree tmp;
-    if (r.kind == Ref::TempSignal) { tmp = SigTree(); tmp.val = r.signal; return tmp; }
+    if (r.kind == Ref::TempSignal) { tmp.is_array = false; tmp.arr.clear(); tmp.val = r.signal; return tmp; }
     Item& it = item(r.name, "get_signal_content");
-    if (it.type != D_Signal) runtime_error("Item not declared: get_signal_content: " + r.name);
+    if (it.type != D_Signal) runtime_error("Item not declared: get_signal_content: " + ref_name(r));
+    if (r.access.empty()) return it.sig;
     return nested_get(it.sig, access_to_u32(r.access));
   }
   uint32_t signal_id(const Ref& r) {  // runtime.rs:341-355
@@ -626,20 +841,14 @@ struct Walker {
       default: fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
     }
   }
-  std::string access_str(const std::string& name, const std::vector<uint32_t>& idx) {  // runtime.rs:594-608
-    std::string s = ctx().ctx_name + "." + name;
-    for (uint32_t i : idx) s += "[" + std::to_string(i) + "]";
-    return s;
-  }
 
   // ---- process.rs
   uint32_t make_constant(uint32_t value) {  // :558-579 — one constant signal per value per visible context
-    std::string name = "const_signal_" + std::to_string(value);
-    auto it = ctx().items.find(name);
-    if (it != ctx().items.end() && it->second.type == D_Signal && !it->second.sig.is_array) return it->second.sig.val;
-    declare_item(D_Signal, name, {});
-    uint32_t id = ctx().items[name].sig.val;
-    ac.add_signal(id, access_str(name, {}), value);
+    const Key name = kConstKey | value;
+    Item* it = ctx().find(name);
+    if (it && it->type == D_Signal && !it->sig.is_array) return it->sig.val;
+    uint32_t id = declare_item(D_Signal, name, Path()).sig.val;
+    ac.add_signal(id, ctx().ctx, name, nullptr, false, value);
     return id;
   }
   uint32_t signal_for_access(const Ref& r) {  // :538-556
@@ -653,7 +862,7 @@ struct Walker {
     Ref r;
     r.kind = Ref::TempSignal;
     r.signal = next_signal_id++;
-    ac.add_signal(r.signal, ctx().ctx_name + ".random_" + std::to_string(r.signal), std::nullopt);
+    ac.add_signal(r.signal, ctx().ctx, 0, nullptr, true, std::nullopt);
     return r;
   }
   static uint32_t execute_op(uint32_t l, uint32_t r, int op) {  // :649-750 (release-build wrapping for + * ** << >>)
@@ -683,13 +892,13 @@ struct Walker {
   }
   Ref temp_var(std::optional<uint32_t> v) { Ref r; r.kind = Ref::TempVar; r.value = v; return r; }
 
-  Ref build_access(const std::string& name, const std::vector<Access>& access) {  // :620-646
+  Ref build_access(Key name, const std::vector<Access>& access) {  // :620-646
     Ref r;
     r.kind = Ref::Named;
     r.name = name;
     for (auto& a : access) {
-      if (a.component) r.access.push_back(SubAccess{true, 0, a.name});
-      else r.access.push_back(SubAccess{false, value_or_empty(process_expression(*a.index)), ""});
+      if (a.component) r.access.push_back(SubAccess{true, a.key});
+      else r.access.push_back(SubAccess{false, value_or_empty(process_expression(*a.index))});
     }
     return r;
   }
@@ -719,51 +928,41 @@ struct Walker {
         ac.add_gate(kGateOf[infix], lid, rid, out.signal);
         return out;
       }
-      case Expr::Number: {  // :294-306: the literal must fit u32
-        const std::string& s = e.text;
-        unsigned long long v = 0;
-        bool hex = s.size() > 2 && (s[1] == 'x' || s[1] == 'X');
-        for (size_t i = hex ? 2 : 0; i < s.size(); ++i) {
-          int d = isdigit((unsigned char)s[i]) ? s[i] - '0' : (tolower(s[i]) - 'a' + 10);
-          v = v * (hex ? 16 : 10) + d;
-          if (v > 0xFFFFFFFFull) fail(C2A_PROG_PARSING_ERROR, "Parsing error");
-        }
-        return temp_var((uint32_t)v);
-      }
-      case Expr::Variable: return build_access(e.text, e.access);
+      case Expr::Number:  // :294-306: the literal must fit u32
+        if (e.num_overflow) fail(C2A_PROG_PARSING_ERROR, "Parsing error");
+        return temp_var(e.num);
+      case Expr::Variable: return build_access(e.key, e.access);
       default: fail(C2A_PROG_EXPRESSION_NOT_IMPLEMENTED, "Expression not implemented");
     }
   }
 
   Ref handle_call(const Expr& e) {  // :315-419
-    auto def = prog.defs.find(e.text);
-    if (def == prog.defs.end()) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
-    const Callable& c = def->second;
-    std::vector<uint32_t> args;
+    if (!e.callee) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
+    const Callable& c = *e.callee;
+    Small<uint32_t, 8> args;
     for (auto& a : e.args) args.push_back(value_or_empty(process_expression(*a)));
     if (++depth > 10000) fail(C2A_PROG_CALL_ERROR, "Call error");
-    frames.push_back(Frame{e.text, {}, {{}}});  // push_context(false, id): empty context named after the callee
-    for (size_t i = 0; i < c.params.size() && i < args.size(); ++i) {
-      declare_item(D_Variable, c.params[i], {});
-      ctx().items[c.params[i]].var.val = args[i];
-    }
+    push_frame((uint32_t)e.key);  // push_context(false, id): empty context named after the callee
+    for (size_t i = 0; i < c.param_keys.size() && i < args.size(); ++i)
+      declare_item(D_Variable, c.param_keys[i], Path()).var.val = args[(uint32_t)i];
     process_statements(c.body);
     Ref ret;
     if (c.is_function) {
       ret.kind = Ref::TempVar;
-      auto it = ctx().items.find(RETURN_VAR);
-      if (it != ctx().items.end() && it->second.type == D_Variable && !it->second.var.is_array) ret.value = it->second.var.val;
+      Item* it = ctx().find(kReturn);
+      if (it && it->type == D_Variable && !it->var.is_array) ret.value = it->var.val;
     } else {
       ret.kind = Ref::TempComp;
       ret.comp = std::make_shared<SigMap>();
-      for (auto* list : {&c.inputs, &c.outputs})
-        for (auto& name : *list) {
-          auto it = ctx().items.find(name);
-          if (it == ctx().items.end() || it->second.type != D_Signal) runtime_error("Item not declared: get_signal: " + name);
-          (*ret.comp)[name] = it->second.sig;
+      ret.comp->v.reserve(c.input_keys.size() + c.output_keys.size());
+      for (auto* list : {&c.input_keys, &c.output_keys})
+        for (Key name : *list) {
+          Item* it = ctx().find(name);
+          if (!it || it->type != D_Signal) runtime_error("Item not declared: get_signal: " + key_str(name));
+          ret.comp->set(name, it->sig);
         }
     }
-    frames.pop_back();
+    pop_frame();
     --depth;
     return ret;
   }
@@ -777,15 +976,17 @@ struct Walker {
     }
   }
 
+  // NOTE: an Item& / SigTree& into the frame dies with the next declare_item (make_constant declares): what is needed
+  // across such a call is copied first (scalars are the common case and copy without touching the heap).
   void handle_substitution(const Stmt& s) {  // :192-277
-    Ref lh = build_access(s.name, s.access);
+    Ref lh = build_access(s.key, s.access);
     Ref rh = process_expression(*s.e);
-    Item& target = item(s.name, "get_item_data_type");
-    switch (target.type) {
+    const DataType target = item(s.key, "get_item_data_type").type;
+    switch (target) {
       case D_Variable: {
         std::optional<uint32_t> v = variable_value(rh);
-        Item& it = item(s.name, "set_variable");
-        auto& slot = nested_get_mut(it.var, access_to_u32(lh.access));
+        Item& it = item(s.key, "set_variable");
+        auto& slot = lh.access.empty() ? it.var : nested_get_mut(it.var, access_to_u32(lh.access));
         if (slot.is_array) runtime_error("Data Item content is not a single value");
         slot.val = v;
         break;
@@ -793,26 +994,28 @@ struct Walker {
       case D_Component:
         if (s.op == A_Var) {  // component instantiation
           SigMap map;
-          if (rh.kind == Ref::TempComp) map = *rh.comp;
-          else {
-            if (rh.kind != Ref::Named) runtime_error("Item not declared: get_component_map: " + rh.name);
+          if (rh.kind == Ref::TempComp) {
+            if (rh.comp.use_count() == 1) map = std::move(*rh.comp);
+            else map = *rh.comp;
+          } else {
+            if (rh.kind != Ref::Named) runtime_error("Item not declared: get_component_map: " + ref_name(rh));
             Item& src = item(rh.name, "get_component_map");
-            if (src.type != D_Component) runtime_error("Item not declared: get_component_map: " + rh.name);
+            if (src.type != D_Component) runtime_error("Item not declared: get_component_map: " + ref_name(rh));
             const auto& n = nested_get(src.comp, access_to_u32(rh.access));
             if (n.is_array) runtime_error("Data Item content is not a single value");
             map = n.val;
           }
-          auto& slot = nested_get_mut(item(s.name, "set_component").comp, access_to_u32(lh.access));
+          auto& slot = nested_get_mut(item(s.key, "set_component").comp, access_to_u32(lh.access));
           if (slot.is_array) runtime_error("Data Item content is not a single value");
           slot.val = std::move(map);
         } else if (s.op == A_ConstraintSignal) {
-          SigTree lhs_content = component_signal_content(lh);
-          if (lhs_content.is_array) {
-            SigTree rhs_content = content_for_access(rh);
+          const SigTree& lhs_ref = component_signal_content(lh);
+          if (lhs_ref.is_array) {  // (nothing is declared while two arrays are wired: the references stay valid)
+            const SigTree& rhs_content = content_for_access(rh);
             if (!rhs_content.is_array) fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
-            connect_signal_arrays(lhs_content, rhs_content);
+            connect_signal_arrays(lhs_ref, rhs_content);
           } else {
-            uint32_t comp_sig = lhs_content.val;
+            uint32_t comp_sig = lhs_ref.val;
             uint32_t assigned = signal_for_access(rh);
             ac.add_connection(assigned, comp_sig);
           }
@@ -820,14 +1023,15 @@ struct Walker {
         break;
       case D_Signal:
         if (s.e->kind == Expr::Variable) {
-          SigTree lhs_content = signal_content(lh);
-          if (lhs_content.is_array) {
-            SigTree rhs_content = content_for_access(rh);
+          const SigTree& lhs_ref = signal_content(lh);
+          if (lhs_ref.is_array) {
+            const SigTree& rhs_content = content_for_access(rh);
             if (!rhs_content.is_array) fail(C2A_PROG_INVALID_DATA_TYPE, "Invalid data type");
-            connect_signal_arrays(lhs_content, rhs_content);
+            connect_signal_arrays(lhs_ref, rhs_content);
           } else {
+            uint32_t lhs_id = lhs_ref.val;
             uint32_t out = signal_for_access(rh);
-            ac.add_connection(out, lhs_content.val);
+            ac.add_connection(out, lhs_id);
           }
         } else if (s.e->kind == Expr::Call || s.e->kind == Expr::InfixOp || s.e->kind == Expr::PrefixOp || s.e->kind == Expr::Number) {
           uint32_t given = signal_id(lh);
@@ -840,27 +1044,29 @@ struct Walker {
 
   void process_statements(const std::vector<StmtP>& v) { for (auto& s : v) process_statement(*s); }
 
+  void announce_signals(const SigTree& n, Key name, Path& at) {  // one add_signal per element, row-major (:79-108)
+    if (!n.is_array) { ac.add_signal(n.val, ctx().ctx, name, &at, false, std::nullopt); return; }
+    for (uint32_t i = 0; i < n.arr.size(); ++i) { at.push_back(i); announce_signals(n.arr[i], name, at); at.pop_back(); }
+  }
+
   void process_statement(const Stmt& s) {  // :36-189
     switch (s.kind) {
       case Stmt::InitBlock:
       case Stmt::Block: process_statements(s.stmts); break;
       case Stmt::Substitution: handle_substitution(s); break;
       case Stmt::Declaration: {
-        std::vector<Ref> dim_refs;
-        for (auto& d : s.dims) dim_refs.push_back(process_expression(*d));
-        std::vector<uint32_t> dims;
-        for (auto& r : dim_refs) dims.push_back(value_or_empty(r));
-        declare_item(s.dtype, s.name, dims);
-        if (s.dtype == D_Signal) {  // one add_signal per element, row-major (:79-108)
-          const SigTree& tree = ctx().items[s.name].sig;
-          std::vector<uint32_t> idx;
-          std::function<void(const SigTree&)> rec = [&](const SigTree& n) {
-            if (!n.is_array) { ac.add_signal(n.val, access_str(s.name, idx), std::nullopt); return; }
-            for (uint32_t i = 0; i < n.arr.size(); ++i) { idx.push_back(i); rec(n.arr[i]); idx.pop_back(); }
-          };
+        Path dims;
+        if (!s.dims.empty()) {
+          std::vector<Ref> dim_refs;
+          for (auto& d : s.dims) dim_refs.push_back(process_expression(*d));
+          for (auto& r : dim_refs) dims.push_back(value_or_empty(r));
+        }
+        Item& it = declare_item(s.dtype, s.key, dims);
+        if (s.dtype == D_Signal) {
           // a zero-length dimension: the reference's index loop still visits index 0 once and fails (:96, IndexOutOfBounds)
-          for (uint32_t d : dims) if (d == 0) runtime_error("Index out of bounds");
-          rec(tree);
+          for (uint32_t k = 0; k < dims.size(); ++k) if (dims[k] == 0) runtime_error("Index out of bounds");
+          Path at;
+          announce_signals(it.sig, s.key, at);
         }
         break;
       }
@@ -884,8 +1090,7 @@ struct Walker {
       }
       case Stmt::Return: {  // :160-174 — no early exit in the reference either
         uint32_t v = value_or_empty(process_expression(*s.e));
-        declare_item(D_Variable, RETURN_VAR, {});
-        ctx().items[RETURN_VAR].var.val = v;
+        declare_item(D_Variable, kReturn, Path()).var.val = v;
         break;
       }
       case Stmt::Assert:
@@ -903,10 +1108,10 @@ struct c2a_program {
   front::Sink sink;
   std::string error;
   std::vector<uint32_t> inputs, outputs;          // signal ids tagged by the prefix match of src/program.rs:57-66, ascending
-  std::vector<std::string> input_names, output_names;
   std::vector<std::string> main_inputs, main_outputs;  // declared names of the main template
   std::vector<uint8_t> packed_kinds;                   // c2a_program_packed(): the recorded calls as a packed stream
   std::vector<uint32_t> packed_words;
+  std::unordered_map<uint32_t, std::string> spelled;   // names handed out by c2a_program_signal_name (pointers stay valid)
 };
 
 static int compile_impl(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
@@ -914,41 +1119,43 @@ static int compile_impl(c2a_program* p, const std::string& src, const std::strin
   p->sink = Sink();
   p->sink.into = into;
   p->error.clear();
-  p->inputs.clear(); p->outputs.clear(); p->input_names.clear(); p->output_names.clear();
+  p->spelled.clear();
+  p->inputs.clear(); p->outputs.clear();
   try {
     Program prog;
     std::set<std::string> seen;
     parse_into(prog, src, file, dir, seen);
     if (!prog.main || prog.main->kind != Expr::Call) fail(C2A_PROG_MAIN_NOT_A_CALL, "Main expression not a call");  // program.rs:68
-    auto def = prog.defs.find(prog.main->text);
-    if (def == prog.defs.end() || def->second.is_function) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
-    const Callable& main = def->second;
+    p->sink.sym.annotate(prog);
+    const Callable* maindef = prog.main->callee;
+    if (!maindef || maindef->is_function) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
+    const Callable& main = *maindef;
     Walker w(prog, p->sink);
     std::vector<std::optional<uint32_t>> values;  // program.rs:30-37
     for (auto& a : prog.main->args) values.push_back(w.variable_value(w.process_expression(*a)));
-    for (size_t i = 0; i < main.params.size() && i < values.size(); ++i) {  // :40-51 declared in the ROOT context
-      w.declare_item(D_Variable, main.params[i], {});
-      w.ctx().items[main.params[i]].var.val = values[i];
-    }
+    for (size_t i = 0; i < main.param_keys.size() && i < values.size(); ++i)  // :40-51 declared in the ROOT context
+      w.declare_item(D_Variable, main.param_keys[i], Path()).var.val = values[i];
     w.process_statements(main.body);  // :54-55
     p->main_inputs = main.inputs;
     p->main_outputs = main.outputs;
-    // :57-66 — prefix match over ALL signal names ("0.c" also tags "0.const_signal_*"): replicate
-    auto tag = [&](const std::vector<std::string>& keys, std::vector<uint32_t>& ids, std::vector<std::string>& names, bool input) {
+    // :57-66 — prefix match over ALL signal names ("0.c" also tags "0.const_signal_*"): replicate.  Only names of the root
+    // context can start with "0." (every other context is named after a template or function).
+    const uint32_t root = p->sink.sym.intern("0");
+    auto tag = [&](const std::vector<std::string>& keys, std::vector<uint32_t>& ids, bool input) {
       std::map<uint32_t, std::string> m;
-      for (auto& k : keys) {
-        std::string filter = "0." + k;
-        for (uint32_t id = 0; id < p->sink.names.size(); ++id)
-          if (p->sink.names[id].compare(0, filter.size(), filter) == 0) m[id] = p->sink.names[id];
+      for (uint32_t id = 0; id < p->sink.names.size(); ++id) {
+        if (p->sink.names[id].ctx != root) continue;
+        std::string name = p->sink.name_of(id);
+        for (auto& k : keys)
+          if (name.compare(2, k.size(), k) == 0) { m[id] = name; break; }
       }
       for (auto& kv : m) {
         ids.push_back(kv.first);
-        names.push_back(kv.second);
         if (into) (input ? c2a_add_input : c2a_add_output)(into, kv.first, kv.second.c_str());
       }
     };
-    tag(main.inputs, p->inputs, p->input_names, true);
-    tag(main.outputs, p->outputs, p->output_names, false);
+    tag(main.inputs, p->inputs, true);
+    tag(main.outputs, p->outputs, false);
   } catch (const front::Error& e) {
     p->error = e.text;
     return e.code;
@@ -989,7 +1196,13 @@ int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {
 uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.events.size(); }
 const c2a_event* c2a_program_events(const c2a_program* p) { return p->sink.events.data(); }
 uint64_t c2a_program_num_signals(const c2a_program* p) { return p->sink.names.size(); }
-const char* c2a_program_signal_name(const c2a_program* p, uint32_t id) { return id < p->sink.names.size() ? p->sink.names[id].c_str() : nullptr; }
+const char* c2a_program_signal_name(const c2a_program* cp, uint32_t id) {  // spelled on first request, then kept
+  if (!cp || id >= cp->sink.names.size()) return nullptr;
+  c2a_program* p = const_cast<c2a_program*>(cp);
+  auto it = p->spelled.find(id);
+  if (it == p->spelled.end()) it = p->spelled.emplace(id, p->sink.name_of(id)).first;
+  return it->second.c_str();
+}
 uint32_t c2a_program_num_inputs(const c2a_program* p) { return (uint32_t)p->inputs.size(); }
 uint32_t c2a_program_num_outputs(const c2a_program* p) { return (uint32_t)p->outputs.size(); }
 const uint32_t* c2a_program_inputs(const c2a_program* p) { return p->inputs.data(); }

@@ -232,3 +232,27 @@ def test_large_loop_is_linear(c2a):
     comp = c2a.compile(None, source=src)
     assert comp.gate_array().shape[0] == 200000
     assert time.time() - t0 < 30
+
+
+# ---- the walker's runtime model on programs the reference fixtures do not reach ------------------------------------
+@pytest.mark.parametrize("case", range(len(fx.WALKER_STRESS)))
+def test_walker_stress_programs(c2a, case):
+    import ctypes as C
+    import hashlib
+    src, status, err, n_events, n_signals, digest = fx.WALKER_STRESS[case]
+    lib = c2a.lib
+    p = lib.c2a_program_new()
+    try:
+        st = lib.c2a_program_compile_source(p, src.encode(), None, None)
+        assert st == status
+        assert (lib.c2a_program_error(p).decode() if st else "") == err
+        n, ns = int(lib.c2a_program_num_events(p)), int(lib.c2a_program_num_signals(p))
+        assert (n, ns) == (n_events, n_signals)
+        ev = C.string_at(lib.c2a_program_events(p), 16 * n) if n else b""
+        names = [lib.c2a_program_signal_name(p, i) for i in range(ns)]
+        u32p = lambda q: C.cast(q, C.POINTER(C.c_uint32))
+        ins = [u32p(lib.c2a_program_inputs(p))[i] for i in range(lib.c2a_program_num_inputs(p))]
+        outs = [u32p(lib.c2a_program_outputs(p))[i] for i in range(lib.c2a_program_num_outputs(p))]
+        assert hashlib.sha256(ev + b"|" + b",".join(names) + b"|" + repr((ins, outs)).encode()).hexdigest()[:16] == digest
+    finally:
+        lib.c2a_program_free(p)
