@@ -167,6 +167,8 @@ def main():
     ap.add_argument("--stream", default="packed", choices=["packed", "aos"],
                     help="event stream format handed to the emitter: packed (kinds byte + payload words, c2a_emit_packed_*) or 16-byte c2a_event records")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-circuits-in-flight e2e leg")
+    ap.add_argument("--no-from-source", action="store_true", help="skip the .circom-text-to-circuit leg")
+    ap.add_argument("--source-chains", type=int, default=1832, help="MiMC chains of the from_source leg (1832 = 1 M gates)")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
     args = ap.parse_args()
 
@@ -546,6 +548,29 @@ def main():
     else:
         gates_h = ins_n = outs_n = None
 
+    # ---- from_source (N = 1, extra): the same workload family as .circom TEXT -> front end (parse + AST walk on one host core,
+    #      csrc/c2a_front.cpp) -> packed stream -> device emitter -> build -> renumbered gates + named wires on the host.
+    #      What a user of compile() sees; the walk, not the device, sets this number.
+    from_source = None
+    if world == 1 and not args.no_from_source:
+        Ws = max(1, min(args.source_chains, args.chains))
+        src_text = c2a.workloads.mimc_circom_source(Ws, args.rounds)
+        t0 = time.perf_counter()
+        dc = c2a.compile(None, source=src_text, emitter="device", context=ctx)
+        t1 = time.perf_counter()
+        info_s = ctx.emit_packed(dc._kinds, dc._words, dc._flags)
+        _o, _w, g_s, wc_s = ctx.emitted_build_circuit(dc.input_signals, dc.output_signals, want_order=False, want_wires=False)
+        ev_s = dc.events
+        named_s = np.concatenate([dc.input_signals, dc.output_signals, ev_s[(ev_s[:, 0] & 0xFF) == 1][:, 1]]).astype(np.uint32)
+        w_s = ctx.emitted_signal_wires(named_s)
+        t2 = time.perf_counter()
+        assert info_s["path"] == 1 and g_s.shape[0] == info_s["n_gates"] and w_s.shape[0] == named_s.shape[0] and wc_s > 0
+        from_source = {"value": info_s["n_gates"] / (t2 - t0), "unit": "gates/s", "gates": int(info_s["n_gates"]), "events": int(ev_s.shape[0]),
+                       "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": t2 - t1, "host_threads": 1,
+                       "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core) + packing = walk_s; emit + build + named-wire lookup through "
+                               "pageable buffers = device_s" % Ws}
+        del dc
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -613,6 +638,8 @@ def main():
         if "value" in pipe:
             pipe["h2d_bytes_per_step"], pipe["d2h_bytes_per_step"] = int(h2d), int(d2h)
         out["e2e_pipelined"] = pipe
+    if from_source is not None:
+        out["from_source"] = from_source
     if host_emit:
         out["e2e_host_emitter"] = {"value": host_emit["gates_per_s"], "unit": "gates/s", "emit_s": host_emit["emit_s"], "build_s": host_emit["build_s"],
                                    "note": "same circuit through the host union-find emitter (c2a_emit_events + c2a_build_circuit), pageable buffers, 1 step"}

@@ -161,6 +161,36 @@ def mimc_chains(W: int, rounds: int = 91, variant: str = "inorder") -> Workload:
         n_gates=gpc * W, n_signals=base0 + S * W, meta={"W": W, "rounds": rounds, "variant": variant, "signals_per_chain": S})
 
 
+def mimc_circom_source(W: int, rounds: int = 91) -> str:
+    """BASELINE config 5 as a real .circom program (W chains of `rounds` MiMC-7 rounds x -> (x + k + c_i)^7, c_i = i, u32 arithmetic):
+    what the front end (csrc/c2a_front.cpp) walks when the pipeline is driven from source text instead of a synthetic stream."""
+    return """pragma circom 2.0.0;
+template Round(c) {
+    signal input x; signal input k; signal output y;
+    signal t; signal t2; signal t4; signal t6;
+    t <== x + k + c;
+    t2 <== t * t; t4 <== t2 * t2; t6 <== t4 * t2;
+    y <== t6 * t;
+}
+template MiMC(n) {
+    signal input x_in; signal input k; signal output out;
+    component r[n];
+    for (var i = 0; i < n; i++) {
+        r[i] = Round(i);
+        r[i].k <== k;
+        if (i == 0) { r[i].x <== x_in; } else { r[i].x <== r[i - 1].y; }
+    }
+    out <== r[n - 1].y + k;
+}
+template Main(W, n) {
+    signal input in[W]; signal input key; signal output out[W];
+    component m[W];
+    for (var w = 0; w < W; w++) { m[w] = MiMC(n); m[w].x_in <== in[w]; m[w].k <== key; out[w] <== m[w].out; }
+}
+component main = Main(%d, %d);
+""" % (W, rounds)
+
+
 def poseidon_shaped(t: int = 3, RF: int = 8, RP: int = 57) -> Workload:
     """Poseidon(2)-shaped permutation (config 2): ARC = AAdd with per-round constants c=(round*t+lane+1),
     S-box x^5 = 3 AMul, MDS = t*t AMul-by-const + t*(t-1) AAdd.  t=3,RF=8,RP=57 -> 1413 gates."""

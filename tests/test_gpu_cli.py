@@ -89,37 +89,12 @@ def test_cli_writes_the_three_files(c2a, orc, tmp_path):  # src/main.rs:34-47
     assert lines[4:4 + G] == [f"2 1 {a} {b} {o} {names[op]}" for op, a, b, o in want["gates"].tolist()]
 
 
-MIMC_SRC = """pragma circom 2.0.0;
-template Round(c) {
-    signal input x; signal input k; signal output y;
-    signal t; signal t2; signal t4; signal t6;
-    t <== x + k + c;
-    t2 <== t * t; t4 <== t2 * t2; t6 <== t4 * t2;
-    y <== t6 * t;
-}
-template MiMC(n) {
-    signal input x_in; signal input k; signal output out;
-    component r[n];
-    for (var i = 0; i < n; i++) {
-        r[i] = Round(i);
-        r[i].k <== k;
-        if (i == 0) { r[i].x <== x_in; } else { r[i].x <== r[i - 1].y; }
-    }
-    out <== r[n - 1].y + k;
-}
-template Main(W, n) {
-    signal input in[W]; signal input key; signal output out[W];
-    component m[W];
-    for (var w = 0; w < W; w++) { m[w] = MiMC(n); m[w].x_in <== in[w]; m[w].k <== key; out[w] <== m[w].out; }
-}
-component main = Main(48, 91);
-"""
 
 
 def test_mimc_circom_through_packed_stream_named_wires_and_evaluator(c2a, ctx):
     """BASELINE config 5 as a real .circom program (MiMC-7 rounds x^7 with c_i = i, u32 arithmetic): front end -> packed stream ->
     device emitter -> build (gates only) -> named-wire lookup -> GPU evaluator, checked against the function computed in Python"""
-    comp = c2a.compile(None, source=MIMC_SRC, context=ctx)
+    comp = c2a.compile(None, source=c2a.workloads.mimc_circom_source(48, 91), context=ctx)
     kinds_b, words, flags = c2a.pack_events(comp.events)
     assert flags == 1                                     # the walker numbers its signals densely (src/runtime.rs:120-125)
     info = ctx.emit_packed(kinds_b, words, flags)
@@ -170,7 +145,7 @@ def test_compile_with_the_device_emitter_gives_the_same_bristol_circuit(c2a, ctx
     """compile(emitter="device"): the walk only records its calls, build_circuit() replays them on the GPU (packed stream) and
     looks the named wires up - same BristolCircuit and same CircuitError as the host-emitter Compiler (src/compiler.rs:321-494)"""
     sources = [fx.ADD_ZERO, fx.INFIX_OPS, fx.MAT_ELEM_MUL, fx.SUM, fx.X_EQ_X, fx.CONSTANT_SUM, fx.DIRECT_OUTPUT,
-               fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), MIMC_SRC.replace("Main(48, 91)", "Main(5, 7)")]
+               fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), c2a.workloads.mimc_circom_source(5, 7)]
     for src in sources:
         host = c2a.compile(None, source=src, context=ctx).build_circuit()
         dev = c2a.compile(None, source=src, context=ctx, emitter="device")
