@@ -18,12 +18,15 @@
 // (c2a_program_signal_name, the input / output prefix match, a host Compiler that wants the names).
 // u32 arithmetic on variables follows a release build: + * ** wrap, shifts use the low 5 bits, - / \ % error as in
 // src/process.rs:649-750.
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <functional>
 #include <map>
+#include <new>
 #include <memory>
 #include <optional>
 #include <set>
@@ -531,6 +534,11 @@ struct Small {
   T a[N];
   uint32_t n = 0;
   std::vector<T> more;
+  Small() = default;
+  Small(const Small& o) : n(o.n), more(o.more) { for (uint32_t i = 0; i < n && i < (uint32_t)N; ++i) a[i] = o.a[i]; }
+  Small(Small&& o) noexcept : n(o.n), more(std::move(o.more)) { for (uint32_t i = 0; i < n && i < (uint32_t)N; ++i) a[i] = o.a[i]; }
+  Small& operator=(const Small& o) { n = o.n; more = o.more; for (uint32_t i = 0; i < n && i < (uint32_t)N; ++i) a[i] = o.a[i]; return *this; }
+  Small& operator=(Small&& o) noexcept { n = o.n; more = std::move(o.more); for (uint32_t i = 0; i < n && i < (uint32_t)N; ++i) a[i] = o.a[i]; return *this; }
   void push_back(const T& v) { if (n < (uint32_t)N) a[n] = v; else more.push_back(v); ++n; }
   void pop_back() { if (n > (uint32_t)N) more.pop_back(); --n; }
   uint32_t size() const { return n; }
@@ -654,6 +662,37 @@ struct Frame {
   }
 };
 
+// Growable array of trivially copyable records on realloc(): for the blocks the recorded stream reaches (hundreds of MB), glibc
+// grows the mapping in place (mremap) - no copy, and only the new pages are touched.  std::vector allocates, copies and
+// first-touches a whole new block at every doubling, which tripled the cost of the replayed appends below.
+template <class T>
+struct PodVec {
+  T* p = nullptr;
+  size_t n = 0, cap = 0;
+  PodVec() = default;
+  PodVec(const PodVec&) = delete;
+  PodVec& operator=(const PodVec&) = delete;
+  PodVec(PodVec&& o) noexcept : p(o.p), n(o.n), cap(o.cap) { o.p = nullptr; o.n = o.cap = 0; }
+  PodVec& operator=(PodVec&& o) noexcept { if (this != &o) { free(p); p = o.p; n = o.n; cap = o.cap; o.p = nullptr; o.n = o.cap = 0; } return *this; }
+  ~PodVec() { free(p); }
+  size_t size() const { return n; }
+  size_t capacity() const { return cap; }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  void reserve(size_t m) {
+    if (m <= cap) return;
+    size_t c = std::max<size_t>(m, std::max<size_t>(2 * cap, 1024));
+    T* q = (T*)realloc(p, c * sizeof(T));
+    if (!q) throw std::bad_alloc();
+    p = q;
+    cap = c;
+  }
+  void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
+  void resize(size_t m) { reserve(m); if (m > n) memset((void*)(p + n), 0, (m - n) * sizeof(T)); n = m; }
+};
+
 struct SigName {  // "<ctx>.<base>[i][j]..." spelled on demand (runtime.rs:594-608, process.rs:464-474, 558-579)
   uint32_t ctx;       // context name symbol
   uint32_t kind_n;    // kind (2 bits: 0 declared name, 1 const_signal_<a>, 2 random_<a>) | number of indices << 2
@@ -663,9 +702,9 @@ struct SigName {  // "<ctx>.<base>[i][j]..." spelled on demand (runtime.rs:594-6
 
 struct Sink {  // where add_signal / add_gate / add_connection go
   c2a_compiler* into = nullptr;
-  std::vector<c2a_event> events;
-  std::vector<SigName> names;  // by signal id (ids are sequential from 0)
-  std::vector<uint32_t> idx;   // array indices of the declared names
+  PodVec<c2a_event> events;
+  PodVec<SigName> names;  // by signal id (ids are sequential from 0)
+  PodVec<uint32_t> idx;   // array indices of the declared names
   Symbols sym;
   void check(int st) {
     if (st == C2A_OK) return;
@@ -685,8 +724,7 @@ struct Sink {  // where add_signal / add_gate / add_connection go
     return s;
   }
   void add_signal(uint32_t id, uint32_t ctx, Key name, const Path* indices, bool random, std::optional<uint32_t> value) {
-    if (names.size() == id) names.emplace_back();
-    else if (names.size() < id) names.resize((size_t)id + 1);
+    if (names.size() <= id) names.resize((size_t)id + 1);
     SigName& n = names[id];
     n.ctx = ctx;
     n.idx_off = (uint32_t)idx.size();
@@ -705,6 +743,41 @@ struct Sink {  // where add_signal / add_gate / add_connection go
   void add_connection(uint32_t a, uint32_t b) {
     events.push_back(c2a_event{(uint32_t)C2A_EV_CONNECT, a, b, 0});
     if (into) check(c2a_add_connection(into, a, b));
+  }
+  // Replay of an earlier instance of the same callable with the same arguments (Walker::handle_call): the calls
+  // events[ev_begin, ev_end) declared the signals [id_begin, id_end); the same calls are recorded again with every signal id
+  // moved by delta.  A call starts an empty context, so each id in the block belongs to the block.
+  void replay(uint64_t ev_begin, uint64_t ev_end, uint32_t id_begin, uint32_t id_end, uint32_t delta) {
+    const uint32_t n_ids = id_end - id_begin, new_begin = id_begin + delta;
+    // (capacity first, then plain appends: the source slice lives in the same vector, and nothing is written twice)
+    names.reserve((size_t)new_begin + n_ids);
+    if (names.size() < new_begin) names.resize(new_begin);
+    for (uint32_t i = 0; i < n_ids; ++i) {
+      SigName nm = names[id_begin + i];
+      if ((nm.kind_n & 3u) == 2u) nm.a += delta;  // random_<id>
+      if (names.size() == (size_t)new_begin + i) names.push_back(nm);  // (declared names share their index list)
+      else names[new_begin + i] = nm;
+    }
+    const size_t base = events.size();
+    events.reserve(base + (ev_end - ev_begin));
+    for (uint64_t i = ev_begin; i < ev_end; ++i) {
+      c2a_event e = events[i];
+      const uint32_t kind = e.kind & 0xFFu;
+      e.a += delta;
+      if (kind >= C2A_EV_GATE) e.b += delta;       // gate, connection: second signal id (a signal event keeps its constant value)
+      if (kind == C2A_EV_GATE) e.c += delta;
+      events.push_back(e);
+    }
+    if (into)
+      for (size_t i = base; i < events.size(); ++i) {
+        const c2a_event& e = events[i];
+        switch (e.kind & 0xFFu) {
+          case C2A_EV_SIGNAL: check(c2a_add_signal(into, e.a, name_of(e.a).c_str(), 0, 0)); break;
+          case C2A_EV_SIGNAL_CONST: check(c2a_add_signal(into, e.a, name_of(e.a).c_str(), 1, e.b)); break;
+          case C2A_EV_GATE: check(c2a_add_gate(into, e.kind >> 8, e.a, e.b, e.c)); break;
+          default: check(c2a_add_connection(into, e.a, e.b)); break;
+        }
+      }
   }
 };
 
@@ -936,12 +1009,77 @@ struct Walker {
     }
   }
 
+  // ---- instance memo.  A call runs in a fresh, empty context (runtime.rs:75-77): it sees its argument values and nothing else,
+  // so what it emits is a function of (callable, arguments) up to the signal id it starts at - every id in its calls is one it
+  // allocated itself (its own signals, constants and temporaries, and those of the calls it makes).  From the second instance
+  // on, the walk of a (callable, arguments) pair is therefore replayed from the first one's slice of the recorded stream with
+  // the ids shifted, instead of being interpreted again (the reference interprets every instance).  Kept per pair: the
+  // slice, the id range, the result (component signal map / function value) and the call depth it needed (:call error).
+  struct MemoKey {
+    const Callable* c;
+    std::vector<uint32_t> args;
+    bool operator==(const MemoKey& o) const { return c == o.c && args == o.args; }
+  };
+  struct MemoHash {
+    size_t operator()(const MemoKey& k) const {
+      uint64_t h = (uint64_t)(uintptr_t)k.c * 0x9E3779B97F4A7C15ull;
+      for (uint32_t a : k.args) h = (h ^ a) * 0x100000001B3ull + (h >> 29);
+      return (size_t)h;
+    }
+  };
+  struct Memo {
+    uint32_t seen = 0;
+    bool cached = false;
+    uint64_t ev_begin = 0, ev_end = 0;
+    uint32_t id_begin = 0, id_end = 0;
+    uint64_t rel_depth = 0;  // deepest call below this one, relative to it
+    std::optional<uint32_t> value;
+    std::shared_ptr<SigMap> comp;
+  };
+  std::unordered_map<MemoKey, Memo, MemoHash> memo;
+  bool memo_on = true;
+  uint64_t depth_hw = 0;  // deepest call since the enclosing call began
+  uint64_t memo_hits = 0;
+
+  static void shift_ids(SigTree& t, uint32_t delta) {
+    if (!t.is_array) { t.val += delta; return; }
+    for (auto& x : t.arr) shift_ids(x, delta);
+  }
+
   Ref handle_call(const Expr& e) {  // :315-419
     if (!e.callee) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
     const Callable& c = *e.callee;
     Small<uint32_t, 8> args;
     for (auto& a : e.args) args.push_back(value_or_empty(process_expression(*a)));
     if (++depth > 10000) fail(C2A_PROG_CALL_ERROR, "Call error");
+    Memo* m = nullptr;
+    bool record = false;
+    if (memo_on) {
+      MemoKey key{&c, {}};
+      key.args.reserve(args.size());
+      for (uint32_t i = 0; i < args.size(); ++i) key.args.push_back(args[i]);
+      m = &memo[std::move(key)];  // (references into an unordered_map survive the insertions the nested calls make)
+      if (m->cached && depth + m->rel_depth <= 10000) {
+        const uint32_t delta = next_signal_id - m->id_begin;
+        ac.replay(m->ev_begin, m->ev_end, m->id_begin, m->id_end, delta);
+        next_signal_id += m->id_end - m->id_begin;
+        depth_hw = std::max(depth_hw, depth + m->rel_depth);
+        ++memo_hits;
+        Ref hit;
+        if (c.is_function) { hit.kind = Ref::TempVar; hit.value = m->value; }
+        else {
+          hit.kind = Ref::TempComp;
+          hit.comp = std::make_shared<SigMap>(*m->comp);
+          for (auto& kv : hit.comp->v) shift_ids(kv.second, delta);
+        }
+        --depth;
+        return hit;
+      }
+      record = !m->cached && m->seen++ >= 1;  // the second instance is the one that is kept: a pair seen once costs nothing
+    }
+    const uint64_t ev_begin = ac.events.size(), saved_hw = depth_hw;
+    const uint32_t id_begin = next_signal_id;
+    depth_hw = depth;
     push_frame((uint32_t)e.key);  // push_context(false, id): empty context named after the callee
     for (size_t i = 0; i < c.param_keys.size() && i < args.size(); ++i)
       declare_item(D_Variable, c.param_keys[i], Path()).var.val = args[(uint32_t)i];
@@ -963,6 +1101,15 @@ struct Walker {
         }
     }
     pop_frame();
+    if (record) {
+      m->ev_begin = ev_begin; m->ev_end = ac.events.size();
+      m->id_begin = id_begin; m->id_end = next_signal_id;
+      m->rel_depth = depth_hw - depth;
+      m->value = ret.value;
+      if (ret.comp) m->comp = std::make_shared<SigMap>(*ret.comp);
+      m->cached = true;
+    }
+    depth_hw = std::max(depth_hw, saved_hw);
     --depth;
     return ret;
   }
@@ -1131,6 +1278,7 @@ static int compile_impl(c2a_program* p, const std::string& src, const std::strin
     if (!maindef || maindef->is_function) fail(C2A_PROG_UNDEFINED_CALLABLE, "Undefined function or template");
     const Callable& main = *maindef;
     Walker w(prog, p->sink);
+    if (const char* off = getenv("C2A_FRONT_NO_MEMO")) w.memo_on = !(off[0] && off[0] != '0');  // diagnostic: interpret every instance
     std::vector<std::optional<uint32_t>> values;  // program.rs:30-37
     for (auto& a : prog.main->args) values.push_back(w.variable_value(w.process_expression(*a)));
     for (size_t i = 0; i < main.param_keys.size() && i < values.size(); ++i)  // :40-51 declared in the ROOT context

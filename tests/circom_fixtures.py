@@ -130,9 +130,10 @@ template ArgMax(n) {
 component main = ArgMax(N);
 """
 # Programs that stress the walker's runtime model (scopes, re-declared variables, the carried return variable, frames with
-# more items than the linear scan handles, `const_signal_<v>` spelled by the user, nested component arrays, every error class).
-# The expected streams were produced by the string-keyed walker this one replaced (a differential run over these programs,
-# the reference's tests/circuits/**/*.circom and every fixture: identical events, names, I/O tags and error texts).
+# more items than the linear scan handles, `const_signal_<v>` spelled by the user, nested component arrays, repeated instances
+# of one (template, arguments) pair - the instance memo -, every error class).  The expected streams were produced by the
+# string-keyed, memo-free walker this one replaced (a differential run over these programs, the reference's
+# tests/circuits/**/*.circom and every fixture: identical events, names, I/O tags and error texts).
 WALKER_STRESS = [
     ('pragma circom 2.0.0;\nfunction f(a, b) { var s = 0; for (var i = 0; i < a; i++) { if (i % 2 == 0) { s += i * b; } else { var t = i; s = s + t; } } return s; }\nfunction g(x) { if (x > 3) { return x * 2; } else { return x + 1; } }\ntemplate T(n) { signal input a[n]; signal output o; var acc = f(n, 3); signal p[n]; p[0] <== a[0] * acc; for (var i = 1; i < n; i++) { p[i] <== p[i-1] + a[i] * g(i); } o <== p[n-1]; }\ncomponent main = T(7);',
      0, '', 56, 35, '2989847c867c1ee8'),
@@ -174,4 +175,10 @@ WALKER_STRESS = [
      0, '', 88, 50, '82cf7bdb3fe3266b'),
     ('pragma circom 2.0.0;\ntemplate A() { signal input a; signal output b; var i = 0; while (i < 40) { i++; } var big[3][2]; big[2][1] = i; big[0][0] = big[2][1] + 1; b <== a * big[0][0]; var u = big[1][1]; b <== a + u; }\ncomponent main = A();',
      104, 'Empty data item', 6, 4, '914e86bb7f526dda'),
+    ('pragma circom 2.0.0;\ntemplate Inner(k) { signal input in[2][3]; signal output out[2][3]; signal mid[2]; for (var i = 0; i < 2; i++) { mid[i] <== in[i][0] * in[i][1]; for (var j = 0; j < 3; j++) { out[i][j] <== in[i][j] * k + mid[i] + 7; } } }\ntemplate Outer() { signal input x[2][3]; signal output y[2][3]; component c[2][2]; for (var a = 0; a < 2; a++) { for (var b = 0; b < 2; b++) { c[a][b] = Inner(3); } }\n c[0][0].in <== x; c[0][1].in <== c[0][0].out; c[1][0].in <== c[0][1].out; c[1][1].in <== c[1][0].out; y <== c[1][1].out; }\ncomponent main = Outer();',
+     0, '', 338, 196, '0109a201e98b4095'),
+    ('pragma circom 2.0.0;\nfunction fib(n) { var a = 0; var b = 1; for (var i = 0; i < n; i++) { var t = a + b; a = b; b = t; } return a; }\nfunction tri(n) { var s = 0; for (var i = 0; i <= n; i++) { s += fib(i % 7); } return s; }\ntemplate Leaf(a) { signal input c; signal output d; signal e; e <== c * tri(a); d <== e + fib(a) + 0; }\ntemplate Mid(n) { signal input c; signal output d; component l[n]; for (var i = 0; i < n; i++) { l[i] = Leaf(i % 3); if (i == 0) { l[i].c <== c; } else { l[i].c <== l[i-1].d; } } d <== l[n-1].d; }\ntemplate Top() { signal input c; signal output d[6]; component m[6]; for (var i = 0; i < 6; i++) { m[i] = Mid(4 + (i % 2)); m[i].c <== c; d[i] <== m[i].d * 2; } }\ncomponent main = Top();',
+     0, '', 427, 241, '81a40adf9ad060f6'),
+    ('pragma circom 2.0.0;\ntemplate Z() { signal output o; o <== 5 + 0; }\ntemplate Y() { signal input i; signal output o; component z1 = Z(); component z2 = Z(); component z3 = Z(); o <== i + z1.o + z2.o + z3.o; }\ntemplate X() { signal input i; signal output o; component y[5]; for (var k = 0; k < 5; k++) { y[k] = Y(); if (k == 0) { y[k].i <== i; } else { y[k].i <== y[k-1].o; } } o <== y[4].o; }\ncomponent main = X();',
+     0, '', 98, 57, '20061b8c61578208'),
 ]

@@ -256,3 +256,27 @@ def test_walker_stress_programs(c2a, case):
         assert hashlib.sha256(ev + b"|" + b",".join(names) + b"|" + repr((ins, outs)).encode()).hexdigest()[:16] == digest
     finally:
         lib.c2a_program_free(p)
+
+
+def _walk(c2a, src):
+    import ctypes as C
+    lib = c2a.lib
+    p = lib.c2a_program_new()
+    try:
+        st = lib.c2a_program_compile_source(p, src.encode(), None, None)
+        n, ns = int(lib.c2a_program_num_events(p)), int(lib.c2a_program_num_signals(p))
+        ev = C.string_at(lib.c2a_program_events(p), 16 * n) if n else b""
+        return st, lib.c2a_program_error(p), ev, [lib.c2a_program_signal_name(p, i) for i in range(ns)]
+    finally:
+        lib.c2a_program_free(p)
+
+
+def test_instance_memo_replays_exactly(c2a, monkeypatch):
+    """From the second instance on, a (callable, arguments) pair is replayed from the first one's slice of the recorded stream
+    with shifted signal ids instead of being interpreted again: calls, ids and names must be those of the full interpretation"""
+    sources = [c2a.workloads.mimc_circom_source(30, 91)] + [c[0] for c in fx.WALKER_STRESS]
+    for src in sources:
+        monkeypatch.delenv("C2A_FRONT_NO_MEMO", raising=False)
+        fast = _walk(c2a, src)
+        monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
+        assert _walk(c2a, src) == fast
