@@ -560,7 +560,7 @@ def main():
         t1 = time.perf_counter()
         info_s = ctx.emit_packed(dc._kinds, dc._words, dc._flags)
         _o, _w, g_s, wc_s = ctx.emitted_build_circuit(dc.input_signals, dc.output_signals, want_order=False, want_wires=False)
-        ev_s = dc.events
+        ev_s = dc._events_view
         named_s = np.concatenate([dc.input_signals, dc.output_signals, ev_s[(ev_s[:, 0] & 0xFF) == 1][:, 1]]).astype(np.uint32)
         w_s = ctx.emitted_signal_wires(named_s)
         t2 = time.perf_counter()

@@ -691,6 +691,7 @@ struct PodVec {
   }
   void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
   void resize(size_t m) { reserve(m); if (m > n) memset((void*)(p + n), 0, (m - n) * sizeof(T)); n = m; }
+  void resize_uninit(size_t m) { reserve(m); n = m; }
 };
 
 struct SigName {  // "<ctx>.<base>[i][j]..." spelled on demand (runtime.rs:594-608, process.rs:464-474, 558-579)
@@ -705,6 +706,7 @@ struct Sink {  // where add_signal / add_gate / add_connection go
   PodVec<c2a_event> events;
   PodVec<SigName> names;  // by signal id (ids are sequential from 0)
   PodVec<uint32_t> idx;   // array indices of the declared names
+  uint64_t n_gates = 0, n_conns = 0;  // counted as recorded: the packed form is then written in one pass
   Symbols sym;
   void check(int st) {
     if (st == C2A_OK) return;
@@ -738,10 +740,12 @@ struct Sink {  // where add_signal / add_gate / add_connection go
   }
   void add_gate(uint32_t op, uint32_t l, uint32_t r, uint32_t o) {
     events.push_back(c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), l, r, o});
+    ++n_gates;
     if (into) check(c2a_add_gate(into, op, l, r, o));
   }
   void add_connection(uint32_t a, uint32_t b) {
     events.push_back(c2a_event{(uint32_t)C2A_EV_CONNECT, a, b, 0});
+    ++n_conns;
     if (into) check(c2a_add_connection(into, a, b));
   }
   // Replay of an earlier instance of the same callable with the same arguments (Walker::handle_call): the calls
@@ -765,7 +769,8 @@ struct Sink {  // where add_signal / add_gate / add_connection go
       const uint32_t kind = e.kind & 0xFFu;
       e.a += delta;
       if (kind >= C2A_EV_GATE) e.b += delta;       // gate, connection: second signal id (a signal event keeps its constant value)
-      if (kind == C2A_EV_GATE) e.c += delta;
+      if (kind == C2A_EV_GATE) { e.c += delta; ++n_gates; }
+      else if (kind == C2A_EV_CONNECT) ++n_conns;
       events.push_back(e);
     }
     if (into)
@@ -1256,8 +1261,8 @@ struct c2a_program {
   std::string error;
   std::vector<uint32_t> inputs, outputs;          // signal ids tagged by the prefix match of src/program.rs:57-66, ascending
   std::vector<std::string> main_inputs, main_outputs;  // declared names of the main template
-  std::vector<uint8_t> packed_kinds;                   // c2a_program_packed(): the recorded calls as a packed stream
-  std::vector<uint32_t> packed_words;
+  front::PodVec<uint8_t> packed_kinds;                 // c2a_program_packed(): the recorded calls as a packed stream
+  front::PodVec<uint32_t> packed_words;
   std::unordered_map<uint32_t, std::string> spelled;   // names handed out by c2a_program_signal_name (pointers stay valid)
 };
 
@@ -1333,12 +1338,39 @@ int c2a_program_compile_source(c2a_program* p, const char* source, const char* i
 int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {
   if (!p || !out) return C2A_ERR_INVALID_ARGUMENT;
   const auto& ev = p->sink.events;
-  uint32_t flags = 0;
-  uint64_t nw = c2a_pack_events(ev.data(), ev.size(), nullptr, nullptr, &flags);
-  p->packed_kinds.resize(ev.size());
-  p->packed_words.resize(nw);
-  c2a_pack_events(ev.data(), ev.size(), p->packed_kinds.data(), p->packed_words.data(), &flags);
-  *out = c2a_packed_events{p->packed_kinds.data(), p->packed_words.data(), (uint64_t)ev.size(), nw, flags, 0};
+  const uint64_t n = ev.size();
+  // The walker numbers its signals 0, 1, 2, ... as it declares them (src/runtime.rs:120-125) and counts its gates and
+  // connections, so the dense packed form is written in ONE pass over the records (c2a_pack_events reads them three times).
+  uint64_t nw = 3 * p->sink.n_gates + 2 * p->sink.n_conns, w = 0, ns = 0;
+  p->packed_kinds.resize_uninit(n);
+  p->packed_words.resize_uninit(nw + 4);
+  uint8_t* kinds = p->packed_kinds.data();
+  uint32_t* words = p->packed_words.data();
+  bool ok = true;
+  for (uint64_t i = 0; i < n && ok; ++i) {
+    const c2a_event& e = ev[i];
+    const uint32_t k = e.kind & 0xFFu;
+    if (k <= C2A_EV_SIGNAL_CONST) { kinds[i] = (uint8_t)k; ok = e.a == ns++; }
+    else if (k == C2A_EV_GATE) {
+      const uint32_t op = e.kind >> 8;
+      ok = op < C2A_GATE_TYPE_COUNT && w + 3 <= nw;
+      kinds[i] = (uint8_t)(C2A_EV_GATE | (op << 2));
+      words[w] = e.a; words[w + 1] = e.b; words[w + 2] = e.c;
+      w += 3;
+    } else if (k == C2A_EV_CONNECT) {
+      ok = w + 2 <= nw;
+      kinds[i] = (uint8_t)C2A_EV_CONNECT;
+      words[w] = e.a; words[w + 1] = e.b;
+      w += 2;
+    } else ok = false;
+  }
+  uint32_t flags = C2A_PACKED_DENSE_IDS;
+  if (!ok || w != nw) {  // not the walker's usual shape: the general packer decides
+    nw = c2a_pack_events(ev.data(), n, nullptr, nullptr, &flags);
+    p->packed_words.resize_uninit(nw + 4);
+    c2a_pack_events(ev.data(), n, p->packed_kinds.data(), p->packed_words.data(), &flags);
+  }
+  *out = c2a_packed_events{p->packed_kinds.data(), p->packed_words.data(), n, nw, flags, 0};
   return C2A_OK;
 }
 uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.events.size(); }

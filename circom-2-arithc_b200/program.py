@@ -52,17 +52,26 @@ class DeviceCompiler:
         self._prog, self._device, self._ctx = prog, device, context
         self.value_type = "sint"
         n = int(lib.c2a_program_num_events(prog))
-        self.events = np.zeros((n, 4), dtype=np.uint32)
-        if n:
-            C.memmove(self.events.ctypes.data, lib.c2a_program_events(prog), 16 * n)
+        # The recorded calls and their packed form stay where the walker wrote them (hundreds of MB at 10 M gates): the arrays
+        # below are VIEWS of the program's memory, alive as long as this object; `events` hands out a copy on first use.
+        view = lambda p, k, ct, dt: np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(k,)) if k else np.zeros(0, dt)
+        self._events_view = view(lib.c2a_program_events(prog), 4 * n, C.c_uint32, np.uint32).reshape(n, 4)
+        self._events_copy = None
         ni, no = int(lib.c2a_program_num_inputs(prog)), int(lib.c2a_program_num_outputs(prog))
-        as_u32 = lambda p, k: np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint32)), shape=(k,)).copy() if k else np.zeros(0, np.uint32)
-        self.input_signals, self.output_signals = as_u32(lib.c2a_program_inputs(prog), ni), as_u32(lib.c2a_program_outputs(prog), no)
+        self.input_signals = view(lib.c2a_program_inputs(prog), ni, C.c_uint32, np.uint32).copy()
+        self.output_signals = view(lib.c2a_program_outputs(prog), no, C.c_uint32, np.uint32).copy()
         pk = PackedEvents()
         lib.c2a_program_packed(prog, C.byref(pk))
-        self._kinds = np.ctypeslib.as_array(C.cast(pk.kinds, C.POINTER(C.c_uint8)), shape=(n,)).copy() if n else np.zeros(0, np.uint8)
-        self._words = as_u32(pk.words, int(pk.n_words))
+        self._kinds = view(pk.kinds, n, C.c_uint8, np.uint8)
+        self._words = view(pk.words, int(pk.n_words), C.c_uint32, np.uint32)
         self._flags = int(pk.flags)
+
+    @property
+    def events(self) -> np.ndarray:
+        """the recorded add_signal / add_gate / add_connection calls as c2a_event rows (a private copy)"""
+        if self._events_copy is None:
+            self._events_copy = self._events_view.copy()
+        return self._events_copy
 
     def __del__(self):
         try:
@@ -99,7 +108,7 @@ class DeviceCompiler:
             if int(nd) in node_to_input:
                 raise CircuitError(Status.INCONSISTENCY, f"Node {int(nd)} used for both input {node_to_input[int(nd)]} and output {nm}")
         order, _wire, gates, wire_count = ctx.emitted_build_circuit(ins, outs, want_wires=False)
-        ev = self.events
+        ev = self._events_view
         consts = ev[(ev[:, 0] & 0xFF) == 1]
         consts = consts[np.argsort(consts[:, 1], kind="stable")]
         named = ctx.emitted_signal_wires(np.concatenate([ins, outs, consts[:, 1]]).astype(np.uint32))
