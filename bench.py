@@ -560,12 +560,11 @@ def main():
         t1 = time.perf_counter()
         info_s = ctx.emit_packed(dc._kinds, dc._words, dc._flags)
         _o, _w, g_s, wc_s = ctx.emitted_build_circuit(dc.input_signals, dc.output_signals, want_order=False, want_wires=False)
-        ev_s = dc._events_view
-        named_s = np.concatenate([dc.input_signals, dc.output_signals, ev_s[(ev_s[:, 0] & 0xFF) == 1][:, 1]]).astype(np.uint32)
+        named_s = np.concatenate([dc.input_signals, dc.output_signals, dc._const_signals]).astype(np.uint32)
         w_s = ctx.emitted_signal_wires(named_s)
         t2 = time.perf_counter()
         assert info_s["path"] == 1 and g_s.shape[0] == info_s["n_gates"] and w_s.shape[0] == named_s.shape[0] and wc_s > 0
-        from_source = {"value": info_s["n_gates"] / (t2 - t0), "unit": "gates/s", "gates": int(info_s["n_gates"]), "events": int(ev_s.shape[0]),
+        from_source = {"value": info_s["n_gates"] / (t2 - t0), "unit": "gates/s", "gates": int(info_s["n_gates"]), "events": int(dc._n_events),
                        "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": t2 - t1, "host_threads": 1,
                        "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core) + packing = walk_s; emit + build + named-wire lookup through "
                                "pageable buffers = device_s" % Ws}

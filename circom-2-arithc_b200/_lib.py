@@ -140,6 +140,9 @@ _SIGS = {
     "c2a_program_num_events": (u64, [vp]),
     "c2a_program_events": (vp, [vp]),
     "c2a_program_num_signals": (u64, [vp]),
+    "c2a_program_num_constants": (u64, [vp]),
+    "c2a_program_constant_signals": (vp, [vp]),
+    "c2a_program_constant_values": (vp, [vp]),
     "c2a_program_signal_name": (cp, [vp, u32]),
     "c2a_program_num_inputs": (u32, [vp]),
     "c2a_program_num_outputs": (u32, [vp]),

@@ -692,22 +692,38 @@ struct PodVec {
   void push_back(const T& v) { if (n == cap) reserve(n + 1); p[n++] = v; }
   void resize(size_t m) { reserve(m); if (m > n) memset((void*)(p + n), 0, (m - n) * sizeof(T)); n = m; }
   void resize_uninit(size_t m) { reserve(m); n = m; }
+  void append_self(size_t b, size_t e) {  // append a copy of [b, e) of this array
+    reserve(n + (e - b));
+    memcpy((void*)(p + n), (const void*)(p + b), (e - b) * sizeof(T));
+    n += e - b;
+  }
 };
 
 struct SigName {  // "<ctx>.<base>[i][j]..." spelled on demand (runtime.rs:594-608, process.rs:464-474, 558-579)
   uint32_t ctx;       // context name symbol
   uint32_t kind_n;    // kind (2 bits: 0 declared name, 1 const_signal_<a>, 2 random_<a>) | number of indices << 2
-  uint32_t a;         // name symbol / constant value / random suffix
+  uint32_t a;         // name symbol / constant value (random_<id>: the suffix is the signal id itself)
   uint32_t idx_off;   // first index in Sink::idx
 };
 
-struct Sink {  // where add_signal / add_gate / add_connection go
+// Where add_signal / add_gate / add_connection go.  The calls are recorded directly in the PACKED form the device emitter reads
+// (include/c2a.h: one kind byte per call, u32 payload words for gates and connections; the walker numbers its signals 0, 1, 2,
+// ... as it declares them, src/runtime.rs:120-125, so a signal call has no payload): 6 B per call instead of a 16-byte record,
+// nothing to convert before the H2D copy.  Constant values and the name records travel beside the stream.
+struct Sink {
   c2a_compiler* into = nullptr;
-  PodVec<c2a_event> events;
-  PodVec<SigName> names;  // by signal id (ids are sequential from 0)
-  PodVec<uint32_t> idx;   // array indices of the declared names
-  uint64_t n_gates = 0, n_conns = 0;  // counted as recorded: the packed form is then written in one pass
+  PodVec<uint8_t> kinds;         // per call: kind | gate type << 2
+  PodVec<uint32_t> words;        // gate: lhs, rhs, out; connection: a, b (signal ids)
+  PodVec<uint32_t> const_ids;    // the constant signals in declaration order ...
+  PodVec<uint32_t> const_vals;   // ... and their values
+  PodVec<SigName> names;         // by signal id
+  PodVec<uint32_t> idx;          // array indices of the declared names
+  PodVec<c2a_event> aos;         // the same calls as c2a_event records, written when somebody asks (c2a_program_events)
+  bool aos_valid = false;
   Symbols sym;
+  struct Mark { uint64_t k, w, c; uint32_t id; };  // a position in the recording
+  Mark mark() const { return Mark{kinds.size(), words.size(), const_ids.size(), (uint32_t)names.size()}; }
+
   void check(int st) {
     if (st == C2A_OK) return;
     std::string why = st == C2A_ERR_INVALID_ARGUMENT || st == C2A_ERR_REFERENCE_PANIC ? c2a_compiler_last_error(into) : c2a_status_string(st);
@@ -720,69 +736,86 @@ struct Sink {  // where add_signal / add_gate / add_connection go
     switch (n.kind_n & 3u) {
       case 0: s += sym.strs[n.a]; break;
       case 1: s += "const_signal_"; s += std::to_string(n.a); break;
-      default: s += "random_"; s += std::to_string(n.a); break;
+      default: s += "random_"; s += std::to_string(id); break;  // the suffix is the signal's own id
     }
     for (uint32_t k = 0; k < (n.kind_n >> 2); ++k) { s += '['; s += std::to_string(idx[n.idx_off + k]); s += ']'; }
     return s;
   }
   void add_signal(uint32_t id, uint32_t ctx, Key name, const Path* indices, bool random, std::optional<uint32_t> value) {
-    if (names.size() <= id) names.resize((size_t)id + 1);
-    SigName& n = names[id];
+    if (id != names.size()) fail(C2A_PROG_RUNTIME_ERROR, "Runtime error: internal: signal ids are not sequential");
+    SigName n;
     n.ctx = ctx;
     n.idx_off = (uint32_t)idx.size();
     const uint32_t ni = indices ? indices->size() : 0u;
-    if (random) { n.kind_n = 2u; n.a = id; }
+    if (random) { n.kind_n = 2u; n.a = 0; }
     else if (name >= kConstKey) { n.kind_n = 1u | (ni << 2); n.a = (uint32_t)name; }
     else { n.kind_n = 0u | (ni << 2); n.a = (uint32_t)name; }
     for (uint32_t k = 0; k < ni; ++k) idx.push_back((*indices)[k]);
-    events.push_back(c2a_event{value ? (uint32_t)C2A_EV_SIGNAL_CONST : (uint32_t)C2A_EV_SIGNAL, id, value.value_or(0), 0});
+    names.push_back(n);
+    kinds.push_back(value ? (uint8_t)C2A_EV_SIGNAL_CONST : (uint8_t)C2A_EV_SIGNAL);
+    if (value) { const_ids.push_back(id); const_vals.push_back(*value); }
     if (into) check(c2a_add_signal(into, id, name_of(id).c_str(), value.has_value(), value.value_or(0)));
   }
   void add_gate(uint32_t op, uint32_t l, uint32_t r, uint32_t o) {
-    events.push_back(c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), l, r, o});
-    ++n_gates;
+    kinds.push_back((uint8_t)(C2A_EV_GATE | (op << 2)));
+    words.reserve(words.size() + 3);
+    words.push_back(l); words.push_back(r); words.push_back(o);
     if (into) check(c2a_add_gate(into, op, l, r, o));
   }
   void add_connection(uint32_t a, uint32_t b) {
-    events.push_back(c2a_event{(uint32_t)C2A_EV_CONNECT, a, b, 0});
-    ++n_conns;
+    kinds.push_back((uint8_t)C2A_EV_CONNECT);
+    words.push_back(a); words.push_back(b);
     if (into) check(c2a_add_connection(into, a, b));
   }
-  // Replay of an earlier instance of the same callable with the same arguments (Walker::handle_call): the calls
-  // events[ev_begin, ev_end) declared the signals [id_begin, id_end); the same calls are recorded again with every signal id
-  // moved by delta.  A call starts an empty context, so each id in the block belongs to the block.
-  void replay(uint64_t ev_begin, uint64_t ev_end, uint32_t id_begin, uint32_t id_end, uint32_t delta) {
-    const uint32_t n_ids = id_end - id_begin, new_begin = id_begin + delta;
-    // (capacity first, then plain appends: the source slice lives in the same vector, and nothing is written twice)
-    names.reserve((size_t)new_begin + n_ids);
-    if (names.size() < new_begin) names.resize(new_begin);
-    for (uint32_t i = 0; i < n_ids; ++i) {
-      SigName nm = names[id_begin + i];
-      if ((nm.kind_n & 3u) == 2u) nm.a += delta;  // random_<id>
-      if (names.size() == (size_t)new_begin + i) names.push_back(nm);  // (declared names share their index list)
-      else names[new_begin + i] = nm;
+  // Replay of an earlier instance of the same callable with the same arguments (Walker::handle_call): the calls recorded
+  // between the marks b and e are recorded again with every signal id moved by delta.  A call starts an empty context, so each
+  // id in the slice belongs to the slice - every payload word is one, and the kind bytes and name records do not change.
+  void replay(const Mark& b, const Mark& e, uint32_t delta) {
+    const Mark at = mark();
+    kinds.append_self(b.k, e.k);
+    names.append_self(b.id, e.id);  // (declared names share their index list)
+    const_vals.append_self(b.c, e.c);
+    const_ids.reserve(const_ids.size() + (e.c - b.c));
+    for (uint64_t i = b.c; i < e.c; ++i) const_ids.push_back(const_ids[i] + delta);
+    words.reserve(words.size() + (e.w - b.w));
+    {
+      const uint32_t* src = words.data() + b.w;
+      uint32_t* dst = words.data() + words.size();
+      const uint64_t n = e.w - b.w;
+      for (uint64_t i = 0; i < n; ++i) dst[i] = src[i] + delta;
+      words.n += n;
     }
-    const size_t base = events.size();
-    events.reserve(base + (ev_end - ev_begin));
-    for (uint64_t i = ev_begin; i < ev_end; ++i) {
-      c2a_event e = events[i];
-      const uint32_t kind = e.kind & 0xFFu;
-      e.a += delta;
-      if (kind >= C2A_EV_GATE) e.b += delta;       // gate, connection: second signal id (a signal event keeps its constant value)
-      if (kind == C2A_EV_GATE) { e.c += delta; ++n_gates; }
-      else if (kind == C2A_EV_CONNECT) ++n_conns;
-      events.push_back(e);
-    }
-    if (into)
-      for (size_t i = base; i < events.size(); ++i) {
-        const c2a_event& e = events[i];
-        switch (e.kind & 0xFFu) {
-          case C2A_EV_SIGNAL: check(c2a_add_signal(into, e.a, name_of(e.a).c_str(), 0, 0)); break;
-          case C2A_EV_SIGNAL_CONST: check(c2a_add_signal(into, e.a, name_of(e.a).c_str(), 1, e.b)); break;
-          case C2A_EV_GATE: check(c2a_add_gate(into, e.kind >> 8, e.a, e.b, e.c)); break;
-          default: check(c2a_add_connection(into, e.a, e.b)); break;
+    if (into) {  // a host emitter is attached: it sees the calls one by one, as if they had been interpreted
+      uint64_t w = at.w, c = at.c;
+      uint32_t id = at.id;
+      for (uint64_t i = at.k; i < kinds.size(); ++i) {
+        const uint32_t kb = kinds[i];
+        switch (kb & 3u) {
+          case C2A_EV_SIGNAL: check(c2a_add_signal(into, id, name_of(id).c_str(), 0, 0)); ++id; break;
+          case C2A_EV_SIGNAL_CONST: check(c2a_add_signal(into, id, name_of(id).c_str(), 1, const_vals[c++])); ++id; break;
+          case C2A_EV_GATE: check(c2a_add_gate(into, kb >> 2, words[w], words[w + 1], words[w + 2])); w += 3; break;
+          default: check(c2a_add_connection(into, words[w], words[w + 1])); w += 2; break;
         }
       }
+    }
+  }
+  // the recording as c2a_event records (include/c2a.h), for callers of c2a_program_events
+  const PodVec<c2a_event>& events() {
+    if (aos_valid) return aos;
+    aos.resize_uninit(kinds.size());
+    uint64_t w = 0, c = 0;
+    uint32_t id = 0;
+    for (uint64_t i = 0; i < kinds.size(); ++i) {
+      const uint32_t kb = kinds[i];
+      switch (kb & 3u) {
+        case C2A_EV_SIGNAL: aos[i] = c2a_event{(uint32_t)C2A_EV_SIGNAL, id++, 0, 0}; break;
+        case C2A_EV_SIGNAL_CONST: aos[i] = c2a_event{(uint32_t)C2A_EV_SIGNAL_CONST, id++, const_vals[c++], 0}; break;
+        case C2A_EV_GATE: aos[i] = c2a_event{(uint32_t)C2A_EV_GATE | ((kb >> 2) << 8), words[w], words[w + 1], words[w + 2]}; w += 3; break;
+        default: aos[i] = c2a_event{(uint32_t)C2A_EV_CONNECT, words[w], words[w + 1], 0}; w += 2; break;
+      }
+    }
+    aos_valid = true;
+    return aos;
   }
 };
 
@@ -1035,8 +1068,7 @@ struct Walker {
   struct Memo {
     uint32_t seen = 0;
     bool cached = false;
-    uint64_t ev_begin = 0, ev_end = 0;
-    uint32_t id_begin = 0, id_end = 0;
+    Sink::Mark begin{}, end{};  // the instance's slice of the recording
     uint64_t rel_depth = 0;  // deepest call below this one, relative to it
     std::optional<uint32_t> value;
     std::shared_ptr<SigMap> comp;
@@ -1065,9 +1097,9 @@ struct Walker {
       for (uint32_t i = 0; i < args.size(); ++i) key.args.push_back(args[i]);
       m = &memo[std::move(key)];  // (references into an unordered_map survive the insertions the nested calls make)
       if (m->cached && depth + m->rel_depth <= 10000) {
-        const uint32_t delta = next_signal_id - m->id_begin;
-        ac.replay(m->ev_begin, m->ev_end, m->id_begin, m->id_end, delta);
-        next_signal_id += m->id_end - m->id_begin;
+        const uint32_t delta = next_signal_id - m->begin.id;
+        ac.replay(m->begin, m->end, delta);
+        next_signal_id += m->end.id - m->begin.id;
         depth_hw = std::max(depth_hw, depth + m->rel_depth);
         ++memo_hits;
         Ref hit;
@@ -1082,8 +1114,8 @@ struct Walker {
       }
       record = !m->cached && m->seen++ >= 1;  // the second instance is the one that is kept: a pair seen once costs nothing
     }
-    const uint64_t ev_begin = ac.events.size(), saved_hw = depth_hw;
-    const uint32_t id_begin = next_signal_id;
+    const Sink::Mark begin = ac.mark();
+    const uint64_t saved_hw = depth_hw;
     depth_hw = depth;
     push_frame((uint32_t)e.key);  // push_context(false, id): empty context named after the callee
     for (size_t i = 0; i < c.param_keys.size() && i < args.size(); ++i)
@@ -1107,8 +1139,7 @@ struct Walker {
     }
     pop_frame();
     if (record) {
-      m->ev_begin = ev_begin; m->ev_end = ac.events.size();
-      m->id_begin = id_begin; m->id_end = next_signal_id;
+      m->begin = begin; m->end = ac.mark();
       m->rel_depth = depth_hw - depth;
       m->value = ret.value;
       if (ret.comp) m->comp = std::make_shared<SigMap>(*ret.comp);
@@ -1261,8 +1292,6 @@ struct c2a_program {
   std::string error;
   std::vector<uint32_t> inputs, outputs;          // signal ids tagged by the prefix match of src/program.rs:57-66, ascending
   std::vector<std::string> main_inputs, main_outputs;  // declared names of the main template
-  front::PodVec<uint8_t> packed_kinds;                 // c2a_program_packed(): the recorded calls as a packed stream
-  front::PodVec<uint32_t> packed_words;
   std::unordered_map<uint32_t, std::string> spelled;   // names handed out by c2a_program_signal_name (pointers stay valid)
 };
 
@@ -1335,46 +1364,17 @@ int c2a_program_compile_source(c2a_program* p, const char* source, const char* i
   if (!p || !source) return C2A_ERR_INVALID_ARGUMENT;
   return compile_impl(p, source, "<source>", include_dir ? include_dir : ".", into);
 }
-int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {
+int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {  // the recording itself: nothing is converted
   if (!p || !out) return C2A_ERR_INVALID_ARGUMENT;
-  const auto& ev = p->sink.events;
-  const uint64_t n = ev.size();
-  // The walker numbers its signals 0, 1, 2, ... as it declares them (src/runtime.rs:120-125) and counts its gates and
-  // connections, so the dense packed form is written in ONE pass over the records (c2a_pack_events reads them three times).
-  uint64_t nw = 3 * p->sink.n_gates + 2 * p->sink.n_conns, w = 0, ns = 0;
-  p->packed_kinds.resize_uninit(n);
-  p->packed_words.resize_uninit(nw + 4);
-  uint8_t* kinds = p->packed_kinds.data();
-  uint32_t* words = p->packed_words.data();
-  bool ok = true;
-  for (uint64_t i = 0; i < n && ok; ++i) {
-    const c2a_event& e = ev[i];
-    const uint32_t k = e.kind & 0xFFu;
-    if (k <= C2A_EV_SIGNAL_CONST) { kinds[i] = (uint8_t)k; ok = e.a == ns++; }
-    else if (k == C2A_EV_GATE) {
-      const uint32_t op = e.kind >> 8;
-      ok = op < C2A_GATE_TYPE_COUNT && w + 3 <= nw;
-      kinds[i] = (uint8_t)(C2A_EV_GATE | (op << 2));
-      words[w] = e.a; words[w + 1] = e.b; words[w + 2] = e.c;
-      w += 3;
-    } else if (k == C2A_EV_CONNECT) {
-      ok = w + 2 <= nw;
-      kinds[i] = (uint8_t)C2A_EV_CONNECT;
-      words[w] = e.a; words[w + 1] = e.b;
-      w += 2;
-    } else ok = false;
-  }
-  uint32_t flags = C2A_PACKED_DENSE_IDS;
-  if (!ok || w != nw) {  // not the walker's usual shape: the general packer decides
-    nw = c2a_pack_events(ev.data(), n, nullptr, nullptr, &flags);
-    p->packed_words.resize_uninit(nw + 4);
-    c2a_pack_events(ev.data(), n, p->packed_kinds.data(), p->packed_words.data(), &flags);
-  }
-  *out = c2a_packed_events{p->packed_kinds.data(), p->packed_words.data(), n, nw, flags, 0};
+  *out = c2a_packed_events{p->sink.kinds.data(), p->sink.words.data(), (uint64_t)p->sink.kinds.size(), (uint64_t)p->sink.words.size(),
+                           C2A_PACKED_DENSE_IDS, 0};
   return C2A_OK;
 }
-uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.events.size(); }
-const c2a_event* c2a_program_events(const c2a_program* p) { return p->sink.events.data(); }
+uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.kinds.size(); }
+const c2a_event* c2a_program_events(const c2a_program* p) { return const_cast<c2a_program*>(p)->sink.events().data(); }
+uint64_t c2a_program_num_constants(const c2a_program* p) { return p->sink.const_ids.size(); }
+const uint32_t* c2a_program_constant_signals(const c2a_program* p) { return p->sink.const_ids.data(); }
+const uint32_t* c2a_program_constant_values(const c2a_program* p) { return p->sink.const_vals.data(); }
 uint64_t c2a_program_num_signals(const c2a_program* p) { return p->sink.names.size(); }
 const char* c2a_program_signal_name(const c2a_program* cp, uint32_t id) {  // spelled on first request, then kept
   if (!cp || id >= cp->sink.names.size()) return nullptr;

@@ -55,8 +55,11 @@ class DeviceCompiler:
         # The recorded calls and their packed form stay where the walker wrote them (hundreds of MB at 10 M gates): the arrays
         # below are VIEWS of the program's memory, alive as long as this object; `events` hands out a copy on first use.
         view = lambda p, k, ct, dt: np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(k,)) if k else np.zeros(0, dt)
-        self._events_view = view(lib.c2a_program_events(prog), 4 * n, C.c_uint32, np.uint32).reshape(n, 4)
+        self._n_events = n
         self._events_copy = None
+        nc = int(lib.c2a_program_num_constants(prog))
+        self._const_signals = view(lib.c2a_program_constant_signals(prog), nc, C.c_uint32, np.uint32)
+        self._const_values = view(lib.c2a_program_constant_values(prog), nc, C.c_uint32, np.uint32)
         ni, no = int(lib.c2a_program_num_inputs(prog)), int(lib.c2a_program_num_outputs(prog))
         self.input_signals = view(lib.c2a_program_inputs(prog), ni, C.c_uint32, np.uint32).copy()
         self.output_signals = view(lib.c2a_program_outputs(prog), no, C.c_uint32, np.uint32).copy()
@@ -69,8 +72,10 @@ class DeviceCompiler:
     @property
     def events(self) -> np.ndarray:
         """the recorded add_signal / add_gate / add_connection calls as c2a_event rows (a private copy)"""
-        if self._events_copy is None:
-            self._events_copy = self._events_view.copy()
+        if self._events_copy is None:  # the walker records the packed form; the 16-byte records are written on this request
+            n = self._n_events
+            self._events_copy = (np.ctypeslib.as_array(C.cast(lib.c2a_program_events(self._prog), C.POINTER(C.c_uint32)), shape=(4 * n,)).reshape(n, 4).copy()
+                                 if n else np.zeros((0, 4), np.uint32))
         return self._events_copy
 
     def __del__(self):
@@ -108,9 +113,8 @@ class DeviceCompiler:
             if int(nd) in node_to_input:
                 raise CircuitError(Status.INCONSISTENCY, f"Node {int(nd)} used for both input {node_to_input[int(nd)]} and output {nm}")
         order, _wire, gates, wire_count = ctx.emitted_build_circuit(ins, outs, want_wires=False)
-        ev = self._events_view
-        consts = ev[(ev[:, 0] & 0xFF) == 1]
-        consts = consts[np.argsort(consts[:, 1], kind="stable")]
+        consts = np.zeros((self._const_signals.shape[0], 4), dtype=np.uint32)   # (kind, signal id, value, 0) rows, ascending ids
+        consts[:, 0], consts[:, 1], consts[:, 2] = 1, self._const_signals, self._const_values
         named = ctx.emitted_signal_wires(np.concatenate([ins, outs, consts[:, 1]]).astype(np.uint32))
         w_in, w_out, w_c = named[:len(ins)], named[len(ins):len(ins) + len(outs)], named[len(ins) + len(outs):]
         ci = CircuitInfo()

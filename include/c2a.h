@@ -323,8 +323,14 @@ uint32_t c2a_program_num_inputs(const c2a_program*);   /* signals tagged as circ
 uint32_t c2a_program_num_outputs(const c2a_program*);
 const uint32_t* c2a_program_inputs(const c2a_program*);
 const uint32_t* c2a_program_outputs(const c2a_program*);
-/* the recorded calls as a packed stream (arrays owned by the program object, valid until it is freed or recompiled) */
+/* the recorded calls as a packed stream (arrays owned by the program object, valid until it is freed or recompiled).  This IS
+ * the walker's recording - nothing is converted; c2a_program_events() writes the 16-byte records on first request. */
 int c2a_program_packed(c2a_program*, c2a_packed_events* out);
+/* the constant signals (add_signal with a value, src/process.rs:558-579) in declaration order, and their values: what the
+ * `constants` map of CircuitInfo is built from (src/compiler.rs:466-493) without reading the event records */
+uint64_t c2a_program_num_constants(const c2a_program*);
+const uint32_t* c2a_program_constant_signals(const c2a_program*);
+const uint32_t* c2a_program_constant_values(const c2a_program*);
 
 #ifdef __cplusplus
 }
