@@ -168,7 +168,7 @@ def main():
                     help="event stream format handed to the emitter: packed (kinds byte + payload words, c2a_emit_packed_*) or 16-byte c2a_event records")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-circuits-in-flight e2e leg")
     ap.add_argument("--no-from-source", action="store_true", help="skip the .circom-text-to-circuit leg")
-    ap.add_argument("--source-chains", type=int, default=1832, help="MiMC chains of the from_source leg (1832 = 1 M gates)")
+    ap.add_argument("--source-chains", type=int, default=0, help="MiMC chains of the from_source leg (default: --chains, the headline workload)")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
     args = ap.parse_args()
 
@@ -553,7 +553,7 @@ def main():
     #      What a user of compile() sees; the walk, not the device, sets this number.
     from_source = None
     if world == 1 and not args.no_from_source:
-        Ws = max(1, min(args.source_chains, args.chains))
+        Ws = max(1, min(args.source_chains or args.chains, args.chains))
         src_text = c2a.workloads.mimc_circom_source(Ws, args.rounds)
         t0 = time.perf_counter()
         dc = c2a.compile(None, source=src_text, emitter="device", context=ctx)
