@@ -50,7 +50,7 @@ for n in (2, 4, 8):
         m = L(P(f"r01_bench_{n}gpu.json"))
         multi.append(f"| N = {n} | value {m['value']/1e9:.2f} G gates/s ({m['ms_per_step']:.3f} ms/step), e2e {m['e2e']['value']/1e6:.0f} M gates/s ({m['e2e']['s_per_step']*1e3:.2f} ms/step) |")
 kern = "\n".join(f"| `{k}` | {v:.4f} | {r['per_kernel_gbs'].get(k, '')} |" for k, v in sorted(r["per_kernel_ms"].items(), key=lambda x: -x[1]))
-pipe, alla, cb = d.get("e2e_pipelined", {}), d.get("e2e_all_arrays", {}), d.get("cpu_baseline", {})
+pipe, alla, cb, fs = d.get("e2e_pipelined", {}), d.get("e2e_all_arrays", {}), d.get("cpu_baseline", {}), d.get("from_source", {})
 readme = f'''# profiles/ — measured evidence, one set per round
 
 All captures: B200 (sm_100a, 148 SMs, `clocks.max.sm` 1965 MHz), driver 580, CUDA 12.9, `--clock-control none`.
@@ -65,7 +65,7 @@ directory from one evidence set in `gpurun_out/`.
 |---|---|---|
 | `r01_bench_packed_10M.json` | the bench line (N = 1, packed event stream, default flags) | `python bench.py --steps 10 --warmup 3` |
 | `r01_bench_aos_stream_10M.json` | same workload handed over as 16-byte `c2a_event` records | `python bench.py --steps 10 --warmup 3 --stream aos --no-cpu-baseline --no-host-emit --no-pipelined` |
-| `r01_bench_2gpu.json`, `r01_bench_4gpu.json` | N = 2, 4 (one independent component subtree per rank, NCCL all-gather + device-side rebase) | `torchrun --nproc-per-node N bench.py --gpus N --steps 10 --warmup 3` under `gpurun --gpus N` |
+| `r01_bench_2gpu.json`, `r01_bench_4gpu.json`, `r01_bench_8gpu.json` | N = 2, 4, 8 (one independent component subtree per rank; numbering, NCCL all-gather of the counts, gate gather with the global offsets applied on the fly; N = 4 and 8 were measured one commit earlier, before the producer map moved into the emitter) | `torchrun --nproc-per-node N bench.py --gpus N --steps 10 --warmup 3` under `gpurun --gpus N` |
 | `r01_bench_reference_arm.json` | the reference's CPU path restated (oracle port, 1 thread) on the same box | `python bench.py --impl reference --steps 2 --warmup 1` |
 | `r01_launches_bench_packed_10M.csv` | every kernel launch of one `bench.py` run, `gpu__time_duration.sum` | `ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file … python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-host-emit --no-pipelined` |
 | `r01_ncu_full_summary.md` | `ncu --set full` of every kernel of the step and of the Kahn levels (DRAM bytes, throughput, occupancy, stall reading) | see the file |
@@ -75,7 +75,7 @@ Headline (10 018 305 gates, MiMC chains W = 18 315, `late` variant = non-identit
 
 | | value |
 |---|---|
-| `value` (stream resident in HBM, emit + build, results in HBM) | **{d['value']/1e9:.2f} G gates/s**, {d['ms_per_step']:.3f} ms/step, {r['whole_step_gbs']:.0f} GB/s algorithmic over the whole step (run-to-run: 1.47–1.53 ms) |
+| `value` (stream resident in HBM, emit + build, results in HBM) | **{d['value']/1e9:.2f} G gates/s**, {d['ms_per_step']:.3f} ms/step, {r['whole_step_gbs']:.0f} GB/s algorithmic over the whole step (run-to-run: 1.40–1.42 ms) |
 | `e2e` (packed stream in pinned host memory → renumbered gates + named wires in pinned host memory) | **{e['value']/1e6:.0f} M gates/s**, {e['s_per_step']*1e3:.2f} ms/step, {e['h2d_bytes_per_step']/1e6:.0f} MB H2D + {e['d2h_bytes_per_step']/1e6:.0f} MB D2H |
 | `e2e_all_arrays` (also `order` and the whole node→wire map) | {alla.get('value', 0)/1e6:.0f} M gates/s, {alla.get('s_per_step', 0)*1e3:.2f} ms/step, {alla.get('d2h_bytes_per_step', 0)/1e6:.0f} MB D2H |
 | `e2e_pipelined` (two handles / two circuits in flight) | {pipe.get('value', 0)/1e6:.0f} M gates/s, {pipe.get('s_per_step', 0)*1e3:.2f} ms/step |
@@ -83,6 +83,7 @@ Headline (10 018 305 gates, MiMC chains W = 18 315, `late` variant = non-identit
 {chr(10).join(multi)}
 | dominant kernel | `{r['kernel']}`: {r['kernel_ms']*1e3:.0f} µs live in the timed steps, {r['achieved']:.0f} GB/s algorithmic = **{r['frac']:.2f} of the measured {r['peak']:.0f} GB/s**; ncu DRAM traffic {r['traffic']/1e6:.0f} MB vs {r['alg_bytes_per_launch']/1e6:.0f} MB algorithmic |
 | reference arm (oracle port, 1 thread, {ref['config']['sample'].split(':')[0]}) | {ref['value']:.0f} gates/s; its back end alone on the full 10 M gates: {cb.get('backend_only_gates_per_s', 0)/1e6:.1f} M gates/s |
+| `from_source` (the same workload as .circom text → front end on one host core → packed stream → device emitter → build → gates + named wires on the host) | {fs.get('value', 0)/1e6:.1f} M gates/s: walk {fs.get('walk_s', 0)*1e3:.0f} ms + device {fs.get('device_s', 0)*1e3:.0f} ms (pageable buffers) |
 | host union-find emitter + `c2a_build_circuit` (same circuit, 1 step) | {d.get('e2e_host_emitter', {}).get('value', 0)/1e6:.1f} M gates/s |
 | clocks during the timed region | {d['clocks']} |
 
