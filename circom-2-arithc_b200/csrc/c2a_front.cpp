@@ -27,6 +27,7 @@
 #include <functional>
 #include <map>
 #include <new>
+#include <pthread.h>
 #include <memory>
 #include <optional>
 #include <set>
@@ -1295,7 +1296,7 @@ struct c2a_program {
   std::unordered_map<uint32_t, std::string> spelled;   // names handed out by c2a_program_signal_name (pointers stay valid)
 };
 
-static int compile_impl(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
+static int compile_body(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
   using namespace front;
   p->sink = Sink();
   p->sink.into = into;
@@ -1346,6 +1347,34 @@ static int compile_impl(c2a_program* p, const std::string& src, const std::strin
     return C2A_ERR_NO_MEMORY;
   }
   return C2A_OK;
+}
+
+// The walk recurses once per nested call / statement / expression level; the call-depth guard (10 000 nested calls, "Call error")
+// must be reached before the native stack ends, so the walk runs on a thread of its own with a 512 MB stack (address space only:
+// pages are touched as the recursion deepens).  The reference has no guard at all (a runaway recursion aborts the process).
+struct CompileJob {
+  c2a_program* p;
+  const std::string *src, *file, *dir;
+  c2a_compiler* into;
+  int status;
+};
+static void* compile_thread(void* arg) {
+  CompileJob* j = (CompileJob*)arg;
+  j->status = compile_body(j->p, *j->src, *j->file, *j->dir, j->into);
+  return nullptr;
+}
+static int compile_impl(c2a_program* p, const std::string& src, const std::string& file, const std::string& dir, c2a_compiler* into) {
+  CompileJob job{p, &src, &file, &dir, into, C2A_OK};
+  pthread_attr_t attr;
+  pthread_t th;
+  bool threaded = false;
+  if (pthread_attr_init(&attr) == 0) {
+    if (pthread_attr_setstacksize(&attr, (size_t)512 << 20) == 0 && pthread_create(&th, &attr, compile_thread, &job) == 0) threaded = true;
+    pthread_attr_destroy(&attr);
+  }
+  if (!threaded) return compile_body(p, src, file, dir, into);  // (no address space for the big stack: the caller's stack has to do)
+  pthread_join(th, nullptr);
+  return job.status;
 }
 
 extern "C" {

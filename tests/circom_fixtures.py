@@ -181,4 +181,6 @@ WALKER_STRESS = [
      0, '', 427, 241, '81a40adf9ad060f6'),
     ('pragma circom 2.0.0;\ntemplate Z() { signal output o; o <== 5 + 0; }\ntemplate Y() { signal input i; signal output o; component z1 = Z(); component z2 = Z(); component z3 = Z(); o <== i + z1.o + z2.o + z3.o; }\ntemplate X() { signal input i; signal output o; component y[5]; for (var k = 0; k < 5; k++) { y[k] = Y(); if (k == 0) { y[k].i <== i; } else { y[k].i <== y[k-1].o; } } o <== y[4].o; }\ncomponent main = X();',
      0, '', 98, 57, '20061b8c61578208'),
+    ('pragma circom 2.0.0;\nfunction f(n) { var r = 0; if (n > 0) { r = f(n - 1); } return r + 1; }\ntemplate A(k) { signal input a; signal output b; var q = f(40) + f(40) + f(k); b <== a * q; }\ntemplate B() { signal input a; signal output b; component x = A(7); component y = A(7); component z = A(41); x.a <== a; y.a <== x.b; z.a <== y.b; b <== z.b; }\ncomponent main = B();',
+     0, '', 24, 14, '42e3ac3aa92ca296'),
 ]

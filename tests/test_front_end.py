@@ -280,3 +280,17 @@ def test_instance_memo_replays_exactly(c2a, monkeypatch):
         fast = _walk(c2a, src)
         monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
         assert _walk(c2a, src) == fast
+
+
+def test_runaway_recursion_is_a_call_error_not_a_crash(c2a):
+    """10 000 nested calls end in ProgramError::CallError (src/program.rs:81-82); the walk runs on its own large stack so that the
+    guard is reached before the native stack ends (the reference has no guard: its process aborts)"""
+    src = """pragma circom 2.0.0;
+function f(n) { var r = 0; if (n > 0) { r = f(n - 1); } return r + 1; }
+template A() { signal input a; signal output b; var q = f(300) + f(300) + f(12000); b <== a + q; }
+component main = A();
+"""
+    st, err, _ev, _names = _walk(c2a, src)
+    assert st == 113 and err == b"Call error"
+    ok = _walk(c2a, src.replace("f(12000)", "f(9000)"))
+    assert ok[0] == 0 and len(ok[3]) == 4
