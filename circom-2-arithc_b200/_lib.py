@@ -153,6 +153,8 @@ _SIGS = {
     "c2a_circuit_order": (vp, [vp]),
     "c2a_circuit_gates": (vp, [vp]),
     "c2a_circuit_info_json": (cp, [vp]),
+    "c2a_circuit_report_json": (cp, [vp, cp]),
+    "c2a_bristol_gate_lines": (u64, [vp, u64, vp, u64]),
 }
 for _name, (_res, _args) in _SIGS.items():
     _f = getattr(lib, _name)  # AttributeError here = the .so does not export what include/c2a.h declares

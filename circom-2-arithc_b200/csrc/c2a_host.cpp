@@ -74,6 +74,7 @@ struct c2a_compiler {
   std::vector<c2a_gate> new_gates;
   uint64_t wire_count = 0;
   std::string info_json;
+  std::string report_json;
 
   uint32_t new_elem(uint32_t sid) {
     uint32_t e = (uint32_t)el.size();
@@ -395,6 +396,82 @@ static std::string jesc(const std::string& s) {
   std::string o;
   for (char ch : s) { if (ch == '"' || ch == '\\') o += '\\'; o += ch; }
   return o;
+}
+
+// Compiler::generate_circuit_report, src/compiler.rs:287-319 + get_node_report :503-531.  inputs = nodes no gate writes,
+// outputs = written nodes no gate reads, both ascending by node id; per node: the names of its signals in merge order without
+// the temporaries ("random_"), and the value of its last constant signal.  One pass over the gates and one over the nodes.
+const char* c2a_circuit_report_json(c2a_compiler* c, const char* value_type) {
+  if (!c) return nullptr;
+  std::vector<std::pair<uint32_t, uint32_t>> v;
+  live_roots(c, &v);
+  std::vector<uint8_t> consumed((size_t)c->node_count + 1, 0);
+  for (const ElemGate& g : c->gates) {
+    consumed[c->el[c->find(g.l)].node_id] = 1;
+    consumed[c->el[c->find(g.r)].node_id] = 1;
+  }
+  std::string& o = c->report_json;
+  o.clear();
+  auto node = [&](uint32_t id, uint32_t r, bool first) {
+    if (!first) o += ",";
+    o += "{\"id\":" + std::to_string(id) + ",\"names\":[";
+    bool first_name = true, has = false;
+    uint32_t value = 0;
+    for (uint32_t e = c->el[r].head; e != kNoElem; e = c->el[e].next) {
+      if (c->el[e].name_off != kNameNone) {
+        std::string nm = c->name_of(e);
+        if (nm.find("random_") == std::string::npos) {
+          if (!first_name) o += ",";
+          o += "\"" + jesc(nm) + "\"";
+          first_name = false;
+        }
+      }
+      if (c->el[e].has_value) { has = true; value = c->el[e].value; }
+    }
+    o += "],\"value\":" + (has ? std::to_string(value) : std::string("null")) + "}";
+  };
+  o += "{\"inputs\":[";
+  bool first = true;
+  for (auto& kv : v)
+    if (!(c->el[kv.second].flags & kOut)) { node(kv.first, kv.second, first); first = false; }
+  o += "],\"outputs\":[";
+  first = true;
+  for (auto& kv : v)
+    if ((c->el[kv.second].flags & kOut) && !consumed[kv.first]) { node(kv.first, kv.second, first); first = false; }
+  o += "],\"value_type\":\"" + jesc(value_type ? value_type : "sint") + "\"}";
+  return o.c_str();
+}
+
+// The gate lines of bristol-circuit's write_bristol ("2 1 <in0> <in1> <out> <Op>\n" per gate; crate un-vendored, layout PARITY
+// UNPINNED - see include/c2a.h).  Returns the number of bytes the lines take; writes them when out != NULL and cap suffices.
+uint64_t c2a_bristol_gate_lines(const c2a_gate* gates, uint64_t G, char* out, uint64_t cap) {
+  auto put_u32 = [](char* p, uint32_t v) -> char* {
+    char tmp[10];
+    int n = 0;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+  };
+  auto digits = [](uint32_t v) -> uint64_t { uint64_t d = 1; while (v >= 10) { v /= 10; ++d; } return d; };
+  size_t name_len[C2A_GATE_TYPE_COUNT];
+  for (int i = 0; i < C2A_GATE_TYPE_COUNT; ++i) name_len[i] = strlen(kGateNames[i]);
+  uint64_t need = 0;
+  for (uint64_t i = 0; i < G; ++i) {
+    if (gates[i].op >= C2A_GATE_TYPE_COUNT) return 0;
+    need += 4 + digits(gates[i].lh) + 1 + digits(gates[i].rh) + 1 + digits(gates[i].out) + 1 + name_len[gates[i].op] + 1;
+  }
+  if (!out || cap < need) return need;
+  char* p = out;
+  for (uint64_t i = 0; i < G; ++i) {
+    const c2a_gate& g = gates[i];
+    memcpy(p, "2 1 ", 4); p += 4;
+    p = put_u32(p, g.lh); *p++ = ' ';
+    p = put_u32(p, g.rh); *p++ = ' ';
+    p = put_u32(p, g.out); *p++ = ' ';
+    memcpy(p, kGateNames[g.op], name_len[g.op]); p += name_len[g.op];
+    *p++ = '\n';
+  }
+  return need;
 }
 
 // Compiler::build_circuit, src/compiler.rs:321-494

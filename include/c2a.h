@@ -294,6 +294,13 @@ const c2a_gate* c2a_circuit_gates(const c2a_compiler*);       /* num_gates, wire
 /* circuit.info as JSON: {"input_name_to_wire_index":{},"constants":{name:{"value":"..","wire_index":n}},
  * "output_name_to_wire_index":{}} with keys sorted */
 const char* c2a_circuit_info_json(const c2a_compiler*);
+/* Compiler::generate_circuit_report (src/compiler.rs:287-319, 503-531) as compact JSON: {"inputs":[{"id","names","value"}..],
+ * "outputs":[..],"value_type":..}; inputs = nodes no gate writes, outputs = written nodes no gate reads, ascending node id.
+ * The string is owned by the compiler object (valid until the next call / free). */
+const char* c2a_circuit_report_json(c2a_compiler*, const char* value_type);
+/* circuit.txt body (src/main.rs:34-36 calls bristol-circuit's write_bristol; crate un-vendored, text layout PARITY UNPINNED): one
+ * line "2 1 <in0> <in1> <out> <Op>\n" per gate, Op = the AGateType Display token.  Returns the byte count; writes when it fits. */
+uint64_t c2a_bristol_gate_lines(const c2a_gate* gates, uint64_t G, char* out, uint64_t cap);
 
 int c2a_signal_value(c2a_compiler*, uint32_t signal_id, int* has_value, uint32_t* value); /* Signal.value (src/compiler.rs:17-27) */
 

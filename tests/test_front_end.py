@@ -221,6 +221,12 @@ def test_report_matches_oracle(c2a, orc):  # compiler.rs:287-319, 503-531
         assert comp.generate_circuit_report() == to_oracle(orc, comp).report()
     rep = c2a.compile(None, source=fx.ADD_ZERO).generate_circuit_report()
     assert rep["outputs"] == [{"id": 5, "names": ["0.out"], "value": None}] and rep["value_type"] == "sint"
+    # the native report (c2a_circuit_report_json) against the one assembled from nodes() / gate_array() in Python
+    from circom_2_arithc_b200.program import _generate_circuit_report_py
+    for src in [fx.INFIX_OPS, fx.PREFIX_OPS, c2a.workloads.mimc_circom_source(5, 7)] + [c[0] for c in fx.WALKER_STRESS if c[1] == 0]:
+        comp = c2a.compile(None, source=src)
+        comp.update_type("sfloat")
+        assert comp.generate_circuit_report() == _generate_circuit_report_py(comp)
 
 
 def test_large_loop_is_linear(c2a):

@@ -83,3 +83,25 @@ def test_get_signals_prefix_match(c2a):  # compiler.rs:676-690
     c.add_signal(1, "signal1", None)
     c.add_signal(2, "filter_signal", None)
     assert c.get_signals("filter") == {2: "filter_signal"}
+
+
+def test_bristol_gate_lines_are_formatted_natively(c2a):
+    """circuit.txt body (src/main.rs:34-36 -> bristol-circuit write_bristol; layout parity unpinned): the native formatter against
+    the obvious Python formatting, including 1- and 10-digit wire ids and every op token"""
+    import numpy as np
+    from circom_2_arithc_b200 import program as P
+    from circom_2_arithc_b200.compiler import BristolCircuit, CircuitInfo
+    rng = np.random.RandomState(3)
+    G = 5000
+    g = np.zeros((G, 4), dtype=np.uint32)
+    g[:, 0] = np.arange(G) % 20
+    g[:, 1:] = rng.randint(0, 2 ** 32, size=(G, 3), dtype=np.int64).astype(np.uint32)
+    g[:4, 1:] = [[0, 1, 9], [10, 99, 100], [4294967295, 0, 7], [1000000000, 999999999, 123456789]]
+    ci = CircuitInfo()
+    ci.input_name_to_wire_index = {"0.a": 0, "0.b": 1}
+    ci.output_name_to_wire_index = {"0.c": 2}
+    names = [t.name for t in c2a.AGateType]
+    want = "\n".join([f"{G} 77", "2 1 1", "1 1", ""] + [f"2 1 {a} {b} {o} {names[op]}" for op, a, b, o in g.tolist()]) + "\n"
+    assert P.bristol_text(BristolCircuit(wire_count=77, info=ci, gate_array=g, order=np.arange(G, dtype=np.uint32))) == want
+    empty = BristolCircuit(wire_count=0, info=CircuitInfo(), gate_array=np.zeros((0, 4), np.uint32), order=np.zeros(0, np.uint32))
+    assert P.bristol_text(empty) == "0 0\n0\n0\n\n"
