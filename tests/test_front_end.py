@@ -300,3 +300,42 @@ component main = A();
     assert st == 113 and err == b"Call error"
     ok = _walk(c2a, src.replace("f(12000)", "f(9000)"))
     assert ok[0] == 0 and len(ok[3]) == 4
+
+
+def test_instance_memo_at_a_million_gates(c2a, monkeypatch):
+    """BASELINE config 5 at the 1 M-gate point as .circom text: the replayed recording (packed stream, constants, names, I/O tags)
+    equals the one obtained by interpreting all 1832 x 91 instances, and it is what c2a_pack_events makes of the 16-byte records"""
+    import ctypes as C
+    from circom_2_arithc_b200._lib import PackedEvents
+    lib = c2a.lib
+    src = c2a.workloads.mimc_circom_source(1832, 91).encode()
+
+    def walk():
+        p = lib.c2a_program_new()
+        assert lib.c2a_program_compile_source(p, src, None, None) == 0
+        pk = PackedEvents()
+        lib.c2a_program_packed(p, C.byref(pk))
+        n, nw, nc, ns = int(pk.n_events), int(pk.n_words), int(lib.c2a_program_num_constants(p)), int(lib.c2a_program_num_signals(p))
+        arr = lambda ptr, k, ct: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(k,)).copy()
+        out = dict(kinds=arr(pk.kinds, n, C.c_uint8), words=arr(pk.words, nw, C.c_uint32), flags=int(pk.flags),
+                   const_ids=arr(lib.c2a_program_constant_signals(p), nc, C.c_uint32), const_vals=arr(lib.c2a_program_constant_values(p), nc, C.c_uint32),
+                   ins=arr(lib.c2a_program_inputs(p), lib.c2a_program_num_inputs(p), C.c_uint32),
+                   outs=arr(lib.c2a_program_outputs(p), lib.c2a_program_num_outputs(p), C.c_uint32),
+                   names=[lib.c2a_program_signal_name(p, i) for i in list(range(0, ns, 9973)) + [ns - 1]],
+                   events=arr(lib.c2a_program_events(p), 4 * n, C.c_uint32).reshape(n, 4))
+        lib.c2a_program_free(p)
+        return out
+
+    monkeypatch.delenv("C2A_FRONT_NO_MEMO", raising=False)
+    fast = walk()
+    monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
+    slow = walk()
+    assert fast["flags"] == slow["flags"] == 1 and fast["names"] == slow["names"]
+    for k in ("kinds", "words", "const_ids", "const_vals", "ins", "outs", "events"):
+        assert np.array_equal(fast[k], slow[k]), k
+    ev = fast["events"]
+    assert int((ev[:, 0] & 0xFF == 2).sum()) == 1832 * 547 and len(fast["ins"]) == 1833 and len(fast["outs"]) == 1832
+    kinds_b, words, flags = c2a.pack_events(ev)
+    assert flags == 1 and np.array_equal(kinds_b, fast["kinds"]) and np.array_equal(words, fast["words"])
+    consts = ev[(ev[:, 0] & 0xFF) == 1]
+    assert np.array_equal(consts[:, 1], fast["const_ids"]) and np.array_equal(consts[:, 2], fast["const_vals"])
