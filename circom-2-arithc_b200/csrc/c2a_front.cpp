@@ -14,7 +14,7 @@
 // Temporaries (`random_<u32>` items, :229) are values, not entries; temporary SIGNALS still consume signal ids and are
 // named "<ctx>.random_<id>" (the reference's suffix is a thread_rng draw, i.e. unspecified).
 // The walk never touches a string: identifiers are interned after parsing (Symbols), `const_signal_<v>` items are keyed
-// by their value, and signal names are kept as 16-byte records that are spelled out only when somebody asks for one
+// by their value, and signal names are kept as 16-byte records (one span record for a whole replayed instance) that are spelled out only when somebody asks for one
 // (c2a_program_signal_name, the input / output prefix match, a host Compiler that wants the names).
 // u32 arithmetic on variables follows a release build: + * ** wrap, shifts use the low 5 bits, - / \ % error as in
 // src/process.rs:649-750.
@@ -717,7 +717,9 @@ struct Sink {
   PodVec<uint32_t> words;        // gate: lhs, rhs, out; connection: a, b (signal ids)
   PodVec<uint32_t> const_ids;    // the constant signals in declaration order ...
   PodVec<uint32_t> const_vals;   // ... and their values
-  PodVec<SigName> names;         // by signal id
+  PodVec<SigName> names;         // by signal id; the records of a REPLAYED id range are never written (nor their pages touched):
+  struct Span { uint32_t dst, len, src; };  // ... ids [dst, dst + len) are named like [src, src + len), src < dst
+  std::vector<Span> spans;       // ascending dst, disjoint
   PodVec<uint32_t> idx;          // array indices of the declared names
   PodVec<c2a_event> aos;         // the same calls as c2a_event records, written when somebody asks (c2a_program_events)
   bool aos_valid = false;
@@ -730,8 +732,19 @@ struct Sink {
     std::string why = st == C2A_ERR_INVALID_ARGUMENT || st == C2A_ERR_REFERENCE_PANIC ? c2a_compiler_last_error(into) : c2a_status_string(st);
     fail(C2A_PROG_CIRCUIT_ERROR, "Circuit error: " + why);
   }
+  uint32_t name_source(uint32_t id) const {  // the id whose record names this one (itself unless it lies in replayed ranges)
+    while (!spans.empty()) {
+      size_t lo = 0, hi = spans.size();  // last span with dst <= id
+      while (lo < hi) { size_t mid = (lo + hi) / 2; if (spans[mid].dst <= id) lo = mid + 1; else hi = mid; }
+      if (lo == 0) break;
+      const Span& sp = spans[lo - 1];
+      if (id - sp.dst >= sp.len) break;
+      id = sp.src + (id - sp.dst);
+    }
+    return id;
+  }
   std::string name_of(uint32_t id) const {
-    const SigName& n = names[id];
+    const SigName& n = names[name_source(id)];
     std::string s = sym.strs[n.ctx];
     s += '.';
     switch (n.kind_n & 3u) {
@@ -774,7 +787,10 @@ struct Sink {
   void replay(const Mark& b, const Mark& e, uint32_t delta) {
     const Mark at = mark();
     kinds.append_self(b.k, e.k);
-    names.append_self(b.id, e.id);  // (declared names share their index list)
+    if (e.id > b.id) {               // the names: one span record instead of 16 bytes per signal
+      names.resize_uninit(names.size() + (e.id - b.id));
+      spans.push_back(Span{at.id, e.id - b.id, b.id});
+    }
     const_vals.append_self(b.c, e.c);
     const_ids.reserve(const_ids.size() + (e.c - b.c));
     for (uint64_t i = b.c; i < e.c; ++i) const_ids.push_back(const_ids[i] + delta);
@@ -1326,7 +1342,10 @@ static int compile_body(c2a_program* p, const std::string& src, const std::strin
     const uint32_t root = p->sink.sym.intern("0");
     auto tag = [&](const std::vector<std::string>& keys, std::vector<uint32_t>& ids, bool input) {
       std::map<uint32_t, std::string> m;
+      size_t sp = 0;  // replayed id ranges belong to callee contexts (and their name records are not materialised): skip them
       for (uint32_t id = 0; id < p->sink.names.size(); ++id) {
+        while (sp < p->sink.spans.size() && p->sink.spans[sp].dst + p->sink.spans[sp].len <= id) ++sp;
+        if (sp < p->sink.spans.size() && p->sink.spans[sp].dst <= id) { id = p->sink.spans[sp].dst + p->sink.spans[sp].len - 1; continue; }
         if (p->sink.names[id].ctx != root) continue;
         std::string name = p->sink.name_of(id);
         for (auto& k : keys)
