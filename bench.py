@@ -558,7 +558,7 @@ def main():
         t0 = time.perf_counter()
         dc = c2a.compile(None, source=src_text, emitter="device", context=ctx)
         t1 = time.perf_counter()
-        info_s = ctx.emit_packed(dc._kinds, dc._words, dc._flags)
+        info_s = ctx.emit_compressed(dc.compressed())   # literal ranges + replay records cross PCIe; the instances are expanded in HBM
         _o, _w, g_s, wc_s = ctx.emitted_build_circuit(dc.input_signals, dc.output_signals, want_order=False, want_wires=False)
         named_s = np.concatenate([dc.input_signals, dc.output_signals, dc._const_signals]).astype(np.uint32)
         w_s = ctx.emitted_signal_wires(named_s)
@@ -566,8 +566,9 @@ def main():
         assert info_s["path"] == 1 and g_s.shape[0] == info_s["n_gates"] and w_s.shape[0] == named_s.shape[0] and wc_s > 0
         from_source = {"value": info_s["n_gates"] / (t2 - t0), "unit": "gates/s", "gates": int(info_s["n_gates"]), "events": int(dc._n_events),
                        "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": t2 - t1, "host_threads": 1,
-                       "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core) + packing = walk_s; emit + build + named-wire lookup through "
-                               "pageable buffers = device_s" % Ws}
+                       "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core; a (template, arguments) pair is interpreted twice at most, later "
+                               "instances are replay records) = walk_s; c2a_emit_compressed_device (records expanded on the GPU) + build + named-wire "
+                               "lookup, results into pageable buffers = device_s" % Ws}
         del dc
 
     if rank != 0:

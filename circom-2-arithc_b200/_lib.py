@@ -60,6 +60,14 @@ class PackedEvents(C.Structure):  # c2a_packed_events
     _fields_ = [("kinds", vp), ("words", vp), ("n_events", u64), ("n_words", u64), ("flags", u32), ("reserved", u32)]
 
 
+class Replay(C.Structure):  # c2a_replay
+    _fields_ = [("k_dst", u64), ("k_src", u64), ("k_len", u64), ("w_dst", u64), ("w_src", u64), ("w_len", u64), ("delta", u32), ("gen", u32)]
+
+
+class CompressedEvents(C.Structure):  # c2a_compressed_events
+    _fields_ = [("kinds", vp), ("words", vp), ("n_events", u64), ("n_words", u64), ("replays", vp), ("n_replays", u64), ("max_gen", u32), ("flags", u32)]
+
+
 load_error = None
 try:
     lib = C.CDLL(LIB_PATH)
@@ -106,6 +114,8 @@ _SIGS = {
     "c2a_emit_packed_device": (i32, [vp, vp, vp, u64p]),
     "c2a_emit_packed_resident": (i32, [vp, vp, vp, u64p]),
     "c2a_program_packed": (i32, [vp, vp]),
+    "c2a_program_compressed": (i32, [vp, vp]),
+    "c2a_emit_compressed_device": (i32, [vp, vp, vp, u64p]),
     "c2a_emitted_fetch": (i32, [vp, vp, vp]),
     "c2a_emitted_build_circuit_device": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_emitted_build_circuit": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),

@@ -247,6 +247,23 @@ class DeviceContext:
         self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
         return dict(self._emit_info)
 
+    def emit_compressed(self, cx) -> dict:
+        """c2a_emit_compressed_device: a walker recording whose replayed instances are expanded on the GPU (cx: CompressedEvents
+        from c2a_program_compressed; the program object must stay alive during the call)."""
+        info = EmitInfo()
+        bad = C.c_uint64(0)
+        st = lib.c2a_emit_compressed_device(self._h, C.byref(cx), C.byref(info), C.byref(bad))
+        if st != 0:
+            e = None
+            try:
+                _raise(st, f"event {bad.value}: {self.last_error()}")
+            except (CircuitError, C2AError) as ex:
+                ex.err_event = bad.value
+                e = ex
+            raise e
+        self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
+        return dict(self._emit_info)
+
     def emit_packed(self, kinds: np.ndarray, words: np.ndarray, flags: int) -> dict:
         """c2a_emit_packed_device: the same replay from a packed stream (pack_events() / Program.packed())."""
         kinds = np.ascontiguousarray(kinds, dtype=np.uint8)

@@ -1186,6 +1186,8 @@ void c2a_destroy(c2a_handle* h) {
   for (auto e : h->ev_pool) cudaEventDestroy(e);
   if (h->slab) cudaFree(h->slab);
   if (h->ev_buf) cudaFree(h->ev_buf);
+  if (h->cx_buf) cudaFree(h->cx_buf);
+  if (h->cx_pinned) cudaFreeHost(h->cx_pinned);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   cudaStreamSynchronize(h->stream2);

@@ -753,6 +753,36 @@ static int emit_host_path(c2a_handle* h, const c2a_event* ev, uint64_t n, uint32
   return C2A_OK;
 }
 
+// ---- compressed streams (include/c2a.h: c2a_compressed_events) ---------------------------------------------------------------
+// The host splits literal ranges and replay records into chunks of at most kCxChunk elements; one CTA per chunk copies it
+// (payload words: + delta).  Chunks of one generation are independent; generations run as consecutive launches.
+constexpr uint32_t kCxChunk = 16384;
+struct CxChunk {
+  unsigned long long dst, src;  // element offsets (bytes for the kind array, words for the payload)
+  uint32_t len, delta;
+};
+__global__ void __launch_bounds__(kBlock) k_cx_copy_u8(const CxChunk* __restrict__ chunks, uint32_t n_chunks, const uint8_t* src_base, uint8_t* dst_base) {
+  for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const CxChunk ch = chunks[c];
+    const uint8_t* s = src_base + ch.src;
+    uint8_t* d = dst_base + ch.dst;
+    if (((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 3) == 0) {  // word-wise body, byte tail
+      const uint32_t nw = ch.len >> 2;
+      for (uint32_t i = threadIdx.x; i < nw; i += kBlock) reinterpret_cast<uint32_t*>(d)[i] = reinterpret_cast<const uint32_t*>(s)[i];
+      for (uint32_t i = (nw << 2) + threadIdx.x; i < ch.len; i += kBlock) d[i] = s[i];
+    } else
+      for (uint32_t i = threadIdx.x; i < ch.len; i += kBlock) d[i] = s[i];
+  }
+}
+__global__ void __launch_bounds__(kBlock) k_cx_copy_u32(const CxChunk* __restrict__ chunks, uint32_t n_chunks, const uint32_t* src_base, uint32_t* dst_base) {
+  for (uint32_t c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const CxChunk ch = chunks[c];
+    const uint32_t* s = src_base + ch.src;
+    uint32_t* d = dst_base + ch.dst;
+    for (uint32_t i = threadIdx.x; i < ch.len; i += kBlock) d[i] = s[i] + ch.delta;
+  }
+}
+
 }  // namespace c2a
 
 extern "C" {
@@ -1098,6 +1128,102 @@ int c2a_emit_packed_resident(c2a_handle* h, const c2a_packed_events* d_pk, c2a_e
   src.pk = d_pk;
   src.pk_on_device = true;
   return emit_events_impl(h, src, d_pk->n_events, info, err_event);
+}
+
+// Compressed stream: only the literal ranges and the replay records cross PCIe; the replayed instances are expanded in HBM,
+// generation by generation, and the expanded stream goes through the resident packed path.
+int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c2a_emit_info* info, uint64_t* err_event) {
+  if (!h || !cx) return C2A_ERR_INVALID_ARGUMENT;
+  const uint64_t n = cx->n_events, nw = cx->n_words, nr = cx->n_replays;
+  int st = check_sizes(h, n, 1);
+  if (st) return st;
+  if ((n && !cx->kinds) || (nw && !cx->words) || (nr && !cx->replays)) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null compressed arrays");
+  if (nw > 3 * n) return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words does not match the kinds");
+  // ---- records: ascending, disjoint, inside the arrays, sources before destinations, generations consistent with the order
+  uint64_t k_at = 0, w_at = 0, lit_k = 0, lit_w = 0;
+  uint32_t max_gen = 0;
+  for (uint64_t i = 0; i < nr; ++i) {
+    const c2a_replay& r = cx->replays[i];
+    if (r.k_dst < k_at || r.w_dst < w_at || r.k_len > n - r.k_dst || r.w_len > nw - r.w_dst || r.k_src + r.k_len > r.k_dst ||
+        r.w_src + r.w_len > r.w_dst || r.gen == 0 || r.gen > 1u << 20)
+      return fail(h, C2A_ERR_INVALID_ARGUMENT, "replay record %llu is inconsistent", (unsigned long long)i);
+    lit_k += r.k_dst - k_at;
+    lit_w += r.w_dst - w_at;
+    k_at = r.k_dst + r.k_len;
+    w_at = r.w_dst + r.w_len;
+    max_gen = std::max(max_gen, r.gen);
+  }
+  lit_k += n - k_at;
+  lit_w += nw - w_at;
+  cudaStream_t s = h->stream;
+  // ---- chunk tables: generation 0 = the literal ranges (source: the packed literal staging), generation g = records of gen g
+  auto n_chunks_of = [](uint64_t len) { return (len + kCxChunk - 1) / kCxChunk; };
+  std::vector<std::vector<CxChunk>> kch(max_gen + 1), wch(max_gen + 1);
+  auto add_chunks = [&](std::vector<CxChunk>& v, uint64_t dst, uint64_t src, uint64_t len, uint32_t delta) {
+    for (uint64_t o = 0; o < len; o += kCxChunk) v.push_back(CxChunk{dst + o, src + o, (uint32_t)std::min<uint64_t>(kCxChunk, len - o), delta});
+  };
+  const size_t lit_k_bytes = align256(lit_k + 16), lit_w_bytes = align256(4 * lit_w + 16);
+  size_t table_entries = n_chunks_of(lit_k) + n_chunks_of(lit_w) + 2 * (nr + 2);
+  for (uint64_t i = 0; i < nr; ++i) table_entries += n_chunks_of(cx->replays[i].k_len) + n_chunks_of(cx->replays[i].w_len);
+  const size_t stage_need = lit_k_bytes + lit_w_bytes + align256(sizeof(CxChunk) * table_entries);
+  if (stage_need > h->cx_pinned_bytes) {
+    if (h->cx_pinned) { cudaStreamSynchronize(s); cudaFreeHost(h->cx_pinned); h->cx_pinned = nullptr; h->cx_pinned_bytes = 0; }
+    if (!cuda_ok(h, cudaHostAlloc((void**)&h->cx_pinned, stage_need + stage_need / 8, cudaHostAllocDefault), "cudaHostAlloc(compressed staging)")) return C2A_ERR_NO_MEMORY;
+    h->cx_pinned_bytes = stage_need + stage_need / 8;
+  } else cudaStreamSynchronize(s);  // the staging may still be the source of the previous call's copy
+  uint8_t* st_k = (uint8_t*)h->cx_pinned;
+  uint32_t* st_w = (uint32_t*)(h->cx_pinned + lit_k_bytes);
+  CxChunk* st_t = (CxChunk*)(h->cx_pinned + lit_k_bytes + lit_w_bytes);
+  {  // pack the literal ranges, build the tables
+    uint64_t pk = 0, pw = 0;
+    k_at = w_at = 0;
+    auto literal = [&](uint64_t k_end, uint64_t w_end) {
+      if (k_end > k_at) { memcpy(st_k + pk, cx->kinds + k_at, k_end - k_at); add_chunks(kch[0], k_at, pk, k_end - k_at, 0); pk += k_end - k_at; }
+      if (w_end > w_at) { memcpy(st_w + pw, cx->words + w_at, 4 * (w_end - w_at)); add_chunks(wch[0], w_at, pw, w_end - w_at, 0); pw += w_end - w_at; }
+    };
+    for (uint64_t i = 0; i < nr; ++i) {
+      const c2a_replay& r = cx->replays[i];
+      literal(r.k_dst, r.w_dst);
+      add_chunks(kch[r.gen], r.k_dst, r.k_src, r.k_len, 0);
+      add_chunks(wch[r.gen], r.w_dst, r.w_src, r.w_len, r.delta);
+      k_at = r.k_dst + r.k_len;
+      w_at = r.w_dst + r.w_len;
+    }
+    literal(n, nw);
+  }
+  size_t t_at = 0;
+  std::vector<size_t> k_off(max_gen + 2), w_off(max_gen + 2);
+  for (uint32_t g = 0; g <= max_gen; ++g) {
+    k_off[g] = t_at; if (!kch[g].empty()) memcpy(st_t + t_at, kch[g].data(), sizeof(CxChunk) * kch[g].size()); t_at += kch[g].size();
+    w_off[g] = t_at; if (!wch[g].empty()) memcpy(st_t + t_at, wch[g].data(), sizeof(CxChunk) * wch[g].size()); t_at += wch[g].size();
+  }
+  // ---- device: [kinds | words | literal kinds | literal words | tables]
+  const size_t d_k_bytes = align256(n + 16), d_w_bytes = align256(4 * nw + 16), d_t_bytes = align256(sizeof(CxChunk) * (t_at + 1));
+  const size_t dev_need = d_k_bytes + d_w_bytes + lit_k_bytes + lit_w_bytes + d_t_bytes;
+  if (dev_need > h->cx_bytes) {
+    if (h->cx_buf) { cudaStreamSynchronize(s); cudaFree(h->cx_buf); h->cx_buf = nullptr; h->cx_bytes = 0; }
+    if (!cuda_ok(h, cudaMalloc(&h->cx_buf, dev_need + dev_need / 16), "cudaMalloc(compressed stream)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+    h->cx_bytes = dev_need + dev_need / 16;
+  }
+  uint8_t* d_kinds = (uint8_t*)h->cx_buf;
+  uint32_t* d_words = (uint32_t*)(h->cx_buf + d_k_bytes);
+  uint8_t* d_lit_k = (uint8_t*)(h->cx_buf + d_k_bytes + d_w_bytes);
+  uint32_t* d_lit_w = (uint32_t*)(h->cx_buf + d_k_bytes + d_w_bytes + lit_k_bytes);
+  CxChunk* d_t = (CxChunk*)(h->cx_buf + d_k_bytes + d_w_bytes + lit_k_bytes + lit_w_bytes);
+  phases_clear(h);
+  if (!cuda_ok(h, cudaMemcpyAsync(d_lit_k, h->cx_pinned, lit_k_bytes + lit_w_bytes + sizeof(CxChunk) * t_at, cudaMemcpyHostToDevice, s), "compressed H2D")) return C2A_ERR_CUDA;
+  const int wide = h->num_sms * 8;
+  for (uint32_t g = 0; g <= max_gen; ++g) {
+    const uint32_t nk = (uint32_t)kch[g].size(), nwc = (uint32_t)wch[g].size();
+    if (nk) LAUNCH(h, k_cx_copy_u8, std::min<uint32_t>(nk, (uint32_t)wide), kBlock, d_t + k_off[g], nk, g ? (const uint8_t*)d_kinds : (const uint8_t*)d_lit_k, d_kinds);
+    if (nwc) LAUNCH(h, k_cx_copy_u32, std::min<uint32_t>(nwc, (uint32_t)wide), kBlock, d_t + w_off[g], nwc, g ? (const uint32_t*)d_words : (const uint32_t*)d_lit_w, d_words);
+  }
+  if (!cuda_ok(h, cudaGetLastError(), "expand kernels")) return C2A_ERR_CUDA;
+  c2a_packed_events pk{d_kinds, d_words, n, nw, cx->flags, 0};
+  EmitSrc src;
+  src.pk = &pk;
+  src.pk_on_device = true;
+  return emit_events_impl(h, src, n, info, err_event);
 }
 
 int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_signal_out) {

@@ -723,9 +723,32 @@ struct Sink {
   PodVec<uint32_t> idx;          // array indices of the declared names
   PodVec<c2a_event> aos;         // the same calls as c2a_event records, written when somebody asks (c2a_program_events)
   bool aos_valid = false;
+  // Without a host emitter attached, a replayed instance is not even copied: kinds / words grow by its length, the range stays
+  // unwritten (untouched pages) and a c2a_replay record says where it comes from.  The device expands the records itself
+  // (c2a_emit_compressed_device: the host ships every distinct instance once); materialise() carries them out on the host for
+  // callers that want the full arrays.  gen = 1 + the largest gen among the records inside the source range (0 if none): all
+  // records of one gen can be expanded concurrently once the smaller gens are done.
+  std::vector<c2a_replay> replays;  // ascending dst
+  size_t replays_done = 0;
+  uint32_t max_gen = 0;
+  bool lazy = false;
   Symbols sym;
-  struct Mark { uint64_t k, w, c; uint32_t id; };  // a position in the recording
-  Mark mark() const { return Mark{kinds.size(), words.size(), const_ids.size(), (uint32_t)names.size()}; }
+  struct Mark { uint64_t k, w, c; uint32_t id; size_t r; };  // a position in the recording
+  Mark mark() const { return Mark{kinds.size(), words.size(), const_ids.size(), (uint32_t)names.size(), replays.size()}; }
+  uint32_t max_gen_between(const Mark& b, const Mark& e) const {
+    uint32_t g = 0;
+    for (size_t i = b.r; i < e.r; ++i) g = std::max(g, replays[i].gen);
+    return g;
+  }
+  void materialise() {
+    for (; replays_done < replays.size(); ++replays_done) {
+      const c2a_replay& r = replays[replays_done];
+      memcpy(kinds.data() + r.k_dst, kinds.data() + r.k_src, r.k_len);
+      const uint32_t* src = words.data() + r.w_src;
+      uint32_t* dst = words.data() + r.w_dst;
+      for (uint64_t i = 0; i < r.w_len; ++i) dst[i] = src[i] + r.delta;
+    }
+  }
 
   void check(int st) {
     if (st == C2A_OK) return;
@@ -784,9 +807,14 @@ struct Sink {
   // Replay of an earlier instance of the same callable with the same arguments (Walker::handle_call): the calls recorded
   // between the marks b and e are recorded again with every signal id moved by delta.  A call starts an empty context, so each
   // id in the slice belongs to the slice - every payload word is one, and the kind bytes and name records do not change.
-  void replay(const Mark& b, const Mark& e, uint32_t delta) {
+  void replay(const Mark& b, const Mark& e, uint32_t delta, uint32_t src_gen) {
     const Mark at = mark();
-    kinds.append_self(b.k, e.k);
+    if (lazy) {
+      kinds.resize_uninit(kinds.size() + (e.k - b.k));
+      words.resize_uninit(words.size() + (e.w - b.w));
+      replays.push_back(c2a_replay{at.k, b.k, e.k - b.k, at.w, b.w, e.w - b.w, delta, src_gen + 1});
+      max_gen = std::max(max_gen, src_gen + 1);
+    } else kinds.append_self(b.k, e.k);
     if (e.id > b.id) {               // the names: one span record instead of 16 bytes per signal
       names.resize_uninit(names.size() + (e.id - b.id));
       spans.push_back(Span{at.id, e.id - b.id, b.id});
@@ -794,8 +822,8 @@ struct Sink {
     const_vals.append_self(b.c, e.c);
     const_ids.reserve(const_ids.size() + (e.c - b.c));
     for (uint64_t i = b.c; i < e.c; ++i) const_ids.push_back(const_ids[i] + delta);
-    words.reserve(words.size() + (e.w - b.w));
-    {
+    if (!lazy) {
+      words.reserve(words.size() + (e.w - b.w));
       const uint32_t* src = words.data() + b.w;
       uint32_t* dst = words.data() + words.size();
       const uint64_t n = e.w - b.w;
@@ -819,6 +847,7 @@ struct Sink {
   // the recording as c2a_event records (include/c2a.h), for callers of c2a_program_events
   const PodVec<c2a_event>& events() {
     if (aos_valid) return aos;
+    materialise();
     aos.resize_uninit(kinds.size());
     uint64_t w = 0, c = 0;
     uint32_t id = 0;
@@ -1086,6 +1115,7 @@ struct Walker {
     uint32_t seen = 0;
     bool cached = false;
     Sink::Mark begin{}, end{};  // the instance's slice of the recording
+    uint32_t gen = 0;           // largest replay generation inside the slice
     uint64_t rel_depth = 0;  // deepest call below this one, relative to it
     std::optional<uint32_t> value;
     std::shared_ptr<SigMap> comp;
@@ -1115,7 +1145,7 @@ struct Walker {
       m = &memo[std::move(key)];  // (references into an unordered_map survive the insertions the nested calls make)
       if (m->cached && depth + m->rel_depth <= 10000) {
         const uint32_t delta = next_signal_id - m->begin.id;
-        ac.replay(m->begin, m->end, delta);
+        ac.replay(m->begin, m->end, delta, m->gen);
         next_signal_id += m->end.id - m->begin.id;
         depth_hw = std::max(depth_hw, depth + m->rel_depth);
         ++memo_hits;
@@ -1157,6 +1187,7 @@ struct Walker {
     pop_frame();
     if (record) {
       m->begin = begin; m->end = ac.mark();
+      m->gen = ac.max_gen_between(m->begin, m->end);
       m->rel_depth = depth_hw - depth;
       m->value = ret.value;
       if (ret.comp) m->comp = std::make_shared<SigMap>(*ret.comp);
@@ -1316,6 +1347,7 @@ static int compile_body(c2a_program* p, const std::string& src, const std::strin
   using namespace front;
   p->sink = Sink();
   p->sink.into = into;
+  p->sink.lazy = into == nullptr;
   p->error.clear();
   p->spelled.clear();
   p->inputs.clear(); p->outputs.clear();
@@ -1414,8 +1446,15 @@ int c2a_program_compile_source(c2a_program* p, const char* source, const char* i
 }
 int c2a_program_packed(c2a_program* p, c2a_packed_events* out) {  // the recording itself: nothing is converted
   if (!p || !out) return C2A_ERR_INVALID_ARGUMENT;
+  p->sink.materialise();
   *out = c2a_packed_events{p->sink.kinds.data(), p->sink.words.data(), (uint64_t)p->sink.kinds.size(), (uint64_t)p->sink.words.size(),
                            C2A_PACKED_DENSE_IDS, 0};
+  return C2A_OK;
+}
+int c2a_program_compressed(c2a_program* p, c2a_compressed_events* out) {  // nothing is expanded here
+  if (!p || !out) return C2A_ERR_INVALID_ARGUMENT;
+  *out = c2a_compressed_events{p->sink.kinds.data(), p->sink.words.data(), (uint64_t)p->sink.kinds.size(), (uint64_t)p->sink.words.size(),
+                               p->sink.replays.data(), (uint64_t)p->sink.replays.size(), p->sink.max_gen, C2A_PACKED_DENSE_IDS};
   return C2A_OK;
 }
 uint64_t c2a_program_num_events(const c2a_program* p) { return p->sink.kinds.size(); }

@@ -41,6 +41,12 @@ struct c2a_handle {
   char* ev_buf = nullptr;
   size_t ev_bytes = 0;
   size_t slab_keep = 0;  // bytes at the start of the slab that slab_reset_keep() preserves (the emitted circuit)
+  // compressed streams (c2a_emit_compressed_device): the expanded packed stream on the device, pinned staging for the literal
+  // ranges and the chunk tables
+  char* cx_buf = nullptr;
+  size_t cx_bytes = 0;
+  char* cx_pinned = nullptr;
+  size_t cx_pinned_bytes = 0;
   struct Emitted {
     bool valid = false;
     bool nos_valid = false;      // node_of_signal[] resident (false for sparse signal ids on the host path)

@@ -18,7 +18,7 @@ from typing import Optional
 
 import numpy as np
 
-from ._lib import lib, CircuitError, PackedEvents, Status
+from ._lib import lib, CircuitError, CompressedEvents, PackedEvents, Status
 from .compiler import AGateType, BristolCircuit, CircuitInfo, Compiler, ConstantInfo, DeviceContext, EVENT_DTYPE, default_context
 
 
@@ -63,11 +63,25 @@ class DeviceCompiler:
         ni, no = int(lib.c2a_program_num_inputs(prog)), int(lib.c2a_program_num_outputs(prog))
         self.input_signals = view(lib.c2a_program_inputs(prog), ni, C.c_uint32, np.uint32).copy()
         self.output_signals = view(lib.c2a_program_outputs(prog), no, C.c_uint32, np.uint32).copy()
-        pk = PackedEvents()
-        lib.c2a_program_packed(prog, C.byref(pk))
-        self._kinds = view(pk.kinds, n, C.c_uint8, np.uint8)
-        self._words = view(pk.words, int(pk.n_words), C.c_uint32, np.uint32)
-        self._flags = int(pk.flags)
+        self._packed = None  # (kinds, words, flags) views of the fully expanded packed stream, made on first use
+        self._view = view
+
+    def compressed(self) -> CompressedEvents:
+        """the recording as the walker keeps it: replayed instances are records, not copies (c2a_program_compressed)"""
+        cx = CompressedEvents()
+        lib.c2a_program_compressed(self._prog, C.byref(cx))
+        return cx
+
+    def _packed_views(self):
+        if self._packed is None:  # c2a_program_packed carries the replay records out on the host
+            pk = PackedEvents()
+            lib.c2a_program_packed(self._prog, C.byref(pk))
+            self._packed = (self._view(pk.kinds, int(pk.n_events), C.c_uint8, np.uint8), self._view(pk.words, int(pk.n_words), C.c_uint32, np.uint32), int(pk.flags))
+        return self._packed
+
+    _kinds = property(lambda self: self._packed_views()[0])
+    _words = property(lambda self: self._packed_views()[1])
+    _flags = property(lambda self: self._packed_views()[2])
 
     @property
     def events(self) -> np.ndarray:
@@ -95,7 +109,7 @@ class DeviceCompiler:
 
     def build_circuit(self) -> BristolCircuit:
         ctx = self._ctx or default_context(self._device)
-        info = ctx.emit_packed(self._kinds, self._words, self._flags)        # raises the reference's CircuitError on a bad stream
+        info = ctx.emit_compressed(self.compressed())                        # raises the reference's CircuitError on a bad stream
         ins, outs = self.input_signals, self.output_signals
         in_names, out_names = [self.signal_name(s) for s in ins], [self.signal_name(s) for s in outs]
         # src/compiler.rs:327-383: input / output <=> node, walked in ascending signal id

@@ -333,6 +333,28 @@ const uint32_t* c2a_program_outputs(const c2a_program*);
 /* the recorded calls as a packed stream (arrays owned by the program object, valid until it is freed or recompiled).  This IS
  * the walker's recording - nothing is converted; c2a_program_events() writes the 16-byte records on first request. */
 int c2a_program_packed(c2a_program*, c2a_packed_events* out);
+/* The recording in COMPRESSED form.  From its second instance on, a (template, arguments) pair is not interpreted again by the
+ * walker: its calls are those of the first instance with every signal id shifted (a call runs in an empty context,
+ * src/runtime.rs:75-77).  Without a host emitter attached the walker does not even copy them: the packed arrays grow by the
+ * instance's length, the range stays unwritten, and a c2a_replay record says where it comes from:
+ *     kinds[k_dst .. k_dst + k_len) = kinds[k_src ..],      words[w_dst .. w_dst + w_len) = words[w_src ..] + delta
+ * (sources lie before their destination; records ascend by destination and are disjoint; a source may contain destinations
+ * of earlier records: gen = 1 + the largest gen inside the source range, so all records of one gen are independent once the
+ * smaller gens are done).  c2a_emit_compressed_device() ships only the written ranges and the records and expands them on the
+ * GPU; c2a_program_packed() / c2a_program_events() carry the records out on the host first. */
+typedef struct { uint64_t k_dst, k_src, k_len, w_dst, w_src, w_len; uint32_t delta, gen; } c2a_replay;
+typedef struct {
+  const uint8_t* kinds;      /* n_events bytes; ranges that are the destination of a replay record may be unwritten */
+  const uint32_t* words;     /* n_words words; likewise */
+  uint64_t n_events, n_words;
+  const c2a_replay* replays;
+  uint64_t n_replays;
+  uint32_t max_gen;
+  uint32_t flags;            /* C2A_PACKED_DENSE_IDS (always set by the walker) */
+} c2a_compressed_events;
+int c2a_program_compressed(c2a_program*, c2a_compressed_events* out);
+/* expand on the device, then exactly c2a_emit_packed_resident on the expanded stream (same results, same errors) */
+int c2a_emit_compressed_device(c2a_handle*, const c2a_compressed_events*, c2a_emit_info* info, uint64_t* err_event);
 /* the constant signals (add_signal with a value, src/process.rs:558-579) in declaration order, and their values: what the
  * `constants` map of CircuitInfo is built from (src/compiler.rs:466-493) without reading the event records */
 uint64_t c2a_program_num_constants(const c2a_program*);

@@ -339,3 +339,52 @@ def test_instance_memo_at_a_million_gates(c2a, monkeypatch):
     assert flags == 1 and np.array_equal(kinds_b, fast["kinds"]) and np.array_equal(words, fast["words"])
     consts = ev[(ev[:, 0] & 0xFF) == 1]
     assert np.array_equal(consts[:, 1], fast["const_ids"]) and np.array_equal(consts[:, 2], fast["const_vals"])
+
+
+def _compressed_and_packed(c2a, src):
+    """(kinds, words) expanded in numpy from the compressed recording the way the device does it - literal ranges first, then the
+    replay records generation by generation, unwritten ranges poisoned - and the host-materialised packed stream"""
+    import ctypes as C
+    from circom_2_arithc_b200._lib import CompressedEvents, PackedEvents, Replay
+    lib = c2a.lib
+    p = lib.c2a_program_new()
+    try:
+        assert lib.c2a_program_compile_source(p, src.encode(), None, None) == 0
+        cx = CompressedEvents()
+        assert lib.c2a_program_compressed(p, C.byref(cx)) == 0
+        n, nw, nr = int(cx.n_events), int(cx.n_words), int(cx.n_replays)
+        arr = lambda ptr, k, ct: np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(k,)).copy() if k else np.zeros(0, ct)
+        kinds, words = arr(cx.kinds, n, C.c_uint8), arr(cx.words, nw, C.c_uint32)
+        recs = [(r.k_dst, r.k_src, r.k_len, r.w_dst, r.w_src, r.w_len, r.delta, r.gen) for r in (Replay * nr).from_address(cx.replays)] if nr else []
+        k_at = w_at = 0
+        for kd, ks, kl, wd, ws, wl, _delta, gen in recs:                      # ascending, disjoint, sources before destinations
+            assert kd >= k_at and wd >= w_at and ks + kl <= kd and ws + wl <= wd and 1 <= gen <= cx.max_gen
+            k_at, w_at = kd + kl, wd + wl
+            kinds[kd:kd + kl] = 0xEE                                             # what the walker left unwritten must not matter
+            words[wd:wd + wl] = 0xDEADBEEF
+        assert k_at <= n and w_at <= nw
+        for g in range(1, int(cx.max_gen) + 1):
+            snap_k, snap_w = kinds.copy(), words.copy()                          # records of one generation only read older data
+            for kd, ks, kl, wd, ws, wl, delta, gen in recs:
+                if gen == g:
+                    kinds[kd:kd + kl] = snap_k[ks:ks + kl]
+                    words[wd:wd + wl] = snap_w[ws:ws + wl] + np.uint32(delta)
+        pk = PackedEvents()
+        assert lib.c2a_program_packed(p, C.byref(pk)) == 0 and int(pk.n_events) == n and int(pk.n_words) == nw and pk.flags == cx.flags == 1
+        return (kinds, words), (arr(pk.kinds, n, C.c_uint8), arr(pk.words, nw, C.c_uint32)), nr, int(cx.max_gen)
+    finally:
+        lib.c2a_program_free(p)
+
+
+def test_compressed_recording_expands_to_the_packed_stream(c2a):
+    """c2a_program_compressed: replayed instances are records (destination, source, id shift, generation), not copies; expanding
+    them generation by generation gives exactly the packed stream c2a_program_packed materialises"""
+    nested = [c[0] for c in fx.WALKER_STRESS if c[1] == 0]
+    seen_gen = 0
+    for src in [c2a.workloads.mimc_circom_source(40, 91), c2a.workloads.mimc_circom_source(3, 2)] + nested:
+        (k1, w1), (k2, w2), nr, max_gen = _compressed_and_packed(c2a, src)
+        assert np.array_equal(k1, k2) and np.array_equal(w1, w2)
+        seen_gen = max(seen_gen, max_gen)
+    (k1, _), _, nr, max_gen = _compressed_and_packed(c2a, c2a.workloads.mimc_circom_source(40, 91))
+    assert nr == 38 and max_gen == 1            # instances 3..40 of MiMC(91) are one record each
+    assert seen_gen >= 2                        # a replayed instance containing replayed instances

@@ -158,3 +158,36 @@ def test_compile_with_the_device_emitter_gives_the_same_bristol_circuit(c2a, ctx
     assert str(e_dev.value) == str(e_host.value) and "used for both input 0.complement" in str(e_dev.value)
     with pytest.raises(c2a.ProgramError):
         c2a.compile(None, source="template T() { signal input a; a === 1; } component main = T();", emitter="device")
+
+
+def test_compressed_recording_is_expanded_on_the_device(c2a, ctx):
+    """c2a_emit_compressed_device: only the literal ranges and the replay records of the walker's recording cross PCIe, the replayed
+    instances are expanded in HBM generation by generation - same emit_info, gates and signal -> node map as the host-materialised
+    packed stream through c2a_emit_packed_device"""
+    import ctypes as C
+    from circom_2_arithc_b200._lib import CompressedEvents, Replay
+    import circom_fixtures as fx
+    lib = c2a.lib
+    sources = [c2a.workloads.mimc_circom_source(48, 91), c2a.workloads.mimc_circom_source(400, 91), c2a.workloads.mimc_circom_source(1, 1),
+               fx.ADD_ZERO, fx.INFIX_OPS] + [c[0] for c in fx.WALKER_STRESS if c[1] == 0]
+    deep = 0
+    for src in sources:
+        dev = c2a.compile(None, source=src, context=ctx, emitter="device")
+        cx = dev.compressed()
+        deep = max(deep, int(cx.max_gen))
+        info_c = ctx.emit_compressed(cx)
+        gates_c, nos_c = ctx.emitted_fetch()
+        info_p = ctx.emit_packed(dev._kinds, dev._words, dev._flags)            # materialises the records on the host
+        gates_p, nos_p = ctx.emitted_fetch()
+        assert info_c == info_p and info_c["path"] == 1
+        assert np.array_equal(gates_c, gates_p) and np.array_equal(nos_c, nos_p)
+    assert deep >= 2
+    # inconsistent records are refused before anything is launched
+    dev = c2a.compile(None, source=c2a.workloads.mimc_circom_source(8, 5), context=ctx, emitter="device")
+    cx = dev.compressed()
+    recs = (Replay * int(cx.n_replays)).from_address(cx.replays)
+    bad = (Replay * int(cx.n_replays))(*recs)
+    bad[0].k_src = bad[0].k_dst                                                 # a source that overlaps its destination
+    cx2 = CompressedEvents(cx.kinds, cx.words, cx.n_events, cx.n_words, C.cast(bad, C.c_void_p), cx.n_replays, cx.max_gen, cx.flags)
+    with pytest.raises((c2a.C2AError, c2a.CircuitError)):
+        ctx.emit_compressed(cx2)
