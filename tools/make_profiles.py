@@ -57,7 +57,7 @@ All captures: B200 (sm_100a, 148 SMs, `clocks.max.sm` 1965 MHz), driver 580, CUD
 Per-launch times in an ncu launch list are cold-cache and serialised: compare SHARES with `bench.py`, not absolutes.
 `superseded/` holds the first captures of this round (before the sync-free pipeline, the node-side wire numbering and the
 packed event stream); they are kept only for the history of the numbers.  `tools/make_profiles.py <prefix>` regenerates this
-directory from one evidence set in `gpurun_out/`.
+directory from one evidence set in `gpurun_out/` (the last set, `r01j`, re-measured the default bench line after the front-end / compressed-stream work; its AoS, reference-arm, launch-list and ncu files are those of `r01i`, taken two hours earlier on the same kernels).
 
 ## Round 1 (final state of the round)
 
@@ -83,7 +83,7 @@ Headline (10 018 305 gates, MiMC chains W = 18 315, `late` variant = non-identit
 {chr(10).join(multi)}
 | dominant kernel | `{r['kernel']}`: {r['kernel_ms']*1e3:.0f} µs live in the timed steps, {r['achieved']:.0f} GB/s algorithmic = **{r['frac']:.2f} of the measured {r['peak']:.0f} GB/s**; ncu DRAM traffic {r['traffic']/1e6:.0f} MB vs {r['alg_bytes_per_launch']/1e6:.0f} MB algorithmic |
 | reference arm (oracle port, 1 thread, {ref['config']['sample'].split(':')[0]}) | {ref['value']:.0f} gates/s; its back end alone on the full 10 M gates: {cb.get('backend_only_gates_per_s', 0)/1e6:.1f} M gates/s |
-| `from_source` (the same workload as .circom text → front end on one host core → packed stream → device emitter → build → gates + named wires on the host) | {fs.get('value', 0)/1e6:.1f} M gates/s: walk {fs.get('walk_s', 0)*1e3:.0f} ms + device {fs.get('device_s', 0)*1e3:.0f} ms (pageable buffers) |
+| `from_source` (the same workload as .circom text → front end on one host core → packed stream → device emitter → build → gates + named wires on the host) | {fs.get('value', 0)/1e6:.0f} M gates/s: walk {fs.get('walk_s', 0)*1e3:.0f} ms + device {fs.get('device_s', 0)*1e3:.1f} ms ({fs.get('replay_records', 0)} replay records expanded in HBM: ≈ 1 MB crosses PCIe instead of 250 MB; gates into pinned host memory) |
 | host union-find emitter + `c2a_build_circuit` (same circuit, 1 step) | {d.get('e2e_host_emitter', {}).get('value', 0)/1e6:.1f} M gates/s |
 | clocks during the timed region | {d['clocks']} |
 
