@@ -154,6 +154,7 @@ _SIGS = {
     "c2a_program_constant_signals": (vp, [vp]),
     "c2a_program_constant_values": (vp, [vp]),
     "c2a_program_signal_name": (cp, [vp, u32]),
+    "c2a_program_signal_names": (u64, [vp, vp, u64, vp, u64]),
     "c2a_program_num_inputs": (u32, [vp]),
     "c2a_program_num_outputs": (u32, [vp]),
     "c2a_program_inputs": (vp, [vp]),

@@ -1470,6 +1470,17 @@ const char* c2a_program_signal_name(const c2a_program* cp, uint32_t id) {  // sp
   if (it == p->spelled.end()) it = p->spelled.emplace(id, p->sink.name_of(id)).first;
   return it->second.c_str();
 }
+// many names at once: '\n'-separated (a signal id that does not exist contributes an empty name); returns the byte count
+uint64_t c2a_program_signal_names(const c2a_program* p, const uint32_t* ids, uint64_t n, char* out, uint64_t cap) {
+  if (!p || (n && !ids)) return 0;
+  uint64_t at = 0;
+  for (uint64_t i = 0; i < n; ++i) {
+    std::string nm = ids[i] < p->sink.names.size() ? p->sink.name_of(ids[i]) : std::string();
+    if (out && at + nm.size() + 1 <= cap) { memcpy(out + at, nm.data(), nm.size()); out[at + nm.size()] = '\n'; }
+    at += nm.size() + 1;
+  }
+  return at;
+}
 uint32_t c2a_program_num_inputs(const c2a_program* p) { return (uint32_t)p->inputs.size(); }
 uint32_t c2a_program_num_outputs(const c2a_program* p) { return (uint32_t)p->outputs.size(); }
 const uint32_t* c2a_program_inputs(const c2a_program* p) { return p->inputs.data(); }

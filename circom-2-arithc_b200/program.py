@@ -107,11 +107,21 @@ class DeviceCompiler:
         p = lib.c2a_program_signal_name(self._prog, int(sid))
         return p.decode() if p is not None else ""
 
+    def signal_names(self, sids) -> list:
+        """names of many signals with one call (c2a_program_signal_names)"""
+        ids = np.ascontiguousarray(sids, dtype=np.uint32)
+        if ids.shape[0] == 0:
+            return []
+        need = int(lib.c2a_program_signal_names(self._prog, ids.ctypes.data_as(C.c_void_p), ids.shape[0], None, 0))
+        buf = C.create_string_buffer(need + 1)
+        lib.c2a_program_signal_names(self._prog, ids.ctypes.data_as(C.c_void_p), ids.shape[0], buf, need)
+        return buf.raw[:need - 1].decode().split("\n")
+
     def build_circuit(self) -> BristolCircuit:
         ctx = self._ctx or default_context(self._device)
         info = ctx.emit_compressed(self.compressed())                        # raises the reference's CircuitError on a bad stream
         ins, outs = self.input_signals, self.output_signals
-        in_names, out_names = [self.signal_name(s) for s in ins], [self.signal_name(s) for s in outs]
+        in_names, out_names = self.signal_names(ins), self.signal_names(outs)
         # src/compiler.rs:327-383: input / output <=> node, walked in ascending signal id
         seen_in, seen_out = set(), set()
         nodes = ctx.emitted_signal_nodes(np.concatenate([ins, outs]))
@@ -133,8 +143,8 @@ class DeviceCompiler:
         w_in, w_out, w_c = named[:len(ins)], named[len(ins):len(ins) + len(outs)], named[len(ins) + len(outs):]
         ci = CircuitInfo()
         ci.input_name_to_wire_index = {nm: int(w) for nm, w in sorted(zip(in_names, w_in.tolist()))}
-        for (_k, sid, val, _z), w in sorted(((tuple(r), w) for r, w in zip(consts.tolist(), w_c.tolist())), key=lambda t: f"{self.signal_name(t[0][1])}_{t[0][1]}"):
-            key = f"{self.signal_name(sid)}_{sid}"                           # :356
+        const_keys = [f"{nm}_{sid}" for nm, sid in zip(self.signal_names(consts[:, 1]), consts[:, 1].tolist())]   # :356
+        for key, val, w in sorted(zip(const_keys, consts[:, 2].tolist(), w_c.tolist())):
             if w == 0xFFFFFFFF:
                 raise CircuitError(Status.REFERENCE_PANIC, f"constant {key} has no wire (the reference panics at src/compiler.rs:473)")
             ci.constants[key] = ConstantInfo(str(int(val)), int(w))

@@ -326,6 +326,8 @@ uint64_t c2a_program_num_events(const c2a_program*);
 const c2a_event* c2a_program_events(const c2a_program*);
 uint64_t c2a_program_num_signals(const c2a_program*);
 const char* c2a_program_signal_name(const c2a_program*, uint32_t signal_id);
+/* many names at once, '\n'-separated; returns the number of bytes they take and writes them when out != NULL and cap suffices */
+uint64_t c2a_program_signal_names(const c2a_program*, const uint32_t* signal_ids, uint64_t n, char* out, uint64_t cap);
 uint32_t c2a_program_num_inputs(const c2a_program*);   /* signals tagged as circuit inputs (ascending ids) */
 uint32_t c2a_program_num_outputs(const c2a_program*);
 const uint32_t* c2a_program_inputs(const c2a_program*);

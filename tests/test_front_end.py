@@ -388,3 +388,11 @@ def test_compressed_recording_expands_to_the_packed_stream(c2a):
     (k1, _), _, nr, max_gen = _compressed_and_packed(c2a, c2a.workloads.mimc_circom_source(40, 91))
     assert nr == 38 and max_gen == 1            # instances 3..40 of MiMC(91) are one record each
     assert seen_gen >= 2                        # a replayed instance containing replayed instances
+
+
+def test_signal_names_in_one_call(c2a):
+    dev = c2a.compile(None, source=c2a.workloads.mimc_circom_source(5, 7), emitter="device")
+    n = int(c2a.lib.c2a_program_num_signals(dev._prog))
+    ids = list(range(n)) + [n + 3]                               # an id that does not exist has the empty name
+    assert dev.signal_names(ids) == [dev.signal_name(i) for i in range(n)] + [""]
+    assert dev.signal_names([]) == [] and dev.signal_names([0]) == ["0.in[0]"]
