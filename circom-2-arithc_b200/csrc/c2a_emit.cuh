@@ -1144,7 +1144,8 @@ int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c
   uint32_t max_gen = 0;
   for (uint64_t i = 0; i < nr; ++i) {
     const c2a_replay& r = cx->replays[i];
-    if (r.k_dst < k_at || r.w_dst < w_at || r.k_len > n - r.k_dst || r.w_len > nw - r.w_dst || r.k_src + r.k_len > r.k_dst ||
+    if (r.k_dst < k_at || r.w_dst < w_at || r.k_dst > n || r.w_dst > nw || r.k_len > n - r.k_dst || r.w_len > nw - r.w_dst ||
+        r.k_src > r.k_dst || r.w_src > r.w_dst || r.k_src + r.k_len > r.k_dst ||
         r.w_src + r.w_len > r.w_dst || r.gen == 0 || r.gen > 1u << 20)
       return fail(h, C2A_ERR_INVALID_ARGUMENT, "replay record %llu is inconsistent", (unsigned long long)i);
     lit_k += r.k_dst - k_at;
