@@ -229,6 +229,65 @@ def poseidon_shaped(t: int = 3, RF: int = 8, RP: int = 57) -> Workload:
                     inputs={i: em.names[i] for i in ins}, outputs={out: "0.out"}, n_gates=em.n_gates, n_signals=em.next)
 
 
+def poseidon_circom_source(t: int = 3, RF: int = 8, RP: int = 57) -> str:
+    """BASELINE config 2 as a .circom program in the subset the reference accepts (circomlib's own Poseidon uses features it rejects):
+    the same permutation as poseidon_shaped() - ARC constants c = round*t + lane + 1, S-box x^5 (3 multiplications), MDS entry
+    ((i+1)*(j+2)) % 7 + 1 - with the capacity lane fed by 0 and lane 0 of the last state as output; u32 arithmetic (wrapping)."""
+    return """pragma circom 2.0.0;
+function arc(r, lane, t) { return r * t + lane + 1; }
+function mds(i, j) { return ((i + 1) * (j + 2)) %% 7 + 1; }
+template Sbox() {
+    signal input in; signal output out;
+    signal x2; signal x4;
+    x2 <== in * in; x4 <== x2 * x2; out <== x4 * in;
+}
+template Round(r, full, t) {
+    signal input in[t]; signal output out[t];
+    signal a[t]; signal b[t];
+    component s[t];
+    for (var i = 0; i < t; i++) {
+        a[i] <== in[i] + arc(r, i, t);
+        if (full == 1 || i == 0) { s[i] = Sbox(); s[i].in <== a[i]; b[i] <== s[i].out; } else { b[i] <== a[i]; }
+    }
+    signal acc[t][t];
+    for (var i = 0; i < t; i++) {
+        acc[i][0] <== b[0] * mds(i, 0);
+        for (var j = 1; j < t; j++) { acc[i][j] <== acc[i][j - 1] + b[j] * mds(i, j); }
+        out[i] <== acc[i][t - 1];
+    }
+}
+template Poseidon(t, RF, RP) {
+    signal input in[t - 1]; signal output out;
+    component rounds[RF + RP];
+    for (var r = 0; r < RF + RP; r++) {
+        var full = 0;
+        if (r < RF \\ 2 || r >= RF \\ 2 + RP) { full = 1; }
+        rounds[r] = Round(r, full, t);
+        if (r == 0) {
+            rounds[r].in[0] <== 0;
+            for (var i = 1; i < t; i++) { rounds[r].in[i] <== in[i - 1]; }
+        } else {
+            for (var i = 0; i < t; i++) { rounds[r].in[i] <== rounds[r - 1].out[i]; }
+        }
+    }
+    out <== rounds[RF + RP - 1].out[0];
+}
+component main = Poseidon(%d, %d, %d);
+""" % (t, RF, RP)
+
+
+def poseidon_reference(inputs: List[int], t: int = 3, RF: int = 8, RP: int = 57) -> int:
+    """the function poseidon_circom_source() / poseidon_shaped() compute, in u32 arithmetic"""
+    M = 0xFFFFFFFF
+    state = [0] + [int(x) & M for x in inputs]
+    for r in range(RF + RP):
+        full = r < RF // 2 or r >= RF // 2 + RP
+        a = [(state[i] + r * t + i + 1) & M for i in range(t)]
+        b = [pow(a[i], 5, 1 << 32) if (full or i == 0) else a[i] for i in range(t)]
+        state = [sum(b[j] * (((i + 1) * (j + 2)) % 7 + 1) for j in range(t)) & M for i in range(t)]
+    return state[0]
+
+
 def _xor(em, a, b):
     return em.gate(G.AXor, a, b)
 

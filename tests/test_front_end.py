@@ -396,3 +396,18 @@ def test_signal_names_in_one_call(c2a):
     ids = list(range(n)) + [n + 3]                               # an id that does not exist has the empty name
     assert dev.signal_names(ids) == [dev.signal_name(i) for i in range(n)] + [""]
     assert dev.signal_names([]) == [] and dev.signal_names([0]) == ["0.in[0]"]
+
+
+def test_poseidon_program(c2a, orc, monkeypatch):
+    """BASELINE config 2 as a real .circom program (functions for the constants, nested loops, 2-D signal arrays, component arrays
+    instantiated under an `if`): 1 413 gates like the synthetic poseidon_shaped() stream, and the circuit computes the permutation"""
+    src = c2a.workloads.poseidon_circom_source()
+    comp = c2a.compile(None, source=src)
+    assert comp.gate_array().shape[0] == 1413 == c2a.workloads.poseidon_shaped().n_gates
+    circ = to_oracle(orc, comp).build_circuit()
+    for a, b in ((0, 0), (1, 2), (0xFFFFFFFF, 0x9E3779B9), (123456789, 987654321)):
+        assert run_named(orc, circ, {"0.in[0]": a, "0.in[1]": b}) == {"0.out": c2a.workloads.poseidon_reference([a, b])}
+    monkeypatch.delenv("C2A_FRONT_NO_MEMO", raising=False)
+    fast = _walk(c2a, src)                      # Sbox() is interpreted twice and replayed 79 times
+    monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
+    assert _walk(c2a, src) == fast and fast[0] == 0

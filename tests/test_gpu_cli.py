@@ -145,7 +145,7 @@ def test_compile_with_the_device_emitter_gives_the_same_bristol_circuit(c2a, ctx
     """compile(emitter="device"): the walk only records its calls, build_circuit() replays them on the GPU (packed stream) and
     looks the named wires up - same BristolCircuit and same CircuitError as the host-emitter Compiler (src/compiler.rs:321-494)"""
     sources = [fx.ADD_ZERO, fx.INFIX_OPS, fx.MAT_ELEM_MUL, fx.SUM, fx.X_EQ_X, fx.CONSTANT_SUM, fx.DIRECT_OUTPUT,
-               fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), c2a.workloads.mimc_circom_source(5, 7)]
+               fx.ARGMAX.replace("ArgMax(N)", "ArgMax(5)"), c2a.workloads.mimc_circom_source(5, 7), c2a.workloads.poseidon_circom_source()]
     for src in sources:
         host = c2a.compile(None, source=src, context=ctx).build_circuit()
         dev = c2a.compile(None, source=src, context=ctx, emitter="device")
@@ -169,7 +169,7 @@ def test_compressed_recording_is_expanded_on_the_device(c2a, ctx):
     import circom_fixtures as fx
     lib = c2a.lib
     sources = [c2a.workloads.mimc_circom_source(48, 91), c2a.workloads.mimc_circom_source(400, 91), c2a.workloads.mimc_circom_source(1, 1),
-               fx.ADD_ZERO, fx.INFIX_OPS] + [c[0] for c in fx.WALKER_STRESS if c[1] == 0]
+               c2a.workloads.poseidon_circom_source(), fx.ADD_ZERO, fx.INFIX_OPS] + [c[0] for c in fx.WALKER_STRESS if c[1] == 0]
     deep = 0
     for src in sources:
         dev = c2a.compile(None, source=src, context=ctx, emitter="device")
