@@ -411,3 +411,29 @@ def test_poseidon_program(c2a, orc, monkeypatch):
     fast = _walk(c2a, src)                      # Sbox() is interpreted twice and replayed 79 times
     monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
     assert _walk(c2a, src) == fast and fast[0] == 0
+
+
+def test_sha256_compression_program_gives_the_real_digest(c2a, orc, monkeypatch):
+    """The SHA-256 compression function (FIPS 180-4) written in the circom subset on the reference's u32 gate arithmetic: front end ->
+    calls -> oracle build_circuit -> simulation = hashlib.  (Templates instantiated hundreds of times with a handful of argument
+    tuples: the instance memo interprets each pair twice and replays the rest.)"""
+    import hashlib
+    import struct
+    src = c2a.workloads.sha256_circom_source()
+    comp = c2a.compile(None, source=src)
+    assert 3000 < comp.gate_array().shape[0] < 4000
+    circ = to_oracle(orc, comp).build_circuit()
+    iv = [0x6a09e667, 0xbb67ae85, 0x3c6ef372, 0xa54ff53a, 0x510e527f, 0x9b05688c, 0x1f83d9ab, 0x5be0cd19]
+    for msg in (b"abc", b"", b"circom-2-arithc on B200: gate graph builder"):
+        blk = msg + b"\x80" + b"\0" * (55 - len(msg)) + struct.pack(">Q", 8 * len(msg))
+        w = list(struct.unpack(">16I", blk))
+        ins = {f"0.h[{i}]": iv[i] for i in range(8)}
+        ins.update({f"0.w[{i}]": w[i] for i in range(16)})
+        out = run_named(orc, circ, ins)
+        digest = b"".join(struct.pack(">I", out[f"0.out[{i}]"]) for i in range(8)).hex()
+        assert digest == hashlib.sha256(msg).hexdigest()
+        assert [out[f"0.out[{i}]"] for i in range(8)] == c2a.workloads.sha256_compress_reference(iv, w)
+    monkeypatch.delenv("C2A_FRONT_NO_MEMO", raising=False)
+    fast = _walk(c2a, src)
+    monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
+    assert _walk(c2a, src) == fast and fast[0] == 0
