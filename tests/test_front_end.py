@@ -437,3 +437,12 @@ def test_sha256_compression_program_gives_the_real_digest(c2a, orc, monkeypatch)
     fast = _walk(c2a, src)
     monkeypatch.setenv("C2A_FRONT_NO_MEMO", "1")
     assert _walk(c2a, src) == fast and fast[0] == 0
+
+
+def test_examples_are_the_generated_programs(c2a):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for name, text in (("sha256_compress", c2a.workloads.sha256_circom_source()), ("poseidon_t3", c2a.workloads.poseidon_circom_source()),
+                       ("mimc_chains_48x91", c2a.workloads.mimc_circom_source(48, 91))):
+        path = os.path.join(root, "examples", name + ".circom")
+        assert open(path).read() == text
+        assert c2a.compile(path).gate_array().shape[0] > 1000    # compile_file path (src/program.rs:18-29)
