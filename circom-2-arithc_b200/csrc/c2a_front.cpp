@@ -14,8 +14,14 @@
 // Temporaries (`random_<u32>` items, :229) are values, not entries; temporary SIGNALS still consume signal ids and are
 // named "<ctx>.random_<id>" (the reference's suffix is a thread_rng draw, i.e. unspecified).
 // The walk never touches a string: identifiers are interned after parsing (Symbols), `const_signal_<v>` items are keyed
-// by their value, and signal names are kept as 16-byte records (one span record for a whole replayed instance) that are spelled out only when somebody asks for one
-// (c2a_program_signal_name, the input / output prefix match, a host Compiler that wants the names).
+// by their value, and signal names are kept as 16-byte records (one span record for a whole replayed instance) that are
+// spelled out only when somebody asks for one (c2a_program_signal_name, the input / output prefix match, a host Compiler
+// that wants the names).
+// Recording.  The calls are recorded in the packed form the device emitter reads (Sink).  A (callable, arguments) pair is
+// interpreted twice at most: a call runs in an empty context, so later instances are the first one's calls with shifted
+// signal ids (Walker::handle_call).  With a host emitter attached they are replayed call by call; without one they are kept
+// as c2a_replay records and expanded on the GPU (c2a_emit_compressed_device) or, on request, on the host (Sink::materialise).
+// The walk runs on a thread with a 512 MB stack so that the call-depth guard fires before the native stack ends.
 // u32 arithmetic on variables follows a release build: + * ** wrap, shifts use the low 5 bits, - / \ % error as in
 // src/process.rs:649-750.
 #include <algorithm>
