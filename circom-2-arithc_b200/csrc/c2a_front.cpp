@@ -1094,7 +1094,12 @@ struct Walker {
       case Expr::Number:  // :294-306: the literal must fit u32
         if (e.num_overflow) fail(C2A_PROG_PARSING_ERROR, "Parsing error");
         return temp_var(e.num);
-      case Expr::Variable: return build_access(e.key, e.access);
+      case Expr::Variable:
+        if (e.access.empty()) {  // a plain variable is read here: the same value every later look-up of the name would give
+          Item* it = ctx().find(e.key);  // (the callee of a call in between runs in its own frame and cannot write it)
+          if (it && it->type == D_Variable && !it->var.is_array) return temp_var(it->var.val);
+        }
+        return build_access(e.key, e.access);
       default: fail(C2A_PROG_EXPRESSION_NOT_IMPLEMENTED, "Expression not implemented");
     }
   }
