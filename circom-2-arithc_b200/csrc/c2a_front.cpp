@@ -1383,20 +1383,40 @@ static int compile_body(c2a_program* p, const std::string& src, const std::strin
     // :57-66 — prefix match over ALL signal names ("0.c" also tags "0.const_signal_*"): replicate.  Only names of the root
     // context can start with "0." (every other context is named after a template or function).
     const uint32_t root = p->sink.sym.intern("0");
+    // A name is "0." + base + "[i][j]..": an identifier key is a prefix of it iff it is a prefix of the base, so the test is made
+    // once per base symbol and no name is spelled unless a host emitter wants it.
     auto tag = [&](const std::vector<std::string>& keys, std::vector<uint32_t>& ids, bool input) {
-      std::map<uint32_t, std::string> m;
+      auto starts = [&](const std::string& base) {
+        for (auto& k : keys) if (base.compare(0, k.size(), k) == 0) return true;
+        return false;
+      };
+      auto may_match = [&](const char* stem) {  // some key agrees with the stem on their common length ("c" and "const_signal_")
+        const size_t L = strlen(stem);
+        for (auto& k : keys) if (k.compare(0, std::min(L, k.size()), stem, std::min(L, k.size())) == 0) return true;
+        return false;
+      };
+      const bool const_may = may_match("const_signal_"), random_may = may_match("random_");
+      std::vector<int8_t> by_sym(p->sink.sym.strs.size(), -1);
       size_t sp = 0;  // replayed id ranges belong to callee contexts (and their name records are not materialised): skip them
       for (uint32_t id = 0; id < p->sink.names.size(); ++id) {
         while (sp < p->sink.spans.size() && p->sink.spans[sp].dst + p->sink.spans[sp].len <= id) ++sp;
         if (sp < p->sink.spans.size() && p->sink.spans[sp].dst <= id) { id = p->sink.spans[sp].dst + p->sink.spans[sp].len - 1; continue; }
-        if (p->sink.names[id].ctx != root) continue;
-        std::string name = p->sink.name_of(id);
-        for (auto& k : keys)
-          if (name.compare(2, k.size(), k) == 0) { m[id] = name; break; }
-      }
-      for (auto& kv : m) {
-        ids.push_back(kv.first);
-        if (into) (input ? c2a_add_input : c2a_add_output)(into, kv.first, kv.second.c_str());
+        const SigName& n = p->sink.names[id];
+        if (n.ctx != root) continue;
+        bool hit;
+        switch (n.kind_n & 3u) {
+          case 0: {
+            int8_t& c = by_sym[n.a];
+            if (c < 0) c = starts(p->sink.sym.strs[n.a]) ? 1 : 0;
+            hit = c == 1;
+            break;
+          }
+          case 1: hit = const_may && starts("const_signal_" + std::to_string(n.a)); break;
+          default: hit = random_may && starts("random_" + std::to_string(id)); break;
+        }
+        if (!hit) continue;
+        ids.push_back(id);  // ascending ids = the deterministic stand-in for the reference's HashMap order
+        if (into) (input ? c2a_add_input : c2a_add_output)(into, id, p->sink.name_of(id).c_str());
       }
     };
     tag(main.inputs, p->inputs, true);
