@@ -700,6 +700,7 @@ struct PodVec {
   void resize(size_t m) { reserve(m); if (m > n) memset((void*)(p + n), 0, (m - n) * sizeof(T)); n = m; }
   void resize_uninit(size_t m) { reserve(m); n = m; }
   void append_self(size_t b, size_t e) {  // append a copy of [b, e) of this array
+    if (e <= b) return;
     reserve(n + (e - b));
     memcpy((void*)(p + n), (const void*)(p + b), (e - b) * sizeof(T));
     n += e - b;
@@ -749,7 +750,7 @@ struct Sink {
   void materialise() {
     for (; replays_done < replays.size(); ++replays_done) {
       const c2a_replay& r = replays[replays_done];
-      memcpy(kinds.data() + r.k_dst, kinds.data() + r.k_src, r.k_len);
+      if (r.k_len) memcpy(kinds.data() + r.k_dst, kinds.data() + r.k_src, r.k_len);
       const uint32_t* src = words.data() + r.w_src;
       uint32_t* dst = words.data() + r.w_dst;
       for (uint64_t i = 0; i < r.w_len; ++i) dst[i] = src[i] + r.delta;
