@@ -9,9 +9,6 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent: its first (and only) run failed on a KeyError of the "
-                                        "test itself (the prefix match of src/program.rs:57-66 also tags ws[*] / hh[*] as inputs), fixed below but not "
-                                        "re-run on hardware; the same program is verified through the oracle in tests/test_front_end.py")
 def test_sha256_from_circom_text_to_digest_on_the_gpu(c2a, ctx):
     dev = c2a.compile(None, source=c2a.workloads.sha256_circom_source(), context=ctx, emitter="device")
     info = ctx.emit_compressed(dev.compressed())
