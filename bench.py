@@ -123,14 +123,14 @@ def bind_to_gpu_numa_node(torch, local_rank):
     return None
 
 
-def cpu_reference_measure(c2a, wl_full, sample_chains, variant, rounds, backend_gates=None):
+def cpu_reference_measure(workloads, wl_full, sample_chains, variant, rounds, backend_gates=None):
     """The reference's CPU path, restated (oracle, faithful data structures), single thread like the reference.
     emit: O(G*S) scans (src/compiler.rs:185-195, 219-226, 260-270) on a bounded prefix of the workload;
     back end: HashMap producer map + DFS + first-seen numbering + gather (src/compiler.rs:388-464)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import numpy as np
     import oracle_lib as orc
-    wl = c2a.workloads.mimc_chains(sample_chains, rounds=rounds, variant=variant)
+    wl = workloads.mimc_chains(sample_chains, rounds=rounds, variant=variant)
     oc = orc.OracleCompiler()
     t0 = time.perf_counter()
     oc.emit_events(wl.events)
@@ -149,6 +149,310 @@ def cpu_reference_measure(c2a, wl_full, sample_chains, variant, rounds, backend_
         res["backend_only_full_gates"] = int(g.shape[0])
         res["backend_only_gates_per_s"] = g.shape[0] / tb
     return res
+
+
+def load_workloads_without_native():
+    """workloads.py (numpy only) loaded under a stub package, so that the reference arm's process never maps libc2a.so
+    (importing the real package loads it)."""
+    import importlib.util
+    import types
+    pkg_dir = os.path.join(ROOT, "circom-2-arithc_b200")
+    stub = types.ModuleType("c2a_workloads_only")
+    stub.__path__ = [pkg_dir]
+    sys.modules["c2a_workloads_only"] = stub
+    mods = {}
+    for name in ("gate_types", "workloads"):
+        spec = importlib.util.spec_from_file_location(f"c2a_workloads_only.{name}", os.path.join(pkg_dir, name + ".py"))
+        m = importlib.util.module_from_spec(spec)
+        sys.modules[spec.name] = m
+        spec.loader.exec_module(m)
+        mods[name] = m
+    return mods["workloads"]
+
+
+# SURVEY.md 8d: algorithmic bytes per gate of the phases.  The exact-order sort this build runs (K2 + K5a-c) moves
+# deps 32 + scratch init 9 + sizes 8 + offsets scan 8 + roots 16 = 73 B/gate; Kahn K1-K4 (CSR) 104 B/gate.
+ALG_SORT_BYTES_PER_GATE = 73
+ALG_KAHN_BYTES_PER_GATE = 104
+SORT_PHASES = ("k_deps", "k_relax", "k_sizes", "k_roots", "k_tree_dfs")
+
+
+class StagedCircuit:
+    """One workload staged for the two measured forms: the packed stream in pinned host memory (e2e) and resident in HBM (value),
+    plus pinned / device result buffers sized by one untimed pass."""
+
+    def __init__(self, c2a, torch, ctx, dev, wl):
+        import numpy as np
+        from circom_2_arithc_b200._lib import EmitInfo, PackedEvents
+        self.c2a, self.torch, self.ctx, self.lib, self.h, self.wl = c2a, torch, ctx, c2a.lib, ctx.handle, wl
+        ev = np.ascontiguousarray(wl.events)
+        self.n_ev = int(ev.shape[0])
+        kinds, words, flags = c2a.pack_events(ev)
+        self.p_kinds = torch.from_numpy(kinds).pin_memory()
+        self.p_words = torch.from_numpy(words.view(np.int32)).pin_memory()
+        self.d_kinds, self.d_words = self.p_kinds.to(dev), self.p_words.to(dev)
+        nw = int(words.shape[0])
+        self.pk_host = PackedEvents(self.p_kinds.data_ptr(), self.p_words.data_ptr(), self.n_ev, nw, flags, 0)
+        self.pk_dev = PackedEvents(self.d_kinds.data_ptr(), self.d_words.data_ptr(), self.n_ev, nw, flags, 0)
+        self.stream_bytes = self.n_ev + 4 * nw
+        self.ins = np.array(sorted(wl.inputs), dtype=np.uint32)
+        self.outs = np.array(sorted(wl.outputs), dtype=np.uint32)
+        kk = ev[:, 0] & 0xFF
+        self.named = np.concatenate([self.ins, self.outs, ev[kk == 1, 1]]).astype(np.uint32)
+        self.info, self.bad, self.wc, self.err = EmitInfo(), C.c_uint64(0), C.c_uint32(0), C.c_uint64(0)
+        st = self.lib.c2a_emit_packed_resident(self.h, C.byref(self.pk_dev), C.byref(self.info), C.byref(self.bad))
+        if st != 0 or self.info.path != 1:
+            raise RuntimeError(f"{wl.name}: emit -> {st} path {self.info.path}: {ctx.last_error()}")
+        self.G, self.nb = int(self.info.n_gates), int(self.info.node_count) + 1
+        G, nb = self.G, self.nb
+        self.d_order = torch.empty(max(G, 1), dtype=torch.int32, device=dev)
+        self.d_wire = torch.empty(nb, dtype=torch.int32, device=dev)
+        self.d_new = torch.empty((max(G, 1), 4), dtype=torch.int32, device=dev)
+        self.p_new = torch.empty((max(G, 1), 4), dtype=torch.int32).pin_memory()
+        self.p_named = torch.from_numpy(self.named.view(np.int32)).pin_memory()
+        self.p_named_w = torch.empty(max(len(self.named), 1), dtype=torch.int32).pin_memory()
+
+    def step_resident(self):
+        """emit + build, packed stream resident in HBM, results stay in HBM"""
+        lib, h, vp = self.lib, self.h, C.c_void_p
+        st = lib.c2a_emit_packed_resident(h, C.byref(self.pk_dev), C.byref(self.info), C.byref(self.bad))
+        if st == 0:
+            st = lib.c2a_emitted_build_circuit_device(h, self.ins.ctypes.data_as(vp), len(self.ins), self.outs.ctypes.data_as(vp), len(self.outs),
+                                                      vp(self.d_order.data_ptr()), vp(self.d_wire.data_ptr()), vp(self.d_new.data_ptr()),
+                                                      C.byref(self.wc), C.byref(self.err))
+        if st != 0:
+            raise RuntimeError(f"{self.wl.name}: resident step -> {st}: {self.ctx.last_error()}")
+
+    def step_e2e(self):
+        """the same through host buffers: packed stream from pinned memory, renumbered gates + named wires into pinned memory"""
+        lib, h, vp = self.lib, self.h, C.c_void_p
+        st = lib.c2a_emit_packed_device(h, C.byref(self.pk_host), C.byref(self.info), C.byref(self.bad))
+        if st == 0:
+            st = lib.c2a_emitted_build_circuit(h, self.ins.ctypes.data_as(vp), len(self.ins), self.outs.ctypes.data_as(vp), len(self.outs), None, None,
+                                               vp(self.p_new.data_ptr()), C.byref(self.wc), C.byref(self.err))
+        if st == 0:
+            st = lib.c2a_emitted_signal_wires(h, vp(self.p_named.data_ptr()), len(self.named), vp(self.p_named_w.data_ptr()))
+        if st != 0:
+            raise RuntimeError(f"{self.wl.name}: e2e step -> {st}: {self.ctx.last_error()}")
+
+    def e2e_bytes(self):
+        return self.stream_bytes + 4 * (len(self.ins) + len(self.outs)) + 4 * len(self.named), 16 * self.G + 4 * len(self.named) + 4 * 32 * 3
+
+
+def time_on_stream(torch, stream, fn, steps, warmup, flush=None):
+    """CUDA events on `stream` around `steps` calls of fn (after `warmup` untimed ones).  flush: a callable run between the timed
+    calls OUTSIDE the event pairs (evicts the L2); then every call gets its own event pair and the mean is returned."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if flush is None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    tot = 0.0
+    for _ in range(steps):
+        flush()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        tot += e0.elapsed_time(e1)
+    return tot / steps
+
+
+def circuit_leg(c2a, torch, ctx, dev, stream, wl, steps, peak, flush, cpu_backend=True, orc=None):
+    """One BASELINE config as a sub-record: value (resident), value with the L2 flushed between steps, e2e (host buffers), the
+    exact-order sort's achieved HBM GB/s, and the CPU oracle's back end on the very same gate vector."""
+    import numpy as np
+    lib, h = c2a.lib, ctx.handle
+    sc = StagedCircuit(c2a, torch, ctx, dev, wl)
+    lib.c2a_set_timing(h, 0)
+    ms = time_on_stream(torch, stream, sc.step_resident, steps, 3)
+    ms_cold = time_on_stream(torch, stream, sc.step_resident, max(3, steps // 4), 1, flush=flush)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sc.step_e2e()
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    lib.c2a_set_timing(h, 1)
+    lib.c2a_set_timing_only(h, None)
+    l0 = ctx.kernel_launches()
+    sc.step_resident()
+    launches = ctx.kernel_launches() - l0
+    ph = ctx.phases()
+    sort_ms = sum(ph.get(k, 0.0) for k in SORT_PHASES)
+    h2d, d2h = sc.e2e_bytes()
+    rec = {"workload": wl.name, "gates": sc.G, "events": sc.n_ev, "node_bound": sc.nb, "value": sc.G / (ms * 1e-3), "unit": "gates/s", "ms_per_step": ms,
+           "value_l2_flushed": sc.G / (ms_cold * 1e-3), "ms_per_step_l2_flushed": ms_cold, "steps": steps, "gpu_launches_per_step": int(launches),
+           "e2e": {"value": sc.G / e2e_s, "unit": "gates/s", "s_per_step": e2e_s, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+           "topo_sort_ms": sort_ms, "topo_hbm_gbs": (ALG_SORT_BYTES_PER_GATE * sc.G / (sort_ms * 1e-3) / 1e9) if sort_ms > 0 else None,
+           "topo_frac_of_peak": (ALG_SORT_BYTES_PER_GATE * sc.G / (sort_ms * 1e-3) / 1e9 / peak) if sort_ms > 0 else None,
+           "l2": "circuit smaller than the 126 MB L2: `value` is L2-warm back-to-back steps, `value_l2_flushed` evicts the L2 (256 MB write) before every step"
+                 if sc.stream_bytes + 16 * sc.G < 100e6 else "inputs larger than L2; no flush needed"}
+    if cpu_backend and orc is not None:
+        sc.ctx._emit_info = {"n_gates": sc.G, "signal_bound": int(sc.info.signal_bound)}
+        gates, nos = ctx.emitted_fetch()
+        tb, st = orc.backend_time(gates, nos[sc.ins], nos[sc.outs], reps=3 if sc.G < 2_000_000 else 1)
+        assert st == 0
+        rec["cpu_backend_gates_per_s"] = sc.G / tb
+        rec["cpu_backend_note"] = "oracle back end (HashMap producer map + DFS + first-seen numbering + gather), 1 thread, same gate vector"
+        # parity on the spot: the GPU result of this very circuit against the oracle
+        st_, _e, o_order, _w, o_gates, o_wc = orc.backend_raw(gates, sc.nb, nos[sc.ins], nos[sc.outs])
+        ok = (st_ == 0 and np.array_equal(sc.d_order[:sc.G].cpu().numpy().astype(np.uint32), o_order)
+              and np.array_equal(sc.d_new[:sc.G].cpu().numpy().astype(np.uint32), o_gates) and o_wc == sc.wc.value)
+        rec["parity_vs_oracle"] = "ok" if ok else "MISMATCH"
+        assert ok, f"{wl.name}: GPU result differs from the oracle"
+    return rec, sc
+
+
+def backend_leg(c2a, torch, ctx, dev, stream, name, gates, nb, ins_nodes, outs_nodes, steps, peak, orc=None, oracle_reps=1):
+    """c2a_build_circuit_device on a caller's gate array resident in HBM (K1..K7): the back end alone."""
+    import numpy as np
+    lib, h, vp = c2a.lib, ctx.handle, C.c_void_p
+    G = int(gates.shape[0])
+    d_gates = torch.from_numpy(np.ascontiguousarray(gates).view(np.int32)).to(dev)
+    d_order = torch.empty(G, dtype=torch.int32, device=dev)
+    d_wire = torch.empty(nb, dtype=torch.int32, device=dev)
+    d_new = torch.empty((G, 4), dtype=torch.int32, device=dev)
+    wc, err = C.c_uint32(0), C.c_uint64(0)
+    ins_nodes, outs_nodes = np.ascontiguousarray(ins_nodes, dtype=np.uint32), np.ascontiguousarray(outs_nodes, dtype=np.uint32)
+
+    def step():
+        st = lib.c2a_build_circuit_device(h, vp(d_gates.data_ptr()), G, nb, ins_nodes.ctypes.data_as(vp), len(ins_nodes), outs_nodes.ctypes.data_as(vp),
+                                          len(outs_nodes), vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+        if st != 0:
+            raise RuntimeError(f"{name}: c2a_build_circuit_device -> {st}: {ctx.last_error()}")
+
+    lib.c2a_set_timing(h, 0)
+    ms = time_on_stream(torch, stream, step, steps, 2)
+    lib.c2a_set_timing(h, 1)
+    lib.c2a_set_timing_only(h, None)
+    step()
+    ph = ctx.phases()
+    sort_ms = sum(ph.get(k, 0.0) for k in SORT_PHASES) + ph.get("k_producer", 0.0)
+    rec = {"workload": name, "gates": G, "value": G / (ms * 1e-3), "unit": "gates/s", "ms_per_step": ms, "steps": steps,
+           "scope": "gate vector resident in HBM -> c2a_build_circuit_device (producer map, deps, exact DFS order, wire numbering, gather); results stay in HBM",
+           "relax_fallback_rounds": int(ph.get("n_relax_fallback_rounds", 0)),
+           "topo_sort_ms": sort_ms, "topo_hbm_gbs": ((ALG_SORT_BYTES_PER_GATE + 20) * G / (sort_ms * 1e-3) / 1e9) if sort_ms > 0 else None,
+           "phases_ms": {k: round(v, 4) for k, v in ph.items()}}
+    if rec["topo_hbm_gbs"]:
+        rec["topo_frac_of_peak"] = rec["topo_hbm_gbs"] / peak
+    if orc is not None:
+        tb, st = orc.backend_time(gates, ins_nodes, outs_nodes, reps=oracle_reps)
+        assert st == 0
+        rec["cpu_backend_gates_per_s"] = G / tb
+        rec["speedup_vs_cpu_backend"] = rec["value"] / rec["cpu_backend_gates_per_s"]
+    return rec, (d_order, d_new, wc)
+
+
+def kahn_leg(c2a, torch, ctx, dev, name, gates, nb, steps, peak):
+    """K1..K4 (producer map, deps, consumer CSR, asynchronous Kahn walk, counting sort by level) on a resident gate array:
+    SURVEY 8d's 104 B/gate against the measured copy peak."""
+    import numpy as np
+    lib, h, vp = c2a.lib, ctx.handle, C.c_void_p
+    G = int(gates.shape[0])
+    d_gates = torch.from_numpy(np.ascontiguousarray(gates).view(np.int32)).to(dev)
+    d_lo = torch.empty(G, dtype=torch.int32, device=dev)
+    cap = 1 << 20
+    d_off = torch.empty(cap + 2, dtype=torch.int32, device=dev)
+    nl, err = C.c_uint32(0), C.c_uint64(0)
+    best_call, best_kern, phases = 1e30, 1e30, {}
+    lib.c2a_set_timing(h, 1)
+    lib.c2a_set_timing_only(h, None)
+    for i in range(steps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        st = lib.c2a_topo_levels_device(h, vp(d_gates.data_ptr()), G, nb, vp(d_lo.data_ptr()), vp(d_off.data_ptr()), cap, C.byref(nl), C.byref(err))
+        dt = (time.perf_counter() - t0) * 1e3
+        if st != 0:
+            raise RuntimeError(f"{name}: c2a_topo_levels_device -> {st}: {ctx.last_error()}")
+        ph = ctx.phases()
+        kern = sum(v for k, v in ph.items() if k.startswith("k_") or k == "init")
+        if i and kern < best_kern:
+            best_kern, phases = kern, ph
+        if i:
+            best_call = min(best_call, dt)
+    ab = ALG_KAHN_BYTES_PER_GATE * G
+    return {"workload": name, "gates": G, "levels": int(nl.value), "ms_kernels": best_kern, "ms_call": best_call, "alg_bytes": ab,
+            "achieved_gbs": ab / (best_kern * 1e-3) / 1e9, "frac": ab / (best_kern * 1e-3) / 1e9 / peak,
+            "latency_floor_note": "%d levels: a chain of %d dependent hops bounds the walk from below (~1 us per DRAM hop)" % (nl.value, nl.value),
+            "phases_ms": {k: round(v, 4) for k, v in phases.items()}}
+
+
+
+def multi_gpu_parity(c2a, torch, dist, ctx, dev, stream, rank, world, variant, rounds):
+    """Driver-visible N>1 parity, run before the timed region on every rank:
+      (a) sharding.build_circuit_sharded of ONE circuit (plan_shards cuts, per-shard build, one all-gather of counts, rebase) against the
+          single-rank build of the same gate vector and against the oracle;
+      (b) the bench's own weak-scaling path (every rank emits and builds its own component subtree, all-gather of counts, offsets applied
+          inside the gather kernel) against the oracle's build of the concatenated circuit (inputs of all ranks, intermediates, outputs).
+    Returns "ok" or raises."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as orc
+    lib, h, vp = c2a.lib, ctx.handle, C.c_void_p
+    ok = True
+    # ---- (a) one circuit, sharded
+    cases = [c2a.workloads.mimc_chains(50 * world, rounds=rounds, variant=variant)]
+    if world == 2:
+        cases.append(c2a.workloads.keccak_shaped(instances=2, rounds=3))
+    for wl in cases:
+        comp = c2a.Compiler(context=ctx)
+        comp.emit_events(wl.events)
+        g, nb = comp.gate_array(), comp.node_count + 1
+        ins = comp.signal_nodes(np.array(sorted(wl.inputs), dtype=np.uint32))
+        outs = comp.signal_nodes(np.array(sorted(wl.outputs), dtype=np.uint32))
+        order, wire, ng, wc, plan = c2a.sharding.build_circuit_sharded(g, nb, ins, outs, ctx=ctx)
+        o1, w1, g1, wc1 = ctx.build_circuit(g, nb, ins, outs)
+        st, _, o_order, o_wire, o_gates, o_wc = orc.backend_raw(g, nb, ins, outs)
+        ok = ok and st == 0 and len(plan) == world and wc == wc1 == o_wc
+        ok = ok and np.array_equal(order, o1) and np.array_equal(order, o_order) and np.array_equal(ng, g1) and np.array_equal(ng, o_gates)
+        ok = ok and np.array_equal(wire, w1) and np.array_equal(wire, o_wire)
+        del comp
+    # ---- (b) the weak-scaling path of this bench on a small workload
+    sc = StagedCircuit(c2a, torch, ctx, dev, c2a.workloads.mimc_chains(40 + rank, rounds=rounds, variant=variant))   # ragged: a different size per rank
+    st = lib.c2a_emit_packed_resident(h, C.byref(sc.pk_dev), C.byref(sc.info), C.byref(sc.bad))
+    assert st == 0 and sc.info.path == 1
+    sc.ctx._emit_info = {"n_gates": sc.G, "signal_bound": int(sc.info.signal_bound)}
+    gates_local, nos = ctx.emitted_fetch()
+    st = lib.c2a_emitted_build_circuit_device(h, sc.ins.ctypes.data_as(vp), len(sc.ins), sc.outs.ctypes.data_as(vp), len(sc.outs), vp(sc.d_order.data_ptr()),
+                                              vp(sc.d_wire.data_ptr()), None, C.byref(sc.wc), C.byref(sc.err))
+    assert st == 0, ctx.last_error()
+    h_counts = torch.tensor([len(sc.ins), sc.wc.value - len(sc.ins) - len(sc.outs), len(sc.outs), sc.G], dtype=torch.int64).pin_memory()
+    d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    d_all = torch.zeros(4 * world, dtype=torch.int64, device=dev)
+    with torch.cuda.stream(stream):
+        d_counts.copy_(h_counts, non_blocking=True)
+        dist.all_gather_into_tensor(d_all, d_counts)
+    st = lib.c2a_emitted_gather_device(h, vp(sc.d_order.data_ptr()), vp(sc.d_new.data_ptr()), vp(d_all.data_ptr()), rank, world)
+    assert st == 0, ctx.last_error()
+    stream.synchronize()
+    mine = {"gates": gates_local, "nb": sc.nb, "ins": nos[sc.ins], "outs": nos[sc.outs], "new": sc.d_new[:sc.G].cpu().numpy().astype(np.uint32),
+            "order": sc.d_order[:sc.G].cpu().numpy().astype(np.uint32)}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    if rank == 0:
+        # concatenated circuit: rank r's node ids shifted by the node bounds before it; inputs / outputs listed rank by rank
+        node_base = np.cumsum([0] + [p_["nb"] for p_ in parts])
+        gg = np.concatenate([p_["gates"] + np.array([0, b, b, b], dtype=np.uint32) for p_, b in zip(parts, node_base[:-1])])
+        gi = np.concatenate([p_["ins"] + np.uint32(b) for p_, b in zip(parts, node_base[:-1])])
+        go = np.concatenate([p_["outs"] + np.uint32(b) for p_, b in zip(parts, node_base[:-1])])
+        st, _, o_order, _w, o_gates, _wc = orc.backend_raw(gg, int(node_base[-1]), gi, go)
+        ok = ok and st == 0 and np.array_equal(np.concatenate([p_["order"] for p_ in parts]), o_order)
+        ok = ok and np.array_equal(np.concatenate([p_["new"] for p_ in parts]), o_gates)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise RuntimeError("multi-GPU parity check failed: the stitched N-rank result differs from the single-rank / oracle result")
+    return "ok"
+
 
 
 def main():
@@ -170,7 +474,10 @@ def main():
     ap.add_argument("--no-from-source", action="store_true", help="skip the .circom-text-to-circuit leg")
     ap.add_argument("--source-chains", type=int, default=0, help="MiMC chains of the from_source leg (default: --chains, the headline workload)")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
+    ap.add_argument("--legs", default="all", help="comma list of the extra sub-records (N = 1): configs,variants,kahn,sweeps,same_config  (all | none)")
+    ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the small-config sub-records")
     args = ap.parse_args()
+    legs = set("configs,variants,kahn,sweeps,same_config".split(",")) if args.legs == "all" else set(x for x in args.legs.split(",") if x and x != "none")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +485,6 @@ def main():
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
 
-    from c2a_loader import c2a
     import numpy as np
 
     workload_name = f"mimc_chains W={args.chains} x {args.rounds} rounds x 6 gates, variant={args.variant}"
@@ -188,11 +494,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # the reference arm never imports the product package: libc2a.so is not mapped into this process (workloads.py is
+        # numpy-only and is loaded on its own; the oracle is oracle/libc2a_oracle.so through tests/oracle_lib.py)
+        workloads = load_workloads_without_native()
         ncores = os.cpu_count()
         vals = []
         last = None
         for i in range(W + K):
-            r = cpu_reference_measure(c2a, None, args.sample_chains, args.variant, args.rounds)
+            r = cpu_reference_measure(workloads, None, args.sample_chains, args.variant, args.rounds)
             if i >= W:
                 vals.append(r["gates_per_s"])
             last = r
@@ -202,8 +511,10 @@ def main():
         v = float(np.mean(vals))
         sample = (f"first {args.sample_chains} chains ({last['sample_gates']} gates) of the workload: faithful O(G*S) emit "
                   f"{last['emit_s']:.2f}s + HashMap/DFS back end {last['backend_s']*1e3:.1f}ms per step; the reference is single-threaded")
+        mapped = sorted({ln.split()[-1] for ln in open("/proc/self/maps") if ln.rstrip().endswith(".so") and ROOT in ln})
+        assert not any(m.endswith("libc2a.so") for m in mapped), "the reference arm must not map the product library"
         print(json.dumps({
-            "impl": "reference", "metric": metric, "value": v, "unit": "gates/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": W,
+            "impl": "reference", "repo_libs_mapped": [os.path.relpath(m, ROOT) for m in mapped], "metric": metric, "value": v, "unit": "gates/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": W,
             "ms_per_step": 1e3 * last["sample_gates"] / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32", "data": "synthetic", "config": {"workload": workload_name, "sample": sample},
             "cpu_baseline": {"value": v, "unit": "gates/s", "cores": 1, "kind": "port", "sample": sample, "host_cores": ncores,
@@ -212,6 +523,7 @@ def main():
         return 0
 
     # ------------------------------------------------------------------------------------------------
+    from c2a_loader import c2a
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -326,6 +638,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    mgp = multi_gpu_parity(c2a, torch, dist, ctx, dev, stream, rank, world, args.variant, args.rounds) if world > 1 else None
+    if world > 1:   # the parity legs used the handle: put the headline circuit back
+        st = emit_resident()
+        assert st == 0 and info.path == 1 and int(info.n_gates) == G
 
     # ---- value: HBM-resident events -> emit -> build, CUDA events on the handle's stream.
     # Per-kernel CUDA events are not free (a pair costs ~4 us of stream time; ~35 phases per step = 0.3 ms at 10 M gates), so:
@@ -590,18 +907,85 @@ def main():
                                "expanded in HBM) + c2a_emitted_build_circuit (gates into pinned host memory) + c2a_emitted_signal_wires = device_s" % Ws}
         del dc
 
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- roofline of the dominant kernel (CUDA-event time of the phase, measured live above)
+    # ---- extra sub-records (N = 1): the other BASELINE configs, the stress variants, the Kahn levels, the sweeps, and the repo arm on
+    #      the reference arm's own sample.  Each is measured like the headline (CUDA events on the handle's stream, warm-up first).
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    extra = {}
+    if world == 1 and legs:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as orc
+        flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def flush():
+            flush_buf.fill_(1)
+
+        Kx = max(3, args.extra_steps)
+        t_extra = time.perf_counter()
+        if "same_config" in legs:
+            rec, _sc = circuit_leg(c2a, torch, ctx, dev, stream, c2a.workloads.mimc_chains(args.sample_chains, rounds=args.rounds, variant=args.variant),
+                                   Kx, peak, flush, cpu_backend=True, orc=orc)
+            rec["note"] = "the repo arm on exactly the bounded sample the reference arm / cpu_baseline times (same stream, same result arrays)"
+            extra["same_config"] = rec
+            del _sc
+        if "configs" in legs:
+            cfgs = {}
+            for key, wlx in (("poseidon_shaped", c2a.workloads.poseidon_shaped()), ("sha256_shaped", c2a.workloads.sha256_shaped()),
+                             ("keccak_shaped_x1", c2a.workloads.keccak_shaped(1)), ("keccak_shaped_x2", c2a.workloads.keccak_shaped(2))):
+                cfgs[key], _sc = circuit_leg(c2a, torch, ctx, dev, stream, wlx, Kx, peak, flush, cpu_backend=True, orc=orc)
+                del _sc
+            extra["configs"] = cfgs
+        gates_late = nos_late = None
+        if legs & {"variants", "kahn", "sweeps"}:
+            st = emit_resident()
+            assert st == 0 and info.path == 1
+            ctx._emit_info = {"n_gates": G, "signal_bound": int(info.signal_bound)}
+            gates_late, nos_late = ctx.emitted_fetch()
+        if "variants" in legs:
+            var = {}
+            perm = np.random.RandomState(1).permutation(G)
+            shuffled = np.ascontiguousarray(gates_late[perm])
+            var["shuffled_10M"], _keep = backend_leg(c2a, torch, ctx, dev, stream, f"{workload_name}, gate vector shuffled (seed 1)", shuffled, nb,
+                                                    nos_late[in_ids], nos_late[out_ids], max(2, K // 2), peak, orc=orc, oracle_reps=1)
+            del _keep, shuffled, perm
+            wl_in = c2a.workloads.mimc_chains(args.chains, rounds=args.rounds, variant="inorder")
+            var["inorder_10M"], _sc = circuit_leg(c2a, torch, ctx, dev, stream, wl_in, max(3, K), peak, flush, cpu_backend=True, orc=orc)
+            del _sc, wl_in
+            extra["variants"] = var
+        if "kahn" in legs:
+            kh = {"547_levels": kahn_leg(c2a, torch, ctx, dev, f"{workload_name} (gate vector of the headline circuit)", gates_late, nb, 3, peak)}
+            w7 = max(1, G // 7)
+            wl7 = c2a.workloads.mimc_chains(w7, rounds=1, variant="late")
+            k7, w7w, f7 = c2a.pack_events(np.ascontiguousarray(wl7.events))
+            i7 = ctx.emit_packed(k7, w7w, f7)
+            g7, _ = ctx.emitted_fetch(want_nodes=False)
+            kh["7_levels"] = kahn_leg(c2a, torch, ctx, dev, f"mimc_chains W={w7} x 1 round, variant=late", g7, int(i7["node_count"]) + 1, 3, peak)
+            del wl7, k7, w7w, g7
+            extra["kahn"] = kh
+        if "sweeps" in legs:
+            kinds_all_ = wl.events[:, 0] & 0xFF
+            c_sig, c_val = wl.events[kinds_all_ == 1, 1], wl.events[kinds_all_ == 1, 2]
+            t0 = time.perf_counter()
+            cm, _cv, dm = ctx.sweep_masks(gates_late, nb, nos_late[c_sig], c_val, nos_late[out_ids])
+            dt_sw = time.perf_counter() - t0
+            ph = ctx.phases()
+            extra["sweeps"] = {"workload": workload_name, "gates": G, "fold_ms": ph.get("k_fold_level"), "dead_ms": ph.get("k_live_level"),
+                               "kahn_levels_ms": sum(v for k, v in ph.items() if k.startswith("k_kahn") or k in ("k_producer", "k_deps", "k_level_sort")),
+                               "call_s_incl_copies": dt_sw, "const_gates": int(cm.sum()), "dead_gates": int(dm.sum()),
+                               "note": "c2a_sweep_masks (K8 constant-fold mask, K9 dead-gate mask) over the Kahn levels; host buffers, copies inside call_s"}
+        extra["extras_wall_s"] = time.perf_counter() - t_extra
+        del gates_late, nos_late
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (CUDA-event time of the phase, measured live above)
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     kern = {k: v / K for k, v in phase_acc.items() if k.split(":")[-1].startswith("k_")}
     dom = dom_phase
@@ -642,6 +1026,8 @@ def main():
                    "e2e_scope": "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
                                 "(new_gates D2H inside) -> c2a_emitted_signal_wires (named signals H2D, their wires D2H); e2e_all_arrays also copies order and the whole wire map",
                    "numa_node": numa,
+                   "oracle_pin": "oracle pinned by the reference's own unit / integration vectors (tests/test_oracle_goldens.py); topological_sort has NO upstream "
+                                 "test, so the DFS order is pinned by a line-by-line restatement of src/topological_sort.rs:3-50 only",
                    "parallelism": "1 GPU" if world == 1 else f"{world} GPUs, one independent component subtree (W chains) per rank, NCCL all-gather of wire counts, global offsets applied inside the gate gather"},
         "roofline": roof,
         "e2e": {"value": e2e_value, "unit": "gates/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "steps": Ke, "s_per_step": dt / Ke,
@@ -653,6 +1039,10 @@ def main():
         "gpu_launches": int(launches),
         "clocks": summarize_clocks(clk_lines),
     }
+    for k_, v_ in extra.items():
+        out[k_] = v_
+    if mgp is not None:
+        out["multi_gpu_parity"] = mgp
     if pipe is not None:
         if "value" in pipe:
             pipe["h2d_bytes_per_step"], pipe["d2h_bytes_per_step"] = int(h2d), int(d2h)
@@ -663,7 +1053,7 @@ def main():
         out["e2e_host_emitter"] = {"value": host_emit["gates_per_s"], "unit": "gates/s", "emit_s": host_emit["emit_s"], "build_s": host_emit["build_s"],
                                    "note": "same circuit through the host union-find emitter (c2a_emit_events + c2a_build_circuit), pageable buffers, 1 step"}
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_measure(c2a, None, args.sample_chains, args.variant, args.rounds,
+        r = cpu_reference_measure(c2a.workloads, None, args.sample_chains, args.variant, args.rounds,
                                   backend_gates=(gates_h, ins_n, outs_n) if gates_h is not None else None)
         out["cpu_baseline"] = {
             "value": r["gates_per_s"], "unit": "gates/s", "cores": 1, "kind": "port", "host_cores": os.cpu_count(),
@@ -672,6 +1062,12 @@ def main():
             "emit_s": r["emit_s"], "backend_s": r["backend_s"]}
         if "backend_only_gates_per_s" in r:
             out["cpu_baseline"]["backend_only_gates_per_s"] = r["backend_only_gates_per_s"]
+        if "same_config" in out:   # one like-for-like ratio: both arms on the identical bounded sample
+            sc_ = out["same_config"]
+            sc_["reference_value"] = r["gates_per_s"]
+            sc_["same_config"] = True
+            sc_["ratio_value_vs_reference"] = sc_["value"] / r["gates_per_s"]
+            sc_["ratio_e2e_vs_reference"] = sc_["e2e"]["value"] / r["gates_per_s"]
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

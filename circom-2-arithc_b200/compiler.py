@@ -24,33 +24,7 @@ from ._lib import lib, C2AError, CircuitError, Status, EmitInfo, PackedEvents
 NONE = 0xFFFFFFFF
 EVENT_DTYPE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
 GATE_DTYPE = np.dtype([("op", "<u4"), ("lh", "<u4"), ("rh", "<u4"), ("out", "<u4")])
-EV_SIGNAL, EV_SIGNAL_CONST, EV_GATE, EV_CONNECT = 0, 1, 2, 3
-
-
-class AGateType(enum.IntEnum):
-    AAdd = 0
-    ADiv = 1
-    AEq = 2
-    AGEq = 3
-    AGt = 4
-    ALEq = 5
-    ALt = 6
-    AMul = 7
-    ANeq = 8
-    ASub = 9
-    AXor = 10
-    APow = 11
-    AIntDiv = 12
-    AMod = 13
-    AShiftL = 14
-    AShiftR = 15
-    ABoolOr = 16
-    ABoolAnd = 17
-    ABitOr = 18
-    ABitAnd = 19
-
-    def __str__(self):  # strum Display: the Bristol op token
-        return self.name
+from .gate_types import AGateType, EV_SIGNAL, EV_SIGNAL_CONST, EV_GATE, EV_CONNECT  # noqa: E402,F401
 
 
 _CIRCUIT_STATUSES = {Status.CYCLIC_DEPENDENCY, Status.INCONSISTENCY, Status.SIGNAL_ALREADY_DECLARED,

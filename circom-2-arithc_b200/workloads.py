@@ -16,7 +16,7 @@ from typing import Callable, Dict, List, Optional
 
 import numpy as np
 
-from .compiler import AGateType as G, EV_CONNECT, EV_GATE, EV_SIGNAL, EV_SIGNAL_CONST
+from .gate_types import AGateType as G, EV_CONNECT, EV_GATE, EV_SIGNAL, EV_SIGNAL_CONST
 
 
 @dataclass

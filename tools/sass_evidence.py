@@ -12,7 +12,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "circom-2-arithc_b200", "libc2a.so")
-MNEMONICS = ["UBLKCP", "UTMALDG", "SYNCS", "LDG.E.128", "STG.E.128", "RED.E", "ATOMG", "LDGSTS", "CCTL", "MEMBAR", "BAR.SYNC", "UCGABAR"]
+MNEMONICS = ["UBLKCP", "UTMALDG", "SYNCS", "LDG.128", "STG.128", "RED", "ATOMG", "LDGSTS", "CCTL", "MEMBAR", "BAR.SYNC", "UCGABAR"]
+PATTERNS = {"LDG.128": r"LDG\.E(\.NA)?\.128", "STG.128": r"STG\.E(\.NA)?\.128", "RED": r"\bRED\.E", "ATOMG": r"\bATOMG\."}
 
 
 def main():
@@ -30,7 +31,7 @@ def main():
         if re.search(r"/\*[0-9a-f]{4}\*/", ln):
             ninstr[cur] += 1
         for mn in MNEMONICS:
-            if mn in ln:
+            if re.search(PATTERNS.get(mn, re.escape(mn)), ln):
                 cnt[cur][mn] += 1
     demangle = subprocess.run(["c++filt"], input="\n".join(ninstr), capture_output=True, text=True).stdout.splitlines()
     names = dict(zip(ninstr, demangle))
