@@ -1,0 +1,824 @@
+// c2a_fused.cuh — emit + build of a SMALL circuit in ONE cooperative kernel (include/c2a.h: c2a_compile_packed*).
+//
+// Below ~1 M gates the multi-kernel pipeline (c2a_emit.cuh + c2a_device.cu: ~55 launches, 3 synchronisations) is bound by the
+// host's enqueue rate: 0.27 ms per circuit whether it has 1 413 gates (BASELINE config 2) or 150 K (config 4).  Here the same
+// phases run inside one persistent kernel, one CTA per SM (or fewer for tiny streams), separated by a grid barrier
+// (one RED + an acquire poll, ~1 us) instead of a kernel boundary; data-dependent loops (Boruvka rounds, relaxation rounds) iterate on
+// device-resident counters, so deep forward-edge cones need no host round trip either.  Everything is carved by upper bounds known
+// before anything is counted (dense packed stream: G <= n_words/3, C <= n_words/2, S <= n - n_words/3), so the host enqueues
+// copy-in, one memset, the kernel and the copy-out and synchronises ONCE.
+//
+// Semantics are exactly those of c2a_emit_packed_* followed by c2a_emitted_build_circuit* (src/compiler.rs:139-278, 321-464;
+// src/topological_sort.rs:3-50): same node ids, same gate vector, same DFS order, same wire ids.  Streams on which the reference
+// errors (or that the device emitter declines) are detected with the same flags and handed to the multi-kernel path, which
+// replays them exactly; the fused kernel only ever commits results for valid streams.
+//
+// Phases (B = grid barrier):
+//   F0  init scratch + per-tile kind counts                                   B
+//   F1  tile-count scan (every CTA, in shared memory), rank + scatter events  B     compiler.rs:139-209
+//   F2  Boruvka pick (round 1) + I/O list positions per signal                B     compiler.rs:213-278
+//   F3  hook (round 1)                                                        B
+//   F4  { pick B hook B } while live edges remain
+//   F5  rank prefix of the effective-connection bitmap + class ids            B     compiler.rs:257
+//   F6  node_of_signal, merge screens, I/O nodes tagged in wire[]             B     compiler.rs:157, 239-245, 392-395, 446-449
+//   F7  gates -> node ids, producer map                                       B     compiler.rs:401-406
+//   F8  deps, forward-edge seeds                                              B     compiler.rs:408-421
+//   F9  (only if some dependency points forward) relax seed B { round B }* sizes B offsets (look-back) B roots B tree DFS B
+//   F10 first appearances B bitmap marks B rank prefix (look-back) B wire ids B gather                compiler.rs:427-464
+#pragma once
+
+namespace c2a {
+
+constexpr int kFusedBlock = 1024;
+constexpr uint32_t kFusedMaxTiles = 4096;                 // 4 M events: the tile-count scan lives in shared memory
+constexpr uint32_t kInBase = 0x7FFFFFFEu;                 // wire[] tag of input list position i:  kInBase - i   (> kOutBase)
+constexpr uint32_t kOutBase = 0x3FFFFFFFu;                // wire[] tag of output list position j: kOutBase - j  (outputs override inputs)
+constexpr uint32_t kOutFloor = 0x20000000u;
+// scalars of the fused kernel
+enum { FS_G = 0, FS_C, FS_S, FS_EFLAGS, FS_NEFF, FS_ROUNDS, FS_BFLAGS, FS_SEEDN, FS_HEAVYN, FS_NMID, FS_ERR_LO = 10, FS_ERR_HI = 11, FS_DONE = 12,
+       FS_RELAX_ROUNDS = 13, FS_QN = 16 /* 4 rotating queue counters */, FS_MSF = 20 /* 4 rotating: cand / cur counters */, FS_COUNT = 32 };
+
+struct FusedParams {
+  const uint8_t* kinds;
+  const uint32_t* words;
+  uint32_t n, n_words, tiles;
+  const uint32_t* io_sigs;  // n_in input signal ids, then n_out output signal ids (device)
+  uint32_t n_in, n_out;
+  uint32_t G_ub, C_ub, S_ub, NB_ub;
+  // emit scratch
+  uint32_t *tile_g, *tile_c;
+  uint2* sig_meta;
+  uint4* egates;
+  uint2* conn;
+  uint32_t* conn_sb;
+  uint8_t* outmark;
+  uint32_t *parent, *best, *nidf, *eff, *effp, *cur;
+  uint4* cand;
+  uint32_t *in_idx1, *out_idx1;
+  // resident results of the emit
+  uint4* gates;
+  uint32_t* nos;
+  uint32_t* prod1;
+  // build scratch
+  uint2* dep;
+  uint32_t *r, *size_off;
+  uint8_t* state;
+  uint32_t *inq, *q0, *q1, *heavy, *bitmap, *bitmap_pre;
+  unsigned long long* agg;  // look-back aggregates: 2 scans x gridDim
+  // results of the build
+  uint32_t* order;       // never null (internal scratch when the caller does not want it)
+  uint32_t* wire;        // NB_ub entries
+  uint4* new_gates;      // may be null
+  uint32_t* sc;          // FS_COUNT scalars, zeroed (ERR = ~0) before the launch
+  unsigned int* bar;     // grid barrier counter, zeroed before the launch
+};
+
+// ---- memory access helpers.  Arrays written by other CTAs in an earlier phase are read through L2 (ld.cg): the barrier's fence
+// invalidates the L1, this makes the phases independent of it.
+template <typename T>
+__device__ __forceinline__ T ldg2(const T* p) { return __ldcg(p); }
+
+struct FusedCtx {
+  unsigned int epoch;  // thread 0 only
+};
+
+__device__ __forceinline__ void grid_bar(const FusedParams& P, FusedCtx& cx) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cx.epoch += gridDim.x;
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar) : "memory");
+    unsigned int v;
+    uint32_t spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.bar) : "memory");
+      if (++spins > (1u << 26)) __trap();  // a CTA never arrived: fail loudly instead of hanging
+    } while (v < cx.epoch);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+#define FUSED_FOR(i, n) for (uint32_t i = blockIdx.x * kFusedBlock + threadIdx.x; i < (n); i += gridDim.x * kFusedBlock)
+
+// block-wide exclusive scan of one value per thread (kFusedBlock threads); returns the exclusive prefix, *total = block sum
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp /* 33 u32 */, uint32_t* total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = warp_incl_scan(v, lane);
+  __syncthreads();  // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = s_warp[lane];
+    uint32_t wi = warp_incl_scan(w, lane);
+    s_warp[lane] = wi - w;
+    if (lane == 31) s_warp[32] = wi;
+  }
+  __syncthreads();
+  if (total) *total = s_warp[32];
+  return s_warp[warp] + incl - v;
+}
+
+// Grid-wide exclusive scan without a grid barrier: CTA b owns the contiguous chunk b of the sequence, publishes its aggregate
+// (tagged with `tag`, so the slots need no reset between scans) and sums the aggregates of the CTAs before it (all co-resident:
+// cooperative launch).  f(i) = the i-th value.  Writes dst[i] = exclusive prefix; returns the grid total to every thread.
+template <typename F>
+__device__ __forceinline__ uint32_t grid_scan(uint32_t n, F f, uint32_t* dst, unsigned long long* agg, uint32_t tag, uint32_t* s_warp) {
+  __shared__ uint32_t s_pre, s_tot;
+  const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
+  const uint32_t lo = min(n, blockIdx.x * per), hi = min(n, lo + per);
+  // local sum
+  uint32_t sum = 0;
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += kFusedBlock) sum += f(i);
+  uint32_t tot = 0;
+  block_excl_scan(sum, s_warp, &tot);
+  if (threadIdx.x == 0) st_volatile_u64(agg + blockIdx.x, ((unsigned long long)tag << 32) | tot);
+  // prefix over the predecessors' aggregates (warp 0), grand total over all (every CTA needs it)
+  if (threadIdx.x < 32) {
+    uint32_t pre = 0, all = 0, spins = 0;
+    for (uint32_t b = threadIdx.x; b < gridDim.x; b += 32) {
+      unsigned long long v;
+      while ((uint32_t)((v = ld_volatile_u64(agg + b)) >> 32) != tag)
+        if (++spins > (1u << 26)) __trap();
+      all += (uint32_t)v;
+      if (b < blockIdx.x) pre += (uint32_t)v;
+    }
+    pre = warp_sum(pre);
+    all = warp_sum(all);
+    if (threadIdx.x == 0) { s_pre = pre; s_tot = all; }
+  }
+  __syncthreads();
+  // local exclusive scan, kFusedBlock elements per round
+  uint32_t carry = s_pre;
+  for (uint32_t base = lo; base < hi; base += kFusedBlock) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < hi ? f(i) : 0u, t = 0;
+    uint32_t ex = block_excl_scan(v, s_warp, &t);
+    if (i < hi) dst[i] = carry + ex;
+    carry += t;
+  }
+  return s_tot;
+}
+
+__device__ __forceinline__ uint32_t fused_find(uint32_t* parent, uint32_t x) {
+  uint32_t r = x, p;
+  while ((p = ldg2(parent + r)) != r) r = p;
+  while (x != r) { p = ldg2(parent + x); if (p != r) parent[x] = r; x = p; }
+  return r;
+}
+__device__ __forceinline__ void fused_red_min(uint32_t* p, uint32_t v) {
+  if (ldg2(p) > v) atomicMin(p, v);
+}
+
+// K5a inside the fused kernel (same protocol as relax_from / enqueue in c2a_device.cu; no __restrict__: dep[] and r[] were written
+// earlier in this very kernel)
+__device__ __forceinline__ void fused_enqueue(uint32_t x, uint32_t* inq, uint32_t* q, uint32_t* qn) {
+  uint32_t bit = 1u << (x & 31);
+  __threadfence();
+  uint32_t old = atomicOr(inq + (x >> 5), bit);
+  if (!(old & bit)) q[atomicAdd(qn, 1u)] = x;
+}
+__device__ __forceinline__ void fused_relax_from(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn) {
+  while (cur != kNone) {
+    uint2 d = ldg2(dep + cur);
+    uint32_t nxt = kNone;
+    if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
+      if (val < atomicMin(r + d.y, val)) fused_enqueue(d.y, inq, q, qn);
+    }
+    if (d.x != kNone && val < __ldcg(r + d.x)) {
+      if (val < atomicMin(r + d.x, val)) nxt = d.x;
+    }
+    cur = nxt;
+  }
+}
+
+__global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedParams P) {
+  __shared__ uint32_t s_tg[kFusedMaxTiles], s_tc[kFusedMaxTiles];  // exclusive tile prefixes (gates, connections)
+  __shared__ uint32_t s_warp[33], s_wg[33], s_wc[33];
+  FusedCtx cx;
+  cx.epoch = 0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt = (1u << lane) - 1u;
+  uint32_t* sc = P.sc;
+  const uint32_t n = P.n;
+
+  // ================= F0: init + per-tile counts (one warp per 1024-event tile) =================
+  FUSED_FOR(i, P.S_ub) { P.parent[i] = i; P.best[i] = 0xFFFFFFFFu; P.nidf[i] = 0; P.outmark[i] = 0; P.in_idx1[i] = 0; P.out_idx1[i] = 0; }
+  FUSED_FOR(i, P.C_ub / 32 + 4) P.eff[i] = 0;
+  FUSED_FOR(i, P.NB_ub) { P.prod1[i] = 0; P.wire[i] = kNone; }
+  FUSED_FOR(i, P.G_ub + 1) { P.size_off[i] = 0; if (i < P.G_ub) { P.r[i] = i; P.state[i] = 0; } }
+  FUSED_FOR(i, (P.G_ub + 31) / 32 + 1) P.inq[i] = 0;
+  FUSED_FOR(i, (3 * P.G_ub + 31) / 32 + 4) P.bitmap[i] = 0;
+  {
+    uint32_t f = 0;
+    const uint32_t nwarps = gridDim.x * (kFusedBlock / 32);
+    for (uint32_t tile = blockIdx.x * (kFusedBlock / 32) + warp; tile < P.tiles; tile += nwarps) {
+      const uint32_t tbase = tile * kEvTile;
+      uint32_t g = 0, c = 0;
+#pragma unroll 4
+      for (int j = 0; j < 32; ++j) {
+        uint32_t i = tbase + j * 32 + lane;
+        if (i < n) {
+          uint32_t kb = P.kinds[i], kind = kb & 3u, op = kb >> 2;
+          if (kind == C2A_EV_GATE) { ++g; if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
+          else { if (kind == C2A_EV_CONNECT) ++c; if (op) f |= EF_BAD_KIND; }
+        }
+      }
+      g = warp_sum(g);
+      c = warp_sum(c);
+      if (lane == 0) { P.tile_g[tile] = g; P.tile_c[tile] = c; }
+    }
+    f = warp_or(f);
+    if (lane == 0 && f) atomicOr(sc + FS_EFLAGS, f);
+  }
+  grid_bar(P, cx);
+
+  // ================= F1: tile-count scan in shared memory (every CTA), then rank + scatter =================
+  uint32_t G, C, S;
+  {
+    constexpr uint32_t per = kFusedMaxTiles / kFusedBlock;  // 4 tiles per thread
+    uint32_t lg[per], lc[per], sg = 0, scn = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < per; ++j) {
+      uint32_t t = threadIdx.x * per + j;
+      lg[j] = t < P.tiles ? ldg2(P.tile_g + t) : 0u;
+      lc[j] = t < P.tiles ? ldg2(P.tile_c + t) : 0u;
+      sg += lg[j];
+      scn += lc[j];
+    }
+    uint32_t totg = 0, totc = 0;
+    uint32_t eg = block_excl_scan(sg, s_warp, &totg);
+    uint32_t ec = block_excl_scan(scn, s_warp, &totc);
+#pragma unroll
+    for (uint32_t j = 0; j < per; ++j) {
+      uint32_t t = threadIdx.x * per + j;
+      s_tg[t] = eg; s_tc[t] = ec;
+      eg += lg[j]; ec += lc[j];
+    }
+    __syncthreads();
+    G = totg; C = totc; S = n - G - C;
+  }
+  // the counts decide everything downstream: every CTA derives the same verdict from the same numbers
+  const bool words_ok = (unsigned long long)P.n_words == 3ull * G + 2ull * C;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[FS_G] = G; sc[FS_C] = C; sc[FS_S] = S;
+    if (!words_ok) atomicOr(sc + FS_EFLAGS, (uint32_t)EF_CAP);  // n_words does not match the kinds: the host reports it
+  }
+  if (!words_ok || (ldg2(sc + FS_EFLAGS) & (EF_BAD_KIND | EF_BAD_OP))) return;  // uniform: flags were complete at the barrier
+  {
+    uint32_t f = 0;
+    for (uint32_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+      const uint32_t tbase = tile * kEvTile, k = threadIdx.x, i = tbase + k;
+      const uint32_t kb = i < n ? (uint32_t)P.kinds[i] : 0x100u;
+      const bool is_g = kb < 0x100u && (kb & 3u) == C2A_EV_GATE, is_c = kb < 0x100u && (kb & 3u) == C2A_EV_CONNECT;
+      const uint32_t gm = __ballot_sync(0xFFFFFFFFu, is_g), cm = __ballot_sync(0xFFFFFFFFu, is_c);
+      __syncthreads();  // s_wg / s_wc of the previous tile
+      if (lane == 0) { s_wg[warp] = __popc(gm); s_wc[warp] = __popc(cm); }
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t a = s_wg[lane], b = s_wc[lane];
+        uint32_t ai = warp_incl_scan(a, lane), bi = warp_incl_scan(b, lane);
+        __syncwarp();
+        s_wg[lane] = ai - a; s_wc[lane] = bi - b;
+      }
+      __syncthreads();
+      const uint32_t dg = s_wg[warp] + __popc(gm & lt), dc = s_wc[warp] + __popc(cm & lt), ds = k - dg - dc;
+      const uint32_t g0 = s_tg[tile], c0 = s_tc[tile], s0 = tbase - g0 - c0;
+      const uint32_t before = s0 + ds;  // signals declared before this event: dense ids => "declared before use" is id < before
+      const unsigned long long w = 3ull * g0 + 2ull * c0 + 3u * dg + 2u * dc;
+      if (is_g) {
+        uint4 gt = make_uint4(kb >> 2, P.words[w], P.words[w + 1], P.words[w + 2]);
+        if (gt.y < before && gt.z < before && gt.w < before) P.outmark[gt.w] = 1;  // compiler.rs:201
+        else { f |= EF_UNKNOWN_REF; gt.y = gt.z = gt.w = 0; }
+        P.egates[g0 + dg] = gt;
+      } else if (is_c) {
+        uint2 ab = make_uint2(P.words[w], P.words[w + 1]);
+        if (!(ab.x < before && ab.y < before)) { f |= EF_UNKNOWN_REF; ab = make_uint2(0, 0); }
+        P.conn[c0 + dc] = ab;
+        P.conn_sb[c0 + dc] = before;
+      } else if (i < n) {
+        P.sig_meta[before] = make_uint2(before | ((kb & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u), c0 + dc);
+      }
+    }
+    f = warp_or(f);
+    if (lane == 0 && f) atomicOr(sc + FS_EFLAGS, f);
+  }
+  grid_bar(P, cx);
+
+  // ================= F2: Boruvka round 1 pick (classes are the signals) + I/O list positions =================
+  uint32_t rounds = 0;
+  {
+    const uint32_t tag = (6u - (rounds % 7u)) << 29;
+    FUSED_FOR(e, C) {
+      uint2 ab = ldg2(P.conn + e);
+      if (ab.x != ab.y) { fused_red_min(P.best + ab.x, tag | e); fused_red_min(P.best + ab.y, tag | e); }
+    }
+    bool bad = false;
+    FUSED_FOR(i, P.n_in + P.n_out) {
+      uint32_t s = P.io_sigs[i];
+      if (s >= S) bad = true;
+      else if (i < P.n_in) atomicMax(P.in_idx1 + s, i + 1);
+      else atomicMax(P.out_idx1 + s, i - P.n_in + 1);
+    }
+    if (bad) atomicOr(sc + FS_EFLAGS, (uint32_t)EF_BAD_IO);
+  }
+  grid_bar(P, cx);
+  // ================= F3: hook round 1 =================
+  {
+    const uint32_t tag = (6u - (rounds % 7u)) << 29;
+    const uint32_t Cw = (C + 31) & ~31u;
+    FUSED_FOR(i, Cw) {
+      bool keep = false, eff = false;
+      if (i < C) {
+        uint2 ab = ldg2(P.conn + i);
+        if (ab.x != ab.y) {
+          uint32_t val = tag | i;
+          bool bu = ldg2(P.best + ab.x) == val, bv = ldg2(P.best + ab.y) == val;
+          if (bu && bv) P.parent[max(ab.x, ab.y)] = min(ab.x, ab.y);
+          else if (bu) P.parent[ab.x] = ab.y;
+          else if (bv) P.parent[ab.y] = ab.x;
+          else keep = true;
+          eff = !keep;
+        }
+      }
+      uint32_t m = __ballot_sync(0xFFFFFFFFu, eff);
+      if (lane == 0 && m) P.eff[i >> 5] = m;  // the warp's 32 connections are exactly one bitmap word
+      warp_append(keep, i, P.cur, sc + FS_MSF + 1);
+    }
+    if (C && blockIdx.x == 0 && threadIdx.x == 0) sc[FS_ROUNDS] = 1;
+    ++rounds;
+  }
+  grid_bar(P, cx);
+  // ================= F4: further rounds while undecided edges remain =================
+  // counters rotate: round j reads cur count FS_MSF + (2j-1)%4, writes cand count FS_MSF + (2j)%4 and cur count FS_MSF + (2j+1)%4
+  if (C) {
+    uint32_t n_cur = ldg2(sc + FS_MSF + 1);
+    uint32_t slot_cur = 1;
+    while (n_cur) {
+      const uint32_t slot_cand = (slot_cur + 1) & 3, slot_next = (slot_cur + 2) & 3;
+      if ((rounds % 7u) == 0) {  // the tags wrapped: forget the old minima (one extra phase every 7 rounds)
+        FUSED_FOR(i, S) P.best[i] = 0xFFFFFFFFu;
+        grid_bar(P, cx);
+      }
+      const uint32_t tag = (6u - (rounds % 7u)) << 29;
+      if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_MSF + slot_next] = 0;
+      const uint32_t nw = (n_cur + 31) & ~31u;
+      FUSED_FOR(i, nw) {
+        bool keep = false;
+        uint4 out = make_uint4(0, 0, 0, 0);
+        if (i < n_cur) {
+          uint32_t e = ldg2(P.cur + i);
+          uint2 ab = ldg2(P.conn + e);
+          uint32_t cu = fused_find(P.parent, ab.x), cv = fused_find(P.parent, ab.y);
+          if (cu != cv) { fused_red_min(P.best + cu, tag | e); fused_red_min(P.best + cv, tag | e); keep = true; out = make_uint4(e, cu, cv, 0); }
+        }
+        warp_append(keep, out, P.cand, sc + FS_MSF + slot_cand);
+      }
+      grid_bar(P, cx);
+      const uint32_t n_cand = ldg2(sc + FS_MSF + slot_cand);
+      if (!n_cand) break;  // every remaining edge became internal
+      if (blockIdx.x == 0 && threadIdx.x == 0) { sc[FS_MSF + ((slot_next + 1) & 3)] = 0; sc[FS_ROUNDS] = rounds + 1; }
+      const uint32_t nc = (n_cand + 31) & ~31u;
+      FUSED_FOR(i, nc) {
+        bool keep = false;
+        uint32_t e = 0;
+        if (i < n_cand) {
+          uint4 c = ldg2(P.cand + i);
+          e = c.x;
+          uint32_t val = tag | e;
+          bool bu = ldg2(P.best + c.y) == val, bv = ldg2(P.best + c.z) == val;
+          if (bu && bv) P.parent[max(c.y, c.z)] = min(c.y, c.z);
+          else if (bu) P.parent[c.y] = c.z;
+          else if (bv) P.parent[c.z] = c.y;
+          else keep = true;
+          if (!keep) atomicOr(P.eff + (e >> 5), 1u << (e & 31));
+        }
+        warp_append(keep, e, P.cur, sc + FS_MSF + slot_next);
+      }
+      ++rounds;
+      grid_bar(P, cx);
+      n_cur = ldg2(sc + FS_MSF + slot_next);
+      slot_cur = slot_next;
+      if (rounds > 96) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(sc + FS_EFLAGS, (uint32_t)EF_CAP); break; }
+    }
+  }
+  // ================= F5: rank prefix of the effective-connection bitmap + class ids (last effective connection) =================
+  uint32_t n_eff = 0;
+  {
+    const uint32_t W = C / 32 + 1;
+    auto f = [&](uint32_t w) { return (uint32_t)__popc(ldg2(P.eff + w)); };
+    n_eff = grid_scan(W, f, P.effp, P.agg, 1u, s_warp);
+    __syncthreads();  // this CTA's chunk of effp is complete (it is the chunk whose connections it handles next)
+    const uint32_t per = (W + gridDim.x - 1) / gridDim.x;
+    const uint32_t wlo = min(W, blockIdx.x * per), whi = min(W, wlo + per);
+    const uint32_t chi = min(C, whi * 32);
+    for (uint32_t c = wlo * 32 + threadIdx.x; c < chi; c += kFusedBlock) {
+      const uint32_t wd = ldg2(P.eff + (c >> 5));
+      if (!((wd >> (c & 31)) & 1u)) continue;  // not effective: no id consumed (compiler.rs:235-237)
+      const uint32_t id = ldg2(P.conn_sb + c) + P.effp[c >> 5] + __popc(wd & ((1u << (c & 31)) - 1u)) + 1u;  // compiler.rs:257
+      atomicMax(P.nidf + fused_find(P.parent, ldg2(P.conn + c).x), id);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_NEFF] = n_eff;
+  }
+  grid_bar(P, cx);
+  // ================= F6: node_of_signal, merge screens, I/O nodes =================
+  {
+    uint32_t f = 0;
+    FUSED_FOR(s, S) {
+      const uint2 m = ldg2(P.sig_meta + s);
+      const uint32_t r = fused_find(P.parent, s);
+      uint32_t node = ldg2(P.nidf + r) & kNidMask;
+      if (node == 0) {
+        const uint32_t c = m.y;
+        node = (m.x & 0x7FFFFFFFu) + 1u + ldg2(P.effp + (c >> 5)) + __popc(ldg2(P.eff + (c >> 5)) & ((1u << (c & 31)) - 1u));  // compiler.rs:157
+      } else {  // merged class: at most one constant and one gate output may meet in it (compiler.rs:239-245)
+        if (m.x & 0x80000000u) { if (atomicOr(P.nidf + r, kHasConst) & kHasConst) f |= EF_CONST_CONST; }
+        if (ldg2(P.outmark + s)) { if (atomicOr(P.nidf + r, kHasOut) & kHasOut) f |= EF_OUT_OUT; }
+      }
+      P.nos[s] = node;
+      // compiler.rs:392-395 / 446-449: list order, a node listed twice keeps the LAST position; an output tag beats an input tag
+      const uint32_t i1 = ldg2(P.in_idx1 + s), o1 = ldg2(P.out_idx1 + s);
+      if (i1) atomicMin(P.wire + node, kInBase - (i1 - 1));
+      if (o1) atomicMin(P.wire + node, kOutBase - (o1 - 1));
+    }
+    f = warp_or(f);
+    if (lane == 0 && f) atomicOr(sc + FS_EFLAGS, f);
+  }
+  grid_bar(P, cx);
+  if (ldg2(sc + FS_EFLAGS)) return;  // the reference errors on this stream (or it needs the exact host replay): nothing is committed
+  const uint32_t NB = S + n_eff + 1;  // node_bound
+  // ================= F7: gates -> node ids + producer map (K1) =================
+  FUSED_FOR(g, G) {
+    const uint4 e = ldg2(P.egates + g);
+    const uint32_t o = ldg2(P.nos + e.w);
+    P.gates[g] = make_uint4(e.x, ldg2(P.nos + e.y), ldg2(P.nos + e.z), o);
+    atomicMax(P.prod1 + o, g + 1);
+  }
+  grid_bar(P, cx);
+  // ================= F8: deps (K2) =================
+  {
+    uint32_t f = 0;
+    const uint32_t Gw = (G + 31) & ~31u;
+    FUSED_FOR(g, Gw) {
+      bool fwd = false;
+      if (g < G) {
+        const uint4 gt = P.gates[g];  // written by this very thread in F7 (same grid-stride mapping)
+        const uint32_t d0 = ldg2(P.prod1 + gt.y) - 1u, d1 = ldg2(P.prod1 + gt.z) - 1u;
+        P.dep[g] = make_uint2(d0, d1);
+        fwd = (d0 != kNone && d0 > g) || (d1 != kNone && d1 > g);
+        if (fwd) f |= F_OOO;
+        if (d0 == g || d1 == g) f |= F_SELF;
+      }
+      warp_append(fwd, g, P.heavy, sc + FS_SEEDN);  // the seeds live in heavy[] until the roots phase reuses it
+    }
+    f = warp_or(f);
+    if (lane == 0 && f) atomicOr(sc + FS_BFLAGS, f);
+  }
+  grid_bar(P, cx);
+  const uint32_t bflags = ldg2(sc + FS_BFLAGS);
+  const bool sorted = (bflags & (F_OOO | F_SELF)) != 0;  // otherwise the DFS post-order is 0..G-1
+  if (sorted) {
+    // ================= F9: exact DFS order (K5a-c) =================
+    {  // seed: r[d] can only be lowered along a forward edge
+      const uint32_t ns = ldg2(sc + FS_SEEDN);
+      FUSED_FOR(i, ns) { uint32_t u = ldg2(P.heavy + i); fused_relax_from(u, u, P.dep, P.r, P.inq, P.q0, sc + FS_QN); }
+    }
+    grid_bar(P, cx);
+    {
+      uint32_t slot = 0, rr = 0;
+      uint32_t* qin = P.q0;
+      uint32_t* qout = P.q1;
+      while (true) {
+        const uint32_t nq = ldg2(sc + FS_QN + slot);
+        if (!nq) break;
+        const uint32_t nslot = (slot + 1) & 3;
+        if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_QN + ((nslot + 1) & 3)] = 0;
+        FUSED_FOR(i, nq) {
+          uint32_t x = ldg2(qin + i);
+          atomicAnd(P.inq + (x >> 5), ~(1u << (x & 31)));
+          __threadfence();
+          fused_relax_from(x, __ldcg(P.r + x), P.dep, P.r, P.inq, qout, sc + FS_QN + nslot);
+        }
+        grid_bar(P, cx);
+        uint32_t* t = qin; qin = qout; qout = t;
+        slot = nslot;
+        ++rr;
+      }
+      if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_RELAX_ROUNDS] = rr;
+    }
+    FUSED_FOR(v, G) atomicAdd(P.size_off + ldg2(P.r + v), 1u);
+    grid_bar(P, cx);
+    {
+      auto f = [&](uint32_t i) { return ldg2(P.size_off + i); };
+      uint32_t tot = grid_scan(G, f, P.size_off, P.agg + gridDim.x, 2u, s_warp);
+      if (blockIdx.x == 0 && threadIdx.x == 0) P.size_off[G] = tot;
+    }
+    grid_bar(P, cx);
+    {
+      const bool check_self = bflags & F_SELF;
+      FUSED_FOR(v, G) {
+        if (ldg2(P.r + v) != v) continue;
+        uint32_t o = ldg2(P.size_off + v), sz = ldg2(P.size_off + v + 1) - o;
+        if (sz == 1) {
+          if (check_self) {
+            uint2 d = ldg2(P.dep + v);
+            if (d.x == v || d.y == v) atomicMin(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ((unsigned long long)v << 32) | v);
+          }
+          P.order[o] = v;
+        } else P.heavy[atomicAdd(sc + FS_HEAVYN, 1u)] = v;
+      }
+    }
+    grid_bar(P, cx);
+    {
+      const uint32_t nh = ldg2(sc + FS_HEAVYN);
+      FUSED_FOR(i, nh) {
+        const uint32_t R = ldg2(P.heavy + i);
+        const uint32_t base = ldg2(P.size_off + R), end = ldg2(P.size_off + R + 1);
+        uint32_t emit = base, top = end;
+        P.state[R] = 1;
+        P.order[--top] = R;
+        while (top < end) {
+          uint32_t v = P.order[top];
+          uint8_t s = P.state[v];
+          if (s <= 2) {
+            uint2 dd = ldg2(P.dep + v);
+            uint32_t d = (s == 1) ? dd.x : dd.y;
+            P.state[v] = s + 1;
+            if (d != kNone && ldg2(P.r + d) == R) {
+              uint8_t sd = P.state[d];
+              if (sd == 0) { P.state[d] = 1; P.order[--top] = d; }
+              else if (sd < 4) {  // visiting[d]  (topological_sort.rs:34-38)
+                atomicMin(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ((unsigned long long)R << 32) | d);
+                break;
+              }
+            }
+          } else { ++top; P.order[emit++] = v; P.state[v] = 4; }
+        }
+      }
+    }
+    grid_bar(P, cx);
+    if (ldg2(sc + FS_ERR_HI) != 0xFFFFFFFFu) return;  // cyclic dependency: the host reports "detected at i=<lo>"
+  } else {
+    FUSED_FOR(i, G) P.order[i] = i;
+  }
+  // ================= F10: wire numbering (K6) + gather (K7) =================
+  FUSED_FOR(k, G) {
+    const uint32_t g = sorted ? ldg2(P.order + k) : k;
+    const uint4 gt = ldg2(P.gates + g);
+    const uint32_t p = kFirstTag | (3u * k);
+    fused_red_min(P.wire + gt.y, p);
+    if (gt.z != gt.y) fused_red_min(P.wire + gt.z, p + 1);
+    if (gt.w != gt.y && gt.w != gt.z) fused_red_min(P.wire + gt.w, p + 2);
+  }
+  grid_bar(P, cx);
+  FUSED_FOR(nd, NB) {
+    const uint32_t w = ldg2(P.wire + nd);
+    if ((w & kFirstTag) && w != kNone) { uint32_t p = w & ~kFirstTag; atomicOr(P.bitmap + (p >> 5), 1u << (p & 31)); }
+  }
+  grid_bar(P, cx);
+  uint32_t n_mid;
+  {
+    const uint32_t BW = (3 * G + 31) / 32 + 1;
+    auto f = [&](uint32_t w) { return (uint32_t)__popc(ldg2(P.bitmap + w)); };
+    n_mid = grid_scan(BW, f, P.bitmap_pre, P.agg + 2 * gridDim.x, 3u, s_warp);
+    if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_NMID] = n_mid;
+  }
+  grid_bar(P, cx);
+  FUSED_FOR(nd, NB) {
+    const uint32_t w = ldg2(P.wire + nd);
+    if (w == kNone) continue;
+    uint32_t id;
+    if (w & kFirstTag) {
+      const uint32_t p = w & ~kFirstTag;
+      id = P.n_in + ldg2(P.bitmap_pre + (p >> 5)) + __popc(ldg2(P.bitmap + (p >> 5)) & ((1u << (p & 31)) - 1u));
+    } else if (w > kOutBase) id = kInBase - w;               // input: its list position
+    else id = P.n_in + n_mid + (kOutBase - w);                // output: after all intermediates
+    P.wire[nd] = id;
+  }
+  grid_bar(P, cx);
+  if (P.new_gates) {
+    FUSED_FOR(k, G) {
+      const uint32_t g = sorted ? ldg2(P.order + k) : k;
+      const uint4 gt = ldg2(P.gates + g);
+      P.new_gates[k] = make_uint4(gt.x, ldg2(P.wire + gt.y), ldg2(P.wire + gt.z), ldg2(P.wire + gt.w));
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_DONE] = 1u;
+}
+
+}  // namespace c2a
+
+using namespace c2a;
+
+extern "C" {
+
+// 0 = never take the fused kernel; otherwise the largest event count it is used for (default: its structural limit)
+static uint64_t g_fused_max_events = (uint64_t)kFusedMaxTiles * kEvTile;
+static uint32_t g_fused_events_per_cta = 4096;
+void c2a_set_fused_limits(uint64_t max_events, uint32_t events_per_cta) {
+  g_fused_max_events = std::min<uint64_t>(max_events, (uint64_t)kFusedMaxTiles * kEvTile);
+  if (events_per_cta) g_fused_events_per_cta = events_per_cta;
+}
+
+static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool pk_on_device, const c2a_compile_io* io, bool out_on_device,
+                               c2a_emit_info* info, uint32_t* wire_count, uint64_t* err_event, uint64_t* err_index) {
+  if (!h) return C2A_ERR_INVALID_ARGUMENT;
+  if (!pk || !io) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
+  const uint64_t n = pk->n_events, nw = pk->n_words;
+  auto classic = [&]() -> int {  // the multi-kernel pipeline: any size, any stream, exact error replay
+    EmitSrc src;
+    src.pk = pk;
+    src.pk_on_device = pk_on_device;
+    int st = emit_events_impl(h, src, n, info, err_event);
+    if (st != C2A_OK) return st;
+    if ((io->order_out || io->new_gates) && io->gates_cap < h->emitted.G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%llu)", (unsigned long long)io->gates_cap, (unsigned long long)h->emitted.G);
+    if (io->wire_of_node && io->wire_cap < h->emitted.node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, h->emitted.node_count + 1);
+    return emitted_build_impl(h, io->input_signals, io->n_in, io->output_signals, io->n_out, io->order_out, io->wire_of_node, io->new_gates, wire_count, err_index, out_on_device);
+  };
+  const bool dense = (pk->flags & C2A_PACKED_DENSE_IDS) != 0;
+  const uint64_t n_io = (uint64_t)io->n_in + io->n_out;
+  if (!dense || n == 0 || n > g_fused_max_events || nw > 3 * n || n_io > (1u << 24) || (n && !pk->kinds) || (nw && !pk->words)) return classic();
+  int st = check_sizes(h, n, 1);
+  if (st) return st;
+  if (info) { memset(info, 0, sizeof *info); info->n_events = n; }
+  phases_clear(h);
+  cudaStream_t s = h->stream;
+
+  FusedParams P;
+  memset(&P, 0, sizeof P);
+  P.n = (uint32_t)n;
+  P.n_words = (uint32_t)nw;
+  P.tiles = (uint32_t)((n + kEvTile - 1) / kEvTile);
+  P.n_in = io->n_in;
+  P.n_out = io->n_out;
+  P.G_ub = (uint32_t)(nw / 3);
+  P.C_ub = (uint32_t)(nw / 2);
+  P.S_ub = (uint32_t)(n - (nw + 2) / 3 + 1);
+  P.NB_ub = P.S_ub + P.C_ub + 1;
+  const uint64_t Gu = P.G_ub, Cu = P.C_ub, Su = P.S_ub, NBu = P.NB_ub;
+  int grid = (int)std::min<uint64_t>((uint64_t)h->num_sms, std::max<uint64_t>(1, (n + g_fused_events_per_cta - 1) / g_fused_events_per_cta));
+  {
+    static int occ = -1;
+    if (occ < 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_fused_compile, kFusedBlock, 0) != cudaSuccess || occ < 1)) { cudaGetLastError(); occ = 0; }
+    if (occ < 1) return classic();
+  }
+  // ---- staging for the stream / I/O lists (host form), then one slab: resident results first, scratch behind them
+  const size_t kbytes = align256(n + 16), wbytes = align256(4 * nw + 16), iobytes = align256(4 * n_io + 16);
+  const size_t stage_need = (pk_on_device ? 0 : kbytes + wbytes) + iobytes;
+  if (stage_need > h->ev_bytes) {
+    if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
+    if (!cuda_ok(h, cudaMalloc(&h->ev_buf, stage_need + stage_need / 8 + 4096), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+    h->ev_bytes = stage_need + stage_need / 8 + 4096;
+  }
+  if ((4 * n_io + 4096) > h->h_pinned_bytes) {
+    cudaStreamSynchronize(s);
+    if (h->h_pinned) cudaFreeHost(h->h_pinned);
+    h->h_pinned_bytes = 4 * n_io + 16384;
+    if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
+  }
+  char* stg = h->ev_buf;
+  uint32_t* d_io = (uint32_t*)stg;
+  stg += iobytes;
+  if (pk_on_device) { P.kinds = pk->kinds; P.words = pk->words; }
+  else { P.kinds = (const uint8_t*)stg; P.words = (const uint32_t*)(stg + kbytes); }
+  P.io_sigs = d_io;
+
+  slab_reset(h);
+  emit_drop_host(h);
+  size_t need = align256(16 * Gu) + align256(4 * Su) + align256(4 * NBu);                                            // resident
+  need += 2 * align256(4 * ((size_t)P.tiles + 2)) + align256(8 * Su) + align256(16 * Gu) + align256(8 * Cu) + align256(4 * Cu) + align256(Su);  // scatter targets
+  need += 5 * align256(4 * Su) + 2 * align256(4 * (Cu / 32 + 8)) + align256(4 * Cu) + align256(16 * Cu);            // union-find, bitmaps, live lists
+  need += align256(8 * Gu) + 2 * align256(4 * (Gu + 1)) + align256(Gu) + align256(4 * (Gu / 32 + 2)) + 3 * align256(4 * Gu) + 2 * align256(4 * ((3 * Gu + 31) / 32 + 8));
+  need += align256(4 * Gu) + align256(4 * NBu) + align256(16 * Gu);                                                 // order / wire / new gates when not the caller's
+  need += align256(4 * FS_COUNT + 64 + 8 * 3 * (size_t)grid) + 4096;
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
+  auto A = [&](size_t bytes) { return slab_alloc(h, bytes); };
+  P.gates = (uint4*)A(16 * Gu);
+  P.nos = (uint32_t*)A(4 * Su);
+  P.prod1 = (uint32_t*)A(4 * NBu);
+  const size_t keep = h->slab_used;
+  P.tile_g = (uint32_t*)A(4 * ((size_t)P.tiles + 2));
+  P.tile_c = (uint32_t*)A(4 * ((size_t)P.tiles + 2));
+  P.sig_meta = (uint2*)A(8 * Su);
+  P.egates = (uint4*)A(16 * Gu);
+  P.conn = (uint2*)A(8 * Cu);
+  P.conn_sb = (uint32_t*)A(4 * Cu);
+  P.outmark = (uint8_t*)A(Su);
+  P.parent = (uint32_t*)A(4 * Su);
+  P.best = (uint32_t*)A(4 * Su);
+  P.nidf = (uint32_t*)A(4 * Su);
+  P.in_idx1 = (uint32_t*)A(4 * Su);
+  P.out_idx1 = (uint32_t*)A(4 * Su);
+  P.eff = (uint32_t*)A(4 * (Cu / 32 + 8));
+  P.effp = (uint32_t*)A(4 * (Cu / 32 + 8));
+  P.cur = (uint32_t*)A(4 * Cu);
+  P.cand = (uint4*)A(16 * Cu);
+  P.dep = (uint2*)A(8 * Gu);
+  P.r = (uint32_t*)A(4 * (Gu + 1));
+  P.size_off = (uint32_t*)A(4 * (Gu + 1));
+  P.state = (uint8_t*)A(Gu);
+  P.inq = (uint32_t*)A(4 * (Gu / 32 + 2));
+  P.q0 = (uint32_t*)A(4 * Gu);
+  P.q1 = (uint32_t*)A(4 * Gu);
+  P.heavy = (uint32_t*)A(4 * Gu);
+  P.bitmap = (uint32_t*)A(4 * ((3 * Gu + 31) / 32 + 8));
+  P.bitmap_pre = (uint32_t*)A(4 * ((3 * Gu + 31) / 32 + 8));
+  // results: straight into the caller's device arrays when they are large enough for the bounds the kernel may reach
+  // (the kernel checks the exact sizes itself before it writes: FS_G / node bound against the capacities)
+  const bool direct = out_on_device;
+  uint32_t* d_order = (direct && io->order_out && io->gates_cap >= Gu) ? io->order_out : (uint32_t*)A(4 * Gu);
+  uint32_t* d_wire = (direct && io->wire_of_node && io->wire_cap >= NBu) ? io->wire_of_node : (uint32_t*)A(4 * NBu);
+  const bool want_new = io->new_gates != nullptr;
+  uint4* d_new = !want_new ? nullptr : ((direct && io->gates_cap >= Gu) ? (uint4*)io->new_gates : (uint4*)A(16 * Gu));
+  char* ctl = (char*)A(4 * FS_COUNT + 64 + 8 * 3 * (size_t)grid);
+  if (!ctl || (want_new && !d_new) || !d_wire || !d_order) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  P.order = d_order;
+  P.wire = d_wire;
+  P.new_gates = d_new;
+  P.sc = (uint32_t*)ctl;
+  P.bar = (unsigned int*)(ctl + 4 * FS_COUNT);
+  P.agg = (unsigned long long*)(ctl + 4 * FS_COUNT + 64);
+
+  // ---- enqueue: copies in, one memset, the kernel, copies out; ONE synchronisation
+  uint32_t* hp = h->h_pinned;
+  if (n_io) {
+    uint32_t* stage = hp + 256;
+    if (io->n_in) memcpy(stage, io->input_signals, 4 * (size_t)io->n_in);
+    if (io->n_out) memcpy(stage + io->n_in, io->output_signals, 4 * (size_t)io->n_out);
+    cudaMemcpyAsync(d_io, stage, 4 * n_io, cudaMemcpyHostToDevice, s);
+  }
+  if (!pk_on_device) {
+    phase_begin(h, "h2d");
+    if (!cuda_ok(h, cudaMemcpyAsync((void*)P.kinds, pk->kinds, n, cudaMemcpyHostToDevice, s), "kinds H2D")) return C2A_ERR_CUDA;
+    if (nw && !cuda_ok(h, cudaMemcpyAsync((void*)P.words, pk->words, 4 * nw, cudaMemcpyHostToDevice, s), "words H2D")) return C2A_ERR_CUDA;
+    phase_end(h);
+  }
+  cudaMemsetAsync(ctl, 0, 4 * FS_COUNT + 64 + 8 * 3 * (size_t)grid, s);
+  cudaMemsetAsync(P.sc + FS_ERR_LO, 0xFF, 8, s);
+  phase_begin(h, "k_fused_compile");
+  {
+    void* args[] = {(void*)&P};
+    if (!cuda_ok(h, cudaLaunchCooperativeKernel((const void*)k_fused_compile, dim3(grid), dim3(kFusedBlock), args, 0, s), "fused launch")) return C2A_ERR_CUDA;
+    h->launches++;
+  }
+  phase_end(h);
+  cudaMemcpyAsync(hp, P.sc, 4 * FS_COUNT, cudaMemcpyDeviceToHost, s);
+  // results the caller wants in host memory, or in device arrays smaller than the bounds: copied by capacity (the exact sizes are
+  // only known after the synchronisation; a caller that sized its arrays exactly copies exactly)
+  const uint64_t gcopy = std::min<uint64_t>(io->gates_cap, Gu), wcopy = std::min<uint64_t>(io->wire_cap, NBu);
+  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  phase_begin(h, "d2h");
+  if (io->order_out && d_order != io->order_out && gcopy) cudaMemcpyAsync(io->order_out, d_order, 4 * gcopy, kind, s);
+  if (io->wire_of_node && d_wire != io->wire_of_node && wcopy) cudaMemcpyAsync(io->wire_of_node, d_wire, 4 * wcopy, kind, s);
+  if (want_new && (void*)d_new != (void*)io->new_gates && gcopy) cudaMemcpyAsync(io->new_gates, d_new, 16 * gcopy, kind, s);
+  phase_end(h);
+  if (!cuda_ok(h, cudaStreamSynchronize(s), "fused sync")) return C2A_ERR_CUDA;
+  if (!cuda_ok(h, cudaGetLastError(), "fused kernel")) return C2A_ERR_CUDA;
+  phases_collect(h);
+
+  const uint32_t G = hp[FS_G], Cn = hp[FS_C], S = hp[FS_S], eflags = hp[FS_EFLAGS];
+  if (eflags || (!hp[FS_DONE] && hp[FS_ERR_HI] == 0xFFFFFFFFu)) {
+    // the reference errors on this stream, or it is not a stream the device path decides itself: the multi-kernel path replays it
+    // exactly (same status, same event index).  Nothing of the fused attempt is kept.
+    slab_reset(h);
+    return classic();
+  }
+  const uint32_t n_eff = hp[FS_NEFF];
+  if (info) {
+    info->n_gates = G; info->n_connections = Cn; info->n_signals = S; info->signal_bound = S; info->n_effective = n_eff;
+    info->node_count = S + n_eff; info->path = C2A_EMIT_PATH_DEVICE; info->rounds = hp[FS_ROUNDS];
+  }
+  h->slab_keep = keep;
+  h->emitted.valid = true;
+  h->emitted.nos_valid = true;
+  h->emitted.gates_off = (char*)P.gates - h->slab;
+  h->emitted.nos_off = (char*)P.nos - h->slab;
+  h->emitted.prod1_valid = true;
+  h->emitted.prod1_off = (char*)P.prod1 - h->slab;
+  h->emitted.G = G;
+  h->emitted.node_count = S + n_eff;
+  h->emitted.signal_bound = S;
+  h->emitted.wire = nullptr;
+  unsigned long long err = ((unsigned long long)hp[FS_ERR_HI] << 32) | hp[FS_ERR_LO];
+  if (err != ~0ull) {
+    if (err_index) *err_index = (uint32_t)err;
+    return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "detected at i=%llu", (unsigned long long)(uint32_t)err);
+  }
+  if ((io->order_out || io->new_gates) && io->gates_cap < G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%u)", (unsigned long long)io->gates_cap, G);
+  if (io->wire_of_node && io->wire_cap < S + n_eff + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, S + n_eff + 1);
+  h->emitted.wire = d_wire;
+  h->emitted.identity = !(hp[FS_BFLAGS] & (F_OOO | F_SELF));
+  if (wire_count) *wire_count = io->n_in + hp[FS_NMID] + io->n_out;
+  return C2A_OK;
+}
+
+int c2a_compile_packed(c2a_handle* h, const c2a_packed_events* pk, const c2a_compile_io* io, c2a_emit_info* info, uint32_t* wire_count,
+                       uint64_t* err_event, uint64_t* err_index) {
+  return compile_packed_impl(h, pk, false, io, false, info, wire_count, err_event, err_index);
+}
+int c2a_compile_packed_resident(c2a_handle* h, const c2a_packed_events* d_pk, const c2a_compile_io* io, c2a_emit_info* info, uint32_t* wire_count,
+                                uint64_t* err_event, uint64_t* err_index) {
+  return compile_packed_impl(h, d_pk, true, io, true, info, wire_count, err_event, err_index);
+}
+
+}  // extern "C"
