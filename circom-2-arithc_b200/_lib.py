@@ -68,6 +68,11 @@ class CompressedEvents(C.Structure):  # c2a_compressed_events
     _fields_ = [("kinds", vp), ("words", vp), ("n_events", u64), ("n_words", u64), ("replays", vp), ("n_replays", u64), ("max_gen", u32), ("flags", u32)]
 
 
+class CompileIO(C.Structure):  # c2a_compile_io
+    _fields_ = [("input_signals", vp), ("output_signals", vp), ("n_in", u32), ("n_out", u32), ("order_out", vp), ("wire_of_node", vp), ("new_gates", vp),
+                ("gates_cap", u64), ("wire_cap", u32), ("reserved", u32)]
+
+
 load_error = None
 try:
     lib = C.CDLL(LIB_PATH)
@@ -113,6 +118,9 @@ _SIGS = {
     "c2a_unpack_events": (i32, [vp, vp]),
     "c2a_emit_packed_device": (i32, [vp, vp, vp, u64p]),
     "c2a_emit_packed_resident": (i32, [vp, vp, vp, u64p]),
+    "c2a_compile_packed": (i32, [vp, vp, vp, vp, u32p, u64p, u64p]),
+    "c2a_compile_packed_resident": (i32, [vp, vp, vp, vp, u32p, u64p, u64p]),
+    "c2a_set_fused_limits": (None, [u64, u32]),
     "c2a_program_packed": (i32, [vp, vp]),
     "c2a_program_compressed": (i32, [vp, vp]),
     "c2a_emit_compressed_device": (i32, [vp, vp, vp, u64p]),

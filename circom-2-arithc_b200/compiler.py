@@ -19,7 +19,7 @@ from typing import Dict, List, Optional
 
 import numpy as np
 
-from ._lib import lib, C2AError, CircuitError, Status, EmitInfo, PackedEvents
+from ._lib import lib, C2AError, CircuitError, Status, EmitInfo, PackedEvents, CompileIO
 
 NONE = 0xFFFFFFFF
 EVENT_DTYPE = np.dtype([("kind", "<u4"), ("a", "<u4"), ("b", "<u4"), ("c", "<u4")])
@@ -256,6 +256,41 @@ class DeviceContext:
             raise e
         self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
         return dict(self._emit_info)
+
+    def compile_packed(self, kinds: np.ndarray, words: np.ndarray, flags: int, input_signals, output_signals,
+                       want_order=True, want_wires=True, want_gates=True):
+        """c2a_compile_packed: emit + build in one call (one synchronisation; circuits up to ~1 M gates run inside one cooperative
+        kernel).  -> (info, order, wire_of_node[node_count+1], new_gates, wire_count); same results and errors as emit_packed()
+        followed by emitted_build_circuit()."""
+        kinds = np.ascontiguousarray(kinds, dtype=np.uint8)
+        words = np.ascontiguousarray(words, dtype=np.uint32)
+        ins = np.ascontiguousarray(input_signals, dtype=np.uint32)
+        outs = np.ascontiguousarray(output_signals, dtype=np.uint32)
+        n = kinds.shape[0]
+        n_g = int(np.count_nonzero((kinds & 3) == 2))
+        n_c = int(np.count_nonzero((kinds & 3) == 3))
+        gcap, wcap = n_g, n - n_g + 1   # node_count + 1 <= signals + connections + 1
+        order = np.empty(gcap, dtype=np.uint32) if want_order else None
+        wire = np.empty(wcap, dtype=np.uint32) if want_wires else None
+        ng = np.empty((gcap, 4), dtype=np.uint32) if want_gates else None
+        pk = PackedEvents(_ptr(kinds), _ptr(words), n, words.shape[0], flags, 0)
+        io = CompileIO(_ptr(ins), _ptr(outs), ins.shape[0], outs.shape[0], _ptr(order), _ptr(wire), _ptr(ng), gcap, wcap, 0)
+        info = EmitInfo()
+        wc, bad, err = C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        st = lib.c2a_compile_packed(self._h, C.byref(pk), C.byref(io), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
+        if st == Status.CYCLIC_DEPENDENCY:
+            raise CircuitError(st, f"detected at i={err.value}")
+        if st != 0:
+            e = None
+            try:
+                _raise(st, f"event {bad.value}: {self.last_error()}")
+            except (CircuitError, C2AError) as ex:
+                ex.err_event = bad.value
+                e = ex
+            raise e
+        self._emit_info = {k: int(getattr(info, k)) for k, _ in EmitInfo._fields_ if k != "reserved"}
+        nb = self._emit_info["node_count"] + 1
+        return dict(self._emit_info), order, (wire[:nb] if wire is not None else None), ng, wc.value
 
     def emitted_signal_wires(self, signals) -> np.ndarray:
         """c2a_emitted_signal_wires: wire ids of the given signals after emitted_build_circuit (0xFFFFFFFF = none)."""

@@ -1388,4 +1388,5 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
 
 #include "c2a_kahn.cuh"
 #include "c2a_emit.cuh"
+#include "c2a_fused.cuh"
 #include "c2a_eval.cuh"

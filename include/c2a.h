@@ -250,6 +250,35 @@ int c2a_unpack_events(const c2a_packed_events* pk, c2a_event* ev_out /* n_events
 int c2a_emit_packed_device(c2a_handle*, const c2a_packed_events* pk, c2a_emit_info* info, uint64_t* err_event);
 int c2a_emit_packed_resident(c2a_handle*, const c2a_packed_events* d_pk, c2a_emit_info* info, uint64_t* err_event);
 
+/* ---- emit + build in ONE call: what src/program.rs::compile's add_* replay followed by Compiler::build_circuit
+ * (src/compiler.rs:139-278, then :321-464) amounts to for a caller that holds the whole recording.  Exactly
+ * c2a_emit_packed_device / _resident followed by c2a_emitted_build_circuit / _device - same c2a_emit_info, same arrays, same
+ * statuses, the emitted circuit stays resident for c2a_emitted_signal_wires() etc. - but with ONE synchronisation, and for
+ * circuits up to ~1 M gates (dense ids, <= 4 M events) the whole pipeline runs inside one cooperative kernel (csrc/c2a_fused.cuh:
+ * grid barriers instead of ~55 kernel launches), which is what makes the small BASELINE configs (Poseidon / SHA-256 / Keccak
+ * shaped, 1 K - 400 K gates) launch-latency free.  The result arrays are sized by the caller: gates_cap entries for order_out /
+ * new_gates, wire_cap entries for wire_of_node (node_count + 1 are needed; n_gates <= n_words / 3 and
+ * node_count < n_events always hold).  Too small -> C2A_ERR_INVALID_ARGUMENT with *info filled, circuit still resident. ---- */
+typedef struct {
+  const uint32_t* input_signals;   /* host pointers: main-template input / output SIGNAL ids, in wire order */
+  const uint32_t* output_signals;
+  uint32_t n_in, n_out;
+  uint32_t* order_out;             /* [gates_cap]  may be NULL */
+  uint32_t* wire_of_node;          /* [wire_cap]   may be NULL */
+  c2a_gate* new_gates;             /* [gates_cap]  may be NULL */
+  uint64_t gates_cap;
+  uint32_t wire_cap, reserved;
+} c2a_compile_io;
+/* kinds / words and the three result arrays are HOST pointers (copies inside the call) */
+int c2a_compile_packed(c2a_handle*, const c2a_packed_events* pk, const c2a_compile_io* io, c2a_emit_info* info, uint32_t* wire_count,
+                       uint64_t* err_event, uint64_t* err_index);
+/* kinds / words and the three result arrays are DEVICE pointers (the structs themselves and the I/O lists are in host memory) */
+int c2a_compile_packed_resident(c2a_handle*, const c2a_packed_events* d_pk, const c2a_compile_io* io, c2a_emit_info* info, uint32_t* wire_count,
+                                uint64_t* err_event, uint64_t* err_index);
+/* tuning / testing: largest event count the single-kernel path is used for (0 = never; default and maximum 4 Mi events) and the
+ * events per CTA that size its grid (0 = keep).  Process-wide. */
+void c2a_set_fused_limits(uint64_t max_events, uint32_t events_per_cta);
+
 /* ---- emit side (host).  Node ids, gate vector and error behaviour identical to the reference Compiler. ---- */
 c2a_compiler* c2a_compiler_new(void);
 void c2a_compiler_free(c2a_compiler*);
