@@ -292,7 +292,7 @@ def time_on_stream(torch, stream, fn, steps, warmup, flush=None):
     return tot / steps
 
 
-def circuit_leg(c2a, torch, ctx, dev, stream, wl, steps, peak, flush, cpu_backend=True, orc=None):
+def circuit_leg(c2a, torch, ctx, dev, stream, wl, steps, peak, flush, cpu_backend=True, orc=None, concurrent=0):
     """One BASELINE config as a sub-record: value (resident), value with the L2 flushed between steps, e2e (host buffers), the
     exact-order sort's achieved HBM GB/s, and the CPU oracle's back end on the very same gate vector."""
     import numpy as np
@@ -309,6 +309,35 @@ def circuit_leg(c2a, torch, ctx, dev, stream, wl, steps, peak, flush, cpu_backen
         sc.step_compile_e2e()
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / steps
+    # throughput with several circuits in flight: T handles on T host threads, each compiling its own copy of this circuit (the
+    # single-kernel path occupies a few CTAs per small circuit, so independent compilations share the GPU)
+    conc = None
+    if concurrent and sc.G <= 500_000:
+        T = int(concurrent)
+        ctxs = [c2a.DeviceContext(ctx.device) for _ in range(T)]
+        scs = [StagedCircuit(c2a, torch, cx_, dev, wl) for cx_ in ctxs]
+        for cx_ in ctxs:
+            lib.c2a_set_timing(cx_.handle, 0)
+        reps = max(20, steps)
+
+        def worker(s_):
+            for _ in range(reps):
+                s_.step_compile_resident()
+
+        for s_ in scs:
+            s_.step_compile_resident()
+        torch.cuda.synchronize()
+        ths = [threading.Thread(target=worker, args=(s_,)) for s_ in scs]
+        t0 = time.perf_counter()
+        for t_ in ths:
+            t_.start()
+        for t_ in ths:
+            t_.join()
+        torch.cuda.synchronize()
+        dtc = time.perf_counter() - t0
+        conc = {"value": T * reps * sc.G / dtc, "unit": "gates/s", "handles_in_flight": T, "circuits": T * reps, "wall_s": dtc,
+                "note": "T handles on T host threads, same call as `value` (c2a_compile_packed_resident), wall clock around all of them"}
+        del scs, ctxs
     # for comparison: the two-call multi-kernel pipeline on the same circuit (what round 1 measured)
     ms_multi = time_on_stream(torch, stream, sc.step_resident, max(3, steps // 2), 2)
     lib.c2a_set_timing(h, 1)
@@ -326,6 +355,7 @@ def circuit_leg(c2a, torch, ctx, dev, stream, wl, steps, peak, flush, cpu_backen
            "value_l2_flushed": sc.G / (ms_cold * 1e-3), "ms_per_step_l2_flushed": ms_cold, "steps": steps, "gpu_launches_per_step": int(launches),
            "path": "c2a_compile_packed_resident: " + ("one cooperative kernel (csrc/c2a_fused.cuh)" if fused else "multi-kernel pipeline, one call"),
            "fused_kernel_ms": fused_ms, "multi_kernel_two_call_ms_per_step": ms_multi,
+           **({"value_concurrent": conc} if conc else {}),
            "e2e": {"value": sc.G / e2e_s, "unit": "gates/s", "s_per_step": e2e_s, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
            "topo_sort_ms": sort_ms, "topo_hbm_gbs": (ALG_SORT_BYTES_PER_GATE * sc.G / (sort_ms * 1e-3) / 1e9) if sort_ms > 0 else None,
            "topo_frac_of_peak": (ALG_SORT_BYTES_PER_GATE * sc.G / (sort_ms * 1e-3) / 1e9 / peak) if sort_ms > 0 else None,
@@ -971,7 +1001,7 @@ def main():
             cfgs = {}
             for key, wlx in (("poseidon_shaped", c2a.workloads.poseidon_shaped()), ("sha256_shaped", c2a.workloads.sha256_shaped()),
                              ("keccak_shaped_x1", c2a.workloads.keccak_shaped(1)), ("keccak_shaped_x2", c2a.workloads.keccak_shaped(2))):
-                cfgs[key], _sc = circuit_leg(c2a, torch, ctx, dev, stream, wlx, Kx, peak, flush, cpu_backend=True, orc=orc)
+                cfgs[key], _sc = circuit_leg(c2a, torch, ctx, dev, stream, wlx, Kx, peak, flush, cpu_backend=True, orc=orc, concurrent=8)
                 del _sc
             extra["configs"] = cfgs
         gates_late = nos_late = None

@@ -1187,6 +1187,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->slab) cudaFree(h->slab);
   if (h->ev_buf) cudaFree(h->ev_buf);
   if (h->cx_buf) cudaFree(h->cx_buf);
+  if (h->fused_ctl) cudaFree(h->fused_ctl);
   if (h->cx_pinned) cudaFreeHost(h->cx_pinned);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);

@@ -35,7 +35,7 @@ constexpr uint32_t kInBase = 0x7FFFFFFEu;                 // wire[] tag of input
 constexpr uint32_t kOutBase = 0x3FFFFFFFu;                // wire[] tag of output list position j: kOutBase - j  (outputs override inputs)
 constexpr uint32_t kOutFloor = 0x20000000u;
 // scalars of the fused kernel
-enum { FS_G = 0, FS_C, FS_S, FS_EFLAGS, FS_NEFF, FS_ROUNDS, FS_BFLAGS, FS_SEEDN, FS_HEAVYN, FS_NMID, FS_ERR_LO = 10, FS_ERR_HI = 11, FS_DONE = 12,
+enum { FS_G = 0, FS_C, FS_S, FS_EFLAGS, FS_NEFF, FS_ROUNDS, FS_BFLAGS, FS_SEEDN, FS_HEAVYN, FS_NMID, FS_ERR_LO = 10 /* ~(root << 32 | i), max = smallest; 0 = no cycle */, FS_ERR_HI = 11, FS_DONE = 12,
        FS_RELAX_ROUNDS = 13, FS_QN = 16 /* 4 rotating queue counters */, FS_MSF = 20 /* 4 rotating: cand / cur counters */, FS_COUNT = 32 };
 
 struct FusedParams {
@@ -65,12 +65,20 @@ struct FusedParams {
   uint8_t* state;
   uint32_t *inq, *q0, *q1, *heavy, *bitmap, *bitmap_pre;
   unsigned long long* agg;  // look-back aggregates: 2 scans x gridDim
-  // results of the build
-  uint32_t* order;       // never null (internal scratch when the caller does not want it)
-  uint32_t* wire;        // NB_ub entries
-  uint4* new_gates;      // may be null
-  uint32_t* sc;          // FS_COUNT scalars, zeroed (ERR = ~0) before the launch
-  unsigned int* bar;     // grid barrier counter, zeroed before the launch
+  // results of the build: the caller's device arrays when the exact sizes fit their capacities (the kernel decides once it knows
+  // them: FS_G after F1, the node bound after F5), else internal scratch of bound size (the host then reports the capacity)
+  uint32_t* order_user;  uint32_t* order_int;   // order_int never null
+  uint32_t* wire_user;   uint32_t* wire_int;    // wire_int: NB_ub entries, never null
+  uint4* new_user;       uint4* new_int;        // both null when the renumbered gates are not wanted
+  unsigned long long gates_cap;
+  uint32_t wire_cap;
+  // control block (double-buffered in the handle: this launch zeroes the other half for the next one - no memset per call)
+  uint32_t* sc;          // FS_COUNT scalars, zero on entry
+  unsigned int* bar;     // grid barrier counter, zero on entry
+  uint32_t* ctl_next;    // the other half, ctl_words u32
+  uint32_t ctl_words;
+  uint32_t* host_sc;     // pinned host memory (mapped): the scalars are stored here by CTA 0 before it exits - no D2H copy
+  unsigned long long* trace;  // diagnostics (C2A_FUSED_TRACE=1): globaltimer of CTA 0 at every barrier exit, [0] = count; else null
 };
 
 // ---- memory access helpers.  Arrays written by other CTAs in an earlier phase are read through L2 (ld.cg): the barrier's fence
@@ -80,13 +88,16 @@ __device__ __forceinline__ T ldg2(const T* p) { return __ldcg(p); }
 
 struct FusedCtx {
   unsigned int epoch;  // thread 0 only
+  unsigned int nbar;
 };
 
+// Grid barrier: bar.sync orders the CTA's threads before thread 0's release (cumulative at gpu scope), the acquire poll orders
+// thread 0 - and through the second bar.sync the whole CTA - after every other CTA's release.  No separate fences: each
+// MEMBAR.GPU costs about as much as the barrier itself.
 __device__ __forceinline__ void grid_bar(const FusedParams& P, FusedCtx& cx) {
   __syncthreads();
   if (threadIdx.x == 0) {
     cx.epoch += gridDim.x;
-    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(P.bar) : "memory");
     unsigned int v;
     uint32_t spins = 0;
@@ -94,9 +105,24 @@ __device__ __forceinline__ void grid_bar(const FusedParams& P, FusedCtx& cx) {
       asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.bar) : "memory");
       if (++spins > (1u << 26)) __trap();  // a CTA never arrived: fail loudly instead of hanging
     } while (v < cx.epoch);
-    __threadfence();
+    if (P.trace && blockIdx.x == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (++cx.nbar < 120) { P.trace[cx.nbar] = t; P.trace[0] = cx.nbar; }
+    }
   }
   __syncthreads();
+}
+
+// diagnostics: an extra timeline entry inside a phase (all threads of the CTA must reach it)
+__device__ __forceinline__ void trace_mark(const FusedParams& P, FusedCtx& cx) {
+  if (!P.trace) return;
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (++cx.nbar < 120) { P.trace[cx.nbar] = t | (1ull << 63); P.trace[0] = cx.nbar; }
+  }
 }
 
 #define FUSED_FOR(i, n) for (uint32_t i = blockIdx.x * kFusedBlock + threadIdx.x; i < (n); i += gridDim.x * kFusedBlock)
@@ -119,36 +145,33 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* s_warp
   return s_warp[warp] + incl - v;
 }
 
-// Grid-wide exclusive scan without a grid barrier: CTA b owns the contiguous chunk b of the sequence, publishes its aggregate
-// (tagged with `tag`, so the slots need no reset between scans) and sums the aggregates of the CTAs before it (all co-resident:
-// cooperative launch).  f(i) = the i-th value.  Writes dst[i] = exclusive prefix; returns the grid total to every thread.
+// Grid-wide exclusive scan: CTA b owns the contiguous chunk b of the sequence, stores its aggregate, one grid barrier, then every
+// CTA sums the aggregates before it (one load per thread) and scans its chunk.  f(i) = the i-th value.  Writes dst[i] = exclusive
+// prefix; returns the grid total to every thread.  (A barrier-free variant - tagged aggregates polled by every CTA - was measured
+// at 3-10 us per scan: 148 CTAs x 148 polling threads slow the very stores they wait for.)
 template <typename F>
-__device__ __forceinline__ uint32_t grid_scan(uint32_t n, F f, uint32_t* dst, unsigned long long* agg, uint32_t tag, uint32_t* s_warp) {
+__device__ __forceinline__ uint32_t grid_scan(const FusedParams& P, FusedCtx& cx, uint32_t n, F f, uint32_t* dst, unsigned long long* agg, uint32_t* s_warp) {
   __shared__ uint32_t s_pre, s_tot;
   const uint32_t per = (n + gridDim.x - 1) / gridDim.x;
   const uint32_t lo = min(n, blockIdx.x * per), hi = min(n, lo + per);
-  // local sum
   uint32_t sum = 0;
   for (uint32_t i = lo + threadIdx.x; i < hi; i += kFusedBlock) sum += f(i);
   uint32_t tot = 0;
   block_excl_scan(sum, s_warp, &tot);
-  if (threadIdx.x == 0) st_volatile_u64(agg + blockIdx.x, ((unsigned long long)tag << 32) | tot);
-  // prefix over the predecessors' aggregates (warp 0), grand total over all (every CTA needs it)
-  if (threadIdx.x < 32) {
-    uint32_t pre = 0, all = 0, spins = 0;
-    for (uint32_t b = threadIdx.x; b < gridDim.x; b += 32) {
-      unsigned long long v;
-      while ((uint32_t)((v = ld_volatile_u64(agg + b)) >> 32) != tag)
-        if (++spins > (1u << 26)) __trap();
-      all += (uint32_t)v;
-      if (b < blockIdx.x) pre += (uint32_t)v;
+  if (threadIdx.x == 0) agg[blockIdx.x] = tot;
+  grid_bar(P, cx);
+  {
+    uint32_t pre = 0, all = 0;
+    if (threadIdx.x < gridDim.x) {
+      all = (uint32_t)__ldcg(agg + threadIdx.x);
+      if (threadIdx.x < blockIdx.x) pre = all;
     }
-    pre = warp_sum(pre);
-    all = warp_sum(all);
-    if (threadIdx.x == 0) { s_pre = pre; s_tot = all; }
+    uint32_t tp = 0, ta = 0;
+    block_excl_scan(pre, s_warp, &tp);
+    block_excl_scan(all, s_warp, &ta);
+    if (threadIdx.x == 0) { s_pre = tp; s_tot = ta; }
   }
   __syncthreads();
-  // local exclusive scan, kFusedBlock elements per round
   uint32_t carry = s_pre;
   for (uint32_t base = lo; base < hi; base += kFusedBlock) {
     uint32_t i = base + threadIdx.x;
@@ -192,11 +215,29 @@ __device__ __forceinline__ void fused_relax_from(uint32_t cur, uint32_t val, con
   }
 }
 
+// CTA 0 hands the scalars to the host through mapped pinned memory (every exit of the kernel follows a grid barrier, or writes
+// of CTA 0's own thread 0, so they are complete)
+__device__ __forceinline__ void fused_publish(const FusedParams& P) {
+  if (blockIdx.x != 0) return;
+  __syncthreads();
+  if (threadIdx.x < FS_COUNT) {
+    volatile uint32_t* hs = P.host_sc;
+    hs[threadIdx.x] = __ldcg(P.sc + threadIdx.x);
+    __threadfence_system();
+  }
+}
+
 __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedParams P) {
   __shared__ uint32_t s_tg[kFusedMaxTiles], s_tc[kFusedMaxTiles];  // exclusive tile prefixes (gates, connections)
   __shared__ uint32_t s_warp[33], s_wg[33], s_wc[33];
   FusedCtx cx;
   cx.epoch = 0;
+  cx.nbar = 0;
+  if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    P.trace[127] = t;  // kernel start
+  }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
   uint32_t* sc = P.sc;
@@ -205,23 +246,44 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   // ================= F0: init + per-tile counts (one warp per 1024-event tile) =================
   FUSED_FOR(i, P.S_ub) { P.parent[i] = i; P.best[i] = 0xFFFFFFFFu; P.nidf[i] = 0; P.outmark[i] = 0; P.in_idx1[i] = 0; P.out_idx1[i] = 0; }
   FUSED_FOR(i, P.C_ub / 32 + 4) P.eff[i] = 0;
-  FUSED_FOR(i, P.NB_ub) { P.prod1[i] = 0; P.wire[i] = kNone; }
+  FUSED_FOR(i, P.NB_ub) P.prod1[i] = 0;
+  FUSED_FOR(i, P.ctl_words) P.ctl_next[i] = 0;
   FUSED_FOR(i, P.G_ub + 1) { P.size_off[i] = 0; if (i < P.G_ub) { P.r[i] = i; P.state[i] = 0; } }
   FUSED_FOR(i, (P.G_ub + 31) / 32 + 1) P.inq[i] = 0;
   FUSED_FOR(i, (3 * P.G_ub + 31) / 32 + 4) P.bitmap[i] = 0;
+  trace_mark(P, cx);
   {
     uint32_t f = 0;
     const uint32_t nwarps = gridDim.x * (kFusedBlock / 32);
+    const bool aligned = !(reinterpret_cast<uintptr_t>(P.kinds) & 15);
     for (uint32_t tile = blockIdx.x * (kFusedBlock / 32) + warp; tile < P.tiles; tile += nwarps) {
       const uint32_t tbase = tile * kEvTile;
       uint32_t g = 0, c = 0;
-#pragma unroll 4
-      for (int j = 0; j < 32; ++j) {
-        uint32_t i = tbase + j * 32 + lane;
-        if (i < n) {
-          uint32_t kb = P.kinds[i], kind = kb & 3u, op = kb >> 2;
-          if (kind == C2A_EV_GATE) { ++g; if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
-          else { if (kind == C2A_EV_CONNECT) ++c; if (op) f |= EF_BAD_KIND; }
+      uint32_t wd[8];
+      if (aligned && tbase + kEvTile <= n) {  // two 128-bit loads per lane, both in flight
+        const uint4 x = *(reinterpret_cast<const uint4*>(P.kinds + tbase) + lane), y = *(reinterpret_cast<const uint4*>(P.kinds + tbase + 512) + lane);
+        wd[0] = x.x; wd[1] = x.y; wd[2] = x.z; wd[3] = x.w; wd[4] = y.x; wd[5] = y.y; wd[6] = y.z; wd[7] = y.w;
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          wd[q] = 0;  // padding = SIGNAL with op 0: neither counted nor flagged
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t i = tbase + (q < 4 ? 0 : 512) + lane * 16 + (q & 3) * 4 + j;
+            if (i < n) wd[q] |= (uint32_t)P.kinds[i] << (8 * j);
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const uint32_t lo = wd[q] & 0x01010101u, hi = (wd[q] >> 1) & 0x01010101u;  // kind bit 0 / bit 1 of each byte
+        g += __popc(hi & ~lo);
+        c += __popc(hi & lo);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t kb = (wd[q] >> (8 * j)) & 0xFFu, op = kb >> 2;
+          if ((kb & 3u) == C2A_EV_GATE) { if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
+          else if (op) f |= EF_BAD_KIND;
         }
       }
       g = warp_sum(g);
@@ -258,13 +320,19 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
     __syncthreads();
     G = totg; C = totc; S = n - G - C;
   }
+  trace_mark(P, cx);
+  // results go straight into the caller's arrays when they hold G entries (every CTA derives the same verdict)
+  const bool gates_fit = (unsigned long long)G <= P.gates_cap;
+  uint32_t* const order = (P.order_user && gates_fit) ? P.order_user : P.order_int;
+  uint4* const new_gates = (P.new_user && gates_fit) ? P.new_user : P.new_int;
+  uint32_t* wire = P.wire_int;  // chosen in F5, when the node bound is known
   // the counts decide everything downstream: every CTA derives the same verdict from the same numbers
   const bool words_ok = (unsigned long long)P.n_words == 3ull * G + 2ull * C;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc[FS_G] = G; sc[FS_C] = C; sc[FS_S] = S;
     if (!words_ok) atomicOr(sc + FS_EFLAGS, (uint32_t)EF_CAP);  // n_words does not match the kinds: the host reports it
   }
-  if (!words_ok || (ldg2(sc + FS_EFLAGS) & (EF_BAD_KIND | EF_BAD_OP))) return;  // uniform: flags were complete at the barrier
+  if (!words_ok || (ldg2(sc + FS_EFLAGS) & (EF_BAD_KIND | EF_BAD_OP))) { fused_publish(P); return; }  // uniform: flags were complete at the barrier
   {
     uint32_t f = 0;
     for (uint32_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
@@ -407,7 +475,8 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   {
     const uint32_t W = C / 32 + 1;
     auto f = [&](uint32_t w) { return (uint32_t)__popc(ldg2(P.eff + w)); };
-    n_eff = grid_scan(W, f, P.effp, P.agg, 1u, s_warp);
+    n_eff = grid_scan(P, cx, W, f, P.effp, P.agg, s_warp);
+    trace_mark(P, cx);
     __syncthreads();  // this CTA's chunk of effp is complete (it is the chunk whose connections it handles next)
     const uint32_t per = (W + gridDim.x - 1) / gridDim.x;
     const uint32_t wlo = min(W, blockIdx.x * per), whi = min(W, wlo + per);
@@ -419,6 +488,10 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
       atomicMax(P.nidf + fused_find(P.parent, ldg2(P.conn + c).x), id);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_NEFF] = n_eff;
+    // the node bound is known: pick the wire map (the caller's when it holds S + n_eff + 1 entries) and clear it
+    const uint32_t NBk = S + n_eff + 1;
+    wire = (P.wire_user && NBk <= P.wire_cap) ? P.wire_user : P.wire_int;
+    FUSED_FOR(i, NBk) wire[i] = kNone;
   }
   grid_bar(P, cx);
   // ================= F6: node_of_signal, merge screens, I/O nodes =================
@@ -438,14 +511,14 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
       P.nos[s] = node;
       // compiler.rs:392-395 / 446-449: list order, a node listed twice keeps the LAST position; an output tag beats an input tag
       const uint32_t i1 = ldg2(P.in_idx1 + s), o1 = ldg2(P.out_idx1 + s);
-      if (i1) atomicMin(P.wire + node, kInBase - (i1 - 1));
-      if (o1) atomicMin(P.wire + node, kOutBase - (o1 - 1));
+      if (i1) atomicMin(wire + node, kInBase - (i1 - 1));
+      if (o1) atomicMin(wire + node, kOutBase - (o1 - 1));
     }
     f = warp_or(f);
     if (lane == 0 && f) atomicOr(sc + FS_EFLAGS, f);
   }
   grid_bar(P, cx);
-  if (ldg2(sc + FS_EFLAGS)) return;  // the reference errors on this stream (or it needs the exact host replay): nothing is committed
+  if (ldg2(sc + FS_EFLAGS)) { fused_publish(P); return; }  // the reference errors on this stream (or it needs the exact host replay): nothing is committed
   const uint32_t NB = S + n_eff + 1;  // node_bound
   // ================= F7: gates -> node ids + producer map (K1) =================
   FUSED_FOR(g, G) {
@@ -510,7 +583,7 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
     grid_bar(P, cx);
     {
       auto f = [&](uint32_t i) { return ldg2(P.size_off + i); };
-      uint32_t tot = grid_scan(G, f, P.size_off, P.agg + gridDim.x, 2u, s_warp);
+      uint32_t tot = grid_scan(P, cx, G, f, P.size_off, P.agg + gridDim.x, s_warp);
       if (blockIdx.x == 0 && threadIdx.x == 0) P.size_off[G] = tot;
     }
     grid_bar(P, cx);
@@ -522,9 +595,9 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
         if (sz == 1) {
           if (check_self) {
             uint2 d = ldg2(P.dep + v);
-            if (d.x == v || d.y == v) atomicMin(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ((unsigned long long)v << 32) | v);
+            if (d.x == v || d.y == v) atomicMax(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ~(((unsigned long long)v << 32) | v));
           }
-          P.order[o] = v;
+          order[o] = v;
         } else P.heavy[atomicAdd(sc + FS_HEAVYN, 1u)] = v;
       }
     }
@@ -536,9 +609,9 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
         const uint32_t base = ldg2(P.size_off + R), end = ldg2(P.size_off + R + 1);
         uint32_t emit = base, top = end;
         P.state[R] = 1;
-        P.order[--top] = R;
+        order[--top] = R;
         while (top < end) {
-          uint32_t v = P.order[top];
+          uint32_t v = order[top];
           uint8_t s = P.state[v];
           if (s <= 2) {
             uint2 dd = ldg2(P.dep + v);
@@ -546,33 +619,33 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
             P.state[v] = s + 1;
             if (d != kNone && ldg2(P.r + d) == R) {
               uint8_t sd = P.state[d];
-              if (sd == 0) { P.state[d] = 1; P.order[--top] = d; }
+              if (sd == 0) { P.state[d] = 1; order[--top] = d; }
               else if (sd < 4) {  // visiting[d]  (topological_sort.rs:34-38)
-                atomicMin(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ((unsigned long long)R << 32) | d);
+                atomicMax(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ~(((unsigned long long)R << 32) | d));
                 break;
               }
             }
-          } else { ++top; P.order[emit++] = v; P.state[v] = 4; }
+          } else { ++top; order[emit++] = v; P.state[v] = 4; }
         }
       }
     }
     grid_bar(P, cx);
-    if (ldg2(sc + FS_ERR_HI) != 0xFFFFFFFFu) return;  // cyclic dependency: the host reports "detected at i=<lo>"
+    if (ldg2(sc + FS_ERR_HI) | ldg2(sc + FS_ERR_LO)) { fused_publish(P); return; }  // cyclic dependency: the host reports "detected at i="
   } else {
-    FUSED_FOR(i, G) P.order[i] = i;
+    FUSED_FOR(i, G) order[i] = i;
   }
   // ================= F10: wire numbering (K6) + gather (K7) =================
   FUSED_FOR(k, G) {
-    const uint32_t g = sorted ? ldg2(P.order + k) : k;
+    const uint32_t g = sorted ? ldg2(order + k) : k;
     const uint4 gt = ldg2(P.gates + g);
     const uint32_t p = kFirstTag | (3u * k);
-    fused_red_min(P.wire + gt.y, p);
-    if (gt.z != gt.y) fused_red_min(P.wire + gt.z, p + 1);
-    if (gt.w != gt.y && gt.w != gt.z) fused_red_min(P.wire + gt.w, p + 2);
+    fused_red_min(wire + gt.y, p);
+    if (gt.z != gt.y) fused_red_min(wire + gt.z, p + 1);
+    if (gt.w != gt.y && gt.w != gt.z) fused_red_min(wire + gt.w, p + 2);
   }
   grid_bar(P, cx);
   FUSED_FOR(nd, NB) {
-    const uint32_t w = ldg2(P.wire + nd);
+    const uint32_t w = ldg2(wire + nd);
     if ((w & kFirstTag) && w != kNone) { uint32_t p = w & ~kFirstTag; atomicOr(P.bitmap + (p >> 5), 1u << (p & 31)); }
   }
   grid_bar(P, cx);
@@ -580,12 +653,12 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   {
     const uint32_t BW = (3 * G + 31) / 32 + 1;
     auto f = [&](uint32_t w) { return (uint32_t)__popc(ldg2(P.bitmap + w)); };
-    n_mid = grid_scan(BW, f, P.bitmap_pre, P.agg + 2 * gridDim.x, 3u, s_warp);
+    n_mid = grid_scan(P, cx, BW, f, P.bitmap_pre, P.agg + 2 * gridDim.x, s_warp);
     if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_NMID] = n_mid;
   }
   grid_bar(P, cx);
   FUSED_FOR(nd, NB) {
-    const uint32_t w = ldg2(P.wire + nd);
+    const uint32_t w = ldg2(wire + nd);
     if (w == kNone) continue;
     uint32_t id;
     if (w & kFirstTag) {
@@ -593,17 +666,21 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
       id = P.n_in + ldg2(P.bitmap_pre + (p >> 5)) + __popc(ldg2(P.bitmap + (p >> 5)) & ((1u << (p & 31)) - 1u));
     } else if (w > kOutBase) id = kInBase - w;               // input: its list position
     else id = P.n_in + n_mid + (kOutBase - w);                // output: after all intermediates
-    P.wire[nd] = id;
+    wire[nd] = id;
   }
   grid_bar(P, cx);
-  if (P.new_gates) {
+  if (new_gates) {
     FUSED_FOR(k, G) {
-      const uint32_t g = sorted ? ldg2(P.order + k) : k;
+      const uint32_t g = sorted ? ldg2(order + k) : k;
       const uint4 gt = ldg2(P.gates + g);
-      P.new_gates[k] = make_uint4(gt.x, ldg2(P.wire + gt.y), ldg2(P.wire + gt.z), ldg2(P.wire + gt.w));
+      new_gates[k] = make_uint4(gt.x, ldg2(wire + gt.y), ldg2(wire + gt.z), ldg2(wire + gt.w));
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_DONE] = 1u;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc[FS_DONE] = 1u;
+    if (P.trace) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); P.trace[126] = t; }
+  }
+  fused_publish(P);
 }
 
 }  // namespace c2a
@@ -614,7 +691,7 @@ extern "C" {
 
 // 0 = never take the fused kernel; otherwise the largest event count it is used for (default: its structural limit)
 static uint64_t g_fused_max_events = (uint64_t)kFusedMaxTiles * kEvTile;
-static uint32_t g_fused_events_per_cta = 4096;
+static uint32_t g_fused_events_per_cta = 1024;  // one event per thread and pass: the phases are latency-bound (measured: 4096 is 10-25 % slower below 100 K gates)
 void c2a_set_fused_limits(uint64_t max_events, uint32_t events_per_cta) {
   g_fused_max_events = std::min<uint64_t>(max_events, (uint64_t)kFusedMaxTiles * kEvTile);
   if (events_per_cta) g_fused_events_per_cta = events_per_cta;
@@ -670,10 +747,10 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     if (!cuda_ok(h, cudaMalloc(&h->ev_buf, stage_need + stage_need / 8 + 4096), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
     h->ev_bytes = stage_need + stage_need / 8 + 4096;
   }
-  if ((4 * n_io + 4096) > h->h_pinned_bytes) {
+  if ((4 * n_io + 8192) > h->h_pinned_bytes) {
     cudaStreamSynchronize(s);
     if (h->h_pinned) cudaFreeHost(h->h_pinned);
-    h->h_pinned_bytes = 4 * n_io + 16384;
+    h->h_pinned_bytes = 4 * n_io + 32768;
     if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
   }
   char* stg = h->ev_buf;
@@ -723,29 +800,52 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   P.heavy = (uint32_t*)A(4 * Gu);
   P.bitmap = (uint32_t*)A(4 * ((3 * Gu + 31) / 32 + 8));
   P.bitmap_pre = (uint32_t*)A(4 * ((3 * Gu + 31) / 32 + 8));
-  // results: straight into the caller's device arrays when they are large enough for the bounds the kernel may reach
-  // (the kernel checks the exact sizes itself before it writes: FS_G / node bound against the capacities)
-  const bool direct = out_on_device;
-  uint32_t* d_order = (direct && io->order_out && io->gates_cap >= Gu) ? io->order_out : (uint32_t*)A(4 * Gu);
-  uint32_t* d_wire = (direct && io->wire_of_node && io->wire_cap >= NBu) ? io->wire_of_node : (uint32_t*)A(4 * NBu);
+  // results: the caller's device arrays are handed to the kernel together with their capacities (it writes them itself once the
+  // exact sizes are known to fit); internal arrays of bound size stand by for host destinations and for capacities that do not fit
   const bool want_new = io->new_gates != nullptr;
-  uint4* d_new = !want_new ? nullptr : ((direct && io->gates_cap >= Gu) ? (uint4*)io->new_gates : (uint4*)A(16 * Gu));
-  char* ctl = (char*)A(4 * FS_COUNT + 64 + 8 * 3 * (size_t)grid);
-  if (!ctl || (want_new && !d_new) || !d_wire || !d_order) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
-  P.order = d_order;
-  P.wire = d_wire;
-  P.new_gates = d_new;
+  const bool user_dev = out_on_device;
+  const bool gates_may_fit = user_dev && io->gates_cap >= 1;
+  P.order_user = (user_dev && io->order_out) ? io->order_out : nullptr;
+  P.new_user = (user_dev && want_new) ? (uint4*)io->new_gates : nullptr;
+  P.wire_user = (user_dev && io->wire_of_node) ? io->wire_of_node : nullptr;
+  P.gates_cap = io->gates_cap;
+  P.wire_cap = io->wire_cap;
+  // (a device caller whose capacities cover the bounds never needs the internal copies; otherwise they are carved - cheap, the slab
+  //  is reused - so that a capacity that turns out too small cannot make the kernel write out of bounds)
+  P.order_int = (P.order_user && io->gates_cap >= Gu) ? P.order_user : (uint32_t*)A(4 * Gu);
+  P.wire_int = (P.wire_user && io->wire_cap >= NBu) ? P.wire_user : (uint32_t*)A(4 * NBu);
+  P.new_int = !want_new ? nullptr : ((P.new_user && io->gates_cap >= Gu) ? P.new_user : (uint4*)A(16 * Gu));
+  (void)gates_may_fit;
+  static const bool want_trace = getenv("C2A_FUSED_TRACE") != nullptr;
+  unsigned long long* d_trace = want_trace ? (unsigned long long*)A(1024) : nullptr;
+  if (!P.order_int || !P.wire_int || (want_new && !P.new_int) || (want_trace && !d_trace)) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  // control block: two halves in the handle, zeroed once; every launch zeroes the half the NEXT launch uses
+  const size_t ctl_half = align256(4 * FS_COUNT + 64 + 8 * 3 * (size_t)h->num_sms);
+  if (!h->fused_ctl) {
+    if (!cuda_ok(h, cudaMalloc(&h->fused_ctl, 2 * ctl_half), "cudaMalloc(fused control)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
+    cudaMemsetAsync(h->fused_ctl, 0, 2 * ctl_half, s);
+    h->fused_parity = 0;
+  }
+  char* ctl = h->fused_ctl + (h->fused_parity ? ctl_half : 0);
   P.sc = (uint32_t*)ctl;
   P.bar = (unsigned int*)(ctl + 4 * FS_COUNT);
   P.agg = (unsigned long long*)(ctl + 4 * FS_COUNT + 64);
+  P.ctl_next = (uint32_t*)(h->fused_ctl + (h->fused_parity ? 0 : ctl_half));
+  P.ctl_words = (uint32_t)(ctl_half / 4);
+  P.trace = d_trace;
+  h->fused_parity ^= 1;
 
-  // ---- enqueue: copies in, one memset, the kernel, copies out; ONE synchronisation
+  // ---- enqueue: (copies in,) the kernel, (copies out); ONE synchronisation.  Scalars come back through mapped pinned memory,
+  // short I/O lists are read by the kernel from pinned memory directly.
   uint32_t* hp = h->h_pinned;
+  P.host_sc = hp;
+  memset(hp, 0, 4 * FS_COUNT);
   if (n_io) {
-    uint32_t* stage = hp + 256;
+    uint32_t* stage = hp + 512;
     if (io->n_in) memcpy(stage, io->input_signals, 4 * (size_t)io->n_in);
     if (io->n_out) memcpy(stage + io->n_in, io->output_signals, 4 * (size_t)io->n_out);
-    cudaMemcpyAsync(d_io, stage, 4 * n_io, cudaMemcpyHostToDevice, s);
+    if (n_io <= 4096) P.io_sigs = stage;  // zero-copy: a few KB over PCIe inside F2
+    else cudaMemcpyAsync(d_io, stage, 4 * n_io, cudaMemcpyHostToDevice, s);
   }
   if (!pk_on_device) {
     phase_begin(h, "h2d");
@@ -753,8 +853,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     if (nw && !cuda_ok(h, cudaMemcpyAsync((void*)P.words, pk->words, 4 * nw, cudaMemcpyHostToDevice, s), "words H2D")) return C2A_ERR_CUDA;
     phase_end(h);
   }
-  cudaMemsetAsync(ctl, 0, 4 * FS_COUNT + 64 + 8 * 3 * (size_t)grid, s);
-  cudaMemsetAsync(P.sc + FS_ERR_LO, 0xFF, 8, s);
+  if (want_trace) cudaMemsetAsync(d_trace, 0, 1024, s);
   phase_begin(h, "k_fused_compile");
   {
     void* args[] = {(void*)&P};
@@ -762,22 +861,37 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     h->launches++;
   }
   phase_end(h);
-  cudaMemcpyAsync(hp, P.sc, 4 * FS_COUNT, cudaMemcpyDeviceToHost, s);
-  // results the caller wants in host memory, or in device arrays smaller than the bounds: copied by capacity (the exact sizes are
-  // only known after the synchronisation; a caller that sized its arrays exactly copies exactly)
-  const uint64_t gcopy = std::min<uint64_t>(io->gates_cap, Gu), wcopy = std::min<uint64_t>(io->wire_cap, NBu);
-  const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
-  phase_begin(h, "d2h");
-  if (io->order_out && d_order != io->order_out && gcopy) cudaMemcpyAsync(io->order_out, d_order, 4 * gcopy, kind, s);
-  if (io->wire_of_node && d_wire != io->wire_of_node && wcopy) cudaMemcpyAsync(io->wire_of_node, d_wire, 4 * wcopy, kind, s);
-  if (want_new && (void*)d_new != (void*)io->new_gates && gcopy) cudaMemcpyAsync(io->new_gates, d_new, 16 * gcopy, kind, s);
-  phase_end(h);
+  if (want_trace) cudaMemcpyAsync(hp + 64, d_trace, 1024, cudaMemcpyDeviceToHost, s);
+  // host destinations: copied by capacity (the exact sizes are only known after the synchronisation; a caller that sized its arrays
+  // exactly copies exactly)
+  if (!out_on_device) {
+    const uint64_t gcopy = std::min<uint64_t>(io->gates_cap, Gu), wcopy = std::min<uint64_t>(io->wire_cap, NBu);
+    phase_begin(h, "d2h");
+    if (io->order_out && gcopy) cudaMemcpyAsync(io->order_out, P.order_int, 4 * gcopy, cudaMemcpyDeviceToHost, s);
+    if (io->wire_of_node && wcopy) cudaMemcpyAsync(io->wire_of_node, P.wire_int, 4 * wcopy, cudaMemcpyDeviceToHost, s);
+    if (want_new && gcopy) cudaMemcpyAsync(io->new_gates, P.new_int, 16 * gcopy, cudaMemcpyDeviceToHost, s);
+    phase_end(h);
+  }
   if (!cuda_ok(h, cudaStreamSynchronize(s), "fused sync")) return C2A_ERR_CUDA;
   if (!cuda_ok(h, cudaGetLastError(), "fused kernel")) return C2A_ERR_CUDA;
   phases_collect(h);
+  if (want_trace) {  // per-barrier timeline of CTA 0 as extra "phases": fused:b<k> = ms between barrier k-1 and k
+    const unsigned long long* tr = (const unsigned long long*)(hp + 64);
+    unsigned long long prev = tr[127];
+    for (unsigned k = 1; k <= tr[0] && k < 120; ++k) {
+      char nm[32];
+      const unsigned long long t = tr[k] & ~(1ull << 63);
+      snprintf(nm, sizeof nm, (tr[k] >> 63) ? "fused:m%02u" : "fused:b%02u", k);
+      h->last_ms.push_back({nm, (double)(t - prev) * 1e-6});
+      prev = t;
+    }
+    if (tr[126]) h->last_ms.push_back({"fused:tail", (double)(tr[126] - prev) * 1e-6});
+    h->last_ms.push_back({"fused:grid", (double)grid});
+  }
 
   const uint32_t G = hp[FS_G], Cn = hp[FS_C], S = hp[FS_S], eflags = hp[FS_EFLAGS];
-  if (eflags || (!hp[FS_DONE] && hp[FS_ERR_HI] == 0xFFFFFFFFu)) {
+  const unsigned long long err_enc = ((unsigned long long)hp[FS_ERR_HI] << 32) | hp[FS_ERR_LO];
+  if (eflags || (!hp[FS_DONE] && !err_enc)) {
     // the reference errors on this stream, or it is not a stream the device path decides itself: the multi-kernel path replays it
     // exactly (same status, same event index).  Nothing of the fused attempt is kept.
     slab_reset(h);
@@ -799,16 +913,18 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   h->emitted.node_count = S + n_eff;
   h->emitted.signal_bound = S;
   h->emitted.wire = nullptr;
-  unsigned long long err = ((unsigned long long)hp[FS_ERR_HI] << 32) | hp[FS_ERR_LO];
-  if (err != ~0ull) {
+  if (err_enc) {
+    const unsigned long long err = ~err_enc;
     if (err_index) *err_index = (uint32_t)err;
     return fail(h, C2A_ERR_CYCLIC_DEPENDENCY, "detected at i=%llu", (unsigned long long)(uint32_t)err);
   }
-  if ((io->order_out || io->new_gates) && io->gates_cap < G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%u)", (unsigned long long)io->gates_cap, G);
-  if (io->wire_of_node && io->wire_cap < S + n_eff + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, S + n_eff + 1);
+  // which wire map the kernel filled (the same rule it applied): needed for the named-wire look-ups that may follow
+  uint32_t* d_wire = (P.wire_user && S + n_eff + 1 <= io->wire_cap) ? P.wire_user : P.wire_int;
   h->emitted.wire = d_wire;
   h->emitted.identity = !(hp[FS_BFLAGS] & (F_OOO | F_SELF));
   if (wire_count) *wire_count = io->n_in + hp[FS_NMID] + io->n_out;
+  if ((io->order_out || io->new_gates) && io->gates_cap < G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%u)", (unsigned long long)io->gates_cap, G);
+  if (io->wire_of_node && io->wire_cap < S + n_eff + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, S + n_eff + 1);
   return C2A_OK;
 }
 

@@ -60,6 +60,9 @@ struct c2a_handle {
     const uint32_t* wire = nullptr;  // wire map of the last successful build on this circuit (device; slab scratch or the caller's array)
     bool identity = true;            // that build's DFS order was 0..G-1
   } emitted;
+  // single-kernel path (c2a_fused.cuh): double-buffered control block (scalars, grid barrier, look-back slots)
+  char* fused_ctl = nullptr;
+  int fused_parity = 0;
   struct c2a_compiler* host_comp = nullptr;  // kept alive when the exact host emitter had to run (sparse ids)
 };
 

@@ -286,6 +286,6 @@ def test_one_cta_and_full_grid_agree(ctx, c2a):
             res.append(ctx.compile_packed(k, w, f, ins, outs))
             assert "k_fused_compile" in ctx.phases()
     finally:
-        c2a.lib.c2a_set_fused_limits(FUSED_MAX, 4096)
+        c2a.lib.c2a_set_fused_limits(FUSED_MAX, 1024)
     for a, b in zip(res[0][1:], res[1][1:]):
         assert np.array_equal(a, b)

@@ -16,7 +16,7 @@ for key in ("same_config",):
               f"launches {x['gpu_launches_per_step']} cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s ratio_e2e {x.get('ratio_e2e_vs_reference')}")
 for name, x in d.get("configs", {}).items():
     print(f"config {name}: {x['gates']} gates value {x['value']/1e6:.1f} M/s ({x['ms_per_step']*1e3:.1f} us) flushed {x['ms_per_step_l2_flushed']*1e3:.1f} us e2e {x['e2e']['value']/1e6:.1f} M/s "
-          f"({x['e2e']['s_per_step']*1e6:.0f} us) sort {x['topo_sort_ms']*1e3:.1f} us {x['topo_hbm_gbs']} GB/s launches {x['gpu_launches_per_step']} cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s {x.get('parity_vs_oracle')}")
+          f"({x['e2e']['s_per_step']*1e6:.0f} us) conc {x.get('value_concurrent', {}).get('value', 0)/1e6:.1f} M/s sort {x['topo_sort_ms']*1e3:.1f} us {x['topo_hbm_gbs']} GB/s launches {x['gpu_launches_per_step']} cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s {x.get('parity_vs_oracle')}")
 for name, x in d.get("variants", {}).items():
     print(f"variant {name}: {x['gates']} gates value {x['value']/1e6:.1f} M/s ({x['ms_per_step']:.3f} ms) sort {x['topo_sort_ms']:.3f} ms cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s fallback {x.get('relax_fallback_rounds')}")
     if "phases_ms" in x:
