@@ -187,7 +187,7 @@ class StagedCircuit:
         self.c2a, self.torch, self.ctx, self.lib, self.h, self.wl = c2a, torch, ctx, c2a.lib, ctx.handle, wl
         ev = np.ascontiguousarray(wl.events)
         self.n_ev = int(ev.shape[0])
-        kinds, words, flags = c2a.pack_events(ev)
+        kinds, words, flags = c2a.pack_events(ev, implicit=True)
         self.p_kinds = torch.from_numpy(kinds).pin_memory()
         self.p_words = torch.from_numpy(words.view(np.int32)).pin_memory()
         self.d_kinds, self.d_words = self.p_kinds.to(dev), self.p_words.to(dev)
@@ -533,8 +533,9 @@ def main():
     ap.add_argument("--sample-chains", type=int, default=37, help="chains in the bounded CPU-reference sample (~20 K gates)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-host-emit", action="store_true", help="skip the host-emitter comparison leg")
-    ap.add_argument("--stream", default="packed", choices=["packed", "aos"],
-                    help="event stream format handed to the emitter: packed (kinds byte + payload words, c2a_emit_packed_*) or 16-byte c2a_event records")
+    ap.add_argument("--stream", default="packed", choices=["packed", "packed6", "aos"],
+                    help="event stream format handed to the emitter: packed (kind byte + payload words with implicit operands, ~4 B/event), "
+                         "packed6 (every gate / connection operand spelled out, 6 B/event) or 16-byte c2a_event records")
     ap.add_argument("--no-pipelined", action="store_true", help="skip the two-circuits-in-flight e2e leg")
     ap.add_argument("--no-from-source", action="store_true", help="skip the .circom-text-to-circuit leg")
     ap.add_argument("--source-chains", type=int, default=0, help="MiMC chains of the from_source leg (default: --chains, the headline workload)")
@@ -609,11 +610,11 @@ def main():
     wl = c2a.workloads.mimc_chains(args.chains, rounds=args.rounds, variant=args.variant)
     dev = torch.device("cuda", local_rank)
     from circom_2_arithc_b200._lib import PackedEvents
-    packed = args.stream == "packed"
+    packed = args.stream in ("packed", "packed6")
     ev_np = np.ascontiguousarray(wl.events)
     n_ev = int(ev_np.shape[0])
-    if packed:   # the walker's output, host side: kinds byte + payload words (c2a_program_packed / c2a_pack_events)
-        kinds_np, words_np, pk_flags = c2a.pack_events(ev_np)
+    if packed:   # the walker's output, host side: kinds byte + payload words (c2a_program_packed / c2a_pack_events_ex)
+        kinds_np, words_np, pk_flags = c2a.pack_events(ev_np, implicit=(args.stream == "packed"))
         p_kinds = torch.from_numpy(kinds_np).pin_memory()
         p_words = torch.from_numpy(words_np.view(np.int32)).pin_memory()
         d_kinds, d_words = p_kinds.to(dev), p_words.to(dev)
@@ -1082,8 +1083,9 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name, "gates_per_gpu": int(G), "node_bound": int(nb), "n_inputs": int(len(in_ids)), "n_outputs": int(len(out_ids)),
                    "events_per_gpu": n_ev,
-                   "stream_format": ("packed: 1 kind byte per event + u32 payload words (3 per gate, 2 per connection; dense signal ids implicit), %.2f B/event"
-                                     % (stream_bytes / n_ev)) if packed else "c2a_event records, 16 B/event", "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
+                   "stream_format": ("packed: 1 kind byte per event + u32 payload words (dense signal ids implicit%s), %.2f B/event"
+                                     % ("; the operand a gate / connection derives from the signal declared last carries no word" if (pk_flags & 2) else
+                                        "; 3 words per gate, 2 per connection", stream_bytes / n_ev)) if packed else "c2a_event records, 16 B/event", "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
                    "boruvka_rounds": int(info.rounds), "order_is_identity": n_identity,
                    "l2": "inputs larger than L2 (event stream %.0f MB, gate array %.0f MB, node arrays %.0f MB each vs 126 MB L2); no flush" % (stream_bytes / 1e6, 16 * G / 1e6, 4 * nb / 1e6),
                    "value_scope": "event stream resident in HBM -> c2a_emit_packed_resident / c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "

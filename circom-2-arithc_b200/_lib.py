@@ -115,6 +115,7 @@ _SIGS = {
     "c2a_emitted_signal_wires_device": (i32, [vp, vp, u64, vp]),
     "c2a_rebase_wire_ids_gathered_device": (i32, [vp, vp, u64, vp, u32, u32]),
     "c2a_pack_events": (u64, [vp, u64, vp, vp, u32p]),
+    "c2a_pack_events_ex": (u64, [vp, u64, u32, vp, vp, u32p]),
     "c2a_unpack_events": (i32, [vp, vp]),
     "c2a_emit_packed_device": (i32, [vp, vp, vp, u64p]),
     "c2a_emit_packed_resident": (i32, [vp, vp, vp, u64p]),

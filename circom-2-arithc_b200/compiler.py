@@ -47,15 +47,20 @@ def _ptr(a: Optional[np.ndarray]):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def pack_events(events: np.ndarray):
-    """c2a_pack_events: AoS events -> (kinds u8[n], words u32[n_words], flags)."""
+PACKED_DENSE_IDS, PACKED_IMPLICIT_OPERANDS = 1, 2
+
+
+def pack_events(events: np.ndarray, implicit: bool = False):
+    """c2a_pack_events[_ex]: AoS events -> (kinds u8[n], words u32[n_words], flags).  implicit=True also drops the operand the
+    walker derives from the signal it declared last (C2A_PACKED_IMPLICIT_OPERANDS: 4 B/event instead of 6 on a walker stream)."""
     ev = np.ascontiguousarray(events)
     n = ev.shape[0]
     flags = C.c_uint32(0)
-    nw = int(lib.c2a_pack_events(_ptr(ev), n, None, None, C.byref(flags)))
+    allow = PACKED_DENSE_IDS | (PACKED_IMPLICIT_OPERANDS if implicit else 0)
+    nw = int(lib.c2a_pack_events_ex(_ptr(ev), n, allow, None, None, C.byref(flags)))
     kinds = np.empty(n, dtype=np.uint8)
     words = np.empty(nw, dtype=np.uint32)
-    lib.c2a_pack_events(_ptr(ev), n, _ptr(kinds), _ptr(words), C.byref(flags))
+    lib.c2a_pack_events_ex(_ptr(ev), n, allow, _ptr(kinds), _ptr(words), C.byref(flags))
     return kinds, words, int(flags.value)
 
 

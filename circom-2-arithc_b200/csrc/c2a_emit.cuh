@@ -40,7 +40,7 @@ namespace c2a {
 constexpr int kEvTile = 1024;  // events per CTA pass: 8 warps x 4 rows x 32 lanes
 constexpr int kSpecMsf = 2;    // Boruvka rounds enqueued without looking at the live-edge count
 // ES_MC0 + 2r / + 2r + 1: candidate / live counts of speculative round r (zeroed once); ES_NCUR / ES_NCAND: the host-driven rounds
-enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_PREV = 7, ES_ROUNDS = 8, ES_IOBAD = 9,
+enum { ES_NGATE = 0, ES_NCONN = 1, ES_SBOUND = 2, ES_FLAGS = 3, ES_NCUR = 4, ES_NCAND = 5, ES_NDECL = 6, ES_PREV = 7, ES_ROUNDS = 8, ES_IOBAD = 9, ES_NIMPL = 10,
        ES_MC0 = 16, ES_COUNT = 32 };
 enum { EF_BAD_KIND = 1, EF_BAD_OP = 2, EF_DUPLICATE = 4, EF_UNKNOWN_REF = 8, EF_CONST_CONST = 16, EF_OUT_OUT = 32, EF_SPARSE = 64, EF_BAD_IO = 128,
        EF_CAP = 256 /* a signal id beyond the table bound the pass was launched with: rerun with the exact bound */ };
@@ -169,8 +169,10 @@ __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__
 // Same ranks, same scatter targets.  The count pass only reads the kind bytes (1 B per event instead of 16); the payload of a
 // tile is one contiguous word range [3*g0 + 2*c0 (+ s0), ...) known from the scanned tile counts, so the scatter stages it in
 // shared memory with coalesced loads issued together with the kind loads.
-__global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__ kinds, uint64_t n, uint32_t tiles, uint32_t* __restrict__ tile_g,
-                                                     uint32_t* __restrict__ tile_c, uint32_t* __restrict__ es) {
+// implicit != 0 (C2A_PACKED_IMPLICIT_OPERANDS): bit 7 of a gate / connection byte = "one operand is the signal declared last, no
+// payload word for it"; tile_i counts those events (payload words of a tile = 3 g + 2 c - i).
+__global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__ kinds, uint64_t n, uint32_t tiles, uint32_t implicit, uint32_t* __restrict__ tile_g,
+                                                     uint32_t* __restrict__ tile_c, uint32_t* __restrict__ tile_i, uint32_t* __restrict__ es) {
   // one WARP per 1024-event tile: two coalesced 128-bit loads per lane, no block-level synchronisation
   const int lane = threadIdx.x & 31;
   const uint32_t nwarps = gridDim.x * (kBlock / 32);
@@ -192,24 +194,31 @@ __global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__
         }
       }
     }
-    uint32_t g = 0, c = 0;
+    uint32_t g = 0, c = 0, im = 0;
+    const uint32_t opmask = implicit ? 31u : 63u;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const uint32_t lo = w[q] & 0x01010101u, hi = (w[q] >> 1) & 0x01010101u;  // kind bit 0 / bit 1 of each byte
-      const uint32_t is_g = hi & ~lo, is_c = hi & lo;
+      const uint32_t is_g = hi & ~lo, is_c = hi & lo, b7 = (w[q] >> 7) & 0x01010101u;
       g += __popc(is_g);
       c += __popc(is_c);
-      // op field (bits 2..7 of each byte): must be < 20 on a gate, 0 elsewhere (c2a_pack_events marks an invalid kind that way)
+      if (implicit) {
+        im += __popc(b7 & hi);
+        if (b7 & ~hi) f |= EF_BAD_KIND;  // the flag on a signal declaration
+      }
+      // op field (bits 2..7 of each byte, 2..6 with implicit operands): must be < 20 on a gate, 0 elsewhere (c2a_pack_events marks
+      // an invalid kind that way)
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        uint32_t kb = (w[q] >> (8 * j)) & 0xFFu, op = kb >> 2;
+        uint32_t kb = (w[q] >> (8 * j)) & 0xFFu, op = (kb >> 2) & opmask;
         if ((kb & 3u) == C2A_EV_GATE) { if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
         else if (op) f |= EF_BAD_KIND;
       }
     }
     g = warp_sum(g);
     c = warp_sum(c);
-    if (lane == 0) { tile_g[tile] = g; tile_c[tile] = c; }
+    if (implicit) im = warp_sum(im);
+    if (lane == 0) { tile_g[tile] = g; tile_c[tile] = c; if (implicit) tile_i[tile] = im; }
   }
   f = warp_or(f);
   if (lane == 0 && f) atomicOr(es + ES_FLAGS, f);
@@ -225,17 +234,23 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint3
 // bytes and the payload word range of its next tile are already in flight.  One elected thread computes the (16-byte aligned)
 // ranges from the scanned tile counts and issues the copies; everybody waits on the stage's mbarrier.
 constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words per event) + alignment slack
-__global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+// kMode 0: every operand spelled out.  C2A_PACKED_IMPLICIT_OPERANDS (tile_i non-null) launches BOTH other instantiations back to
+// back; each looks at the scanned totals and exits at once unless the stream is its kind:
+// kMode 2: every gate and connection is flagged (what the walker emits) - the third rank is the sum of the other two, a gate has 2
+//          payload words and a connection 1, nothing per event has to be tested;  kMode 1: flagged and unflagged events mixed.
+template <int kMode>
+__global__ void __launch_bounds__(kBlock, 7) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
-                                                       const uint32_t* __restrict__ tile_c, uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
+                                                       const uint32_t* __restrict__ tile_c, const uint32_t* __restrict__ tile_i /* null: no implicit operands */,
+                                                       uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
                                                        uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
                                                        uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint8_t* __restrict__ outmark,
                                                        uint32_t* __restrict__ es) {
   __shared__ __align__(16) uint32_t s_w[2][kPkWordsCap];
   __shared__ __align__(16) uint8_t s_k[2][kEvTile];
   __shared__ __align__(8) unsigned long long s_bar[2];
-  __shared__ uint32_t s_meta[2][8];  // g0, c0, s0, first payload word - aligned start, words staged, kind bytes staged, #gates, #connections
-  __shared__ uint32_t s_g[8], s_c[8];
+  __shared__ uint32_t s_meta[2][10];  // g0, c0, s0, first payload word - aligned start, words staged, kind bytes staged, #gates, #connections, i0, #implicit
+  __shared__ uint32_t s_g[8], s_c[8], s_i[8];
   __shared__ uint32_t s_list[kEvTile];  // the tile's events filed by kind (phase A -> phase B)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -250,10 +265,16 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
   __syncthreads();
 
   // producer side (thread 0 only): counts of a tile -> ranges -> bulk copies into `stage`
-  auto issue = [&](uint32_t tile, int stage, uint4 cnt) {  // cnt = {g0, c0, g1, c1}
+  constexpr bool implicit = kMode != 0;
+  if (implicit) {
+    const bool all_flagged = __ldg(tile_i + tiles) == __ldg(tile_g + tiles) + __ldg(tile_c + tiles);
+    if (all_flagged != (kMode == 2)) return;  // the other instantiation's stream
+  }
+  auto issue = [&](uint32_t tile, int stage, uint4 cnt, uint2 ci) {  // cnt = {g0, c0, g1, c1}, ci = {i0, i1}
+    if (kMode == 2) ci = make_uint2(cnt.x + cnt.y, cnt.z + cnt.w);  // every gate and connection is flagged
     const uint64_t tbase = (uint64_t)tile * kEvTile, tend = min(n, tbase + kEvTile);
     const uint32_t s0 = (uint32_t)tbase - cnt.x - cnt.y, s1 = (uint32_t)tend - cnt.z - cnt.w;
-    const uint64_t w0 = 3ull * cnt.x + 2ull * cnt.y + (dense ? 0u : s0), w1 = 3ull * cnt.z + 2ull * cnt.w + (dense ? 0u : s1);
+    const uint64_t w0 = 3ull * cnt.x + 2ull * cnt.y - ci.x + (dense ? 0u : s0), w1 = 3ull * cnt.z + 2ull * cnt.w - ci.y + (dense ? 0u : s1);
     uint64_t a0 = w0 & ~3ull, a1 = min((w1 + 3) & ~3ull, n_words & ~3ull);
     if (a1 < a0 || !tma_ok || a1 - a0 > (uint64_t)kPkWordsCap) a1 = a0;       // (a corrupt count pair cannot overrun the stage)
     const uint32_t wbytes = (uint32_t)(a1 - a0) * 4u;
@@ -261,6 +282,7 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     s_meta[stage][0] = cnt.x; s_meta[stage][1] = cnt.y; s_meta[stage][2] = s0;
     s_meta[stage][3] = (uint32_t)(w0 - a0); s_meta[stage][4] = (uint32_t)(a1 - a0); s_meta[stage][5] = kbytes;
     s_meta[stage][6] = min(cnt.z - cnt.x, (uint32_t)kEvTile); s_meta[stage][7] = min(cnt.w - cnt.y, (uint32_t)kEvTile);
+    s_meta[stage][8] = ci.x; s_meta[stage][9] = min(ci.y - ci.x, (uint32_t)kEvTile);
     uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was last read through the generic proxy
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + kbytes) : "memory");
@@ -268,12 +290,14 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     if (kbytes) bulk_g2s(&s_k[stage][0], kinds + tbase, kbytes, &s_bar[stage]);
   };
   auto load_counts = [&](uint32_t tile) { return make_uint4(__ldg(tile_g + tile), __ldg(tile_c + tile), __ldg(tile_g + tile + 1), __ldg(tile_c + tile + 1)); };
+  auto load_ci = [&](uint32_t tile) { return kMode == 1 ? make_uint2(__ldg(tile_i + tile), __ldg(tile_i + tile + 1)) : make_uint2(0u, 0u); };
 
   uint4 next_cnt = make_uint4(0, 0, 0, 0);
+  uint2 next_ci = make_uint2(0, 0);
   uint32_t tile = blockIdx.x;
   if (threadIdx.x == 0 && tile < tiles) {
-    issue(tile, 0, load_counts(tile));
-    if (tile + gridDim.x < tiles) next_cnt = load_counts(tile + gridDim.x);
+    issue(tile, 0, load_counts(tile), load_ci(tile));
+    if (tile + gridDim.x < tiles) { next_cnt = load_counts(tile + gridDim.x); next_ci = load_ci(tile + gridDim.x); }
   }
   uint32_t f = 0, smax = 0;
   for (uint32_t it = 0; tile < tiles; tile += gridDim.x, ++it) {
@@ -281,8 +305,8 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     if (threadIdx.x == 0) {
       const uint32_t nt = tile + gridDim.x;
       if (nt < tiles) {
-        issue(nt, stage ^ 1, next_cnt);
-        if (nt + gridDim.x < tiles) next_cnt = load_counts(nt + gridDim.x);  // consumed one iteration later
+        issue(nt, stage ^ 1, next_cnt, next_ci);
+        if (nt + gridDim.x < tiles) { next_cnt = load_counts(nt + gridDim.x); next_ci = load_ci(nt + gridDim.x); }  // consumed one iteration later
       }
     }
     {  // wait for this stage's bytes
@@ -292,9 +316,10 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     }
     const uint32_t g0 = s_meta[stage][0], c0 = s_meta[stage][1], s0 = s_meta[stage][2], woff = s_meta[stage][3], wcov = s_meta[stage][4], kcov = s_meta[stage][5];
     const uint32_t ng = s_meta[stage][6], nc = s_meta[stage][7];  // gates / connections in this tile
+    const uint32_t i0 = s_meta[stage][8], ni = s_meta[stage][9];  // implicit-operand events before / in this tile
     const uint64_t tbase = (uint64_t)tile * kEvTile;
     const uint32_t nev = (uint32_t)(min(n, tbase + kEvTile) - tbase);
-    const uint64_t w0 = 3ull * g0 + 2ull * c0 + (dense ? 0u : s0);
+    const uint64_t w0 = 3ull * g0 + 2ull * c0 - i0 + (dense ? 0u : s0);
     auto word = [&](uint32_t wl) -> uint32_t {  // payload word wl of this tile: staged, or (unaligned source / stream tail) straight from global
       uint32_t k = wl + woff;
       if (k < wcov) return s_w[stage][k];
@@ -303,8 +328,11 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
     // ---- phase A, one lane per event: rank the event inside the tile and file it under its kind.
     // s_list = [gates | connections | signals]; entry = local event index | (a second rank << 10): together with the entry's own
     // position they give all three in-tile ranks (dg + dc + ds = local index), hence the payload offset 3*dg + 2*dc (+ ds).
-    uint32_t kb[4], gm[4], cm[4];
-    uint32_t wg = 0, wc = 0;
+    // a walker stream flags EVERY gate and connection: then the third rank is the sum of the other two and need not be counted
+    constexpr bool all_impl = kMode == 2;
+    constexpr bool mixed = kMode == 1;
+    uint32_t kb[4], gm[4], cm[4], im[4];
+    uint32_t wg = 0, wc = 0, wi = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       uint32_t k = warp * 128 + j * 32 + lane;
@@ -313,24 +341,29 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
       cm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_CONNECT);
       wg += __popc(gm[j]);
       wc += __popc(cm[j]);
+      if (mixed) { im[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 0x82u) == 0x82u); wi += __popc(im[j]); }  // bit 7 on a gate / connection
+      else im[j] = 0;
     }
-    if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; }
+    if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; s_i[warp] = wi; }
     __syncthreads();
-    uint32_t dg = 0, dc = 0;  // in-tile ranks
+    uint32_t dg = 0, dc = 0, di = 0;  // in-tile ranks
     for (int w = 0; w < warp; ++w) { dg += s_g[w]; dc += s_c[w]; }
+    if (mixed) for (int w = 0; w < warp; ++w) di += s_i[w];
     // (this loop is the hot spot of an issue-bound kernel: one select-built shared-memory store for gates and connections,
     //  one predicated 8-byte store for a dense signal, no per-event bounds checks or reductions)
     if (dense && threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t k = warp * 128 + j * 32 + lane;
-      const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
+      const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt), my_di = di + __popc(im[j] & lt);
       dg += __popc(gm[j]);
       dc += __popc(cm[j]);
+      di += __popc(im[j]);
       const bool is_g = (gm[j] >> lane) & 1u, is_c = (cm[j] >> lane) & 1u;
       const uint32_t ds = k - my_dg - my_dc;
       if (is_g | is_c) {  // (both masks exclude lanes past the end of the stream)
-        s_list[min(is_g ? my_dg : ng + my_dc, (uint32_t)kEvTile - 1)] = k | ((is_g ? my_dc : my_dg) << 10);
+        // entry: local event index | the rank under the other kind << 10 | the rank among implicit-operand events << 20
+        s_list[min(is_g ? my_dg : ng + my_dc, (uint32_t)kEvTile - 1)] = k | ((is_g ? my_dc : my_dg) << 10) | (my_di << 20);
       } else if (k < nev) {
         const uint32_t cbit = (kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u;
         // dense ids: the id IS the declaration rank (< n <= S_cap) - the record is complete right here, lanes holding signals write
@@ -352,10 +385,12 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
       // panic) is the local test id < #signals declared before this event, so the E2 kernels, the event-time arrays and the
       // declaration table are not needed at all; out-of-range references are flagged and neutralised right here.
       for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
-        uint32_t e = s_list[r], k = e & 1023u, my_dc = e >> 10;
+        uint32_t e = s_list[r], k = e & 1023u, my_dc = (e >> 10) & 1023u, my_di = all_impl ? r + my_dc : e >> 20;
         uint32_t ds = k - r - my_dc;
-        uint32_t wl = 3u * r + 2u * my_dc + (dense ? 0u : ds);
-        uint4 gt = make_uint4(K(k) >> 2, W(wl), W(wl + 1), W(wl + 2));
+        uint32_t wl = 3u * r + 2u * my_dc - my_di + (dense ? 0u : ds);
+        const uint32_t kbyte = K(k);
+        const bool im_out = all_impl || (implicit && (kbyte & 0x80u));  // out = the signal declared last (dense ids: its id is its rank)
+        uint4 gt = make_uint4(implicit ? (kbyte >> 2) & 31u : kbyte >> 2, W(wl), W(wl + 1), im_out ? s0 + ds - 1u : W(wl + 2));
         if (dense) {
           const uint32_t before = s0 + ds;
           if (gt.y < before && gt.z < before && gt.w < before) outmark[gt.w] = 1;  // compiler.rs:201 marks the out node is_out
@@ -364,10 +399,11 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
         egates[g0 + r] = gt;
       }
       for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
-        uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = e >> 10;
+        uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_di = all_impl ? my_dg + r : e >> 20;
         uint32_t ds = k - my_dg - r;
-        uint32_t wl = 3u * my_dg + 2u * r + (dense ? 0u : ds);
-        uint2 ab = make_uint2(W(wl), W(wl + 1));
+        uint32_t wl = 3u * my_dg + 2u * r - my_di + (dense ? 0u : ds);
+        const bool im_a = all_impl || (implicit && (K(k) & 0x80u));  // a = the signal declared last
+        uint2 ab = im_a ? make_uint2(s0 + ds - 1u, W(wl)) : make_uint2(W(wl), W(wl + 1));
         if (dense) {
           if (!(ab.x < s0 + ds && ab.y < s0 + ds)) { f |= EF_UNKNOWN_REF; ab = make_uint2(0, 0); }
         } else conn_t[c0 + r] = (uint32_t)tbase + k;
@@ -391,7 +427,7 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter(const uint8_t* __restr
         }
       }
     };
-    const uint32_t wn = 3u * ng + 2u * nc + (dense ? 0u : nev - min(nev, ng + nc));  // payload words of the tile
+    const uint32_t wn = 3u * ng + 2u * nc - ni + (dense ? 0u : nev - min(nev, ng + nc));  // payload words of the tile
     if (kcov == nev && woff + wn <= wcov && ng + nc <= nev) phase_b(std::true_type{});
     else phase_b(std::false_type{});
     __syncthreads();  // the stage (and s_g / s_c) may be refilled from the next iteration on
@@ -801,6 +837,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   const c2a_event* ev_dev = src.ev_dev;
   const c2a_packed_events* pk = src.pk;
   const bool pk_dense = pk && (pk->flags & C2A_PACKED_DENSE_IDS);
+  const bool pk_impl = pk_dense && (pk->flags & C2A_PACKED_IMPLICIT_OPERANDS);  // bit 7 of a gate / connection byte: one operand is implicit
   int st = check_sizes(h, n, 1);
   if (st) return st;
   if (n && !ev_host && !ev_dev && !pk) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null event array");
@@ -834,10 +871,11 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     // Dense packed stream: S = n - G - C and n_words = 3G + 2C give S <= n - n_words/3 and C <= n_words/2 BEFORE anything is
     // counted, so the union-find arrays can be carved (here, in the staging allocation) and initialised on the side stream
     // while the count / scatter kernels run; the main stream joins just before the first Boruvka kernel.
+    // (with implicit operands a connection may carry a single word: C <= n_words; S <= n - n_words/3 holds either way)
     const uint64_t S_side = pk_dense ? n - (pk->n_words + 2) / 3 + 1 : 0;
-    const uint64_t effw_side = pk_dense ? pk->n_words / 64 + 4 : 0;
+    const uint64_t effw_side = pk_dense ? pk->n_words / (pk_impl ? 32 : 64) + 4 : 0;
     const size_t side_bytes = pk_dense ? 3 * align256(4 * S_side) + 2 * align256(4 * effw_side) : 0;
-    const size_t ev_need = side_bytes + ev_copy + 2 * align256(4 * ((size_t)tiles + 2)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
+    const size_t ev_need = side_bytes + ev_copy + 3 * align256(4 * ((size_t)tiles + 2)) + align256(8 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
                            align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
     if (ev_need > h->ev_bytes) {
       if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
@@ -850,7 +888,9 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     const uint32_t ctiles = scan_tiles((uint64_t)tiles + 1, kScanItems);
     uint32_t* tile_g = (uint32_t*)take(4 * ((size_t)tiles + 2));
     uint32_t* tile_c = (uint32_t*)take(4 * ((size_t)tiles + 2));
+    uint32_t* tile_i = (uint32_t*)take(4 * ((size_t)tiles + 2));
     unsigned long long* cnt_state = (unsigned long long*)take(16 * ((size_t)ctiles + 1));  // look-back states of the two count scans
+    unsigned long long* cnt_state_i = (unsigned long long*)take(8 * ((size_t)ctiles + 1));  // ... and of the implicit-operand counts
     es = (uint32_t*)take(4 * ES_COUNT);
     sig_t = (uint32_t*)take(4 * S_cap);
     sig_meta = (uint2*)take(8 * S_cap);
@@ -890,6 +930,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     }
     phase_begin(h, "init");
     cudaMemsetAsync(cnt_state, 0, 16 * ((size_t)ctiles + 1), s);
+    if (pk_impl) cudaMemsetAsync(cnt_state_i, 0, 8 * ((size_t)ctiles + 1), s);
     cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
     if (!pk_dense) cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
     cudaMemsetAsync(outmark, 0, pk_dense ? std::min<uint64_t>(S_cap, n + 1) : S_cap, s);
@@ -897,21 +938,28 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     if (tiles) {
       const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
       phase_begin(h, "k_ev_count");
-      if (pk) LAUNCH(h, k_pk_count, egrid, kBlock, d_kinds, n, tiles, tile_g, tile_c, es);
+      if (pk) LAUNCH(h, k_pk_count, egrid, kBlock, d_kinds, n, tiles, pk_impl ? 1u : 0u, tile_g, tile_c, tile_i, es);
       else LAUNCH(h, k_ev_count, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_count, kBlock, n)), kBlock, d_ev, n, tiles, tile_g, tile_c, es);
       phase_end(h);
       phase_begin(h, "k_scan_u32");
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
+      if (pk_impl) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_i, tile_i, tiles, cnt_state_i, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
-      if (pk) LAUNCH(h, k_pk_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta,
+      if (pk && pk_impl) {
+        LAUNCH(h, k_pk_scatter_t<2>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es);
+        LAUNCH(h, k_pk_scatter_t<1>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es);
+      } else if (pk) LAUNCH(h, k_pk_scatter_t<0>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<0>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)nullptr, sig_t, sig_meta,
                      egates, gate_t, conn, conn_t, conn_sb, outmark, es);
       else LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_scatter, kBlock, n)), kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
       cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
       cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
+      if (pk_impl) cudaMemcpyAsync(es + ES_NIMPL, tile_i + tiles, 4, cudaMemcpyDeviceToDevice, s);
     }
     cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
     if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
@@ -921,7 +969,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     S = hp[ES_SBOUND];
     flags = hp[ES_FLAGS];
     n_sig = n - G - C;
-    if (pk && !(flags & EF_BAD_KIND) && pk->n_words != 3 * G + 2 * C + (pk_dense ? 0 : n_sig))
+    const uint64_t n_impl = pk_impl ? hp[ES_NIMPL] : 0;
+    if (pk && !(flags & EF_BAD_KIND) && pk->n_words != 3 * G + 2 * C - n_impl + (pk_dense ? 0 : n_sig))
       return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words (%llu) does not match the kinds (%llu gates, %llu connections, %llu signals)",
                   (unsigned long long)pk->n_words, (unsigned long long)G, (unsigned long long)C, (unsigned long long)n_sig);
     if (!(flags & (EF_BAD_KIND | EF_SPARSE)) && (uint64_t)S > 4 * n_sig + (1u << 20)) flags |= EF_SPARSE;  // a dense table would be mostly holes

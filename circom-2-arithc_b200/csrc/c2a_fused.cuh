@@ -31,6 +31,7 @@ namespace c2a {
 
 constexpr int kFusedBlock = 1024;
 constexpr uint32_t kFusedMaxTiles = 4096;                 // 4 M events: the tile-count scan lives in shared memory
+constexpr size_t kFusedSmem = 3 * 4 * (size_t)kFusedMaxTiles;  // dynamic shared memory of the kernel
 constexpr uint32_t kInBase = 0x7FFFFFFEu;                 // wire[] tag of input list position i:  kInBase - i   (> kOutBase)
 constexpr uint32_t kOutBase = 0x3FFFFFFFu;                // wire[] tag of output list position j: kOutBase - j  (outputs override inputs)
 constexpr uint32_t kOutFloor = 0x20000000u;
@@ -42,11 +43,12 @@ struct FusedParams {
   const uint8_t* kinds;
   const uint32_t* words;
   uint32_t n, n_words, tiles;
+  uint32_t implicit;        // C2A_PACKED_IMPLICIT_OPERANDS: bit 7 of a gate / connection byte = one operand is the signal declared last
   const uint32_t* io_sigs;  // n_in input signal ids, then n_out output signal ids (device)
   uint32_t n_in, n_out;
   uint32_t G_ub, C_ub, S_ub, NB_ub;
   // emit scratch
-  uint32_t *tile_g, *tile_c;
+  uint32_t *tile_g, *tile_c, *tile_i;
   uint2* sig_meta;
   uint4* egates;
   uint2* conn;
@@ -228,8 +230,11 @@ __device__ __forceinline__ void fused_publish(const FusedParams& P) {
 }
 
 __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedParams P) {
-  __shared__ uint32_t s_tg[kFusedMaxTiles], s_tc[kFusedMaxTiles];  // exclusive tile prefixes (gates, connections)
-  __shared__ uint32_t s_warp[33], s_wg[33], s_wc[33];
+  extern __shared__ uint32_t s_dyn[];  // 3 x kFusedMaxTiles: exclusive tile prefixes of the gates, connections, implicit-operand events
+  uint32_t* const s_tg = s_dyn;
+  uint32_t* const s_tc = s_dyn + kFusedMaxTiles;
+  uint32_t* const s_ti = s_dyn + 2 * kFusedMaxTiles;
+  __shared__ uint32_t s_warp[33], s_wg[33], s_wc[33], s_wi[33];
   FusedCtx cx;
   cx.epoch = 0;
   cx.nbar = 0;
@@ -258,7 +263,8 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
     const bool aligned = !(reinterpret_cast<uintptr_t>(P.kinds) & 15);
     for (uint32_t tile = blockIdx.x * (kFusedBlock / 32) + warp; tile < P.tiles; tile += nwarps) {
       const uint32_t tbase = tile * kEvTile;
-      uint32_t g = 0, c = 0;
+      uint32_t g = 0, c = 0, im = 0;
+      const uint32_t opmask = P.implicit ? 31u : 63u;
       uint32_t wd[8];
       if (aligned && tbase + kEvTile <= n) {  // two 128-bit loads per lane, both in flight
         const uint4 x = *(reinterpret_cast<const uint4*>(P.kinds + tbase) + lane), y = *(reinterpret_cast<const uint4*>(P.kinds + tbase + 512) + lane);
@@ -279,16 +285,22 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
         const uint32_t lo = wd[q] & 0x01010101u, hi = (wd[q] >> 1) & 0x01010101u;  // kind bit 0 / bit 1 of each byte
         g += __popc(hi & ~lo);
         c += __popc(hi & lo);
+        if (P.implicit) {
+          const uint32_t b7 = (wd[q] >> 7) & 0x01010101u;
+          im += __popc(b7 & hi);
+          if (b7 & ~hi) f |= EF_BAD_KIND;
+        }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const uint32_t kb = (wd[q] >> (8 * j)) & 0xFFu, op = kb >> 2;
+          const uint32_t kb = (wd[q] >> (8 * j)) & 0xFFu, op = (kb >> 2) & opmask;
           if ((kb & 3u) == C2A_EV_GATE) { if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
           else if (op) f |= EF_BAD_KIND;
         }
       }
       g = warp_sum(g);
       c = warp_sum(c);
-      if (lane == 0) { P.tile_g[tile] = g; P.tile_c[tile] = c; }
+      im = warp_sum(im);
+      if (lane == 0) { P.tile_g[tile] = g; P.tile_c[tile] = c; P.tile_i[tile] = im; }
     }
     f = warp_or(f);
     if (lane == 0 && f) atomicOr(sc + FS_EFLAGS, f);
@@ -296,29 +308,32 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   grid_bar(P, cx);
 
   // ================= F1: tile-count scan in shared memory (every CTA), then rank + scatter =================
-  uint32_t G, C, S;
+  uint32_t G, C, S, I;
   {
     constexpr uint32_t per = kFusedMaxTiles / kFusedBlock;  // 4 tiles per thread
-    uint32_t lg[per], lc[per], sg = 0, scn = 0;
+    uint32_t lg[per], lc[per], li[per], sg = 0, scn = 0, si = 0;
 #pragma unroll
     for (uint32_t j = 0; j < per; ++j) {
       uint32_t t = threadIdx.x * per + j;
       lg[j] = t < P.tiles ? ldg2(P.tile_g + t) : 0u;
       lc[j] = t < P.tiles ? ldg2(P.tile_c + t) : 0u;
+      li[j] = t < P.tiles ? ldg2(P.tile_i + t) : 0u;
       sg += lg[j];
       scn += lc[j];
+      si += li[j];
     }
-    uint32_t totg = 0, totc = 0;
+    uint32_t totg = 0, totc = 0, toti = 0;
     uint32_t eg = block_excl_scan(sg, s_warp, &totg);
     uint32_t ec = block_excl_scan(scn, s_warp, &totc);
+    uint32_t ei = block_excl_scan(si, s_warp, &toti);
 #pragma unroll
     for (uint32_t j = 0; j < per; ++j) {
       uint32_t t = threadIdx.x * per + j;
-      s_tg[t] = eg; s_tc[t] = ec;
-      eg += lg[j]; ec += lc[j];
+      s_tg[t] = eg; s_tc[t] = ec; s_ti[t] = ei;
+      eg += lg[j]; ec += lc[j]; ei += li[j];
     }
     __syncthreads();
-    G = totg; C = totc; S = n - G - C;
+    G = totg; C = totc; S = n - G - C; I = toti;
   }
   trace_mark(P, cx);
   // results go straight into the caller's arrays when they hold G entries (every CTA derives the same verdict)
@@ -327,7 +342,7 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   uint4* const new_gates = (P.new_user && gates_fit) ? P.new_user : P.new_int;
   uint32_t* wire = P.wire_int;  // chosen in F5, when the node bound is known
   // the counts decide everything downstream: every CTA derives the same verdict from the same numbers
-  const bool words_ok = (unsigned long long)P.n_words == 3ull * G + 2ull * C;
+  const bool words_ok = (unsigned long long)P.n_words + I == 3ull * G + 2ull * C;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc[FS_G] = G; sc[FS_C] = C; sc[FS_S] = S;
     if (!words_ok) atomicOr(sc + FS_EFLAGS, (uint32_t)EF_CAP);  // n_words does not match the kinds: the host reports it
@@ -339,28 +354,29 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
       const uint32_t tbase = tile * kEvTile, k = threadIdx.x, i = tbase + k;
       const uint32_t kb = i < n ? (uint32_t)P.kinds[i] : 0x100u;
       const bool is_g = kb < 0x100u && (kb & 3u) == C2A_EV_GATE, is_c = kb < 0x100u && (kb & 3u) == C2A_EV_CONNECT;
-      const uint32_t gm = __ballot_sync(0xFFFFFFFFu, is_g), cm = __ballot_sync(0xFFFFFFFFu, is_c);
+      const bool is_i = P.implicit && (is_g || is_c) && (kb & 0x80u);  // one operand is the signal declared last: no payload word for it
+      const uint32_t gm = __ballot_sync(0xFFFFFFFFu, is_g), cm = __ballot_sync(0xFFFFFFFFu, is_c), im = __ballot_sync(0xFFFFFFFFu, is_i);
       __syncthreads();  // s_wg / s_wc of the previous tile
-      if (lane == 0) { s_wg[warp] = __popc(gm); s_wc[warp] = __popc(cm); }
+      if (lane == 0) { s_wg[warp] = __popc(gm); s_wc[warp] = __popc(cm); s_wi[warp] = __popc(im); }
       __syncthreads();
       if (warp == 0) {
-        uint32_t a = s_wg[lane], b = s_wc[lane];
-        uint32_t ai = warp_incl_scan(a, lane), bi = warp_incl_scan(b, lane);
+        uint32_t a = s_wg[lane], b = s_wc[lane], c3 = s_wi[lane];
+        uint32_t ai = warp_incl_scan(a, lane), bi = warp_incl_scan(b, lane), ci = warp_incl_scan(c3, lane);
         __syncwarp();
-        s_wg[lane] = ai - a; s_wc[lane] = bi - b;
+        s_wg[lane] = ai - a; s_wc[lane] = bi - b; s_wi[lane] = ci - c3;
       }
       __syncthreads();
-      const uint32_t dg = s_wg[warp] + __popc(gm & lt), dc = s_wc[warp] + __popc(cm & lt), ds = k - dg - dc;
+      const uint32_t dg = s_wg[warp] + __popc(gm & lt), dc = s_wc[warp] + __popc(cm & lt), di = s_wi[warp] + __popc(im & lt), ds = k - dg - dc;
       const uint32_t g0 = s_tg[tile], c0 = s_tc[tile], s0 = tbase - g0 - c0;
       const uint32_t before = s0 + ds;  // signals declared before this event: dense ids => "declared before use" is id < before
-      const unsigned long long w = 3ull * g0 + 2ull * c0 + 3u * dg + 2u * dc;
+      const unsigned long long w = 3ull * g0 + 2ull * c0 - s_ti[tile] + 3u * dg + 2u * dc - di;
       if (is_g) {
-        uint4 gt = make_uint4(kb >> 2, P.words[w], P.words[w + 1], P.words[w + 2]);
+        uint4 gt = make_uint4(P.implicit ? (kb >> 2) & 31u : kb >> 2, P.words[w], P.words[w + 1], is_i ? before - 1u : P.words[w + 2]);
         if (gt.y < before && gt.z < before && gt.w < before) P.outmark[gt.w] = 1;  // compiler.rs:201
         else { f |= EF_UNKNOWN_REF; gt.y = gt.z = gt.w = 0; }
         P.egates[g0 + dg] = gt;
       } else if (is_c) {
-        uint2 ab = make_uint2(P.words[w], P.words[w + 1]);
+        uint2 ab = is_i ? make_uint2(before - 1u, P.words[w]) : make_uint2(P.words[w], P.words[w + 1]);
         if (!(ab.x < before && ab.y < before)) { f |= EF_UNKNOWN_REF; ab = make_uint2(0, 0); }
         P.conn[c0 + dc] = ab;
         P.conn_sb[c0 + dc] = before;
@@ -728,15 +744,20 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   P.tiles = (uint32_t)((n + kEvTile - 1) / kEvTile);
   P.n_in = io->n_in;
   P.n_out = io->n_out;
-  P.G_ub = (uint32_t)(nw / 3);
-  P.C_ub = (uint32_t)(nw / 2);
+  const bool implicit = (pk->flags & C2A_PACKED_IMPLICIT_OPERANDS) != 0;  // a gate carries >= 2 words, a connection >= 1
+  P.implicit = implicit ? 1u : 0u;
+  P.G_ub = (uint32_t)(implicit ? nw / 2 : nw / 3);
+  P.C_ub = (uint32_t)(implicit ? nw : nw / 2);
   P.S_ub = (uint32_t)(n - (nw + 2) / 3 + 1);
   P.NB_ub = P.S_ub + P.C_ub + 1;
   const uint64_t Gu = P.G_ub, Cu = P.C_ub, Su = P.S_ub, NBu = P.NB_ub;
   int grid = (int)std::min<uint64_t>((uint64_t)h->num_sms, std::max<uint64_t>(1, (n + g_fused_events_per_cta - 1) / g_fused_events_per_cta));
   {
     static int occ = -1;
-    if (occ < 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_fused_compile, kFusedBlock, 0) != cudaSuccess || occ < 1)) { cudaGetLastError(); occ = 0; }
+    if (occ < 0) {
+      if (cudaFuncSetAttribute((const void*)k_fused_compile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem) != cudaSuccess ||
+          cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_fused_compile, kFusedBlock, kFusedSmem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 0; }
+    }
     if (occ < 1) return classic();
   }
   // ---- staging for the stream / I/O lists (host form), then one slab: resident results first, scratch behind them
@@ -763,7 +784,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   slab_reset(h);
   emit_drop_host(h);
   size_t need = align256(16 * Gu) + align256(4 * Su) + align256(4 * NBu);                                            // resident
-  need += 2 * align256(4 * ((size_t)P.tiles + 2)) + align256(8 * Su) + align256(16 * Gu) + align256(8 * Cu) + align256(4 * Cu) + align256(Su);  // scatter targets
+  need += 3 * align256(4 * ((size_t)P.tiles + 2)) + align256(8 * Su) + align256(16 * Gu) + align256(8 * Cu) + align256(4 * Cu) + align256(Su);  // scatter targets
   need += 5 * align256(4 * Su) + 2 * align256(4 * (Cu / 32 + 8)) + align256(4 * Cu) + align256(16 * Cu);            // union-find, bitmaps, live lists
   need += align256(8 * Gu) + 2 * align256(4 * (Gu + 1)) + align256(Gu) + align256(4 * (Gu / 32 + 2)) + 3 * align256(4 * Gu) + 2 * align256(4 * ((3 * Gu + 31) / 32 + 8));
   need += align256(4 * Gu) + align256(4 * NBu) + align256(16 * Gu);                                                 // order / wire / new gates when not the caller's
@@ -776,6 +797,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   const size_t keep = h->slab_used;
   P.tile_g = (uint32_t*)A(4 * ((size_t)P.tiles + 2));
   P.tile_c = (uint32_t*)A(4 * ((size_t)P.tiles + 2));
+  P.tile_i = (uint32_t*)A(4 * ((size_t)P.tiles + 2));
   P.sig_meta = (uint2*)A(8 * Su);
   P.egates = (uint4*)A(16 * Gu);
   P.conn = (uint2*)A(8 * Cu);
@@ -857,7 +879,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   phase_begin(h, "k_fused_compile");
   {
     void* args[] = {(void*)&P};
-    if (!cuda_ok(h, cudaLaunchCooperativeKernel((const void*)k_fused_compile, dim3(grid), dim3(kFusedBlock), args, 0, s), "fused launch")) return C2A_ERR_CUDA;
+    if (!cuda_ok(h, cudaLaunchCooperativeKernel((const void*)k_fused_compile, dim3(grid), dim3(kFusedBlock), args, kFusedSmem, s), "fused launch")) return C2A_ERR_CUDA;
     h->launches++;
   }
   phase_end(h);

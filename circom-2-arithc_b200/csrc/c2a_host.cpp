@@ -234,52 +234,83 @@ int c2a_emit_events(c2a_compiler* c, const c2a_event* ev, uint64_t n, uint64_t* 
 }
 
 // ---- packed event stream (include/c2a.h): kinds byte + payload words -----------------------------------------------
-uint64_t c2a_pack_events(const c2a_event* ev, uint64_t n, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out) {
+uint64_t c2a_pack_events_ex(const c2a_event* ev, uint64_t n, uint32_t allow_flags, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out) {
   // dense = the declared ids are exactly 0, 1, 2, ... in declaration order (Runtime::gen_signal, src/runtime.rs:120-125)
   bool dense = true;
-  uint64_t ns = 0, ng = 0, nc = 0;
+  uint64_t ns = 0, ng = 0, nc = 0, ni = 0;
   for (uint64_t i = 0; i < n; ++i) {
     uint32_t k = ev[i].kind & 0xFF;
     if (k <= C2A_EV_SIGNAL_CONST) { if (ev[i].a != ns) dense = false; ++ns; }
     else if (k == C2A_EV_GATE) ++ng;
     else ++nc;  // CONNECT, or an invalid kind (kept as kind 3 with op bits set below so that the device flags it)
   }
-  const uint64_t n_words = 3 * ng + 2 * nc + (dense ? 0 : ns);
-  if (flags_out) *flags_out = dense ? C2A_PACKED_DENSE_IDS : 0u;
+  // implicit operands (dense ids only): a gate whose out signal / a connection whose first signal is the signal declared last
+  // (what the walker always emits: src/process.rs:470-475 creates the temporary right before the gate, :241-273 connects it)
+  const bool implicit = dense && (allow_flags & C2A_PACKED_IMPLICIT_OPERANDS);
+  if (implicit) {
+    uint64_t s_before = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+      uint32_t k = ev[i].kind & 0xFF;
+      if (k <= C2A_EV_SIGNAL_CONST) ++s_before;
+      else if (k == C2A_EV_GATE) { if (s_before && ev[i].c == s_before - 1 && (ev[i].kind >> 8) < 31) ++ni; }
+      else if (k == C2A_EV_CONNECT) { if (s_before && ev[i].a == s_before - 1) ++ni; }
+    }
+  }
+  const uint64_t n_words = 3 * ng + 2 * nc - ni + (dense ? 0 : ns);
+  if (flags_out) *flags_out = (dense ? C2A_PACKED_DENSE_IDS : 0u) | (implicit ? C2A_PACKED_IMPLICIT_OPERANDS : 0u);
   if (!kinds_out || !words_out) return n_words;
-  uint64_t w = 0;
+  uint64_t w = 0, s_before = 0;
   for (uint64_t i = 0; i < n; ++i) {
     uint32_t k = ev[i].kind & 0xFF;
     if (k <= C2A_EV_SIGNAL_CONST) {
       kinds_out[i] = (uint8_t)k;
       if (!dense) words_out[w++] = ev[i].a;
+      ++s_before;
     } else if (k == C2A_EV_GATE) {
       uint32_t op = ev[i].kind >> 8;
-      kinds_out[i] = (uint8_t)(C2A_EV_GATE | (op < 63 ? op << 2 : 63u << 2));  // an out-of-range op stays out of range
-      words_out[w++] = ev[i].a; words_out[w++] = ev[i].b; words_out[w++] = ev[i].c;
+      if (implicit) {  // op in bits 2..6, bit 7 = "out is the signal declared last"
+        const bool im = s_before && ev[i].c == s_before - 1 && op < 31;
+        kinds_out[i] = (uint8_t)(C2A_EV_GATE | (op < 31 ? op << 2 : 31u << 2) | (im ? 0x80u : 0u));
+        words_out[w++] = ev[i].a; words_out[w++] = ev[i].b;
+        if (!im) words_out[w++] = ev[i].c;
+      } else {
+        kinds_out[i] = (uint8_t)(C2A_EV_GATE | (op < 63 ? op << 2 : 63u << 2));  // an out-of-range op stays out of range
+        words_out[w++] = ev[i].a; words_out[w++] = ev[i].b; words_out[w++] = ev[i].c;
+      }
     } else {
-      kinds_out[i] = (uint8_t)(C2A_EV_CONNECT | (k == C2A_EV_CONNECT ? 0u : 1u << 2));  // op bits on a non-gate = invalid kind
-      words_out[w++] = ev[i].a; words_out[w++] = ev[i].b;
+      const bool valid = k == C2A_EV_CONNECT;
+      const bool im = implicit && valid && s_before && ev[i].a == s_before - 1;
+      kinds_out[i] = (uint8_t)(C2A_EV_CONNECT | (valid ? 0u : 1u << 2) | (im ? 0x80u : 0u));  // op bits on a non-gate = invalid kind
+      if (!im) words_out[w++] = ev[i].a;
+      words_out[w++] = ev[i].b;
     }
   }
   return n_words;
 }
 
+uint64_t c2a_pack_events(const c2a_event* ev, uint64_t n, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out) {
+  return c2a_pack_events_ex(ev, n, C2A_PACKED_DENSE_IDS, kinds_out, words_out, flags_out);
+}
+
 int c2a_unpack_events(const c2a_packed_events* pk, c2a_event* out) {
   if (!pk || (pk->n_events && (!pk->kinds || !out))) return C2A_ERR_INVALID_ARGUMENT;
   const bool dense = pk->flags & C2A_PACKED_DENSE_IDS;
+  const bool implicit = dense && (pk->flags & C2A_PACKED_IMPLICIT_OPERANDS);
   uint64_t w = 0, ns = 0;
   for (uint64_t i = 0; i < pk->n_events; ++i) {
-    uint32_t kb = pk->kinds[i], k = kb & 3u, op = kb >> 2;
-    uint32_t need = k <= C2A_EV_SIGNAL_CONST ? (dense ? 0u : 1u) : (k == C2A_EV_GATE ? 3u : 2u);
+    uint32_t kb = pk->kinds[i], k = kb & 3u, op = implicit ? (kb >> 2) & 31u : kb >> 2;
+    const bool im = implicit && (kb & 0x80u);
+    uint32_t need = k <= C2A_EV_SIGNAL_CONST ? (dense ? 0u : 1u) : (k == C2A_EV_GATE ? 3u : 2u) - (im ? 1u : 0u);
     if (w + need > pk->n_words || (need && !pk->words)) return C2A_ERR_INVALID_ARGUMENT;
+    const uint32_t last = (uint32_t)ns - 1u;  // the signal declared last (0xFFFFFFFF when there is none: an undeclared reference)
     if (k <= C2A_EV_SIGNAL_CONST) {
-      out[i] = c2a_event{op ? 0xFFu : k, dense ? (uint32_t)ns : pk->words[w], 0, 0};
+      out[i] = c2a_event{(op || im) ? 0xFFu : k, dense ? (uint32_t)ns : pk->words[w], 0, 0};
       ++ns;
     } else if (k == C2A_EV_GATE) {
-      out[i] = c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), pk->words[w], pk->words[w + 1], pk->words[w + 2]};
+      out[i] = c2a_event{(uint32_t)C2A_EV_GATE | (op << 8), pk->words[w], pk->words[w + 1], im ? last : pk->words[w + 2]};
     } else {
-      out[i] = c2a_event{op ? 0xFFu : (uint32_t)C2A_EV_CONNECT, pk->words[w], pk->words[w + 1], 0};
+      out[i] = im ? c2a_event{op ? 0xFFu : (uint32_t)C2A_EV_CONNECT, last, pk->words[w], 0}
+                  : c2a_event{op ? 0xFFu : (uint32_t)C2A_EV_CONNECT, pk->words[w], pk->words[w + 1], 0};
     }
     w += need;
   }

@@ -233,6 +233,13 @@ int c2a_emitted_signal_wires_device(c2a_handle*, const uint32_t* d_signals, uint
  * Constant VALUES are not part of it: they never influence node ids, gates or errors (src/compiler.rs:139-278) and stay with
  * the host-side name / constant maps.  n_words must equal 3*gates + 2*connections (+ signals without DENSE_IDS). ---- */
 #define C2A_PACKED_DENSE_IDS 1u
+/* With dense ids the two operands the walker always derives from the signal it declared last need no payload word either
+ * (src/process.rs:470-475 creates the temporary right before its gate; :241-273 connects that temporary to the assigned signal):
+ * the op of a GATE then lives in bits 2..6 of its kind byte and bit 7 set means "out = the signal declared last" (payload: lhs,
+ * rhs); bit 7 set on a CONNECT means "a = the signal declared last" (payload: b).  Events without bit 7 carry all their words.
+ * n_words = 3*gates + 2*connections - flagged events.  4.0 B/event instead of 6.0 on a walker stream: it is PCIe that bounds
+ * the host-to-device form of the emitter. */
+#define C2A_PACKED_IMPLICIT_OPERANDS 2u
 typedef struct {
   const uint8_t* kinds;
   const uint32_t* words;
@@ -242,6 +249,9 @@ typedef struct {
 /* AoS -> packed.  Returns n_words and *flags_out; writes kinds_out[n] / words_out[n_words] when they are non-NULL
  * (call once with NULL buffers to size them). */
 uint64_t c2a_pack_events(const c2a_event* ev, uint64_t n, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out);
+/* same; allow_flags says which compactions may be used (C2A_PACKED_DENSE_IDS is applied whenever it holds; add
+ * C2A_PACKED_IMPLICIT_OPERANDS for the 4 B/event form).  *flags_out = the flags the stream actually carries. */
+uint64_t c2a_pack_events_ex(const c2a_event* ev, uint64_t n, uint32_t allow_flags, uint8_t* kinds_out, uint32_t* words_out, uint32_t* flags_out);
 /* packed -> AoS (constant values read back as 0); C2A_ERR_INVALID_ARGUMENT when n_words does not match the kinds */
 int c2a_unpack_events(const c2a_packed_events* pk, c2a_event* ev_out /* n_events */);
 /* c2a_emit_events_device / _resident on a packed stream (kinds / words are host, resp. DEVICE pointers; the struct itself is

@@ -132,6 +132,13 @@ def check_against(ctx, ref, ev, expect_path=DEVICE):
     gates_p, nos_p = ctx.emitted_fetch()
     assert {k: v for k, v in info_p.items() if k != "decline_flags"} == {k: v for k, v in info.items() if k != "decline_flags"}
     assert np.array_equal(gates_p, gates) and np.array_equal(nos_p, nos)
+    if flags & 1:   # dense ids: the 4 B/event form (operands derived from the signal declared last carry no word) replays identically
+        kinds_i, words_i, flags_i = c2a.pack_events(ev, implicit=True)
+        assert flags_i == 3 and len(words_i) <= len(words)
+        info_i = ctx.emit_packed(kinds_i, words_i, flags_i)
+        gates_i, nos_i = ctx.emitted_fetch()
+        assert {k: v for k, v in info_i.items() if k != "decline_flags"} == {k: v for k, v in info.items() if k != "decline_flags"}
+        assert np.array_equal(gates_i, gates) and np.array_equal(nos_i, nos)
     return info, gates, nos
 
 
@@ -291,10 +298,26 @@ def test_dense_packed_streams_with_forward_references(ctx, orc, c2a, seed):
         gates, _ = ctx.emitted_fetch()
         assert np.array_equal(gates, oc.gate_array()) and info["node_count"] == oc.node_count
     else:
-        with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:
-            ctx.emit_packed(kinds_b, words, flags)
-        assert int(ex.value.status) == err.status
-        assert f"event {ex.value.err_event}" == err.message
+        for imp in (False, True):
+            with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:
+                ctx.emit_packed(*c2a.pack_events(ev, implicit=imp))
+            assert int(ex.value.status) == err.status
+            assert f"event {ex.value.err_event}" == err.message
+
+
+def test_implicit_operand_stream_at_scale(ctx, c2a):
+    """1 M gates: the 4 B/event packed form (TMA-staged scatter with the third rank) against the 6 B/event form"""
+    wl = c2a.workloads.mimc_chains(1832, rounds=91, variant="late")
+    ev = np.ascontiguousarray(wl.events)
+    k6, w6, f6 = c2a.pack_events(ev)
+    k4, w4, f4 = c2a.pack_events(ev, implicit=True)
+    assert f4 == 3 and (k4.nbytes + w4.nbytes) / len(ev) < 4.1 < (k6.nbytes + w6.nbytes) / len(ev)
+    i6 = ctx.emit_packed(k6, w6, f6)
+    g6, n6 = ctx.emitted_fetch()
+    i4 = ctx.emit_packed(k4, w4, f4)
+    g4, n4 = ctx.emitted_fetch()
+    assert i4["path"] == DEVICE and {k: v for k, v in i4.items()} == {k: v for k, v in i6.items()}
+    assert np.array_equal(g4, g6) and np.array_equal(n4, n6)
 
 
 def test_merge_errors(ctx, c2a):

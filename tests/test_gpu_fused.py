@@ -44,6 +44,12 @@ def run_both(ctx, c2a, ev, ins, outs, expect_fused=True):
     assert np.array_equal(fo, co), f"order differs first at {int(np.argmax(fo != co))}"
     assert np.array_equal(fw, cw), f"wire map differs first at node {int(np.argmax(fw != cw))}"
     assert np.array_equal(fg, cg) and fwc == cwc
+    # the 4 B/event form of the same stream (implicit operands) through the fused kernel
+    ki, wi, fl = c2a.pack_events(np.ascontiguousarray(ev), implicit=True)
+    if fl == 3:
+        ii, io_, iw, ig, iwc = ctx.compile_packed(ki, wi, fl, ins, outs)
+        assert ("k_fused_compile" in ctx.phases()) == expect_fused and strip(ii) == strip(ci)
+        assert np.array_equal(io_, co) and np.array_equal(iw, cw) and np.array_equal(ig, cg) and iwc == cwc
     # named-wire look-ups work on the resident result of the fused call
     sig = np.concatenate([np.asarray(ins, dtype=np.uint32), np.asarray(outs, dtype=np.uint32)])
     if len(sig):
@@ -221,10 +227,11 @@ def test_streams_the_reference_rejects_fall_back_to_the_exact_replay(ctx, c2a, o
         st, _, o_order, o_wire, o_gates, o_wc = orc.backend_raw(gates, oc.node_count + 1, [oc.signal_node(0)], [])
         assert st == 0 and np.array_equal(order, o_order) and np.array_equal(wire, o_wire) and np.array_equal(ng, o_gates) and wc == o_wc
     else:
-        with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:
-            ctx.compile_packed(k, w, f, [0], [])
-        assert int(ex.value.status) == err.status
-        assert f"event {ex.value.err_event}" == err.message
+        for imp in (False, True):
+            with pytest.raises((c2a.CircuitError, c2a.C2AError)) as ex:
+                ctx.compile_packed(*c2a.pack_events(ev, implicit=imp), [0], [])
+            assert int(ex.value.status) == err.status
+            assert f"event {ex.value.err_event}" == err.message
 
 
 def test_bad_io_signal_and_capacities(ctx, c2a):

@@ -80,3 +80,51 @@ def test_device_compiler_records_without_a_gpu(c2a):
     assert [dc.signal_name(s) for s in dc.output_signals] == ["0.c", "0.const_signal_3"]
     if host is not None:
         assert np.array_equal(host.events, dc.events)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_implicit_operands_round_trip(c2a, seed):
+    """C2A_PACKED_IMPLICIT_OPERANDS: a gate whose out signal / a connection whose first signal is the signal declared last carries no
+    word for it; mixed with events that do not qualify, invalid ops and kinds, references before any declaration"""
+    rng = np.random.RandomState(50 + seed)
+    ev, ns = [], 0
+    for _ in range(int(rng.randint(1, 400))):
+        x = rng.rand()
+        if x < 0.4 or ns == 0:
+            ev.append((EV_SC, ns, int(rng.randint(0, 9)), 0) if rng.rand() < 0.2 else (EV_S, ns, 0, 0))
+            ns += 1
+        elif x < 0.7:
+            op = int(rng.randint(0, 20)) if rng.rand() < 0.95 else int(rng.choice([20, 31, 40, 63, 200]))
+            out = ns - 1 if rng.rand() < 0.7 else int(rng.randint(0, ns + 2))
+            ev.append((EV_G | (op << 8), int(rng.randint(0, ns + 2)), int(rng.randint(0, ns + 2)), out))
+        else:
+            a = ns - 1 if rng.rand() < 0.7 else int(rng.randint(0, ns + 2))
+            ev.append((EV_C, a, int(rng.randint(0, ns + 2)), 0))
+    if seed == 0:
+        ev = [(EV_G, 0, 0, 0), (EV_C, 0, 0, 0)] + ev      # events before any declaration cannot use the implicit form
+    ev = np.asarray(ev, dtype=np.uint32).reshape(-1, 4)
+    k = ev[:, 0] & 0xFF
+    if seed == 0:
+        ev[k <= 1, 1] = np.arange((k <= 1).sum())
+    kinds, words, flags = c2a.pack_events(ev, implicit=True)
+    assert flags == 3
+    k0, w0, f0 = c2a.pack_events(ev)
+    assert f0 == 1 and len(words) <= len(w0) and np.array_equal(kinds & 3, k0 & 3)
+    n_flagged = int(((kinds & 0x80) != 0).sum())
+    assert len(words) == len(w0) - n_flagged
+    back = c2a.unpack_events(kinds, words, flags)
+    want = _zero_values(ev)
+    bad_op = (k == EV_G) & ((ev[:, 0] >> 8) >= 31)        # out-of-range ops stay out of range, not bit-identical
+    assert np.array_equal(back[~bad_op], want[~bad_op])
+    assert ((back[bad_op, 0] >> 8) >= 20).all() and np.array_equal(back[bad_op, 1:], want[bad_op, 1:])
+
+
+def test_implicit_operands_shrink_a_walker_stream(c2a):
+    wl = c2a.workloads.mimc_chains(5, rounds=9, variant="late")
+    ev = np.ascontiguousarray(wl.events)
+    kinds, words, flags = c2a.pack_events(ev, implicit=True)
+    k = ev[:, 0] & 0xFF
+    G, Cn = int((k == EV_G).sum()), int((k == EV_C).sum())
+    assert flags == 3 and len(words) <= 2 * G + 2 * Cn - G + 8       # every gate, and the connection after every gate, lost a word
+    assert (kinds.nbytes + words.nbytes) / len(ev) < 4.2
+    assert np.array_equal(c2a.unpack_events(kinds, words, flags), _zero_values(ev))
