@@ -71,6 +71,15 @@ __device__ __forceinline__ uint32_t warp_or(uint32_t v) {
   return v;
 }
 
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
 constexpr int kBlock = 256;
 constexpr uint32_t kNone = C2A_NONE;
 static void emit_drop_host(c2a_handle* h);  // c2a_emit.cuh
@@ -124,8 +133,27 @@ __global__ void __launch_bounds__(kBlock) k_producer(const uint4* __restrict__ g
 // (compiler.rs:412-418).  flags |= F_OOO when some dep index >= g: only then can the DFS post-order differ
 // from 0..G-1 (otherwise every root's deps are already visited when the root loop reaches it).
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates, uint32_t G, uint32_t node_bound, const uint32_t* __restrict__ prod1,
-                                                 uint2* __restrict__ dep, uint32_t* __restrict__ seeds, uint32_t* __restrict__ scalars) {
+// kCount (Kahn, K3): also counts the consumers of every producer (row lengths of the consumer CSR) while the dependencies are in
+// registers - no second pass over dep[]; the forward-edge list (K5a seeds) is then not collected.
+template <bool kCount>
+__global__ void __launch_bounds__(kBlock) k_deps_t(const uint4* __restrict__ gates, uint32_t G, uint32_t node_bound, const uint32_t* __restrict__ prod1,
+                                                   uint2* __restrict__ dep, uint32_t* __restrict__ seeds, uint32_t* __restrict__ cnt, uint32_t* __restrict__ scalars) {
+  constexpr int kPend = 4;  // forward-edge gates a thread holds back: one warp-aggregated atomic per kPend iterations
+  uint32_t pend[kPend];
+  int np = 0;
+  const int lane = threadIdx.x & 31;
+  auto flush = [&]() {
+    // warp-wide: offsets by an inclusive scan of the pending counts, one atomic for the warp's total
+    if (!__ballot_sync(0xFFFFFFFFu, np != 0)) return;
+    const uint32_t incl = warp_incl_scan((uint32_t)np, lane);
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 31) base = atomicAdd(scalars + S_SEEDN, total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - np;
+#pragma unroll
+    for (int i = 0; i < kPend; ++i) if (i < np) seeds[base + i] = pend[i];
+    np = 0;
+  };
   uint32_t f = 0;
   const uint32_t iters = (G + gridDim.x * kBlock - 1) / (gridDim.x * kBlock);  // full-warp iterations (warp-aggregated append below)
   for (uint32_t it = 0; it < iters; ++it) {
@@ -140,18 +168,23 @@ __global__ void __launch_bounds__(kBlock) k_deps(const uint4* __restrict__ gates
       fwd = (d0 != kNone && d0 > g) || (d1 != kNone && d1 > g);
       if (fwd) f |= F_OOO;
       if (d0 == g || d1 == g) f |= F_SELF;
+      if (kCount) {
+        if (d0 != kNone) atomicAdd(cnt + d0, 1u);
+        if (d1 != kNone && d1 != d0) atomicAdd(cnt + d1, 1u);  // lh == rh: one producer, listed once
+      }
     }
+    if (kCount) continue;
     // gates with a forward dependency are where the relaxation starts (K5a): collect them, the seed kernel does not
-    // have to stream dep[] again to find them
-    uint32_t m = __ballot_sync(0xFFFFFFFFu, fwd);
-    if (m) {
-      const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(scalars + S_SEEDN, (uint32_t)__popc(m));
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (fwd) seeds[base + __popc(m & ((1u << lane) - 1))] = g;
+    // have to stream dep[] again to find them.  Held back per thread and appended once per kPend iterations: a shuffled gate
+    // vector has a forward edge in every other gate, and one atomic per warp and iteration on the one counter then bounds the kernel.
+    if (fwd) {
+#pragma unroll
+      for (int i = 0; i < kPend; ++i) if (i == np) pend[i] = g;
+      ++np;
     }
+    if ((it % kPend) == kPend - 1) flush();
   }
+  if (!kCount) flush();
   uint32_t any_ooo = __syncthreads_or(f & F_OOO), any_self = __syncthreads_or(f & F_SELF);
   if (threadIdx.x == 0 && (any_ooo || any_self)) atomicOr(scalars + S_FLAGS, (any_ooo ? F_OOO : 0u) | (any_self ? F_SELF : 0u));
 }
@@ -269,14 +302,6 @@ __global__ void __launch_bounds__(kBlock) k_sizes(const uint32_t* __restrict__ r
 // ---------------------------------------------------------------------------------------------------
 constexpr unsigned long long kStAgg = 1ull << 32, kStInc = 2ull << 32;
 
-__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, v, o);
-    if (lane >= o) v += t;
-  }
-  return v;
-}
 
 // scan_tile_prefix returns the exclusive prefix of this thread's `thread_sum` over the whole grid-wide sequence of tiles.
 // Must be called by all kBlock threads.  s_mem: >= 10 u32 of shared memory.
@@ -492,6 +517,8 @@ __global__ void __launch_bounds__(kBlock) k_io_max(const uint32_t* __restrict__ 
 // RED.MIN per slot: inputs / pending outputs hold smaller words and are left untouched.
 // Every thread keeps kWireIlp independent gates in flight: the order[] loads, then the gate loads, then the wire[] probes are
 // issued as batches (a single gate is a chain of three dependent memory round trips).
+// (Skipping the operand probes of nodes that have a producer - their first appearance is the producer's out slot - by reading dep[]
+//  instead was measured: 0.085 ms against 0.080 ms, the 8-byte dep[] stream costs what the two L2-resident probes cost.)
 constexpr int kWireIlp = 4;
 __global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
                                                        uint32_t* __restrict__ wire, const uint32_t* __restrict__ sc) {
@@ -510,7 +537,8 @@ __global__ void __launch_bounds__(kBlock) k_wire_first(const uint4* __restrict__
 #pragma unroll
     for (int i = 0; i < kWireIlp; ++i) gt[i] = order ? __ldg(gates + g[i]) : ldg_stream(gates + g[i]);
     // Read before the RED: words only ever decrease, so a (possibly stale) value <= p proves the RED is a no-op.
-    // This removes the serialisation on hot nodes (a shared input such as a key feeds millions of gates).
+    // This removes the serialisation on hot nodes (a shared input such as a key feeds millions of gates), and a RED on a sector
+    // that is not in L2 yet is 3.5x slower than load-then-RED (measured: 0.28 ms instead of 0.08 ms for this kernel).
 #pragma unroll
     for (int i = 0; i < kWireIlp; ++i) { w[i][0] = wire[gt[i].y]; w[i][1] = wire[gt[i].z]; w[i][2] = wire[gt[i].w]; }
 #pragma unroll
@@ -1043,7 +1071,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     phase_end(h);
   }
   phase_begin(h, "k_deps");
-  if (G) LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, s.heavy, sc);
+  if (G) LAUNCH(h, k_deps_t<false>, grid_for(h, (const void*)k_deps_t<false>, kBlock, G), kBlock, d_gates, G, p.node_bound, prod1, dep, s.heavy, (uint32_t*)nullptr, sc);
   phase_end(h);
 
   uint32_t* d_order = d_order_user ? d_order_user : order_int;

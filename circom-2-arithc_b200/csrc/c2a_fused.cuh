@@ -654,9 +654,11 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   FUSED_FOR(k, G) {
     const uint32_t g = sorted ? ldg2(order + k) : k;
     const uint4 gt = ldg2(P.gates + g);
+    const uint2 dd = ldg2(P.dep + g);
     const uint32_t p = kFirstTag | (3u * k);
-    fused_red_min(wire + gt.y, p);
-    if (gt.z != gt.y) fused_red_min(wire + gt.z, p + 1);
+    // an operand whose node has a producer cannot hold the node's first appearance (see k_wire_first)
+    if (dd.x == kNone) fused_red_min(wire + gt.y, p);
+    if (dd.y == kNone && gt.z != gt.y) fused_red_min(wire + gt.z, p + 1);
     if (gt.w != gt.y && gt.w != gt.z) fused_red_min(wire + gt.w, p + 2);
   }
   grid_bar(P, cx);

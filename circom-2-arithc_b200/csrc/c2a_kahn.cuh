@@ -5,7 +5,7 @@
 // of its lh and rh nodes.  Kahn yields a valid topological order and the levels (longest-path depth), NOT the reference's
 // DFS post-order (that is K5, c2a_device.cu); it is used for cycle screening, the sweeps and the evaluator.
 //
-//   K3  k_kahn_count / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G].  A col entry is 16 bytes:
+//   K3  (row lengths counted by k_deps_t<true>) / k_scan_u32 / k_kahn_fill   consumer CSR  row_off[G+1], col[<=2G].  A col entry is 16 bytes:
 //       {consumer | two-producer flag << 31, the consumer's own row begin, its row length, 0} - the walker that releases the
 //       consumer already holds its row, so a hop costs one dependent load (plus one atomic for a two-producer consumer).
 //       A gate that reads the same producer on both operands is listed once and counts as a one-producer consumer.
@@ -29,14 +29,6 @@ constexpr uint32_t kLongRow = 512;        // consumers; rows at least this long 
 constexpr int kWalkStack = 16;            // released-but-not-yet-walked consumers a thread keeps for itself
 constexpr uint32_t kTwoSlots = 0x80000000u;
 enum { KC_QN0 = 0, KC_QN1 = 1, KC_LONGN0 = 2, KC_LONGN1 = 3, KC_DONE = 4, KC_MAXLV = 5, KC_ERRMIN = 6, KC_COUNT = 16 };
-
-__global__ void __launch_bounds__(kBlock) k_kahn_count(const uint2* __restrict__ dep, uint32_t G, uint32_t* __restrict__ cnt) {
-  for (uint32_t g = blockIdx.x * kBlock + threadIdx.x; g < G; g += gridDim.x * kBlock) {
-    uint2 d = dep[g];
-    if (d.x != kNone) atomicAdd(cnt + d.x, 1u);
-    if (d.y != kNone && d.y != d.x) atomicAdd(cnt + d.y, 1u);  // lh == rh: one producer, listed once
-  }
-}
 
 __global__ void __launch_bounds__(kBlock) k_kahn_fill(const uint2* __restrict__ dep, uint32_t G, const uint32_t* __restrict__ row_off,
                                                       uint32_t* __restrict__ cursor, uint4* __restrict__ col) {
@@ -399,10 +391,8 @@ static int kahn_core(c2a_handle* h, const uint4* d_gates, uint32_t G, uint32_t n
     LAUNCH(h, k_producer, grid_for(h, (const void*)k_producer, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.scalars);
     phase_end(h);
     phase_begin(h, "k_deps");
-    LAUNCH(h, k_deps, grid_for(h, (const void*)k_deps, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, (uint32_t*)b.q[0], b.scalars);  // the forward-edge list is not used here: park it in a queue buffer
-    phase_end(h);
-    phase_begin(h, "k_kahn_count");
-    LAUNCH(h, k_kahn_count, grid_for(h, (const void*)k_kahn_count, kBlock, G), kBlock, b.dep, G, b.row_off);
+    // K2 + the row lengths of the consumer CSR in one pass (k_kahn_count fused into the dependency kernel)
+    LAUNCH(h, k_deps_t<true>, grid_for(h, (const void*)k_deps_t<true>, kBlock, G), kBlock, d_gates, G, node_bound, b.prod1, b.dep, (uint32_t*)nullptr, b.row_off, b.scalars);
     phase_end(h);
     uint32_t tiles = scan_tiles(G, kScanItems);
     cudaMemsetAsync(b.tile_state, 0, 8 * (size_t)tiles, st);
