@@ -118,9 +118,9 @@ def bind_to_gpu_numa_node(torch, local_rank):
         if node >= 0 and cpus:
             os.sched_setaffinity(0, cpus & os.sched_getaffinity(0) or cpus)
             return node
-    except Exception:
-        pass
-    return None
+        return "sysfs numa_node = %d for %s (a single-NUMA-node VM exposes no GPU affinity): nothing to bind" % (node, dev)
+    except Exception as e:  # noqa: BLE001
+        return "unavailable (%s)" % type(e).__name__
 
 
 def cpu_reference_measure(workloads, wl_full, sample_chains, variant, rounds, backend_gates=None):
