@@ -520,6 +520,115 @@ def multi_gpu_parity(c2a, torch, dist, ctx, dev, stream, rank, world, variant, r
 
 
 
+def strong_scaling_leg(c2a, torch, dist, ctx, dev, stream, rank, world, wl, steps):
+    """ONE circuit (the headline workload, every rank holds the whole packed stream) built by `world` GPUs: every rank replays the
+    stream (the emit is replicated: node ids are global prefix counts), plans the shards ON THE DEVICE (c2a_plan_shards_device),
+    builds its own gate range (c2a_emitted_build_range_device, shared I/O lists), the ranks all-gather their (n_in, n_mid, n_out, G)
+    and shift their wire ids / gate indices to the global numbering.  Device time, max over ranks; the stitched result is checked
+    against a single-rank build once before the timed steps."""
+    import numpy as np
+    lib, h, vp = c2a.lib, ctx.handle, C.c_void_p
+    sc = StagedCircuit(c2a, torch, ctx, dev, wl)
+    G, nb = sc.G, sc.nb
+    ins_n = None
+    d_order = torch.empty(G, dtype=torch.int32, device=dev)
+    d_wire = torch.empty(nb, dtype=torch.int32, device=dev)
+    d_new = torch.empty((G, 4), dtype=torch.int32, device=dev)
+    d_counts = torch.zeros(4, dtype=torch.int64, device=dev)
+    d_all = torch.zeros(4 * world, dtype=torch.int64, device=dev)
+    h_counts = torch.zeros(4, dtype=torch.int64).pin_memory()
+    wc, err = C.c_uint32(0), C.c_uint64(0)
+    bounds = (C.c_uint64 * (world + 1))()
+    nsh = C.c_uint32(0)
+    t_phase = {"emit": 0.0, "plan": 0.0, "build": 0.0, "reconcile": 0.0}
+    state = {}
+
+    def step(timed=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timed else None
+        if timed:
+            ev[0].record(stream)
+        st = lib.c2a_emit_packed_resident(h, C.byref(sc.pk_dev), C.byref(sc.info), C.byref(sc.bad))
+        assert st == 0 and sc.info.path == 1, ctx.last_error()
+        if timed:
+            ev[1].record(stream)
+        if ins_n is None:
+            return
+        gp = lib.c2a_emitted_gates_device(h)
+        st = lib.c2a_plan_shards_device(h, vp(gp), G, nb, ins_n.ctypes.data_as(vp), len(ins_n), outs_n.ctypes.data_as(vp), len(outs_n), world, bounds, C.byref(nsh))
+        assert st == 0 and nsh.value == world, (st, nsh.value, ctx.last_error())
+        if timed:
+            ev[2].record(stream)
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        st = lib.c2a_emitted_build_range_device(h, lo, hi, sc.ins.ctypes.data_as(vp), len(sc.ins), sc.outs.ctypes.data_as(vp), len(sc.outs),
+                                                vp(d_order.data_ptr()), vp(d_wire.data_ptr()), vp(d_new.data_ptr()), C.byref(wc), C.byref(err))
+        assert st == 0, ctx.last_error()
+        if timed:
+            ev[3].record(stream)
+        n_mid = wc.value - len(sc.ins) - len(sc.outs)
+        h_counts[0], h_counts[1], h_counts[2], h_counts[3] = len(sc.ins), n_mid, len(sc.outs), hi - lo
+        with torch.cuda.stream(stream):
+            d_counts.copy_(h_counts, non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_counts)
+        stream.synchronize()
+        counts = d_all.view(world, 4).cpu().numpy()
+        off_in, off_mid, off_out, gate_base = c2a.sharding.rebase_offsets(counts, rank, shared_io=True)
+        st = lib.c2a_rebase_wires_device(h, vp(d_new.data_ptr()), vp(d_order.data_ptr()), hi - lo, len(sc.ins), n_mid, off_in, off_mid, off_out, gate_base)
+        assert st == 0, ctx.last_error()
+        if timed:
+            ev[4].record(stream)
+            torch.cuda.synchronize()
+            for k_, (a, b) in zip(("emit", "plan", "build", "reconcile"), zip(ev[:-1], ev[1:])):
+                t_phase[k_] += a.elapsed_time(b)
+        state.update(lo=lo, hi=hi, n_mid=n_mid, counts=counts)
+
+    step()      # emit only: the I/O node ids of the plan come from the resident signal -> node map
+    sc.ctx._emit_info = {"n_gates": G, "signal_bound": int(sc.info.signal_bound)}
+    nos = ctx.emitted_fetch(want_gates=False)[1]
+    ins_n, outs_n = np.ascontiguousarray(nos[sc.ins]), np.ascontiguousarray(nos[sc.outs])
+    # ---- parity of the stitched result against the single-rank build of the same circuit (order + renumbered gates, by slice)
+    step()
+    lo, hi = state["lo"], state["hi"]
+    mine_o = d_order[:hi - lo].cpu().numpy().astype(np.uint32)
+    mine_g = d_new[:hi - lo].cpu().numpy().astype(np.uint32)
+    st = lib.c2a_emit_packed_resident(h, C.byref(sc.pk_dev), C.byref(sc.info), C.byref(sc.bad))
+    st = st or lib.c2a_emitted_build_circuit_device(h, sc.ins.ctypes.data_as(vp), len(sc.ins), sc.outs.ctypes.data_as(vp), len(sc.outs), vp(sc.d_order.data_ptr()),
+                                                    vp(sc.d_wire.data_ptr()), vp(sc.d_new.data_ptr()), C.byref(wc), C.byref(err))
+    assert st == 0, ctx.last_error()
+    ok = np.array_equal(mine_o, sc.d_order[lo:hi].cpu().numpy().astype(np.uint32)) and np.array_equal(mine_g, sc.d_new[lo:hi].cpu().numpy().astype(np.uint32))
+    ok = ok and wc.value == len(sc.ins) + int(state["counts"][:, 1].sum()) + len(sc.outs)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise RuntimeError("strong scaling: the stitched sharded build differs from the single-rank build")
+    lib.c2a_set_timing(h, 0)
+    for _ in range(2):
+        step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    for k_ in t_phase:
+        t_phase[k_] = 0.0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    for _ in range(2):
+        step(timed=True)
+    lib.c2a_set_timing(h, 1)
+    ms = float(t.item())
+    return {"workload": wl.name, "gates_total": G, "n_gpus": world, "value": G / (ms * 1e-3), "unit": "gates/s", "ms_per_step": ms, "steps": steps,
+            "shard_gates_this_rank": state["hi"] - state["lo"], "parity_vs_single_rank": "ok",
+            "phases_ms_rank0": {k_: v / 2 for k_, v in t_phase.items()},
+            "scope": "ONE circuit: stream replayed on every rank (replicated emit), shards planned on the device, each rank builds its gate range, "
+                     "one all-gather of counts, wire ids / gate indices shifted to the global numbering; results stay in HBM, sharded by rank",
+            "note": "the emit is not sharded (node ids are global prefix counts over the whole stream), so it bounds the speed-up: see phases_ms_rank0"}
+
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -540,6 +649,7 @@ def main():
     ap.add_argument("--no-from-source", action="store_true", help="skip the .circom-text-to-circuit leg")
     ap.add_argument("--source-chains", type=int, default=0, help="MiMC chains of the from_source leg (default: --chains, the headline workload)")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (one circuit sharded across the ranks)")
     ap.add_argument("--legs", default="all", help="comma list of the extra sub-records (N = 1): configs,variants,kahn,sweeps,same_config  (all | none)")
     ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the small-config sub-records")
     args = ap.parse_args()
@@ -1046,6 +1156,9 @@ def main():
         extra["extras_wall_s"] = time.perf_counter() - t_extra
         del gates_late, nos_late
 
+    strong = None
+    if world > 1 and not args.no_strong:
+        strong = strong_scaling_leg(c2a, torch, dist, ctx, dev, stream, rank, world, wl, max(3, K // 2))
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1110,6 +1223,8 @@ def main():
         out[k_] = v_
     if mgp is not None:
         out["multi_gpu_parity"] = mgp
+    if strong is not None:
+        out["strong_scaling"] = strong
     if pipe is not None:
         if "value" in pipe:
             pipe["h2d_bytes_per_step"], pipe["d2h_bytes_per_step"] = int(h2d), int(d2h)

@@ -103,6 +103,7 @@ _SIGS = {
     "c2a_rebase_wires_device": (i32, [vp, vp, vp, u64, u32, u32, u32, u32, u32, u32]),
     "c2a_rebase_wire_map_device": (i32, [vp, vp, u64, u32, u32, u32, u32, u32]),
     "c2a_rebase_wires_gathered_device": (i32, [vp, vp, vp, u64, vp, u32, u32]),
+    "c2a_plan_shards_device": (i32, [vp, vp, u64, u32, vp, u32, vp, u32, u32, u64p, u32p]),
     "c2a_topo_levels": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_topo_levels_device": (i32, [vp, vp, u64, u32, vp, vp, u32, u32p, u64p]),
     "c2a_sweep_masks": (i32, [vp, vp, u64, u32, vp, vp, u32, vp, u32, vp, vp, vp, u64p]),
@@ -128,6 +129,8 @@ _SIGS = {
     "c2a_emitted_fetch": (i32, [vp, vp, vp]),
     "c2a_emitted_build_circuit_device": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
     "c2a_emitted_build_circuit": (i32, [vp, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
+    "c2a_emitted_build_range_device": (i32, [vp, u64, u64, vp, u32, vp, u32, vp, vp, vp, u32p, u64p]),
+    "c2a_emitted_gates_device": (vp, [vp]),
     "c2a_compiler_new": (vp, []),
     "c2a_compiler_free": (None, [vp]),
     "c2a_compiler_last_error": (cp, [vp]),

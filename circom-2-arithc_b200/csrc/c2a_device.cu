@@ -1216,6 +1216,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->ev_buf) cudaFree(h->ev_buf);
   if (h->cx_buf) cudaFree(h->cx_buf);
   if (h->fused_ctl) cudaFree(h->fused_ctl);
+  if (h->plan_buf) cudaFree(h->plan_buf);
   if (h->cx_pinned) cudaFreeHost(h->cx_pinned);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
@@ -1418,4 +1419,5 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
 #include "c2a_kahn.cuh"
 #include "c2a_emit.cuh"
 #include "c2a_fused.cuh"
+#include "c2a_shard.cuh"
 #include "c2a_eval.cuh"

@@ -1289,12 +1289,16 @@ int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_sign
   return C2A_OK;
 }
 
+// gate range [g_lo, g_hi) of the resident circuit (g_hi = ~0: all of it).  A proper sub-range is one shard of a sharded build
+// (c2a_plan_shards_device): no dependency edge leaves it, so its producer map is rebuilt for the range alone.
 static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                               uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index,
-                              bool outputs_on_device) {
+                              bool outputs_on_device, uint64_t g_lo = 0, uint64_t g_hi = ~0ull) {
   if (!h) return C2A_ERR_INVALID_ARGUMENT;
   if (!h->emitted.valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no emitted circuit is resident on this handle");
-  const uint64_t G = h->emitted.G;
+  const bool whole = g_lo == 0 && (g_hi == ~0ull || g_hi == h->emitted.G);
+  if (!whole && (g_lo > g_hi || g_hi > h->emitted.G)) return fail(h, C2A_ERR_INVALID_ARGUMENT, "bad gate range");
+  const uint64_t G = whole ? h->emitted.G : g_hi - g_lo;
   const uint32_t node_bound = h->emitted.node_count + 1;
   int st = check_sizes(h, G, node_bound);
   if (st) return st;
@@ -1304,8 +1308,8 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   const size_t n_pairs = (size_t)n_in + n_out;
   slab_reset_keep(h);
   size_t need = h->slab_keep + core_scratch_bytes(p, n_pairs) + align256(4 * n_pairs + 4) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)node_bound) + align256(4 * ES_COUNT);
-  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;
-  const uint4* d_gates = (const uint4*)(h->slab + h->emitted.gates_off);
+  if (!slab_reserve(h, need)) return C2A_ERR_NO_MEMORY;  // (the slab may move: pointers into it are taken below)
+  const uint4* d_gates = (const uint4*)(h->slab + h->emitted.gates_off) + (whole ? 0 : g_lo);
   const uint32_t* nos = (const uint32_t*)(h->slab + h->emitted.nos_off);
   uint32_t* io_sigs = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
   uint32_t* io_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
@@ -1341,8 +1345,8 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   h->emitted.wire = nullptr;
   bool identity = true;
   st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, &identity, io_nodes, io_flag,
-                  h->emitted.prod1_valid ? (const uint32_t*)(h->slab + h->emitted.prod1_off) : nullptr);
-  if (st == C2A_OK) { h->emitted.wire = d_wire; h->emitted.identity = identity; }  // stay valid until the next call that carves the slab
+                  (whole && h->emitted.prod1_valid) ? (const uint32_t*)(h->slab + h->emitted.prod1_off) : nullptr);
+  if (st == C2A_OK && whole) { h->emitted.wire = d_wire; h->emitted.identity = identity; }  // stay valid until the next call that carves the slab
   if (st == C2A_OK && !outputs_on_device) {
     phase_begin(h, "d2h");
     if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
@@ -1431,6 +1435,14 @@ int c2a_emitted_build_circuit_device(c2a_handle* h, const uint32_t* input_signal
                                      uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
                                      uint64_t* err_index) {
   return emitted_build_impl(h, input_signals, n_in, output_signals, n_out, d_order_out, d_wire_of_node, d_new_gates, wire_count, err_index, true);
+}
+int c2a_emitted_build_range_device(c2a_handle* h, uint64_t gate_lo, uint64_t gate_hi, const uint32_t* input_signals, uint32_t n_in,
+                                   const uint32_t* output_signals, uint32_t n_out, uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates,
+                                   uint32_t* wire_count, uint64_t* err_index) {
+  return emitted_build_impl(h, input_signals, n_in, output_signals, n_out, d_order_out, d_wire_of_node, d_new_gates, wire_count, err_index, true, gate_lo, gate_hi);
+}
+const c2a_gate* c2a_emitted_gates_device(c2a_handle* h) {
+  return (h && h->emitted.valid) ? (const c2a_gate*)(h->slab + h->emitted.gates_off) : nullptr;
 }
 
 }  // extern "C"

@@ -61,6 +61,8 @@ struct c2a_handle {
     bool identity = true;            // that build's DFS order was 0..G-1
   } emitted;
   // single-kernel path (c2a_fused.cuh): double-buffered control block (scalars, grid barrier, look-back slots)
+  char* plan_buf = nullptr;  // c2a_plan_shards_device scratch (grow-only, outside the slab)
+  size_t plan_bytes = 0;
   char* fused_ctl = nullptr;
   int fused_parity = 0;
   struct c2a_compiler* host_comp = nullptr;  // kept alive when the exact host emitter had to run (sparse ids)

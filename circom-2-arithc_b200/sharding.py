@@ -85,6 +85,25 @@ def plan_shards(gates: np.ndarray, node_bound: int, input_nodes, output_nodes, w
     return list(zip(bounds[:-1], bounds[1:]))
 
 
+def plan_shards_device(ctx, d_gates_ptr: int, G: int, node_bound: int, input_nodes, output_nodes, world: int) -> Optional[List[Tuple[int, int]]]:
+    """plan_shards on the GPU (c2a_plan_shards_device): the gate vector is already resident at device address d_gates_ptr (e.g. a
+    torch tensor's data_ptr()).  Same result as plan_shards() whenever a neighbouring cut exists for every target."""
+    import ctypes as C
+    from ._lib import lib
+    ins = np.ascontiguousarray(input_nodes, dtype=np.uint32)
+    outs = np.ascontiguousarray(output_nodes, dtype=np.uint32)
+    bounds = (C.c_uint64 * (world + 1))()
+    n = C.c_uint32(0)
+    vp = C.c_void_p
+    st = lib.c2a_plan_shards_device(ctx.handle, vp(d_gates_ptr), G, node_bound, ins.ctypes.data_as(vp), len(ins), outs.ctypes.data_as(vp), len(outs),
+                                    world, bounds, C.byref(n))
+    if st != 0:
+        raise RuntimeError(f"c2a_plan_shards_device -> {st}: {ctx.last_error()}")
+    if n.value != world:
+        return None
+    return [(int(bounds[k]), int(bounds[k + 1])) for k in range(world)]
+
+
 def rebase_offsets(counts: np.ndarray, rank: int, shared_io: bool):
     """counts[r] = (n_in, n_mid, n_out, G) of rank r  ->  (off_in, off_mid, off_out, gate_base) for c2a_rebase_wires_device.
     shared_io=True : every rank was given the SAME global input/output lists (sharded build of one circuit);

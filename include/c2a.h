@@ -144,6 +144,17 @@ int c2a_rebase_wire_ids_gathered_device(c2a_handle*, uint32_t* d_wire_ids, uint6
 int c2a_rebase_wire_map_device(c2a_handle*, uint32_t* d_wire_of_node, uint64_t n, uint32_t n_in, uint32_t n_mid,
                                uint32_t off_in, uint32_t off_mid, uint32_t off_out);
 
+/* Where does ONE gate vector split into `world` independent component subtrees?  bounds_out[world + 1] receives
+ * contiguous gate ranges [bounds[k], bounds[k+1]) balanced by gate count such that no dependency edge (src/compiler.rs:408-421) and
+ * no non-I/O node crosses a bound: building every range on its own GPU with the SAME input / output node lists and shifting the wire
+ * ids by the other ranks' intermediate counts (c2a_emitted_gather_device, c2a_rebase_*) reproduces the single-GPU circuit bit for
+ * bit.  *n_shards = world, or 1 when the DAG has fewer independent subtrees (one SHA-256 / Keccak instance, one long chain):
+ * replicas only.  d_gates: DEVICE pointer (it may be the resident emitted circuit); the I/O node lists are host pointers.  All on
+ * the device (first / last use per node, dependency spans, one running maximum) - the numpy planner of the Python mirror walks
+ * the gate vector on the host. */
+int c2a_plan_shards_device(c2a_handle*, const c2a_gate* d_gates, uint64_t G, uint32_t node_bound, const uint32_t* input_nodes, uint32_t n_in,
+                           const uint32_t* output_nodes, uint32_t n_out, uint32_t world, uint64_t* bounds_out, uint32_t* n_shards);
+
 /* Level-synchronous Kahn frontier over the same dependency relation (not the reference order; used for the
  * layer-wise sweeps and the evaluator).  level_order[G] is level-major; level_off[*n_levels+1] delimits levels
  * (caller provides capacity level_cap+1; more levels than level_cap -> C2A_ERR_INVALID_ARGUMENT).
@@ -205,6 +216,17 @@ int c2a_emitted_build_circuit(c2a_handle*, const uint32_t* input_signals, uint32
 int c2a_emitted_build_circuit_device(c2a_handle*, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                                      uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates, uint32_t* wire_count,
                                      uint64_t* err_index);
+
+/* One shard of a sharded build of the resident circuit: c2a_emitted_build_circuit_device restricted to the gates
+ * [gate_lo, gate_hi) - a range c2a_plan_shards_device returned, so no dependency edge and no non-I/O node leaves it.  The I/O lists
+ * are the GLOBAL ones (every rank passes the same); order entries are local to the range (0 .. gate_hi - gate_lo), wire ids local to
+ * the shard: c2a_rebase_wires_device / c2a_rebase_wire_map_device shift them once the ranks have exchanged their counts. */
+int c2a_emitted_build_range_device(c2a_handle*, uint64_t gate_lo, uint64_t gate_hi, const uint32_t* input_signals, uint32_t n_in,
+                                   const uint32_t* output_signals, uint32_t n_out, uint32_t* d_order_out, uint32_t* d_wire_of_node, c2a_gate* d_new_gates,
+                                   uint32_t* wire_count, uint64_t* err_index);
+/* DEVICE pointer to the resident node-id gate vector (n_gates records; NULL when nothing is resident).  Valid until the next call
+ * on the handle that emits, or that grows the handle's scratch (any build): take it again after such a call. */
+const c2a_gate* c2a_emitted_gates_device(c2a_handle*);
 
 /* Sharded builds, second half: after c2a_emitted_build_circuit_device(..., d_new_gates = NULL, ...) numbered the
  * rank's own circuit and the ranks all-gathered their (n_in, n_mid, n_out, G) counts, this gathers the renumbered gates and

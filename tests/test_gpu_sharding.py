@@ -60,3 +60,28 @@ def test_sharded_build_two_gpus():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert all(ok for _, ok in res), res
+
+
+@pytest.mark.parametrize("name", ["mimc_late", "mimc_inorder", "keccak2", "sha", "shared_node"])
+def test_device_shard_planner_matches_the_host_planner(c2a, ctx, name):
+    """c2a_plan_shards_device (first / last use per node, dependency spans, one running maximum on the GPU) against
+    sharding.plan_shards (numpy on the host) - 1 GPU is enough: planning is per rank"""
+    import torch
+    if name == "shared_node":   # two otherwise independent gates share the producer-less, non-I/O node 9
+        cases = [(np.array([[0, 1, 9, 5], [0, 2, 9, 6]], dtype=np.uint32), 10, [1, 2], [5, 6]),
+                 (np.array([[0, 1, 9, 5], [0, 2, 9, 6]], dtype=np.uint32), 10, [1, 2, 9], [5, 6])]
+    else:
+        wl = {"mimc_late": lambda: c2a.workloads.mimc_chains(61, rounds=17, variant="late"),
+              "mimc_inorder": lambda: c2a.workloads.mimc_chains(40, rounds=9, variant="inorder"),
+              "keccak2": lambda: c2a.workloads.keccak_shaped(instances=2, rounds=2),
+              "sha": lambda: c2a.workloads.sha256_shaped(rounds=3)}[name]()
+        comp = c2a.Compiler(context=ctx)
+        comp.emit_events(wl.events)
+        cases = [(comp.gate_array(), comp.node_count + 1, comp.signal_nodes(np.array(sorted(wl.inputs), dtype=np.uint32)),
+                  comp.signal_nodes(np.array(sorted(wl.outputs), dtype=np.uint32)))]
+    for g, nb, ins, outs in cases:
+        d = torch.from_numpy(np.ascontiguousarray(g).view(np.int32)).to("cuda:0")
+        for world in (1, 2, 3, 4, 8):
+            want = c2a.sharding.plan_shards(g, nb, ins, outs, world)
+            got = c2a.sharding.plan_shards_device(ctx, d.data_ptr(), g.shape[0], nb, ins, outs, world)
+            assert got == want, (name, world, got, want)

@@ -13,4 +13,4 @@ lscpu | grep -i -E "numa|socket|model name" | head
 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/r2_bench_2gpu.json 2> gpurun_out/r2_bench_2gpu.err; echo "rc=$?"
 tail -5 gpurun_out/r2_bench_2gpu.err
 python tools/show_bench.py gpurun_out/r2_bench_2gpu.json | grep -E "^value|multi_gpu|e2e"
-timeout 600 python -m pytest tests/test_gpu_sharding.py -x -q 2>&1 | tail -3
+

@@ -26,6 +26,6 @@ for name, x in d.get("kahn", {}).items():
     print("    ", x["phases_ms"])
 if "sweeps" in d:
     print("sweeps", {k: v for k, v in d["sweeps"].items() if k != "note"})
-for k in ("e2e_pipelined", "from_source", "e2e_host_emitter", "cpu_baseline", "multi_gpu_parity", "extras_wall_s"):
+for k in ("strong_scaling", "e2e_pipelined", "from_source", "e2e_host_emitter", "cpu_baseline", "multi_gpu_parity", "extras_wall_s"):
     if k in d:
         print(k, d[k])
