@@ -650,10 +650,10 @@ def main():
     ap.add_argument("--source-chains", type=int, default=0, help="MiMC chains of the from_source leg (default: --chains, the headline workload)")
     ap.add_argument("--no-phase-timing", action="store_true", help="diagnostic: run the timed loop without the per-kernel CUDA events")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the strong-scaling leg (one circuit sharded across the ranks)")
-    ap.add_argument("--legs", default="all", help="comma list of the extra sub-records (N = 1): configs,variants,kahn,sweeps,same_config  (all | none)")
+    ap.add_argument("--legs", default="all", help="comma list of the extra sub-records (N = 1): configs,variants,kahn,sweeps,same_config,deep  (all | none)")
     ap.add_argument("--extra-steps", type=int, default=20, help="timed steps of the small-config sub-records")
     args = ap.parse_args()
-    legs = set("configs,variants,kahn,sweeps,same_config".split(",")) if args.legs == "all" else set(x for x in args.legs.split(",") if x and x != "none")
+    legs = set("configs,variants,kahn,sweeps,same_config,deep".split(",")) if args.legs == "all" else set(x for x in args.legs.split(",") if x and x != "none")
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -1132,6 +1132,28 @@ def main():
             var["inorder_10M"], _sc = circuit_leg(c2a, torch, ctx, dev, stream, wl_in, max(3, K), peak, flush, cpu_backend=True, orc=orc)
             del _sc, wl_in
             extra["variants"] = var
+        if "deep" in legs:
+            # worst-case shapes of the exact-order sort at 1 M gates: one DFS tree holding every gate (reversed chain through the lh / rh
+            # operand: 1 M forward edges), and a fan-in tree emitted root first.  GPU: bounded walks + pointer jumping (k_relax_loop,
+            # k_tree_blocks); CPU: the oracle's DFS (the reference recurses 1 M deep here)
+            Gd = 1_000_000
+            deep = {}
+            for nm, slot in (("reversed_chain_lh_1M", 1), ("reversed_chain_rh_1M", 2)):
+                gd = np.zeros((Gd, 4), dtype=np.uint32)
+                gd[:, 0], gd[:, 3], gd[:, 3 - slot] = 7, 10 + np.arange(Gd), 1
+                gd[:, slot] = 10 + np.arange(Gd) + 1
+                gd[Gd - 1, slot] = 2
+                deep[nm], _k = backend_leg(c2a, torch, ctx, dev, stream, nm, gd, 10 + Gd + 1, [1, 2], [10], 3, peak, orc=orc, oracle_reps=1)
+                del _k
+            Gt = (1 << 20) - 1
+            gi = np.arange(Gt)
+            gt_ = np.zeros((Gt, 4), dtype=np.uint32)
+            gt_[:, 3] = 10 + gi
+            gt_[:, 1] = np.where(2 * gi + 1 < Gt, 10 + 2 * gi + 1, 1)
+            gt_[:, 2] = np.where(2 * gi + 2 < Gt, 10 + 2 * gi + 2, 2)
+            deep["fan_in_tree_root_first_1M"], _k = backend_leg(c2a, torch, ctx, dev, stream, "complete binary fan-in tree, heap order", gt_, 10 + Gt, [1, 2], [10], 3, peak, orc=orc, oracle_reps=1)
+            del _k, gd, gt_
+            extra["worst_case_shapes"] = deep
         if "kahn" in legs:
             kh = {"547_levels": kahn_leg(c2a, torch, ctx, dev, f"{workload_name} (gate vector of the headline circuit)", gates_late, nb, 3, peak)}
             w7 = max(1, G // 7)

@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 
 constexpr int kBlock = 256;
 constexpr uint32_t kNone = C2A_NONE;
+constexpr uint32_t kBigBlock = 1024;  // DFS blocks at least this large go through the pointer-jumping path when they are trees
 static void emit_drop_host(c2a_handle* h);  // c2a_emit.cuh
 // wire[] encoding while numbering is in flight (compiler.rs:388-449):
 //   < kOutPending        : final wire id
@@ -95,9 +96,12 @@ constexpr uint32_t kFirstTag = 0x80000000u;
 // S_QN0 .. S_QN0+kSpecRounds: queue lengths of the speculative relax rounds (round j reads S_QN0+j, appends to S_QN0+j+1);
 // S_QN_LAST != 0 after them means "r[] has not converged yet": every later kernel of the call parks itself and the host
 // drains the queue with synchronised rounds (S_QA / S_QB) before re-issuing the tail of the pipeline.
-constexpr int kSpecRounds = 4;
-enum { S_FLAGS = 0, S_HEAVYN = 1, S_NMID = 2, S_SEEDN = 3, S_ERR_LO = 6, S_ERR_HI = 7, S_QN0 = 8, S_QN_LAST = S_QN0 + kSpecRounds,
-       S_QA = 13, S_QB = 14, S_COUNT = 32 };
+// S_QN0 .. S_QN0+3: rotating queue lengths of the relaxation rounds (k_relax_loop); S_BAR*: grid-barrier counters of the two
+// cooperative kernels of the sort; S_RELAX_ROUNDS / S_ROBUST: diagnostics (rounds run, pointer-jumping stage taken);
+// S_CHG0..+2: "something changed" words of the jumping rounds (round i sets word i % 3 and clears word (i + 1) % 3, which was last
+// read two barriers ago); S_BIGN: nodes in big tree-shaped DFS blocks (k_tree_blocks)
+enum { S_FLAGS = 0, S_HEAVYN = 1, S_NMID = 2, S_SEEDN = 3, S_ERR_LO = 6, S_ERR_HI = 7, S_QN0 = 8,
+       S_BAR1 = 16, S_BAR2 = 17, S_RELAX_ROUNDS = 18, S_ROBUST = 19, S_CHG0 = 20 /* 3 rotating words */, S_BIGN = 23, S_BIGBLK = 24, S_CAP0 = 25 /* 3 rotating: walks cut at kHopCap per round */, S_COUNT = 32 };
 enum { F_OOO = 1, F_BAD = 2, F_SELF = 4, F_BAD_IO = 8 };
 
 // Device-side control flow: the host enqueues the whole pipeline without looking at intermediate results; kernels decide
@@ -106,11 +110,9 @@ __device__ __forceinline__ bool sort_wanted(const uint32_t* __restrict__ sc) {  
   uint32_t f = sc[S_FLAGS];
   return !(f & F_BAD) && (f & (F_OOO | F_SELF));
 }
-__device__ __forceinline__ bool sort_parked(const uint32_t* __restrict__ sc) {  // r[] not converged within the speculative rounds
-  return sc[S_QN_LAST] != 0;
-}
-__device__ __forceinline__ bool tail_parked(const uint32_t* __restrict__ sc) {  // kernels after the sort: bad input, pending sort, cycle found
-  return (sc[S_FLAGS] & F_BAD) || sc[S_QN_LAST] != 0 || sc[S_ERR_HI] != 0xFFFFFFFFu;
+__device__ __forceinline__ bool sort_parked(const uint32_t*) { return false; }  // (the relaxation always converges on the device: k_relax_loop)
+__device__ __forceinline__ bool tail_parked(const uint32_t* __restrict__ sc) {  // kernels after the sort: bad input, cycle found
+  return (sc[S_FLAGS] & F_BAD) || sc[S_ERR_HI] != 0xFFFFFFFFu;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -262,29 +264,152 @@ __device__ __forceinline__ void relax_from(uint32_t cur, uint32_t val, const uin
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_relax_seed(const uint2* __restrict__ dep, const uint32_t* __restrict__ seeds, uint32_t* __restrict__ r,
-                                                       uint32_t* __restrict__ inq, uint32_t* __restrict__ q, uint32_t* __restrict__ qn,
-                                                       const uint32_t* __restrict__ sc) {
-  if (!sort_wanted(sc)) return;
-  const uint32_t n = sc[S_SEEDN];
-  // r[d] <= d always, so val=u can only lower r[d] along a forward edge (d > u): exactly the gates k_deps collected
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    uint32_t u = seeds[i];
-    relax_from(u, u, dep, r, inq, q, qn);
+// Grid barrier of the cooperative kernels of the sort (all CTAs co-resident): bar.sync orders the CTA before thread 0's release,
+// the acquire poll orders it - and through the second bar.sync the whole CTA - behind every other CTA's release.
+__device__ __forceinline__ void sort_grid_bar(unsigned int* bar, unsigned int& epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    epoch += gridDim.x;
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");
+    unsigned int v;
+    uint32_t spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+      if (++spins > (1u << 26)) __trap();
+    } while (v < epoch);
+  }
+  __syncthreads();
+}
+
+// relax_from with a bounded walk: after kHopCap hops the node reached is queued and continues in the next round, so one round costs
+// O(queue x kHopCap) whatever the shape of the DAG (an unbounded walk down a 1 M-gate chain is a second of dependent loads).
+// The seeds probe with a short cap (a reversed chain makes EVERY seed walk to the cap); the rounds use a long one, so that a walk
+// inside a shuffled component (hundreds of hops) is not cut into several rounds - a round lasts as long as its longest walk.
+constexpr uint32_t kSeedHopCap = 64, kRoundHopCap = 2048;
+__device__ __forceinline__ void relax_capped(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn, uint32_t* ncut,
+                                             uint32_t cap) {
+  for (uint32_t hop = 0; cur != kNone; ++hop) {
+    if (hop == cap) { enqueue(cur, inq, q, qn); atomicAdd(ncut, 1u); return; }
+    uint2 d = __ldcg(dep + cur);
+    uint32_t nxt = kNone;
+    if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
+      if (val < atomicMin(r + d.y, val)) enqueue(d.y, inq, q, qn);
+    }
+    if (d.x != kNone && val < __ldcg(r + d.x)) {
+      if (val < atomicMin(r + d.x, val)) nxt = d.x;
+    }
+    cur = nxt;
   }
 }
 
-__global__ void __launch_bounds__(kBlock) k_relax_round(const uint2* __restrict__ dep, uint32_t* __restrict__ r, uint32_t* __restrict__ inq,
-                                                        const uint32_t* __restrict__ q_in, const uint32_t* __restrict__ q_in_n,
-                                                        uint32_t* __restrict__ q_out, uint32_t* __restrict__ q_out_n) {
-  uint32_t n = *q_in_n;
-  for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-    uint32_t x = q_in[i];
-    atomicAnd(inq + (x >> 5), ~(1u << (x & 31)));
-    __threadfence();  // clear the flag before sampling r[x]: a later lowering re-queues x
-    uint32_t val = __ldcg(r + x);
-    relax_from(x, val, dep, r, inq, q_out, q_out_n);
+// K5a as ONE cooperative kernel: seeds, then data-driven rounds on device-resident queue counters with a grid barrier between
+// rounds (a host-synchronised round costs ~50 us; a shuffled 10 M-gate vector needs ~90 of them).  When walks keep running into
+// the hop cap - many of them after the second round, or any at all after kPatientRounds - the DAG is deep (a long forward chain) and
+// label-by-label propagation is a latency chain: stage 2 computes, by pointer jumping in O(log depth) sweeps, the
+// minimum of r[] along every gate's chain of smallest-index consumers (up[]: exact for forests, an upper bound otherwise - every
+// value is still the index of a real transitive consumer), then the data-driven rounds finish from the violations that are left.
+constexpr uint32_t kPatientRounds = 4, kMaxDataRounds = 2048;
+__global__ void __launch_bounds__(kBlock) k_relax_loop(const uint2* dep, uint32_t n, const uint32_t* seeds, uint32_t* r, uint32_t* inq, uint32_t* q0, uint32_t* q1,
+                                                       uint32_t* sc) {
+  if (!sort_wanted(sc)) return;
+  unsigned int epoch = 0;
+  unsigned int* bar = reinterpret_cast<unsigned int*>(sc + S_BAR1);
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x, nth = gridDim.x * kBlock;
+  // r[d] <= d always, so val = u can only lower r[d] along a forward edge (d > u): exactly the gates k_deps collected.
+  // When every fourth gate holds a forward edge (a shuffled gate vector) the jumping stage runs FIRST: it replaces millions of
+  // overlapping walks by O(log depth) sweeps, and the data-driven rounds only repair what the chains of smallest-index consumers miss.
+  const uint32_t ns = __ldcg(sc + S_SEEDN);
+  const bool dense_seeds = ns > n / 4;
+  if (!dense_seeds) {
+    for (uint32_t i = tid; i < ns; i += nth) { uint32_t u = __ldcg(seeds + i); relax_capped(u, u, dep, r, inq, q0, sc + S_QN0, sc + S_CAP0, kSeedHopCap); }
   }
+  sort_grid_bar(bar, epoch);
+  uint32_t slot = 0, rounds = 0;
+  uint32_t* qin = q0;
+  uint32_t* qout = q1;
+  uint32_t capw = 0;  // the S_CAP word the previous phase counted into (the seeds: word 0)
+  uint32_t prev_nq = 0xFFFFFFFFu;
+  auto data_rounds = [&](bool patient) -> bool {  // true: drained; false (only when !patient): deep DAG, go pointer jumping
+    for (uint32_t k = 0;; ++k) {
+      const uint32_t nq = __ldcg(sc + S_QN0 + slot);
+      if (!nq) return true;
+      const uint32_t ncut = __ldcg(sc + S_CAP0 + capw);  // walks of the previous phase that ran into the hop cap
+      // deep DAG?  most seeds walked into the (short) cap; many walks still run into the long one; some still do after a few
+      // rounds (one label travelling down one long chain); or the queue stays long and does not shrink (one hop per round through
+      // the rh operand: nothing is ever cut)
+      const bool stuck = k >= 3 && nq > n / 64 && (unsigned long long)nq * 8 > (unsigned long long)prev_nq * 7;
+      if (!patient && ((k == 0 && ncut > n / 8) || (k >= 1 && ncut > n / 64) || (k >= kPatientRounds && ncut) || stuck || k >= kMaxDataRounds)) return false;
+      prev_nq = nq;
+      const uint32_t nslot = (slot + 1) & 3, ncapw = (capw + 1) % 3;
+      if (tid == 0) { sc[S_QN0 + ((nslot + 1) & 3)] = 0; sc[S_CAP0 + (ncapw + 1) % 3] = 0; }
+      for (uint32_t i = tid; i < nq; i += nth) {
+        uint32_t x = __ldcg(qin + i);
+        atomicAnd(inq + (x >> 5), ~(1u << (x & 31)));
+        __threadfence();  // clear the flag before sampling r[x]: a later lowering re-queues x
+        relax_capped(x, __ldcg(r + x), dep, r, inq, qout, sc + S_QN0 + nslot, sc + S_CAP0 + ncapw, kRoundHopCap);
+      }
+      capw = ncapw;
+      sort_grid_bar(bar, epoch);
+      uint32_t* t = qin; qin = qout; qout = t;
+      slot = nslot;
+      ++rounds;
+    }
+  };
+  if (dense_seeds || !data_rounds(false)) {
+    // ---- stage 2: pointer jumping along the smallest-index consumer.  The queues are abandoned (violations are recollected below).
+    uint32_t* upA = q0;
+    uint32_t* upB = q1;
+    sort_grid_bar(bar, epoch);  // every CTA has read the queue length that sent it here before the counters are reset
+    for (uint32_t v = tid; v < n; v += nth) upA[v] = kNone;
+    for (uint32_t w = tid; w < (n + 31) / 32 + 1; w += nth) inq[w] = 0;
+    if (tid == 0) {
+      sc[S_QN0] = sc[S_QN0 + 1] = sc[S_QN0 + 2] = sc[S_QN0 + 3] = 0;
+      sc[S_CHG0] = sc[S_CHG0 + 1] = sc[S_CHG0 + 2] = 0;
+      sc[S_CAP0] = sc[S_CAP0 + 1] = sc[S_CAP0 + 2] = 0;
+      sc[S_ROBUST] = 1;
+    }
+    sort_grid_bar(bar, epoch);
+    for (uint32_t u = tid; u < n; u += nth) {
+      const uint2 d = __ldcg(dep + u);
+      if (d.x != kNone && d.x != u) atomicMin(upA + d.x, u);
+      if (d.y != kNone && d.y != d.x && d.y != u) atomicMin(upA + d.y, u);
+    }
+    sort_grid_bar(bar, epoch);
+    for (uint32_t it = 0;; ++it) {
+      // synchronous doubling on the pointers (upA read, upB written), r[] in place: a fresher r[a] only covers MORE of a's chain
+      uint32_t chg = 0;
+      for (uint32_t v = tid; v < n; v += nth) {
+        const uint32_t a = __ldcg(upA + v);
+        uint32_t nu = kNone;
+        if (a != kNone) {
+          const uint32_t ra = __ldcg(r + a);
+          if (ra < __ldcg(r + v)) atomicMin(r + v, ra);
+          nu = __ldcg(upA + a);
+          chg = 1;
+        }
+        upB[v] = nu;
+      }
+      if (__syncthreads_or(chg) && threadIdx.x == 0) atomicOr(sc + S_CHG0 + it % 3, 1u);
+      if (tid == 0) sc[S_CHG0 + (it + 1) % 3] = 0;
+      sort_grid_bar(bar, epoch);
+      uint32_t* t = upA; upA = upB; upB = t;
+      ++rounds;
+      if (!__ldcg(sc + S_CHG0 + it % 3)) break;
+      if (it > 64) break;  // 2^64 > any depth: cannot happen
+    }
+    // the chain of smallest-index consumers misses the other consumers of a shared gate: collect what is still violated ...
+    qin = q0; qout = q1; slot = 0; capw = 0;   // (up[] is dead: the arrays are queues again)
+    for (uint32_t u = tid; u < n; u += nth) {
+      const uint2 d = __ldcg(dep + u);
+      const uint32_t ru = __ldcg(r + u);
+      if (d.x != kNone && ru < __ldcg(r + d.x)) { if (ru < atomicMin(r + d.x, ru)) enqueue(d.x, inq, qin, sc + S_QN0); }
+      if (d.y != kNone && d.y != d.x && ru < __ldcg(r + d.y)) { if (ru < atomicMin(r + d.y, ru)) enqueue(d.y, inq, qin, sc + S_QN0); }
+    }
+    sort_grid_bar(bar, epoch);
+    // ... and finish data-driven (every round strictly lowers some r[]: it terminates)
+    data_rounds(true);
+  }
+  if (tid == 0) sc[S_RELAX_ROUNDS] = rounds;
 }
 
 // K5b: block sizes.  size[root] = number of items first reached from root.
@@ -446,19 +571,147 @@ __global__ void __launch_bounds__(kBlock) k_roots(const uint32_t* __restrict__ r
       order[o] = v;
     } else {
       heavy[atomicAdd(scalars + S_HEAVYN, 1u)] = v;
+      if (sz >= kBigBlock) atomicAdd(scalars + S_BIGBLK, 1u);  // k_tree_blocks looks at it: a one-thread DFS would take sz x ~6 us
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K5c for BIG blocks that are trees (every gate of the block has exactly one consumer inside the block: a reversed chain, a
+// forward chain through either operand, any fan-in tree).  There the DFS post-order is a closed formula,
+//     post(v) = off[R] + L(v) + size(v) - 1,      L(v) = sum over the ancestors a of v (v included) that are rh children of
+//                                                        size(lh sibling subtree)   (topological_sort.rs:42-47: lh before rh),
+// and both size() and L() are pointer-jumping computations: O(log depth) sweeps instead of size x ~6 us of dependent loads in one
+// thread (a 1 M-gate chain: 6 s; the reference's recursion: 0.15 s).  One cooperative kernel; it exits at once when k_roots saw no
+// big block.  Blocks with a shared gate (in-block in-degree 2: a DAG, where "who visits first" is the sequential part of the
+// problem) and blocks holding a cycle are flagged in sz[R] and left to k_tree_dfs.
+//   indeg, list: the two relaxation queues (dead by now);  par / anc0 / anc1 / v0 / v1 / sz: six more gate-indexed arrays.
+// ---------------------------------------------------------------------------------------------------
+struct TreeArrays { uint32_t *indeg, *list, *par, *anc0, *anc1, *v0, *v1, *sz; };
+constexpr uint32_t kNotATree = 0xFFFFFFFFu;
+__global__ void __launch_bounds__(kBlock) k_tree_blocks(const uint2* dep, const uint32_t* r, const uint32_t* off, uint32_t n, uint32_t* order, TreeArrays t,
+                                                        uint32_t* sc) {
+  if (!sort_wanted(sc) || __ldcg(sc + S_BIGBLK) == 0) return;
+  unsigned int epoch = 0;
+  unsigned int* bar = reinterpret_cast<unsigned int*>(sc + S_BAR2);
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x, nth = gridDim.x * kBlock;
+  const int lane = threadIdx.x & 31;
+  auto big = [&](uint32_t R) { return __ldcg(off + R + 1) - __ldcg(off + R) >= kBigBlock; };
+  for (uint32_t v = tid; v < n; v += nth) { t.indeg[v] = 0; t.sz[v] = 0; }
+  if (tid == 0) { sc[S_CHG0] = sc[S_CHG0 + 1] = sc[S_CHG0 + 2] = 0; sc[S_BIGN] = 0; }
+  sort_grid_bar(bar, epoch);
+  // T1: parents and in-block in-degrees of the gates of big blocks
+  for (uint32_t u = tid; u < n; u += nth) {
+    const uint32_t R = __ldcg(r + u);
+    if (!big(R)) continue;
+    const uint2 d = __ldcg(dep + u);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint32_t x = j ? d.y : d.x;
+      if (x == kNone || (j && d.y == d.x) || __ldcg(r + x) != R) continue;
+      t.par[x] = u | (j ? 0x80000000u : 0u);  // (with in-degree 1 there is one writer)
+      if (atomicAdd(t.indeg + x, 1u) >= 1u || x == R) t.sz[R] = kNotATree;  // shared gate / a cycle through the root: k_tree_dfs
+    }
+  }
+  sort_grid_bar(bar, epoch);
+  // T2: the gates of big TREE blocks: list, initial ancestors and counts
+  {
+    const uint32_t iters = (n + nth - 1) / nth;
+    for (uint32_t it = 0; it < iters; ++it) {
+      const uint32_t v = it * nth + tid;
+      bool in = false;
+      if (v < n) {
+        const uint32_t R = __ldcg(r + v);
+        in = big(R) && __ldcg(t.sz + R) != kNotATree;
+        if (in) { t.anc0[v] = v == R ? kNone : (__ldcg(t.par + v) & 0x7FFFFFFFu); t.v0[v] = 1; }
+      }
+      const uint32_t m = __ballot_sync(0xFFFFFFFFu, in);
+      if (m) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(sc + S_BIGN, (uint32_t)__popc(m));
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (in) t.list[base + __popc(m & ((1u << lane) - 1))] = v;
+      }
+    }
+  }
+  sort_grid_bar(bar, epoch);
+  const uint32_t nb = __ldcg(sc + S_BIGN);
+  if (nb == 0) return;  // every big block is a DAG: nothing to do here (uniform)
+  uint32_t *a0 = t.anc0, *a1 = t.anc1, *c0 = t.v0, *c1 = t.v1;
+  // T3: subtree sizes.  cnt_k[v] = gates of v's subtree at distance < 2^k, anc_k[v] = the ancestor at distance 2^k:
+  //     cnt_{k+1}[a] = cnt_k[a] + sum of cnt_k[v] over the v with anc_k[v] = a;  anc_{k+1}[v] = anc_k[anc_k[v]]
+  for (uint32_t it = 0;; ++it) {
+    for (uint32_t i = tid; i < nb; i += nth) { const uint32_t v = __ldcg(t.list + i); c1[v] = __ldcg(c0 + v); }
+    if (tid == 0) sc[S_CHG0 + (it + 1) % 3] = 0;
+    sort_grid_bar(bar, epoch);
+    uint32_t chg = 0;
+    for (uint32_t i = tid; i < nb; i += nth) {
+      const uint32_t v = __ldcg(t.list + i), a = __ldcg(a0 + v);
+      uint32_t na = kNone;
+      if (a != kNone) { atomicAdd(c1 + a, __ldcg(c0 + v)); na = __ldcg(a0 + a); chg = 1; }
+      a1[v] = na;
+    }
+    if (__syncthreads_or(chg) && threadIdx.x == 0) atomicOr(sc + S_CHG0 + it % 3, 1u);
+    sort_grid_bar(bar, epoch);
+    uint32_t* x = a0; a0 = a1; a1 = x;
+    x = c0; c0 = c1; c1 = x;
+    if (!__ldcg(sc + S_CHG0 + it % 3) || it > 40) break;
+  }
+  // sizes are final in c0; keep them in sz[], start the offset sums: w(v) = size(lh sibling) for an rh child whose lh sibling is a
+  // child too, else 0
+  for (uint32_t i = tid; i < nb; i += nth) t.sz[__ldcg(t.list + i)] = __ldcg(c0 + __ldcg(t.list + i));
+  sort_grid_bar(bar, epoch);
+  if (tid == 0) sc[S_CHG0] = sc[S_CHG0 + 1] = sc[S_CHG0 + 2] = 0;  // (behind a barrier: every CTA has left the loop above)
+  for (uint32_t i = tid; i < nb; i += nth) {
+    const uint32_t v = __ldcg(t.list + i), R = __ldcg(r + v);
+    uint32_t w = 0, a = kNone;
+    if (v != R) {
+      const uint32_t pw = __ldcg(t.par + v);
+      a = pw & 0x7FFFFFFFu;
+      if (pw & 0x80000000u) {  // rh child: everything under the lh sibling is emitted first
+        const uint32_t c1n = __ldcg(dep + a).x;
+        if (c1n != kNone && c1n != v && __ldcg(r + c1n) == R) w = __ldcg(t.sz + c1n);
+      }
+    }
+    c0[v] = w;
+    a0[v] = a;
+  }
+  sort_grid_bar(bar, epoch);
+  // T4: L(v) = w(v) + L(parent): pull-doubling (both arrays ping-pong)
+  for (uint32_t it = 0;; ++it) {
+    uint32_t chg = 0;
+    for (uint32_t i = tid; i < nb; i += nth) {
+      const uint32_t v = __ldcg(t.list + i), a = __ldcg(a0 + v);
+      uint32_t L = __ldcg(c0 + v), na = kNone;
+      if (a != kNone) { L += __ldcg(c0 + a); na = __ldcg(a0 + a); chg = 1; }
+      c1[v] = L;
+      a1[v] = na;
+    }
+    if (__syncthreads_or(chg) && threadIdx.x == 0) atomicOr(sc + S_CHG0 + it % 3, 1u);
+    if (tid == 0) sc[S_CHG0 + (it + 1) % 3] = 0;
+    sort_grid_bar(bar, epoch);
+    uint32_t* x = a0; a0 = a1; a1 = x;
+    x = c0; c0 = c1; c1 = x;
+    if (!__ldcg(sc + S_CHG0 + it % 3) || it > 40) break;
+  }
+  // T5: sorted.push order (topological_sort.rs:47)
+  for (uint32_t i = tid; i < nb; i += nth) {
+    const uint32_t v = __ldcg(t.list + i), R = __ldcg(r + v);
+    order[__ldcg(off + R) + __ldcg(c0 + v) + __ldcg(t.sz + v) - 1u] = v;
   }
 }
 
 __global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ heavy,
                                                   const uint2* __restrict__ dep, const uint32_t* __restrict__ r,
                                                   const uint32_t* __restrict__ off, uint8_t* __restrict__ state,
-                                                  uint32_t* __restrict__ order, uint32_t* scalars) {
+                                                  uint32_t* __restrict__ order, const uint32_t* __restrict__ tree_sz, uint32_t* scalars) {
   if (!sort_wanted(scalars) || sort_parked(scalars)) return;
   uint32_t nh = scalars[S_HEAVYN];
+  const bool trees_done = scalars[S_BIGBLK] != 0;  // k_tree_blocks ran: it emitted the big blocks it did not flag
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += gridDim.x * blockDim.x) {
     const uint32_t R = heavy[i];
     const uint32_t base = off[R], end = off[R + 1];
+    if (trees_done && end - base >= kBigBlock && tree_sz[R] != kNotATree) continue;
     uint32_t emit = base, top = end;
     // state: 0 unvisited, 1 entered (lh next), 2 (rh next), 3 (both examined, emit next), 4 visited
     state[R] = 1;
@@ -869,6 +1122,7 @@ size_t sort_scratch_bytes(uint64_t n) {
   b += align256(n);                // state
   b += align256(4 * ((n + 31) / 32 + 1));  // inq
   b += 3 * align256(4 * n);        // q0 q1 heavy
+  b += 6 * align256(4 * n);        // k_tree_blocks: par, anc x2, value x2, sz
   b += align256(8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(wire_bitmap_words(n), kScanItems) + 2));  // tile_state: block-offset scan + bitmap scan
   b += 2 * align256(4 * ((size_t)wire_bitmap_words(n) + 4));  // first-appearance bitmap + its rank prefix
   b += align256(4 * S_COUNT);
@@ -883,6 +1137,7 @@ bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s) {
   s->q0 = (uint32_t*)slab_alloc(h, 4 * n);
   s->q1 = (uint32_t*)slab_alloc(h, 4 * n);
   s->heavy = (uint32_t*)slab_alloc(h, 4 * n);
+  for (int i = 0; i < 6; ++i) s->tree[i] = (uint32_t*)slab_alloc(h, 4 * n);
   s->tile_state_bytes = 8 * (size_t)(scan_tiles(n, kScanItems) + scan_tiles(wire_bitmap_words(n), kScanItems) + 2);
   s->bitmap_words = wire_bitmap_words(n);
   s->bitmap = (uint32_t*)slab_alloc(h, 4 * ((size_t)s->bitmap_words + 4));
@@ -903,12 +1158,10 @@ void sort_scalars_reset(c2a_handle* h, const SortScratch& s) {
 
 // ---------------------------------------------------------------------------------------------------
 // Exact reference order from dependency pairs (K5a-c), enqueued WITHOUT host round trips:
-//   sort_enqueue_relax   scratch init, seed, kSpecRounds relax rounds (a round with an empty queue exits at once)
+//   sort_enqueue_relax   scratch init, k_relax_loop (seeds + every relaxation round, cooperative)
 //   sort_enqueue_emit    block sizes, offsets scan, size-1 blocks, per-tree DFS
 // every kernel reads scalars[] to decide whether it has work (identity order / bad input / r[] not yet converged).
-// After the caller's final status read, sort_pending() tells whether the speculative rounds were not enough; then
-// sort_drain() finishes the relaxation with host-synchronised rounds and the caller re-issues everything from
-// sort_enqueue_emit on (sort_rearm() restores the scalars those kernels consume).
+// (The relaxation runs to convergence inside one cooperative kernel, k_relax_loop: no host-drained continuation any more.)
 // Precondition: scalars zeroed except S_FLAGS, S_ERR = ~0 (sort_scalars_reset + the deps kernel).
 // ---------------------------------------------------------------------------------------------------
 void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s) {
@@ -918,10 +1171,17 @@ void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const Sor
   LAUNCH(h, k_sort_init, grid_for(h, (const void*)k_sort_init, kBlock, (uint64_t)n + 1), kBlock, n, s.r, s.size_off, s.state, s.inq, sc);
   phase_end(h);
   phase_begin(h, "k_relax");
-  LAUNCH(h, k_relax_seed, h->num_sms * 4, kBlock, d_dep, s.heavy, s.r, s.inq, s.q0, sc + S_QN0, sc);  // seeds live in heavy[] until k_roots reuses it
-  const int round_grid = h->num_sms * 4;
-  for (int j = 0; j < kSpecRounds; ++j)
-    LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, (j & 1) ? s.q1 : s.q0, sc + S_QN0 + j, (j & 1) ? s.q0 : s.q1, sc + S_QN0 + j + 1);
+  {  // one cooperative launch: seeds + every relaxation round (the seeds live in heavy[] until k_roots reuses it)
+    static int occ = 0;
+    if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_relax_loop, kBlock, 0) != cudaSuccess || occ < 1)) { cudaGetLastError(); occ = 1; }
+    const uint2* a_dep = d_dep;
+    uint32_t a_n = n;
+    const uint32_t* a_seeds = s.heavy;
+    uint32_t *a_r = s.r, *a_inq = s.inq, *a_q0 = s.q0, *a_q1 = s.q1, *a_sc = sc;
+    void* args[] = {&a_dep, &a_n, &a_seeds, &a_r, &a_inq, &a_q0, &a_q1, &a_sc};
+    cudaLaunchCooperativeKernel((const void*)k_relax_loop, dim3(h->num_sms * std::min(occ, 4)), dim3(kBlock), args, 0, h->stream);
+    h->launches++;
+  }
   phase_end(h);
 }
 
@@ -938,51 +1198,24 @@ void sort_enqueue_emit(c2a_handle* h, const uint2* d_dep, uint32_t n, const Sort
   LAUNCH(h, k_roots, grid_for(h, (const void*)k_roots, kBlock, n), kBlock, s.r, s.size_off, n, d_dep, d_order, s.heavy, sc);
   phase_end(h);
   // heavy count is only known on the device: launch a grid sized for the worst case the hardware can hold
-  phase_begin(h, "k_tree_dfs");
-  LAUNCH(h, k_tree_dfs, h->num_sms * 8, 128, s.heavy, d_dep, s.r, s.size_off, s.state, d_order, sc);
-  phase_end(h);
-}
-
-bool sort_pending(const uint32_t* host_scalars) { return host_scalars[S_QN_LAST] != 0; }
-
-// host-synchronised continuation of the relaxation (deep out-of-order cones); returns the number of extra rounds or <0
-int sort_drain(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s) {
-  cudaStream_t st = h->stream;
-  uint32_t* sc = s.scalars;
-  // the live queue is the output of the last speculative round
-  uint32_t *qin = (kSpecRounds & 1) ? s.q1 : s.q0, *qout = (kSpecRounds & 1) ? s.q0 : s.q1;
-  int nin = S_QN_LAST, nout = S_QA, extra = 0;
-  const int round_grid = h->num_sms * 4;
-  phase_begin(h, "k_relax");
-  while (true) {
-    for (int b = 0; b < 4; ++b) {
-      cudaMemsetAsync(sc + nout, 0, 4, st);
-      LAUNCH(h, k_relax_round, round_grid, kBlock, d_dep, s.r, s.inq, qin, sc + nin, qout, sc + nout);
-      std::swap(qin, qout);
-      nin = nout;
-      nout = (nin == S_QA) ? S_QB : S_QA;
-      ++extra;
-    }
-    if (!cuda_ok(h, cudaMemcpyAsync(h->h_pinned + 32, sc + nin, 4, cudaMemcpyDeviceToHost, st), "relax count copy")) return -1;
-    if (!cuda_ok(h, cudaStreamSynchronize(st), "relax sync")) return -1;
-    if (h->h_pinned[32] == 0) break;
+  phase_begin(h, "k_tree_blocks");
+  {  // big tree-shaped blocks by pointer jumping (cooperative; exits at once when there is none)
+    static int occ = 0;
+    if (!occ && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, (const void*)k_tree_blocks, kBlock, 0) != cudaSuccess || occ < 1)) { cudaGetLastError(); occ = 1; }
+    const uint2* a_dep = d_dep;
+    const uint32_t *a_r = s.r, *a_off = s.size_off;
+    uint32_t a_n = n;
+    uint32_t* a_order = d_order;
+    TreeArrays a_t{s.q0, s.q1, s.tree[0], s.tree[1], s.tree[2], s.tree[3], s.tree[4], s.tree[5]};
+    uint32_t* a_sc = sc;
+    void* args[] = {&a_dep, &a_r, &a_off, &a_n, &a_order, &a_t, &a_sc};
+    cudaLaunchCooperativeKernel((const void*)k_tree_blocks, dim3(h->num_sms * std::min(occ, 4)), dim3(kBlock), args, 0, h->stream);
+    h->launches++;
   }
   phase_end(h);
-  h->relax_fallback_rounds += extra;
-  return extra;
-}
-
-// after sort_drain: everything sort_enqueue_emit and the wire kernels consume is put back to its initial state
-void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s) {
-  cudaStream_t st = h->stream;
-  uint32_t* sc = s.scalars;
-  cudaMemsetAsync(sc + S_HEAVYN, 0, 4 * 2, st);  // heavy count, n_mid
-  cudaMemsetAsync(sc + S_ERR_LO, 0xFF, 8, st);
-  cudaMemsetAsync(sc + S_QN_LAST, 0, 4, st);
-  cudaMemsetAsync(s.tile_state, 0, s.tile_state_bytes, st);
-  cudaMemsetAsync(s.bitmap, 0, 4 * ((size_t)s.bitmap_words + 4), st);
-  cudaMemsetAsync(s.size_off, 0, 4 * ((size_t)n + 1), st);
-  cudaMemsetAsync(s.state, 0, n, st);
+  phase_begin(h, "k_tree_dfs");
+  LAUNCH(h, k_tree_dfs, h->num_sms * 8, 128, s.heavy, d_dep, s.r, s.size_off, s.state, d_order, (const uint32_t*)s.tree[5], sc);
+  phase_end(h);
 }
 
 // status words -> reference error (topological_sort.rs:34-38)
@@ -1131,13 +1364,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   const uint32_t* hs = hp + 64;
   if (io_flags_dev && hs[S_COUNT]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
   if (hs[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "a gate references a node id >= node_bound (%u)", p.node_bound);
-  if (sort_pending(hs)) {
-    if (sort_drain(h, dep, G, s) < 0) return C2A_ERR_CUDA;
-    sort_rearm(h, G, s);
-    if (p.want_wire) cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, st);
-    enqueue_tail();
-    if (!read_status()) return C2A_ERR_CUDA;
-  }
+  h->relax_fallback_rounds = hs[S_RELAX_ROUNDS] | (hs[S_ROBUST] ? 0x10000u : 0u);  // diagnostics: rounds run; bit 16 = pointer-jumping stage taken
   int stt = sort_status(h, hs, err_index);
   if (stt != C2A_OK) return stt;
   if (identity_out) *identity_out = !(hs[S_FLAGS] & (F_OOO | F_SELF));
@@ -1400,11 +1627,6 @@ int c2a_topo_sort_deps(c2a_handle* h, uint64_t n, const uint64_t* dep_off, const
   if (!tail()) return C2A_ERR_CUDA;
   const uint32_t* hs = hp + 64;
   if (hs[S_FLAGS] & F_BAD) return fail(h, C2A_ERR_INVALID_ARGUMENT, "dependency rows must have <= 2 entries with indices < n");
-  if (sort_pending(hs)) {
-    if (sort_drain(h, dep, nn, s) < 0) return C2A_ERR_CUDA;
-    sort_rearm(h, nn, s);
-    if (!tail()) return C2A_ERR_CUDA;
-  }
   st = sort_status(h, hs, err_index);
   if (st == C2A_OK) {
     cudaMemcpyAsync(order_out, d_order, 4 * n, cudaMemcpyDeviceToHost, stq);

@@ -95,6 +95,7 @@ struct SortScratch {
   uint32_t* q0;
   uint32_t* q1;
   uint32_t* heavy;     // n
+  uint32_t* tree[6];   // n each: k_tree_blocks (parents, ancestors x2, values x2, subtree sizes)
   unsigned long long* tile_state;   // look-back states of the block-offset scan ...
   unsigned long long* tile_state2;  // ... and of the wire-numbering bitmap scan (one allocation, zeroed together)
   uint32_t* bitmap;                 // first-appearance bitmap over the 3n (position, slot) pairs
@@ -108,9 +109,6 @@ bool sort_scratch_carve(c2a_handle* h, uint64_t n, SortScratch* s);
 void sort_scalars_reset(c2a_handle* h, const SortScratch& s);
 void sort_enqueue_relax(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s);
 void sort_enqueue_emit(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s, uint32_t* d_order);
-bool sort_pending(const uint32_t* host_scalars);
-int sort_drain(c2a_handle* h, const uint2* d_dep, uint32_t n, const SortScratch& s);
-void sort_rearm(c2a_handle* h, uint32_t n, const SortScratch& s);
 int sort_status(c2a_handle* h, const uint32_t* host_scalars, uint64_t* err_index);
 
 int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n);

@@ -21,6 +21,9 @@ for name, x in d.get("variants", {}).items():
     print(f"variant {name}: {x['gates']} gates value {x['value']/1e6:.1f} M/s ({x['ms_per_step']:.3f} ms) sort {x['topo_sort_ms']:.3f} ms cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s fallback {x.get('relax_fallback_rounds')}")
     if "phases_ms" in x:
         print("    ", x["phases_ms"])
+for name, x in d.get("worst_case_shapes", {}).items():
+    print(f"deep {name}: {x['gates']} gates value {x['value']/1e6:.1f} M/s ({x['ms_per_step']:.3f} ms) cpu_backend {x.get('cpu_backend_gates_per_s', 0)/1e6:.2f} M/s x{x.get('speedup_vs_cpu_backend', 0):.1f} rounds {x.get('relax_fallback_rounds')}")
+    print("    ", x["phases_ms"])
 for name, x in d.get("kahn", {}).items():
     print(f"kahn {name}: {x['gates']} gates {x['levels']} levels kernels {x['ms_kernels']:.3f} ms call {x['ms_call']:.3f} ms {x['achieved_gbs']:.0f} GB/s frac {x['frac']:.3f}")
     print("    ", x["phases_ms"])
