@@ -37,7 +37,7 @@ constexpr uint32_t kOutBase = 0x3FFFFFFFu;                // wire[] tag of outpu
 constexpr uint32_t kOutFloor = 0x20000000u;
 // scalars of the fused kernel
 enum { FS_G = 0, FS_C, FS_S, FS_EFLAGS, FS_NEFF, FS_ROUNDS, FS_BFLAGS, FS_SEEDN, FS_HEAVYN, FS_NMID, FS_ERR_LO = 10 /* ~(root << 32 | i), max = smallest; 0 = no cycle */, FS_ERR_HI = 11, FS_DONE = 12,
-       FS_RELAX_ROUNDS = 13, FS_QN = 16 /* 4 rotating queue counters */, FS_MSF = 20 /* 4 rotating: cand / cur counters */, FS_COUNT = 32 };
+       FS_RELAX_ROUNDS = 13, FS_NCUT = 14, FS_QN = 16 /* 4 rotating queue counters */, FS_MSF = 20 /* 4 rotating: cand / cur counters */, FS_COUNT = 32 };
 
 struct FusedParams {
   const uint8_t* kinds;
@@ -203,8 +203,13 @@ __device__ __forceinline__ void fused_enqueue(uint32_t x, uint32_t* inq, uint32_
   uint32_t old = atomicOr(inq + (x >> 5), bit);
   if (!(old & bit)) q[atomicAdd(qn, 1u)] = x;
 }
-__device__ __forceinline__ void fused_relax_from(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn) {
-  while (cur != kNone) {
+// (walks are bounded like in k_relax_loop; a stream whose DAG turns out to be deep leaves the fused kernel - EF_DEEP - and goes
+//  through the multi-kernel path, which has the pointer-jumping stages)
+constexpr uint32_t EF_DEEP = 512;
+__device__ __forceinline__ void fused_relax_from(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn,
+                                                 uint32_t cap, uint32_t* ncut) {
+  for (uint32_t hop = 0; cur != kNone; ++hop) {
+    if (hop == cap) { fused_enqueue(cur, inq, q, qn); atomicAdd(ncut, 1u); return; }
     uint2 d = ldg2(dep + cur);
     uint32_t nxt = kNone;
     if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
@@ -568,25 +573,31 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
   const bool sorted = (bflags & (F_OOO | F_SELF)) != 0;  // otherwise the DFS post-order is 0..G-1
   if (sorted) {
     // ================= F9: exact DFS order (K5a-c) =================
-    {  // seed: r[d] can only be lowered along a forward edge
-      const uint32_t ns = ldg2(sc + FS_SEEDN);
-      FUSED_FOR(i, ns) { uint32_t u = ldg2(P.heavy + i); fused_relax_from(u, u, P.dep, P.r, P.inq, P.q0, sc + FS_QN); }
-    }
-    grid_bar(P, cx);
-    {
-      uint32_t slot = 0, rr = 0;
+    const uint32_t ns = ldg2(sc + FS_SEEDN);
+    const bool sizable = G > 4096;  // below that even the quadratic worst case is microseconds
+    bool deep = sizable && ns > G / 4;  // a forward edge in every fourth gate: the jumping stage of the multi-kernel path is the tool
+    if (!deep) {  // seed: r[d] can only be lowered along a forward edge
+      FUSED_FOR(i, ns) { uint32_t u = ldg2(P.heavy + i); fused_relax_from(u, u, P.dep, P.r, P.inq, P.q0, sc + FS_QN, kSeedHopCap, sc + FS_NCUT); }
+      grid_bar(P, cx);
+      uint32_t slot = 0, rr = 0, prev_nq = 0xFFFFFFFFu;
       uint32_t* qin = P.q0;
       uint32_t* qout = P.q1;
       while (true) {
-        const uint32_t nq = ldg2(sc + FS_QN + slot);
+        const uint32_t nq = ldg2(sc + FS_QN + slot), ncut = ldg2(sc + FS_NCUT);
         if (!nq) break;
+        // the criteria of k_relax_loop: walks keep running into the cap, or the queue stays long (one hop per round through rh)
+        if (sizable && ((rr == 0 && ncut > G / 8) || (rr >= 1 && ncut > G / 64) || (rr >= 3 && nq > G / 64 && (unsigned long long)nq * 8 > (unsigned long long)prev_nq * 7) ||
+                        (rr >= kPatientRounds && ncut) || rr >= kMaxDataRounds)) { deep = true; break; }
+        prev_nq = nq;
         const uint32_t nslot = (slot + 1) & 3;
-        if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_QN + ((nslot + 1) & 3)] = 0;
+        grid_bar(P, cx);  // everybody has read the cut count of the previous phase
+        if (blockIdx.x == 0 && threadIdx.x == 0) { sc[FS_QN + ((nslot + 1) & 3)] = 0; sc[FS_NCUT] = 0; }
+        grid_bar(P, cx);
         FUSED_FOR(i, nq) {
           uint32_t x = ldg2(qin + i);
           atomicAnd(P.inq + (x >> 5), ~(1u << (x & 31)));
           __threadfence();
-          fused_relax_from(x, __ldcg(P.r + x), P.dep, P.r, P.inq, qout, sc + FS_QN + nslot);
+          fused_relax_from(x, __ldcg(P.r + x), P.dep, P.r, P.inq, qout, sc + FS_QN + nslot, kRoundHopCap, sc + FS_NCUT);
         }
         grid_bar(P, cx);
         uint32_t* t = qin; qin = qout; qout = t;
@@ -594,6 +605,11 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
         ++rr;
       }
       if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_RELAX_ROUNDS] = rr;
+    }
+    if (deep) {  // uniform: every CTA derived it from the same scalars
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(sc + FS_EFLAGS, EF_DEEP);
+      fused_publish(P);
+      return;
     }
     FUSED_FOR(v, G) atomicAdd(P.size_off + ldg2(P.r + v), 1u);
     grid_bar(P, cx);
@@ -614,10 +630,14 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
             if (d.x == v || d.y == v) atomicMax(reinterpret_cast<unsigned long long*>(sc + FS_ERR_LO), ~(((unsigned long long)v << 32) | v));
           }
           order[o] = v;
-        } else P.heavy[atomicAdd(sc + FS_HEAVYN, 1u)] = v;
+        } else {
+          P.heavy[atomicAdd(sc + FS_HEAVYN, 1u)] = v;
+          if (sz >= 4 * kBigBlock) atomicOr(sc + FS_EFLAGS, EF_DEEP);  // a one-thread DFS of thousands of gates: k_tree_blocks' job
+        }
       }
     }
     grid_bar(P, cx);
+    if (ldg2(sc + FS_EFLAGS) & EF_DEEP) { fused_publish(P); return; }
     {
       const uint32_t nh = ldg2(sc + FS_HEAVYN);
       FUSED_FOR(i, nh) {

@@ -153,6 +153,23 @@ def test_deep_forward_chain(ctx, c2a, orc, slot):
     assert res[1].tolist() == list(range(n - 1, -1, -1))
 
 
+@pytest.mark.parametrize("slot", ["lh", "rh"])
+def test_deep_chain_leaves_the_fused_kernel(ctx, c2a, orc, slot):
+    """30 K gates, every one with a forward edge: the fused kernel bounds its walks, recognises the deep DAG and hands the stream to
+    the multi-kernel path (pointer jumping); same result either way"""
+    n = 30000
+    ev = _decl(n + 2)
+    nxt = n + 2
+    for i in range(n):
+        ev.append((EV_S, nxt, 0, 0))
+        ev.append((EV_G | (7 << 8), i + 1, n + 1, nxt) if slot == "lh" else (EV_G | (7 << 8), n + 1, i + 1, nxt))
+        ev.append((EV_C, nxt, i, 0))
+        nxt += 1
+    ev = np.asarray(ev, dtype=np.uint32)
+    res = run_both(ctx, c2a, ev, [n, n + 1], [0], expect_fused=False)
+    assert res[1].tolist() == list(range(n - 1, -1, -1))
+
+
 def test_cycles_and_self_loops_report_the_reference_index(ctx, c2a, orc):
     for cyc in ("pair", "self", "late"):
         ev = _decl(6)
