@@ -310,9 +310,11 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter_t(const uint8_t* __res
       }
     }
     {  // wait for this stage's bytes
-      uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]), parity = (it >> 1) & 1u, done = 0;
-      while (!done)
+      uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]), parity = (it >> 1) & 1u, done = 0, spins = 0;
+      while (!done) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (!done && ++spins > (1u << 24)) __trap();  // a bulk copy that never completes: fail loudly, do not hang (try_wait sleeps in hardware between polls)
+      }
     }
     const uint32_t g0 = s_meta[stage][0], c0 = s_meta[stage][1], s0 = s_meta[stage][2], woff = s_meta[stage][3], wcov = s_meta[stage][4], kcov = s_meta[stage][5];
     const uint32_t ng = s_meta[stage][6], nc = s_meta[stage][7];  // gates / connections in this tile
@@ -1205,6 +1207,40 @@ int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c
   }
   lit_k += n - k_at;
   lit_w += nw - w_at;
+  // generations: a record may only read what is complete when its launch starts - literal bytes, or the destination of a record of a
+  // SMALLER generation.  (Records ascend by destination: the destinations that intersect a source range are a run of records,
+  // found by binary search; the largest generation in the run by a sparse table.)  Without this an inconsistent record would read
+  // bytes that are unwritten in this launch, or stale ones from the previous call, and expand to a plausible but wrong stream.
+  if (nr) {
+    std::vector<std::vector<uint32_t>> tab(1, std::vector<uint32_t>(nr));
+    for (uint64_t i = 0; i < nr; ++i) tab[0][i] = cx->replays[i].gen;
+    for (uint64_t len = 2, lv = 1; len <= nr; len <<= 1, ++lv) {
+      tab.emplace_back(nr - len + 1);
+      for (uint64_t i = 0; i + len <= nr; ++i) tab[lv][i] = std::max(tab[lv - 1][i], tab[lv - 1][i + len / 2]);
+    }
+    auto range_max = [&](uint64_t lo, uint64_t hi) -> uint32_t {  // max gen of records [lo, hi)
+      if (lo >= hi) return 0;
+      const int lv = 63 - __builtin_clzll(hi - lo);
+      return std::max(tab[lv][lo], tab[lv][hi - (1ull << lv)]);
+    };
+    for (uint64_t i = 0; i < nr; ++i) {
+      const c2a_replay& r = cx->replays[i];
+      for (int which = 0; which < 2; ++which) {
+        const uint64_t src = which ? r.w_src : r.k_src, len = which ? r.w_len : r.k_len;
+        if (!len) continue;
+        auto dst_of = [&](uint64_t j) { return which ? cx->replays[j].w_dst : cx->replays[j].k_dst; };
+        auto len_of = [&](uint64_t j) { return which ? cx->replays[j].w_len : cx->replays[j].k_len; };
+        // first record whose destination ends behind src, first record whose destination starts at or behind src + len (both < i)
+        uint64_t lo = 0, hi = i;
+        while (lo < hi) { uint64_t m = (lo + hi) / 2; if (dst_of(m) + len_of(m) > src) hi = m; else lo = m + 1; }
+        const uint64_t first = lo;
+        lo = first; hi = i;
+        while (lo < hi) { uint64_t m = (lo + hi) / 2; if (dst_of(m) >= src + len) hi = m; else lo = m + 1; }
+        if (range_max(first, lo) >= r.gen)
+          return fail(h, C2A_ERR_INVALID_ARGUMENT, "replay record %llu reads the destination of a record of generation >= its own (%u)", (unsigned long long)i, r.gen);
+      }
+    }
+  }
   cudaStream_t s = h->stream;
   // ---- chunk tables: generation 0 = the literal ranges (source: the packed literal staging), generation g = records of gen g
   auto n_chunks_of = [](uint64_t len) { return (len + kCxChunk - 1) / kCxChunk; };

@@ -141,6 +141,7 @@ struct Expr {
   // filled by Symbols::annotate after parsing
   Key key = 0;                       // Variable: interned name; Call: the callee's name symbol
   const Callable* callee = nullptr;  // Call: resolved definition (null: undefined)
+  uint32_t depth = 1;                // height of the expression tree below this node (bounded by the parser: kMaxExprDepth)
   uint32_t num = 0;                  // Number: the literal's value ...
   bool num_overflow = false;         // ... or "does not fit u32" (src/process.rs:294-306; raised only when evaluated)
 };
@@ -192,8 +193,26 @@ struct Parser {
   std::string ident() { if (cur().t != T_ID) err("expected identifier"); return t[p++].s; }
 
   // ---- expressions: precedence of circom's grammar (lowest first): ?: || && cmp | ^ & shift +- */\% ** prefix
-  ExprP mk_infix(int op, ExprP l, ExprP r) { auto e = std::make_shared<Expr>(); e->kind = Expr::InfixOp; e->op = op; e->l = l; e->r = r; return e; }
-  ExprP expr() { return ternary(); }
+  // A library behind a C ABI must not take the caller down with it: expression NESTING (100 000 parentheses) would overflow the
+  // parser's recursion, a left-deep CHAIN (a + a + ... two million times) the recursion of everything that later walks or frees
+  // the tree.  Both are parse errors beyond kMaxExprDepth.
+  static constexpr uint32_t kMaxExprDepth = 5000;
+  uint32_t nest = 0;
+  struct Nest {
+    Parser& ps;
+    explicit Nest(Parser& q) : ps(q) { if (++ps.nest > kMaxExprDepth) ps.err("expression nested too deeply"); }
+    ~Nest() { --ps.nest; }
+  };
+  ExprP deep(ExprP e, uint32_t below) {
+    e->depth = below + 1;
+    if (e->depth > kMaxExprDepth) err("expression too deep");
+    return e;
+  }
+  ExprP mk_infix(int op, ExprP l, ExprP r) {
+    auto e = std::make_shared<Expr>(); e->kind = Expr::InfixOp; e->op = op; e->l = l; e->r = r;
+    return deep(e, std::max(l->depth, r->depth));
+  }
+  ExprP expr() { Nest guard(*this); return ternary(); }
   ExprP ternary() {
     ExprP c = level(0);
     if (accept_op("?")) {  // InlineSwitchOp: parsed, rejected by the walker (src/process.rs:310)
@@ -230,8 +249,9 @@ struct Parser {
       auto e = std::make_shared<Expr>();
       e->kind = Expr::PrefixOp;
       e->op = op;
+      Nest guard(*this);
       e->r = prefix();
-      return e;
+      return deep(e, e->r->depth);
     }
     return term();
   }
@@ -261,6 +281,7 @@ struct Parser {
         e->text = name;
         if (!is_op(")")) { e->args.push_back(expr()); while (accept_op(",")) e->args.push_back(expr()); }
         expect_op(")");
+        for (auto& a : e->args) e->depth = std::max(e->depth, a->depth + 1);
         if (is_op("(")) {  // anonymous component T(..)(..)
           int depth = 0;
           do { if (is_op("(")) ++depth; if (is_op(")")) --depth; ++p; } while (depth > 0 && cur().t != T_EOF);
@@ -272,6 +293,7 @@ struct Parser {
       e->kind = Expr::Variable;
       e->text = name;
       e->access = accesses();
+      for (auto& a : e->access) if (a.index) e->depth = std::max(e->depth, a.index->depth + 1);
       return e;
     }
     err("expected expression");

@@ -35,6 +35,7 @@ struct c2a_handle {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_next = 0;
   std::vector<std::pair<std::string, double>> last_ms;
+  int nvtx_open = 0;  // NVTX ranges pushed by phase_begin and not yet popped
   bool timing = true;
   std::string timing_only;  // non-empty: events are recorded around this phase only
   // ---- device emitter (c2a_emit.cuh): event staging buffer (separate from the slab) and the resident result

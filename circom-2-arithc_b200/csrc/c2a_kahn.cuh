@@ -143,9 +143,10 @@ __device__ __forceinline__ void bulk_load_row(uint32_t* smem_dst, const uint32_t
                  : "memory");
   }
   // all threads wait for the phase to complete
-  uint32_t done = 0;
+  uint32_t done = 0, spins = 0;
   while (!done) {
     asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(phase) : "memory");
+    if (!done && ++spins > (1u << 24)) __trap();  // a lost completion surfaces as a CUDA error, not a hang
   }
 }
 

@@ -446,3 +446,17 @@ def test_examples_are_the_generated_programs(c2a):
         path = os.path.join(root, "examples", name + ".circom")
         assert open(path).read() == text
         assert c2a.compile(path).gate_array().shape[0] > 1000    # compile_file path (src/program.rs:18-29)
+
+
+def test_pathological_expression_depth_is_a_parse_error_not_a_crash(c2a):
+    """100 000 nested parentheses / a two-million-term chain used to overflow the native stack (parser recursion, resp. the recursion
+    of everything that walks or frees a left-deep tree); behind a C ABI that must be `Parsing error`, not a dead host process"""
+    head = "pragma circom 2.0.0; template T(){ signal input a; signal output c; c <== "
+    tail = "; } component main = T();"
+    for body in ("(" * 100000 + "a" + ")" * 100000, "a" + " + a" * 2000000, "a" + "[a" * 50000 + "]" * 50000, "! " * 100000 + "a"):
+        with pytest.raises(c2a.ProgramError) as ex:
+            c2a.compile(None, source=head + body + tail, emitter="host")
+        assert "Parsing error" in str(ex.value)
+    # well inside the bound: still compiles
+    comp = c2a.compile(None, source=head + "(" * 1500 + "a" + ")" * 1500 + " + a" * 2000 + tail, emitter="host")
+    assert comp.gate_array().shape[0] == 2000

@@ -191,3 +191,20 @@ def test_compressed_recording_is_expanded_on_the_device(c2a, ctx):
     cx2 = CompressedEvents(cx.kinds, cx.words, cx.n_events, cx.n_words, C.cast(bad, C.c_void_p), cx.n_replays, cx.max_gen, cx.flags)
     with pytest.raises((c2a.C2AError, c2a.CircuitError)):
         ctx.emit_compressed(cx2)
+    # ... and so is a generation that is not larger than the generation of a record its source reads (it would expand to a
+    # plausible but wrong stream: bytes unwritten in this launch, or stale ones of the previous call)
+    for src in sources:
+        dev = c2a.compile(None, source=src, context=ctx, emitter="device")
+        cx = dev.compressed()
+        if cx.max_gen >= 2:
+            break
+    assert cx.max_gen >= 2
+    recs = (Replay * int(cx.n_replays)).from_address(cx.replays)
+    deep_i = max(range(int(cx.n_replays)), key=lambda i: recs[i].gen)
+    bad = (Replay * int(cx.n_replays))(*recs)
+    bad[deep_i].gen = 1
+    cx3 = CompressedEvents(cx.kinds, cx.words, cx.n_events, cx.n_words, C.cast(bad, C.c_void_p), cx.n_replays, cx.max_gen, cx.flags)
+    with pytest.raises((c2a.C2AError, c2a.CircuitError)) as ex:
+        ctx.emit_compressed(cx3)
+    assert "generation" in str(ex.value)
+    ctx.emit_compressed(cx)   # the untouched records still expand
