@@ -239,7 +239,7 @@ constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words p
 // kMode 2: every gate and connection is flagged (what the walker emits) - the third rank is the sum of the other two, a gate has 2
 //          payload words and a connection 1, nothing per event has to be tested;  kMode 1: flagged and unflagged events mixed.
 template <int kMode>
-__global__ void __launch_bounds__(kBlock, 7) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+__global__ void __launch_bounds__(kBlock, 6) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, const uint32_t* __restrict__ tile_i /* null: no implicit operands */,
                                                        uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter_t(const uint8_t* __res
   __shared__ __align__(16) uint8_t s_k[2][kEvTile];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ uint32_t s_meta[2][10];  // g0, c0, s0, first payload word - aligned start, words staged, kind bytes staged, #gates, #connections, i0, #implicit
-  __shared__ uint32_t s_g[8], s_c[8], s_i[8];
+  __shared__ uint2 s_cnt[8];  // per warp: {gates | connections << 16, implicit-operand events} of its 128 events
   __shared__ uint32_t s_list[kEvTile];  // the tile's events filed by kind (phase A -> phase B)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -333,47 +333,68 @@ __global__ void __launch_bounds__(kBlock, 7) k_pk_scatter_t(const uint8_t* __res
     // a walker stream flags EVERY gate and connection: then the third rank is the sum of the other two and need not be counted
     constexpr bool all_impl = kMode == 2;
     constexpr bool mixed = kMode == 1;
-    uint32_t kb[4], gm[4], cm[4], im[4];
-    uint32_t wg = 0, wc = 0, wi = 0;
+    // Interior tiles (1024 events, all kind bytes staged by the bulk copy) take the instantiation without bounds tests: this phase
+    // is two thirds of the instructions of an instruction-issue-bound kernel.
+    auto phase_a = [&](auto fast_tag) {
+      constexpr bool kFast = decltype(fast_tag)::value;
+      const uint8_t* __restrict__ skl = &s_k[stage][warp * 128 + lane];
+      uint32_t kb[4], gm[4], cm[4], im[4];
+      uint32_t wg = 0, wc = 0, wi = 0;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint32_t k = warp * 128 + j * 32 + lane;
-      kb[j] = k < nev ? (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) : 0x100u;  // 0x100: past the end
-      gm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_GATE);
-      cm[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 3u) == C2A_EV_CONNECT);
-      wg += __popc(gm[j]);
-      wc += __popc(cm[j]);
-      if (mixed) { im[j] = __ballot_sync(0xFFFFFFFFu, kb[j] < 0x100u && (kb[j] & 0x82u) == 0x82u); wi += __popc(im[j]); }  // bit 7 on a gate / connection
-      else im[j] = 0;
-    }
-    if (lane == 0) { s_g[warp] = wg; s_c[warp] = wc; s_i[warp] = wi; }
-    __syncthreads();
-    uint32_t dg = 0, dc = 0, di = 0;  // in-tile ranks
-    for (int w = 0; w < warp; ++w) { dg += s_g[w]; dc += s_c[w]; }
-    if (mixed) for (int w = 0; w < warp; ++w) di += s_i[w];
-    // (this loop is the hot spot of an issue-bound kernel: one select-built shared-memory store for gates and connections,
-    //  one predicated 8-byte store for a dense signal, no per-event bounds checks or reductions)
-    if (dense && threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t k = warp * 128 + j * 32 + lane;
-      const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt), my_di = di + __popc(im[j] & lt);
-      dg += __popc(gm[j]);
-      dc += __popc(cm[j]);
-      di += __popc(im[j]);
-      const bool is_g = (gm[j] >> lane) & 1u, is_c = (cm[j] >> lane) & 1u;
-      const uint32_t ds = k - my_dg - my_dc;
-      if (is_g | is_c) {  // (both masks exclude lanes past the end of the stream)
-        // entry: local event index | the rank under the other kind << 10 | the rank among implicit-operand events << 20
-        s_list[min(is_g ? my_dg : ng + my_dc, (uint32_t)kEvTile - 1)] = k | ((is_g ? my_dc : my_dg) << 10) | (my_di << 20);
-      } else if (k < nev) {
-        const uint32_t cbit = (kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u;
-        // dense ids: the id IS the declaration rank (< n <= S_cap) - the record is complete right here, lanes holding signals write
-        // consecutive slots (no filing, no phase-B pass for the most frequent kind)
-        if (dense) sig_meta[s0 + ds] = make_uint2((s0 + ds) | cbit, c0 + my_dc);
-        else s_list[min(ng + nc + ds, (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | cbit;
+      for (int j = 0; j < 4; ++j) {
+        if (kFast) kb[j] = skl[j * 32];
+        else {
+          const uint32_t k = warp * 128 + j * 32 + lane;
+          kb[j] = k < nev ? (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) : 0x100u;  // 0x100: past the end
+        }
+        const bool live = kFast || kb[j] < 0x100u;
+        gm[j] = __ballot_sync(0xFFFFFFFFu, live && (kb[j] & 3u) == C2A_EV_GATE);
+        cm[j] = __ballot_sync(0xFFFFFFFFu, live && (kb[j] & 3u) == C2A_EV_CONNECT);
+        wg += __popc(gm[j]);
+        wc += __popc(cm[j]);
+        if (mixed) { im[j] = __ballot_sync(0xFFFFFFFFu, live && (kb[j] & 0x82u) == 0x82u); wi += __popc(im[j]); }  // bit 7 on a gate / connection
+        else im[j] = 0;
       }
-    }
+      if (lane == 0) s_cnt[warp] = make_uint2(wg | (wc << 16), wi);  // (counts and their prefix sums are <= 1024: 16 bits each)
+      __syncthreads();
+      // in-tile ranks of the warp's first event: sum over the warps before it - lanes 0..7 hold one warp's counts each
+      uint32_t dg, dc, di;
+      {
+        uint2 v = (lane < 8 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int o = 4; o; o >>= 1) { v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o); if (mixed) v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o); }
+        v.x = __shfl_sync(0xFFFFFFFFu, v.x, 0);
+        dg = v.x & 0xFFFFu;
+        dc = v.x >> 16;
+        di = mixed ? __shfl_sync(0xFFFFFFFFu, v.y, 0) : 0u;
+      }
+      // (this loop is the hot spot: one select-built shared-memory store for gates and connections, one 8-byte store for a dense
+      //  signal, no per-event reductions)
+      if (dense && threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t k = warp * 128 + j * 32 + lane;
+        const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt), my_di = di + __popc(im[j] & lt);
+        dg += __popc(gm[j]);
+        dc += __popc(cm[j]);
+        di += __popc(im[j]);
+        const bool is_g = (gm[j] >> lane) & 1u, is_c = (cm[j] >> lane) & 1u;
+        const uint32_t ds = k - my_dg - my_dc;
+        if (is_g | is_c) {  // (both masks exclude lanes past the end of the stream)
+          // entry: local event index | the rank under the other kind << 10 | the rank among implicit-operand events << 20
+          const uint32_t slot = is_g ? my_dg : ng + my_dc;
+          s_list[kFast ? slot : min(slot, (uint32_t)kEvTile - 1)] = k | ((is_g ? my_dc : my_dg) << 10) | (my_di << 20);
+        } else if (kFast || k < nev) {
+          const uint32_t cbit = (kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u;
+          // dense ids: the id IS the declaration rank (< n <= S_cap) - the record is complete right here, lanes holding signals write
+          // consecutive slots (no filing, no phase-B pass for the most frequent kind)
+          if (dense) sig_meta[s0 + ds] = make_uint2((s0 + ds) | cbit, c0 + my_dc);
+          else s_list[min(ng + nc + ds, (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | cbit;
+        }
+      }
+    };
+    if (nev == (uint32_t)kEvTile && kcov == (uint32_t)kEvTile && ng + nc <= (uint32_t)kEvTile) phase_a(std::true_type{});
+    else phase_a(std::false_type{});
     __syncthreads();
     // ---- phase B, one lane per OUTPUT record, kind by kind: no divergence, fully coalesced stores.
     // Interior tiles (everything staged by the bulk copies) take the check-free instantiation.
