@@ -282,25 +282,7 @@ __device__ __forceinline__ bool exec_op_u32(uint32_t op, uint32_t a, uint32_t b,
   return false;
 }
 
-// node_const[node]: bit0 = value known; node_val[node] = value.  One launch per level (forward).
-__global__ void __launch_bounds__(kBlock) k_fold_level(const uint4* __restrict__ gates, const uint32_t* __restrict__ level_order, uint32_t lo,
-                                                       uint32_t hi, const uint32_t* __restrict__ prod1, uint8_t* __restrict__ node_const,
-                                                       uint32_t* __restrict__ node_val, uint8_t* __restrict__ const_mask,
-                                                       uint32_t* __restrict__ const_value) {
-  for (uint32_t i = lo + blockIdx.x * kBlock + threadIdx.x; i < hi; i += gridDim.x * kBlock) {
-    uint32_t g = level_order[i];
-    uint4 gt = gates[g];
-    uint32_t r = 0;
-    bool c = node_const[gt.y] && node_const[gt.z] && exec_op_u32(gt.x, node_val[gt.y], node_val[gt.z], &r);
-    const_mask[g] = c;
-    const_value[g] = c ? r : 0u;
-    if (prod1[gt.w] == g + 1) {  // this gate is the node's producer (last writer wins, compiler.rs:403-406)
-      node_const[gt.w] = c;
-      node_val[gt.w] = r;
-    }
-  }
-}
-
+// node_const[node]: bit0 = value known; node_val[node] = value (k_sweep_levels<true> below).
 __global__ void __launch_bounds__(kBlock) k_set_node_consts(const uint32_t* __restrict__ nodes, const uint32_t* __restrict__ vals, uint32_t n,
                                                             uint32_t node_bound, uint8_t* __restrict__ node_const, uint32_t* __restrict__ node_val) {
   for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock)
@@ -312,17 +294,54 @@ __global__ void __launch_bounds__(kBlock) k_mark_nodes(const uint32_t* __restric
     if (nodes[i] < node_bound) mark[nodes[i]] = 1;
 }
 
-// reverse sweep: a gate is live when it produces an output node or feeds a live gate
-__global__ void __launch_bounds__(kBlock) k_live_level(const uint4* __restrict__ gates, const uint32_t* __restrict__ level_order, uint32_t lo,
-                                                       uint32_t hi, const uint32_t* __restrict__ prod1, const uint32_t* __restrict__ row_off,
-                                                       const uint4* __restrict__ col, const uint8_t* __restrict__ out_mark,
-                                                       uint8_t* __restrict__ live) {
-  for (uint32_t i = lo + blockIdx.x * kBlock + threadIdx.x; i < hi; i += gridDim.x * kBlock) {
-    uint32_t g = level_order[i];
-    uint4 gt = gates[g];
-    bool l = out_mark[gt.w] && prod1[gt.w] == g + 1;
-    for (uint32_t j = row_off[g]; !l && j < row_off[g + 1]; ++j) l = live[col[j].x & ~kTwoSlots] != 0;
-    live[g] = l;
+// (reverse sweep: a gate is live when it produces an output node or feeds a live gate)
+// Both sweeps as ONE cooperative launch each: the levels are walked on the device with a grid barrier in between (a launch per
+// level - 547 on the MiMC circuit, thousands on a bit-sliced SHA-256 - costs ~6 us of launch latency per level; the barrier ~2 us).
+// Values written for level l are read by other CTAs in level l +- 1: those reads go through L2 (ld.cg).
+template <bool kFold>
+__global__ void __launch_bounds__(kBlock) k_sweep_levels(const uint4* __restrict__ gates, const uint32_t* __restrict__ level_order,
+                                                         const uint32_t* __restrict__ level_off, uint32_t nl, uint32_t G, const uint32_t* __restrict__ prod1,
+                                                         uint8_t* node_const, uint32_t* node_val, uint8_t* __restrict__ const_mask, uint32_t* __restrict__ const_value,
+                                                         const uint32_t* __restrict__ row_off, const uint4* __restrict__ col, const uint8_t* __restrict__ out_mark,
+                                                         uint8_t* live, unsigned int* bar) {
+  unsigned int epoch = 0;
+  const uint32_t tid = blockIdx.x * kBlock + threadIdx.x;
+  auto range = [&](uint32_t step, uint32_t& lo, uint32_t& hi) {
+    const uint32_t l = kFold ? step : nl - 1 - step;
+    lo = __ldg(level_off + l);
+    hi = l + 1 == nl ? G : __ldg(level_off + l + 1);
+  };
+  // a level is a chain of dependent loads (order -> gate -> operand values): the first two do not depend on the previous level and
+  // are fetched BEFORE the barrier that ends it
+  uint32_t lo, hi, g_pre = 0;
+  uint4 gt_pre = make_uint4(0, 0, 0, 0);
+  if (nl) { range(0, lo, hi); if (lo + tid < hi) { g_pre = __ldg(level_order + lo + tid); gt_pre = __ldg(gates + g_pre); } }
+  for (uint32_t step = 0; step < nl; ++step) {
+    for (uint32_t i = lo + tid; i < hi; i += gridDim.x * kBlock) {
+      const bool first = i == lo + tid;
+      const uint32_t g = first ? g_pre : __ldg(level_order + i);
+      const uint4 gt = first ? gt_pre : __ldg(gates + g);
+      if (kFold) {
+        uint32_t r = 0;
+        const bool c = __ldcg(node_const + gt.y) && __ldcg(node_const + gt.z) && exec_op_u32(gt.x, __ldcg(node_val + gt.y), __ldcg(node_val + gt.z), &r);
+        const_mask[g] = c;
+        const_value[g] = c ? r : 0u;
+        if (__ldg(prod1 + gt.w) == g + 1) {  // this gate is the node's producer (last writer wins, compiler.rs:403-406)
+          node_const[gt.w] = c;
+          node_val[gt.w] = r;
+        }
+      } else {
+        bool lv = __ldg(out_mark + gt.w) && __ldg(prod1 + gt.w) == g + 1;
+        const uint32_t e = __ldg(row_off + g + 1);
+        for (uint32_t j = __ldg(row_off + g); !lv && j < e; ++j) lv = __ldcg(live + (__ldg(col + j).x & ~kTwoSlots)) != 0;
+        live[g] = lv;
+      }
+    }
+    if (step + 1 < nl) {
+      range(step + 1, lo, hi);
+      if (lo + tid < hi) { g_pre = __ldg(level_order + lo + tid); gt_pre = __ldg(gates + g_pre); }
+      sort_grid_bar(bar, epoch);
+    }
   }
 }
 
@@ -560,13 +579,27 @@ int c2a_sweep_masks(c2a_handle* h, const c2a_gate* gates, uint64_t G, uint32_t n
   off[nl] = (uint32_t)G;
   if (n_const) LAUNCH(h, k_set_node_consts, grid_for(h, (const void*)k_set_node_consts, kBlock, n_const), kBlock, d_cn, d_cv, n_const, node_bound, node_const, node_val);
   if (n_out) LAUNCH(h, k_mark_nodes, grid_for(h, (const void*)k_mark_nodes, kBlock, n_out), kBlock, d_on, n_out, node_bound, out_mark);
+  // one cooperative launch per sweep (the barrier counters live in the Kahn control words, unused by now)
+  cudaMemsetAsync(b.ctrl, 0, 4 * KC_COUNT, s);
+  auto sweep = [&](bool fold) {
+    const uint4* a_gates = d_gates;
+    const uint32_t *a_lo = d_lo, *a_off = d_off, *a_prod = b.prod1, *a_row = b.row_off;
+    uint32_t a_nl = nl, a_G = (uint32_t)G;
+    uint8_t *a_nc = node_const, *a_cm = d_cmask, *a_live = d_live;
+    const uint8_t* a_om = out_mark;
+    uint32_t *a_nv = node_val, *a_cv = d_cval;
+    const uint4* a_col = b.col;
+    unsigned int* a_bar = reinterpret_cast<unsigned int*>(b.ctrl) + (fold ? 0 : 1);
+    void* args[] = {&a_gates, &a_lo, &a_off, &a_nl, &a_G, &a_prod, &a_nc, &a_nv, &a_cm, &a_cv, &a_row, &a_col, &a_om, &a_live, &a_bar};
+    const void* fn = fold ? (const void*)k_sweep_levels<true> : (const void*)k_sweep_levels<false>;
+    cudaLaunchCooperativeKernel(fn, dim3(h->num_sms), dim3(kBlock), args, 0, s);
+    h->launches++;
+  };
   phase_begin(h, "k_fold_level");
-  for (uint32_t l = 0; l < nl; ++l)
-    if (off[l + 1] > off[l]) LAUNCH(h, k_fold_level, grid_for(h, (const void*)k_fold_level, kBlock, off[l + 1] - off[l]), kBlock, d_gates, d_lo, off[l], off[l + 1], b.prod1, node_const, node_val, d_cmask, d_cval);
+  if (nl) sweep(true);
   phase_end(h);
   phase_begin(h, "k_live_level");
-  for (uint32_t l = nl; l-- > 0;)
-    if (off[l + 1] > off[l]) LAUNCH(h, k_live_level, grid_for(h, (const void*)k_live_level, kBlock, off[l + 1] - off[l]), kBlock, d_gates, d_lo, off[l], off[l + 1], b.prod1, b.row_off, b.col, out_mark, d_live);
+  if (nl) sweep(false);
   if (G) LAUNCH(h, k_invert_u8, grid_for(h, (const void*)k_invert_u8, kBlock, G), kBlock, d_live, d_dead, (uint32_t)G);
   phase_end(h);
   if (G) {
