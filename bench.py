@@ -789,8 +789,22 @@ def main():
 
     dom_probe = {"name": None, "in_emit": False, "ms": 0.0}   # timed steps: one double read instead of parsing every phase
 
+    from circom_2_arithc_b200._lib import CompileIO
+    use_compile = packed and world == 1   # one call (c2a_compile_packed*): the emit's final status is read with the build's
+    io_res = CompileIO(in_ids.ctypes.data_as(vp), out_ids.ctypes.data_as(vp), len(in_ids), len(out_ids), vp(d_order.data_ptr()), vp(d_wire.data_ptr()),
+                       vp(d_new.data_ptr()), G, nb, 0)
+
     def device_step(record=False):
         """emit + build with the event stream already resident in HBM; results stay in HBM"""
+        if use_compile:
+            st = lib.c2a_compile_packed_resident(h, C.byref(pk_dev), C.byref(io_res), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
+            if st != 0 or info.path != 1:
+                raise RuntimeError(f"c2a_compile_packed_resident -> {st} path {info.path}: {ctx.last_error()}")
+            if record:
+                acc_phases("")     # (the emit's phases carry their "emit:" prefix already)
+            elif dom_probe["name"]:
+                dom_probe["ms"] += lib.c2a_last_kernel_ms(h, dom_probe["full"])
+            return
         st = emit_resident()
         if st != 0 or info.path != 1:
             raise RuntimeError(f"emit (resident) -> {st} path {info.path}: {ctx.last_error()}")
@@ -845,7 +859,7 @@ def main():
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     if not args.no_phase_timing:
-        dom_probe.update(name=dom_phase.split(":")[-1].encode(), in_emit=dom_phase.startswith("emit:"), ms=0.0)
+        dom_probe.update(name=dom_phase.split(":")[-1].encode(), full=dom_phase.encode(), in_emit=dom_phase.startswith("emit:"), ms=0.0)
     e0.record(stream)
     for _ in range(K):
         device_step()
@@ -890,7 +904,20 @@ def main():
     d_named = torch.empty(len(named), dtype=torch.int32, device=dev)
     d_named_w = torch.empty(len(named), dtype=torch.int32, device=dev)
 
+    io_host = CompileIO(in_ids.ctypes.data_as(vp), out_ids.ctypes.data_as(vp), len(in_ids), len(out_ids), None, None, vp(p_new.data_ptr()), G, 0, 0)
+    io_host_all = CompileIO(in_ids.ctypes.data_as(vp), out_ids.ctypes.data_as(vp), len(in_ids), len(out_ids), vp(p_order.data_ptr()), vp(p_wire.data_ptr()),
+                            vp(p_new.data_ptr()), G, nb, 0)
+
     def e2e_step(all_arrays):
+        if use_compile:
+            st = lib.c2a_compile_packed(h, C.byref(pk_host), C.byref(io_host_all if all_arrays else io_host), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
+            if st != 0 or info.path != 1:
+                raise RuntimeError(f"c2a_compile_packed -> {st} path {info.path}: {ctx.last_error()}")
+            if not all_arrays:
+                st = lib.c2a_emitted_signal_wires(h, vp(p_named.data_ptr()), len(named), vp(p_named_w.data_ptr()))
+                if st != 0:
+                    raise RuntimeError(f"c2a_emitted_signal_wires -> {st}: {ctx.last_error()}")
+            return
         st = emit_from_host()
         if st != 0 or info.path != 1:
             raise RuntimeError(f"emit (host stream) -> {st} path {info.path}: {ctx.last_error()}")
@@ -1223,9 +1250,15 @@ def main():
                                         "; 3 words per gate, 2 per connection", stream_bytes / n_ev)) if packed else "c2a_event records, 16 B/event", "signals_per_gpu": counts["n_sig"], "connections_per_gpu": counts["C"], "effective_merges_per_gpu": counts["Ceff"],
                    "boruvka_rounds": int(info.rounds), "order_is_identity": n_identity,
                    "l2": "inputs larger than L2 (event stream %.0f MB, gate array %.0f MB, node arrays %.0f MB each vs 126 MB L2); no flush" % (stream_bytes / 1e6, 16 * G / 1e6, 4 * nb / 1e6),
-                   "value_scope": "event stream resident in HBM -> c2a_emit_packed_resident / c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "
+                   "value_scope": ("event stream resident in HBM -> c2a_compile_packed_resident = device emitter (scatter, Boruvka MSF, node ids, gate resolve) + build "
+                                   "(deps, DFS-order reconstruction, wire numbering, gather) in ONE call, the emit's status read together with the build's; results stay in HBM")
+                                  if use_compile else
+                                  "event stream resident in HBM -> c2a_emit_packed_resident / c2a_emit_events_resident (device emitter: scatter, Boruvka MSF, node ids, gate resolve) -> "
                                   "c2a_emitted_build_circuit_device (producer map, deps, DFS-order reconstruction, wire numbering, gather); results stay in HBM",
-                   "e2e_scope": "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
+                   "e2e_scope": ("event stream in pinned host memory -> c2a_compile_packed (H2D inside; renumbered gates D2H into pinned host buffers) -> "
+                                 "c2a_emitted_signal_wires (named signals H2D, their wires D2H); e2e_all_arrays also copies order and the whole wire map")
+                                if use_compile else
+                                "event stream in pinned host memory -> c2a_emit_packed_device / c2a_emit_events_device (H2D inside) -> c2a_emitted_build_circuit into pinned host buffers "
                                 "(new_gates D2H inside) -> c2a_emitted_signal_wires (named signals H2D, their wires D2H); e2e_all_arrays also copies order and the whole wire map",
                    "numa_node": numa,
                    "oracle_pin": "oracle pinned by the reference's own unit / integration vectors (tests/test_oracle_goldens.py); topological_sort has NO upstream "

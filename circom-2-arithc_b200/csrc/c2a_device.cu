@@ -22,6 +22,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
@@ -1081,7 +1082,7 @@ void phase_begin(c2a_handle* h, const char* name) {
   h->nvtx_open++;
   if (!h->timing) return;
   if (!h->timing_only.empty() && h->timing_only != name) return;
-  c2a_handle::Phase p{name, next_event(h), next_event(h), true};
+  c2a_handle::Phase p{h->phase_prefix.empty() ? std::string(name) : h->phase_prefix + name, next_event(h), next_event(h), true};
   cudaEventRecord(p.a, h->stream);
   h->phases.push_back(p);
 }
@@ -1443,6 +1444,7 @@ int c2a_create(int device, c2a_handle** out) {
     return C2A_ERR_CUDA;
   }
   h->h_pinned_bytes = 1 << 16;
+  if (cudaHostAlloc((void**)&h->h_emit_status, 256, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->h_emit_status = nullptr; }
   if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     cudaEventDestroy(h->ev_side);
@@ -1469,6 +1471,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->cx_pinned) cudaFreeHost(h->cx_pinned);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
+  if (h->h_emit_status) cudaFreeHost(h->h_emit_status);
   cudaStreamSynchronize(h->stream2);
   cudaEventDestroy(h->ev_side);
   cudaEventDestroy(h->ev_main);

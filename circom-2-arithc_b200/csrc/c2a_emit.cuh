@@ -855,7 +855,16 @@ struct EmitSrc {
   bool pk_on_device = false;
 };
 
-static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_emit_info* info, uint64_t* err_event) {
+// c2a_compile_packed* on a large stream: the emit does not wait for its own final status - the build is enqueued right behind
+// it (with an upper bound as node bound) and ONE synchronisation at the end of the build returns both.  What the emit could
+// not check is validated then (compile_packed_impl); a stream that fails the check is replayed the ordinary way.
+struct EmitDefer {
+  bool pending = false;
+  uint32_t wire_cap = 0;  // capacity of the caller's device wire map (0: none) - caps the provisional node bound
+  uint64_t n_sig = 0, C = 0;
+};
+
+static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_emit_info* info, uint64_t* err_event, EmitDefer* defer = nullptr) {
   const c2a_event* ev_host = src.ev_host;
   const c2a_event* ev_dev = src.ev_dev;
   const c2a_packed_events* pk = src.pk;
@@ -1101,7 +1110,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   };
   // ---- node ids (re-issued when the speculative rounds turn out not to have finished the forest)
   int nid_runs = 0;
-  auto node_ids = [&]() {
+  auto node_ids = [&](bool sync = true) {
     uint32_t stiles = scan_tiles(C + 1, kScanItems);
     phase_begin(h, "init");
     cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
@@ -1124,8 +1133,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     phase_begin(h, "k_ev_gates");
     if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates, prod1, NB_ub);
     phase_end(h);
-    cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(hp + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, s);
+    uint32_t* dst = sync ? hp : h->h_emit_status;  // (deferred: a buffer of its own - the build re-stages, even re-allocates, hp)
+    cudaMemcpyAsync(dst, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(dst + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, s);
+    if (!sync) return true;
     if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return false;
     return cuda_ok(h, cudaGetLastError(), "emit kernels");
   };
@@ -1133,6 +1144,28 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   if (C) {
     for (int r = 0; r < kSpecMsf; ++r)
       msf_round(r ? es + ES_MC0 + 2 * (r - 1) + 1 : nullptr, es + ES_MC0 + 2 * r, es + ES_MC0 + 2 * r + 1);
+  }
+  if (defer && pk_dense && h->h_emit_status) {
+    // provisional result: exact gates / signals, node ids bounded by signals + connections; fixed up by the caller after the build's sync
+    node_ids(false);
+    uint64_t nc_ub = n_sig + C;
+    if (defer->wire_cap) nc_ub = std::min<uint64_t>(nc_ub, defer->wire_cap - 1);
+    defer->pending = true;
+    defer->n_sig = n_sig;
+    defer->C = C;
+    h->slab_used = keep;
+    h->slab_keep = keep;
+    h->emitted.valid = true;
+    h->emitted.nos_valid = true;
+    h->emitted.gates_off = (char*)d_gates - h->slab;
+    h->emitted.nos_off = (char*)nos - h->slab;
+    h->emitted.prod1_valid = true;
+    h->emitted.prod1_off = (char*)prod1 - h->slab;
+    h->emitted.G = G;
+    h->emitted.node_count = (uint32_t)nc_ub;
+    h->emitted.signal_bound = S;
+    h->emitted.wire = nullptr;
+    return C2A_OK;
   }
   if (!node_ids()) return C2A_ERR_CUDA;
   if (C && hp[ES_MC0 + 2 * (kSpecMsf - 1)] != 0 && hp[ES_MC0 + 2 * (kSpecMsf - 1) + 1] != 0) {
@@ -1350,7 +1383,7 @@ int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_sign
 // (c2a_plan_shards_device): no dependency edge leaves it, so its producer map is rebuilt for the range alone.
 static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                               uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index,
-                              bool outputs_on_device, uint64_t g_lo = 0, uint64_t g_hi = ~0ull) {
+                              bool outputs_on_device, uint64_t g_lo = 0, uint64_t g_hi = ~0ull, bool keep_phases = false) {
   if (!h) return C2A_ERR_INVALID_ARGUMENT;
   if (!h->emitted.valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no emitted circuit is resident on this handle");
   const bool whole = g_lo == 0 && (g_hi == ~0ull || g_hi == h->emitted.G);
@@ -1359,7 +1392,7 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   const uint32_t node_bound = h->emitted.node_count + 1;
   int st = check_sizes(h, G, node_bound);
   if (st) return st;
-  phases_clear(h);
+  if (!keep_phases) phases_clear(h);
   cudaStream_t s = h->stream;
   BuildPlan p{G, node_bound, n_in, n_out, true};
   const size_t n_pairs = (size_t)n_in + n_out;

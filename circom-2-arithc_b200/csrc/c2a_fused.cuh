@@ -740,16 +740,40 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
   if (!h) return C2A_ERR_INVALID_ARGUMENT;
   if (!pk || !io) return fail(h, C2A_ERR_INVALID_ARGUMENT, "null argument");
   const uint64_t n = pk->n_events, nw = pk->n_words;
-  auto classic = [&]() -> int {  // the multi-kernel pipeline: any size, any stream, exact error replay
+  // the multi-kernel pipeline: any size, any stream, exact error replay.  defer_ok: the emit's final status is read together with the
+  // build's (one synchronisation less); a stream that fails the deferred check is replayed with defer_ok = false.
+  std::function<int(bool)> classic_run = [&](bool defer_ok) -> int {
     EmitSrc src;
     src.pk = pk;
     src.pk_on_device = pk_on_device;
-    int st = emit_events_impl(h, src, n, info, err_event);
+    EmitDefer df;
+    df.wire_cap = (out_on_device && io->wire_of_node) ? io->wire_cap : 0u;
+    h->phase_prefix = "emit:";
+    int st = emit_events_impl(h, src, n, info, err_event, defer_ok ? &df : nullptr);
+    h->phase_prefix.clear();
     if (st != C2A_OK) return st;
     if ((io->order_out || io->new_gates) && io->gates_cap < h->emitted.G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%llu)", (unsigned long long)io->gates_cap, (unsigned long long)h->emitted.G);
-    if (io->wire_of_node && io->wire_cap < h->emitted.node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, h->emitted.node_count + 1);
-    return emitted_build_impl(h, io->input_signals, io->n_in, io->output_signals, io->n_out, io->order_out, io->wire_of_node, io->new_gates, wire_count, err_index, out_on_device);
+    if (!df.pending && io->wire_of_node && io->wire_cap < h->emitted.node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, h->emitted.node_count + 1);
+    st = emitted_build_impl(h, io->input_signals, io->n_in, io->output_signals, io->n_out, io->order_out, io->wire_of_node, io->new_gates, wire_count, err_index, out_on_device,
+                            0, ~0ull, /*keep_phases=*/true);
+    if (!df.pending) return st;
+    // ---- the emit's own status, now that the stream has been synchronised
+    const uint32_t* es = h->h_emit_status;
+    uint32_t flags = es[ES_FLAGS];
+    if (es[ES_NDECL] != df.n_sig) flags |= EF_DUPLICATE;
+    const bool converged = !(df.C && es[ES_MC0 + 2 * (kSpecMsf - 1)] != 0 && es[ES_MC0 + 2 * (kSpecMsf - 1) + 1] != 0);
+    if (flags || !converged) {  // the reference rejects the stream, or the forest needed more Boruvka rounds: the ordinary way
+      slab_reset(h);
+      return classic_run(false);
+    }
+    const uint32_t n_eff = df.C ? es[ES_COUNT] : 0u;
+    const uint32_t node_count = (uint32_t)(df.n_sig + n_eff);
+    h->emitted.node_count = node_count;
+    if (info) { info->n_effective = n_eff; info->node_count = node_count; info->path = C2A_EMIT_PATH_DEVICE; info->rounds = es[ES_ROUNDS]; }
+    if (io->wire_of_node && io->wire_cap < node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, node_count + 1);
+    return st;
   };
+  auto classic = [&]() -> int { return classic_run(true); };
   const bool dense = (pk->flags & C2A_PACKED_DENSE_IDS) != 0;
   const uint64_t n_io = (uint64_t)io->n_in + io->n_out;
   if (!dense || n == 0 || n > g_fused_max_events || nw > 3 * n || n_io > (1u << 24) || (n && !pk->kinds) || (nw && !pk->words)) return classic();

@@ -20,6 +20,8 @@ struct c2a_handle {
   size_t slab_bytes = 0;
   size_t slab_used = 0;
   // pinned host staging for scalars and small metadata (I/O pairs)
+  uint32_t* h_emit_status = nullptr;  // pinned, 64 u32: the emit's final scalars when its status read is deferred behind the build
+  std::string phase_prefix;           // prepended to the phase names recorded while it is set ("emit:" inside c2a_compile_packed*)
   uint32_t* h_pinned = nullptr;
   size_t h_pinned_bytes = 0;
   std::string err;
