@@ -1088,13 +1088,19 @@ def main():
         ins_s, outs_s = np.ascontiguousarray(dc.input_signals), np.ascontiguousarray(dc.output_signals)
         wc_s, err_s = C.c_uint32(0), C.c_uint64(0)
 
+        leg_t = {}
+
         def device_leg():
+            ta = time.perf_counter()
             ctx.emit_compressed(dc.compressed())
+            tb = time.perf_counter()
             st_ = lib.c2a_emitted_build_circuit(h, ins_s.ctypes.data_as(vp), len(ins_s), outs_s.ctypes.data_as(vp), len(outs_s), None, None,
                                                 vp(ps_new.data_ptr()), C.byref(wc_s), C.byref(err_s))
             assert st_ == 0, ctx.last_error()
+            tc = time.perf_counter()
             st_ = lib.c2a_emitted_signal_wires(h, vp(ps_named.data_ptr()), len(named_s), vp(ps_named_w.data_ptr()))
             assert st_ == 0, ctx.last_error()
+            leg_t.update(emit_compressed_s=tb - ta, build_incl_gates_d2h_s=tc - tb, named_wires_s=time.perf_counter() - tc)
 
         device_leg()
         td = time.perf_counter()
@@ -1104,7 +1110,7 @@ def main():
         assert info_s["path"] == 1 and wc_s.value > 0 and int(ps_named_w[:len(named_s)].max()) < wc_s.value
         from_source = {"value": Gs / ((t1 - t0) + dev_s), "unit": "gates/s", "gates": Gs, "events": int(dc._n_events),
                        "source_bytes": len(src_text), "walk_s": t1 - t0, "device_s": dev_s, "host_threads": 1,
-                       "replay_records": int(dc.compressed().n_replays),
+                       "replay_records": int(dc.compressed().n_replays), "device_s_breakdown": dict(leg_t),
                        "note": "mimc_circom_source(W=%d): parse + AST walk (1 host core; a (template, arguments) pair is interpreted twice at most, later "
                                "instances are replay records) = walk_s; c2a_emit_compressed_device (literal ranges + records cross PCIe, the instances are "
                                "expanded in HBM) + c2a_emitted_build_circuit (gates into pinned host memory) + c2a_emitted_signal_wires = device_s" % Ws}

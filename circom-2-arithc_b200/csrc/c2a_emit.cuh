@@ -607,11 +607,14 @@ __device__ __forceinline__ uint32_t eff_rank(const uint32_t* __restrict__ eff, c
   return __ldg(effp + (c >> 5)) + __popc(__ldg(eff + (c >> 5)) & ((1u << (c & 31)) - 1u));
 }
 constexpr int kChaseIlp = 4;
+constexpr uint32_t kHasConst = 0x80000000u, kHasOut = 0x40000000u, kNidMask = 0x3FFFFFFFu;
 __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2* __restrict__ conn, const uint32_t* __restrict__ conn_sb,
                                                          const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
                                                          uint32_t* __restrict__ parent, uint32_t* __restrict__ nidf) {
   const uint32_t stride = gridDim.x * kBlock;
-  for (uint32_t c0 = blockIdx.x * kBlock + threadIdx.x; c0 < C; c0 += stride * kChaseIlp) {
+  const int lane = threadIdx.x & 31;
+  for (uint32_t w0 = blockIdx.x * kBlock + (threadIdx.x & ~31u); w0 < C; w0 += stride * kChaseIlp) {  // warp-uniform trip count (match below)
+    const uint32_t c0 = w0 + lane;
     uint32_t x[kChaseIlp], sb[kChaseIlp], a[kChaseIlp], r0[kChaseIlp], r1[kChaseIlp];
     bool is_eff[kChaseIlp];
 #pragma unroll
@@ -627,17 +630,20 @@ __global__ void __launch_bounds__(kBlock) k_ev_nid_edges(uint32_t C, const uint2
     for (int i = 0; i < kChaseIlp; ++i) r0[i] = parent[a[i]];
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) r1[i] = r0[i] == a[i] ? r0[i] : parent[r0[i]];  // a root needs no second probe (fewer sectors per warp)
+    // One class may hold millions of effective connections (a key wired into every round of every chain: 1.7 M on the MiMC program
+    // compiled from source - 1.8 ms of same-address atomics).  Ids grow with the connection index, so of the lanes of a warp that
+    // share a root only the HIGHEST lane needs the atomic, and a word that already holds a larger id needs none.
 #pragma unroll
     for (int i = 0; i < kChaseIlp; ++i) {
-      if (c0 + i * stride >= C || !is_eff[i]) continue;      // not effective: no id consumed (compiler.rs:235-237)
-      uint32_t id = sb[i] + x[i] + 1u;                        // compiler.rs:257 with node_count = signals + effective merges so far
-      uint32_t r = r1[i] == r0[i] ? r0[i] : uf_find(parent, a[i]);
-      atomicMax(nidf + r, id);
+      const bool act = c0 + i * stride < C && is_eff[i];      // not effective: no id consumed (compiler.rs:235-237)
+      const uint32_t id = sb[i] + x[i] + 1u;                  // compiler.rs:257 with node_count = signals + effective merges so far
+      const uint32_t r = !act ? kNone : (r1[i] == r0[i] ? r0[i] : uf_find(parent, a[i]));
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, r);
+      if (act && 31 - __clz(peers) == lane && (__ldcg(nidf + r) & kNidMask) < id) atomicMax(nidf + r, id);
     }
   }
 }
 // node_of_signal + the merge-error screens (compiler.rs:239-245)
-constexpr uint32_t kHasConst = 0x80000000u, kHasOut = 0x40000000u, kNidMask = 0x3FFFFFFFu;
 constexpr int kFinIlp = 2;
 __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32_t* __restrict__ sig_t, const uint2* __restrict__ sig_meta,
                                                         const uint8_t* __restrict__ outmark, const uint32_t* __restrict__ eff, const uint32_t* __restrict__ effp,
@@ -853,6 +859,7 @@ struct EmitSrc {
   const c2a_event* ev_dev = nullptr;
   const c2a_packed_events* pk = nullptr;
   bool pk_on_device = false;
+  bool keep_phases = false;  // the caller already opened this call's phase list (the expansion of a compressed stream)
 };
 
 // c2a_compile_packed* on a large stream: the emit does not wait for its own final status - the build is enqueued right behind
@@ -878,7 +885,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   const c2a_event* ev = ev_host;
   if (info) memset(info, 0, sizeof *info);
   if (info) info->n_events = n;
-  phases_clear(h);
+  if (!src.keep_phases) phases_clear(h);
   cudaStream_t s = h->stream;
   const uint32_t tiles = (uint32_t)((n + kEvTile - 1) / kEvTile);
   uint32_t* hp = h->h_pinned;
@@ -1266,14 +1273,18 @@ int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c
   // found by binary search; the largest generation in the run by a sparse table.)  Without this an inconsistent record would read
   // bytes that are unwritten in this launch, or stale ones from the previous call, and expand to a plausible but wrong stream.
   if (nr) {
-    std::vector<std::vector<uint32_t>> tab(1, std::vector<uint32_t>(nr));
-    for (uint64_t i = 0; i < nr; ++i) tab[0][i] = cx->replays[i].gen;
-    for (uint64_t len = 2, lv = 1; len <= nr; len <<= 1, ++lv) {
-      tab.emplace_back(nr - len + 1);
-      for (uint64_t i = 0; i + len <= nr; ++i) tab[lv][i] = std::max(tab[lv - 1][i], tab[lv - 1][i + len / 2]);
+    std::vector<std::vector<uint32_t>> tab;
+    if (max_gen > 1) {  // (one generation: any destination inside a source range is already an error - no table needed)
+      tab.emplace_back(nr);
+      for (uint64_t i = 0; i < nr; ++i) tab[0][i] = cx->replays[i].gen;
+      for (uint64_t len = 2, lv = 1; len <= nr; len <<= 1, ++lv) {
+        tab.emplace_back(nr - len + 1);
+        for (uint64_t i = 0; i + len <= nr; ++i) tab[lv][i] = std::max(tab[lv - 1][i], tab[lv - 1][i + len / 2]);
+      }
     }
     auto range_max = [&](uint64_t lo, uint64_t hi) -> uint32_t {  // max gen of records [lo, hi)
       if (lo >= hi) return 0;
+      if (max_gen <= 1) return 1;
       const int lv = 63 - __builtin_clzll(hi - lo);
       return std::max(tab[lv][lo], tab[lv][hi - (1ull << lv)]);
     };
@@ -1299,6 +1310,7 @@ int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c
   // ---- chunk tables: generation 0 = the literal ranges (source: the packed literal staging), generation g = records of gen g
   auto n_chunks_of = [](uint64_t len) { return (len + kCxChunk - 1) / kCxChunk; };
   std::vector<std::vector<CxChunk>> kch(max_gen + 1), wch(max_gen + 1);
+  if (max_gen == 1) { kch[1].reserve(nr + n / kCxChunk + 1); wch[1].reserve(nr + nw / kCxChunk + 1); }
   auto add_chunks = [&](std::vector<CxChunk>& v, uint64_t dst, uint64_t src, uint64_t len, uint32_t delta) {
     for (uint64_t o = 0; o < len; o += kCxChunk) v.push_back(CxChunk{dst + o, src + o, (uint32_t)std::min<uint64_t>(kCxChunk, len - o), delta});
   };
@@ -1353,16 +1365,19 @@ int c2a_emit_compressed_device(c2a_handle* h, const c2a_compressed_events* cx, c
   phases_clear(h);
   if (!cuda_ok(h, cudaMemcpyAsync(d_lit_k, h->cx_pinned, lit_k_bytes + lit_w_bytes + sizeof(CxChunk) * t_at, cudaMemcpyHostToDevice, s), "compressed H2D")) return C2A_ERR_CUDA;
   const int wide = h->num_sms * 8;
+  phase_begin(h, "k_cx_copy");
   for (uint32_t g = 0; g <= max_gen; ++g) {
     const uint32_t nk = (uint32_t)kch[g].size(), nwc = (uint32_t)wch[g].size();
     if (nk) LAUNCH(h, k_cx_copy_u8, std::min<uint32_t>(nk, (uint32_t)wide), kBlock, d_t + k_off[g], nk, g ? (const uint8_t*)d_kinds : (const uint8_t*)d_lit_k, d_kinds);
     if (nwc) LAUNCH(h, k_cx_copy_u32, std::min<uint32_t>(nwc, (uint32_t)wide), kBlock, d_t + w_off[g], nwc, g ? (const uint32_t*)d_words : (const uint32_t*)d_lit_w, d_words);
   }
+  phase_end(h);
   if (!cuda_ok(h, cudaGetLastError(), "expand kernels")) return C2A_ERR_CUDA;
   c2a_packed_events pk{d_kinds, d_words, n, nw, cx->flags, 0};
   EmitSrc src;
   src.pk = &pk;
   src.pk_on_device = true;
+  src.keep_phases = true;
   return emit_events_impl(h, src, n, info, err_event);
 }
 

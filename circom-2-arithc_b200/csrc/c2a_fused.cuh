@@ -506,7 +506,8 @@ __global__ void __launch_bounds__(kFusedBlock, 1) k_fused_compile(const FusedPar
       const uint32_t wd = ldg2(P.eff + (c >> 5));
       if (!((wd >> (c & 31)) & 1u)) continue;  // not effective: no id consumed (compiler.rs:235-237)
       const uint32_t id = ldg2(P.conn_sb + c) + P.effp[c >> 5] + __popc(wd & ((1u << (c & 31)) - 1u)) + 1u;  // compiler.rs:257
-      atomicMax(P.nidf + fused_find(P.parent, ldg2(P.conn + c).x), id);
+      const uint32_t root = fused_find(P.parent, ldg2(P.conn + c).x);
+      if ((ldg2(P.nidf + root) & kNidMask) < id) atomicMax(P.nidf + root, id);  // (a class may hold most connections: skip what cannot raise the word)
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) sc[FS_NEFF] = n_eff;
     // the node bound is known: pick the wire map (the caller's when it holds S + n_eff + 1 entries) and clear it

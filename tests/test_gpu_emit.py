@@ -479,3 +479,32 @@ def test_resident_circuit_survives_other_sizes(ctx, orc, c2a):
     ctx.emit_events(np.ascontiguousarray(a.events))
     _workload_case(ctx, orc, c2a, b, False)
     _workload_case(ctx, orc, c2a, a, True)
+
+
+@pytest.mark.parametrize("name", ["sha256_full", "keccak_r8"])
+def test_baseline_sized_streams_against_the_oracle_emit(ctx, orc, c2a, name):
+    """BASELINE config 3 at FULL size (SHA-256-shaped, 115 920 gates, 233 K events) and a third of config 4 (Keccak-shaped, 8 rounds,
+    64 K gates): the device emitter, the 4 B/event stream, the fused / multi-kernel compile against the ORACLE's faithful linear-scan
+    emit (src/compiler.rs:139-278: about two minutes of host time for the SHA stream) and its back end - not against this
+    repo's own host emitter."""
+    wl = c2a.workloads.sha256_shaped() if name == "sha256_full" else c2a.workloads.keccak_shaped(1, rounds=8)
+    ev = np.ascontiguousarray(wl.events)
+    oc = orc.OracleCompiler()
+    oc.emit_events(ev)
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    nodes = lambda s: np.array([oc.signal_node(int(x)) for x in s], dtype=np.uint32)
+    st, _, o_order, o_wire, o_gates, o_wc = orc.backend_raw(oc.gate_array(), oc.node_count + 1, nodes(ins), nodes(outs))
+    assert st == 0
+    info = ctx.emit_events(ev)
+    g, _ = ctx.emitted_fetch(want_nodes=False)
+    assert info["path"] == DEVICE and info["node_count"] == oc.node_count and np.array_equal(g, oc.gate_array())
+    for implicit in (False, True):
+        k, w, f = c2a.pack_events(ev, implicit=implicit)
+        for fused in (0, 1 << 22):
+            c2a.lib.c2a_set_fused_limits(fused, 0)
+            try:
+                i2, order, wire, ng, wc = ctx.compile_packed(k, w, f, ins, outs)
+            finally:
+                c2a.lib.c2a_set_fused_limits(1 << 22, 0)
+            assert i2["node_count"] == oc.node_count and wc == o_wc
+            assert np.array_equal(order, o_order) and np.array_equal(wire, o_wire) and np.array_equal(ng, o_gates)
