@@ -1435,9 +1435,11 @@ int c2a_create(int device, c2a_handle** out) {
   if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); delete h; return C2A_ERR_CUDA; }
   if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_side2, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     if (h->ev_side) cudaEventDestroy(h->ev_side);
+    if (h->ev_side2) cudaEventDestroy(h->ev_side2);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1448,6 +1450,7 @@ int c2a_create(int device, c2a_handle** out) {
   if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
     cudaGetLastError();
     cudaEventDestroy(h->ev_side);
+    cudaEventDestroy(h->ev_side2);
     cudaEventDestroy(h->ev_main);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
@@ -1474,6 +1477,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->h_emit_status) cudaFreeHost(h->h_emit_status);
   cudaStreamSynchronize(h->stream2);
   cudaEventDestroy(h->ev_side);
+  cudaEventDestroy(h->ev_side2);
   cudaEventDestroy(h->ev_main);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);

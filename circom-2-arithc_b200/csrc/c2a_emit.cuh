@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(kBlock) k_ev_count(const uint4* __restrict__ e
 // tile_g / tile_c: exclusive scans of the per-tile counts (k_scan_u32), entry [tiles] = totals.
 // sig_t[sid]    event index of the declaration (kNone = never declared)
 // sig_meta[sid] {signal index (declaration rank) | is_const << 31, #connections before the declaration}
+// (dense ids: one 4-byte word per signal instead, #connections before the declaration | is_const << 31)
 // egates[g]     {op, lhs signal, rhs signal, out signal};  gate_t[g] event index
 // conn[c]       {a, b};  conn_t[c] event index;  conn_sb[c] #signals declared before the connection
 __global__ void __launch_bounds__(kBlock) k_ev_scatter(const uint4* __restrict__ ev, uint64_t n, uint32_t tiles, uint32_t S_cap,
@@ -194,27 +195,30 @@ __global__ void __launch_bounds__(kBlock) k_pk_count(const uint8_t* __restrict__
         }
       }
     }
-    uint32_t g = 0, c = 0, im = 0;
-    const uint32_t opmask = implicit ? 31u : 63u;
+    // byte-parallel: 0/1 per byte for "gate" / "connection" / "flagged", summed over the 8 words (<= 8 per byte) and folded once;
+    // the op field of all four bytes is validated with two masked compares (this kernel was ALU-bound on per-byte tests and POPC)
+    uint32_t ag = 0, ac = 0, ai = 0, bad_kind = 0, bad_op = 0;
+    const uint32_t opm = implicit ? 0x1F1F1F1Fu : 0x3F3F3F3Fu;
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
       const uint32_t lo = w[q] & 0x01010101u, hi = (w[q] >> 1) & 0x01010101u;  // kind bit 0 / bit 1 of each byte
-      const uint32_t is_g = hi & ~lo, is_c = hi & lo, b7 = (w[q] >> 7) & 0x01010101u;
-      g += __popc(is_g);
-      c += __popc(is_c);
-      if (implicit) {
-        im += __popc(b7 & hi);
-        if (b7 & ~hi) f |= EF_BAD_KIND;  // the flag on a signal declaration
-      }
+      const uint32_t is_g = hi & ~lo, is_c = hi & lo;
+      ag += is_g;
+      ac += is_c;
       // op field (bits 2..7 of each byte, 2..6 with implicit operands): must be < 20 on a gate, 0 elsewhere (c2a_pack_events marks
       // an invalid kind that way)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t kb = (w[q] >> (8 * j)) & 0xFFu, op = (kb >> 2) & opmask;
-        if ((kb & 3u) == C2A_EV_GATE) { if (op >= C2A_GATE_TYPE_COUNT) f |= EF_BAD_OP; }
-        else if (op) f |= EF_BAD_KIND;
+      const uint32_t op = (w[q] >> 2) & opm, mg = is_g * 0xFFu;
+      bad_kind |= op & ~mg;
+      bad_op |= ((op & mg) + 0x01010101u * (0x80u - C2A_GATE_TYPE_COUNT)) & 0x80808080u;  // (op <= 63: no carry into the next byte)
+      if (implicit) {
+        const uint32_t b7 = (w[q] >> 7) & 0x01010101u;
+        ai += b7 & hi;
+        bad_kind |= b7 & ~hi;  // the flag on a signal declaration
       }
     }
+    if (bad_kind) f |= EF_BAD_KIND;
+    if (bad_op) f |= EF_BAD_OP;
+    uint32_t g = (ag * 0x01010101u) >> 24, c = (ac * 0x01010101u) >> 24, im = (ai * 0x01010101u) >> 24;
     g = warp_sum(g);
     c = warp_sum(c);
     if (implicit) im = warp_sum(im);
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_pk_scatter_t(const uint8_t* __res
           const uint32_t cbit = (kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u;
           // dense ids: the id IS the declaration rank (< n <= S_cap) - the record is complete right here, lanes holding signals write
           // consecutive slots (no filing, no phase-B pass for the most frequent kind)
-          if (dense) sig_meta[s0 + ds] = make_uint2((s0 + ds) | cbit, c0 + my_dc);
+          if (dense) reinterpret_cast<uint32_t*>(sig_meta)[s0 + ds] = (c0 + my_dc) | cbit;  // dense record: 4 bytes (the rank is the index)
           else s_list[min(ng + nc + ds, (uint32_t)kEvTile - 1)] = k | (my_dg << 10) | cbit;
         }
       }
@@ -658,7 +662,10 @@ __global__ void __launch_bounds__(kBlock) k_ev_finalize(uint32_t S, const uint32
     for (int i = 0; i < kFinIlp; ++i) {
       uint32_t s = min(s0 + i * stride, S - 1);
       t[i] = sig_t ? sig_t[s] : 0u;  // dense ids: no declaration table, every id below S is declared
-      m[i] = t[i] != kNone ? sig_meta[s] : make_uint2(0, 0);  // (an undeclared id has no record: do not read uninitialised memory)
+      if (!sig_t) {  // dense record: #connections before the declaration | is_const << 31; the declaration rank is the id
+        const uint32_t v = reinterpret_cast<const uint32_t*>(sig_meta)[s];
+        m[i] = make_uint2(s | (v & 0x80000000u), v & 0x7FFFFFFFu);
+      } else m[i] = t[i] != kNone ? sig_meta[s] : make_uint2(0, 0);  // (an undeclared id has no record: do not read uninitialised memory)
       om[i] = outmark[s];
       r0[i] = parent[s];
     }
@@ -945,6 +952,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       side_nidf = (uint32_t*)take(4 * S_side);
       side_eff = (uint32_t*)take(4 * effw_side);
       side_effp = (uint32_t*)take(4 * effw_side);
+      cudaMemsetAsync(outmark, 0, std::min<uint64_t>(S_cap, n + 1), h->stream2);
+      cudaEventRecord(h->ev_side2, h->stream2);
       cudaMemsetAsync(side_best, 0xFF, 4 * S_side, h->stream2);
       cudaMemsetAsync(side_nidf, 0, 4 * S_side, h->stream2);
       cudaMemsetAsync(side_eff, 0, 4 * effw_side, h->stream2);
@@ -968,11 +977,11 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       copied = true;
     }
     phase_begin(h, "init");
-    cudaMemsetAsync(cnt_state, 0, 16 * ((size_t)ctiles + 1), s);
-    if (pk_impl) cudaMemsetAsync(cnt_state_i, 0, 8 * ((size_t)ctiles + 1), s);
-    cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
-    if (!pk_dense) cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
-    cudaMemsetAsync(outmark, 0, pk_dense ? std::min<uint64_t>(S_cap, n + 1) : S_cap, s);
+    cudaMemsetAsync(cnt_state, 0, (char*)es + 4 * ES_COUNT - (char*)cnt_state, s);  // look-back states of the count scans + the status block (carved back to back)
+    if (!pk_dense) {
+      cudaMemsetAsync(sig_t, 0xFF, 4 * S_cap, s);
+      cudaMemsetAsync(outmark, 0, S_cap, s);
+    }  // (dense: outmark is cleared on the side stream, beside the count pass - the scatter waits for it)
     phase_end(h);
     if (tiles) {
       const uint32_t egrid = std::min<uint32_t>(tiles, (uint32_t)wide);
@@ -985,6 +994,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       if (pk_impl) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_i, tile_i, tiles, cnt_state_i, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
+      if (pk_dense) cudaStreamWaitEvent(s, h->ev_side2, 0);  // outmark is clear
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
       if (pk && pk_impl) {
