@@ -243,7 +243,7 @@ constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words p
 // kMode 2: every gate and connection is flagged (what the walker emits) - the third rank is the sum of the other two, a gate has 2
 //          payload words and a connection 1, nothing per event has to be tested;  kMode 1: flagged and unflagged events mixed.
 template <int kMode>
-__global__ void __launch_bounds__(kBlock, 6) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+__global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, const uint32_t* __restrict__ tile_i /* null: no implicit operands */,
                                                        uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
@@ -397,6 +397,70 @@ __global__ void __launch_bounds__(kBlock, 6) k_pk_scatter_t(const uint8_t* __res
         }
       }
     };
+    // ---- dense ids, interior tile: ONE pass, one lane per event, every record stored from the lane that ranked it.  The lanes of a
+    // warp split three ways (gate / connection / signal), but nothing is filed in shared memory and re-derived in a second pass -
+    // about half the instructions of phase A + phase B in a kernel that is bound by instruction issue.  Lanes that hold the same
+    // kind write consecutive records, so the stores still fill whole sectors.
+    auto phase_direct = [&]() {
+      const uint8_t* __restrict__ skl = &s_k[stage][warp * 128 + lane];
+      const uint32_t* __restrict__ sw = &s_w[stage][woff];
+      uint32_t kb[4], gm[4], cm[4], im[4];
+      uint32_t wg = 0, wc = 0, wi = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        kb[j] = skl[j * 32];
+        gm[j] = __ballot_sync(0xFFFFFFFFu, (kb[j] & 3u) == C2A_EV_GATE);
+        cm[j] = __ballot_sync(0xFFFFFFFFu, (kb[j] & 3u) == C2A_EV_CONNECT);
+        wg += __popc(gm[j]);
+        wc += __popc(cm[j]);
+        if (mixed) { im[j] = __ballot_sync(0xFFFFFFFFu, (kb[j] & 0x82u) == 0x82u); wi += __popc(im[j]); }
+        else im[j] = 0;
+      }
+      if (lane == 0) s_cnt[warp] = make_uint2(wg | (wc << 16), wi);
+      __syncthreads();
+      uint32_t dg, dc, di;
+      {
+        uint2 v = (lane < 8 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
+#pragma unroll
+        for (int o = 4; o; o >>= 1) { v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o); if (mixed) v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o); }
+        v.x = __shfl_sync(0xFFFFFFFFu, v.x, 0);
+        dg = v.x & 0xFFFFu;
+        dc = v.x >> 16;
+        di = mixed ? __shfl_sync(0xFFFFFFFFu, v.y, 0) : 0u;
+      }
+      if (threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t k = warp * 128 + j * 32 + lane;
+        const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
+        const uint32_t my_di = all_impl ? my_dg + my_dc : (mixed ? di + __popc(im[j] & lt) : 0u);
+        dg += __popc(gm[j]);
+        dc += __popc(cm[j]);
+        if (mixed) di += __popc(im[j]);
+        const uint32_t before = s0 + (k - my_dg - my_dc);  // signals declared before this event (dense ids: every id below it exists)
+        const uint32_t wl = 3u * my_dg + 2u * my_dc - my_di;
+        const bool flagged = all_impl || (implicit && (kb[j] & 0x80u));
+        if ((gm[j] >> lane) & 1u) {
+          uint4 gt = make_uint4(implicit ? (kb[j] >> 2) & 31u : kb[j] >> 2, sw[wl], sw[wl + 1], flagged ? before - 1u : sw[wl + 2]);
+          if (gt.y < before && gt.z < before && gt.w < before) outmark[gt.w] = 1;  // compiler.rs:201 marks the out node is_out
+          else { f |= EF_UNKNOWN_REF; gt.y = gt.z = gt.w = 0; }
+          egates[g0 + my_dg] = gt;
+        } else if ((cm[j] >> lane) & 1u) {
+          uint2 ab = flagged ? make_uint2(before - 1u, sw[wl]) : make_uint2(sw[wl], sw[wl + 1]);
+          if (!(ab.x < before && ab.y < before)) { f |= EF_UNKNOWN_REF; ab = make_uint2(0, 0); }
+          conn[c0 + my_dc] = ab;
+          conn_sb[c0 + my_dc] = before;
+        } else {
+          reinterpret_cast<uint32_t*>(sig_meta)[before] = (c0 + my_dc) | ((kb[j] & 3u) == C2A_EV_SIGNAL_CONST ? 0x80000000u : 0u);
+        }
+      }
+    };
+    const uint32_t wn_all = 3u * ng + 2u * nc - ni;  // payload words of a dense tile
+    if (dense && nev == (uint32_t)kEvTile && kcov == (uint32_t)kEvTile && ng + nc <= (uint32_t)kEvTile && woff + wn_all <= wcov) {
+      phase_direct();
+      __syncthreads();  // the stage may be refilled from the next iteration on
+      continue;
+    }
     if (nev == (uint32_t)kEvTile && kcov == (uint32_t)kEvTile && ng + nc <= (uint32_t)kEvTile) phase_a(std::true_type{});
     else phase_a(std::false_type{});
     __syncthreads();
