@@ -1106,6 +1106,16 @@ void phases_collect(c2a_handle* h) {
     acc[p.name] += ms;
   }
   for (auto& n : names) h->last_ms.push_back({n, acc[n]});
+  if (getenv("C2A_PHASE_TIMELINE")) {  // developer aid: where the stream idles between phases (start offset, duration, gap before)
+    float prev_end = 0;
+    for (auto& p : h->phases) {
+      if (p.open) continue;
+      float t0 = 0, d = 0;
+      if (cudaEventElapsedTime(&t0, h->phases.front().a, p.a) != cudaSuccess || cudaEventElapsedTime(&d, p.a, p.b) != cudaSuccess) { cudaGetLastError(); continue; }
+      fprintf(stderr, "[c2a timeline] %-28s start %8.3f ms  dur %7.3f ms  gap before %7.3f ms\n", p.name.c_str(), t0, d, t0 - prev_end);
+      prev_end = t0 + d;
+    }
+  }
   float tot = 0;
   if (cudaEventElapsedTime(&tot, h->phases.front().a, h->phases.back().b) == cudaSuccess) h->last_ms.push_back({"total", tot});
   else cudaGetLastError();
@@ -1436,10 +1446,12 @@ int c2a_create(int device, c2a_handle** out) {
   if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_side2, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_counts, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_main, cudaEventDisableTiming) != cudaSuccess) {
     cudaGetLastError();
     if (h->ev_side) cudaEventDestroy(h->ev_side);
     if (h->ev_side2) cudaEventDestroy(h->ev_side2);
+    if (h->ev_counts) cudaEventDestroy(h->ev_counts);
     if (h->stream2) cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
     delete h;
@@ -1451,6 +1463,7 @@ int c2a_create(int device, c2a_handle** out) {
     cudaGetLastError();
     cudaEventDestroy(h->ev_side);
     cudaEventDestroy(h->ev_side2);
+    cudaEventDestroy(h->ev_counts);
     cudaEventDestroy(h->ev_main);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->stream);
@@ -1478,6 +1491,7 @@ void c2a_destroy(c2a_handle* h) {
   cudaStreamSynchronize(h->stream2);
   cudaEventDestroy(h->ev_side);
   cudaEventDestroy(h->ev_side2);
+  cudaEventDestroy(h->ev_counts);
   cudaEventDestroy(h->ev_main);
   cudaStreamDestroy(h->stream2);
   cudaStreamDestroy(h->stream);

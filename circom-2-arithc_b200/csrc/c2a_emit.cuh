@@ -970,11 +970,14 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint2 *sig_meta = nullptr, *conn = nullptr;
   uint4* egates = nullptr;
   uint8_t* outmark = nullptr;
+  unsigned long long* nid_state = nullptr;
   uint32_t *side_best = nullptr, *side_parent = nullptr, *side_nidf = nullptr, *side_eff = nullptr, *side_effp = nullptr;
   const uint4* d_ev = nullptr;
   uint64_t G = 0, C = 0, n_sig = 0;
   uint32_t S = 0, flags = 0;
   bool copied = false;
+  constexpr int kEarlyAt = 40;  // word offset of the early totals in h_emit_status (behind the final status block)
+  const bool early = defer && pk_dense && h->h_emit_status;
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t pk_kbytes = pk ? align256(n + 4) : 0;  // packed staging: kinds, then words
     const size_t ev_copy = pk ? (src.pk_on_device ? 0 : pk_kbytes + align256(4 * pk->n_words + 4)) : (ev_dev ? 0 : align256(16 * n));
@@ -986,7 +989,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     const uint64_t effw_side = pk_dense ? pk->n_words / (pk_impl ? 32 : 64) + 4 : 0;
     const size_t side_bytes = pk_dense ? 3 * align256(4 * S_side) + 2 * align256(4 * effw_side) : 0;
     const size_t ev_need = side_bytes + ev_copy + 3 * align256(4 * ((size_t)tiles + 2)) + align256(8 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
-                           align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
+                           align256(8 * ((size_t)scan_tiles(n / 32 + 2, kScanItems) + 1)) + align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
     if (ev_need > h->ev_bytes) {
       if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
       if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
@@ -1001,6 +1004,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     uint32_t* tile_i = (uint32_t*)take(4 * ((size_t)tiles + 2));
     unsigned long long* cnt_state = (unsigned long long*)take(16 * ((size_t)ctiles + 1));  // look-back states of the two count scans
     unsigned long long* cnt_state_i = (unsigned long long*)take(8 * ((size_t)ctiles + 1));  // ... and of the implicit-operand counts
+    nid_state = (unsigned long long*)take(8 * ((size_t)scan_tiles(n / 32 + 2, kScanItems) + 1));  // ... and of the effective-connection bitmap scan (C <= n)
     es = (uint32_t*)take(4 * ES_COUNT);
     sig_t = (uint32_t*)take(4 * S_cap);
     sig_meta = (uint2*)take(8 * S_cap);
@@ -1058,6 +1062,19 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       if (pk_impl) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_i, tile_i, tiles, cnt_state_i, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
       phase_end(h);
+      if (early) {
+        // The host needs the totals only to size what FOLLOWS the scatter, and they exist once the count scans are done: the side
+        // stream copies them out while the scatter runs, the host waits for that copy instead of for the scatter (whose own flags
+        // are read with the final status - a deferred emit looks at them after the build's synchronisation anyway).
+        uint32_t* e = h->h_emit_status + kEarlyAt;
+        cudaEventRecord(h->ev_main, s);
+        cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
+        cudaMemcpyAsync(e + 0, tile_g + tiles, 4, cudaMemcpyDeviceToHost, h->stream2);
+        cudaMemcpyAsync(e + 1, tile_c + tiles, 4, cudaMemcpyDeviceToHost, h->stream2);
+        if (pk_impl) cudaMemcpyAsync(e + 2, tile_i + tiles, 4, cudaMemcpyDeviceToHost, h->stream2);
+        cudaMemcpyAsync(e + 3, es + ES_FLAGS, 4, cudaMemcpyDeviceToHost, h->stream2);  // the count pass's verdict on kinds and ops
+        cudaEventRecord(h->ev_counts, h->stream2);
+      }
       if (pk_dense) cudaStreamWaitEvent(s, h->ev_side2, 0);  // outmark is clear
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
@@ -1074,15 +1091,29 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
       if (pk_impl) cudaMemcpyAsync(es + ES_NIMPL, tile_i + tiles, 4, cudaMemcpyDeviceToDevice, s);
     }
-    cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-    if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
-    if (!cuda_ok(h, cudaGetLastError(), "event scatter")) return C2A_ERR_CUDA;
-    G = hp[ES_NGATE];
-    C = hp[ES_NCONN];
-    S = hp[ES_SBOUND];
-    flags = hp[ES_FLAGS];
-    n_sig = n - G - C;
-    const uint64_t n_impl = pk_impl ? hp[ES_NIMPL] : 0;
+    bool have_counts = false;
+    uint64_t n_impl = 0;
+    if (early && tiles) {
+      if (!cuda_ok(h, cudaEventSynchronize(h->ev_counts), "count sync")) return C2A_ERR_CUDA;
+      const uint32_t* e = h->h_emit_status + kEarlyAt;
+      G = e[0];
+      C = e[1];
+      n_impl = pk_impl ? e[2] : 0;
+      // anything irregular goes the ordinary way: wait for the scatter and look at the whole status block
+      have_counts = e[3] == 0 && G + C <= n && pk->n_words == 3 * G + 2 * C - n_impl;
+      if (have_counts) { n_sig = n - G - C; S = (uint32_t)n_sig; flags = 0; }  // dense ids: the table bound is the number of declarations
+    }
+    if (!have_counts) {
+      cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
+      if (!cuda_ok(h, cudaStreamSynchronize(s), "scatter sync")) return C2A_ERR_CUDA;
+      if (!cuda_ok(h, cudaGetLastError(), "event scatter")) return C2A_ERR_CUDA;
+      G = hp[ES_NGATE];
+      C = hp[ES_NCONN];
+      S = hp[ES_SBOUND];
+      flags = hp[ES_FLAGS];
+      n_sig = n - G - C;
+      n_impl = pk_impl ? hp[ES_NIMPL] : 0;
+    }
     if (pk && !(flags & EF_BAD_KIND) && pk->n_words != 3 * G + 2 * C - n_impl + (pk_dense ? 0 : n_sig))
       return fail(h, C2A_ERR_INVALID_ARGUMENT, "n_words (%llu) does not match the kinds (%llu gates, %llu connections, %llu signals)",
                   (unsigned long long)pk->n_words, (unsigned long long)G, (unsigned long long)C, (unsigned long long)n_sig);
@@ -1148,9 +1179,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   if (!parent || !best || !nidf || !eff || !effp) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
   uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
   uint4* cand = (uint4*)slab_alloc(h, 16 * C);
-  unsigned long long* tile_state = (unsigned long long*)slab_alloc(h, 8 * (size_t)(scan_tiles(C + 1, kScanItems) + 1));
-  uint32_t* ticket = (uint32_t*)slab_alloc(h, 256);
-  if (!ticket) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  if (!cand) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  unsigned long long* tile_state = nid_state;  // in the staging block: zeroed by the first memset of the call
 
   phase_begin(h, "init");
   if (pk_dense) cudaStreamWaitEvent(s, h->ev_side, 0);  // initialised on the side stream while E0 / E1 ran
@@ -1194,10 +1224,12 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   auto node_ids = [&](bool sync = true) {
     uint32_t stiles = scan_tiles(C + 1, kScanItems);
     phase_begin(h, "init");
-    cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
-    cudaMemsetAsync(ticket, 0, 4, s);
-    if (!pk_dense || nid_runs++) cudaMemsetAsync(nidf, 0, 4 * (size_t)S, s);  // (dense, first run: zeroed on the side stream)
-    cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
+    if (nid_runs) {  // a second run (the forest needed more rounds): forget the first one
+      cudaMemsetAsync(tile_state, 0, 8 * (size_t)stiles, s);
+      cudaMemsetAsync(es + ES_NDECL, 0, 4, s);
+    }
+    if (!pk_dense || nid_runs) cudaMemsetAsync(nidf, 0, 4 * (size_t)S, s);  // (dense, first run: zeroed on the side stream)
+    ++nid_runs;
     phase_end(h);
     // effp = exclusive scan of popcount(eff words); effp[effw] receives the total (= effective connections)
     phase_begin(h, "k_scan_u32");

@@ -14,6 +14,7 @@ struct c2a_handle {
   cudaStream_t stream = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: initialisation of arrays that are only needed later runs next to the kernels before them
   cudaEvent_t ev_side = nullptr;
+  cudaEvent_t ev_counts = nullptr;  // side stream: the emitter's early totals have reached the host
   cudaEvent_t ev_side2 = nullptr;  // an earlier point of the side stream (the emitter's outmark clear)
   cudaEvent_t ev_main = nullptr;   // orders the side stream after what the main stream already holds
   // one growable device slab carved per call by a bump allocator (no per-call cudaMalloc)
