@@ -527,11 +527,8 @@ __device__ __forceinline__ uint32_t scan_tile_prefix(uint32_t tile, uint32_t thr
 // guard_kind: 0 none, 1 = part of the sort (guard = its scalars), 2 = part of the wire numbering.
 constexpr int kScanItems = 16;  // 4096 elements per tile: fewer links in the look-back chain
 template <bool kPopc>  // kPopc: scan popcount(src[i]) instead of src[i] (rank structure over a bitmap)
-__global__ void __launch_bounds__(kBlock) k_scan_u32_t(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
-                                                       uint32_t* __restrict__ total_out, const uint32_t* __restrict__ guard, int guard_kind) {
-  __shared__ uint32_t s_mem[10];
-  if (guard_kind == 1 && (!sort_wanted(guard) || sort_parked(guard))) return;
-  if (guard_kind == 2 && tail_parked(guard)) return;
+__device__ __forceinline__ void scan_u32_body(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
+                                              uint32_t* __restrict__ total_out, uint32_t* s_mem) {
   const uint32_t tiles = (n + kBlock * kScanItems - 1) / (kBlock * kScanItems);
   const uint32_t tile = blockIdx.x;
   uint32_t base = tile * (kBlock * kScanItems) + threadIdx.x * kScanItems;
@@ -563,6 +560,21 @@ __global__ void __launch_bounds__(kBlock) k_scan_u32_t(const uint32_t* src, uint
 #pragma unroll
     for (int i = 0; i < kScanItems; ++i) if (base + i < n) dst[base + i] = v[i];
   }
+}
+template <bool kPopc>
+__global__ void __launch_bounds__(kBlock) k_scan_u32_t(const uint32_t* src, uint32_t* dst, uint32_t n, unsigned long long* __restrict__ tile_state,
+                                                       uint32_t* __restrict__ total_out, const uint32_t* __restrict__ guard, int guard_kind) {
+  __shared__ uint32_t s_mem[10];
+  if (guard_kind == 1 && (!sort_wanted(guard) || sort_parked(guard))) return;
+  if (guard_kind == 2 && tail_parked(guard)) return;
+  scan_u32_body<kPopc>(src, dst, n, tile_state, total_out, s_mem);
+}
+// up to three independent in-place scans of equal length in ONE launch (blockIdx.y picks the array): the emitter's per-tile gate /
+// connection / implicit-operand counts - three back-to-back launches of a latency-bound 10-CTA kernel otherwise
+struct ScanJobs { uint32_t* a[3]; unsigned long long* state[3]; };
+__global__ void __launch_bounds__(kBlock) k_scan_u32_multi(ScanJobs jobs, uint32_t n) {
+  __shared__ uint32_t s_mem[10];
+  scan_u32_body<false>(jobs.a[blockIdx.y], jobs.a[blockIdx.y], n, jobs.state[blockIdx.y], nullptr, s_mem);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1143,6 +1155,11 @@ int grid_for(c2a_handle* h, const void* kernel, int block, uint64_t n) {
     kernel<<<(grid), (block), 0, (h)->stream>>>(__VA_ARGS__);         \
     (h)->launches++;                                                  \
   } while (0)
+#define LAUNCH_SIDE(h, kernel, grid, block, ...)                      \
+  do {                                                                \
+    kernel<<<(grid), (block), 0, (h)->stream2>>>(__VA_ARGS__);        \
+    (h)->launches++;                                                  \
+  } while (0)
 
 static inline uint32_t scan_tiles(uint64_t n, int items) { return (uint32_t)((n + (uint64_t)kBlock * items - 1) / ((uint64_t)kBlock * items)); }
 
@@ -1321,10 +1338,18 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   // wire[] is first touched after the sort: its fill runs on the side stream next to K1 / K2 / K5 (several of which are
   // latency-bound) and the main stream joins in front of the first wire kernel
   bool wire_join = false;
-  if (p.want_wire && p.node_bound) {
+  if (p.want_wire) {
     cudaEventRecord(h->ev_main, st);
     cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
-    cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, h->stream2);
+    if (p.node_bound) cudaMemsetAsync(d_wire, 0xFF, 4 * (size_t)p.node_bound, h->stream2);
+    // ... and so do the I/O tags (inputs: their wire ids right away; outputs: "pending") - they depend on the fill only, not on the sort
+    const uint32_t* t_in = io_nodes;
+    const uint32_t* t_out = io_nodes + p.n_in;
+    if (p.n_in) {
+      LAUNCH_SIDE(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, p.n_in), kBlock, t_in, p.n_in, p.node_bound, 0u, d_wire, sc);
+      LAUNCH_SIDE(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, p.n_in), kBlock, t_in, p.n_in, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
+    }
+    if (p.n_out) LAUNCH_SIDE(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, p.n_out), kBlock, t_out, p.n_out, p.node_bound, kOutPending, d_wire, sc);
     cudaEventRecord(h->ev_side, h->stream2);
     wire_join = true;
   }
@@ -1344,7 +1369,6 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   sort_enqueue_relax(h, dep, G, s);
 
   const uint32_t ni = p.n_in, no = p.n_out;
-  const uint32_t* d_in = io_nodes;
   const uint32_t* d_out = io_nodes + ni;
   // everything downstream of the relaxation; issued again after sort_drain() when the speculative rounds did not converge
   auto enqueue_tail = [&]() {
@@ -1355,12 +1379,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
       phase_end(h);
     }
     if (!p.want_wire) return;
-    if (wire_join) { cudaStreamWaitEvent(st, h->ev_side, 0); wire_join = false; }
-    if (ni) {
-      LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, d_wire, sc);
-      LAUNCH(h, k_io_max, grid_for(h, (const void*)k_io_max, kBlock, ni), kBlock, d_in, ni, p.node_bound, 0u, (const uint32_t*)nullptr, d_wire);
-    }
-    if (no) LAUNCH(h, k_io_set, grid_for(h, (const void*)k_io_set, kBlock, no), kBlock, d_out, no, p.node_bound, kOutPending, d_wire, sc);
+    if (wire_join) { cudaStreamWaitEvent(st, h->ev_side, 0); wire_join = false; }  // wire[] filled, I/O nodes tagged
     if (G) {
       phase_begin(h, "k_wire_first");
       LAUNCH(h, k_wire_first, grid_for(h, (const void*)k_wire_first, kBlock, ((uint64_t)G + kWireIlp - 1) / kWireIlp), kBlock, d_gates, d_order, G, d_wire, sc);
@@ -1484,6 +1503,7 @@ void c2a_destroy(c2a_handle* h) {
   if (h->cx_buf) cudaFree(h->cx_buf);
   if (h->fused_ctl) cudaFree(h->fused_ctl);
   if (h->plan_buf) cudaFree(h->plan_buf);
+  if (h->io_buf) cudaFree(h->io_buf);
   if (h->cx_pinned) cudaFreeHost(h->cx_pinned);
   emit_drop_host(h);
   if (h->h_pinned) cudaFreeHost(h->h_pinned);

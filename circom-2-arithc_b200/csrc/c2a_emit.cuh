@@ -940,6 +940,7 @@ struct EmitDefer {
   bool pending = false;
   uint32_t wire_cap = 0;  // capacity of the caller's device wire map (0: none) - caps the provisional node bound
   uint64_t n_sig = 0, C = 0;
+  uint32_t* es = nullptr;  // the emit's device status block (stays valid through the build: ES_IOBAD is the build's to use)
 };
 
 static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_emit_info* info, uint64_t* err_event, EmitDefer* defer = nullptr) {
@@ -1058,9 +1059,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       else LAUNCH(h, k_ev_count, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_count, kBlock, n)), kBlock, d_ev, n, tiles, tile_g, tile_c, es);
       phase_end(h);
       phase_begin(h, "k_scan_u32");
-      LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_g, tile_g, tiles, cnt_state, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
-      LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_c, tile_c, tiles, cnt_state + ctiles + 1, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
-      if (pk_impl) LAUNCH(h, k_scan_u32_t<false>, scan_tiles(tiles, kScanItems), kBlock, tile_i, tile_i, tiles, cnt_state_i, (uint32_t*)nullptr, (const uint32_t*)nullptr, 0);
+      ScanJobs jobs{{tile_g, tile_c, tile_i}, {cnt_state, cnt_state + ctiles + 1, cnt_state_i}};
+      LAUNCH(h, k_scan_u32_multi, dim3(scan_tiles(tiles, kScanItems), pk_impl ? 3 : 2), kBlock, jobs, tiles);
       phase_end(h);
       if (early) {
         // The host needs the totals only to size what FOLLOWS the scatter, and they exist once the count scans are done: the side
@@ -1247,8 +1247,16 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     if (G) LAUNCH(h, k_ev_gates, grid_for(h, (const void*)k_ev_gates, kBlock, G), kBlock, egates, (uint32_t)G, S, nos, d_gates, prod1, NB_ub);
     phase_end(h);
     uint32_t* dst = sync ? hp : h->h_emit_status;  // (deferred: a buffer of its own - the build re-stages, even re-allocates, hp)
-    cudaMemcpyAsync(dst, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(dst + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, s);
+    // deferred: the copies ride on the side stream (the build joins it in front of its wire kernels, so its final synchronisation
+    // covers them) - the main stream goes straight on to the build
+    cudaStream_t cs = s;
+    if (!sync) {
+      cudaEventRecord(h->ev_main, s);
+      cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
+      cs = h->stream2;
+    }
+    cudaMemcpyAsync(dst, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, cs);
+    cudaMemcpyAsync(dst + ES_COUNT, effp + effw, 4, cudaMemcpyDeviceToHost, cs);
     if (!sync) return true;
     if (!cuda_ok(h, cudaStreamSynchronize(s), "emit sync")) return false;
     return cuda_ok(h, cudaGetLastError(), "emit kernels");
@@ -1264,6 +1272,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     uint64_t nc_ub = n_sig + C;
     if (defer->wire_cap) nc_ub = std::min<uint64_t>(nc_ub, defer->wire_cap - 1);
     defer->pending = true;
+    defer->es = es;
     defer->n_sig = n_sig;
     defer->C = C;
     h->slab_used = keep;
@@ -1504,7 +1513,8 @@ int c2a_emitted_fetch(c2a_handle* h, c2a_gate* gates_out, uint32_t* node_of_sign
 // (c2a_plan_shards_device): no dependency edge leaves it, so its producer map is rebuilt for the range alone.
 static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint32_t n_in, const uint32_t* output_signals, uint32_t n_out,
                               uint32_t* order_out, uint32_t* wire_of_node, c2a_gate* new_gates, uint32_t* wire_count, uint64_t* err_index,
-                              bool outputs_on_device, uint64_t g_lo = 0, uint64_t g_hi = ~0ull, bool keep_phases = false) {
+                              bool outputs_on_device, uint64_t g_lo = 0, uint64_t g_hi = ~0ull, bool keep_phases = false,
+                              const uint32_t* d_io_sigs_ready = nullptr /* the two lists, already on the device */, uint32_t* es_ready = nullptr /* a zeroed status block */) {
   if (!h) return C2A_ERR_INVALID_ARGUMENT;
   if (!h->emitted.valid) return fail(h, C2A_ERR_INVALID_ARGUMENT, "no emitted circuit is resident on this handle");
   const bool whole = g_lo == 0 && (g_hi == ~0ull || g_hi == h->emitted.G);
@@ -1524,7 +1534,7 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   const uint32_t* nos = (const uint32_t*)(h->slab + h->emitted.nos_off);
   uint32_t* io_sigs = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
   uint32_t* io_nodes = (uint32_t*)slab_alloc(h, 4 * n_pairs + 4);
-  uint32_t* es = (uint32_t*)slab_alloc(h, 4 * ES_COUNT);
+  uint32_t* es = es_ready ? es_ready : (uint32_t*)slab_alloc(h, 4 * ES_COUNT);
   uint4* d_new = outputs_on_device ? (uint4*)new_gates : (new_gates ? (uint4*)slab_alloc(h, 16 * G) : nullptr);
   uint32_t* d_order = outputs_on_device ? order_out : (order_out ? (uint32_t*)slab_alloc(h, 4 * G) : nullptr);
   uint32_t* d_wire = outputs_on_device && wire_of_node ? wire_of_node : (uint32_t*)slab_alloc(h, 4 * (size_t)node_bound);
@@ -1538,10 +1548,13 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   if (n_pairs) {
     uint32_t* stage = h->h_pinned + 256;
     if (h->emitted.nos_valid) {
-      if (n_in) memcpy(stage, input_signals, 4 * (size_t)n_in);
-      if (n_out) memcpy(stage + n_in, output_signals, 4 * (size_t)n_out);
-      cudaMemcpyAsync(io_sigs, stage, 4 * n_pairs, cudaMemcpyHostToDevice, s);
-      cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
+      if (d_io_sigs_ready) io_sigs = const_cast<uint32_t*>(d_io_sigs_ready);
+      else {
+        if (n_in) memcpy(stage, input_signals, 4 * (size_t)n_in);
+        if (n_out) memcpy(stage + n_in, output_signals, 4 * (size_t)n_out);
+        cudaMemcpyAsync(io_sigs, stage, 4 * n_pairs, cudaMemcpyHostToDevice, s);
+      }
+      if (!es_ready) cudaMemsetAsync(es, 0, 4 * ES_COUNT, s);
       LAUNCH(h, k_ev_map_io, grid_for(h, (const void*)k_ev_map_io, kBlock, n_pairs), kBlock, io_sigs, (uint32_t)n_pairs, h->emitted.signal_bound, nos, io_nodes, es);
       io_flag = es + ES_IOBAD;  // read together with the build's final status: an unmapped signal yields node 0, which is harmless until then
     } else {  // sparse ids: map through the host emitter that produced the circuit

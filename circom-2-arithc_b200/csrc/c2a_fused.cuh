@@ -749,6 +749,30 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     src.pk_on_device = pk_on_device;
     EmitDefer df;
     df.wire_cap = (out_on_device && io->wire_of_node) ? io->wire_cap : 0u;
+    // the I/O signal lists go up on the side stream before anything else (the emit's scatter joins that stream: they have landed
+    // long before the build maps them to nodes)
+    const uint64_t n_io_all = (uint64_t)io->n_in + io->n_out;
+    const uint32_t* d_io_sigs = nullptr;
+    if (defer_ok && n_io_all && n_io_all <= (1u << 24) && (pk->flags & C2A_PACKED_DENSE_IDS)) {
+      if ((4 * n_io_all + 2048) > h->h_pinned_bytes) {
+        cudaStreamSynchronize(h->stream);
+        if (h->h_pinned) cudaFreeHost(h->h_pinned);
+        h->h_pinned_bytes = 4 * n_io_all + 8192;
+        if (!cuda_ok(h, cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault), "cudaHostAlloc")) return C2A_ERR_CUDA;
+      }
+      if (4 * n_io_all + 16 > h->io_bytes) {
+        if (h->io_buf) { cudaStreamSynchronize(h->stream2); cudaFree(h->io_buf); h->io_buf = nullptr; h->io_bytes = 0; }
+        if (cudaMalloc(&h->io_buf, 4 * n_io_all + 4096) == cudaSuccess) h->io_bytes = 4 * n_io_all + 4096;
+        else cudaGetLastError();
+      }
+      if (h->io_buf) {
+        uint32_t* stage = h->h_pinned + 256;
+        if (io->n_in) memcpy(stage, io->input_signals, 4 * (size_t)io->n_in);
+        if (io->n_out) memcpy(stage + io->n_in, io->output_signals, 4 * (size_t)io->n_out);
+        cudaMemcpyAsync(h->io_buf, stage, 4 * n_io_all, cudaMemcpyHostToDevice, h->stream2);
+        d_io_sigs = (const uint32_t*)h->io_buf;
+      }
+    }
     h->phase_prefix = "emit:";
     int st = emit_events_impl(h, src, n, info, err_event, defer_ok ? &df : nullptr);
     h->phase_prefix.clear();
@@ -756,7 +780,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     if ((io->order_out || io->new_gates) && io->gates_cap < h->emitted.G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%llu)", (unsigned long long)io->gates_cap, (unsigned long long)h->emitted.G);
     if (!df.pending && io->wire_of_node && io->wire_cap < h->emitted.node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, h->emitted.node_count + 1);
     st = emitted_build_impl(h, io->input_signals, io->n_in, io->output_signals, io->n_out, io->order_out, io->wire_of_node, io->new_gates, wire_count, err_index, out_on_device,
-                            0, ~0ull, /*keep_phases=*/true);
+                            0, ~0ull, /*keep_phases=*/true, df.pending ? d_io_sigs : nullptr, df.pending ? df.es : nullptr);
     if (!df.pending) return st;
     // ---- the emit's own status, now that the stream has been synchronised
     const uint32_t* es = h->h_emit_status;

@@ -66,6 +66,8 @@ struct c2a_handle {
     bool identity = true;            // that build's DFS order was 0..G-1
   } emitted;
   // single-kernel path (c2a_fused.cuh): double-buffered control block (scalars, grid barrier, look-back slots)
+  char* io_buf = nullptr;    // c2a_compile_packed*: the I/O signal lists, uploaded on the side stream ahead of the emit (grow-only)
+  size_t io_bytes = 0;
   char* plan_buf = nullptr;  // c2a_plan_shards_device scratch (grow-only, outside the slab)
   size_t plan_bytes = 0;
   char* fused_ctl = nullptr;
