@@ -53,13 +53,16 @@ serialised: compare SHARES with the bench line, not absolutes.  DRAM MB = `dram_
 
 {table}
 Reading:
-* `k_pk_scatter_t<1>` (the dominant kernel; `<2>` is the all-flagged instantiation, which exits on this stream): 587 MB of DRAM
-  traffic for 578 MB algorithmic - no re-read waste; `smsp__issue_active` 75.5 %, DRAM 28 %: instruction-issue-bound (profiles/r02_ncu_scatter_formats.md).
-* streaming kernels (`k_ev_gates`, `k_gather`, `k_producer`, `k_deps_t`, `k_ev_finalize`, `k_wire_assign`): 57-77 % of DRAM peak (4.7-6.3 TB/s physical).
-* `k_ev_nid_edges` (2.25 TB/s, L2 hit 24 %) and `k_wire_first` (50 % warps active at 59 registers) stay latency-bound on random 32-byte sectors.
+* `k_pk_scatter_t<1>` (the dominant kernel; `<2>` is the all-flagged instantiation, which exits on this stream): 499 MB of DRAM
+  traffic for 542 MB algorithmic - no re-read waste; 151 M warp instructions, `smsp__issue_active` 67.5 %, DRAM 30 %, 64 registers / 4 CTAs per SM:
+  instruction-issue-bound (profiles/r02_ncu_scatter_formats.md).  Alone (here) 203 us; inside the step 225-236 us, because the side stream
+  fills 370 MB of union-find arrays at the same time (deliberately: a bandwidth-bound fill next to an issue-bound kernel).
+* `k_pk_count` 17 us (was 36 us: per-byte tests and POPC replaced by byte-parallel arithmetic); `k_scan_u32_multi`: the three tile-count scans in one 30-CTA launch.
+* streaming kernels (`k_ev_gates`, `k_gather`, `k_producer`, `k_deps_t`, `k_ev_finalize`, `k_wire_assign`): 49-76 % of DRAM peak (4.0-6.2 TB/s physical).
+* `k_ev_nid_edges` (2.7 TB/s, L2 hit 38 %) and `k_wire_first` (49 % warps active at 59 registers) stay latency-bound on random 32-byte sectors.
 * `k_relax_loop` / `k_tree_blocks` (cooperative, 592 CTAs): 11 us / 5 us on the headline stream (18 315 forward edges, no big block).
-* `k_fused_compile`: 148 CTAs x 1024 threads, 64 registers, 54 us for 115 920 gates - ~17 grid barriers; DRAM traffic 1.2 MB: the whole circuit lives in L2.
-* `k_kahn_walk_roots`: 884 us at 6 % DRAM: a 547-hop dependency chain per MiMC component (latency floor), see DESIGN.md.
+* `k_fused_compile`: 148 CTAs x 1024 threads, 64 registers, 53 us for 115 920 gates - ~17 grid barriers; DRAM traffic 1.2 MB: the whole circuit lives in L2.
+* `k_kahn_walk_roots`: 867 us at 6 % DRAM: a 547-hop dependency chain per MiMC component (latency floor), see DESIGN.md.
 
 ## Launch list of the bench command (shares)
 
