@@ -790,9 +790,10 @@ def main():
     dom_probe = {"name": None, "in_emit": False, "ms": 0.0}   # timed steps: one double read instead of parsing every phase
 
     from circom_2_arithc_b200._lib import CompileIO
-    use_compile = packed and world == 1   # one call (c2a_compile_packed*): the emit's final status is read with the build's
+    use_compile = packed   # one call (c2a_compile_packed*): the emit's final status is read with the build's
+    # N > 1: the rank's gates are gathered by reconcile() with the global offsets, not by the build
     io_res = CompileIO(in_ids.ctypes.data_as(vp), out_ids.ctypes.data_as(vp), len(in_ids), len(out_ids), vp(d_order.data_ptr()), vp(d_wire.data_ptr()),
-                       vp(d_new.data_ptr()), G, nb, 0)
+                       vp(d_new.data_ptr()) if world == 1 else None, G, nb, 0)
 
     def device_step(record=False):
         """emit + build with the event stream already resident in HBM; results stay in HBM"""
@@ -804,6 +805,8 @@ def main():
                 acc_phases("")     # (the emit's phases carry their "emit:" prefix already)
             elif dom_probe["name"]:
                 dom_probe["ms"] += lib.c2a_last_kernel_ms(h, dom_probe["full"])
+            if world > 1:
+                reconcile()
             return
         st = emit_resident()
         if st != 0 or info.path != 1:
@@ -909,7 +912,7 @@ def main():
                             vp(p_new.data_ptr()), G, nb, 0)
 
     def e2e_step(all_arrays):
-        if use_compile:
+        if use_compile and world == 1:   # (N > 1: emit, build, named wires and the rebase against the gathered counts are separate calls)
             st = lib.c2a_compile_packed(h, C.byref(pk_host), C.byref(io_host_all if all_arrays else io_host), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
             if st != 0 or info.path != 1:
                 raise RuntimeError(f"c2a_compile_packed -> {st} path {info.path}: {ctx.last_error()}")
