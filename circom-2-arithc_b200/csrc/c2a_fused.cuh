@@ -748,7 +748,7 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     src.pk = pk;
     src.pk_on_device = pk_on_device;
     EmitDefer df;
-    df.wire_cap = (out_on_device && io->wire_of_node) ? io->wire_cap : 0u;
+    df.wire_cap = io->wire_of_node ? io->wire_cap : 0u;  // host array or device array: nothing may be written behind wire_cap
     // the I/O signal lists go up on the side stream before anything else (the emit's scatter joins that stream: they have landed
     // long before the build maps them to nodes)
     const uint64_t n_io_all = (uint64_t)io->n_in + io->n_out;
@@ -798,7 +798,8 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     if (io->wire_of_node && io->wire_cap < node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, node_count + 1);
     return st;
   };
-  auto classic = [&]() -> int { return classic_run(true); };
+  // (a wire map without room for a single entry can only fail: the undeferred form reports it before anything is built)
+  auto classic = [&]() -> int { return classic_run(!(io->wire_of_node && io->wire_cap == 0)); };
   const bool dense = (pk->flags & C2A_PACKED_DENSE_IDS) != 0;
   const uint64_t n_io = (uint64_t)io->n_in + io->n_out;
   if (!dense || n == 0 || n > g_fused_max_events || nw > 3 * n || n_io > (1u << 24) || (n && !pk->kinds) || (nw && !pk->words)) return classic();

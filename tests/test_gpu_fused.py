@@ -313,3 +313,48 @@ def test_one_cta_and_full_grid_agree(ctx, c2a):
         c2a.lib.c2a_set_fused_limits(FUSED_MAX, 1024)
     for a, b in zip(res[0][1:], res[1][1:]):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_host_wire_map_of_exact_size_is_not_overrun(ctx, c2a, fused):
+    """c2a_compile_packed with a HOST wire_of_node of exactly node_count + 1 entries on a stream with redundant connections
+    (node_count < signals + connections): the call must not write behind the array.  (The multi-kernel path builds while the emit's
+    final node count is still in flight - its provisional bound is signals + connections - so the copy-out has to respect wire_cap.)"""
+    from circom_2_arithc_b200._lib import CompileIO, EmitInfo, PackedEvents
+    wl = c2a.workloads.mimc_chains(7, rounds=9, variant="late")
+    ev = np.ascontiguousarray(wl.events).astype(np.uint32)
+    conns = ev[(ev[:, 0] & 0xFF) == EV_C]
+    again = conns[::2].copy()                       # every other connection once more, operands swapped: already one node each
+    again[:, [1, 2]] = again[:, [2, 1]]
+    ev = np.ascontiguousarray(np.concatenate([ev, again]))
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    k, w, f = c2a.pack_events(ev)
+    c2a.lib.c2a_set_fused_limits(FUSED_MAX if fused else 0, 0)
+    try:
+        info0, r_order, r_wire, r_gates, r_wc = ctx.compile_packed(k, w, f, ins, outs)
+        nc, G = info0["node_count"], info0["n_gates"]
+        n_sig, n_conn = info0["n_signals"], info0["n_connections"]
+        assert nc < n_sig + n_conn, "the stream must hold redundant connections for this test to bite"
+        guard = 0xDEADBEEF
+        wire = np.full(nc + 1 + 4096, guard, dtype=np.uint32)
+        order = np.full(G + 64, guard, dtype=np.uint32)
+        ng = np.full((G + 64, 4), guard, dtype=np.uint32)
+        vp = C.c_void_p
+        pk = PackedEvents(k.ctypes.data_as(vp), w.ctypes.data_as(vp), k.shape[0], w.shape[0], f, 0)
+        io = CompileIO(ins.ctypes.data_as(vp), outs.ctypes.data_as(vp), len(ins), len(outs), order.ctypes.data_as(vp), wire.ctypes.data_as(vp),
+                       ng.ctypes.data_as(vp), G, nc + 1, 0)
+        info, wc, bad, err = EmitInfo(), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        st = c2a.lib.c2a_compile_packed(ctx.handle, C.byref(pk), C.byref(io), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
+        assert st == 0, ctx.last_error()
+        assert ("k_fused_compile" in ctx.phases()) == fused
+        assert (wire[nc + 1:] == guard).all(), "wire_of_node was written behind wire_cap"
+        assert (order[G:] == guard).all() and (ng[G:] == guard).all()
+        assert np.array_equal(wire[:nc + 1], r_wire[:nc + 1]) and np.array_equal(order[:G], r_order) and np.array_equal(ng[:G], r_gates) and wc.value == r_wc
+        # one entry short: the reference-facing error, nothing written behind the array either
+        wire[:] = guard
+        io2 = CompileIO(ins.ctypes.data_as(vp), outs.ctypes.data_as(vp), len(ins), len(outs), None, wire.ctypes.data_as(vp), None, 0, nc, 0)
+        st = c2a.lib.c2a_compile_packed(ctx.handle, C.byref(pk), C.byref(io2), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
+        assert st == c2a.Status.INVALID_ARGUMENT and "wire_cap" in ctx.last_error()
+        assert (wire[nc:] == guard).all()
+    finally:
+        c2a.lib.c2a_set_fused_limits(FUSED_MAX, 0)
