@@ -1190,8 +1190,9 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     if (S) LAUNCH(h, k_iota, grid_for(h, (const void*)k_iota, kBlock, S), kBlock, parent, S);
   }
   phase_end(h);
-  // prod1 is zeroed on the side stream next to the Boruvka / node-id kernels; k_ev_gates joins.  (The main stream is idle
-  // after the scatter sync, so the side stream needs no event from it.)
+  // prod1 is zeroed on the side stream next to the Boruvka / node-id kernels; k_ev_gates joins.  (Nothing on the main stream
+  // touches the slab at this point - it is idle after the scatter sync, or still running the scatter, which writes the staging
+  // block only - so the side stream needs no event from it.)
   cudaMemsetAsync(prod1, 0, 4 * (size_t)NB_ub, h->stream2);
   cudaEventRecord(h->ev_side, h->stream2);
   prod1_pending = true;

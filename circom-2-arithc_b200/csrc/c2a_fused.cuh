@@ -1,6 +1,6 @@
 // c2a_fused.cuh — emit + build of a SMALL circuit in ONE cooperative kernel (include/c2a.h: c2a_compile_packed*).
 //
-// Below ~1 M gates the multi-kernel pipeline (c2a_emit.cuh + c2a_device.cu: ~55 launches, 3 synchronisations) is bound by the
+// Below ~1 M gates the multi-kernel pipeline (c2a_emit.cuh + c2a_device.cu: ~35 launches and as many memsets / event operations) is bound by the
 // host's enqueue rate: 0.27 ms per circuit whether it has 1 413 gates (BASELINE config 2) or 150 K (config 4).  Here the same
 // phases run inside one persistent kernel, one CTA per SM (or fewer for tiny streams), separated by a grid barrier
 // (one RED + an acquire poll, ~1 us) instead of a kernel boundary; data-dependent loops (Boruvka rounds, relaxation rounds) iterate on
