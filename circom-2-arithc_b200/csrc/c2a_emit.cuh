@@ -1021,6 +1021,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       side_nidf = (uint32_t*)take(4 * S_side);
       side_eff = (uint32_t*)take(4 * effw_side);
       side_effp = (uint32_t*)take(4 * effw_side);
+      // (the side stream starts behind whatever an earlier call may have left running on the main stream - a call that returned an
+      //  error before its final synchronisation - since these fills reuse the staging block those kernels work on)
+      cudaEventRecord(h->ev_main, s);
+      cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
       cudaMemsetAsync(outmark, 0, std::min<uint64_t>(S_cap, n + 1), h->stream2);
       cudaEventRecord(h->ev_side2, h->stream2);
       cudaMemsetAsync(side_best, 0xFF, 4 * S_side, h->stream2);

@@ -766,6 +766,8 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
         else cudaGetLastError();
       }
       if (h->io_buf) {
+        cudaEventRecord(h->ev_main, h->stream);  // (behind anything an earlier, failed call left running: it may still read io_buf)
+        cudaStreamWaitEvent(h->stream2, h->ev_main, 0);
         uint32_t* stage = h->h_pinned + 256;
         if (io->n_in) memcpy(stage, io->input_signals, 4 * (size_t)io->n_in);
         if (io->n_out) memcpy(stage + io->n_in, io->output_signals, 4 * (size_t)io->n_out);
@@ -777,11 +779,20 @@ static int compile_packed_impl(c2a_handle* h, const c2a_packed_events* pk, bool 
     int st = emit_events_impl(h, src, n, info, err_event, defer_ok ? &df : nullptr);
     h->phase_prefix.clear();
     if (st != C2A_OK) return st;
-    if ((io->order_out || io->new_gates) && io->gates_cap < h->emitted.G) return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%llu)", (unsigned long long)io->gates_cap, (unsigned long long)h->emitted.G);
+    // a deferred emit has not synchronised: every way out of this function below does (the build's final synchronisation, or here)
+    auto quiesce = [&]() { if (df.pending) { cudaStreamSynchronize(h->stream2); cudaStreamSynchronize(h->stream); } };
+    if ((io->order_out || io->new_gates) && io->gates_cap < h->emitted.G) {
+      if (df.pending) {  // report it the undeferred way: *info complete, and a stream the reference rejects keeps its own error
+        quiesce();
+        slab_reset(h);
+        return classic_run(false);
+      }
+      return fail(h, C2A_ERR_INVALID_ARGUMENT, "gates_cap (%llu) < number of gates (%llu)", (unsigned long long)io->gates_cap, (unsigned long long)h->emitted.G); }
     if (!df.pending && io->wire_of_node && io->wire_cap < h->emitted.node_count + 1) return fail(h, C2A_ERR_INVALID_ARGUMENT, "wire_cap (%u) < node_count + 1 (%u)", io->wire_cap, h->emitted.node_count + 1);
     st = emitted_build_impl(h, io->input_signals, io->n_in, io->output_signals, io->n_out, io->order_out, io->wire_of_node, io->new_gates, wire_count, err_index, out_on_device,
                             0, ~0ull, /*keep_phases=*/true, df.pending ? d_io_sigs : nullptr, df.pending ? df.es : nullptr);
     if (!df.pending) return st;
+    if (st != C2A_OK) quiesce();  // (an error from before the build's own synchronisation: sizes, memory)
     // ---- the emit's own status, now that the stream has been synchronised
     const uint32_t* es = h->h_emit_status;
     uint32_t flags = es[ES_FLAGS];
