@@ -251,7 +251,15 @@ def test_streams_the_reference_rejects_fall_back_to_the_exact_replay(ctx, c2a, o
             assert f"event {ex.value.err_event}" == err.message
 
 
-def test_bad_io_signal_and_capacities(ctx, c2a):
+@pytest.fixture(params=[True, False], ids=["fused", "multi_kernel"])
+def either_path(request, c2a):
+    """run the test through the single-kernel path and through the multi-kernel one (deferred emit status)"""
+    c2a.lib.c2a_set_fused_limits(FUSED_MAX if request.param else 0, 0)
+    yield request.param
+    c2a.lib.c2a_set_fused_limits(FUSED_MAX, 0)
+
+
+def test_bad_io_signal_and_capacities(ctx, c2a, either_path):
     wl = c2a.workloads.mimc_chains(3, rounds=5, variant="late")
     k, w, f = c2a.pack_events(np.ascontiguousarray(wl.events))
     with pytest.raises(c2a.C2AError) as ex:
@@ -267,6 +275,9 @@ def test_bad_io_signal_and_capacities(ctx, c2a):
     info, wc, bad, err = EmitInfo(), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
     st = c2a.lib.c2a_compile_packed(ctx.handle, C.byref(pk), C.byref(io), C.byref(info), C.byref(wc), C.byref(bad), C.byref(err))
     assert st == c2a.Status.INVALID_ARGUMENT and "gates_cap" in ctx.last_error() and info.n_gates == wl.n_gates
+    # the handle is idle and usable right away: the same stream with enough room
+    _i, order, _w, gates, _wc = ctx.compile_packed(k, w, f, ins, outs)
+    assert ("k_fused_compile" in ctx.phases()) == either_path and len(order) == wl.n_gates and gates.shape == (wl.n_gates, 4)
 
 
 @pytest.mark.parametrize("exact_caps", [True, False])
