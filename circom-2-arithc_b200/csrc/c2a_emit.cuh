@@ -242,8 +242,12 @@ constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words p
 // back; each looks at the scanned totals and exits at once unless the stream is its kind:
 // kMode 2: every gate and connection is flagged (what the walker emits) - the third rank is the sum of the other two, a gate has 2
 //          payload words and a connection 1, nothing per event has to be tested;  kMode 1: flagged and unflagged events mixed.
+// kPkBlock threads per 1 024-event tile: 8 events per lane - the per-tile fixed cost (barrier wait, tile header, cross-warp prefix) is a
+// quarter of the instructions of this issue-bound kernel, and it is per WARP
+constexpr int kPkBlock = 128, kPkPerLane = kEvTile / kPkBlock, kPkCtasPerSm = 6;  // (32 KB of shared memory per CTA: 6 fit)
+static_assert(kPkPerLane * kPkBlock == kEvTile && kPkBlock / 32 <= 8, "tile / block shape");
 template <int kMode>
-__global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
+__global__ void __launch_bounds__(kPkBlock, kPkCtasPerSm) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, const uint32_t* __restrict__ tile_i /* null: no implicit operands */,
                                                        uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
   __shared__ __align__(16) uint8_t s_k[2][kEvTile];
   __shared__ __align__(8) unsigned long long s_bar[2];
   __shared__ uint32_t s_meta[2][10];  // g0, c0, s0, first payload word - aligned start, words staged, kind bytes staged, #gates, #connections, i0, #implicit
-  __shared__ uint2 s_cnt[8];  // per warp: {gates | connections << 16, implicit-operand events} of its 128 events
+  __shared__ uint2 s_cnt[kPkBlock / 32];  // per warp: {gates | connections << 16, implicit-operand events} of its 32 * kPkPerLane events
   __shared__ uint32_t s_list[kEvTile];  // the tile's events filed by kind (phase A -> phase B)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt = (1u << lane) - 1u;
@@ -341,14 +345,14 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
     // is two thirds of the instructions of an instruction-issue-bound kernel.
     auto phase_a = [&](auto fast_tag) {
       constexpr bool kFast = decltype(fast_tag)::value;
-      const uint8_t* __restrict__ skl = &s_k[stage][warp * 128 + lane];
-      uint32_t kb[4], gm[4], cm[4], im[4];
+      const uint8_t* __restrict__ skl = &s_k[stage][warp * (32 * kPkPerLane) + lane];
+      uint32_t kb[kPkPerLane], gm[kPkPerLane], cm[kPkPerLane], im[kPkPerLane];
       uint32_t wg = 0, wc = 0, wi = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kPkPerLane; ++j) {
         if (kFast) kb[j] = skl[j * 32];
         else {
-          const uint32_t k = warp * 128 + j * 32 + lane;
+          const uint32_t k = warp * (32 * kPkPerLane) + j * 32 + lane;
           kb[j] = k < nev ? (k < kcov ? (uint32_t)s_k[stage][k] : (uint32_t)__ldg(kinds + tbase + k)) : 0x100u;  // 0x100: past the end
         }
         const bool live = kFast || kb[j] < 0x100u;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
       // in-tile ranks of the warp's first event: sum over the warps before it - lanes 0..7 hold one warp's counts each
       uint32_t dg, dc, di;
       {
-        uint2 v = (lane < 8 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
+        uint2 v = (lane < kPkBlock / 32 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
 #pragma unroll
         for (int o = 4; o; o >>= 1) { v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o); if (mixed) v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o); }
         v.x = __shfl_sync(0xFFFFFFFFu, v.x, 0);
@@ -376,8 +380,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
       //  signal, no per-event reductions)
       if (dense && threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t k = warp * 128 + j * 32 + lane;
+      for (int j = 0; j < kPkPerLane; ++j) {
+        const uint32_t k = warp * (32 * kPkPerLane) + j * 32 + lane;
         const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt), my_di = di + __popc(im[j] & lt);
         dg += __popc(gm[j]);
         dc += __popc(cm[j]);
@@ -402,12 +406,12 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
     // about half the instructions of phase A + phase B in a kernel that is bound by instruction issue.  Lanes that hold the same
     // kind write consecutive records, so the stores still fill whole sectors.
     auto phase_direct = [&]() {
-      const uint8_t* __restrict__ skl = &s_k[stage][warp * 128 + lane];
+      const uint8_t* __restrict__ skl = &s_k[stage][warp * (32 * kPkPerLane) + lane];
       const uint32_t* __restrict__ sw = &s_w[stage][woff];
-      uint32_t kb[4], gm[4], cm[4], im[4];
+      uint32_t kb[kPkPerLane], gm[kPkPerLane], cm[kPkPerLane], im[kPkPerLane];
       uint32_t wg = 0, wc = 0, wi = 0;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < kPkPerLane; ++j) {
         kb[j] = skl[j * 32];
         gm[j] = __ballot_sync(0xFFFFFFFFu, (kb[j] & 3u) == C2A_EV_GATE);
         cm[j] = __ballot_sync(0xFFFFFFFFu, (kb[j] & 3u) == C2A_EV_CONNECT);
@@ -420,7 +424,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
       __syncthreads();
       uint32_t dg, dc, di;
       {
-        uint2 v = (lane < 8 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
+        uint2 v = (lane < kPkBlock / 32 && lane < warp) ? s_cnt[lane] : make_uint2(0u, 0u);
 #pragma unroll
         for (int o = 4; o; o >>= 1) { v.x += __shfl_xor_sync(0xFFFFFFFFu, v.x, o); if (mixed) v.y += __shfl_xor_sync(0xFFFFFFFFu, v.y, o); }
         v.x = __shfl_sync(0xFFFFFFFFu, v.x, 0);
@@ -430,8 +434,8 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
       }
       if (threadIdx.x == 0 && nev > ng + nc) smax = max(smax, s0 + (nev - ng - nc));  // 1 + largest id declared in this tile
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const uint32_t k = warp * 128 + j * 32 + lane;
+      for (int j = 0; j < kPkPerLane; ++j) {
+        const uint32_t k = warp * (32 * kPkPerLane) + j * 32 + lane;
         const uint32_t my_dg = dg + __popc(gm[j] & lt), my_dc = dc + __popc(cm[j] & lt);
         const uint32_t my_di = all_impl ? my_dg + my_dc : (mixed ? di + __popc(im[j] & lt) : 0u);
         dg += __popc(gm[j]);
@@ -475,7 +479,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
       // Dense ids (id = declaration rank): "declared before use" (compiler.rs:183, :201 resolve an undeclared signal to node 0 /
       // panic) is the local test id < #signals declared before this event, so the E2 kernels, the event-time arrays and the
       // declaration table are not needed at all; out-of-range references are flagged and neutralised right here.
-      for (uint32_t r = threadIdx.x; r < ng; r += kBlock) {  // gate r of the tile
+      for (uint32_t r = threadIdx.x; r < ng; r += kPkBlock) {  // gate r of the tile
         uint32_t e = s_list[r], k = e & 1023u, my_dc = (e >> 10) & 1023u, my_di = all_impl ? r + my_dc : e >> 20;
         uint32_t ds = k - r - my_dc;
         uint32_t wl = 3u * r + 2u * my_dc - my_di + (dense ? 0u : ds);
@@ -489,7 +493,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
         } else gate_t[g0 + r] = (uint32_t)tbase + k;
         egates[g0 + r] = gt;
       }
-      for (uint32_t r = threadIdx.x; r < nc; r += kBlock) {  // connection r of the tile
+      for (uint32_t r = threadIdx.x; r < nc; r += kPkBlock) {  // connection r of the tile
         uint32_t e = s_list[ng + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_di = all_impl ? my_dg + r : e >> 20;
         uint32_t ds = k - my_dg - r;
         uint32_t wl = 3u * my_dg + 2u * r - my_di + (dense ? 0u : ds);
@@ -502,7 +506,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_pk_scatter_t(const uint8_t* __res
         conn_sb[c0 + r] = s0 + ds;  // signals declared before the connection
       }
       const uint32_t ns = dense ? 0u : nev - min(nev, ng + nc);  // (dense: already stored in phase A)
-      for (uint32_t r = threadIdx.x; r < ns; r += kBlock) {  // signal r of the tile
+      for (uint32_t r = threadIdx.x; r < ns; r += kPkBlock) {  // signal r of the tile
         uint32_t e = s_list[ng + nc + r], k = e & 1023u, my_dg = (e >> 10) & 1023u, my_dc = k - my_dg - r;
         uint32_t sid = dense ? s0 + r : W(3u * my_dg + 2u * my_dc + r);
         if (sid == 0xFFFFFFFFu) f |= EF_SPARSE;
@@ -1083,11 +1087,11 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
       if (pk && pk_impl) {
-        LAUNCH(h, k_pk_scatter_t<2>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+        LAUNCH(h, k_pk_scatter_t<2>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
                egates, gate_t, conn, conn_t, conn_sb, outmark, es);
-        LAUNCH(h, k_pk_scatter_t<1>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+        LAUNCH(h, k_pk_scatter_t<1>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
                egates, gate_t, conn, conn_t, conn_sb, outmark, es);
-      } else if (pk) LAUNCH(h, k_pk_scatter_t<0>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<0>, kBlock, n)), kBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)nullptr, sig_t, sig_meta,
+      } else if (pk) LAUNCH(h, k_pk_scatter_t<0>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<0>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)nullptr, sig_t, sig_meta,
                      egates, gate_t, conn, conn_t, conn_sb, outmark, es);
       else LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_scatter, kBlock, n)), kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
