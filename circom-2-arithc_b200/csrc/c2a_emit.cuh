@@ -244,7 +244,7 @@ constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words p
 //          payload words and a connection 1, nothing per event has to be tested;  kMode 1: flagged and unflagged events mixed.
 // kPkBlock threads per 1 024-event tile: 8 events per lane - the per-tile fixed cost (barrier wait, tile header, cross-warp prefix) is a
 // quarter of the instructions of this issue-bound kernel, and it is per WARP
-constexpr int kPkBlock = 128, kPkPerLane = kEvTile / kPkBlock, kPkCtasPerSm = 6;  // (32 KB of shared memory per CTA: 6 fit)
+constexpr int kPkBlock = 128, kPkPerLane = kEvTile / kPkBlock, kPkCtasPerSm = 6;  // (7 CTAs per SM fit, at 72 registers: measured slower, 0.226 against 0.213 ms)
 static_assert(kPkPerLane * kPkBlock == kEvTile && kPkBlock / 32 <= 8, "tile / block shape");
 template <int kMode>
 __global__ void __launch_bounds__(kPkBlock, kPkCtasPerSm) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
