@@ -54,8 +54,8 @@ serialised: compare SHARES with the bench line, not absolutes.  DRAM MB = `dram_
 {table}
 Reading:
 * `k_pk_scatter_t<1>` (the dominant kernel; `<2>` is the all-flagged instantiation, which exits on this stream): 499 MB of DRAM
-  traffic for 542 MB algorithmic - no re-read waste; 151 M warp instructions, `smsp__issue_active` 67.5 %, DRAM 30 %, 64 registers / 4 CTAs per SM:
-  instruction-issue-bound (profiles/r02_ncu_scatter_formats.md).  Alone (here) 203 us; inside the step 225-236 us, because the side stream
+  traffic for 542 MB algorithmic - no re-read waste; 134.5 M warp instructions, `smsp__issue_active` 64 %, DRAM 31 %, 128-thread CTAs, 80 registers / 6 CTAs per SM:
+  instruction-issue-bound (profiles/r02_ncu_scatter_formats.md).  Alone (here) 194 us; inside the step 215-218 us, because the side stream
   fills 370 MB of union-find arrays at the same time (deliberately: a bandwidth-bound fill next to an issue-bound kernel).
 * `k_pk_count` 17 us (was 36 us: per-byte tests and POPC replaced by byte-parallel arithmetic); `k_scan_u32_multi`: the three tile-count scans in one 30-CTA launch.
 * streaming kernels (`k_ev_gates`, `k_gather`, `k_producer`, `k_deps_t`, `k_ev_finalize`, `k_wire_assign`): 49-76 % of DRAM peak (4.0-6.2 TB/s physical).
