@@ -746,30 +746,39 @@ __global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ h
     const uint32_t base = off[R], end = off[R + 1];
     if (trees_done && end - base >= kBigBlock && tree_sz[R] != kNotATree) continue;
     uint32_t emit = base, top = end;
-    // state: 0 unvisited, 1 entered (lh next), 2 (rh next), 3 (both examined, emit next), 4 visited
+    // state: 0 unvisited, 1 entered (lh next), 2 (rh next), 3 (both examined, emit next), 4 visited.
+    // The gate being visited lives in REGISTERS (v, its progress s, its dependency pair dd); the block's slice of order[] holds the
+    // emitted gates (growing up) and the stack of its ancestors (growing down).  A step is then one round trip for the probe of a
+    // dependency (r[], state[] and - speculatively - its own dependency pair, three independent loads) and two for a return to the
+    // parent, instead of five dependent loads per step and three steps per gate.
+    uint32_t v = R, s = 1;
+    uint2 dd = dep[R];
     state[R] = 1;
-    order[--top] = R;
-    while (top < end) {
-      uint32_t v = order[top];
-      uint8_t s = state[v];
+    while (true) {
       if (s <= 2) {
-        uint2 dd = dep[v];
-        uint32_t d = (s == 1) ? dd.x : dd.y;
-        state[v] = s + 1;
-        if (d != kNone && r[d] == R) {
-          uint8_t sd = state[d];
-          if (sd == 0) {
-            state[d] = 1;
-            order[--top] = d;
-          } else if (sd < 4) {  // visiting[d]  (topological_sort.rs:34-38)
-            atomicMin(reinterpret_cast<unsigned long long*>(scalars + S_ERR_LO), ((unsigned long long)R << 32) | d);
-            break;
-          }
+        const uint32_t d = (s == 1) ? dd.x : dd.y;
+        ++s;
+        if (d == kNone) continue;
+        const uint32_t rd = r[d];
+        const uint8_t sd = state[d];
+        const uint2 dn = dep[d];  // (used only when the walk descends into d)
+        if (rd != R) continue;    // emitted by an earlier root: visited
+        if (sd == 0) {            // descend: the current gate becomes an ancestor
+          state[v] = (uint8_t)s;
+          order[--top] = v;
+          v = d; s = 1; dd = dn;
+          state[d] = 1;
+        } else if (sd < 4) {      // visiting[d]  (topological_sort.rs:34-38)
+          atomicMin(reinterpret_cast<unsigned long long*>(scalars + S_ERR_LO), ((unsigned long long)R << 32) | d);
+          break;
         }
       } else {
-        ++top;
         order[emit++] = v;  // sorted.push(i)
         state[v] = 4;       // visited[i] = true
+        if (top == end) break;
+        v = order[top++];
+        s = state[v];
+        dd = dep[v];
       }
     }
   }
