@@ -288,14 +288,32 @@ __device__ __forceinline__ void sort_grid_bar(unsigned int* bar, unsigned int& e
 // The seeds probe with a short cap (a reversed chain makes EVERY seed walk to the cap); the rounds use a long one, so that a walk
 // inside a shuffled component (hundreds of hops) is not cut into several rounds - a round lasts as long as its longest walk.
 constexpr uint32_t kSeedHopCap = 64, kRoundHopCap = 2048;
+// The rh side of a lowered gate goes on a small per-thread stack and is walked by the same thread once the lh chain ends (the global
+// queue takes the overflow): a label then crosses a whole shuffled component in ONE round instead of one rh hop per round
+// (BASELINE config 5 shuffled: 101 rounds before).  The hop cap counts the whole walk; whatever is pending when it is reached is queued.
+constexpr int kRelaxStack = 8;
 __device__ __forceinline__ void relax_capped(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn, uint32_t* ncut,
                                              uint32_t cap) {
-  for (uint32_t hop = 0; cur != kNone; ++hop) {
-    if (hop == cap) { enqueue(cur, inq, q, qn); atomicAdd(ncut, 1u); return; }
+  uint32_t stk[kRelaxStack];
+  int sp = 0;
+  for (uint32_t hop = 0;; ++hop) {
+    if (cur == kNone) {
+      if (!sp) return;
+      cur = stk[--sp];
+    }
+    if (hop == cap) {
+      enqueue(cur, inq, q, qn);
+      while (sp) enqueue(stk[--sp], inq, q, qn);
+      atomicAdd(ncut, 1u);
+      return;
+    }
     uint2 d = __ldcg(dep + cur);
     uint32_t nxt = kNone;
     if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
-      if (val < atomicMin(r + d.y, val)) enqueue(d.y, inq, q, qn);
+      if (val < atomicMin(r + d.y, val)) {
+        if (sp < kRelaxStack) stk[sp++] = d.y;
+        else enqueue(d.y, inq, q, qn);
+      }
     }
     if (d.x != kNone && val < __ldcg(r + d.x)) {
       if (val < atomicMin(r + d.x, val)) nxt = d.x;
