@@ -5,7 +5,7 @@ root first, a tree block with a cycle behind it, and a big block that is a DAG (
 
 What makes them hard on a GPU: r[] (the DFS root that first reaches a gate) is a minimum over all transitive consumers - a label
 that has to travel down a 1 M-long dependency chain - and the post-order of a 1 M-gate block is one sequential walk.  The product
-path (csrc/c2a_device.cu) bounds every data-driven walk (k_relax_loop: rounds on device-resident queues, pointer jumping along the
+path (csrc/c2a_device.cu) bounds every data-driven walk (k_relax_loop: rounds on device-resident queues, a per-thread stack for the rh side, pointer jumping along the
 smallest-index consumer when the queues do not drain) and emits tree-shaped big blocks by pointer jumping (k_tree_blocks)."""
 import time
 
