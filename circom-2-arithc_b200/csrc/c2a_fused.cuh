@@ -206,14 +206,30 @@ __device__ __forceinline__ void fused_enqueue(uint32_t x, uint32_t* inq, uint32_
 // (walks are bounded like in k_relax_loop; a stream whose DAG turns out to be deep leaves the fused kernel - EF_DEEP - and goes
 //  through the multi-kernel path, which has the pointer-jumping stages)
 constexpr uint32_t EF_DEEP = 512;
+// (the rh side of a lowered gate goes on a per-thread stack, as in relax_capped of c2a_device.cu: fewer rounds, and a round costs
+//  three grid barriers here)
 __device__ __forceinline__ void fused_relax_from(uint32_t cur, uint32_t val, const uint2* dep, uint32_t* r, uint32_t* inq, uint32_t* q, uint32_t* qn,
                                                  uint32_t cap, uint32_t* ncut) {
-  for (uint32_t hop = 0; cur != kNone; ++hop) {
-    if (hop == cap) { fused_enqueue(cur, inq, q, qn); atomicAdd(ncut, 1u); return; }
+  uint32_t stk[kRelaxStack];
+  int sp = 0;
+  for (uint32_t hop = 0;; ++hop) {
+    if (cur == kNone) {
+      if (!sp) return;
+      cur = stk[--sp];
+    }
+    if (hop == cap) {
+      fused_enqueue(cur, inq, q, qn);
+      while (sp) fused_enqueue(stk[--sp], inq, q, qn);
+      atomicAdd(ncut, 1u);
+      return;
+    }
     uint2 d = ldg2(dep + cur);
     uint32_t nxt = kNone;
     if (d.y != kNone && d.y != d.x && val < __ldcg(r + d.y)) {
-      if (val < atomicMin(r + d.y, val)) fused_enqueue(d.y, inq, q, qn);
+      if (val < atomicMin(r + d.y, val)) {
+        if (sp < kRelaxStack) stk[sp++] = d.y;
+        else fused_enqueue(d.y, inq, q, qn);
+      }
     }
     if (d.x != kNone && val < __ldcg(r + d.x)) {
       if (val < atomicMin(r + d.x, val)) nxt = d.x;
