@@ -983,6 +983,8 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   bool copied = false;
   constexpr int kEarlyAt = 40;  // word offset of the early totals in h_emit_status (behind the final status block)
   const bool early = defer && pk_dense && h->h_emit_status;
+  bool scatter_in_flight = false;  // early totals were used: the scatter (which may read the CALLER's device arrays) is still running
+  auto settle = [&]() { if (scatter_in_flight) { cudaStreamSynchronize(s); scatter_in_flight = false; } };  // before any error return
   for (int attempt = 0; attempt < 2; ++attempt) {
     const size_t pk_kbytes = pk ? align256(n + 4) : 0;  // packed staging: kinds, then words
     const size_t ev_copy = pk ? (src.pk_on_device ? 0 : pk_kbytes + align256(4 * pk->n_words + 4)) : (ev_dev ? 0 : align256(16 * n));
@@ -1109,7 +1111,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       n_impl = pk_impl ? e[2] : 0;
       // anything irregular goes the ordinary way: wait for the scatter and look at the whole status block
       have_counts = e[3] == 0 && G + C <= n && pk->n_words == 3 * G + 2 * C - n_impl;
-      if (have_counts) { n_sig = n - G - C; S = (uint32_t)n_sig; flags = 0; }  // dense ids: the table bound is the number of declarations
+      if (have_counts) { n_sig = n - G - C; S = (uint32_t)n_sig; flags = 0; scatter_in_flight = true; }  // dense ids: the table bound is the number of declarations
     }
     if (!have_counts) {
       cudaMemcpyAsync(hp, es, 4 * ES_COUNT, cudaMemcpyDeviceToHost, s);
@@ -1172,11 +1174,11 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   size_t build_need = core_scratch_bytes(bp, 1u << 20) + align256(16 * G) + align256(4 * G) + align256(4 * (size_t)NB_ub);
   slab_reset(h);
   emit_drop_host(h);
-  if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(G, C, S), build_need))) return C2A_ERR_NO_MEMORY;
+  if (!slab_reserve(h, resident + std::max(emit_scratch_bytes(G, C, S), build_need))) { settle(); return C2A_ERR_NO_MEMORY; }
   uint4* d_gates = (uint4*)slab_alloc(h, 16 * G);
   uint32_t* nos = (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* prod1 = (uint32_t*)slab_alloc(h, 4 * (size_t)NB_ub);  // producer map of the build (K1), filled by k_ev_gates
-  if (!prod1) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  if (!prod1) { settle(); return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted"); }
   const size_t keep = h->slab_used;
   const uint32_t effw = (uint32_t)(C / 32 + 1);  // bitmap words; one spare bit at least, so rank(C) = total is addressable
   uint32_t* parent = pk_dense ? side_parent : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
@@ -1184,10 +1186,10 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   uint32_t* nidf = pk_dense ? side_nidf : (uint32_t*)slab_alloc(h, 4 * (size_t)S);
   uint32_t* eff = pk_dense ? side_eff : (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
   uint32_t* effp = pk_dense ? side_effp : (uint32_t*)slab_alloc(h, 4 * ((size_t)effw + 3));
-  if (!parent || !best || !nidf || !eff || !effp) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  if (!parent || !best || !nidf || !eff || !effp) { settle(); return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted"); }
   uint32_t* cur = (uint32_t*)slab_alloc(h, 4 * C);
   uint4* cand = (uint4*)slab_alloc(h, 16 * C);
-  if (!cand) return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted");
+  if (!cand) { settle(); return fail(h, C2A_ERR_NO_MEMORY, "scratch slab exhausted"); }
   unsigned long long* tile_state = nid_state;  // in the staging block: zeroed by the first memset of the call
 
   phase_begin(h, "init");
