@@ -369,3 +369,32 @@ def test_host_wire_map_of_exact_size_is_not_overrun(ctx, c2a, fused):
         assert (wire[nc:] == guard).all()
     finally:
         c2a.lib.c2a_set_fused_limits(FUSED_MAX, 0)
+
+
+def test_irregular_packed_streams_through_both_compile_paths(ctx, c2a, either_path):
+    """a gate type out of range, a word count that does not match the kinds, the implicit-operand flag on a declaration: the count pass
+    sees them before the scatter has finished - the multi-kernel compile (which sizes its later launches from totals copied out while the
+    scatter runs) has to fall back to the ordinary synchronised status and report what c2a_emit_packed_device reports"""
+    wl = c2a.workloads.mimc_chains(40, rounds=30, variant="late")
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    for implicit in (False, True):
+        k, w, f = c2a.pack_events(np.ascontiguousarray(wl.events), implicit=implicit)
+        good = ctx.compile_packed(k, w, f, ins, outs)
+        gi = np.flatnonzero((k & 3) == 2)
+        cases = []
+        bad = k.copy(); bad[gi[len(gi) // 2]] = (bad[gi[len(gi) // 2]] & 0x83) | (25 << 2); cases.append((bad, w))   # gate type 25
+        cases.append((k, w[:-1])); cases.append((k, np.concatenate([w, w[:2]])))                                    # word count off
+        if implicit:
+            si = np.flatnonzero((k & 3) == 0)
+            bad = k.copy(); bad[si[7]] |= 0x80; cases.append((bad, w))                                              # flag on a declaration
+        for kk, ww in cases:
+            errs = []
+            for call in (lambda: ctx.emit_packed(kk, ww, f), lambda: ctx.compile_packed(kk, ww, f, ins, outs)):
+                with pytest.raises((c2a.C2AError, c2a.CircuitError)) as ex:
+                    call()
+                errs.append((int(ex.value.status), str(ex.value)))
+            assert errs[0] == errs[1], errs
+        again = ctx.compile_packed(k, w, f, ins, outs)      # and the handle is fine afterwards
+        assert ("k_fused_compile" in ctx.phases()) == either_path
+        for a, b in zip(good[1:4], again[1:4]):
+            assert np.array_equal(a, b)
