@@ -769,35 +769,51 @@ __global__ void __launch_bounds__(128) k_tree_dfs(const uint32_t* __restrict__ h
     // emitted gates (growing up) and the stack of its ancestors (growing down).  A step is then one round trip for the probe of a
     // dependency (r[], state[] and - speculatively - its own dependency pair, three independent loads) and two for a return to the
     // parent, instead of five dependent loads per step and three steps per gate.
-    uint32_t v = R, s = 1;
+    uint32_t v = R, s = 1, pv = kNone;
     uint2 dd = dep[R];
     state[R] = 1;
+    bool popping = false;  // the parent's index has been read from the stack, its state / dependency pair are still to be fetched
+    // The 32 lanes of a warp walk 32 different blocks and are rarely in the same kind of step.  Every iteration therefore has ONE place
+    // where loads are issued - a dependency probe, the stack read of a return, or the parent's record - and the results are consumed
+    // afterwards: the lanes' round trips overlap instead of following one another branch by branch (that serialisation was ~2/3 of
+    // this kernel's time on the shuffled BASELINE vector).
     while (true) {
-      if (s <= 2) {
-        const uint32_t d = (s == 1) ? dd.x : dd.y;
-        ++s;
-        if (d == kNone) continue;
-        const uint32_t rd = r[d];
-        const uint8_t sd = state[d];
-        const uint2 dn = dep[d];  // (used only when the walk descends into d)
-        if (rd != R) continue;    // emitted by an earlier root: visited
-        if (sd == 0) {            // descend: the current gate becomes an ancestor
+      uint32_t d = kNone;
+      bool want_probe = false, want_pop1 = false;
+      const bool want_pop2 = popping;
+      if (!popping) {
+        if (s <= 2) {
+          d = (s == 1) ? dd.x : dd.y;
+          ++s;
+          want_probe = d != kNone;
+        } else {
+          order[emit++] = v;  // sorted.push(i)
+          state[v] = 4;       // visited[i] = true
+          if (top == end) break;
+          want_pop1 = true;
+        }
+      }
+      // ---- issue
+      uint32_t rd = 0, nv = 0;
+      uint8_t sd = 0, ps = 0;
+      uint2 dn = make_uint2(kNone, kNone), pdd = make_uint2(kNone, kNone);
+      if (want_probe) { rd = r[d]; sd = state[d]; dn = dep[d]; }  // (dn is used only when the walk descends into d)
+      if (want_pop1) nv = order[top];
+      if (want_pop2) { ps = state[pv]; pdd = dep[pv]; }
+      // ---- consume
+      if (want_probe && rd == R) {  // (rd != R: emitted by an earlier root - visited)
+        if (sd == 0) {              // descend: the current gate becomes an ancestor
           state[v] = (uint8_t)s;
           order[--top] = v;
           v = d; s = 1; dd = dn;
           state[d] = 1;
-        } else if (sd < 4) {      // visiting[d]  (topological_sort.rs:34-38)
+        } else if (sd < 4) {        // visiting[d]  (topological_sort.rs:34-38)
           atomicMin(reinterpret_cast<unsigned long long*>(scalars + S_ERR_LO), ((unsigned long long)R << 32) | d);
           break;
         }
-      } else {
-        order[emit++] = v;  // sorted.push(i)
-        state[v] = 4;       // visited[i] = true
-        if (top == end) break;
-        v = order[top++];
-        s = state[v];
-        dd = dep[v];
       }
+      if (want_pop1) { pv = nv; ++top; popping = true; }
+      else if (want_pop2) { v = pv; s = ps; dd = pdd; popping = false; }
     }
   }
 }
