@@ -1522,6 +1522,10 @@ int c2a_create(int device, c2a_handle** out) {
     delete h;
     return C2A_ERR_CUDA;
   }
+  if (cudaStreamCreateWithFlags(&h->stream3, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
+    cudaGetLastError();  // (optional: without it the payload words are copied on the main stream)
+    if (h->stream3) { cudaStreamDestroy(h->stream3); h->stream3 = nullptr; }
+  }
   h->h_pinned_bytes = 1 << 16;
   if (cudaHostAlloc((void**)&h->h_emit_status, 256, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); h->h_emit_status = nullptr; }
   if (cudaHostAlloc((void**)&h->h_pinned, h->h_pinned_bytes, cudaHostAllocDefault) != cudaSuccess) {
@@ -1555,6 +1559,8 @@ void c2a_destroy(c2a_handle* h) {
   if (h->h_pinned) cudaFreeHost(h->h_pinned);
   if (h->h_emit_status) cudaFreeHost(h->h_emit_status);
   cudaStreamSynchronize(h->stream2);
+  if (h->stream3) { cudaStreamSynchronize(h->stream3); cudaStreamDestroy(h->stream3); }
+  if (h->ev_copy) cudaEventDestroy(h->ev_copy);
   cudaEventDestroy(h->ev_side);
   cudaEventDestroy(h->ev_side2);
   cudaEventDestroy(h->ev_counts);

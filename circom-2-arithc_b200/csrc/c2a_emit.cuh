@@ -246,14 +246,14 @@ constexpr int kPkWordsCap = 3 * kEvTile + 8;  // payload of a tile (<= 3 words p
 // quarter of the instructions of this issue-bound kernel, and it is per WARP
 constexpr int kPkBlock = 128, kPkPerLane = kEvTile / kPkBlock, kPkCtasPerSm = 6;  // (7 CTAs per SM fit, at 72 registers: measured slower, 0.226 against 0.213 ms)
 static_assert(kPkPerLane * kPkBlock == kEvTile && kPkBlock / 32 <= 8, "tile / block shape");
-template <int kMode>
+template <int kMode, bool kPoll = false>  // kPoll: the payload words are still arriving (`arrived` = the running count): wait per tile
 __global__ void __launch_bounds__(kPkBlock, kPkCtasPerSm) k_pk_scatter_t(const uint8_t* __restrict__ kinds, const uint32_t* __restrict__ words, uint64_t n, uint64_t n_words,
                                                        uint32_t dense, uint32_t tiles, uint32_t S_cap, const uint32_t* __restrict__ tile_g,
                                                        const uint32_t* __restrict__ tile_c, const uint32_t* __restrict__ tile_i /* null: no implicit operands */,
                                                        uint32_t* __restrict__ sig_t, uint2* __restrict__ sig_meta,
                                                        uint4* __restrict__ egates, uint32_t* __restrict__ gate_t, uint2* __restrict__ conn,
                                                        uint32_t* __restrict__ conn_t, uint32_t* __restrict__ conn_sb, uint8_t* __restrict__ outmark,
-                                                       uint32_t* __restrict__ es) {
+                                                       uint32_t* __restrict__ es, const uint32_t* arrived /* null, or: payload words copied in so far */) {
   __shared__ __align__(16) uint32_t s_w[2][kPkWordsCap];
   __shared__ __align__(16) uint8_t s_k[2][kEvTile];
   __shared__ __align__(8) unsigned long long s_bar[2];
@@ -291,6 +291,19 @@ __global__ void __launch_bounds__(kPkBlock, kPkCtasPerSm) k_pk_scatter_t(const u
     s_meta[stage][3] = (uint32_t)(w0 - a0); s_meta[stage][4] = (uint32_t)(a1 - a0); s_meta[stage][5] = kbytes;
     s_meta[stage][6] = min(cnt.z - cnt.x, (uint32_t)kEvTile); s_meta[stage][7] = min(cnt.w - cnt.y, (uint32_t)kEvTile);
     s_meta[stage][8] = ci.x; s_meta[stage][9] = min(ci.y - ci.x, (uint32_t)kEvTile);
+    if (kPoll) {
+      // the payload is still on its way over PCIe (chunked copy on a stream of its own, each chunk followed by a copy of the running
+      // word count): wait until this tile's range has landed.  The copy engine does not depend on this kernel, so the wait ends.
+      const uint32_t need = (uint32_t)min(n_words, max(a1, w1));
+      uint32_t have, spins = 0;
+      while (true) {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(have) : "l"(arrived) : "memory");
+        if (have >= need) break;
+        if (++spins > (1u << 23)) __trap();  // ~8 s: the copy died - fail loudly, do not hang
+        __nanosleep(1000);
+      }
+      asm volatile("fence.proxy.async;" ::: "memory");  // the bulk copies below read what the acquire made visible
+    }
     uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar[stage]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the stage was last read through the generic proxy
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + kbytes) : "memory");
@@ -983,6 +996,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
   bool copied = false;
   constexpr int kEarlyAt = 40;  // word offset of the early totals in h_emit_status (behind the final status block)
   const bool early = defer && pk_dense && h->h_emit_status;
+  bool chunked = false;            // the payload words arrive on the copy stream while the scatter already runs
   bool scatter_in_flight = false;  // early totals were used: the scatter (which may read the CALLER's device arrays) is still running
   auto settle = [&]() { if (scatter_in_flight) { cudaStreamSynchronize(s); scatter_in_flight = false; } };  // before any error return
   for (int attempt = 0; attempt < 2; ++attempt) {
@@ -996,7 +1010,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     const uint64_t effw_side = pk_dense ? pk->n_words / (pk_impl ? 32 : 64) + 4 : 0;
     const size_t side_bytes = pk_dense ? 3 * align256(4 * S_side) + 2 * align256(4 * effw_side) : 0;
     const size_t ev_need = side_bytes + ev_copy + 3 * align256(4 * ((size_t)tiles + 2)) + align256(8 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) + align256(16 * ((size_t)scan_tiles((uint64_t)tiles + 1, kScanItems) + 1)) +
-                           align256(8 * ((size_t)scan_tiles(n / 32 + 2, kScanItems) + 1)) + align256(4 * ES_COUNT) + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
+                           align256(8 * ((size_t)scan_tiles(n / 32 + 2, kScanItems) + 1)) + align256(4 * ES_COUNT) + 256 + align256(4 * S_cap) + align256(8 * S_cap) + align256(16 * n) + 3 * align256(4 * n) + align256(8 * n) + align256(S_cap);
     if (ev_need > h->ev_bytes) {
       if (h->ev_buf) { cudaStreamSynchronize(s); cudaFree(h->ev_buf); h->ev_buf = nullptr; h->ev_bytes = 0; }
       if (!cuda_ok(h, cudaMalloc(&h->ev_buf, ev_need + ev_need / 16), "cudaMalloc(event staging)")) { cudaGetLastError(); return C2A_ERR_NO_MEMORY; }
@@ -1013,6 +1027,7 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
     unsigned long long* cnt_state_i = (unsigned long long*)take(8 * ((size_t)ctiles + 1));  // ... and of the implicit-operand counts
     nid_state = (unsigned long long*)take(8 * ((size_t)scan_tiles(n / 32 + 2, kScanItems) + 1));  // ... and of the effective-connection bitmap scan (C <= n)
     es = (uint32_t*)take(4 * ES_COUNT);
+    uint32_t* d_arrived = (uint32_t*)take(256);  // (outside the block the first memset clears: it is written by the copy stream)
     sig_t = (uint32_t*)take(4 * S_cap);
     sig_meta = (uint2*)take(8 * S_cap);
     egates = (uint4*)take(16 * n);
@@ -1048,8 +1063,31 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       phase_begin(h, "h2d");
       if (pk) {
         if (n && !src.pk_on_device) {
+          // A big dense stream in the one-call form: the count pass needs the kind bytes only, so the payload words follow on a copy
+          // stream of their own, in chunks, each chunk followed by a 4-byte copy of the running word count - the scatter (whose tiles
+          // use ascending word ranges) starts as soon as the counts are scanned and consumes the payload while it is still arriving.
+          chunked = early && pk_impl && h->stream3 && pk->n_words >= (1u << 22) && pk->n_words < (1ull << 32);
+          if (chunked) cudaMemsetAsync(d_arrived, 0, 4, s);
           if (!cuda_ok(h, cudaMemcpyAsync(h->ev_buf, pk->kinds, n, cudaMemcpyHostToDevice, s), "kinds H2D")) return C2A_ERR_CUDA;
-          if (pk->n_words && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf + pk_kbytes, pk->words, 4 * pk->n_words, cudaMemcpyHostToDevice, s), "words H2D")) return C2A_ERR_CUDA;
+          if (chunked) {
+            cudaEventRecord(h->ev_main, s);
+            cudaStreamWaitEvent(h->stream3, h->ev_main, 0);  // PCIe carries the kind bytes first
+            uint32_t* cum = h->h_emit_status + 48;           // pinned: the running word counts, one per chunk
+            constexpr int kChunks = 4;  // (every chunk costs two copy operations: 12 chunks lost to their latency what the finer overlap won)
+            const uint64_t per = ((pk->n_words + kChunks - 1) / kChunks + 3) & ~3ull;
+            int ci = 0;
+            for (uint64_t off = 0; off < pk->n_words; off += per, ++ci) {
+              const uint64_t len = std::min<uint64_t>(per, pk->n_words - off);
+              cum[ci] = (uint32_t)(off + len);
+              if (!cuda_ok(h, cudaMemcpyAsync(h->ev_buf + pk_kbytes + 4 * off, pk->words + off, 4 * len, cudaMemcpyHostToDevice, h->stream3), "words H2D (chunk)") ||
+                  !cuda_ok(h, cudaMemcpyAsync(d_arrived, cum + ci, 4, cudaMemcpyHostToDevice, h->stream3), "words H2D (progress)")) {
+                cudaStreamSynchronize(h->stream3);
+                cudaStreamSynchronize(s);
+                return C2A_ERR_CUDA;
+              }
+            }
+            cudaEventRecord(h->ev_copy, h->stream3);
+          } else if (pk->n_words && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf + pk_kbytes, pk->words, 4 * pk->n_words, cudaMemcpyHostToDevice, s), "words H2D")) return C2A_ERR_CUDA;
         }
       } else if (n && !ev_dev && !cuda_ok(h, cudaMemcpyAsync(h->ev_buf, ev, 16 * n, cudaMemcpyHostToDevice, s), "events H2D")) return C2A_ERR_CUDA;
       phase_end(h);
@@ -1089,14 +1127,19 @@ static int emit_events_impl(c2a_handle* h, const EmitSrc& src, uint64_t n, c2a_e
       phase_begin(h, "k_ev_scatter");
       // persistent CTAs: exactly one resident wave (a partial second wave would run on a fraction of the SMs)
       if (pk && pk_impl) {
-        LAUNCH(h, k_pk_scatter_t<2>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
-               egates, gate_t, conn, conn_t, conn_sb, outmark, es);
-        LAUNCH(h, k_pk_scatter_t<1>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
-               egates, gate_t, conn, conn_t, conn_sb, outmark, es);
+        if (chunked) LAUNCH(h, (k_pk_scatter_t<2, true>), std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2, true>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es, (const uint32_t*)d_arrived);
+        else LAUNCH(h, k_pk_scatter_t<2>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<2>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es, (const uint32_t*)nullptr);
+        if (chunked) LAUNCH(h, (k_pk_scatter_t<1, true>), std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1, true>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es, (const uint32_t*)d_arrived);
+        else LAUNCH(h, k_pk_scatter_t<1>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<1>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, 1u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)tile_i, sig_t, sig_meta,
+               egates, gate_t, conn, conn_t, conn_sb, outmark, es, (const uint32_t*)nullptr);
       } else if (pk) LAUNCH(h, k_pk_scatter_t<0>, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_pk_scatter_t<0>, kPkBlock, n)), kPkBlock, d_kinds, d_words, n, pk->n_words, pk_dense ? 1u : 0u, tiles, (uint32_t)S_cap, tile_g, tile_c, (const uint32_t*)nullptr, sig_t, sig_meta,
-                     egates, gate_t, conn, conn_t, conn_sb, outmark, es);
+                     egates, gate_t, conn, conn_t, conn_sb, outmark, es, (const uint32_t*)nullptr);
       else LAUNCH(h, k_ev_scatter, std::min<uint32_t>(tiles, (uint32_t)grid_for(h, (const void*)k_ev_scatter, kBlock, n)), kBlock, d_ev, n, tiles, (uint32_t)S_cap, tile_g, tile_c, sig_t, sig_meta, egates, gate_t, conn, conn_t, conn_sb, es);
       phase_end(h);
+      if (chunked) cudaStreamWaitEvent(s, h->ev_copy, 0);  // (the main stream is ordered behind the copy stream again)
       cudaMemcpyAsync(es + ES_NGATE, tile_g + tiles, 4, cudaMemcpyDeviceToDevice, s);  // totals land behind the scanned arrays
       cudaMemcpyAsync(es + ES_NCONN, tile_c + tiles, 4, cudaMemcpyDeviceToDevice, s);
       if (pk_impl) cudaMemcpyAsync(es + ES_NIMPL, tile_i + tiles, 4, cudaMemcpyDeviceToDevice, s);

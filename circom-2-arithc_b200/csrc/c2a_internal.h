@@ -12,6 +12,8 @@ struct c2a_handle {
   int device = 0;
   int num_sms = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream3 = nullptr;  // copy stream: the payload words of a big packed stream, chunked, while the scatter already consumes them
+  cudaEvent_t ev_copy = nullptr;
   cudaStream_t stream2 = nullptr;  // side stream: initialisation of arrays that are only needed later runs next to the kernels before them
   cudaEvent_t ev_side = nullptr;
   cudaEvent_t ev_counts = nullptr;  // side stream: the emitter's early totals have reached the host

@@ -398,3 +398,40 @@ def test_irregular_packed_streams_through_both_compile_paths(ctx, c2a, either_pa
         assert ("k_fused_compile" in ctx.phases()) == either_path
         for a, b in zip(good[1:4], again[1:4]):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("implicit", [False, True])
+def test_big_host_stream_arrives_in_chunks(ctx, c2a, implicit):
+    """c2a_compile_packed on a host stream of > 4 Mi payload words: the words are copied on a stream of their own, in chunks, and the
+    scatter consumes them while they arrive (it polls the running word count) - same circuit as the two-call form, which copies the
+    whole stream first"""
+    wl = c2a.workloads.mimc_chains(3000, rounds=91, variant="late")     # 1.64 M gates, 6.9 M events: the multi-kernel path
+    ins, outs = np.array(sorted(wl.inputs), dtype=np.uint32), np.array(sorted(wl.outputs), dtype=np.uint32)
+    k, w, f = c2a.pack_events(np.ascontiguousarray(wl.events), implicit=implicit)
+    assert len(w) >= (1 << 22)
+    info2 = ctx.emit_packed(k, w, f)
+    gates2, nos2 = ctx.emitted_fetch()
+    order2, wire2, ng2, wc2 = ctx.emitted_build_circuit(ins, outs)
+    for _ in range(2):
+        info, order, wire, ng, wc = ctx.compile_packed(k, w, f, ins, outs)
+        assert "k_fused_compile" not in ctx.phases()
+        gates, nos = ctx.emitted_fetch()
+        strip = lambda d: {a: b for a, b in d.items() if a != "decline_flags"}
+        assert strip(info) == strip(info2) and wc == wc2
+        assert np.array_equal(gates, gates2) and np.array_equal(nos, nos2)
+        nb = info["node_count"] + 1
+        assert np.array_equal(order, order2) and np.array_equal(wire[:nb], wire2[:nb]) and np.array_equal(ng, ng2)
+    # a stream the device emitter declines (an operand far beyond every declared signal: the reference resolves it to node 0,
+    # src/compiler.rs:183), big enough for the chunked copy: the scatter's flag is read with the final status, the call falls back to
+    # the exact host replay - same outcome as the two-call form
+    wbad = w.copy()
+    wbad[len(w) // 2] = 0x7FFFFFF0
+    outcomes = []
+    for call in (lambda: ctx.emit_packed(k, wbad, f), lambda: ctx.compile_packed(k, wbad, f, ins, outs)[0]):
+        try:
+            i = call()
+            g_, n_ = ctx.emitted_fetch(want_nodes=False)
+            outcomes.append(("ok", i["path"], i["node_count"], int(g_.sum(dtype=np.uint64))))
+        except (c2a.C2AError, c2a.CircuitError) as e:
+            outcomes.append(("err", int(e.status), str(e)))
+    assert outcomes[0] == outcomes[1], outcomes
