@@ -1352,7 +1352,8 @@ static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pai
 static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, const uint32_t* in_nodes_host,
                       const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
                       uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr,
-                      const uint32_t* io_flags_dev = nullptr, const uint32_t* prod1_ready = nullptr) {
+                      const uint32_t* io_flags_dev = nullptr, const uint32_t* prod1_ready = nullptr,
+                      const std::function<void()>* before_status = nullptr /* enqueued behind the pipeline, in front of the status read: the caller's copy-out */) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
   size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
@@ -1458,6 +1459,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   };
 
   enqueue_tail();
+  if (before_status) (*before_status)();
   if (!read_status()) return C2A_ERR_CUDA;
   const uint32_t* hs = hp + 64;
   if (io_flags_dev && hs[S_COUNT]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");
