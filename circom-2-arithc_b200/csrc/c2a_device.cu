@@ -928,12 +928,14 @@ __global__ void __launch_bounds__(kBlock) k_wire_assign(uint32_t* __restrict__ w
 
 // K7: gather (compiler.rs:452-464).  op stays numeric; the host maps it to the strum Display token.
 constexpr int kGatherIlp = 2;
-__global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t G,
+// (sorted positions [base, base + cnt): the whole circuit, or one chunk of it when the copy-out of the previous chunk runs beside it)
+__global__ void __launch_bounds__(kBlock) k_gather(const uint4* __restrict__ gates, const uint32_t* __restrict__ order_arr, uint32_t base, uint32_t cnt,
                                                    const uint32_t* __restrict__ wire, uint4* __restrict__ new_gates, const uint32_t* __restrict__ sc) {
   if (tail_parked(sc)) return;
   const uint32_t* __restrict__ order = sort_wanted(sc) ? order_arr : nullptr;
   const uint32_t stride = gridDim.x * kBlock;
-  for (uint32_t k0 = blockIdx.x * kBlock + threadIdx.x; k0 < G; k0 += stride * kGatherIlp) {
+  const uint32_t G = base + cnt;
+  for (uint32_t k0 = base + blockIdx.x * kBlock + threadIdx.x; k0 < G; k0 += stride * kGatherIlp) {
     uint32_t g[kGatherIlp];
     uint4 gt[kGatherIlp];
 #pragma unroll
@@ -1334,6 +1336,13 @@ struct BuildPlan {
   bool want_wire;  // wire numbering + gather wanted (build_circuit) or order only (topo_sort)
 };
 
+// the caller's host arrays (one synchronisation per call): the renumbered gates are copied chunk by chunk on the copy stream while the
+// gather of the next chunk runs; `rest` enqueues the other copies on the main stream
+struct HostCopyOut {
+  uint4* new_gates_host;
+  std::function<void()> rest;
+};
+
 static size_t core_scratch_bytes(const BuildPlan& p, size_t n_pairs) {  // n_pairs = n_in + n_out
   size_t b = 0;
   b += align256(4 * (size_t)p.node_bound);  // prod1
@@ -1353,7 +1362,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
                       const uint32_t* out_nodes_host, uint32_t* d_order_user, uint32_t* d_wire, uint4* d_new_gates,
                       uint32_t* wire_count, uint64_t* err_index, bool* identity_out, const uint32_t* d_io_ready = nullptr,
                       const uint32_t* io_flags_dev = nullptr, const uint32_t* prod1_ready = nullptr,
-                      const std::function<void()>* before_status = nullptr /* enqueued behind the pipeline, in front of the status read: the caller's copy-out */) {
+                      const HostCopyOut* out = nullptr /* host arrays: copied out behind the pipeline, in front of the status read */) {
   cudaStream_t st = h->stream;
   const uint32_t G = (uint32_t)p.G;
   size_t n_pairs = p.want_wire ? (size_t)p.n_in + p.n_out : 0;
@@ -1417,6 +1426,7 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
 
   const uint32_t ni = p.n_in, no = p.n_out;
   const uint32_t* d_out = io_nodes + ni;
+  bool gates_copied = false;  // the copy stream took the renumbered gates, chunk by chunk
   // everything downstream of the relaxation; issued again after sort_drain() when the speculative rounds did not converge
   auto enqueue_tail = [&]() {
     sort_enqueue_emit(h, dep, G, s, d_order);
@@ -1447,7 +1457,19 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
     }
     if (d_new_gates && G) {
       phase_begin(h, "k_gather");
-      LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, ((uint64_t)G + kGatherIlp - 1) / kGatherIlp), kBlock, d_gates, d_order, G, d_wire, d_new_gates, sc);
+      const bool chunked = out && out->new_gates_host && h->stream3 && G >= (1u << 22);
+      const uint32_t nch = chunked ? 4u : 1u;
+      for (uint32_t c = 0; c < nch; ++c) {
+        const uint32_t lo = (uint32_t)((uint64_t)G * c / nch), hi = (uint32_t)((uint64_t)G * (c + 1) / nch);
+        LAUNCH(h, k_gather, grid_for(h, (const void*)k_gather, kBlock, ((uint64_t)(hi - lo) + kGatherIlp - 1) / kGatherIlp), kBlock, d_gates, d_order, lo, hi - lo, d_wire,
+               d_new_gates, sc);
+        if (chunked) {
+          cudaEventRecord(h->ev_main, st);
+          cudaStreamWaitEvent(h->stream3, h->ev_main, 0);
+          cudaMemcpyAsync(out->new_gates_host + lo, d_new_gates + lo, 16 * (size_t)(hi - lo), cudaMemcpyDeviceToHost, h->stream3);
+        }
+      }
+      if (chunked) { cudaEventRecord(h->ev_copy, h->stream3); gates_copied = true; }
       phase_end(h);
     }
   };
@@ -1459,7 +1481,13 @@ static int build_core(c2a_handle* h, const BuildPlan& p, const uint4* d_gates, c
   };
 
   enqueue_tail();
-  if (before_status) (*before_status)();
+  if (out) {
+    phase_begin(h, "d2h");
+    if (!gates_copied && out->new_gates_host && d_new_gates && G) cudaMemcpyAsync(out->new_gates_host, d_new_gates, 16 * (size_t)G, cudaMemcpyDeviceToHost, st);
+    if (out->rest) out->rest();
+    if (gates_copied) cudaStreamWaitEvent(st, h->ev_copy, 0);  // the status read below then covers the copy stream too
+    phase_end(h);
+  }
   if (!read_status()) return C2A_ERR_CUDA;
   const uint32_t* hs = hp + 64;
   if (io_flags_dev && hs[S_COUNT]) return fail(h, C2A_ERR_INVALID_ARGUMENT, "an input/output signal was never declared");

@@ -1624,12 +1624,11 @@ static int emitted_build_impl(c2a_handle* h, const uint32_t* input_signals, uint
   bool identity = true;
   // host arrays: the copy-out is enqueued behind the pipeline and in FRONT of the build's status read, so the call synchronises once
   // (after an error the arrays hold unspecified contents - never anything behind their capacities)
-  const std::function<void()> copy_out = [&]() {
-    phase_begin(h, "d2h");
+  HostCopyOut copy_out;
+  copy_out.new_gates_host = (uint4*)new_gates;
+  copy_out.rest = [&]() {
     if (order_out && G) cudaMemcpyAsync(order_out, d_order, 4 * G, cudaMemcpyDeviceToHost, s);
     if (wire_of_node && node_bound) cudaMemcpyAsync(wire_of_node, d_wire, 4 * (size_t)node_bound, cudaMemcpyDeviceToHost, s);
-    if (new_gates && G) cudaMemcpyAsync(new_gates, d_new, 16 * G, cudaMemcpyDeviceToHost, s);
-    phase_end(h);
   };
   st = build_core(h, p, d_gates, nullptr, nullptr, d_order, d_wire, d_new, wire_count, err_index, &identity, io_nodes, io_flag,
                   (whole && h->emitted.prod1_valid) ? (const uint32_t*)(h->slab + h->emitted.prod1_off) : nullptr, outputs_on_device ? nullptr : &copy_out);
